@@ -1,0 +1,82 @@
+/*
+ * refcode.c -- execute the reference's OWN machine code for the CGR fill loop.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/kameris_oracle.c header).  Runs only in the build
+ * container, where /root/reference is mounted; its outputs are committed as
+ * tests/golden/refcode_cgr.json by oracle/refcode/gen_golden.py.
+ *
+ * What it does: kameris ships its hot path only as prebuilt executables.  In
+ * kameris/scripts/generation_cgr_windows_avx2.exe the per-file CGR fill is an out-of-line LEAF
+ * function (no calls, no imports, position independent):
+ *     VA 0x140016040 .. 0x1400161a8   (file offset 0x15440, 0x168 bytes)
+ *     void fill(std::vector<uint16_t>& count, const std::string& record, unsigned k,
+ *               const char* const& order)          -- Windows x64 ABI (rcx, rdx, r8d, r9)
+ * called from VA 0x14001564b with order -> "ACGT" (.rdata VA 0x1400a20b1).
+ * We map those bytes from the file where it lies (nothing is copied into the repo), build the two
+ * MSVC container headers the code dereferences ([rcx] = data pointer of the vector; the string is
+ * {ptr/SSO buffer @0, size @0x10, capacity @0x18}), and call it through an ms_abi pointer.
+ * x86-64 + BMI2 (shlx) host required.
+ */
+#define _GNU_SOURCE
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+
+#define FILL_FILE_OFF 0x15440l
+#define FILL_LEN 0x168
+#define ORDER_FILE_OFF 0xa0ab1l
+
+typedef void(__attribute__((ms_abi)) * fill_fn)(void *vec, void *str, uint32_t k, void *order);
+
+struct msvc_string {
+    char *ptr;
+    uint64_t pad;
+    uint64_t size;
+    uint64_t cap;
+};
+struct msvc_vector {
+    void *first, *last, *end;
+};
+
+static void *g_code = NULL;
+static char g_order[8];
+
+/* returns 0 on success; negative on failure */
+int refcode_load(const char *pe_path) {
+    if (g_code) return 0;
+    FILE *f = fopen(pe_path, "rb");
+    if (!f) return -1;
+    unsigned char buf[FILL_LEN];
+    if (fseek(f, FILL_FILE_OFF, SEEK_SET) || fread(buf, 1, FILL_LEN, f) != FILL_LEN) {
+        fclose(f);
+        return -2;
+    }
+    if (fseek(f, ORDER_FILE_OFF, SEEK_SET) || fread(g_order, 1, 4, f) != 4) {
+        fclose(f);
+        return -3;
+    }
+    fclose(f);
+    /* sanity: prologue "push rbx; push rsi; push rdi; sub rsp,0x40" and the final jmp */
+    static const unsigned char prologue[] = {0x53, 0x56, 0x57, 0x48, 0x83, 0xec, 0x40};
+    if (memcmp(buf, prologue, sizeof prologue) != 0 || buf[FILL_LEN - 5] != 0xe9) return -4;
+    void *m = mmap(NULL, 4096, PROT_READ | PROT_WRITE | PROT_EXEC, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m == MAP_FAILED) return -5;
+    memset(m, 0xcc, 4096);
+    memcpy(m, buf, FILL_LEN);
+    g_code = m;
+    return 0;
+}
+
+const char *refcode_order(void) { return g_order; }
+
+/* count must hold 4^k zero-initialised uint16 (the caller's value-initialised vector). */
+int refcode_cgr_u16(const char *rec, uint64_t n, uint32_t k, uint16_t *count) {
+    if (!g_code) return -1;
+    struct msvc_string s = {(char *)rec, 0, n, n < 16 ? 16 : n};
+    struct msvc_vector v = {count, count + ((uint64_t)1 << (2 * k)), count + ((uint64_t)1 << (2 * k))};
+    char *order = g_order;
+    ((fill_fn)g_code)(&v, &s, k, &order);
+    return 0;
+}
