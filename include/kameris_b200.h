@@ -1,0 +1,157 @@
+/*
+ * kameris_b200.h -- C ABI of libkameris_b200.so, the B200 (sm_100a) backend for the two kameris
+ * hot paths: the `kmers` job step (FASTA records -> 4^k CGR / k-mer count vectors) and the
+ * `distances` job step (pairwise distance matrices over those vectors).
+ *
+ * What each entry point replaces in the reference (stephensolis/kameris; binary addresses are
+ * kameris/scripts/generation_{cgr,dists}_mac_avx2 virtual addresses):
+ *
+ *   kam_pack_ascii        the per-character classification of the CGR loop
+ *                         (generation_cgr @0x10000e22e-0x10000e248: only 'A','C','G','T' are bases)
+ *   kam_kmer_count        the per-file CGR fill (generation_cgr @0x10000d330 / @0x100011320, loop
+ *                         @0x10000e1d2-0x10000e304) and, for KAM_OUT_FREQ_*, the numpy pass
+ *                         kameris/job_steps/backend.py:42-56
+ *   kam_kmers_host        `generation_cgr cgr <dir> <out> <k> <bits>` as invoked by
+ *                         kameris/job_steps/backend.py:34-40, minus file I/O (host buffers in/out)
+ *   kam_manhattan_*       manhat row lambda (generation_dists @0x10001bd87-0x10001bfc8)
+ *   kam_info_tri          info row lambda   (generation_dists @0x10001bab5-0x10001bcb0)
+ *   kam_gram_*            euclid / cosine / pearson -- NOT in the reference (schema enum
+ *                         kameris/schemas/job_options.json:97 has only manhat, info); defined as
+ *                         scipy.spatial.distance {euclidean, cosine, correlation}
+ *   kam_dists_host        `generation_dists <in> <prefix> <names>` as invoked by
+ *                         kameris/job_steps/backend.py:59-66, minus file I/O
+ *
+ * Conventions: every function returns 0 on success and a negative KAM_E_* code on failure;
+ * kam_last_error() returns a thread-local message.  No exceptions and no ownership cross the ABI:
+ * the caller owns every buffer.  Pointers named d_* are device pointers on the current CUDA
+ * device, h_* are host pointers; `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream).  Device entry points are asynchronous on `stream` unless stated otherwise.
+ */
+#ifndef KAMERIS_B200_H
+#define KAMERIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KAM_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define KAM_OK 0
+#define KAM_E_INVALID (-1)   /* bad argument */
+#define KAM_E_CUDA (-2)      /* CUDA runtime error, see kam_last_error() */
+#define KAM_E_WORKSPACE (-3) /* workspace too small */
+#define KAM_E_UNSUPPORTED (-4)
+#define KAM_E_NOMEM (-5)
+
+/* element types: the .mm-repr / .mm-dist element_type codes */
+#define KAM_U8 0
+#define KAM_U16 1
+#define KAM_U32 2
+#define KAM_U64 3
+#define KAM_F32 4
+#define KAM_F64 5
+
+/* kam_kmer_count output kinds */
+#define KAM_OUT_COUNTS 0   /* uint16 / uint32 counts, wrapping mod 2^bits like the reference */
+#define KAM_OUT_FREQ_F32 1 /* (float)((double)count / sum) */
+#define KAM_OUT_FREQ_F64 2 /* (double)count / sum: bit-exact numpy true division (backend.py:49) */
+
+/* distance metrics (bit mask) */
+#define KAM_M_MANHAT 1u  /* uint32, reference `manhat` */
+#define KAM_M_INFO 2u    /* float32, reference `info` */
+#define KAM_M_EUCLID 4u  /* float32 */
+#define KAM_M_COSINE 8u  /* float32 */
+#define KAM_M_PEARSON 16u /* float32 */
+
+int kam_version(void);
+const char *kam_last_error(void);
+/* SM count, free and total bytes of the current device. */
+int kam_device_info(int *sm_count, size_t *free_bytes, size_t *total_bytes);
+
+/* ---------------------------------------------------------------------------------------------
+ * Packed sequence layout ("planes").  All sequences of a batch form ONE flat stream of valid
+ * bases (non-ACGT characters removed, sequences back to back).  Base p of the stream lives in
+ * 64-bit word p/32: bit p%32 of the low half is its x-bit (1 for G,T), bit p%32 of the high half
+ * its y-bit (1 for A,T) -- the two CGR coordinate bits of generation_cgr @0x10000e24a-0x10000e2a4.
+ * d_base_start[s] .. d_base_start[s+1] is the range of sequence s; d_head_mask[s] has bit i set
+ * when raw character i (i < 32) of sequence s is a base, which is all that is needed to reproduce
+ * the raw-index emit test of the reference (quirk Q1).
+ * ------------------------------------------------------------------------------------------- */
+
+/* number of 64-bit plane words to allocate for `total_chars` input characters */
+size_t kam_planes_words(uint64_t total_chars);
+size_t kam_pack_workspace_bytes(uint64_t total_chars, uint32_t n_seqs);
+
+/* ASCII -> planes.  d_chars (16-byte aligned) holds the records back to back; d_char_start[n+1]
+ * their offsets.  Writes d_planes[kam_planes_words()], d_base_start[n+1], d_head_mask[n]. */
+int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_t n_seqs,
+                   uint64_t total_chars, uint64_t *d_planes, uint64_t *d_base_start,
+                   uint32_t *d_head_mask, void *d_ws, size_t ws_bytes, void *stream);
+
+size_t kam_kmer_workspace_bytes(uint32_t n_seqs, int k);
+
+/* planes -> n_seqs vectors of 4^k bins (row s at d_out + s*out_stride elements).
+ * count_bits: 16|32 (wrap width of the counts, also for the frequencies derived from them).
+ * out_kind: KAM_OUT_*.  Element type of d_out: uint16/uint32 for COUNTS, float/double for FREQ.
+ * Synchronises `stream` once internally (to learn how many sequences need the long-sequence
+ * path); the results are complete on return of the stream's work. */
+int kam_kmer_count(const uint64_t *d_planes, const uint64_t *d_base_start,
+                   const uint32_t *d_head_mask, uint32_t n_seqs, int k, int count_bits,
+                   int out_kind, void *d_out, uint64_t out_stride, void *d_ws, size_t ws_bytes,
+                   void *stream);
+
+/* Host-buffer form of the whole `kmers` step (what generation_cgr + the numpy pass compute):
+ * h_chars/h_char_start are the concatenated FASTA records (record[0] of each file, see
+ * kam_fasta_record0), h_out receives n_seqs x 4^k elements.  Copies, packing, counting and the
+ * copy back are pipelined over chunks on internal streams; blocking. */
+int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_t n_seqs, int k,
+                   int count_bits, int out_kind, void *h_out);
+
+/* A.1: first FASTA record of a file image (generation_cgr @0x10000d691-0x10000d83e).  Writes at
+ * most n bytes to out; returns the record length or -1 when the file holds no record. */
+int64_t kam_fasta_record0(const char *buf, size_t n, char *out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Distances.  x is a row-major n x d matrix (row stride `ld` elements) of element type `elem`.
+ * Triangle outputs use the .mm-dist order: for i<j, index n*i - i*(i+3)/2 + j - 1
+ * (generation_dists @0x10001bf7e).  [row_begin,row_end) selects the block of rows i a rank
+ * computes (all j>i); entries of other rows are left untouched.
+ * ------------------------------------------------------------------------------------------- */
+int kam_manhattan_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
+                      uint32_t row_begin, uint32_t row_end, uint32_t *d_tri, void *stream);
+/* rectangular m x c: out[i*c + j] = manhat(x_i, y_j) */
+int kam_manhattan_rect(const void *d_x, const void *d_y, int elem, uint32_t m, uint32_t c,
+                       uint64_t d, uint64_t ldx, uint64_t ldy, uint32_t *d_out, void *stream);
+/* float32 L1 distance to float32 centroids (BASELINE config 4); out[i*c+j] = sum |x_i - y_j| */
+int kam_manhattan_rect_f32(const void *d_x, int elem_x, const float *d_y, uint32_t m, uint32_t c,
+                           uint64_t d, uint64_t ldx, uint64_t ldy, float *d_out, void *stream);
+size_t kam_info_workspace_bytes(uint32_t n, uint64_t d);
+int kam_info_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
+                 uint32_t row_begin, uint32_t row_end, float *d_tri, void *d_ws, size_t ws_bytes,
+                 void *stream);
+
+/* Gram-matrix metrics on count vectors (uint16/uint32): G = X X^T on the tcgen05 tensor cores
+ * with exact integer-valued fp16 operands and fp32 TMEM accumulation, fused epilogue.
+ * metrics: any of KAM_M_EUCLID|KAM_M_COSINE|KAM_M_PEARSON; d_tri[m] (may be NULL when the metric
+ * is not requested) receive float32 triangles.  euclid_on_freq != 0 computes euclidean distance
+ * between the frequency vectors x_i/sum(x_i) (what a `frequencies` .mm-repr holds). */
+size_t kam_gram_workspace_bytes(uint32_t n, uint64_t d);
+int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
+                 uint32_t row_begin, uint32_t row_end, unsigned metrics, int euclid_on_freq,
+                 float *d_tri_euclid, float *d_tri_cosine, float *d_tri_pearson, void *d_ws,
+                 size_t ws_bytes, void *stream);
+
+/* Host-buffer form of the whole `distances` step: x is the n x d matrix read from a .mm-repr,
+ * outputs are packed triangles (NULL = not requested). */
+int kam_dists_host(const void *h_x, int elem, uint32_t n, uint64_t d, unsigned metrics,
+                   uint32_t *h_manhat, float *h_info, float *h_euclid, float *h_cosine,
+                   float *h_pearson);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KAMERIS_B200_H */

@@ -1,0 +1,73 @@
+"""ctypes binding of libkameris_b200.so (C ABI: include/kameris_b200.h).
+
+There is NO CPU fallback: if the library is missing it is built with nvcc; if that fails, or a
+call fails, the error is raised.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+c_void_p, c_size_t, c_int, c_uint32, c_uint64 = (ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                                 ctypes.c_uint32, ctypes.c_uint64)
+
+KAM_U8, KAM_U16, KAM_U32, KAM_U64, KAM_F32, KAM_F64 = range(6)
+KAM_OUT_COUNTS, KAM_OUT_FREQ_F32, KAM_OUT_FREQ_F64 = 0, 1, 2
+KAM_M_MANHAT, KAM_M_INFO, KAM_M_EUCLID, KAM_M_COSINE, KAM_M_PEARSON = 1, 2, 4, 8, 16
+
+# every symbol include/kameris_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "kam_version": (c_int, []),
+    "kam_last_error": (ctypes.c_char_p, []),
+    "kam_device_info": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]),
+    "kam_planes_words": (c_size_t, [c_uint64]),
+    "kam_pack_workspace_bytes": (c_size_t, [c_uint64, c_uint32]),
+    "kam_pack_ascii": (c_int, [c_void_p, c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_size_t, c_void_p]),
+    "kam_kmer_workspace_bytes": (c_size_t, [c_uint32, c_int]),
+    "kam_kmer_count": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_int, c_int, c_void_p, c_uint64,
+                               c_void_p, c_size_t, c_void_p]),
+    "kam_kmers_host": (c_int, [c_void_p, c_void_p, c_uint32, c_int, c_int, c_int, c_void_p]),
+    "kam_fasta_record0": (ctypes.c_int64, [c_void_p, c_size_t, c_void_p]),
+    "kam_manhattan_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p,
+                                  c_void_p]),
+    "kam_manhattan_rect": (c_int, [c_void_p, c_void_p, c_int, c_uint32, c_uint32, c_uint64, c_uint64, c_uint64,
+                                   c_void_p, c_void_p]),
+    "kam_manhattan_rect_f32": (c_int, [c_void_p, c_int, c_void_p, c_uint32, c_uint32, c_uint64, c_uint64, c_uint64,
+                                       c_void_p, c_void_p]),
+    "kam_info_workspace_bytes": (c_size_t, [c_uint32, c_uint64]),
+    "kam_info_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p,
+                             c_size_t, c_void_p]),
+    "kam_gram_workspace_bytes": (c_size_t, [c_uint32, c_uint64]),
+    "kam_gram_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, ctypes.c_uint,
+                             c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kam_dists_host": (c_int, [c_void_p, c_int, c_uint32, c_uint64, ctypes.c_uint, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class KamError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (building if needed) libkameris_b200.so.  Raises when it cannot be had."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if not os.path.exists(path):
+            _build.build()
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError if the ABI is incomplete
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise KamError("libkameris_b200 error %d: %s" % (rc, load().kam_last_error().decode(errors="replace")))

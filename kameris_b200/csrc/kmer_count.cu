@@ -1,0 +1,478 @@
+// kmer_count.cu -- planes -> 4^k CGR count / frequency vectors.
+//
+// Replaces the per-file CGR fill of the reference (generation_cgr_mac_avx2 @0x10000d330 u16,
+// @0x100011320 u32; loop @0x10000e1d2-0x10000e304, increment @0x10000ec41) and, for the FREQ
+// outputs, the numpy normalisation kameris/job_steps/backend.py:42-56.
+//
+// Index of the k-mer ending at base j of a sequence: with the x/y bit planes
+// LSB-first, x = the k x-bits of bases j-k+1..j read as an integer (oldest base in bit 0), y
+// likewise, bin = (y << k) | x.  For the first k-1 bases the CGR "centre" bit is still inside
+// the window: x = (bits << (k-m)) | 1 << (k-m-1) with m = j+1 bases seen; the reference emits
+// those only when non-base characters pushed the raw index to >= k-1 (quirk Q1), which
+// head_mask encodes: base j emits iff j >= popc(head_mask & ((1<<(k-1))-1)).
+//
+// Path A (cgr_tile_kernel): one CTA per sequence, persistent over a dynamic queue.  The 4^k
+// table is produced in tiles of <= 32768 bins held in shared memory (uint8 counters for k >= 7,
+// uint32 for k <= 6); per tile the CTA re-scans the (L1-resident) planes of its sequence,
+// increments the bins that fall in the tile, then streams the tile out with 16-byte stores in
+// the output type, fusing the frequency division.  The output (4^k * sizeof(out) per sequence,
+// >96% zeros for 9 kb genomes at k=9) is written exactly once and never read: HBM-write-bound.
+// A uint8 counter that would pass 255, or a sequence too long for this path, puts the sequence
+// on the spill list.
+//
+// Path B (spill): uint32 tables in global memory (L2-resident: a few sequences at a time),
+// RED.ADD increments from many CTAs per sequence, then a finalize pass (wrap to 16 bits,
+// normalise).  This is the "global-atomic spill" for long sequences (5 Mb genomes at k=9).
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int A_THREADS = 256;
+constexpr int TILE_BINS_LOG2 = 15;
+constexpr uint32_t TILE_BINS = 1u << TILE_BINS_LOG2;   // 32768 bins: 32 KB of uint8 counters
+constexpr uint64_t A_MAX_LEN = 1ull << 17;              // longer sequences go to path B when tiled
+constexpr int B_THREADS = 256;
+constexpr uint32_t B_CHUNK = 32768;                     // bases per CTA in path B
+
+struct SeqInfo {
+    uint64_t p0, n;     // first flat base, number of bases
+    uint32_t lead;      // bases [lead, n) emit
+};
+
+__device__ __forceinline__ SeqInfo seq_info(const uint64_t *__restrict__ base_start,
+                                            const uint32_t *__restrict__ head_mask, uint32_t s, int k) {
+    SeqInfo q;
+    q.p0 = base_start[s];
+    q.n = base_start[s + 1] - q.p0;
+    q.lead = __popc(head_mask[s] & ((k > 1 ? (1u << (k - 1)) : 1u) - 1u));
+    return q;
+}
+
+// x and y windows of the k-mer ending at flat position p (needs p - (k-1) >= seq start)
+__device__ __forceinline__ uint32_t kmer_bin(unsigned long long vx, unsigned long long vy, uint32_t sh, int k,
+                                             uint32_t mask) {
+    const uint32_t xw = (uint32_t)(vx >> sh) & mask;
+    const uint32_t yw = (uint32_t)(vy >> sh) & mask;
+    return (yw << k) | xw;
+}
+
+// The <= k-1 partial k-mers at the head of a dirty sequence (quirk Q1).  Serial, executed by one
+// thread; `emit(bin)` is called for each.
+template <class F>
+__device__ __forceinline__ void head_partials(const uint2 *__restrict__ planes, const SeqInfo &q, int k, F emit) {
+    const uint64_t jend = q.n < (uint64_t)(k - 1) ? q.n : (uint64_t)(k - 1);
+    uint32_t x = 1u << (k - 1), y = x;   // the literal reference recurrence
+    for (uint64_t j = 0; j < jend; ++j) {
+        const uint64_t p = q.p0 + j;
+        const uint2 w = planes[p >> 5];
+        const uint32_t b = (uint32_t)(p & 31);
+        x = (x >> 1) | (((w.x >> b) & 1u) << (k - 1));
+        y = (y >> 1) | (((w.y >> b) & 1u) << (k - 1));
+        if (j >= q.lead) emit((y << k) | x);
+    }
+}
+
+template <typename OUT>
+__device__ __forceinline__ OUT convert_count(uint32_t c, double inv_unused, double sum) {
+    (void)inv_unused;
+    if constexpr (sizeof(OUT) == 8 && !std::is_integral<OUT>::value) return (double)c / sum;   // numpy true division
+    else if constexpr (std::is_same<OUT, float>::value) return (float)((double)c / sum);
+    else return (OUT)c;   // wraps mod 2^bits like `inc WORD/DWORD PTR`
+}
+
+// ---- path A ------------------------------------------------------------------------------------
+// CT: shared-memory counter type (uint8_t with overflow detection, or uint32_t).
+// OUT: uint16_t / uint32_t (counts), float / double (frequencies).
+template <typename CT, typename OUT>
+__global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__restrict__ planes,
+                                                             const uint64_t *__restrict__ base_start,
+                                                             const uint32_t *__restrict__ head_mask, uint32_t n_seqs,
+                                                             int k, int count_bits, OUT *__restrict__ out,
+                                                             uint64_t out_stride, uint32_t *__restrict__ queue,
+                                                             uint32_t *__restrict__ spill_count,
+                                                             uint32_t *__restrict__ spill_list,
+                                                             unsigned long long *__restrict__ spill_maxlen) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *tab32 = reinterpret_cast<uint32_t *>(smem_raw);
+    __shared__ uint32_t s_seq;
+    __shared__ uint32_t s_flag;
+    __shared__ unsigned long long s_red[A_THREADS / 32];
+
+    const uint32_t bins = 1u << (2 * k);
+    const uint32_t tile_bins = bins < TILE_BINS ? bins : TILE_BINS;
+    const uint32_t n_tiles = bins / tile_bins;
+    const uint32_t tile_words = tile_bins * sizeof(CT) / 4;   // >= 1 (k=1,u8: 4 bins = 1 word)
+    const uint32_t mask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+    constexpr int BPS = 16 / (int)sizeof(OUT);                // bins per 16-byte store
+
+    for (uint32_t i = threadIdx.x; i < tile_words; i += A_THREADS) tab32[i] = 0;
+
+    for (;;) {
+        __syncthreads();   // table is clear; previous s_seq/s_flag consumed
+        if (threadIdx.x == 0) {
+            s_seq = atomicAdd(queue, 1u);
+            s_flag = 0;
+        }
+        __syncthreads();
+        const uint32_t s = s_seq;
+        if (s >= n_seqs) break;
+        const SeqInfo q = seq_info(base_start, head_mask, s, k);
+        OUT *row = out + (uint64_t)s * out_stride;
+
+        bool spill = (n_tiles > 1 && q.n > A_MAX_LEN);
+        if (sizeof(CT) == 1 && q.n > 64ull * bins && q.n > 255) spill = true;   // mean count > 64: uint8 will overflow
+        if (spill) {
+            if (threadIdx.x == 0) {
+                spill_list[atomicAdd(spill_count, 1u)] = s;
+                atomicMax(spill_maxlen, (unsigned long long)q.n);
+            }
+            continue;
+        }
+
+        // groups of 8 flat positions covering [p0 + k-1, p0 + n): full k-mers only
+        const uint64_t pf = q.p0 + (uint64_t)(k - 1);   // first flat position with a full window
+        const uint64_t pe = q.p0 + q.n;
+        const bool has_full = q.n >= (uint64_t)k;
+        const uint64_t g0 = pf >> 3, g1 = has_full ? ((pe - 1) >> 3) + 1 : g0;   // group range
+        const uint64_t emit_from = q.p0 + (q.lead > (uint32_t)(k - 1) ? q.lead : (uint32_t)(k - 1));
+        // Σ counts = number of emitting bases (no wrap possible on this path: counts <= 255 or n < 2^32)
+        const uint64_t total = q.n > q.lead ? q.n - q.lead : 0;
+        double sum = (double)total;
+
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+            for (uint64_t g = g0 + threadIdx.x; g < g1; g += A_THREADS) {
+                const uint64_t W = g >> 2;                  // word holding the group
+                const uint2 hi = __ldg(planes + W);
+                const uint2 lo = W ? __ldg(planes + W - 1) : make_uint2(0, 0);
+                const unsigned long long vx = ((unsigned long long)hi.x << 32) | lo.x;
+                const unsigned long long vy = ((unsigned long long)hi.y << 32) | lo.y;
+                const uint64_t pbase = g << 3;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const uint64_t p = pbase + b;
+                    if (p < emit_from || p >= pe) continue;
+                    // window start p-k+1 relative to bit 0 of word W-1
+                    const uint32_t sh = (uint32_t)(p - (uint64_t)(k - 1) + 32 - (W << 5));
+                    const uint32_t bin = kmer_bin(vx, vy, sh, k, mask);
+                    if ((bin >> TILE_BINS_LOG2) != t && n_tiles > 1) continue;
+                    const uint32_t lb = bin & (tile_bins - 1);
+                    if constexpr (sizeof(CT) == 1) {
+                        const uint32_t bsh = (lb & 3u) * 8u;
+                        const uint32_t old = atomicAdd(&tab32[lb >> 2], 1u << bsh);
+                        if (((old >> bsh) & 0xffu) == 0xffu) s_flag = 1;
+                    } else {
+                        atomicAdd(&tab32[lb], 1u);
+                    }
+                }
+            }
+            if (threadIdx.x == 0 && q.lead < (uint32_t)(k - 1)) {   // dirty head (rare)
+                head_partials(planes, q, k, [&](uint32_t bin) {
+                    if ((bin >> TILE_BINS_LOG2) != t && n_tiles > 1) return;
+                    const uint32_t lb = bin & (tile_bins - 1);
+                    if constexpr (sizeof(CT) == 1) {
+                        const uint32_t bsh = (lb & 3u) * 8u;
+                        const uint32_t old = atomicAdd(&tab32[lb >> 2], 1u << bsh);
+                        if (((old >> bsh) & 0xffu) == 0xffu) s_flag = 1;
+                    } else {
+                        atomicAdd(&tab32[lb], 1u);
+                    }
+                });
+            }
+            __syncthreads();
+
+            if constexpr (sizeof(CT) == 4) {
+                // frequencies of 16-bit counts that wrapped: the divisor is the sum of the WRAPPED values
+                if (t == 0 && !std::is_integral<OUT>::value && count_bits == 16 && q.n > 65535) {
+                    unsigned long long part = 0;
+                    for (uint32_t i = threadIdx.x; i < tile_bins; i += A_THREADS) part += tab32[i] & 0xffffu;
+                    part = warp_sum64(part);
+                    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+                    __syncthreads();
+                    unsigned long long tot = 0;
+#pragma unroll
+                    for (int w = 0; w < A_THREADS / 32; ++w) tot += s_red[w];
+                    sum = (double)tot;
+                }
+            }
+
+            // stream the tile out (and clear it).  Store c covers bins [c*BPS, c*BPS+BPS).
+            OUT *trow = row + (uint64_t)t * tile_bins;
+            const bool vec_ok = (tile_bins % BPS == 0) && ((reinterpret_cast<uintptr_t>(trow) & 15) == 0);
+            const uint32_t wrapmask = (count_bits == 16) ? 0xffffu : 0xffffffffu;
+            if (vec_ok) {
+                const uint32_t n_stores = tile_bins / BPS;
+                for (uint32_t c = threadIdx.x; c < n_stores; c += A_THREADS) {
+                    uint32_t cnt[BPS];
+                    if constexpr (sizeof(CT) == 1) {
+                        if constexpr (BPS == 8) {
+                            uint2 w = *reinterpret_cast<uint2 *>(&tab32[c * 2]);
+                            *reinterpret_cast<uint2 *>(&tab32[c * 2]) = make_uint2(0, 0);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                cnt[i] = (w.x >> (8 * i)) & 0xffu;
+                                cnt[4 + i] = (w.y >> (8 * i)) & 0xffu;
+                            }
+                        } else if constexpr (BPS == 4) {
+                            const uint32_t w = tab32[c];
+                            tab32[c] = 0;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) cnt[i] = (w >> (8 * i)) & 0xffu;
+                        } else {   // BPS == 2
+                            unsigned short *t16 = reinterpret_cast<unsigned short *>(tab32);
+                            const uint32_t w = t16[c];
+                            t16[c] = 0;
+                            cnt[0] = w & 0xffu;
+                            cnt[1] = w >> 8;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BPS; ++i) {
+                            cnt[i] = tab32[c * BPS + i] & wrapmask;
+                            tab32[c * BPS + i] = 0;
+                        }
+                    }
+                    union {
+                        uint4 v;
+                        OUT e[BPS];
+                    } u;
+#pragma unroll
+                    for (int i = 0; i < BPS; ++i) u.e[i] = convert_count<OUT>(cnt[i], 0.0, sum);
+                    st_stream16(trow + (uint64_t)c * BPS, u.v);
+                }
+            } else {   // tiny or misaligned rows (k=1 with 16-bit counts)
+                for (uint32_t i = threadIdx.x; i < tile_bins; i += A_THREADS) {
+                    uint32_t c;
+                    if constexpr (sizeof(CT) == 1) c = reinterpret_cast<unsigned char *>(tab32)[i];
+                    else c = tab32[i] & wrapmask;
+                    trow[i] = convert_count<OUT>(c, 0.0, sum);
+                }
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < tile_words; i += A_THREADS) tab32[i] = 0;
+            }
+            __syncthreads();
+        }
+        if (sizeof(CT) == 1 && threadIdx.x == 0 && s_flag) {   // a uint8 counter overflowed: redo on path B
+            spill_list[atomicAdd(spill_count, 1u)] = s;
+            atomicMax(spill_maxlen, (unsigned long long)q.n);
+        }
+    }
+}
+
+// ---- path B ------------------------------------------------------------------------------------
+// grid (chunks, batch): CTA (c, b) counts bases [c*B_CHUNK, (c+1)*B_CHUNK) of sequence
+// spill_list[first + b] into tables[b] (4^k uint32, zeroed beforehand) with RED.ADD.
+__global__ void __launch_bounds__(B_THREADS) cgr_spill_count_kernel(const uint2 *__restrict__ planes,
+                                                                    const uint64_t *__restrict__ base_start,
+                                                                    const uint32_t *__restrict__ head_mask,
+                                                                    const uint32_t *__restrict__ spill_list,
+                                                                    uint32_t first, int k,
+                                                                    uint32_t *__restrict__ tables,
+                                                                    uint64_t table_stride) {
+    const uint32_t s = spill_list[first + blockIdx.y];
+    const SeqInfo q = seq_info(base_start, head_mask, s, k);
+    uint32_t *tab = tables + (uint64_t)blockIdx.y * table_stride;
+    const uint32_t mask = (1u << k) - 1u;
+    const uint64_t c0 = (uint64_t)blockIdx.x * B_CHUNK;
+    if (c0 >= q.n) return;
+    const uint64_t c1 = c0 + B_CHUNK < q.n ? c0 + B_CHUNK : q.n;
+    // this CTA emits k-mers ending at sequence bases [c0, c1) that are full and >= lead
+    uint64_t lo = c0;
+    if (lo < (uint64_t)(k - 1)) lo = (uint64_t)(k - 1);
+    if (lo < q.lead) lo = q.lead;
+    const uint64_t pa = q.p0 + lo, pe = q.p0 + c1;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && q.lead < (uint32_t)(k - 1))
+        head_partials(planes, q, k, [&](uint32_t bin) { atomicAdd(&tab[bin], 1u); });
+    if (pa >= pe) return;
+    const uint64_t g0 = pa >> 3, g1 = ((pe - 1) >> 3) + 1;
+    for (uint64_t g = g0 + threadIdx.x; g < g1; g += B_THREADS) {
+        const uint64_t W = g >> 2;
+        const uint2 hi = __ldg(planes + W);
+        const uint2 lw = W ? __ldg(planes + W - 1) : make_uint2(0, 0);
+        const unsigned long long vx = ((unsigned long long)hi.x << 32) | lw.x;
+        const unsigned long long vy = ((unsigned long long)hi.y << 32) | lw.y;
+        const uint64_t pbase = g << 3;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const uint64_t p = pbase + b;
+            if (p < pa || p >= pe) continue;
+            const uint32_t sh = (uint32_t)(p - (uint64_t)(k - 1) + 32 - (W << 5));
+            atomicAdd(&tab[kmer_bin(vx, vy, sh, k, mask)], 1u);   // result unused -> RED.ADD
+        }
+    }
+}
+
+// per-table sum of the (wrapped) counts, needed as the frequency divisor
+__global__ void __launch_bounds__(256) cgr_spill_sum_kernel(const uint32_t *__restrict__ tables, uint64_t table_stride,
+                                                            uint32_t bins, uint32_t wrapmask,
+                                                            unsigned long long *__restrict__ sums) {
+    const uint32_t *tab = tables + (uint64_t)blockIdx.y * table_stride;
+    unsigned long long part = 0;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < bins; i += gridDim.x * 256) part += tab[i] & wrapmask;
+    part = warp_sum64(part);
+    if ((threadIdx.x & 31) == 0 && part) atomicAdd(&sums[blockIdx.y], part);
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(256) cgr_spill_finalize_kernel(const uint32_t *__restrict__ tables,
+                                                                 uint64_t table_stride, uint32_t bins,
+                                                                 uint32_t wrapmask,
+                                                                 const unsigned long long *__restrict__ sums,
+                                                                 const uint32_t *__restrict__ spill_list,
+                                                                 uint32_t first, OUT *__restrict__ out,
+                                                                 uint64_t out_stride) {
+    const uint32_t *tab = tables + (uint64_t)blockIdx.y * table_stride;
+    OUT *row = out + (uint64_t)spill_list[first + blockIdx.y] * out_stride;
+    const double sum = (double)sums[blockIdx.y];
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < bins; i += gridDim.x * 256)
+        row[i] = convert_count<OUT>(tab[i] & wrapmask, 0.0, sum);
+}
+
+struct KmerWs {
+    uint32_t *queue;                 // [1]
+    uint32_t *spill_count;           // [1]
+    unsigned long long *spill_maxlen;// [1]
+    uint32_t *spill_list;            // [n_seqs]
+    unsigned long long *sums;        // [batch]
+    uint32_t *tables;                // [batch][4^k]
+    uint32_t batch;
+};
+
+constexpr size_t SPILL_TABLE_BUDGET = 48ull << 20;   // keep the live uint32 tables well inside the 126 MB L2
+
+inline uint32_t spill_batch(int k) {
+    const size_t tb = ((size_t)1 << (2 * k)) * 4;
+    size_t b = SPILL_TABLE_BUDGET / tb;
+    if (b < 1) b = 1;
+    if (b > 1024) b = 1024;
+    return (uint32_t)b;
+}
+
+inline size_t ws_layout(uint32_t n_seqs, int k, void *base, KmerWs *w) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void *p = base ? (char *)base + off : nullptr;
+        off += kam_align_up(bytes, 256);
+        return p;
+    };
+    const uint32_t batch = spill_batch(k);
+    void *hdr = take(64);
+    void *list = take((size_t)(n_seqs ? n_seqs : 1) * 4);
+    void *sums = take((size_t)batch * 8);
+    void *tables = take((size_t)batch * (((size_t)1 << (2 * k)) * 4));
+    if (w) {
+        w->queue = (uint32_t *)hdr;
+        w->spill_count = (uint32_t *)hdr + 1;
+        w->spill_maxlen = (unsigned long long *)((char *)hdr + 8);
+        w->spill_list = (uint32_t *)list;
+        w->sums = (unsigned long long *)sums;
+        w->tables = (uint32_t *)tables;
+        w->batch = batch;
+    }
+    return off;
+}
+
+template <typename CT, typename OUT>
+int launch_tile(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, uint32_t n_seqs, int k,
+                int count_bits, OUT *out, uint64_t out_stride, const KmerWs &w, cudaStream_t st) {
+    const uint32_t bins = 1u << (2 * k);
+    const uint32_t tile_bins = bins < TILE_BINS ? bins : TILE_BINS;
+    size_t smem = (size_t)tile_bins * sizeof(CT);
+    if (smem < 16) smem = 16;
+    auto kern = cgr_tile_kernel<CT, OUT>;
+    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    KAM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, A_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)kam_sm_count() * per_sm;   // persistent: a whole number of CTAs per SM
+    if (grid > n_seqs) grid = n_seqs;
+    kern<<<(unsigned)grid, A_THREADS, smem, st>>>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
+                                                  out_stride, w.queue, w.spill_count, w.spill_list, w.spill_maxlen);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+template <typename OUT>
+int run_kmer(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, uint32_t n_seqs, int k,
+             int count_bits, OUT *out, uint64_t out_stride, const KmerWs &w, cudaStream_t st) {
+    KAM_CUDA(cudaMemsetAsync(w.queue, 0, 64, st));
+    int rc = (k <= 6) ? launch_tile<uint32_t, OUT>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
+                                                    out_stride, w, st)
+                      : launch_tile<uint8_t, OUT>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
+                                                   out_stride, w, st);
+    if (rc) return rc;
+
+    struct {
+        uint32_t queue, count;
+        unsigned long long maxlen;
+    } h;
+    KAM_CUDA(cudaMemcpyAsync(&h, w.queue, 16, cudaMemcpyDeviceToHost, st));
+    KAM_CUDA(cudaStreamSynchronize(st));
+    if (h.count == 0) return KAM_OK;
+
+    // path B over the spill list, `batch` sequences at a time so the live tables stay in L2
+    const uint32_t bins = 1u << (2 * k);
+    const uint32_t wrapmask = count_bits == 16 ? 0xffffu : 0xffffffffu;
+    const uint32_t chunks = (uint32_t)((h.maxlen + B_CHUNK - 1) / B_CHUNK);
+    uint32_t fin_blocks = bins / 256 / 8;
+    if (fin_blocks < 1) fin_blocks = 1;
+    if (fin_blocks > 1024) fin_blocks = 1024;
+    for (uint32_t first = 0; first < h.count; first += w.batch) {
+        const uint32_t nb = h.count - first < w.batch ? h.count - first : w.batch;
+        KAM_CUDA(cudaMemsetAsync(w.tables, 0, (size_t)nb * bins * 4, st));
+        KAM_CUDA(cudaMemsetAsync(w.sums, 0, (size_t)nb * 8, st));
+        cgr_spill_count_kernel<<<dim3(chunks ? chunks : 1, nb), B_THREADS, 0, st>>>(
+            planes, base_start, head_mask, w.spill_list, first, k, w.tables, bins);
+        cgr_spill_sum_kernel<<<dim3(fin_blocks, nb), 256, 0, st>>>(w.tables, bins, bins, wrapmask, w.sums);
+        cgr_spill_finalize_kernel<OUT><<<dim3(fin_blocks, nb), 256, 0, st>>>(w.tables, bins, bins, wrapmask, w.sums,
+                                                                             w.spill_list, first, out, out_stride);
+        KAM_CUDA(cudaGetLastError());
+    }
+    return KAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t kam_kmer_workspace_bytes(uint32_t n_seqs, int k) {
+    if (k < 1 || k > 15) return 0;
+    return ws_layout(n_seqs, k, nullptr, nullptr);
+}
+
+int kam_kmer_count(const uint64_t *d_planes, const uint64_t *d_base_start, const uint32_t *d_head_mask,
+                   uint32_t n_seqs, int k, int count_bits, int out_kind, void *d_out, uint64_t out_stride,
+                   void *d_ws, size_t ws_bytes, void *stream) {
+    if (k < 1 || 2 * k > 64) {
+        kam_set_error("k is too large to fit in the index");   // the reference's message (cgr @0x10000e15f)
+        return KAM_E_INVALID;
+    }
+    if (k > 15) {
+        kam_set_error("k=%d: 4^k bins exceed what this build addresses (k <= 15)", k);
+        return KAM_E_UNSUPPORTED;
+    }
+    KAM_REQUIRE(count_bits == 16 || count_bits == 32, "count_bits must be 16 or 32");
+    KAM_REQUIRE(out_kind >= KAM_OUT_COUNTS && out_kind <= KAM_OUT_FREQ_F64, "bad out_kind");
+    KAM_REQUIRE(d_planes && d_base_start && d_head_mask && d_out && d_ws, "null pointer");
+    KAM_REQUIRE(out_stride >= (1ull << (2 * k)), "out_stride smaller than 4^k");
+    if (ws_bytes < kam_kmer_workspace_bytes(n_seqs, k)) {
+        kam_set_error("kam_kmer_count: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    if (n_seqs == 0) return KAM_OK;
+    KmerWs w;
+    ws_layout(n_seqs, k, d_ws, &w);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint2 *pl = (const uint2 *)d_planes;
+    if (out_kind == KAM_OUT_COUNTS) {
+        if (count_bits == 16)
+            return run_kmer<uint16_t>(pl, d_base_start, d_head_mask, n_seqs, k, 16, (uint16_t *)d_out, out_stride, w, st);
+        return run_kmer<uint32_t>(pl, d_base_start, d_head_mask, n_seqs, k, 32, (uint32_t *)d_out, out_stride, w, st);
+    }
+    if (out_kind == KAM_OUT_FREQ_F32)
+        return run_kmer<float>(pl, d_base_start, d_head_mask, n_seqs, k, count_bits, (float *)d_out, out_stride, w, st);
+    return run_kmer<double>(pl, d_base_start, d_head_mask, n_seqs, k, count_bits, (double *)d_out, out_stride, w, st);
+}
+
+}  // extern "C"

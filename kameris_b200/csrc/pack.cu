@@ -1,0 +1,254 @@
+// pack.cu -- ASCII records -> flat 2-bit "planes" stream (see include/kameris_b200.h).
+//
+// Replaces the character classification of the reference CGR loop
+// (generation_cgr_mac_avx2 @0x10000e22e-0x10000e248): only 'A','C','G','T' are bases,
+// everything else is skipped without resetting the k-mer window, so removing the other
+// characters up front is exact -- except for the raw-index emit test (quirk Q1), which
+// head_mask preserves.
+//
+// Three launches over tiles of 4096 characters:
+//   pack_count_kernel   valid bases per tile
+//   pack_scan_kernel    exclusive scan of the tile counts (one CTA), grand total
+//   pack_scatter_kernel compaction: x/y bits land at their flat position; per-sequence starts
+// HBM-bound byte work: 16-byte loads, one uint2 store per 32 bases.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_CPT = 16;                         // characters per thread
+constexpr int PACK_TILE = PACK_THREADS * PACK_CPT;   // 4096
+constexpr int SCAN_THREADS = 1024;
+
+// bit (c & 31) of these masks, for c in 0x40..0x5f:  A=0x41 C=0x43 G=0x47 T=0x54
+constexpr uint32_t LUT_VALID = (1u << 1) | (1u << 3) | (1u << 7) | (1u << 20);
+constexpr uint32_t LUT_X = (1u << 7) | (1u << 20);   // G, T
+constexpr uint32_t LUT_Y = (1u << 1) | (1u << 20);   // A, T
+
+struct Cls {
+    uint32_t cnt, x, y, vmask;   // compacted x/y bits (cnt of them), validity of the 16 raw chars
+};
+
+__device__ __forceinline__ void cls_byte(uint32_t c, Cls &r, int i) {
+    const uint32_t sel = c & 31u;
+    const uint32_t v = ((c & 0xE0u) == 0x40u) ? ((LUT_VALID >> sel) & 1u) : 0u;
+    r.x |= (v & (LUT_X >> sel)) << r.cnt;
+    r.y |= (v & (LUT_Y >> sel)) << r.cnt;
+    r.vmask |= v << i;
+    r.cnt += v;
+}
+
+// classify the 16 characters at chars[pos .. pos+16) (those at or beyond `total` are invalid)
+__device__ __forceinline__ Cls classify16(const uint8_t *__restrict__ chars, uint64_t pos, uint64_t total) {
+    Cls r{0, 0, 0, 0};
+    if (pos + PACK_CPT <= total) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(chars + pos));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) cls_byte((w[q] >> (8 * b)) & 0xFFu, r, q * 4 + b);
+    } else {
+        for (int i = 0; i < PACK_CPT; ++i)
+            if (pos + i < total) cls_byte(chars[pos + i], r, i);
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(PACK_THREADS) pack_count_kernel(const uint8_t *__restrict__ chars,
+                                                                  uint64_t total, uint32_t *__restrict__ tile_count) {
+    __shared__ uint32_t wsum[PACK_THREADS / 32];
+    const uint64_t pos = (uint64_t)blockIdx.x * PACK_TILE + (uint64_t)threadIdx.x * PACK_CPT;
+    uint32_t c = pos < total ? classify16(chars, pos, total).cnt : 0;
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int i = 0; i < PACK_THREADS / 32; ++i) s += wsum[i];
+        tile_count[blockIdx.x] = s;
+    }
+}
+
+// one CTA: tile_off[t] = sum of tile_count[0..t); base_start[s] = grand total for every trailing
+// sequence that starts at `total` (they own no tile); base_start[n_seqs] likewise.
+__global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(const uint32_t *__restrict__ tile_count,
+                                                                 uint64_t n_tiles, uint64_t *__restrict__ tile_off,
+                                                                 const uint64_t *__restrict__ char_start,
+                                                                 uint32_t n_seqs, uint64_t total,
+                                                                 uint64_t *__restrict__ base_start) {
+    __shared__ unsigned long long part[SCAN_THREADS];
+    const uint64_t per = (n_tiles + SCAN_THREADS - 1) / SCAN_THREADS;
+    const uint64_t b = (uint64_t)threadIdx.x * per;
+    const uint64_t e = b + per < n_tiles ? b + per : n_tiles;
+    unsigned long long s = 0;
+    for (uint64_t i = b; i < e; ++i) s += tile_count[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+        unsigned long long v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned long long run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    for (uint64_t i = b; i < e; ++i) {
+        tile_off[i] = run;
+        run += tile_count[i];
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long grand = part[SCAN_THREADS - 1];
+        tile_off[n_tiles] = grand;
+        base_start[n_seqs] = grand;
+        for (int64_t q = (int64_t)n_seqs - 1; q >= 0 && char_start[q] >= total; --q) base_start[q] = grand;
+    }
+}
+
+__global__ void __launch_bounds__(PACK_THREADS) pack_scatter_kernel(const uint8_t *__restrict__ chars, uint64_t total,
+                                                                    const uint64_t *__restrict__ tile_off,
+                                                                    const uint64_t *__restrict__ char_start,
+                                                                    uint32_t n_seqs, uint2 *__restrict__ planes,
+                                                                    uint64_t *__restrict__ base_start) {
+    constexpr int NW = PACK_THREADS / 32;
+    constexpr int SW = PACK_TILE / 32 + 2;   // words a tile's compacted bases can touch
+    __shared__ uint32_t sx[SW], sy[SW];
+    __shared__ uint32_t wsum[NW];
+    __shared__ uint32_t pref[PACK_THREADS];
+    __shared__ uint32_t vmask[PACK_THREADS];
+    __shared__ uint32_t first_seq;
+
+    const uint64_t tile_begin = (uint64_t)blockIdx.x * PACK_TILE;
+    const uint64_t tile_end = tile_begin + PACK_TILE < total ? tile_begin + PACK_TILE : total;
+    const uint64_t goff = tile_off[blockIdx.x];            // flat base index of this tile's first base
+    const uint32_t bit0 = (uint32_t)(goff & 31);
+    const uint64_t word0 = goff >> 5;
+
+    for (int i = threadIdx.x; i < SW; i += PACK_THREADS) {
+        sx[i] = 0;
+        sy[i] = 0;
+    }
+    if (threadIdx.x == 0) {
+        // lower_bound(char_start, tile_begin) over [0, n_seqs)
+        uint32_t lo = 0, hi = n_seqs;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (char_start[mid] < tile_begin) lo = mid + 1; else hi = mid;
+        }
+        first_seq = lo;
+    }
+
+    const uint64_t pos = tile_begin + (uint64_t)threadIdx.x * PACK_CPT;
+    Cls r = pos < total ? classify16(chars, pos, total) : Cls{0, 0, 0, 0};
+
+    // block exclusive scan of r.cnt
+    uint32_t inc = r.cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((threadIdx.x & 31) >= o) inc += v;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+        if (w < (int)(threadIdx.x >> 5)) woff += wsum[w];
+    const uint32_t excl = woff + inc - r.cnt;
+    pref[threadIdx.x] = excl;
+    vmask[threadIdx.x] = r.vmask;
+
+    if (r.cnt) {
+        const uint32_t bitpos = bit0 + excl;
+        const uint32_t lw = bitpos >> 5, sh = bitpos & 31;
+        atomicOr(&sx[lw], r.x << sh);
+        atomicOr(&sy[lw], r.y << sh);
+        if (sh + r.cnt > 32) {
+            atomicOr(&sx[lw + 1], r.x >> (32 - sh));
+            atomicOr(&sy[lw + 1], r.y >> (32 - sh));
+        }
+    }
+    __syncthreads();
+
+    const uint32_t tile_cnt = wsum[0] + wsum[1] + wsum[2] + wsum[3] + wsum[4] + wsum[5] + wsum[6] + wsum[7];
+    static_assert(NW == 8, "tile_cnt sum assumes 8 warps");
+    const uint32_t nwords = (bit0 + tile_cnt + 31) >> 5;   // words touched (0 when the tile has no base)
+    for (uint32_t i = threadIdx.x; i < nwords; i += PACK_THREADS) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(planes + word0 + i);
+        if (i == 0 || i == nwords - 1) {       // may be shared with a neighbouring tile (planes pre-zeroed)
+            if (sx[i]) atomicOr(dst, sx[i]);
+            if (sy[i]) atomicOr(dst + 1, sy[i]);
+        } else {
+            planes[word0 + i] = make_uint2(sx[i], sy[i]);
+        }
+    }
+
+    // sequences that start inside this tile
+    for (uint32_t s = first_seq + threadIdx.x; s < n_seqs; s += PACK_THREADS) {
+        const uint64_t c0 = char_start[s];
+        if (c0 >= tile_end) break;             // char_start is non-decreasing
+        const uint32_t rel = (uint32_t)(c0 - tile_begin);
+        const uint32_t th = rel / PACK_CPT, o = rel % PACK_CPT;
+        base_start[s] = goff + pref[th] + __popc(vmask[th] & ((1u << o) - 1u));
+    }
+}
+
+__global__ void head_mask_kernel(const uint8_t *__restrict__ chars, const uint64_t *__restrict__ char_start,
+                                 uint32_t n_seqs, uint32_t *__restrict__ head_mask) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seqs) return;
+    const uint64_t b = char_start[s], e = char_start[s + 1];
+    const uint32_t n = e - b < 32 ? (uint32_t)(e - b) : 32u;
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t c = chars[b + i];
+        const uint32_t v = ((c & 0xE0u) == 0x40u) ? ((LUT_VALID >> (c & 31u)) & 1u) : 0u;
+        m |= v << i;
+    }
+    head_mask[s] = m;
+}
+
+inline uint64_t n_tiles_of(uint64_t total) { return (total + PACK_TILE - 1) / PACK_TILE; }
+
+}  // namespace
+
+extern "C" {
+
+size_t kam_planes_words(uint64_t total_chars) { return (size_t)(total_chars / 32 + 2); }
+
+size_t kam_pack_workspace_bytes(uint64_t total_chars, uint32_t n_seqs) {
+    (void)n_seqs;
+    const uint64_t nt = n_tiles_of(total_chars);
+    return kam_align_up((nt + 1) * sizeof(uint32_t), 256) + kam_align_up((nt + 1) * sizeof(uint64_t), 256);
+}
+
+int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_t n_seqs, uint64_t total_chars,
+                   uint64_t *d_planes, uint64_t *d_base_start, uint32_t *d_head_mask, void *d_ws, size_t ws_bytes,
+                   void *stream) {
+    KAM_REQUIRE(d_char_start && d_planes && d_base_start && d_head_mask, "null pointer");
+    KAM_REQUIRE(total_chars == 0 || d_chars, "null d_chars");
+    KAM_REQUIRE(((uintptr_t)d_chars & 15) == 0, "d_chars must be 16-byte aligned");
+    if (ws_bytes < kam_pack_workspace_bytes(total_chars, n_seqs)) {
+        kam_set_error("kam_pack_ascii: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t nt = n_tiles_of(total_chars);
+    KAM_REQUIRE(nt < (1ull << 31), "input too large for one call");
+    uint32_t *tile_count = (uint32_t *)d_ws;
+    uint64_t *tile_off = (uint64_t *)((char *)d_ws + kam_align_up((nt + 1) * sizeof(uint32_t), 256));
+
+    KAM_CUDA(cudaMemsetAsync(d_planes, 0, kam_planes_words(total_chars) * sizeof(uint64_t), st));
+    if (nt) pack_count_kernel<<<(unsigned)nt, PACK_THREADS, 0, st>>>(d_chars, total_chars, tile_count);
+    pack_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_count, nt, tile_off, d_char_start, n_seqs, total_chars,
+                                                 d_base_start);
+    if (nt)
+        pack_scatter_kernel<<<(unsigned)nt, PACK_THREADS, 0, st>>>(d_chars, total_chars, tile_off, d_char_start,
+                                                                   n_seqs, (uint2 *)d_planes, d_base_start);
+    if (n_seqs) head_mask_kernel<<<(n_seqs + 255) / 256, 256, 0, st>>>(d_chars, d_char_start, n_seqs, d_head_mask);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+"""GPU parity: pack + kmer_count CUDA kernels (through the C ABI) vs the oracle and the golden
+vectors produced by the reference's own machine code.  Bit-exact for counts and float64
+frequencies; float32 frequencies within 1e-6 relative (north_star tolerance: 1e-5)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import HIV_P, synth_records
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def R():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from kameris_b200 import repr as R
+    return R
+
+
+def _gpu_counts(R, recs, k, bits=16, out="counts"):
+    b = R.pack_records(recs)
+    return R.kmer_vectors(b, k, bits, out).cpu().numpy()
+
+
+def test_pack_layout(R):
+    recs = [b"NACGTTGCA", b"", b"acgtACGT", b"T" * 100, b"NNNN", b"GATTACA" * 700]
+    b = R.pack_records(recs)
+    base = b.base_start.cpu().numpy()
+    planes = b.planes.cpu().numpy().view(np.uint64)
+    head = b.head_mask.cpu().numpy().view(np.uint32)
+    pos = 0
+    for s, rec in enumerate(recs):
+        valid = [c for c in rec if c in b"ACGT"]
+        assert base[s] == pos and base[s + 1] - base[s] == len(valid)
+        for j, c in enumerate(valid):
+            w, bit = divmod(pos + j, 32)
+            x = (int(planes[w]) >> bit) & 1
+            y = (int(planes[w]) >> (32 + bit)) & 1
+            assert x == (c in b"GT") and y == (c in b"AT")
+        hm = sum(1 << i for i, c in enumerate(rec[:32]) if c in b"ACGT")
+        assert head[s] == hm
+        pos += len(valid)
+
+
+def test_golden_reference_machine_code(R, refcode_cases):
+    """Every golden case (quirks Q1/Q3/Q4, demo genomes, random dirty records), k <= 10."""
+    ks = sorted({int(k) for c in refcode_cases for k in c["k"] if int(k) <= 10})
+    for k in ks:
+        cases = [c for c in refcode_cases if str(k) in c["k"]]
+        recs = [c["record"].encode("latin-1") for c in cases]
+        got = _gpu_counts(R, recs, k, 16)
+        for i, c in enumerate(cases):
+            e = c["k"][str(k)]
+            assert hashlib.sha1(got[i].astype("<u2").tobytes()).hexdigest() == e["sha1"], (c["name"], k)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("bits", [16, 32])
+def test_demo_and_random_vs_oracle(R, demo_records, k, bits):
+    recs = [r for _, r in demo_records] + synth_records(40, 9000, seed=20261002 + k, dirty=0.002, p=HIV_P,
+                                                        jitter=900)
+    got = _gpu_counts(R, recs, k, bits)
+    for i, r in enumerate(recs):
+        assert np.array_equal(got[i], O.cgr_count(r, k, bits)), (i, k, bits)
+
+
+@pytest.mark.parametrize("k", [3, 6, 9])
+def test_frequencies(R, demo_records, k):
+    recs = [r for _, r in demo_records] + synth_records(10, 5000, seed=5 + k, dirty=0.01)
+    f64 = _gpu_counts(R, recs, k, 16, "freq64")
+    f32 = _gpu_counts(R, recs, k, 16, "freq32")
+    for i, r in enumerate(recs):
+        ref = O.frequencies(O.cgr_count(r, k, 16))
+        assert np.array_equal(f64[i], ref)                      # bit-exact numpy true division
+        np.testing.assert_allclose(f32[i], ref, rtol=1e-6, atol=0)
+
+
+def test_short_reads_k6(R):
+    """BASELINE config 4 shape: 150 bp reads, k=6 counts (ragged, some shorter than k, some empty)."""
+    recs = synth_records(3000, 150, seed=20261004, jitter=20) + [b"", b"ACG", b"NNNNNN", b"ACGTAC"]
+    got = _gpu_counts(R, recs, 6, 16)
+    chars = np.frombuffer(b"".join(recs), dtype=np.uint8)
+    start = np.concatenate([[0], np.cumsum([len(r) for r in recs])]).astype(np.uint64)
+    assert np.array_equal(got, O.cgr_batch(chars, start, 6, 16))
+
+
+@pytest.mark.parametrize("k,bits", [(9, 16), (9, 32), (8, 16), (7, 16), (2, 16), (12, 16)])
+def test_long_sequences_spill_path(R, k, bits):
+    """Sequences beyond the shared-memory path (length, or uint8 overflow) take the RED.ADD spill."""
+    recs = synth_records(3, 400000, seed=11 + k, dirty=0.001) + [b"ACGT" * 3000, b"A" * 70000,
+                                                                 synth_records(1, 9000, seed=2)[0]]
+    got = _gpu_counts(R, recs, k, bits)
+    for i, r in enumerate(recs):
+        assert np.array_equal(got[i], O.cgr_count(r, k, bits)), (i, k, bits)
+
+
+def test_wrap_and_wrapped_frequencies(R):
+    recs = [b"A" * 70000, b"T" * 65536, b"AC" * 40000]
+    for k in (1, 2, 9):
+        got = _gpu_counts(R, recs, k, 16)
+        f = _gpu_counts(R, recs, k, 16, "freq64")
+        for i, r in enumerate(recs):
+            c = O.cgr_count(r, k, 16)
+            assert np.array_equal(got[i], c)
+            with np.errstate(all="ignore"):
+                assert np.array_equal(f[i], O.frequencies(c), equal_nan=True)
+
+
+def test_property_full_size_k9(R):
+    """BASELINE config 2 size (10k x 9 kb, k=9) through size-independent properties: row sums equal
+    the number of emitting bases, and 64 sampled rows equal the oracle."""
+    n, L, k = 10000, 9000, 9
+    recs = synth_records(n, L, seed=20261002, p=HIV_P)
+    b = R.pack_records(recs)
+    out = R.kmer_vectors(b, k, 16)
+    sums = out.to(torch.int32).sum(dim=1).cpu().numpy()
+    assert (sums == L - k + 1).all()
+    rng = np.random.Generator(np.random.PCG64(1))
+    for i in rng.choice(n, 64, replace=False):
+        assert np.array_equal(out[i].cpu().numpy(), O.cgr_count(recs[i], k, 16))
+
+
+def test_errors(R):
+    b = R.pack_records([b"ACGT"])
+    with pytest.raises(ValueError):
+        R.kmer_vectors(b, 33)
+    with pytest.raises(ValueError):
+        R.kmer_vectors(b, 4, bits=8)
