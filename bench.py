@@ -1,0 +1,295 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of kameris_b200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): synthetic HIV-1-like set, 10 000 sequences x 9 kb, k=9 CGR
+frequency vectors (float32, 4^9 bins) -- the configuration "CGR vectors/sec (k=9)" is quoted on.
+One step = one pass of the `kmers` hot path over the whole batch.
+
+  value : vectors/s with the 2-bit planes already resident in HBM (kam_kmer_count only)
+  e2e   : vectors/s through kam_kmers_host with HOST buffers: ASCII records in pinned host memory
+          -> H2D -> pack -> count -> D2H of the float32 vectors into pinned host memory
+  roofline : HBM; algorithmic bytes/vector = ceil(L/4) + 4^k*4 over the CUDA-event
+          time of the kam_kmer_count launches, against MEASURED_PEAKS.json
+  cpu_baseline : the oracle's threaded restatement of the reference (`kind: port`; the reference's
+          executables cannot run here) on all host cores, on a bounded sample of the same workload
+  distances : secondary lines -- pairs/s of the distance kernels on vectors of the same shape
+
+With --gpus N (torchrun, one rank per GPU) every rank processes its own 10 000-sequence shard
+(sequences are independent: no data-path collective, weak scaling); value = all ranks' vectors /
+max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SEQS, SEQ_LEN, K, SEED = 10000, 9000, 9, 20261002
+HIV_P = np.array([0.36, 0.18, 0.24, 0.22])
+BINS = 4 ** K
+ALG_BYTES_PER_VEC = (SEQ_LEN + 3) // 4 + BINS * 4          # 2250 + 1 048 576
+
+
+def synth_chars(n, length, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+    chars = alpha[rng.choice(4, size=n * length, p=HIV_P)]
+    start = (np.arange(n + 1, dtype=np.uint64) * np.uint64(length))
+    return chars, start
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(sample_n=None, reps=3):
+    """Threaded oracle (restatement of generation_cgr + the numpy frequency pass) on the host cores."""
+    from oracle import oracle as O
+    threads = O.host_threads()
+    n = sample_n or max(64, 250 * threads)        # ~10-30 s of CPU work in total
+    chars, start = synth_chars(n, SEQ_LEN, SEED)
+    out = np.zeros((n, BINS), dtype=np.float32)     # pre-touched: no first-touch page faults in the timing
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.cgr_freq_batch(chars, start, K, 16, f64=False, threads=threads, out=out)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": n / best, "unit": "vectors/s", "cores": threads, "kind": "port",
+            "sample": "%d of the %d sequences x %d bp, k=%d, u16 counts + float32 frequencies, best of %d, "
+                      "output buffer pre-touched" % (n, N_SEQS, SEQ_LEN, K, reps)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port: its executables cannot run here)."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = O.host_threads()
+    n = max(64, 250 * threads)
+    chars, start = synth_chars(n, SEQ_LEN, SEED)
+    out = np.zeros((n, BINS), dtype=np.float32)
+    for _ in range(args.warmup):
+        O.cgr_freq_batch(chars, start, K, 16, f64=False, threads=threads, out=out)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.cgr_freq_batch(chars, start, K, 16, f64=False, threads=threads, out=out)
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    sample = "%d sequences x %d bp per step (bounded sample of the %d-sequence workload)" % (n, SEQ_LEN, N_SEQS)
+    print(json.dumps({
+        "impl": "reference", "metric": "cgr_vectors_per_sec_k9", "value": v, "unit": "vectors/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic HIV-1-like 10k x 9 kb, k=9 CGR frequency vectors (configs[1])",
+                   "n_seqs_per_step": n, "seq_len": SEQ_LEN, "k": K},
+        "cpu_baseline": {"value": v, "unit": "vectors/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def distance_lines(torch, dev, hbm_peak, tf_peak):
+    """Secondary measurements: pairs/s of the distance kernels (filled in as they are built)."""
+    try:
+        from kameris_b200 import dist
+    except ImportError:
+        return None
+    try:
+        return dist.bench_lines(torch, dev, hbm_peak, tf_peak)
+    except Exception as e:  # a distance kernel that is not built yet must not hide the headline
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-distances", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist_pg
+    from kameris_b200 import _lib
+    from kameris_b200 import repr as R
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist_pg.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    hbm_peak, tf_peak, peak_src = load_peaks()
+
+    # ---- inputs: every rank its own shard (weak scaling) ------------------------------------------------
+    chars, start = synth_chars(N_SEQS, SEQ_LEN, SEED + rank)
+    h_chars = torch.from_numpy(chars.copy()).pin_memory()
+    h_start = torch.from_numpy(start.astype(np.int64))
+    d_chars = torch.zeros(len(chars) + 16, dtype=torch.uint8, device=dev)
+    d_chars[:len(chars)] = h_chars.to(dev)
+    batch = R.pack_chars(d_chars, h_start.to(dev), N_SEQS, len(chars))
+    out = torch.empty((N_SEQS, BINS), dtype=torch.float32, device=dev)      # 10.5 GB
+    ws = R.kmer_workspace(N_SEQS, K, dev)
+
+    def step():
+        R.kmer_vectors(batch, K, 16, "freq32", out_tensor=out, workspace=ws)
+
+    def barrier():
+        if world > 1:
+            dist_pg.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    # sanity before timing: row sums of counts == L-k+1  <=>  frequencies sum to 1
+    s = out[:64].sum(dim=1)
+    assert torch.allclose(s, torch.ones_like(s), atol=1e-4), "frequency rows do not sum to 1"
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop()
+
+    # ---- e2e: host ASCII -> host float32 vectors through the C ABI --------------------------------------
+    h_out = torch.empty((N_SEQS, BINS), dtype=torch.float32).pin_memory()
+    h_start_u64 = start.astype(np.uint64)
+
+    def e2e_step():
+        _lib.check(lib.kam_kmers_host(h_chars.data_ptr(), h_start_u64.ctypes.data, N_SEQS, K, 16,
+                                      _lib.KAM_OUT_FREQ_F32, h_out.data_ptr()))
+
+    e2e_step()                                   # warm-up: allocates the pipeline's device buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    chk = float(h_out[N_SEQS // 2].sum())
+    assert abs(chk - 1.0) < 1e-4, "e2e output row does not sum to 1"
+
+    # ---- max over ranks -----------------------------------------------------------------------------------
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist_pg.all_reduce(t, op=dist_pg.ReduceOp.MAX)
+    total_ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = world * N_SEQS / (ms_per_step * 1e-3)
+        k_ms = float(np.mean(kernel_ms))
+        achieved = ALG_BYTES_PER_VEC * N_SEQS / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the ncu capture
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("cgr_tile_kernel_f32_k9_bytes_per_launch")
+        line = {
+            "metric": "cgr_vectors_per_sec_k9", "value": value, "unit": "vectors/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "synthetic HIV-1-like 10k x 9 kb, k=9 CGR frequency vectors (configs[1])",
+                       "n_seqs_per_gpu": N_SEQS, "seq_len": SEQ_LEN, "k": K, "bins": BINS, "out": "float32",
+                       "l2": "each step writes 10.5 GB of vectors (>> 126 MB L2), nothing is re-read",
+                       "parallelism": "sequence shards, no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "kernel": "cgr_tile_kernel<uint8,float>",
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_vector": ALG_BYTES_PER_VEC,
+                         "peak_source": peak_src},
+            "e2e": {"value": world * N_SEQS / e2e_s, "unit": "vectors/s",
+                    "h2d_bytes_per_step": int(len(chars) + (N_SEQS + 1) * 8),
+                    "d2h_bytes_per_step": int(N_SEQS * BINS * 4), "ms_per_step": e2e_s * 1e3,
+                    "api": "kam_kmers_host (C ABI, pinned host buffers)"},
+            "gpu_launches": args.steps * 1,
+            "clocks": clocks,
+            "host": {"cores": len(os.sched_getaffinity(0))},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_distances:
+            d = distance_lines(torch, dev, hbm_peak, tf_peak)
+            if d is not None:
+                line["distances"] = d
+        print(json.dumps(line))
+    if world > 1:
+        dist_pg.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -7,7 +7,6 @@
     return KAM_E_UNSUPPORTED;
 
 extern "C" {
-int kam_kmers_host(const uint8_t *, const uint64_t *, uint32_t, int, int, int, void *) { KAM_STUB(kam_kmers_host) }
 int kam_manhattan_tri(const void *, int, uint32_t, uint64_t, uint64_t, uint32_t, uint32_t, uint32_t *, void *) { KAM_STUB(kam_manhattan_tri) }
 int kam_manhattan_rect(const void *, const void *, int, uint32_t, uint32_t, uint64_t, uint64_t, uint64_t, uint32_t *, void *) { KAM_STUB(kam_manhattan_rect) }
 int kam_manhattan_rect_f32(const void *, int, const float *, uint32_t, uint32_t, uint64_t, uint64_t, uint64_t, float *, void *) { KAM_STUB(kam_manhattan_rect_f32) }

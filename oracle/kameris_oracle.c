@@ -250,6 +250,50 @@ int orc_cgr_batch(const char *chars, const uint64_t *start, size_t n_seqs, int k
     return 0;
 }
 
+/* The reference `kmers` step with mode=frequencies: run<T> (above) followed by the numpy pass
+ * backend.py:42-56.  Here both run inside the per-sequence task, on all threads (generous to the
+ * reference: its numpy pass is single-threaded), writing float32 or float64 frequencies. */
+typedef struct {
+    const char *chars;
+    const uint64_t *start;
+    int k, bits, out_f64;
+    void *out;
+    void *scratch; /* n_threads? no: one count vector per task slot, allocated per task */
+} orc_freq_job;
+
+static void orc_freq_task(void *c, size_t i) {
+    orc_freq_job *j = (orc_freq_job *)c;
+    const size_t d = (size_t)1 << (2 * j->k);
+    const char *rec = j->chars + j->start[i];
+    const size_t n = (size_t)(j->start[i + 1] - j->start[i]);
+    uint64_t s = 0;
+    if (j->bits == 16) {
+        uint16_t *cnt = (uint16_t *)calloc(d, sizeof(uint16_t));
+        orc_cgr_count_u16(rec, n, j->k, cnt);
+        for (size_t q = 0; q < d; q++) s += cnt[q];
+        const double ds = (double)s;
+        if (j->out_f64) { double *o = (double *)j->out + i * d; for (size_t q = 0; q < d; q++) o[q] = (double)cnt[q] / ds; }
+        else { float *o = (float *)j->out + i * d; for (size_t q = 0; q < d; q++) o[q] = (float)((double)cnt[q] / ds); }
+        free(cnt);
+    } else {
+        uint32_t *cnt = (uint32_t *)calloc(d, sizeof(uint32_t));
+        orc_cgr_count_u32(rec, n, j->k, cnt);
+        for (size_t q = 0; q < d; q++) s += cnt[q];
+        const double ds = (double)s;
+        if (j->out_f64) { double *o = (double *)j->out + i * d; for (size_t q = 0; q < d; q++) o[q] = (double)cnt[q] / ds; }
+        else { float *o = (float *)j->out + i * d; for (size_t q = 0; q < d; q++) o[q] = (float)((double)cnt[q] / ds); }
+        free(cnt);
+    }
+}
+
+int orc_cgr_freq_batch(const char *chars, const uint64_t *start, size_t n_seqs, int k, int bits,
+                       int out_f64, void *out, int n_threads) {
+    if (k < 1 || 2 * k > 64 || (bits != 16 && bits != 32)) return -1;
+    orc_freq_job job = {chars, start, k, bits, out_f64, out, NULL};
+    orc_execute(orc_freq_task, &job, n_seqs, n_threads);
+    return 0;
+}
+
 /* generation_dists main: one task per row i computing every j>i (dists@0x10001b8cd-0x10001b942),
  * packed strict upper triangle, index n*i - i(i+3)/2 + j - 1 (dists@0x10001bf7e-0x10001bfc0). */
 typedef struct {

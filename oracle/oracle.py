@@ -75,6 +75,9 @@ def lib():
         L.orc_cgr_batch.restype = ctypes.c_int
         L.orc_cgr_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.orc_cgr_freq_batch.restype = ctypes.c_int
+        L.orc_cgr_freq_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.orc_dists_triangle.restype = ctypes.c_int
         L.orc_dists_triangle.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
@@ -155,6 +158,20 @@ def cgr_batch(chars: np.ndarray, start: np.ndarray, k: int, bits: int = 16, thre
     chars = np.ascontiguousarray(chars, dtype=np.uint8)
     start = np.ascontiguousarray(start, dtype=np.uint64)
     rc = lib().orc_cgr_batch(_ptr(chars), _ptr(start), n, k, bits, _ptr(out), threads or host_threads())
+    if rc != 0:
+        raise ValueError("bad k/bits")
+    return out
+
+
+def cgr_freq_batch(chars, start, k, bits=16, f64=False, threads=0, out=None):
+    """`kmers` step with mode=frequencies (run<T> + backend.py:42-56), threaded; float32/float64."""
+    n = len(start) - 1
+    if out is None:
+        out = np.empty((n, 4 ** k), dtype=np.float64 if f64 else np.float32)
+    chars = np.ascontiguousarray(chars, dtype=np.uint8)
+    start = np.ascontiguousarray(start, dtype=np.uint64)
+    rc = lib().orc_cgr_freq_batch(_ptr(chars), _ptr(start), n, k, bits, int(f64), _ptr(out),
+                                  threads or host_threads())
     if rc != 0:
         raise ValueError("bad k/bits")
     return out
