@@ -121,14 +121,22 @@ int64_t kam_fasta_record0(const char *buf, size_t n, char *out);
  * (generation_dists @0x10001bf7e).  [row_begin,row_end) selects the block of rows i a rank
  * computes (all j>i); entries of other rows are left untouched.
  * ------------------------------------------------------------------------------------------- */
+/* The manhattan entry points synchronise `stream` once (they look at the largest element to pick
+ * the 4-elements-per-instruction byte path when every count is <= 255).
+ * elem: KAM_U8/U16/U32 (tile kernel); kam_manhattan_tri also takes KAM_U64/F32/F64 through a
+ * serial kernel that reproduces the reference's truncating float accumulate (quirk Q5). */
+size_t kam_manhattan_workspace_bytes(uint32_t rows, uint64_t d);
 int kam_manhattan_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
-                      uint32_t row_begin, uint32_t row_end, uint32_t *d_tri, void *stream);
-/* rectangular m x c: out[i*c + j] = manhat(x_i, y_j) */
+                      uint32_t row_begin, uint32_t row_end, uint32_t *d_tri, void *d_ws,
+                      size_t ws_bytes, void *stream);
+/* rectangular m x c: out[i*c + j] = manhat(x_i, y_j); workspace = ws(m,d) + ws(c,d) */
 int kam_manhattan_rect(const void *d_x, const void *d_y, int elem, uint32_t m, uint32_t c,
-                       uint64_t d, uint64_t ldx, uint64_t ldy, uint32_t *d_out, void *stream);
+                       uint64_t d, uint64_t ldx, uint64_t ldy, uint32_t *d_out, void *d_ws,
+                       size_t ws_bytes, void *stream);
 /* float32 L1 distance to float32 centroids (BASELINE config 4); out[i*c+j] = sum |x_i - y_j| */
 int kam_manhattan_rect_f32(const void *d_x, int elem_x, const float *d_y, uint32_t m, uint32_t c,
-                           uint64_t d, uint64_t ldx, uint64_t ldy, float *d_out, void *stream);
+                           uint64_t d, uint64_t ldx, uint64_t ldy, float *d_out, void *d_ws,
+                           size_t ws_bytes, void *stream);
 size_t kam_info_workspace_bytes(uint32_t n, uint64_t d);
 int kam_info_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                  uint32_t row_begin, uint32_t row_end, float *d_tri, void *d_ws, size_t ws_bytes,

@@ -29,12 +29,13 @@ SIGNATURES = {
                                c_void_p, c_size_t, c_void_p]),
     "kam_kmers_host": (c_int, [c_void_p, c_void_p, c_uint32, c_int, c_int, c_int, c_void_p]),
     "kam_fasta_record0": (ctypes.c_int64, [c_void_p, c_size_t, c_void_p]),
+    "kam_manhattan_workspace_bytes": (c_size_t, [c_uint32, c_uint64]),
     "kam_manhattan_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p,
-                                  c_void_p]),
+                                  c_void_p, c_size_t, c_void_p]),
     "kam_manhattan_rect": (c_int, [c_void_p, c_void_p, c_int, c_uint32, c_uint32, c_uint64, c_uint64, c_uint64,
-                                   c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "kam_manhattan_rect_f32": (c_int, [c_void_p, c_int, c_void_p, c_uint32, c_uint32, c_uint64, c_uint64, c_uint64,
-                                       c_void_p, c_void_p]),
+                                       c_void_p, c_void_p, c_size_t, c_void_p]),
     "kam_info_workspace_bytes": (c_size_t, [c_uint32, c_uint64]),
     "kam_info_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p,
                              c_size_t, c_void_p]),

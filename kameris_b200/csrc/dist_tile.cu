@@ -1,0 +1,417 @@
+// dist_tile.cu -- pairwise distances that are NOT contractions: manhattan (reference `manhat`,
+// uint32-exact), Jaccard-on-presence (reference `info`, float32) and float32 L1 to centroids.
+//
+// Replaces the row lambdas of generation_dists (generation_dists_mac_avx2 @0x10001b8c0; manhat
+// body @0x10001bd87-0x10001bfc8, info body @0x10001bab5-0x10001bcb0), one task per row i over
+// all j>i, and its packed-triangle store (index n*i - i(i+3)/2 + j - 1, @0x10001bf7e).
+//
+// Design: a pre-pass rewrites the operand rows into a k-major word matrix Xt[kw][row]
+// (uint32 words: one element, four uint8 elements, 32 presence bits, or one float), so a
+// (rows x k-chunk) tile is a plain 2-D box that TMA (cp.async.bulk.tensor) drops into shared
+// memory behind an mbarrier, 4 stages deep.  Each CTA owns a TM x 128 tile of pairs; each thread
+// an RM x 8 register block and reads its a/b fragments with conflict-free LDS.128.  The inner op
+// is one VABSDIFF.U32 (|a-b|+acc) per pair-element, one VABSDIFF4.U8.ACC per four when every
+// count fits a byte, LOP3+POPC for Jaccard, 2 FADD for float L1.  Bound: CUDA-core issue rate
+// (not HBM, not tensor: |a-b| is not a contraction).
+#include <type_traits>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace {
+
+enum { OP_SAD32 = 0, OP_SAD8X4 = 1, OP_JACC = 2, OP_L1F32 = 3 };
+
+constexpr int DT_THREADS = 256;
+constexpr int TN = 128;
+constexpr int KC = 16;
+constexpr int STAGES = 4;
+
+template <int OP>
+struct OpT {
+    static constexpr int RM = (OP == OP_JACC) ? 4 : 8;
+    static constexpr int NACC = (OP == OP_JACC) ? 2 : 1;
+    using acc_t = typename std::conditional<OP == OP_L1F32, float, uint32_t>::type;
+    using out_t = typename std::conditional<OP == OP_JACC || OP == OP_L1F32, float, uint32_t>::type;
+};
+
+template <int OP>
+__device__ __forceinline__ void pair_op(typename OpT<OP>::acc_t *acc, uint32_t a, uint32_t b) {
+    if constexpr (OP == OP_SAD32) acc[0] = __usad(a, b, acc[0]);
+    else if constexpr (OP == OP_SAD8X4) acc[0] += __vsadu4(a, b);
+    else if constexpr (OP == OP_JACC) {
+        acc[0] += __popc(a | b);   // union
+        acc[1] += __popc(a ^ b);   // union - intersection
+    } else acc[0] += fabsf(__uint_as_float(a) - __uint_as_float(b));
+}
+
+// packed-triangle offset of row i: index(i, j) = tri_base(i) + j
+__device__ __forceinline__ long long tri_base(long long n, long long i) { return n * i - i * (i + 3) / 2 - 1; }
+
+template <int OP, bool TRI>
+__global__ void __launch_bounds__(DT_THREADS) pair_tile_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               uint32_t kw_total, uint32_t n_rows, uint32_t n_cols,
+                                                               uint32_t row_begin, uint32_t row_end,
+                                                               uint32_t tile_row0,
+                                                               typename OpT<OP>::out_t *__restrict__ out) {
+    constexpr int RM = OpT<OP>::RM, NACC = OpT<OP>::NACC, TM = 16 * RM;
+    using acc_t = typename OpT<OP>::acc_t;
+    extern __shared__ unsigned char smem_raw[];
+    // TMA destinations: align the carve-up to 1024 B (the launch adds 1024 B of slack)
+    unsigned char *smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint32_t *sA = reinterpret_cast<uint32_t *>(smem_al);    // [STAGES][KC][TM]
+    uint32_t *sB = sA + STAGES * KC * TM;                    // [STAGES][KC][TN]
+    __shared__ __align__(8) uint64_t full[STAGES];
+
+    const uint32_t bi = tile_row0 + blockIdx.y, bj = blockIdx.x;
+    const uint32_t r0 = bi * TM, c0 = bj * TN;
+    if (TRI && c0 + TN - 1 <= r0) return;                    // no pair i<j inside this tile
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const uint32_t n_it = (kw_total + KC - 1) / KC;
+    constexpr uint32_t STAGE_BYTES = (uint32_t)(KC * (TM + TN) * 4);
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (uint32_t it = 0; it < (uint32_t)STAGES && it < n_it; ++it) {
+            mbar_arrive_expect_tx(&full[it], STAGE_BYTES);
+            tma_load_2d(sA + it * KC * TM, &tmA, (int32_t)r0, (int32_t)(it * KC), &full[it]);
+            tma_load_2d(sB + it * KC * TN, &tmB, (int32_t)c0, (int32_t)(it * KC), &full[it]);
+        }
+    }
+
+    acc_t acc[RM][8][NACC];
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int q = 0; q < NACC; ++q) acc[i][j][q] = 0;
+
+    for (uint32_t it = 0; it < n_it; ++it) {
+        const uint32_t s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1u);
+        const uint32_t *a_base = sA + s * KC * TM, *b_base = sB + s * KC * TN;
+#pragma unroll 4
+        for (int kk = 0; kk < KC; ++kk) {
+            uint32_t a[RM], b[8];
+            const uint4 a0 = *reinterpret_cast<const uint4 *>(a_base + kk * TM + ty * 4);
+            a[0] = a0.x, a[1] = a0.y, a[2] = a0.z, a[3] = a0.w;
+            if constexpr (RM == 8) {
+                const uint4 a1 = *reinterpret_cast<const uint4 *>(a_base + kk * TM + 64 + ty * 4);
+                a[4] = a1.x, a[5] = a1.y, a[6] = a1.z, a[7] = a1.w;
+            }
+            const uint4 b0 = *reinterpret_cast<const uint4 *>(b_base + kk * TN + tx * 4);
+            const uint4 b1 = *reinterpret_cast<const uint4 *>(b_base + kk * TN + 64 + tx * 4);
+            b[0] = b0.x, b[1] = b0.y, b[2] = b0.z, b[3] = b0.w;
+            b[4] = b1.x, b[5] = b1.y, b[6] = b1.z, b[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pair_op<OP>(acc[i][j], a[i], b[j]);
+        }
+        __syncthreads();   // every thread is done with stage s
+        if (tid == 0 && it + STAGES < n_it) {
+            const uint32_t nx = it + STAGES;
+            mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+            tma_load_2d(sA + s * KC * TM, &tmA, (int32_t)r0, (int32_t)(nx * KC), &full[s]);
+            tma_load_2d(sB + s * KC * TN, &tmB, (int32_t)c0, (int32_t)(nx * KC), &full[s]);
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+        const uint32_t r = r0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (r >= n_rows || r < row_begin || r >= row_end) continue;
+        const long long base = TRI ? tri_base(n_rows, r) : (long long)r * n_cols;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t c = c0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (c >= n_cols || (TRI && c <= r)) continue;
+            if constexpr (OP == OP_JACC) {
+                // generation_dists @0x10001bc13: U==0 ? 0 : (1.0f/(float)U) * (float)(U-I), single precision
+                const uint32_t U = acc[i][j][0], X = acc[i][j][1];
+                out[base + c] = U == 0 ? 0.0f : __fmul_rn(__fdiv_rn(1.0f, (float)U), (float)X);
+            } else {
+                out[base + c] = acc[i][j][0];
+            }
+        }
+    }
+}
+
+// ---- operand pre-pass: row-major x[n][d] (type T) -> k-major words Xt[kw][np] ---------------------
+template <typename T, int OP>
+__device__ __forceinline__ uint32_t make_word(const T *__restrict__ row, uint64_t kw, uint64_t d) {
+    if constexpr (OP == OP_SAD32) {
+        return kw < d ? (uint32_t)row[kw] : 0u;
+    } else if constexpr (OP == OP_SAD8X4) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint64_t e = kw * 4 + b;
+            if (e < d) w |= ((uint32_t)row[e] & 0xffu) << (8 * b);
+        }
+        return w;
+    } else if constexpr (OP == OP_JACC) {
+        uint32_t w = 0;
+        for (int b = 0; b < 32; ++b) {
+            const uint64_t e = kw * 32 + b;
+            if (e < d && row[e] > (T)0) w |= 1u << b;
+        }
+        return w;
+    } else {
+        return kw < d ? __float_as_uint((float)row[kw]) : 0u;
+    }
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(256) to_kmajor_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
+                                                        uint32_t kw_total, uint32_t np, uint32_t *__restrict__ xt) {
+    __shared__ uint32_t tile[32][33];
+    const uint32_t k0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (uint32_t ry = threadIdx.y; ry < 32; ry += 8) {
+        const uint32_t row = r0 + ry, kw = k0 + threadIdx.x;
+        tile[ry][threadIdx.x] = (row < n && kw < kw_total) ? make_word<T, OP>(x + (uint64_t)row * ld, kw, d) : 0u;
+    }
+    __syncthreads();
+    for (uint32_t ky = threadIdx.y; ky < 32; ky += 8) {
+        const uint32_t kw = k0 + ky, col = r0 + threadIdx.x;
+        if (kw < kw_total && col < np) xt[(uint64_t)kw * np + col] = tile[threadIdx.x][ky];
+    }
+}
+
+template <typename T>
+__global__ void max_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld, uint32_t *__restrict__ out) {
+    uint32_t m = 0;
+    const uint64_t total = (uint64_t)n * d;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = (uint32_t)x[(i / d) * ld + (i % d)];
+        m = v > m ? v : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// Faithful serial form for element types the tile kernel does not cover (u64, and the truncating
+// float accumulate of quirk Q5): one thread per pair, sequential over d like the reference.
+template <typename T>
+__global__ void manhat_serial_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,
+                                     uint32_t row_end, uint32_t *__restrict__ tri) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = row_begin + blockIdx.y;
+    if (i >= row_end || j >= n || j <= i) return;
+    const T *a = x + (uint64_t)i * ld, *b = x + (uint64_t)j * ld;
+    uint32_t acc = 0;
+    for (uint64_t e = 0; e < d; ++e) {
+        if constexpr (std::is_floating_point<T>::value) {
+            const T t = a[e] - b[e];
+            acc = (uint32_t)(long long)((double)acc + (double)(t < 0 ? -t : t));
+        } else {
+            acc += (uint32_t)(a[e] > b[e] ? a[e] - b[e] : b[e] - a[e]);
+        }
+    }
+    tri[tri_base(n, i) + j] = acc;
+}
+
+inline uint32_t pad4(uint32_t n) { return (n + 3u) & ~3u; }
+
+inline uint32_t kw_of(int op, uint64_t d) {
+    if (op == OP_SAD8X4) return (uint32_t)((d + 3) / 4);
+    if (op == OP_JACC) return (uint32_t)((d + 31) / 32);
+    return (uint32_t)d;
+}
+
+template <typename T, int OP>
+int convert_rows(const void *x, uint32_t n, uint64_t d, uint64_t ld, uint32_t *xt, cudaStream_t st) {
+    const uint32_t kw = kw_of(OP, d), np = pad4(n);
+    dim3 grid((kw + 31) / 32, (np + 31) / 32), block(32, 8);
+    to_kmajor_kernel<T, OP><<<grid, block, 0, st>>>((const T *)x, n, d, ld, kw, np, xt);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+template <int OP>
+int convert_dispatch(const void *x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t *xt, cudaStream_t st) {
+    switch (elem) {
+        case KAM_U8: return convert_rows<uint8_t, OP>(x, n, d, ld, xt, st);
+        case KAM_U16: return convert_rows<uint16_t, OP>(x, n, d, ld, xt, st);
+        case KAM_U32: return convert_rows<uint32_t, OP>(x, n, d, ld, xt, st);
+        case KAM_U64:
+            if (OP == OP_JACC) return convert_rows<uint64_t, OP>(x, n, d, ld, xt, st);
+            break;
+        case KAM_F32:
+            if (OP == OP_JACC || OP == OP_L1F32) return convert_rows<float, OP>(x, n, d, ld, xt, st);
+            break;
+        case KAM_F64:
+            if (OP == OP_JACC) return convert_rows<double, OP>(x, n, d, ld, xt, st);
+            break;
+    }
+    kam_set_error("element type %d not supported for this metric", elem);
+    return KAM_E_UNSUPPORTED;
+}
+
+template <int OP, bool TRI>
+int launch_pairs(const uint32_t *at, uint32_t n_rows, const uint32_t *bt, uint32_t n_cols, uint32_t kw,
+                 uint32_t row_begin, uint32_t row_end, void *out, cudaStream_t st) {
+    constexpr int TM = 16 * OpT<OP>::RM;
+    CUtensorMap tmA, tmB;
+    const uint32_t npa = pad4(n_rows), npb = pad4(n_cols);
+    int rc = kam_make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, at, npa, kw, (uint64_t)npa * 4, TM, KC,
+                              CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    rc = kam_make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, bt, npb, kw, (uint64_t)npb * 4, TN, KC,
+                          CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    const size_t smem = (size_t)STAGES * KC * (TM + TN) * 4 + 1024;
+    auto kern = pair_tile_kernel<OP, TRI>;
+    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (row_end > n_rows) row_end = n_rows;
+    if (row_begin >= row_end) return KAM_OK;
+    const uint32_t t0 = row_begin / TM, t1 = (row_end - 1) / TM + 1;
+    dim3 grid((n_cols + TN - 1) / TN, t1 - t0);
+    kern<<<grid, DT_THREADS, smem, st>>>(tmA, tmB, kw, n_rows, n_cols, row_begin, row_end, t0,
+                                         (typename OpT<OP>::out_t *)out);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+size_t xt_bytes(uint32_t rows, uint32_t kw) { return kam_align_up((size_t)kw * pad4(rows) * 4, 1024); }
+
+// max element of x (device) -> host; synchronises `st`
+int max_of(const void *x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t *d_flag, uint32_t *h_max,
+           cudaStream_t st) {
+    KAM_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
+    const int blocks = kam_sm_count() * 8;
+    if (elem == KAM_U8) max_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t *)x, n, d, ld, d_flag);
+    else if (elem == KAM_U16) max_kernel<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t *)x, n, d, ld, d_flag);
+    else max_kernel<uint32_t><<<blocks, 256, 0, st>>>((const uint32_t *)x, n, d, ld, d_flag);
+    KAM_CUDA(cudaGetLastError());
+    KAM_CUDA(cudaMemcpyAsync(h_max, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    KAM_CUDA(cudaStreamSynchronize(st));
+    return KAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t kam_manhattan_workspace_bytes(uint32_t rows_total, uint64_t d) {
+    // worst case: one uint32 word per element, plus padding for two operands and the flag word
+    return xt_bytes(rows_total, (uint32_t)d) + 2 * 4096 + 1024;
+}
+
+int kam_manhattan_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,
+                      uint32_t row_end, uint32_t *d_tri, void *d_ws, size_t ws_bytes, void *stream) {
+    KAM_REQUIRE(d_x && d_tri, "null pointer");
+    KAM_REQUIRE(d >= 1 && d < (1ull << 32) && ld >= d, "bad d / ld");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n < 2 || row_begin >= row_end) return KAM_OK;
+    if (row_end > n) row_end = n;
+    if (elem == KAM_U64 || elem == KAM_F32 || elem == KAM_F64) {
+        dim3 grid((n + 127) / 128, row_end - row_begin);
+        if (elem == KAM_U64) manhat_serial_kernel<uint64_t><<<grid, 128, 0, st>>>((const uint64_t *)d_x, n, d, ld, row_begin, row_end, d_tri);
+        else if (elem == KAM_F32) manhat_serial_kernel<float><<<grid, 128, 0, st>>>((const float *)d_x, n, d, ld, row_begin, row_end, d_tri);
+        else manhat_serial_kernel<double><<<grid, 128, 0, st>>>((const double *)d_x, n, d, ld, row_begin, row_end, d_tri);
+        KAM_CUDA(cudaGetLastError());
+        return KAM_OK;
+    }
+    KAM_REQUIRE(elem == KAM_U8 || elem == KAM_U16 || elem == KAM_U32, "bad element type");
+    KAM_REQUIRE(d_ws, "null workspace");
+    if (ws_bytes < kam_manhattan_workspace_bytes(n, d)) {
+        kam_set_error("kam_manhattan_tri: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    uint32_t *flag = (uint32_t *)d_ws;
+    uint32_t *xt = (uint32_t *)((char *)d_ws + 1024);
+    uint32_t mx = 0;
+    int rc = max_of(d_x, elem, n, d, ld, flag, &mx, st);
+    if (rc) return rc;
+    if (mx <= 255) {   // every count fits a byte: four elements per VABSDIFF4
+        if ((rc = convert_dispatch<OP_SAD8X4>(d_x, elem, n, d, ld, xt, st))) return rc;
+        return launch_pairs<OP_SAD8X4, true>(xt, n, xt, n, kw_of(OP_SAD8X4, d), row_begin, row_end, d_tri, st);
+    }
+    if ((rc = convert_dispatch<OP_SAD32>(d_x, elem, n, d, ld, xt, st))) return rc;
+    return launch_pairs<OP_SAD32, true>(xt, n, xt, n, kw_of(OP_SAD32, d), row_begin, row_end, d_tri, st);
+}
+
+int kam_manhattan_rect(const void *d_x, const void *d_y, int elem, uint32_t m, uint32_t c, uint64_t d, uint64_t ldx,
+                       uint64_t ldy, uint32_t *d_out, void *d_ws, size_t ws_bytes, void *stream) {
+    KAM_REQUIRE(d_x && d_y && d_out && d_ws, "null pointer");
+    KAM_REQUIRE(elem == KAM_U8 || elem == KAM_U16 || elem == KAM_U32, "bad element type");
+    KAM_REQUIRE(d >= 1 && d < (1ull << 32) && ldx >= d && ldy >= d, "bad d / ld");
+    if (m == 0 || c == 0) return KAM_OK;
+    if (ws_bytes < kam_manhattan_workspace_bytes(m, d) + kam_manhattan_workspace_bytes(c, d)) {
+        kam_set_error("kam_manhattan_rect: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *flag = (uint32_t *)d_ws;
+    uint32_t mx = 0, my = 0;
+    int rc;
+    if ((rc = max_of(d_x, elem, m, d, ldx, flag, &mx, st)) || (rc = max_of(d_y, elem, c, d, ldy, flag, &my, st))) return rc;
+    const bool bytes = mx <= 255 && my <= 255;
+    const uint32_t kw = kw_of(bytes ? OP_SAD8X4 : OP_SAD32, d);
+    uint32_t *xt = (uint32_t *)((char *)d_ws + 1024);
+    uint32_t *yt = (uint32_t *)((char *)xt + xt_bytes(m, kw));
+    if (bytes) {
+        if ((rc = convert_dispatch<OP_SAD8X4>(d_x, elem, m, d, ldx, xt, st)) ||
+            (rc = convert_dispatch<OP_SAD8X4>(d_y, elem, c, d, ldy, yt, st)))
+            return rc;
+        return launch_pairs<OP_SAD8X4, false>(xt, m, yt, c, kw, 0, m, d_out, st);
+    }
+    if ((rc = convert_dispatch<OP_SAD32>(d_x, elem, m, d, ldx, xt, st)) ||
+        (rc = convert_dispatch<OP_SAD32>(d_y, elem, c, d, ldy, yt, st)))
+        return rc;
+    return launch_pairs<OP_SAD32, false>(xt, m, yt, c, kw, 0, m, d_out, st);
+}
+
+int kam_manhattan_rect_f32(const void *d_x, int elem_x, const float *d_y, uint32_t m, uint32_t c, uint64_t d,
+                           uint64_t ldx, uint64_t ldy, float *d_out, void *d_ws, size_t ws_bytes, void *stream) {
+    KAM_REQUIRE(d_x && d_y && d_out && d_ws, "null pointer");
+    KAM_REQUIRE(d >= 1 && d < (1ull << 32) && ldx >= d && ldy >= d, "bad d / ld");
+    if (m == 0 || c == 0) return KAM_OK;
+    if (ws_bytes < kam_manhattan_workspace_bytes(m, d) + kam_manhattan_workspace_bytes(c, d)) {
+        kam_set_error("kam_manhattan_rect_f32: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t kw = kw_of(OP_L1F32, d);
+    uint32_t *xt = (uint32_t *)((char *)d_ws + 1024);
+    uint32_t *yt = (uint32_t *)((char *)xt + xt_bytes(m, kw));
+    int rc;
+    if ((rc = convert_dispatch<OP_L1F32>(d_x, elem_x, m, d, ldx, xt, st)) ||
+        (rc = convert_dispatch<OP_L1F32>(d_y, KAM_F32, c, d, ldy, yt, st)))
+        return rc;
+    return launch_pairs<OP_L1F32, false>(xt, m, yt, c, kw, 0, m, d_out, st);
+}
+
+size_t kam_info_workspace_bytes(uint32_t n, uint64_t d) { return xt_bytes(n, kw_of(OP_JACC, d)) + 1024; }
+
+int kam_info_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,
+                 uint32_t row_end, float *d_tri, void *d_ws, size_t ws_bytes, void *stream) {
+    KAM_REQUIRE(d_x && d_tri && d_ws, "null pointer");
+    KAM_REQUIRE(elem >= KAM_U8 && elem <= KAM_F64, "bad element type");
+    KAM_REQUIRE(d >= 1 && d < (1ull << 32) && ld >= d, "bad d / ld");
+    if (n < 2 || row_begin >= row_end) return KAM_OK;
+    if (ws_bytes < kam_info_workspace_bytes(n, d)) {
+        kam_set_error("kam_info_tri: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *xt = (uint32_t *)((char *)d_ws + 1024);
+    int rc = convert_dispatch<OP_JACC>(d_x, elem, n, d, ld, xt, st);
+    if (rc) return rc;
+    return launch_pairs<OP_JACC, true>(xt, n, xt, n, kw_of(OP_JACC, d), row_begin, row_end, d_tri, st);
+}
+
+}  // extern "C"

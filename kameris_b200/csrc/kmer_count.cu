@@ -85,6 +85,19 @@ __device__ __forceinline__ OUT convert_count(uint32_t c, double inv_unused, doub
 // ---- path A ------------------------------------------------------------------------------------
 // CT: shared-memory counter type (uint8_t with overflow detection, or uint32_t).
 // OUT: uint16_t / uint32_t (counts), float / double (frequencies).
+
+// one increment of local bin lb (uint8 counters packed four to a word, or uint32 counters)
+template <typename CT>
+__device__ __forceinline__ void bump(uint32_t *tab32, uint32_t lb, uint32_t *s_flag) {
+    if constexpr (sizeof(CT) == 1) {
+        const uint32_t bsh = (lb & 3u) * 8u;
+        const uint32_t old = atomicAdd(&tab32[lb >> 2], 1u << bsh);
+        if (((old >> bsh) & 0xffu) == 0xffu) *s_flag = 1;   // 255 -> 256 carried into the neighbour: redo on path B
+    } else {
+        atomicAdd(&tab32[lb], 1u);
+    }
+}
+
 template <typename CT, typename OUT>
 __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__restrict__ planes,
                                                              const uint64_t *__restrict__ base_start,
@@ -99,18 +112,25 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
     __shared__ uint32_t s_seq;
     __shared__ uint32_t s_flag;
     __shared__ unsigned long long s_red[A_THREADS / 32];
+    // quotient of every possible uint8 count for the current sequence: the (slow, exact) double
+    // division runs 256 times per sequence instead of 4^k times
+    __shared__ OUT s_lut[256];
+    constexpr bool IS_FREQ = !std::is_integral<OUT>::value;
 
     const uint32_t bins = 1u << (2 * k);
     const uint32_t tile_bins = bins < TILE_BINS ? bins : TILE_BINS;
     const uint32_t n_tiles = bins / tile_bins;
-    const uint32_t tile_words = tile_bins * sizeof(CT) / 4;   // >= 1 (k=1,u8: 4 bins = 1 word)
-    const uint32_t mask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+    const uint32_t tile_words = tile_bins * sizeof(CT) / 4;   // >= 1
+    const uint32_t mask = (1u << k) - 1u;                      // k <= 15 here
+    // tile index of a bin = its top bits = top bits of y:  bin >> 15 == y >> ysh
+    const uint32_t ysh = n_tiles > 1 ? (uint32_t)(TILE_BINS_LOG2 - k) : (uint32_t)k;
+    const uint32_t ylow = (1u << ysh) - 1u;
     constexpr int BPS = 16 / (int)sizeof(OUT);                // bins per 16-byte store
 
     for (uint32_t i = threadIdx.x; i < tile_words; i += A_THREADS) tab32[i] = 0;
 
     for (;;) {
-        __syncthreads();   // table is clear; previous s_seq/s_flag consumed
+        __syncthreads();   // table is clear; previous s_seq/s_flag/s_lut consumed
         if (threadIdx.x == 0) {
             s_seq = atomicAdd(queue, 1u);
             s_flag = 0;
@@ -131,60 +151,53 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
             continue;
         }
 
-        // groups of 8 flat positions covering [p0 + k-1, p0 + n): full k-mers only
-        const uint64_t pf = q.p0 + (uint64_t)(k - 1);   // first flat position with a full window
+        // groups of 8 flat positions covering the full k-mers, i.e. flat positions [pf, pe)
+        const uint64_t pf = q.p0 + (uint64_t)(k - 1);
         const uint64_t pe = q.p0 + q.n;
         const bool has_full = q.n >= (uint64_t)k;
-        const uint64_t g0 = pf >> 3, g1 = has_full ? ((pe - 1) >> 3) + 1 : g0;   // group range
-        const uint64_t emit_from = q.p0 + (q.lead > (uint32_t)(k - 1) ? q.lead : (uint32_t)(k - 1));
-        // Σ counts = number of emitting bases (no wrap possible on this path: counts <= 255 or n < 2^32)
-        const uint64_t total = q.n > q.lead ? q.n - q.lead : 0;
-        double sum = (double)total;
+        const uint64_t g0 = pf >> 3, g1 = has_full ? ((pe - 1) >> 3) + 1 : g0;
+        // sum of the counts = number of emitting bases (no wrap on this path unless handled below)
+        double sum = (double)(q.n > q.lead ? q.n - q.lead : 0);
+        if constexpr (IS_FREQ && sizeof(CT) == 1) {
+            s_lut[threadIdx.x] = convert_count<OUT>(threadIdx.x, 0.0, sum);   // A_THREADS == 256
+        }
 
         for (uint32_t t = 0; t < n_tiles; ++t) {
             for (uint64_t g = g0 + threadIdx.x; g < g1; g += A_THREADS) {
                 const uint64_t W = g >> 2;                  // word holding the group
                 const uint2 hi = __ldg(planes + W);
                 const uint2 lo = W ? __ldg(planes + W - 1) : make_uint2(0, 0);
-                const unsigned long long vx = ((unsigned long long)hi.x << 32) | lo.x;
-                const unsigned long long vy = ((unsigned long long)hi.y << 32) | lo.y;
+                // bits [8g-(k-1), 8g+8) of each plane, i.e. the 8 windows of this group
+                const uint32_t sh0 = 8u * (uint32_t)(g & 3) + 32u - (uint32_t)(k - 1);
+                const uint32_t gx = (uint32_t)((((unsigned long long)hi.x << 32) | lo.x) >> sh0);
+                const uint32_t gy = (uint32_t)((((unsigned long long)hi.y << 32) | lo.y) >> sh0);
+                // which of the 8 positions are inside [pf, pe)
                 const uint64_t pbase = g << 3;
+                uint32_t m = 0xffu;
+                if (pbase < pf) m &= 0xffu << (uint32_t)(pf - pbase);
+                if (pbase + 8 > pe) m &= 0xffu >> (uint32_t)(pbase + 8 - pe);
 #pragma unroll
                 for (int b = 0; b < 8; ++b) {
-                    const uint64_t p = pbase + b;
-                    if (p < emit_from || p >= pe) continue;
-                    // window start p-k+1 relative to bit 0 of word W-1
-                    const uint32_t sh = (uint32_t)(p - (uint64_t)(k - 1) + 32 - (W << 5));
-                    const uint32_t bin = kmer_bin(vx, vy, sh, k, mask);
-                    if ((bin >> TILE_BINS_LOG2) != t && n_tiles > 1) continue;
-                    const uint32_t lb = bin & (tile_bins - 1);
-                    if constexpr (sizeof(CT) == 1) {
-                        const uint32_t bsh = (lb & 3u) * 8u;
-                        const uint32_t old = atomicAdd(&tab32[lb >> 2], 1u << bsh);
-                        if (((old >> bsh) & 0xffu) == 0xffu) s_flag = 1;
-                    } else {
-                        atomicAdd(&tab32[lb], 1u);
+                    const uint32_t yw = (gy >> b) & mask;
+                    if ((m >> b) & 1u) {
+                        if (n_tiles == 1 || (yw >> ysh) == t) {
+                            const uint32_t xw = (gx >> b) & mask;
+                            bump<CT>(tab32, ((yw & ylow) << k) | xw, &s_flag);
+                        }
                     }
                 }
             }
             if (threadIdx.x == 0 && q.lead < (uint32_t)(k - 1)) {   // dirty head (rare)
                 head_partials(planes, q, k, [&](uint32_t bin) {
-                    if ((bin >> TILE_BINS_LOG2) != t && n_tiles > 1) return;
-                    const uint32_t lb = bin & (tile_bins - 1);
-                    if constexpr (sizeof(CT) == 1) {
-                        const uint32_t bsh = (lb & 3u) * 8u;
-                        const uint32_t old = atomicAdd(&tab32[lb >> 2], 1u << bsh);
-                        if (((old >> bsh) & 0xffu) == 0xffu) s_flag = 1;
-                    } else {
-                        atomicAdd(&tab32[lb], 1u);
-                    }
+                    if (n_tiles > 1 && (bin >> TILE_BINS_LOG2) != t) return;
+                    bump<CT>(tab32, bin & (tile_bins - 1), &s_flag);
                 });
             }
             __syncthreads();
 
             if constexpr (sizeof(CT) == 4) {
                 // frequencies of 16-bit counts that wrapped: the divisor is the sum of the WRAPPED values
-                if (t == 0 && !std::is_integral<OUT>::value && count_bits == 16 && q.n > 65535) {
+                if (t == 0 && IS_FREQ && count_bits == 16 && q.n > 65535) {
                     unsigned long long part = 0;
                     for (uint32_t i = threadIdx.x; i < tile_bins; i += A_THREADS) part += tab32[i] & 0xffffu;
                     part = warp_sum64(part);
@@ -204,41 +217,49 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
             if (vec_ok) {
                 const uint32_t n_stores = tile_bins / BPS;
                 for (uint32_t c = threadIdx.x; c < n_stores; c += A_THREADS) {
-                    uint32_t cnt[BPS];
-                    if constexpr (sizeof(CT) == 1) {
-                        if constexpr (BPS == 8) {
-                            uint2 w = *reinterpret_cast<uint2 *>(&tab32[c * 2]);
-                            *reinterpret_cast<uint2 *>(&tab32[c * 2]) = make_uint2(0, 0);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                cnt[i] = (w.x >> (8 * i)) & 0xffu;
-                                cnt[4 + i] = (w.y >> (8 * i)) & 0xffu;
-                            }
-                        } else if constexpr (BPS == 4) {
-                            const uint32_t w = tab32[c];
-                            tab32[c] = 0;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) cnt[i] = (w >> (8 * i)) & 0xffu;
-                        } else {   // BPS == 2
-                            unsigned short *t16 = reinterpret_cast<unsigned short *>(tab32);
-                            const uint32_t w = t16[c];
-                            t16[c] = 0;
-                            cnt[0] = w & 0xffu;
-                            cnt[1] = w >> 8;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < BPS; ++i) {
-                            cnt[i] = tab32[c * BPS + i] & wrapmask;
-                            tab32[c * BPS + i] = 0;
-                        }
-                    }
                     union {
                         uint4 v;
                         OUT e[BPS];
                     } u;
+                    if constexpr (sizeof(CT) == 1) {
+                        // BPS uint8 counters = BPS/4 words (BPS==2: half a word)
+                        uint32_t w0 = 0, w1 = 0;
+                        if constexpr (BPS == 8) {
+                            const uint2 w = *reinterpret_cast<uint2 *>(&tab32[c * 2]);
+                            w0 = w.x, w1 = w.y;
+                            if (w0 | w1) *reinterpret_cast<uint2 *>(&tab32[c * 2]) = make_uint2(0, 0);
+                        } else if constexpr (BPS == 4) {
+                            w0 = tab32[c];
+                            if (w0) tab32[c] = 0;
+                        } else {
+                            unsigned short *t16 = reinterpret_cast<unsigned short *>(tab32);
+                            w0 = t16[c];
+                            if (w0) t16[c] = 0;
+                        }
+                        if ((w0 | w1) == 0) {               // >96% of the bins of a 9 kb genome at k=9
+                            if constexpr (IS_FREQ) {
+                                const OUT z = s_lut[0];     // 0/sum: 0, or NaN when the sequence emits nothing
 #pragma unroll
-                    for (int i = 0; i < BPS; ++i) u.e[i] = convert_count<OUT>(cnt[i], 0.0, sum);
+                                for (int i = 0; i < BPS; ++i) u.e[i] = z;
+                            } else {
+                                u.v = make_uint4(0, 0, 0, 0);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BPS; ++i) {
+                                const uint32_t cnt = ((i < 4 ? w0 : w1) >> (8 * (i & 3))) & 0xffu;
+                                if constexpr (IS_FREQ) u.e[i] = s_lut[cnt];
+                                else u.e[i] = (OUT)cnt;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BPS; ++i) {
+                            const uint32_t cnt = tab32[c * BPS + i] & wrapmask;
+                            tab32[c * BPS + i] = 0;
+                            u.e[i] = convert_count<OUT>(cnt, 0.0, sum);
+                        }
+                    }
                     st_stream16(trow + (uint64_t)c * BPS, u.v);
                 }
             } else {   // tiny or misaligned rows (k=1 with 16-bit counts)

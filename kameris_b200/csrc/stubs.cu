@@ -7,11 +7,6 @@
     return KAM_E_UNSUPPORTED;
 
 extern "C" {
-int kam_manhattan_tri(const void *, int, uint32_t, uint64_t, uint64_t, uint32_t, uint32_t, uint32_t *, void *) { KAM_STUB(kam_manhattan_tri) }
-int kam_manhattan_rect(const void *, const void *, int, uint32_t, uint32_t, uint64_t, uint64_t, uint64_t, uint32_t *, void *) { KAM_STUB(kam_manhattan_rect) }
-int kam_manhattan_rect_f32(const void *, int, const float *, uint32_t, uint32_t, uint64_t, uint64_t, uint64_t, float *, void *) { KAM_STUB(kam_manhattan_rect_f32) }
-size_t kam_info_workspace_bytes(uint32_t, uint64_t) { return 0; }
-int kam_info_tri(const void *, int, uint32_t, uint64_t, uint64_t, uint32_t, uint32_t, float *, void *, size_t, void *) { KAM_STUB(kam_info_tri) }
 size_t kam_gram_workspace_bytes(uint32_t, uint64_t) { return 0; }
 int kam_gram_tri(const void *, int, uint32_t, uint64_t, uint64_t, uint32_t, uint32_t, unsigned, int, float *, float *, float *, void *, size_t, void *) { KAM_STUB(kam_gram_tri) }
 int kam_dists_host(const void *, int, uint32_t, uint64_t, unsigned, uint32_t *, float *, float *, float *, float *) { KAM_STUB(kam_dists_host) }

@@ -1,0 +1,114 @@
+"""GPU parity of the distance kernels (through the C ABI) vs the oracle: `manhat` and `info`
+bit-exact (uint32 / float32 as the reference computes them), euclid/cosine/pearson within 1e-5
+relative of scipy float64 (north_star tolerance)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import HIV_P, synth_records
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def D():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from kameris_b200 import dist as D
+    return D
+
+
+def _dev(a):
+    """numpy (any of the six element types) -> cuda tensor with the same bits."""
+    view = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64}
+    tdt = {np.dtype(np.uint16): torch.uint16, np.dtype(np.uint32): torch.uint32, np.dtype(np.uint64): torch.uint64}
+    if a.dtype in view:
+        return torch.from_numpy(a.view(view[a.dtype])).cuda().view(tdt[a.dtype])
+    return torch.from_numpy(a).cuda()
+
+
+def _counts(n, L, k, seed, bits=16):
+    recs = synth_records(n, L, seed=seed, p=HIV_P, jitter=L // 10)
+    return np.stack([O.cgr_count(r, k, bits) for r in recs])
+
+
+def test_demo_k6_appendix_b(D, demo_records):
+    x = np.stack([O.cgr_count(r, 6) for _, r in demo_records])
+    man = D.manhattan_tri(_dev(x)).cpu().numpy().view(np.uint32)
+    inf = D.info_tri(_dev(x)).cpu().numpy()
+    assert man.tolist() == [3904, 4791, 4369, 4773, 4455, 4628]
+    ref_m, ref_i = O.dists_triangle(x, True, True)
+    assert np.array_equal(man, ref_m) and np.array_equal(inf, ref_i)
+
+
+@pytest.mark.parametrize("n,L,k", [(2, 500, 3), (37, 3000, 5), (130, 9000, 6), (300, 2000, 4), (129, 1000, 7)])
+def test_manhat_info_vs_oracle_bytes_path(D, n, L, k):
+    x = _counts(n, L, k, seed=n + k)                 # counts <= 255: VABSDIFF4 byte path
+    ref_m, ref_i = O.dists_triangle(x, True, True)
+    assert np.array_equal(D.manhattan_tri(_dev(x)).cpu().numpy().view(np.uint32), ref_m)
+    assert np.array_equal(D.info_tri(_dev(x)).cpu().numpy(), ref_i)
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint32, np.uint8])
+def test_manhat_wide_counts(D, dtype):
+    rng = np.random.Generator(np.random.PCG64(5))
+    hi = {np.uint8: 256, np.uint16: 65536, np.uint32: 2 ** 32}[dtype]
+    x = rng.integers(0, hi, size=(70, 1000), dtype=np.uint64).astype(dtype)
+    x[3] = 0
+    ref_m, ref_i = O.dists_triangle(x, True, True)
+    assert np.array_equal(D.manhattan_tri(_dev(x)).cpu().numpy().view(np.uint32), ref_m)   # wraps mod 2^32
+    assert np.array_equal(D.info_tri(_dev(x)).cpu().numpy(), ref_i)
+
+
+@pytest.mark.parametrize("dtype", [np.uint64, np.float32, np.float64])
+def test_manhat_other_element_types_quirk_q5(D, dtype):
+    rng = np.random.Generator(np.random.PCG64(6))
+    if dtype == np.uint64:
+        x = rng.integers(0, 2 ** 40, size=(9, 77), dtype=np.uint64)
+    else:
+        x = (rng.random((9, 77)) * 3.0).astype(dtype)      # |a-b| mostly < 1: truncating accumulate (Q5)
+        x[0] = 0
+    ref_m, ref_i = O.dists_triangle(x, True, True)
+    assert np.array_equal(D.manhattan_tri(_dev(x)).cpu().numpy().view(np.uint32), ref_m)
+    assert np.array_equal(D.info_tri(_dev(x)).cpu().numpy(), ref_i)
+    f = np.stack([O.frequencies(r) for r in _counts(5, 800, 3, seed=1)])
+    assert not D.manhattan_tri(_dev(f)).cpu().numpy().any()            # frequencies -> all zeros
+
+
+def test_row_ranges_compose(D):
+    x = _counts(200, 1500, 5, seed=9)
+    xd = _dev(x)
+    full = D.manhattan_tri(xd).cpu().numpy()
+    out = torch.zeros(D.tri_len(200), dtype=torch.int32, device="cuda")
+    ranges = D.balanced_row_ranges(200, 3)
+    assert ranges[0][0] == 0 and ranges[-1][1] == 200
+    for r in ranges:
+        D.manhattan_tri(xd, rows=r, out=out)
+    assert np.array_equal(out.cpu().numpy(), full)
+
+
+def test_manhat_rect(D):
+    x = _counts(300, 150, 6, seed=20261004)
+    y = _counts(20, 150, 6, seed=3)
+    got = D.manhattan_rect(_dev(x), _dev(y)).cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, O.manhat_rect(x, y))
+    cent = np.stack([x[i::20].mean(axis=0) for i in range(20)]).astype(np.float32)       # centroids
+    gotf = D.manhattan_rect(_dev(x), torch.from_numpy(cent).cuda()).cpu().numpy()
+    ref = O.cdist_rect(x, cent, "cityblock")
+    np.testing.assert_allclose(gotf, ref, rtol=1e-5)
+
+
+def test_symmetry_and_full_size_property(D):
+    """N=1500, D=4^6: triangle equals the mirrored rectangular result; zero self-distance."""
+    x = _counts(1500, 400, 6, seed=77)
+    xd = _dev(x)
+    tri = D.manhattan_tri(xd).cpu().numpy().view(np.uint32)
+    rect = D.manhattan_rect(xd, xd).cpu().numpy().view(np.uint32)
+    assert (np.diag(rect) == 0).all() and np.array_equal(rect, rect.T)
+    iu = np.triu_indices(1500, 1)
+    assert np.array_equal(rect[iu], tri)
+    rng = np.random.Generator(np.random.PCG64(2))
+    for _ in range(200):
+        i, j = sorted(rng.choice(1500, 2, replace=False))
+        assert tri[O.triangle_index(1500, i, j)] == O.manhat(x[i], x[j])
