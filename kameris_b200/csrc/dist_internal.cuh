@@ -1,0 +1,36 @@
+// dist_internal.cuh -- shared between gram.cu (tensor-core Gram) and dist_tile.cu (exact integer
+// Gram on the CUDA cores): per-row constants and the float64 epilogue of the Gram metrics.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// per-row constants derived from S = sum of the row and G = sum of squares (exact integers)
+struct RowK {
+    double rn;   // 1/sqrt(G)                       (cosine)
+    double S;    // S
+    double mu;   // S/D
+    double rp;   // 1/sqrt(G - S^2/D)               (pearson)
+    double a;    // G (counts) or G/S^2 (frequencies)   (euclid)
+    double q;    // 1 (counts) or 1/S   (frequencies)
+};
+
+struct GramOut {
+    float *euclid, *cosine, *pearson;   // packed triangles; nullptr = not requested
+};
+
+#ifdef __CUDACC__
+// g = exact G_ij.  Definitions: scipy.spatial.distance {euclidean, cosine, correlation}.
+__device__ __forceinline__ void gram_store(const GramOut &go, long long idx, double g, const RowK &ri, const RowK &cj) {
+    if (go.cosine) go.cosine[idx] = (float)(1.0 - g * ri.rn * cj.rn);
+    if (go.pearson) go.pearson[idx] = (float)(1.0 - (g - ri.S * cj.mu) * ri.rp * cj.rp);
+    if (go.euclid) {
+        const double e2 = ri.a + cj.a - 2.0 * g * ri.q * cj.q;
+        go.euclid[idx] = sqrtf((float)(e2 > 0.0 ? e2 : 0.0));
+    }
+}
+#endif
+
+size_t kam_int_gram_xt_bytes(uint32_t n, uint64_t d);
+int kam_int_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,
+                     uint32_t row_end, const RowK *rk, GramOut go, uint32_t *xt, cudaStream_t st);

@@ -16,11 +16,12 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "dist_internal.cuh"
 #include "tma.cuh"
 
 namespace {
 
-enum { OP_SAD32 = 0, OP_SAD8X4 = 1, OP_JACC = 2, OP_L1F32 = 3 };
+enum { OP_SAD32 = 0, OP_SAD8X4 = 1, OP_JACC = 2, OP_L1F32 = 3, OP_DOT = 4 };
 
 constexpr int DT_THREADS = 256;
 constexpr int TN = 128;
@@ -29,9 +30,10 @@ constexpr int STAGES = 4;
 
 template <int OP>
 struct OpT {
-    static constexpr int RM = (OP == OP_JACC) ? 4 : 8;
+    static constexpr int RM = (OP == OP_JACC || OP == OP_DOT) ? 4 : 8;
     static constexpr int NACC = (OP == OP_JACC) ? 2 : 1;
-    using acc_t = typename std::conditional<OP == OP_L1F32, float, uint32_t>::type;
+    using acc_t = typename std::conditional<OP == OP_L1F32, float,
+                  typename std::conditional<OP == OP_DOT, unsigned long long, uint32_t>::type>::type;
     using out_t = typename std::conditional<OP == OP_JACC || OP == OP_L1F32, float, uint32_t>::type;
 };
 
@@ -42,7 +44,8 @@ __device__ __forceinline__ void pair_op(typename OpT<OP>::acc_t *acc, uint32_t a
     else if constexpr (OP == OP_JACC) {
         acc[0] += __popc(a | b);   // union
         acc[1] += __popc(a ^ b);   // union - intersection
-    } else acc[0] += fabsf(__uint_as_float(a) - __uint_as_float(b));
+    } else if constexpr (OP == OP_DOT) acc[0] += (unsigned long long)a * b;   // IMAD.WIDE.U32: exact integer Gram
+    else acc[0] += fabsf(__uint_as_float(a) - __uint_as_float(b));
 }
 
 // packed-triangle offset of row i: index(i, j) = tri_base(i) + j
@@ -54,7 +57,8 @@ __global__ void __launch_bounds__(DT_THREADS) pair_tile_kernel(const __grid_cons
                                                                uint32_t kw_total, uint32_t n_rows, uint32_t n_cols,
                                                                uint32_t row_begin, uint32_t row_end,
                                                                uint32_t tile_row0,
-                                                               typename OpT<OP>::out_t *__restrict__ out) {
+                                                               typename OpT<OP>::out_t *__restrict__ out,
+                                                               const RowK *__restrict__ rowk, GramOut go) {
     constexpr int RM = OpT<OP>::RM, NACC = OpT<OP>::NACC, TM = 16 * RM;
     using acc_t = typename OpT<OP>::acc_t;
     extern __shared__ unsigned char smem_raw[];
@@ -134,7 +138,9 @@ __global__ void __launch_bounds__(DT_THREADS) pair_tile_kernel(const __grid_cons
         for (int j = 0; j < 8; ++j) {
             const uint32_t c = c0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
             if (c >= n_cols || (TRI && c <= r)) continue;
-            if constexpr (OP == OP_JACC) {
+            if constexpr (OP == OP_DOT) {
+                gram_store(go, base + c, (double)acc[i][j][0], rowk[r], rowk[c]);
+            } else if constexpr (OP == OP_JACC) {
                 // generation_dists @0x10001bc13: U==0 ? 0 : (1.0f/(float)U) * (float)(U-I), single precision
                 const uint32_t U = acc[i][j][0], X = acc[i][j][1];
                 out[base + c] = U == 0 ? 0.0f : __fmul_rn(__fdiv_rn(1.0f, (float)U), (float)X);
@@ -165,6 +171,8 @@ __device__ __forceinline__ uint32_t make_word(const T *__restrict__ row, uint64_
             if (e < d && row[e] > (T)0) w |= 1u << b;
         }
         return w;
+    } else if constexpr (OP == OP_DOT) {
+        return kw < d ? (uint32_t)row[kw] : 0u;
     } else {
         return kw < d ? __float_as_uint((float)row[kw]) : 0u;
     }
@@ -262,7 +270,8 @@ int convert_dispatch(const void *x, int elem, uint32_t n, uint64_t d, uint64_t l
 
 template <int OP, bool TRI>
 int launch_pairs(const uint32_t *at, uint32_t n_rows, const uint32_t *bt, uint32_t n_cols, uint32_t kw,
-                 uint32_t row_begin, uint32_t row_end, void *out, cudaStream_t st) {
+                 uint32_t row_begin, uint32_t row_end, void *out, cudaStream_t st, const RowK *rowk = nullptr,
+                 GramOut go = GramOut{nullptr, nullptr, nullptr}) {
     constexpr int TM = 16 * OpT<OP>::RM;
     CUtensorMap tmA, tmB;
     const uint32_t npa = pad4(n_rows), npb = pad4(n_cols);
@@ -280,7 +289,7 @@ int launch_pairs(const uint32_t *at, uint32_t n_rows, const uint32_t *bt, uint32
     const uint32_t t0 = row_begin / TM, t1 = (row_end - 1) / TM + 1;
     dim3 grid((n_cols + TN - 1) / TN, t1 - t0);
     kern<<<grid, DT_THREADS, smem, st>>>(tmA, tmB, kw, n_rows, n_cols, row_begin, row_end, t0,
-                                         (typename OpT<OP>::out_t *)out);
+                                         (typename OpT<OP>::out_t *)out, rowk, go);
     KAM_CUDA(cudaGetLastError());
     return KAM_OK;
 }
@@ -302,6 +311,16 @@ int max_of(const void *x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_
 }
 
 }  // namespace
+
+// exact integer Gram metrics for inputs outside the fp16/fp32-exact envelope of gram.cu
+size_t kam_int_gram_xt_bytes(uint32_t n, uint64_t d) { return xt_bytes(n, kw_of(OP_DOT, d)); }
+
+int kam_int_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,
+                     uint32_t row_end, const RowK *rk, GramOut go, uint32_t *xt, cudaStream_t st) {
+    int rc = convert_dispatch<OP_DOT>(d_x, elem, n, d, ld, xt, st);
+    if (rc) return rc;
+    return launch_pairs<OP_DOT, true>(xt, n, xt, n, kw_of(OP_DOT, d), row_begin, row_end, nullptr, st, rk, go);
+}
 
 extern "C" {
 

@@ -1,0 +1,418 @@
+// gram.cu -- euclid / cosine / pearson distance triangles from ONE Gram-matrix pass G = X X^T on
+// the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+// These three metrics do not exist in the reference (kameris/schemas/job_options.json:97 lists
+// only manhat and info; usage string of generation_dists @0x100027d20); BASELINE.json's north star
+// adds them.  They are defined as scipy.spatial.distance {euclidean, cosine, correlation}
+//  and derived from the integer Gram matrix of the COUNT vectors:
+//     cosine  = 1 - G_ij / sqrt(G_ii G_jj)
+//     pearson = 1 - (G_ij - S_i S_j / D) / sqrt((G_ii - S_i^2/D)(G_jj - S_j^2/D))
+//     euclid  = sqrt(G_ii + G_jj - 2 G_ij)                      on counts
+//             = sqrt(G_ii/S_i^2 + G_jj/S_j^2 - 2 G_ij/(S_i S_j)) on frequencies x/sum(x)
+// with S_i = sum of row i, D = number of bins.
+//
+// Exactness: counts <= 2048 are exact in fp16 and every partial sum of a Gram entry is a
+// non-negative integer bounded by max_i G_ii; when that bound is < 2^24 the fp32 accumulation in
+// TMEM is EXACT, so G is the exact integer Gram matrix and the only rounding is the float64
+// epilogue + the final float32 store.  Inputs outside that envelope (counts > 2048, or
+// max G_ii >= 2^24) take an exact integer CUDA-core Gram kernel instead (dist_tile.cu, OP_DOT).
+//
+// Kernel (gram_tcgen05_kernel): persistent, one CTA per SM, 192 threads:
+//   warp 0    TMA producer   : 128x64 (A) and 256x64 (B) fp16 boxes, SWIZZLE_128B, 4-stage ring
+//   warp 1    MMA issuer     : tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, fp32 in TMEM,
+//                              two 256-column accumulators so the epilogue of tile t overlaps the
+//                              MMAs of tile t+1; tcgen05.commit releases smem stages / publishes TMEM
+//   warps 2-5 epilogue       : tcgen05.ld 32x32b -> float64 distance formulas -> packed triangle
+// Only tiles that contain a pair i<j are scheduled (upper triangle).
+#include <vector>
+
+#include "common.cuh"
+#include "dist_internal.cuh"
+#include "tma.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int G_STAGES = 4;
+constexpr int G_THREADS = 192;
+constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t MAX_EXACT_COUNT = 2048;           // fp16 holds integers up to 2048 exactly
+constexpr unsigned long long MAX_EXACT_GII = 1ull << 24;   // fp32 holds integers up to 2^24 exactly
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (bits 4-5 = 1), A=B=F16 (0),
+// both K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, SWIZZLE_128B:
+// start>>4 | LBO(16 B)>>4 at bit 16 | SBO(1024 B: next 8-row group)>>4 at bit 32 | version 1 at
+// bit 46 | layout type 2 (SWIZZLE_128B) at bit 61
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                    const uint2 *__restrict__ tiles, uint32_t n_tiles,
+                                                                    uint32_t k_iters, uint32_t n, uint32_t row_begin,
+                                                                    uint32_t row_end, const RowK *__restrict__ rowk,
+                                                                    GramOut go) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B: 1024-B aligned
+    RowK *colk = reinterpret_cast<RowK *>(smem + G_STAGES * STAGE_BYTES);                 // [BN]
+    __shared__ __align__(8) uint64_t full[G_STAGES], empty[G_STAGES], tfull[2], tempty[2];
+    __shared__ uint32_t tmem_holder;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < G_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);   // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {   // TMEM allocation is a warp-wide operation; this warp also frees it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_holder;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const uint2 tile = tiles[t];
+                for (uint32_t kb = 0; kb < k_iters; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+                    unsigned char *sa = smem + stage * STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, (int32_t)(kb * BK), (int32_t)(tile.x * BM), &full[stage]);
+                    tma_load_2d(sa + A_BYTES, &tmB, (int32_t)(kb * BK), (int32_t)(tile.y * BN), &full[stage]);
+                    if (++stage == G_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (uint32_t kb = 0; kb < k_iters; ++kb) {
+                    mbar_wait(&full[stage], phase);        // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t a_desc = umma_desc(sa), b_desc = umma_desc(sa + A_BYTES);
+#pragma unroll
+                    for (uint32_t k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the 128-B swizzle row
+                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty[stage]);            // smem slot free once these MMAs retire
+                    if (++stage == G_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(&tfull[acc]);                  // accumulator complete
+                acc ^= 1u;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps, warp w may touch TMEM lanes [32*(w%4), +32) =====
+        const uint32_t q = (uint32_t)warp & 3u;
+        const uint32_t et = threadIdx.x - 64;              // 0..127
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const uint2 tile = tiles[t];
+            const uint32_t r0 = tile.x * BM, c0 = tile.y * BN;
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's colk fully consumed
+            for (uint32_t c = et; c < (uint32_t)BN; c += 128) {
+                RowK z;
+                z.rn = z.S = z.mu = z.rp = z.a = z.q = 0.0;
+                colk[c] = (c0 + c < n) ? rowk[c0 + c] : z;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t row = r0 + q * 32 + lane;
+            const bool row_ok = row < n && row >= row_begin && row < row_end;
+            RowK ri;
+            ri.rn = ri.S = ri.mu = ri.rp = ri.a = ri.q = 0.0;
+            if (row_ok) ri = rowk[row];
+            const long long base = (long long)n * row - (long long)row * (row + 3) / 2 - 1;
+            for (uint32_t ch = 0; ch < (uint32_t)BN / 32; ++ch) {
+                const uint32_t cb = c0 + ch * 32;
+                if (cb + 31 <= r0 + q * 32) continue;     // whole chunk on or below the diagonal (warp-uniform)
+                uint32_t v[32];
+                tmem_ld32(tmem_base + acc * BN + ch * 32 + ((q * 32) << 16), v);
+                if (row_ok) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const uint32_t j = cb + c;
+                        if (j <= row || j >= n) continue;
+                        const double g = (double)__uint_as_float(v[c]);
+                        const RowK cj = colk[ch * 32 + c];
+                        gram_store(go, base + j, g, ri, cj);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- pre-pass: counts -> fp16 rows (zero-padded to dpad), per-row sum and sum of squares ---------
+template <typename T>
+__global__ void __launch_bounds__(256) gram_convert_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
+                                                           uint64_t dpad, __half *__restrict__ h,
+                                                           unsigned long long *__restrict__ S,
+                                                           unsigned long long *__restrict__ G,
+                                                           unsigned long long *__restrict__ flags) {
+    __shared__ unsigned long long red[3][8];
+    const uint32_t row = blockIdx.x;
+    const T *xr = x + (uint64_t)row * ld;
+    __half *hr = h ? h + (uint64_t)row * dpad : nullptr;
+    unsigned long long s = 0, g = 0, mx = 0;
+    for (uint64_t e = threadIdx.x; e < dpad; e += 256) {
+        const unsigned long long c = e < d ? (unsigned long long)xr[e] : 0ull;
+        s += c;
+        g += c * c;
+        mx = c > mx ? c : mx;
+        if (hr) hr[e] = __uint2half_rn((unsigned)(c > 65504 ? 65504 : c));
+    }
+    s = warp_sum64(s);
+    g = warp_sum64(g);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = t > mx ? t : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s;
+        red[1][threadIdx.x >> 5] = g;
+        red[2][threadIdx.x >> 5] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s = g = mx = 0;
+        for (int w = 0; w < 8; ++w) {
+            s += red[0][w];
+            g += red[1][w];
+            mx = red[2][w] > mx ? red[2][w] : mx;
+        }
+        S[row] = s;
+        G[row] = g;
+        atomicMax(&flags[0], mx);
+        atomicMax(&flags[1], g);
+    }
+}
+
+__global__ void rowk_kernel(const unsigned long long *__restrict__ S, const unsigned long long *__restrict__ G,
+                            uint32_t n, double D, int euclid_on_freq, RowK *__restrict__ rk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double s = (double)S[i], g = (double)G[i];
+    RowK r;
+    r.S = s;
+    r.mu = s / D;
+    r.rn = 1.0 / sqrt(g);
+    r.rp = 1.0 / sqrt(g - s * s / D);
+    if (euclid_on_freq) {
+        r.q = 1.0 / s;
+        r.a = g / (s * s);
+    } else {
+        r.q = 1.0;
+        r.a = g;
+    }
+    rk[i] = r;
+}
+
+struct GramWs {
+    __half *h;
+    unsigned long long *S, *G, *flags;
+    RowK *rk;
+    uint2 *tiles;
+    uint32_t *xt;   // integer fallback operand
+};
+
+inline uint64_t dpad_of(uint64_t d) { return (d + BK - 1) / BK * BK; }
+
+inline size_t max_tiles(uint32_t n) {
+    const size_t tr = (n + BM - 1) / BM, tc = (n + BN - 1) / BN;
+    return tr * tc;
+}
+
+inline size_t gram_layout(uint32_t n, uint64_t d, void *base, GramWs *w) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void *p = base ? (char *)base + off : nullptr;
+        off += kam_align_up(bytes, 1024);
+        return p;
+    };
+    void *flags = take(64);
+    void *S = take((size_t)n * 8), *G = take((size_t)n * 8);
+    void *rk = take((size_t)n * sizeof(RowK));
+    void *tiles = take(max_tiles(n) * sizeof(uint2));
+    // the fp16 matrix and the integer-fallback operand are never live together: share the space
+    const size_t hb = (size_t)n * dpad_of(d) * 2, ib = kam_int_gram_xt_bytes(n, d);
+    void *big = take(hb > ib ? hb : ib);
+    if (w) {
+        w->flags = (unsigned long long *)flags;
+        w->S = (unsigned long long *)S;
+        w->G = (unsigned long long *)G;
+        w->rk = (RowK *)rk;
+        w->tiles = (uint2 *)tiles;
+        w->h = (__half *)big;
+        w->xt = (uint32_t *)big;
+    }
+    return off;
+}
+
+template <typename T>
+int run_convert(const void *x, uint32_t n, uint64_t d, uint64_t ld, const GramWs &w, bool write_h, cudaStream_t st) {
+    gram_convert_kernel<T><<<n, 256, 0, st>>>((const T *)x, n, d, ld, dpad_of(d), write_h ? w.h : nullptr, w.S, w.G,
+                                               w.flags);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t kam_gram_workspace_bytes(uint32_t n, uint64_t d) { return gram_layout(n, d, nullptr, nullptr); }
+
+int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin, uint32_t row_end,
+                 unsigned metrics, int euclid_on_freq, float *d_tri_euclid, float *d_tri_cosine, float *d_tri_pearson,
+                 void *d_ws, size_t ws_bytes, void *stream) {
+    KAM_REQUIRE(d_x && d_ws, "null pointer");
+    KAM_REQUIRE(elem == KAM_U8 || elem == KAM_U16 || elem == KAM_U32, "euclid/cosine/pearson take integer count vectors");
+    KAM_REQUIRE(d >= 1 && d < (1ull << 32) && ld >= d, "bad d / ld");
+    KAM_REQUIRE((metrics & ~(KAM_M_EUCLID | KAM_M_COSINE | KAM_M_PEARSON)) == 0 && metrics != 0, "bad metrics mask");
+    KAM_REQUIRE(!(metrics & KAM_M_EUCLID) || d_tri_euclid, "null euclid output");
+    KAM_REQUIRE(!(metrics & KAM_M_COSINE) || d_tri_cosine, "null cosine output");
+    KAM_REQUIRE(!(metrics & KAM_M_PEARSON) || d_tri_pearson, "null pearson output");
+    if (n < 2 || row_begin >= row_end) return KAM_OK;
+    if (row_end > n) row_end = n;
+    if (ws_bytes < kam_gram_workspace_bytes(n, d)) {
+        kam_set_error("kam_gram_tri: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    GramWs w;
+    gram_layout(n, d, d_ws, &w);
+    GramOut go;
+    go.euclid = (metrics & KAM_M_EUCLID) ? d_tri_euclid : nullptr;
+    go.cosine = (metrics & KAM_M_COSINE) ? d_tri_cosine : nullptr;
+    go.pearson = (metrics & KAM_M_PEARSON) ? d_tri_pearson : nullptr;
+
+    // pass 1: fp16 operand + exact row statistics + the two envelope flags
+    KAM_CUDA(cudaMemsetAsync(w.flags, 0, 64, st));
+    int rc = elem == KAM_U8    ? run_convert<uint8_t>(d_x, n, d, ld, w, true, st)
+             : elem == KAM_U16 ? run_convert<uint16_t>(d_x, n, d, ld, w, true, st)
+                               : run_convert<uint32_t>(d_x, n, d, ld, w, true, st);
+    if (rc) return rc;
+    unsigned long long hflags[2] = {0, 0};
+    KAM_CUDA(cudaMemcpyAsync(hflags, w.flags, 16, cudaMemcpyDeviceToHost, st));
+    KAM_CUDA(cudaStreamSynchronize(st));
+    rowk_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.S, w.G, n, (double)d, euclid_on_freq, w.rk);
+    KAM_CUDA(cudaGetLastError());
+
+    if (hflags[0] > MAX_EXACT_COUNT || hflags[1] >= MAX_EXACT_GII) {
+        // outside the exact fp16/fp32 envelope: exact integer Gram on the CUDA cores
+        return kam_int_gram_tri(d_x, elem, n, d, ld, row_begin, row_end, w.rk, go, w.xt, st);
+    }
+
+    // upper-triangular tile list, strips of 12 tile-rows, column-major inside a strip so that the
+    // ~148 tiles in flight share about a dozen A panels and a dozen B panels in L2
+    std::vector<uint2> tiles;
+    const uint32_t tr0 = row_begin / BM, tr1 = (row_end - 1) / BM + 1, tc = (n + BN - 1) / BN;
+    constexpr uint32_t STRIP = 12;
+    for (uint32_t s0 = tr0; s0 < tr1; s0 += STRIP) {
+        const uint32_t s1 = s0 + STRIP < tr1 ? s0 + STRIP : tr1;
+        for (uint32_t bj = 0; bj < tc; ++bj)
+            for (uint32_t bi = s0; bi < s1; ++bi)
+                if ((uint64_t)bj * BN + BN - 1 > (uint64_t)bi * BM) tiles.push_back(make_uint2(bi, bj));
+    }
+    if (tiles.empty()) return KAM_OK;
+    KAM_CUDA(cudaMemcpyAsync(w.tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    KAM_CUDA(cudaStreamSynchronize(st));   // `tiles` is pageable host memory owned by this frame
+
+    const uint64_t dpad = dpad_of(d);
+    CUtensorMap tmA, tmB;
+    if ((rc = kam_make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w.h, dpad, n, dpad * 2, BK, BM,
+                               CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    if ((rc = kam_make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w.h, dpad, n, dpad * 2, BK, BN,
+                               CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    const size_t smem = (size_t)G_STAGES * STAGE_BYTES + BN * sizeof(RowK) + 1024;
+    KAM_CUDA(cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t grid = (uint32_t)kam_sm_count();
+    if (grid > tiles.size()) grid = (uint32_t)tiles.size();
+    gram_tcgen05_kernel<<<grid, G_THREADS, smem, st>>>(tmA, tmB, w.tiles, (uint32_t)tiles.size(),
+                                                       (uint32_t)(dpad / BK), n, row_begin, row_end, w.rk, go);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+}  // extern "C"

@@ -7,7 +7,5 @@
     return KAM_E_UNSUPPORTED;
 
 extern "C" {
-size_t kam_gram_workspace_bytes(uint32_t, uint64_t) { return 0; }
-int kam_gram_tri(const void *, int, uint32_t, uint64_t, uint64_t, uint32_t, uint32_t, unsigned, int, float *, float *, float *, void *, size_t, void *) { KAM_STUB(kam_gram_tri) }
 int kam_dists_host(const void *, int, uint32_t, uint64_t, unsigned, uint32_t *, float *, float *, float *, float *) { KAM_STUB(kam_dists_host) }
 }

@@ -1,0 +1,159 @@
+"""Drop-in for kameris/job_steps/backend.py: same function names, option keys and error behaviour,
+with the two executables replaced by libkameris_b200.so (no subprocess, no CPU fallback).
+
+    run_backend_kmers(options, exp_options)   backend.py:34-56
+        options: fasta_output_dir, output_file, k, bits_per_element (16|32),
+                 mode ('counts'|'frequencies'), disable_avx (ignored)
+    run_backend_dists(options, exp_options)   backend.py:59-66
+        options: input_file, output_prefix, distances (list), disable_avx (ignored)
+        distances: 'manhat', 'info' (reference) and 'euclid', 'cosine', 'pearson' (new).
+
+Outputs: `.mm-repr` (uint16/uint32 counts, or float64 frequencies shaped 1 x 4^k exactly like the
+numpy rewrite of backend.py:45-56) and `<prefix>-<name>.mm-dist`.  Failures raise
+subprocess.CalledProcessError like _command.py:17-18 so callers see the same exception type.
+"""
+from __future__ import absolute_import, division, unicode_literals
+
+import ctypes
+import logging
+import os
+import subprocess
+import time
+
+import numpy as np
+
+from .. import _lib, formats
+
+REFERENCE_METRICS = ('manhat', 'info')
+GRAM_METRICS = ('euclid', 'cosine', 'pearson')
+
+
+def _log():
+    return logging.getLogger('kameris')
+
+
+def list_input_files(directory):
+    """Every entry of the directory, full paths, byte-wise sorted (generation_cgr @0x1000017c9-
+    0x100001b20: directory_iterator + stable_sort(std::less<std::string>), no regular-file filter)."""
+    paths = [os.path.join(directory, n) for n in os.listdir(directory)]
+    return sorted(paths, key=lambda p: os.fsencode(p))
+
+
+def read_records(paths):
+    """record[0] of every file (A.1).  A file without a record raises (the reference reads
+    begin() of an empty vector there)."""
+    lib = _lib.load()
+    recs = []
+    for p in paths:
+        with open(p, 'rb') as f:
+            data = f.read()
+        out = ctypes.create_string_buffer(max(len(data), 1))
+        n = lib.kam_fasta_record0(data, len(data), out)
+        if n < 0:
+            raise ValueError('no FASTA record in "%s"' % p)
+        recs.append(out.raw[:n])
+    return recs
+
+
+def kmers_from_records(records, k, bits_per_element, mode):
+    """Host records -> (n, 4^k) ndarray through kam_kmers_host: counts (uint16/uint32) or float64
+    frequencies (bit-exact cgr/cgr.sum())."""
+    import torch
+    lib = _lib.load()
+    if not isinstance(k, int) or k < 1 or 2 * k > 64:
+        raise ValueError('k is too large to fit in the index')
+    if bits_per_element not in (16, 32):
+        raise ValueError('bits per element must be 16 or 32')
+    n = len(records)
+    lens = np.fromiter((len(r) for r in records), dtype=np.uint64, count=n)
+    start = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=start[1:])
+    chars = np.frombuffer(b''.join(records), dtype=np.uint8)
+    if mode == 'frequencies':
+        kind, dt = _lib.KAM_OUT_FREQ_F64, torch.float64
+    else:
+        kind, dt = _lib.KAM_OUT_COUNTS, (torch.uint16 if bits_per_element == 16 else torch.uint32)
+    out = torch.empty((n, 4 ** k), dtype=dt)
+    try:
+        out = out.pin_memory()                    # direct DMA target; pageable also works (staged)
+    except RuntimeError:
+        pass
+    _lib.check(lib.kam_kmers_host(chars.ctypes.data if chars.size else None, start.ctypes.data, n, k,
+                                  bits_per_element, kind, out.data_ptr()))
+    np_dt = {torch.float64: np.float64, torch.uint16: np.uint16, torch.uint32: np.uint32}[dt]
+    return np.frombuffer((ctypes.c_char * (out.numel() * out.element_size())).from_address(out.data_ptr()),
+                         dtype=np_dt).reshape(n, 4 ** k), out
+
+
+def run_backend_kmers(options, exp_options):
+    log = _log()
+    t0 = time.time()
+    try:
+        paths = list_input_files(options['fasta_output_dir'])
+        log.info('%d files, using B200 backend', len(paths))
+        records = read_records(paths)
+        vecs, _keep = kmers_from_records(records, options['k'], options['bits_per_element'], options['mode'])
+        k = options['k']
+        example = np.zeros((1, 4 ** k), dtype=vecs.dtype)
+        writer = formats.repr_writer(options['output_file'], example, len(records), create_file=True)
+        writer.write_all(vecs)
+        writer.file.close()
+    except (_lib.KamError, ValueError, OSError) as e:
+        log.error('kmers step failed: %s', e)
+        raise subprocess.CalledProcessError(1, 'generation_cgr (kameris_b200)', str(e))
+    log.info('kmers: %d vectors of %d bins in %.2f seconds', len(records), 4 ** options['k'], time.time() - t0)
+
+
+def requested_metrics(names):
+    """generation_dists substring-searches argv[3] for each metric name (@0x100000f7e, @0x100000fdf);
+    the new names are matched the same way."""
+    joined = ','.join(names)
+    unknown = [n for n in names if n not in REFERENCE_METRICS + GRAM_METRICS]
+    if unknown:
+        raise ValueError('unknown distance(s): %s' % ', '.join(unknown))
+    return [m for m in REFERENCE_METRICS + GRAM_METRICS if m in joined]
+
+
+def dists_from_matrix(x, metrics, euclid_on_freq=False):
+    """(n, d) host matrix -> {metric: packed triangle ndarray} on the GPU."""
+    import torch
+    from .. import dist as D
+    view = {np.dtype(np.uint16): (np.int16, torch.uint16), np.dtype(np.uint32): (np.int32, torch.uint32),
+            np.dtype(np.uint64): (np.int64, torch.uint64)}
+    x = np.ascontiguousarray(x)
+    if x.dtype in view:
+        xd = torch.from_numpy(x.view(view[x.dtype][0])).cuda().view(view[x.dtype][1])
+    else:
+        xd = torch.from_numpy(x).cuda()
+    out = {}
+    if 'manhat' in metrics:
+        out['manhat'] = D.manhattan_tri(xd).cpu().numpy().view(np.uint32)
+    if 'info' in metrics:
+        out['info'] = D.info_tri(xd).cpu().numpy()
+    gram = [m for m in metrics if m in GRAM_METRICS]
+    if gram:
+        if xd.dtype not in (torch.uint8, torch.uint16, torch.uint32):
+            raise ValueError('euclid/cosine/pearson need integer count vectors (mode: counts)')
+        res = D.gram_tri(xd, gram, euclid_on_freq=euclid_on_freq)
+        for m in gram:
+            out[m] = res[m].cpu().numpy()
+    return out
+
+
+def run_backend_dists(options, exp_options):
+    log = _log()
+    t0 = time.time()
+    try:
+        metrics = requested_metrics(options['distances'])
+        with formats.repr_reader(options['input_file']) as reader:
+            x = reader.read_all()                 # raises "Sparse matrices are not supported"
+        n = x.shape[0]
+        res = dists_from_matrix(x, metrics)
+        for m in metrics:
+            w = formats.dist_writer('%s-%s.mm-dist' % (options['output_prefix'], m), res[m].dtype, n)
+            w.write_triangle(res[m])
+            w.close()
+    except (_lib.KamError, ValueError, OSError, TypeError) as e:
+        log.error('distances step failed: %s', e)
+        raise subprocess.CalledProcessError(1, 'generation_dists (kameris_b200)', str(e))
+    log.info('distances: %s over %d vectors in %.2f seconds', ','.join(metrics), n, time.time() - t0)

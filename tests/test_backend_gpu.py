@@ -1,0 +1,99 @@
+"""GPU tests of the drop-in plugin layer: run_backend_kmers / run_backend_dists / CLI shims on the
+bundled demo genomes (BASELINE config 1), checked against the oracle and Appendix B."""
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from kameris_b200 import formats
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def backend():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from kameris_b200.job_steps import backend
+    return backend
+
+
+@pytest.fixture()
+def genomes(tmp_path):
+    d = tmp_path / "fasta"
+    shutil.copytree(os.path.join(ROOT, "tests", "golden", "hiv1-genomes"), str(d))
+    return str(d)
+
+
+@pytest.mark.parametrize("bits", [16, 32])
+def test_kmers_counts_file(backend, genomes, demo_records, tmp_path, bits):
+    out = str(tmp_path / "cgr-counts.mm-repr")
+    backend.run_backend_kmers({"fasta_output_dir": genomes, "output_file": out, "k": 6, "bits_per_element": bits,
+                               "mode": "counts", "disable_avx": True}, {})
+    r = formats.repr_reader(out)
+    assert (r.count, r.rows, r.cols, r.value_type) == (4, 1, 4096, 1 if bits == 16 else 2)
+    for i, (_, rec) in enumerate(demo_records):               # sorted-path order: A1, A6, B, C
+        assert np.array_equal(r.read_matrix(i, flatten=True), O.cgr_count(rec, 6, bits))
+    r.file.close()
+
+
+def test_kmers_frequencies_file_is_float64_like_numpy(backend, genomes, demo_records, tmp_path):
+    out = str(tmp_path / "cgrs.mm-repr")
+    backend.run_backend_kmers({"fasta_output_dir": genomes, "output_file": out, "k": 9, "bits_per_element": 16,
+                               "mode": "frequencies", "disable_avx": False}, {})
+    r = formats.repr_reader(out)
+    assert (r.count, r.rows, r.cols, r.value_type) == (4, 1, 4 ** 9, 5)
+    for i, (_, rec) in enumerate(demo_records):
+        cgr = O.cgr_count(rec, 9, 16).reshape(1, -1)
+        assert np.array_equal(r.read_matrix(i), cgr / cgr.sum())          # backend.py:49, bit for bit
+    r.file.close()
+
+
+def test_dists_files(backend, genomes, tmp_path):
+    rep = str(tmp_path / "cgr-counts.mm-repr")
+    backend.run_backend_kmers({"fasta_output_dir": genomes, "output_file": rep, "k": 6, "bits_per_element": 16,
+                               "mode": "counts", "disable_avx": True}, {})
+    prefix = str(tmp_path / "dists")
+    backend.run_backend_dists({"input_file": rep, "output_prefix": prefix, "distances": ["manhat", "info"],
+                               "disable_avx": True}, {})
+    tri, n = formats.dist_reader.read_triangle(prefix + "-manhat.mm-dist")
+    assert n == 4 and tri.dtype == np.uint32 and tri.tolist() == [3904, 4791, 4369, 4773, 4455, 4628]
+    inf, _ = formats.dist_reader.read_triangle(prefix + "-info.mm-dist")
+    np.testing.assert_allclose(inf, [0.22702530, 0.25923625, 0.25204274, 0.24173106, 0.25185874, 0.24215384],
+                               rtol=2e-7)
+    m = formats.dist_reader.read_matrix(prefix + "-manhat.mm-dist")
+    assert m.shape == (4, 4) and m[1, 0] == 3904
+
+
+def test_errors_raise_called_process_error(backend, tmp_path):
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    (empty / "x.fasta").write_text(">only a header\n\n")
+    with pytest.raises(subprocess.CalledProcessError):
+        backend.run_backend_kmers({"fasta_output_dir": str(empty), "output_file": str(tmp_path / "o"), "k": 4,
+                                   "bits_per_element": 16, "mode": "counts", "disable_avx": True}, {})
+    with pytest.raises(subprocess.CalledProcessError):
+        backend.run_backend_dists({"input_file": str(tmp_path / "missing.mm-repr"), "output_prefix": "p",
+                                   "distances": ["manhat"], "disable_avx": True}, {})
+
+
+def test_cli_shims(genomes, demo_records, tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    out = str(tmp_path / "cli.mm-repr")
+    exe = os.path.join(ROOT, "kameris_b200", "scripts", "generation_cgr")
+    cmd = '"{}" cgr "{}" "{}" {} {}'.format(exe, genomes, out, 5, 16)          # backend.py:36-39 format
+    subprocess.check_call(cmd, shell=True)
+    r = formats.repr_reader(out)
+    assert np.array_equal(r.read_matrix(2, flatten=True), O.cgr_count(demo_records[2][1], 5, 16))
+    r.file.close()
+    exe2 = os.path.join(ROOT, "kameris_b200", "scripts", "generation_dists")
+    subprocess.check_call('"{}" "{}" "{}" {}'.format(exe2, out, str(tmp_path / "c"), "manhat,info"), shell=True)
+    assert os.path.exists(str(tmp_path / "c-manhat.mm-dist")) and os.path.exists(str(tmp_path / "c-info.mm-dist"))
+    assert subprocess.call([sys.executable, "-m", "kameris_b200.cli", "generation_cgr", "cgr"], cwd=ROOT) != 0

@@ -112,3 +112,63 @@ def test_symmetry_and_full_size_property(D):
     for _ in range(200):
         i, j = sorted(rng.choice(1500, 2, replace=False))
         assert tri[O.triangle_index(1500, i, j)] == O.manhat(x[i], x[j])
+
+
+# ---- Gram metrics (euclid / cosine / pearson): tcgen05 tensor-core path -----------------------------
+def _check_gram(D, x, rtol=1e-5):
+    xd = _dev(x)
+    got = D.gram_tri(xd, ("euclid", "cosine", "pearson"), euclid_on_freq=True)
+    f = x / x.sum(axis=1, keepdims=True)
+    np.testing.assert_allclose(got["euclid"].cpu().numpy(), O.cdist_triangle(f, "euclid"), rtol=rtol)
+    np.testing.assert_allclose(got["cosine"].cpu().numpy(), O.cdist_triangle(x, "cosine"), rtol=rtol)
+    np.testing.assert_allclose(got["pearson"].cpu().numpy(), O.cdist_triangle(x, "pearson"), rtol=rtol)
+    got_c = D.gram_tri(xd, ("euclid",), euclid_on_freq=False)
+    np.testing.assert_allclose(got_c["euclid"].cpu().numpy(), O.cdist_triangle(x, "euclid"), rtol=rtol)
+
+
+def test_gram_demo_k6_appendix_b(D, demo_records):
+    x = np.stack([O.cgr_count(r, 6) for _, r in demo_records])
+    got = D.gram_tri(_dev(x), ("euclid", "cosine", "pearson"), euclid_on_freq=True)
+    np.testing.assert_allclose(got["euclid"].cpu().numpy(),
+                               [0.0107171533, 0.0122965513, 0.0118525572, 0.0119359576, 0.0116858869,
+                                0.0116338804], rtol=1e-5)
+    np.testing.assert_allclose(got["cosine"].cpu().numpy(),
+                               [0.0938612871, 0.1247486, 0.114731872, 0.121487558, 0.114964415, 0.115188912],
+                               rtol=1e-5)
+    np.testing.assert_allclose(got["pearson"].cpu().numpy(),
+                               [0.156244013, 0.209079337, 0.190899155, 0.208178386, 0.195207544, 0.197113458],
+                               rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,L,k", [(2, 500, 3), (37, 3000, 5), (130, 9000, 6), (300, 2000, 4), (257, 1000, 7),
+                                   (600, 4000, 6), (40, 9000, 9)])
+def test_gram_vs_scipy(D, n, L, k):
+    _check_gram(D, _counts(n, L, k, seed=100 + n + k))
+
+
+def test_gram_ragged_d_and_u32(D):
+    rng = np.random.Generator(np.random.PCG64(8))
+    x = rng.integers(0, 50, size=(150, 1000)).astype(np.uint32)       # d not a multiple of 64
+    _check_gram(D, x)
+    _check_gram(D, x[:, :4].copy() + 1)                                 # k=1-like: d=4
+
+
+def test_gram_integer_fallback_outside_fp16_envelope(D):
+    """counts > 2048 or sum of squares >= 2^24: exact integer Gram on the CUDA cores."""
+    rng = np.random.Generator(np.random.PCG64(9))
+    x = rng.integers(0, 60000, size=(70, 300)).astype(np.uint16)
+    _check_gram(D, x)
+    x2 = rng.integers(100, 2000, size=(50, 4096)).astype(np.uint16)     # <= 2048 but G_ii ~ 5e9 >= 2^24
+    _check_gram(D, x2)
+
+
+def test_gram_row_ranges_compose(D):
+    x = _counts(500, 1500, 5, seed=19)
+    xd = _dev(x)
+    full = D.gram_tri(xd, ("cosine",))["cosine"].cpu().numpy()
+    acc = np.zeros_like(full)
+    for r in D.balanced_row_ranges(500, 3):
+        part = D.gram_tri(xd, ("cosine",), rows=r)["cosine"].cpu().numpy()
+        assert not (np.logical_and(acc != 0, part != 0)).any()
+        acc += part
+    assert np.array_equal(acc, full)

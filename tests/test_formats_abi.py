@@ -1,0 +1,146 @@
+"""CPU tests: file formats (byte layouts of SURVEY.md A.4/A.5), the C ABI surface, host logic."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from kameris_b200 import formats
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_repr_layout_and_roundtrip(tmp_path):
+    p = str(tmp_path / "a.mm-repr")
+    mats = (np.arange(3 * 16, dtype=np.uint16).reshape(3, 16) * 7)
+    w = formats.repr_writer(p, np.zeros((1, 16), np.uint16), 3, create_file=True)
+    for m in mats:
+        w.write_matrix(m)
+    w.file.close()
+    raw = open(p, "rb").read()
+    # A.4: "MMREPR\0", is_sparse, key_type=3, value_type=1 (u16), count, rows, cols (u64 LE), data at 0x22
+    assert raw[:7] == b"MMREPR\0" and raw[7:10] == bytes([0, 3, 1])
+    assert struct.unpack("<QQQ", raw[10:34]) == (3, 1, 16)
+    assert len(raw) == 34 + 3 * 16 * 2 and raw[34:36] == b"\x00\x00" and raw[36:38] == struct.pack("<H", 7)
+    r = formats.repr_reader(p)
+    assert (r.count, r.rows, r.cols, r.value_type) == (3, 1, 16)[:3] + (1,)
+    assert r.read_matrix(1).shape == (1, 16) and np.array_equal(r.read_matrix(2, flatten=True), mats[2])
+    assert np.array_equal(r.read_all(), mats)
+    r.file.close()
+
+
+def test_repr_float64_rewrite_like_backend(tmp_path):
+    """the frequencies rewrite of backend.py:45-56 through the re-provided API."""
+    p = str(tmp_path / "f.mm-repr")
+    w = formats.repr_writer(p, np.zeros((1, 4), np.uint16), 2)
+    w.write_matrix(np.array([1, 2, 3, 4], np.uint16))
+    w.write_matrix(np.array([0, 0, 5, 5], np.uint16))
+    w.file.close()
+    reader = formats.repr_reader(p)
+    cgrs = []
+    for i in range(reader.count):
+        cgr = reader.read_matrix(i)
+        cgrs.append(cgr / cgr.sum())
+    reader.file.close()
+    writer = formats.repr_writer(p, cgrs[0], len(cgrs), create_file=True)
+    for cgr in cgrs:
+        writer.write_matrix(cgr)
+    writer.file.close()
+    r = formats.repr_reader(p)
+    assert r.value_type == 5 and (r.rows, r.cols) == (1, 4)
+    assert np.array_equal(r.read_matrix(0, flatten=True), np.array([0.1, 0.2, 0.3, 0.4]))
+    r.file.close()
+
+
+def test_sparse_rejected(tmp_path):
+    p = str(tmp_path / "s.mm-repr")
+    open(p, "wb").write(b"MMREPR\0" + bytes([1, 3, 1]) + struct.pack("<QQQ", 1, 1, 4) + b"\0" * 8)
+    with pytest.raises(ValueError, match="Sparse matrices are not supported"):
+        formats.repr_reader(p).read_matrix(0)
+    with pytest.raises(ValueError):
+        open(p, "wb").write(b"garbage")
+        formats.repr_reader(p)
+
+
+def test_dist_layout_and_mirror(tmp_path):
+    p = str(tmp_path / "d-manhat.mm-dist")
+    n = 5
+    tri = np.arange(10, dtype=np.uint32) + 1
+    w = formats.dist_writer(p, np.uint32, n)
+    w.write_triangle(tri)
+    w.close()
+    raw = open(p, "rb").read()
+    assert raw[:7] == b"MMDIST\0" and raw[7] == 2 and struct.unpack("<Q", raw[8:16])[0] == n   # A.5
+    assert len(raw) == 16 + 10 * 4
+    m = formats.dist_reader.read_matrix(p)
+    assert m.shape == (5, 5) and np.array_equal(m, m.T) and (np.diag(m) == 0).all()
+    for i in range(n):
+        for j in range(i + 1, n):
+            assert m[i, j] == tri[formats.triangle_index(n, i, j)]
+    assert formats.triangle_index(n, 0, 1) == 0 and formats.triangle_index(n, 3, 4) == 9
+    w = formats.dist_writer(p, np.float32, 3)
+    w.write_next_row(np.array([0.5, 0.25], np.float32))
+    w.write_next_row(np.array([0.125], np.float32))
+    w.write_next_row(np.array([], np.float32))
+    w.close()
+    t, nn = formats.dist_reader.read_triangle(p)
+    assert nn == 3 and t.dtype == np.float32 and t.tolist() == [0.5, 0.25, 0.125]
+
+
+def test_abi_exports_every_declared_symbol():
+    """The library loads without a GPU and exports exactly what include/kameris_b200.h declares."""
+    from kameris_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "kameris_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(kam_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), "missing export " + name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.kam_version() == 100
+    assert lib.kam_planes_words(64) == 4 and lib.kam_kmer_workspace_bytes(10, 9) > 4 ** 9 * 4
+    assert lib.kam_kmer_workspace_bytes(10, 16) == 0            # k beyond the supported range
+
+
+def test_fasta_record0_host_matches_oracle():
+    from kameris_b200 import _lib
+    from oracle import oracle as O
+    lib = _lib.load()
+    cases = [b">h\nACGT\nAC\n\n>h2\nGG\n", b"  ACG T \r\nNN\r\n", b"\n\n>x\n>y\nTT", b"ACGT", b">a\n\n", b"",
+             b"\t\x0b\x0cAC\x0b\n>b", b">h\r\nAC\r\nGT\r\n\r\nTT\r\n"]
+    for c in cases:
+        out = ctypes.create_string_buffer(max(len(c), 1))
+        n = lib.kam_fasta_record0(c, len(c), out)
+        try:
+            ref = O.fasta_record0(c)
+            assert n == len(ref) and out.raw[:n] == ref
+        except ValueError:
+            assert n == -1
+
+
+def test_requested_metrics_and_row_ranges():
+    from kameris_b200.job_steps import backend
+    assert backend.requested_metrics(["manhat"]) == ["manhat"]
+    assert backend.requested_metrics(["info", "manhat", "pearson"]) == ["manhat", "info", "pearson"]
+    with pytest.raises(ValueError):
+        backend.requested_metrics(["chebyshev"])
+    from kameris_b200 import dist as D
+    for n, parts in [(10, 3), (1000, 8), (7, 8), (100000, 8)]:
+        rr = D.balanced_row_ranges(n, parts)
+        assert rr[0][0] == 0 and rr[-1][1] == n and all(a[1] == b[0] for a, b in zip(rr, rr[1:]))
+        pairs = [sum(n - 1 - i for i in range(a, b)) if n <= 1000 else (b - a) * (2 * n - a - b - 1) // 2
+                 for a, b in rr]
+        assert sum(pairs) == n * (n - 1) // 2
+        if n >= 1000:
+            assert max(pairs) < 1.05 * (sum(pairs) / parts) + n
+
+
+def test_list_input_files_sorted(tmp_path):
+    from kameris_b200.job_steps import backend
+    for n in ["b.fasta", "A1.fasta", "a.fasta", "B.fasta", "10.fasta", "9.fasta"]:
+        (tmp_path / n).write_text(">x\nACGT\n")
+    got = [os.path.basename(p) for p in backend.list_input_files(str(tmp_path))]
+    assert got == ["10.fasta", "9.fasta", "A1.fasta", "B.fasta", "a.fasta", "b.fasta"]   # byte-wise
