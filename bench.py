@@ -8,12 +8,16 @@ frequency vectors (float32, 4^9 bins) -- the configuration "CGR vectors/sec (k=9
 One step = one pass of the `kmers` hot path over the whole batch.
 
   value : vectors/s with the 2-bit planes already resident in HBM (kam_kmer_count only)
-  e2e   : vectors/s through kam_kmers_host with HOST buffers: ASCII records in pinned host memory
-          -> H2D -> pack -> count -> D2H of the float32 vectors into pinned host memory
+  e2e   : vectors/s of the whole `kmers` step in the reference's default mode (frequencies, as in
+          demo/hiv1-lanl.yml) through kam_kmers_host with HOST buffers: ASCII records in pinned
+          host memory -> H2D -> pack -> count -> D2H of float64 frequency vectors (the reference's
+          .mm-repr value type, bit-exact cgr/cgr.sum()) into pinned host memory
   roofline : HBM; algorithmic bytes/vector = ceil(L/4) + 4^k*4 over the CUDA-event
           time of the kam_kmer_count launches, against MEASURED_PEAKS.json
-  cpu_baseline : the oracle's threaded restatement of the reference (`kind: port`; the reference's
-          executables cannot run here) on all host cores, on a bounded sample of the same workload
+  cpu_baseline : the reference `kmers` step (`kind: port`; its executables cannot run here): the
+          oracle's threaded restatement of generation_cgr on all host cores followed by the
+          reference's own single-threaded numpy pass (backend.py:45-49), on a bounded sample.  The
+          all-threads float32 C variant is reported beside it as `threaded_c_f32`.
   distances : secondary lines -- pairs/s of the distance kernels on vectors of the same shape
 
 With --gpus N (torchrun, one rank per GPU) every rank processes its own 10 000-sequence shard
@@ -97,21 +101,43 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(sample_n=None, reps=3):
-    """Threaded oracle (restatement of generation_cgr + the numpy frequency pass) on the host cores."""
+def reference_kmers_step(O, chars, start, n, counts, threads):
+    """The reference `kmers` step, mode=frequencies, minus file I/O: generation_cgr (threaded port,
+    uint16 counts) then the numpy loop of kameris/job_steps/backend.py:45-49 verbatim."""
+    O.lib().orc_cgr_batch(chars.ctypes.data, start.ctypes.data, n, K, 16, counts.ctypes.data, threads)
+    cgrs = []
+    for i in range(n):
+        cgr = counts[i].reshape(1, -1)          # reader.read_matrix(i)
+        cgrs.append(cgr / cgr.sum())
+    return cgrs
+
+
+def cpu_baseline(sample_n=1500, reps=2):
     from oracle import oracle as O
     threads = O.host_threads()
-    n = sample_n or max(64, 250 * threads)        # ~10-30 s of CPU work in total
+    n = sample_n
     chars, start = synth_chars(n, SEQ_LEN, SEED)
-    out = np.zeros((n, BINS), dtype=np.float32)     # pre-touched: no first-touch page faults in the timing
+    counts = np.zeros((n, BINS), dtype=np.uint16)
     best = float("inf")
     for _ in range(reps):
         t0 = time.perf_counter()
-        O.cgr_freq_batch(chars, start, K, 16, f64=False, threads=threads, out=out)
+        reference_kmers_step(O, chars, start, n, counts, threads)
         best = min(best, time.perf_counter() - t0)
+    n2 = max(64, 250 * threads)
+    chars2, start2 = synth_chars(n2, SEQ_LEN, SEED)
+    out = np.zeros((n2, BINS), dtype=np.float32)     # pre-touched
+    best2 = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        O.cgr_freq_batch(chars2, start2, K, 16, f64=False, threads=threads, out=out)
+        best2 = min(best2, time.perf_counter() - t0)
     return {"value": n / best, "unit": "vectors/s", "cores": threads, "kind": "port",
-            "sample": "%d of the %d sequences x %d bp, k=%d, u16 counts + float32 frequencies, best of %d, "
-                      "output buffer pre-touched" % (n, N_SEQS, SEQ_LEN, K, reps)}
+            "sample": "%d of the %d sequences x %d bp, k=%d: threaded uint16 counts (port of generation_cgr, %d "
+                      "threads) + the reference's single-threaded numpy float64 pass (backend.py:45-49), best of %d"
+                      % (n, N_SEQS, SEQ_LEN, K, threads, reps),
+            "threaded_c_f32": {"value": n2 / best2, "unit": "vectors/s",
+                               "what": "counts + float32 normalisation fused in C on all %d threads, output "
+                                       "pre-touched (NOT what the reference does; upper bound for a CPU)" % threads}}
 
 
 def run_reference(args, rank, world):
@@ -120,23 +146,24 @@ def run_reference(args, rank, world):
         return
     from oracle import oracle as O
     threads = O.host_threads()
-    n = max(64, 250 * threads)
+    n = 500
     chars, start = synth_chars(n, SEQ_LEN, SEED)
-    out = np.zeros((n, BINS), dtype=np.float32)
+    counts = np.zeros((n, BINS), dtype=np.uint16)
     for _ in range(args.warmup):
-        O.cgr_freq_batch(chars, start, K, 16, f64=False, threads=threads, out=out)
+        reference_kmers_step(O, chars, start, n, counts, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.cgr_freq_batch(chars, start, K, 16, f64=False, threads=threads, out=out)
+        reference_kmers_step(O, chars, start, n, counts, threads)
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
-    sample = "%d sequences x %d bp per step (bounded sample of the %d-sequence workload)" % (n, SEQ_LEN, N_SEQS)
+    sample = ("%d sequences x %d bp per step (bounded sample of the %d-sequence workload): threaded uint16 counts "
+              "(%d threads) + single-threaded numpy float64 pass (backend.py:45-49)" % (n, SEQ_LEN, N_SEQS, threads))
     print(json.dumps({
         "impl": "reference", "metric": "cgr_vectors_per_sec_k9", "value": v, "unit": "vectors/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic HIV-1-like 10k x 9 kb, k=9 CGR frequency vectors (configs[1])",
-                   "n_seqs_per_step": n, "seq_len": SEQ_LEN, "k": K},
+                   "n_seqs_per_step": n, "seq_len": SEQ_LEN, "k": K, "out": "float64"},
         "cpu_baseline": {"value": v, "unit": "vectors/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -158,7 +185,7 @@ def distance_lines(torch, dev, hbm_peak, tf_peak):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -226,13 +253,17 @@ def main():
     kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     clocks = sampler.stop()
 
-    # ---- e2e: host ASCII -> host float32 vectors through the C ABI --------------------------------------
-    h_out = torch.empty((N_SEQS, BINS), dtype=torch.float32).pin_memory()
+    # ---- e2e: host ASCII -> host float64 frequency vectors through the C ABI ----------------------------
+    # the step's 10 000 vectors (21 GB of float64) return through a reused pinned buffer, SUB rows a call
+    SUB = 2500
+    h_out = torch.empty((SUB, BINS), dtype=torch.float64).pin_memory()
     h_start_u64 = start.astype(np.uint64)
+    sub_starts = [(h_start_u64[i:i + SUB + 1] - h_start_u64[i]).copy() for i in range(0, N_SEQS, SUB)]
 
     def e2e_step():
-        _lib.check(lib.kam_kmers_host(h_chars.data_ptr(), h_start_u64.ctypes.data, N_SEQS, K, 16,
-                                      _lib.KAM_OUT_FREQ_F32, h_out.data_ptr()))
+        for bi, i in enumerate(range(0, N_SEQS, SUB)):
+            _lib.check(lib.kam_kmers_host(h_chars.data_ptr() + int(h_start_u64[i]), sub_starts[bi].ctypes.data,
+                                          min(SUB, N_SEQS - i), K, 16, _lib.KAM_OUT_FREQ_F64, h_out.data_ptr()))
 
     e2e_step()                                   # warm-up: allocates the pipeline's device buffers
     barrier()
@@ -241,8 +272,8 @@ def main():
         e2e_step()
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    chk = float(h_out[N_SEQS // 2].sum())
-    assert abs(chk - 1.0) < 1e-4, "e2e output row does not sum to 1"
+    chk = float(h_out[SUB // 2].sum())
+    assert abs(chk - 1.0) < 1e-9, "e2e output row does not sum to 1"
 
     # ---- max over ranks -----------------------------------------------------------------------------------
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
@@ -265,7 +296,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "synthetic HIV-1-like 10k x 9 kb, k=9 CGR frequency vectors (configs[1])",
-                       "n_seqs_per_gpu": N_SEQS, "seq_len": SEQ_LEN, "k": K, "bins": BINS, "out": "float32",
+                       "n_seqs_per_gpu": N_SEQS, "seq_len": SEQ_LEN, "k": K, "bins": BINS,
+                       "out": "float32 on device for value/roofline (SURVEY.md 8d); e2e returns float64",
                        "l2": "each step writes 10.5 GB of vectors (>> 126 MB L2), nothing is re-read",
                        "parallelism": "sequence shards, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -274,8 +306,9 @@ def main():
                          "peak_source": peak_src},
             "e2e": {"value": world * N_SEQS / e2e_s, "unit": "vectors/s",
                     "h2d_bytes_per_step": int(len(chars) + (N_SEQS + 1) * 8),
-                    "d2h_bytes_per_step": int(N_SEQS * BINS * 4), "ms_per_step": e2e_s * 1e3,
-                    "api": "kam_kmers_host (C ABI, pinned host buffers)"},
+                    "d2h_bytes_per_step": int(N_SEQS * BINS * 8), "ms_per_step": e2e_s * 1e3,
+                    "out": "float64 frequencies, bit-exact cgr/cgr.sum() (the reference's .mm-repr value type)",
+                    "api": "kam_kmers_host (C ABI, pinned host buffers), %d vectors per call" % SUB},
             "gpu_launches": args.steps * 1,
             "clocks": clocks,
             "host": {"cores": len(os.sched_getaffinity(0))},

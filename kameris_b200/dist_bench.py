@@ -1,0 +1,88 @@
+"""Secondary benchmark lines for bench.py: pairs/s of the distance kernels with their rooflines.
+
+  gram      : N=8192 count vectors of D=4^9 (9 kb genomes, k=9): cosine+pearson+euclid from one
+              tcgen05 Gram pass.  Algorithmic flops = 2*D per unique pair; peak =
+              measured bf16 tensor throughput (MEASURED_PEAKS.json).
+  manhattan : BASELINE config 4 shape -- M reads x C=1000 centroids, D=4^6, uint32-exact manhat
+              (byte path, VABSDIFF4) ; bound = CUDA-core issue rate, reported as pair-elements/s.
+"""
+import numpy as np
+
+
+def _time(torch, fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def synth_counts(torch, dev, n, L, k, seed):
+    """count vectors of n synthetic genomes, produced by the repr path itself."""
+    from . import repr as R
+    rng = np.random.Generator(np.random.PCG64(seed))
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+    chars = alpha[rng.choice(4, size=n * L, p=[0.36, 0.18, 0.24, 0.22])]
+    start = np.arange(n + 1, dtype=np.int64) * L
+    d_chars = torch.zeros(len(chars) + 16, dtype=torch.uint8, device=dev)
+    d_chars[:len(chars)] = torch.from_numpy(chars.copy()).to(dev)
+    batch = R.pack_chars(d_chars, torch.from_numpy(start).to(dev), n, len(chars))
+    return R.kmer_vectors(batch, k, 16, "counts")
+
+
+def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
+    from . import _lib
+    from . import dist as D
+    lib = _lib.load()
+    out = {}
+
+    # ---- Gram metrics at k=9 -------------------------------------------------------------------------
+    n, k = n_gram, 9
+    d = 4 ** k
+    x = synth_counts(torch, dev, n, 9000, k, 20261003)
+    pairs = n * (n - 1) // 2
+    tri = {m: torch.empty(pairs, dtype=torch.float32, device=dev) for m in ("euclid", "cosine", "pearson")}
+    ws = torch.empty(lib.kam_gram_workspace_bytes(n, d), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def gram():
+        _lib.check(lib.kam_gram_tri(x.data_ptr(), 1, n, d, x.stride(0), 0, n, 4 | 8 | 16, 1, tri["euclid"].data_ptr(),
+                                    tri["cosine"].data_ptr(), tri["pearson"].data_ptr(), ws.data_ptr(), ws.numel(),
+                                    stream))
+    t = _time(torch, gram, reps)
+    tflops = 2.0 * d * pairs / t / 1e12
+    out["gram"] = {"metric": "distance_pairs_per_sec", "value": pairs / t, "unit": "pairs/s",
+                   "config": {"workload": "N=%d count vectors, D=4^9, euclid+cosine+pearson from one Gram pass" % n,
+                              "includes": "fp16 conversion + row statistics + tile list + tcgen05 kernel"},
+                   "ms": t * 1e3,
+                   "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s",
+                                "frac": tflops / tf_peak, "traffic": None,
+                                "algorithmic_flops_per_pair": 2 * d, "kernel": "gram_tcgen05_kernel"}}
+    del x, tri, ws
+
+    # ---- manhattan, config-4 shape ----------------------------------------------------------------------
+    m, c, k6 = 131072, 1000, 6
+    d6 = 4 ** k6
+    reads = synth_counts(torch, dev, m, 150, k6, 20261004)
+    cent = synth_counts(torch, dev, c, 150, k6, 3)
+    o = torch.empty((m, c), dtype=torch.int32, device=dev)
+    ws = torch.empty(lib.kam_manhattan_workspace_bytes(m, d6) + lib.kam_manhattan_workspace_bytes(c, d6),
+                     dtype=torch.uint8, device=dev)
+
+    def manh():
+        _lib.check(lib.kam_manhattan_rect(reads.data_ptr(), cent.data_ptr(), 1, m, c, d6, reads.stride(0),
+                                          cent.stride(0), o.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    t = _time(torch, manh, reps)
+    lane_peak = 148 * 128 * 1.965e9            # nominal FP32/INT32 lane-ops per second
+    out["manhattan"] = {"metric": "distance_pairs_per_sec", "value": m * c / t, "unit": "pairs/s",
+                        "config": {"workload": "%d reads (150 bp, k=6 counts) x %d centroids, D=4096, uint32 manhat"
+                                               % (m, c), "includes": "operand transposition pre-pass + tile kernel"},
+                        "ms": t * 1e3,
+                        "roofline": {"bound": "cuda-core issue", "achieved": m * c * d6 / t / 1e12,
+                                     "peak": lane_peak / 1e12, "unit": "T pair-elements/s (peak: 1 lane-op each)",
+                                     "frac": m * c * d6 / t / lane_peak, "kernel": "pair_tile_kernel<SAD8X4>"}}
+    return out
