@@ -86,3 +86,17 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
                                      "peak": lane_peak / 1e12, "unit": "T pair-elements/s (peak: 1 lane-op each)",
                                      "frac": m * c * d6 / t / lane_peak, "kernel": "pair_tile_kernel<SAD8X4>"}}
     return out
+
+
+if __name__ == "__main__":
+    import json
+    import os
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    pth = os.path.join(root, "MEASURED_PEAKS.json")
+    if os.path.exists(pth):
+        peaks.update(json.load(open(pth)))
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    print(json.dumps(run(torch, dev, peaks["hbm_gbs"], peaks["bf16_tflops"])))
