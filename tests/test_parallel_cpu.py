@@ -1,0 +1,84 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: sequence sharding, all-gather of the
+feature rows, balanced triangle row blocks, slice offsets, gathering the triangle on rank 0."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from kameris_b200 import parallel
+from kameris_b200.dist import balanced_row_ranges
+
+
+def test_shard_by_bases():
+    rng = np.random.Generator(np.random.PCG64(0))
+    lens = rng.integers(100, 5_000_000, size=1000)
+    for world in (1, 2, 4, 8):
+        sh = parallel.shard_by_bases(lens, world)
+        assert sh[0][0] == 0 and sh[-1][1] == 1000 and all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+        tot = [int(lens[a:b].sum()) for a, b in sh]
+        assert max(tot) - min(tot) <= 2 * lens.max()
+    assert parallel.shard_by_bases([5], 4)[-1] == (1, 1) or parallel.shard_by_bases([5], 4)[0] == (0, 1)
+
+
+def test_tri_row_offset():
+    n = 9
+    k = 0
+    for r in range(n):
+        assert parallel.tri_row_offset(n, r) == k
+        k += n - 1 - r
+    assert parallel.tri_row_offset(n, n) == n * (n - 1) // 2
+
+
+def _host_compute(x_full, metrics, rows, tri_offset, slice_len):
+    """numpy stand-in for the CUDA kernels (plumbing test only)."""
+    from oracle import oracle as O
+    x = x_full.view(torch.int16).numpy().view(np.uint16)
+    man, _ = O.dists_triangle(x, True, False, threads=1)
+    return {"manhat": torch.from_numpy(man[tri_offset:tri_offset + slice_len].view(np.int32).copy())}
+
+
+def _worker(rank, world, port, x_all, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shards = parallel.shard_by_bases([1] * x_all.shape[0], world)     # ragged on purpose below
+        if world == 2:
+            shards = [(0, 5), (5, x_all.shape[0])]
+        b, e = shards[rank]
+        x_local = x_all[b:e].clone()
+        x_full, counts = parallel.all_gather_rows(x_local)
+        assert counts == [s[1] - s[0] for s in shards] and torch.equal(x_full, x_all)
+        slices, (r0, r1), n = parallel.distances_sharded(x_local, ["manhat"], compute=_host_compute)
+        assert (r0, r1) == balanced_row_ranges(n, world)[rank]
+        full = parallel.gather_triangle(slices["manhat"], n)
+        if rank == 0:
+            ret.put(full.numpy().copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distances_sharded_gloo_world2():
+    from oracle import oracle as O
+    rng = np.random.Generator(np.random.PCG64(4))
+    x = rng.integers(0, 300, size=(23, 64)).astype(np.uint16)
+    x_t = torch.from_numpy(x.view(np.int16)).view(torch.uint16)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, x_t, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full = ret.get()
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref, _ = O.dists_triangle(x, True, False)
+    assert np.array_equal(full.view(np.uint32), ref)
