@@ -154,7 +154,8 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                  size_t ws_bytes, void *stream);
 
 /* Host-buffer form of the whole `distances` step: x is the n x d matrix read from a .mm-repr,
- * outputs are packed triangles (NULL = not requested). */
+ * outputs are packed triangles (NULL = not requested).  euclid is taken between the rows as
+ * stored (counts).  Blocking; allocates and frees its device buffers. */
 int kam_dists_host(const void *h_x, int elem, uint32_t n, uint64_t d, unsigned metrics,
                    uint32_t *h_manhat, float *h_info, float *h_euclid, float *h_cosine,
                    float *h_pearson);

@@ -114,29 +114,26 @@ def requested_metrics(names):
     return [m for m in REFERENCE_METRICS + GRAM_METRICS if m in joined]
 
 
-def dists_from_matrix(x, metrics, euclid_on_freq=False):
-    """(n, d) host matrix -> {metric: packed triangle ndarray} on the GPU."""
-    import torch
-    from .. import dist as D
-    view = {np.dtype(np.uint16): (np.int16, torch.uint16), np.dtype(np.uint32): (np.int32, torch.uint32),
-            np.dtype(np.uint64): (np.int64, torch.uint64)}
+def dists_from_matrix(x, metrics):
+    """(n, d) host matrix -> {metric: packed triangle ndarray} through kam_dists_host."""
+    lib = _lib.load()
     x = np.ascontiguousarray(x)
-    if x.dtype in view:
-        xd = torch.from_numpy(x.view(view[x.dtype][0])).cuda().view(view[x.dtype][1])
-    else:
-        xd = torch.from_numpy(x).cuda()
-    out = {}
-    if 'manhat' in metrics:
-        out['manhat'] = D.manhattan_tri(xd).cpu().numpy().view(np.uint32)
-    if 'info' in metrics:
-        out['info'] = D.info_tri(xd).cpu().numpy()
-    gram = [m for m in metrics if m in GRAM_METRICS]
-    if gram:
-        if xd.dtype not in (torch.uint8, torch.uint16, torch.uint32):
-            raise ValueError('euclid/cosine/pearson need integer count vectors (mode: counts)')
-        res = D.gram_tri(xd, gram, euclid_on_freq=euclid_on_freq)
-        for m in gram:
-            out[m] = res[m].cpu().numpy()
+    n, d = x.shape
+    elem = formats.element_type_of(x.dtype)
+    pairs = n * (n - 1) // 2
+    bits = {'manhat': _lib.KAM_M_MANHAT, 'info': _lib.KAM_M_INFO, 'euclid': _lib.KAM_M_EUCLID,
+            'cosine': _lib.KAM_M_COSINE, 'pearson': _lib.KAM_M_PEARSON}
+    out, mask = {}, 0
+    for m in metrics:
+        out[m] = np.zeros(pairs, dtype=np.uint32 if m == 'manhat' else np.float32)
+        mask |= bits[m]
+    if any(m in GRAM_METRICS for m in metrics) and elem > 2:
+        raise ValueError('euclid/cosine/pearson need integer count vectors (mode: counts)')
+
+    def p(m):
+        return out[m].ctypes.data if m in out else None
+    _lib.check(lib.kam_dists_host(x.ctypes.data, elem, n, d, mask, p('manhat'), p('info'), p('euclid'), p('cosine'),
+                                  p('pearson')))
     return out
 
 

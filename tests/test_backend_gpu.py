@@ -97,3 +97,28 @@ def test_cli_shims(genomes, demo_records, tmp_path):
     subprocess.check_call('"{}" "{}" "{}" {}'.format(exe2, out, str(tmp_path / "c"), "manhat,info"), shell=True)
     assert os.path.exists(str(tmp_path / "c-manhat.mm-dist")) and os.path.exists(str(tmp_path / "c-info.mm-dist"))
     assert subprocess.call([sys.executable, "-m", "kameris_b200.cli", "generation_cgr", "cgr"], cwd=ROOT) != 0
+
+
+def test_dists_gram_metrics_files(backend, genomes, tmp_path):
+    """the metrics the north star adds, through the same step function and file format (float32)."""
+    rep = str(tmp_path / "cgr-counts.mm-repr")
+    backend.run_backend_kmers({"fasta_output_dir": genomes, "output_file": rep, "k": 6, "bits_per_element": 16,
+                               "mode": "counts", "disable_avx": True}, {})
+    prefix = str(tmp_path / "g")
+    backend.run_backend_dists({"input_file": rep, "output_prefix": prefix,
+                               "distances": ["cosine", "pearson", "euclid", "manhat"], "disable_avx": True}, {})
+    with formats.repr_reader(rep) as r:
+        x = r.read_all()
+    for m in ("cosine", "pearson", "euclid"):
+        tri, n = formats.dist_reader.read_triangle("%s-%s.mm-dist" % (prefix, m))
+        assert n == 4 and tri.dtype == np.float32
+        np.testing.assert_allclose(tri, O.cdist_triangle(x, m), rtol=1e-5)
+    tri, _ = formats.dist_reader.read_triangle(prefix + "-manhat.mm-dist")
+    assert tri.tolist() == [3904, 4791, 4369, 4773, 4455, 4628]
+    # a frequencies file is rejected for the Gram metrics (integer counts required)
+    frq = str(tmp_path / "f.mm-repr")
+    backend.run_backend_kmers({"fasta_output_dir": genomes, "output_file": frq, "k": 4, "bits_per_element": 16,
+                               "mode": "frequencies", "disable_avx": True}, {})
+    with pytest.raises(subprocess.CalledProcessError):
+        backend.run_backend_dists({"input_file": frq, "output_prefix": prefix, "distances": ["cosine"],
+                                   "disable_avx": True}, {})
