@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
     // tile index of a bin = its top bits = top bits of y:  bin >> 15 == y >> ysh
     const uint32_t ysh = n_tiles > 1 ? (uint32_t)(TILE_BINS_LOG2 - k) : (uint32_t)k;
     const uint32_t ylow = (1u << ysh) - 1u;
+    const uint32_t tbits = n_tiles > 1 ? (uint32_t)(2 * k - TILE_BINS_LOG2) : 0u;   // log2(n_tiles)
     constexpr int BPS = 16 / (int)sizeof(OUT);                // bins per 16-byte store
 
     for (uint32_t i = threadIdx.x; i < tile_words; i += A_THREADS) tab32[i] = 0;
@@ -176,15 +177,18 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
                 uint32_t m = 0xffu;
                 if (pbase < pf) m &= 0xffu << (uint32_t)(pf - pbase);
                 if (pbase + 8 > pe) m &= 0xffu >> (uint32_t)(pbase + 8 - pe);
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const uint32_t yw = (gy >> b) & mask;
-                    if ((m >> b) & 1u) {
-                        if (n_tiles == 1 || (yw >> ysh) == t) {
-                            const uint32_t xw = (gx >> b) & mask;
-                            bump<CT>(tab32, ((yw & ylow) << k) | xw, &s_flag);
-                        }
-                    }
+                // ... and fall into tile t: the tile index is the top `tbits` bits of y, i.e. the y-bits
+                // of the newest `tbits` bases of each k-mer -> one whole-word compare per tile bit
+#pragma unroll 1
+                for (uint32_t i = 0; i < tbits; ++i) {
+                    const uint32_t want = 0u - ((t >> (tbits - 1 - i)) & 1u);        // all-ones / all-zeros
+                    m &= ~((gy >> (uint32_t)(k - 1 - i)) ^ want);
+                }
+                while (m) {                                   // on average one k-mer of the 8 is in the tile
+                    const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                    m &= m - 1u;
+                    const uint32_t yw = (gy >> b) & mask, xw = (gx >> b) & mask;
+                    bump<CT>(tab32, ((yw & ylow) << k) | xw, &s_flag);
                 }
             }
             if (threadIdx.x == 0 && q.lead < (uint32_t)(k - 1)) {   // dirty head (rare)
@@ -222,35 +226,28 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
                         OUT e[BPS];
                     } u;
                     if constexpr (sizeof(CT) == 1) {
-                        // BPS uint8 counters = BPS/4 words (BPS==2: half a word)
+                        // BPS uint8 counters = BPS/4 words (BPS==2: half a word); branch-free
                         uint32_t w0 = 0, w1 = 0;
                         if constexpr (BPS == 8) {
                             const uint2 w = *reinterpret_cast<uint2 *>(&tab32[c * 2]);
                             w0 = w.x, w1 = w.y;
-                            if (w0 | w1) *reinterpret_cast<uint2 *>(&tab32[c * 2]) = make_uint2(0, 0);
+                            *reinterpret_cast<uint2 *>(&tab32[c * 2]) = make_uint2(0, 0);
                         } else if constexpr (BPS == 4) {
                             w0 = tab32[c];
-                            if (w0) tab32[c] = 0;
+                            tab32[c] = 0;
                         } else {
                             unsigned short *t16 = reinterpret_cast<unsigned short *>(tab32);
                             w0 = t16[c];
-                            if (w0) t16[c] = 0;
+                            t16[c] = 0;
                         }
-                        if ((w0 | w1) == 0) {               // >96% of the bins of a 9 kb genome at k=9
-                            if constexpr (IS_FREQ) {
-                                const OUT z = s_lut[0];     // 0/sum: 0, or NaN when the sequence emits nothing
+                        if constexpr (IS_FREQ) {              // >96% of the lanes read s_lut[0]: a broadcast
 #pragma unroll
-                                for (int i = 0; i < BPS; ++i) u.e[i] = z;
-                            } else {
-                                u.v = make_uint4(0, 0, 0, 0);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < BPS; ++i) {
-                                const uint32_t cnt = ((i < 4 ? w0 : w1) >> (8 * (i & 3))) & 0xffu;
-                                if constexpr (IS_FREQ) u.e[i] = s_lut[cnt];
-                                else u.e[i] = (OUT)cnt;
-                            }
+                            for (int i = 0; i < BPS; ++i) u.e[i] = s_lut[((i < 4 ? w0 : w1) >> (8 * (i & 3))) & 0xffu];
+                        } else if constexpr (BPS == 8) {      // uint16 counts: two bytes -> two halfwords per PRMT
+                            u.v = make_uint4(__byte_perm(w0, 0, 0x4140), __byte_perm(w0, 0, 0x4342),
+                                             __byte_perm(w1, 0, 0x4140), __byte_perm(w1, 0, 0x4342));
+                        } else {                              // uint32 counts
+                            u.v = make_uint4(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu, w0 >> 24);
                         }
                     } else {
 #pragma unroll
@@ -423,6 +420,7 @@ int run_kmer(const uint2 *planes, const uint64_t *base_start, const uint32_t *he
                       : launch_tile<uint8_t, OUT>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
                                                    out_stride, w, st);
     if (rc) return rc;
+    if (k <= 6) return KAM_OK;   // uint32 counters, single tile: nothing can spill, no need to look
 
     struct {
         uint32_t queue, count;
