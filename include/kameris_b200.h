@@ -143,11 +143,15 @@ int kam_info_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                  void *stream);
 
 /* Gram-matrix metrics on count vectors (uint16/uint32): G = X X^T on the tcgen05 tensor cores
- * with exact integer-valued fp16 operands and fp32 TMEM accumulation, fused epilogue.
+ * with exact operands: uint8 x uint8 -> int32 (kind::i8) when every count <= 255, integer-valued
+ * fp16 -> fp32 (kind::f16) up to 2048, exact uint64 CUDA-core Gram beyond; fused float64 epilogue.
  * metrics: any of KAM_M_EUCLID|KAM_M_COSINE|KAM_M_PEARSON; d_tri[m] (may be NULL when the metric
  * is not requested) receive float32 triangles.  euclid_on_freq != 0 computes euclidean distance
  * between the frequency vectors x_i/sum(x_i) (what a `frequencies` .mm-repr holds). */
 size_t kam_gram_workspace_bytes(uint32_t n, uint64_t d);
+/* test hook: non-zero forces the fp16 (kind::f16) tensor path where the uint8 (kind::i8) path would
+ * be chosen; both are exact inside their envelopes. */
+void kam_gram_force_f16(int on);
 int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                  uint32_t row_begin, uint32_t row_end, unsigned metrics, int euclid_on_freq,
                  float *d_tri_euclid, float *d_tri_cosine, float *d_tri_pearson, void *d_ws,

@@ -32,17 +32,23 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int BM = 128, BN = 256;
+constexpr int BK_BYTES = 128;                        // one SWIZZLE_128B row of K per stage: 64 fp16 or 128 uint8
 constexpr int G_STAGES = 4;
 constexpr int G_THREADS = 192;
-constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t A_BYTES = BM * BK_BYTES, B_BYTES = BN * BK_BYTES, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t MAX_EXACT_COUNT = 2048;           // fp16 holds integers up to 2048 exactly
-constexpr unsigned long long MAX_EXACT_GII = 1ull << 24;   // fp32 holds integers up to 2^24 exactly
+// exactness envelopes (see the header comment)
+constexpr uint32_t MAX_I8_COUNT = 255;                       // uint8 operands, int32 accumulation
+constexpr unsigned long long MAX_I8_GII = 1ull << 31;
+constexpr uint32_t MAX_F16_COUNT = 2048;                     // fp16 holds integers up to 2048 exactly
+constexpr unsigned long long MAX_F16_GII = 1ull << 24;       // fp32 holds integers up to 2^24 exactly
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (bits 4-5 = 1), A=B=F16 (0),
-// both K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28
-constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format at bits 4-5 (1 = F32, 2 = S32),
+// a/b format at bits 7-9 / 10-12 (kind::f16: 0 = F16; kind::i8: 0 = unsigned 8-bit), both K-major
+// (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28
+constexpr uint32_t IDESC_F16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC_I8 = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, SWIZZLE_128B:
 // start>>4 | LBO(16 B)>>4 at bit 16 | SBO(1024 B: next 8-row group)>>4 at bit 32 | version 1 at
@@ -52,13 +58,24 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
            (2ull << 61);
 }
 
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
-        : "memory");
+// D[tmem] (+)= A[smem] * B[smem]^T : M128 x N256 x K(32 bytes) per instruction, issued by ONE thread
+template <bool I8>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    if constexpr (I8) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC_I8), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC_F16), "r"(accumulate)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -81,6 +98,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <bool I8>
 __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const uint2 *__restrict__ tiles, uint32_t n_tiles,
@@ -129,8 +147,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
                     unsigned char *sa = smem + stage * STAGE_BYTES;
-                    tma_load_2d(sa, &tmA, (int32_t)(kb * BK), (int32_t)(tile.x * BM), &full[stage]);
-                    tma_load_2d(sa + A_BYTES, &tmB, (int32_t)(kb * BK), (int32_t)(tile.y * BN), &full[stage]);
+                    // inner coordinate in elements: 64 fp16 or 128 uint8 per 128-byte row
+                    const int32_t kc = (int32_t)(kb * (I8 ? BK_BYTES : BK_BYTES / 2));
+                    tma_load_2d(sa, &tmA, kc, (int32_t)(tile.x * BM), &full[stage]);
+                    tma_load_2d(sa + A_BYTES, &tmB, kc, (int32_t)(tile.y * BN), &full[stage]);
                     if (++stage == G_STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -152,8 +172,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t a_desc = umma_desc(sa), b_desc = umma_desc(sa + A_BYTES);
 #pragma unroll
-                    for (uint32_t k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the 128-B swizzle row
-                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+                    for (uint32_t k = 0; k < BK_BYTES / 32; ++k)   // +32 B per MMA inside the 128-B swizzle row
+                        umma<I8>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, (kb | k) != 0 ? 1u : 0u);
                     umma_commit(&empty[stage]);            // smem slot free once these MMAs retire
                     if (++stage == G_STAGES) {
                         stage = 0;
@@ -198,7 +218,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
                     for (int c = 0; c < 32; ++c) {
                         const uint32_t j = cb + c;
                         if (j <= row || j >= n) continue;
-                        const double g = (double)__uint_as_float(v[c]);
+                        const double g = I8 ? (double)(int)v[c] : (double)__uint_as_float(v[c]);
                         const RowK cj = colk[ch * 32 + c];
                         gram_store(go, base + j, g, ri, cj);
                     }
@@ -220,24 +240,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
     }
 }
 
-// ---- pre-pass: counts -> fp16 rows (zero-padded to dpad), per-row sum and sum of squares ---------
+// ---- pre-pass 1: exact per-row sum and sum of squares, largest count, largest G_ii --------------
 template <typename T>
-__global__ void __launch_bounds__(256) gram_convert_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
-                                                           uint64_t dpad, __half *__restrict__ h,
-                                                           unsigned long long *__restrict__ S,
-                                                           unsigned long long *__restrict__ G,
-                                                           unsigned long long *__restrict__ flags) {
+__global__ void __launch_bounds__(256) gram_stats_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
+                                                         unsigned long long *__restrict__ S,
+                                                         unsigned long long *__restrict__ G,
+                                                         unsigned long long *__restrict__ flags) {
     __shared__ unsigned long long red[3][8];
     const uint32_t row = blockIdx.x;
     const T *xr = x + (uint64_t)row * ld;
-    __half *hr = h ? h + (uint64_t)row * dpad : nullptr;
     unsigned long long s = 0, g = 0, mx = 0;
-    for (uint64_t e = threadIdx.x; e < dpad; e += 256) {
-        const unsigned long long c = e < d ? (unsigned long long)xr[e] : 0ull;
+    for (uint64_t e = threadIdx.x; e < d; e += 256) {
+        const unsigned long long c = (unsigned long long)xr[e];
         s += c;
         g += c * c;
         mx = c > mx ? c : mx;
-        if (hr) hr[e] = __uint2half_rn((unsigned)(c > 65504 ? 65504 : c));
     }
     s = warp_sum64(s);
     g = warp_sum64(g);
@@ -266,6 +283,20 @@ __global__ void __launch_bounds__(256) gram_convert_kernel(const T *__restrict__
     }
 }
 
+// ---- pre-pass 2: counts -> tensor-core operand rows (uint8 or fp16), zero-padded to dpad ----------
+template <typename T, typename OP>
+__global__ void __launch_bounds__(256) gram_operand_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
+                                                           uint64_t dpad, OP *__restrict__ h) {
+    const uint32_t row = blockIdx.y;
+    const T *xr = x + (uint64_t)row * ld;
+    OP *hr = h + (uint64_t)row * dpad;
+    for (uint64_t e = (uint64_t)blockIdx.x * 256 + threadIdx.x; e < dpad; e += (uint64_t)gridDim.x * 256) {
+        const unsigned c = e < d ? (unsigned)xr[e] : 0u;
+        if constexpr (sizeof(OP) == 1) hr[e] = (OP)c;
+        else hr[e] = __uint2half_rn(c);
+    }
+}
+
 __global__ void rowk_kernel(const unsigned long long *__restrict__ S, const unsigned long long *__restrict__ G,
                             uint32_t n, double D, int euclid_on_freq, RowK *__restrict__ rk) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -286,15 +317,17 @@ __global__ void rowk_kernel(const unsigned long long *__restrict__ S, const unsi
     rk[i] = r;
 }
 
+bool g_force_f16 = false;
+
 struct GramWs {
-    __half *h;
+    void *h;
     unsigned long long *S, *G, *flags;
     RowK *rk;
     uint2 *tiles;
     uint32_t *xt;   // integer fallback operand
 };
 
-inline uint64_t dpad_of(uint64_t d) { return (d + BK - 1) / BK * BK; }
+inline uint64_t dpad_of(uint64_t d) { return (d + BK_BYTES - 1) / BK_BYTES * BK_BYTES; }   // elements (either width)
 
 inline size_t max_tiles(uint32_t n) {
     const size_t tr = (n + BM - 1) / BM, tc = (n + BN - 1) / BN;
@@ -321,16 +354,48 @@ inline size_t gram_layout(uint32_t n, uint64_t d, void *base, GramWs *w) {
         w->G = (unsigned long long *)G;
         w->rk = (RowK *)rk;
         w->tiles = (uint2 *)tiles;
-        w->h = (__half *)big;
+        w->h = big;
         w->xt = (uint32_t *)big;
     }
     return off;
 }
 
 template <typename T>
-int run_convert(const void *x, uint32_t n, uint64_t d, uint64_t ld, const GramWs &w, bool write_h, cudaStream_t st) {
-    gram_convert_kernel<T><<<n, 256, 0, st>>>((const T *)x, n, d, ld, dpad_of(d), write_h ? w.h : nullptr, w.S, w.G,
-                                               w.flags);
+int run_stats(const void *x, uint32_t n, uint64_t d, uint64_t ld, const GramWs &w, cudaStream_t st) {
+    gram_stats_kernel<T><<<n, 256, 0, st>>>((const T *)x, n, d, ld, w.S, w.G, w.flags);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+template <typename T>
+int run_operand(const void *x, uint32_t n, uint64_t d, uint64_t ld, const GramWs &w, bool i8, cudaStream_t st) {
+    const uint64_t dpad = dpad_of(d);
+    uint32_t gx = (uint32_t)((dpad + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, n);
+    if (i8) gram_operand_kernel<T, uint8_t><<<grid, 256, 0, st>>>((const T *)x, n, d, ld, dpad, (uint8_t *)w.h);
+    else gram_operand_kernel<T, __half><<<grid, 256, 0, st>>>((const T *)x, n, d, ld, dpad, (__half *)w.h);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+template <bool I8>
+int launch_gram(const GramWs &w, size_t n_tiles, uint32_t n, uint64_t d, uint32_t row_begin, uint32_t row_end,
+                GramOut go, cudaStream_t st) {
+    const uint64_t dpad = dpad_of(d);
+    const uint32_t esz = I8 ? 1 : 2, bk = BK_BYTES / esz;
+    const CUtensorMapDataType dt = I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUtensorMap tmA, tmB;
+    int rc;
+    if ((rc = kam_make_tmap_2d(&tmA, dt, esz, w.h, dpad, n, dpad * esz, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = kam_make_tmap_2d(&tmB, dt, esz, w.h, dpad, n, dpad * esz, bk, BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    const size_t smem = (size_t)G_STAGES * STAGE_BYTES + BN * sizeof(RowK) + 1024;
+    auto kern = gram_tcgen05_kernel<I8>;
+    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t grid = (uint32_t)kam_sm_count();
+    if (grid > n_tiles) grid = (uint32_t)n_tiles;
+    kern<<<grid, G_THREADS, smem, st>>>(tmA, tmB, w.tiles, (uint32_t)n_tiles, (uint32_t)(dpad / bk), n, row_begin,
+                                        row_end, w.rk, go);
     KAM_CUDA(cudaGetLastError());
     return KAM_OK;
 }
@@ -365,11 +430,11 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     go.cosine = (metrics & KAM_M_COSINE) ? d_tri_cosine : nullptr;
     go.pearson = (metrics & KAM_M_PEARSON) ? d_tri_pearson : nullptr;
 
-    // pass 1: fp16 operand + exact row statistics + the two envelope flags
+    // pass 1: exact row statistics + the envelope flags (largest count, largest G_ii)
     KAM_CUDA(cudaMemsetAsync(w.flags, 0, 64, st));
-    int rc = elem == KAM_U8    ? run_convert<uint8_t>(d_x, n, d, ld, w, true, st)
-             : elem == KAM_U16 ? run_convert<uint16_t>(d_x, n, d, ld, w, true, st)
-                               : run_convert<uint32_t>(d_x, n, d, ld, w, true, st);
+    int rc = elem == KAM_U8    ? run_stats<uint8_t>(d_x, n, d, ld, w, st)
+             : elem == KAM_U16 ? run_stats<uint16_t>(d_x, n, d, ld, w, st)
+                               : run_stats<uint32_t>(d_x, n, d, ld, w, st);
     if (rc) return rc;
     unsigned long long hflags[2] = {0, 0};
     KAM_CUDA(cudaMemcpyAsync(hflags, w.flags, 16, cudaMemcpyDeviceToHost, st));
@@ -377,10 +442,16 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     rowk_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.S, w.G, n, (double)d, euclid_on_freq, w.rk);
     KAM_CUDA(cudaGetLastError());
 
-    if (hflags[0] > MAX_EXACT_COUNT || hflags[1] >= MAX_EXACT_GII) {
-        // outside the exact fp16/fp32 envelope: exact integer Gram on the CUDA cores
+    // operand type: uint8 x uint8 -> int32 (kind::i8) when every count fits a byte; fp16 -> fp32
+    // (kind::f16) up to 2048; otherwise the exact integer Gram on the CUDA cores
+    const bool use_i8 = hflags[0] <= MAX_I8_COUNT && hflags[1] < MAX_I8_GII && !g_force_f16;
+    const bool use_f16 = !use_i8 && hflags[0] <= MAX_F16_COUNT && hflags[1] < MAX_F16_GII;
+    if (!use_i8 && !use_f16)
         return kam_int_gram_tri(d_x, elem, n, d, ld, row_begin, row_end, w.rk, go, w.xt, st);
-    }
+    rc = elem == KAM_U8    ? run_operand<uint8_t>(d_x, n, d, ld, w, use_i8, st)
+         : elem == KAM_U16 ? run_operand<uint16_t>(d_x, n, d, ld, w, use_i8, st)
+                           : run_operand<uint32_t>(d_x, n, d, ld, w, use_i8, st);
+    if (rc) return rc;
 
     // upper-triangular tile list, strips of 12 tile-rows, column-major inside a strip so that the
     // ~148 tiles in flight share about a dozen A panels and a dozen B panels in L2
@@ -397,22 +468,11 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     KAM_CUDA(cudaMemcpyAsync(w.tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
     KAM_CUDA(cudaStreamSynchronize(st));   // `tiles` is pageable host memory owned by this frame
 
-    const uint64_t dpad = dpad_of(d);
-    CUtensorMap tmA, tmB;
-    if ((rc = kam_make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w.h, dpad, n, dpad * 2, BK, BM,
-                               CU_TENSOR_MAP_SWIZZLE_128B)))
-        return rc;
-    if ((rc = kam_make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w.h, dpad, n, dpad * 2, BK, BN,
-                               CU_TENSOR_MAP_SWIZZLE_128B)))
-        return rc;
-    const size_t smem = (size_t)G_STAGES * STAGE_BYTES + BN * sizeof(RowK) + 1024;
-    KAM_CUDA(cudaFuncSetAttribute(gram_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t grid = (uint32_t)kam_sm_count();
-    if (grid > tiles.size()) grid = (uint32_t)tiles.size();
-    gram_tcgen05_kernel<<<grid, G_THREADS, smem, st>>>(tmA, tmB, w.tiles, (uint32_t)tiles.size(),
-                                                       (uint32_t)(dpad / BK), n, row_begin, row_end, w.rk, go);
-    KAM_CUDA(cudaGetLastError());
-    return KAM_OK;
+    return use_i8 ? launch_gram<true>(w, tiles.size(), n, d, row_begin, row_end, go, st)
+                  : launch_gram<false>(w, tiles.size(), n, d, row_begin, row_end, go, st);
 }
+
+// test hook: force the fp16 tensor path even when the uint8 path would apply
+void kam_gram_force_f16(int on) { g_force_f16 = on != 0; }
 
 }  // extern "C"

@@ -98,7 +98,7 @@ def info_tri(x, rows=None, out=None):
     return out[:tri_len(n)]
 
 
-def gram_tri(x, metrics=("euclid", "cosine", "pearson"), euclid_on_freq=True, rows=None):
+def gram_tri(x, metrics=("euclid", "cosine", "pearson"), euclid_on_freq=True, rows=None, force_f16=False):
     """euclid / cosine / pearson of every pair i<j from one tensor-core Gram pass: dict of float32
     packed triangles.  x: uint16/uint32 count vectors."""
     lib = _lib.load()
@@ -114,9 +114,13 @@ def gram_tri(x, metrics=("euclid", "cosine", "pearson"), euclid_on_freq=True, ro
         outs[m] = torch.zeros(max(tri_len(n), 1), dtype=torch.float32, device=dev)
     ws = torch.empty(max(lib.kam_gram_workspace_bytes(n, d), 256), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        check(lib.kam_gram_tri(_ptr(x), _ELEM[x.dtype], n, d, x.stride(0), r0, r1, mask, int(euclid_on_freq),
-                               _ptr(outs.get("euclid")), _ptr(outs.get("cosine")), _ptr(outs.get("pearson")),
-                               _ptr(ws), ws.numel(), _stream(dev)))
+        lib.kam_gram_force_f16(int(force_f16))         # test hook: fp16 tensor path instead of uint8
+        try:
+            check(lib.kam_gram_tri(_ptr(x), _ELEM[x.dtype], n, d, x.stride(0), r0, r1, mask, int(euclid_on_freq),
+                                   _ptr(outs.get("euclid")), _ptr(outs.get("cosine")), _ptr(outs.get("pearson")),
+                                   _ptr(ws), ws.numel(), _stream(dev)))
+        finally:
+            lib.kam_gram_force_f16(0)
     return {m: t[:tri_len(n)] for m, t in outs.items()}
 
 

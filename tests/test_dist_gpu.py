@@ -115,9 +115,9 @@ def test_symmetry_and_full_size_property(D):
 
 
 # ---- Gram metrics (euclid / cosine / pearson): tcgen05 tensor-core path -----------------------------
-def _check_gram(D, x, rtol=1e-5):
+def _check_gram(D, x, rtol=1e-5, force_f16=False):
     xd = _dev(x)
-    got = D.gram_tri(xd, ("euclid", "cosine", "pearson"), euclid_on_freq=True)
+    got = D.gram_tri(xd, ("euclid", "cosine", "pearson"), euclid_on_freq=True, force_f16=force_f16)
     f = x / x.sum(axis=1, keepdims=True)
     np.testing.assert_allclose(got["euclid"].cpu().numpy(), O.cdist_triangle(f, "euclid"), rtol=rtol)
     np.testing.assert_allclose(got["cosine"].cpu().numpy(), O.cdist_triangle(x, "cosine"), rtol=rtol)
@@ -143,7 +143,24 @@ def test_gram_demo_k6_appendix_b(D, demo_records):
 @pytest.mark.parametrize("n,L,k", [(2, 500, 3), (37, 3000, 5), (130, 9000, 6), (300, 2000, 4), (257, 1000, 7),
                                    (600, 4000, 6), (40, 9000, 9)])
 def test_gram_vs_scipy(D, n, L, k):
-    _check_gram(D, _counts(n, L, k, seed=100 + n + k))
+    x = _counts(n, L, k, seed=100 + n + k)
+    _check_gram(D, x)                      # uint8 x uint8 -> int32 tensor path (counts <= 255)
+    _check_gram(D, x, force_f16=True)      # fp16 -> fp32 tensor path
+
+
+def test_gram_i8_and_f16_paths_agree_exactly(D):
+    """both tensor paths produce the exact integer Gram matrix, hence identical float32 outputs."""
+    x = _dev(_counts(300, 5000, 6, seed=5))
+    a = D.gram_tri(x)
+    b = D.gram_tri(x, force_f16=True)
+    for m in a:
+        assert torch.equal(a[m], b[m])
+
+
+def test_gram_f16_path_mid_counts(D):
+    rng = np.random.Generator(np.random.PCG64(12))
+    x = rng.integers(0, 1500, size=(200, 12)).astype(np.uint16)       # 255 < max <= 2048, G_ii < 2^24
+    _check_gram(D, x)
 
 
 def test_gram_ragged_d_and_u32(D):
