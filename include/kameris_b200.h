@@ -152,6 +152,9 @@ size_t kam_gram_workspace_bytes(uint32_t n, uint64_t d);
 /* test hook: non-zero forces the fp16 (kind::f16) tensor path where the uint8 (kind::i8) path would
  * be chosen; both are exact inside their envelopes. */
 void kam_gram_force_f16(int on);
+/* tuning/test hook: thread-block cluster size of the Gram kernel (2 = B panel multicast between the
+ * two CTAs of a cluster, default; 1 = no cluster). */
+void kam_gram_set_cluster(int cl);
 int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                  uint32_t row_begin, uint32_t row_end, unsigned metrics, int euclid_on_freq,
                  float *d_tri_euclid, float *d_tri_cosine, float *d_tri_pearson, void *d_ws,

@@ -41,6 +41,7 @@ SIGNATURES = {
                              c_size_t, c_void_p]),
     "kam_gram_workspace_bytes": (c_size_t, [c_uint32, c_uint64]),
     "kam_gram_force_f16": (None, [c_int]),
+    "kam_gram_set_cluster": (None, [c_int]),
     "kam_gram_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, ctypes.c_uint,
                              c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "kam_dists_host": (c_int, [c_void_p, c_int, c_uint32, c_uint64, ctypes.c_uint, c_void_p, c_void_p, c_void_p,

@@ -81,6 +81,12 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// commit that arrives on the same barrier offset in every CTA of cta_mask (cluster multicast)
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -98,7 +104,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <bool I8>
+// CL = cluster size along M (1 or 2).  With CL == 2 the two CTAs of a cluster work on the tiles
+// (2p, bj) and (2p+1, bj): they need the same B panel, so each CTA fetches half of it and TMA
+// multicasts it into both shared memories -- 32 KB instead of 48 KB of L2 traffic per CTA and stage.
+template <bool I8, int CL>
 __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const uint2 *__restrict__ tiles, uint32_t n_tiles,
@@ -112,13 +121,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
     __shared__ uint32_t tmem_holder;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < G_STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);   // every CTA of the cluster must have consumed the stage
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
@@ -133,7 +144,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();   // peers' barriers are initialised before anyone signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_holder;
 
@@ -143,14 +155,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const uint2 tile = tiles[t];
+                const uint32_t bi = tile.x * CL + crank;
                 for (uint32_t kb = 0; kb < k_iters; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
                     unsigned char *sa = smem + stage * STAGE_BYTES;
                     // inner coordinate in elements: 64 fp16 or 128 uint8 per 128-byte row
                     const int32_t kc = (int32_t)(kb * (I8 ? BK_BYTES : BK_BYTES / 2));
-                    tma_load_2d(sa, &tmA, kc, (int32_t)(tile.x * BM), &full[stage]);
-                    tma_load_2d(sa + A_BYTES, &tmB, kc, (int32_t)(tile.y * BN), &full[stage]);
+                    tma_load_2d(sa, &tmA, kc, (int32_t)(bi * BM), &full[stage]);
+                    if constexpr (CL == 1) {
+                        tma_load_2d(sa + A_BYTES, &tmB, kc, (int32_t)(tile.y * BN), &full[stage]);
+                    } else {   // my half of the B panel, to both CTAs (tmA's 128-row box)
+                        tma_load_2d_mc(sa + A_BYTES + crank * (B_BYTES / CL), &tmA, kc,
+                                       (int32_t)(tile.y * BN + crank * (BN / CL)), &full[stage], CMASK);
+                    }
                     if (++stage == G_STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -174,7 +192,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
 #pragma unroll
                     for (uint32_t k = 0; k < BK_BYTES / 32; ++k)   // +32 B per MMA inside the 128-B swizzle row
                         umma<I8>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty[stage]);            // smem slot free once these MMAs retire
+                    // smem slot free once these MMAs retire (in every CTA that was sent data for it)
+                    if constexpr (CL == 1) umma_commit(&empty[stage]);
+                    else umma_commit_mc(&empty[stage], CMASK);
                     if (++stage == G_STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -192,7 +212,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const uint2 tile = tiles[t];
-            const uint32_t r0 = tile.x * BM, c0 = tile.y * BN;
+            const uint32_t r0 = (tile.x * CL + crank) * BM, c0 = tile.y * BN;
             asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's colk fully consumed
             for (uint32_t c = et; c < (uint32_t)BN; c += 128) {
                 RowK z;
@@ -233,7 +253,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still write its smem / barriers
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -318,6 +339,7 @@ __global__ void rowk_kernel(const unsigned long long *__restrict__ S, const unsi
 }
 
 bool g_force_f16 = false;
+uint32_t g_cluster = 2;
 
 struct GramWs {
     void *h;
@@ -379,7 +401,7 @@ int run_operand(const void *x, uint32_t n, uint64_t d, uint64_t ld, const GramWs
     return KAM_OK;
 }
 
-template <bool I8>
+template <bool I8, int CL>
 int launch_gram(const GramWs &w, size_t n_tiles, uint32_t n, uint64_t d, uint32_t row_begin, uint32_t row_end,
                 GramOut go, cudaStream_t st) {
     const uint64_t dpad = dpad_of(d);
@@ -390,13 +412,26 @@ int launch_gram(const GramWs &w, size_t n_tiles, uint32_t n, uint64_t d, uint32_
     if ((rc = kam_make_tmap_2d(&tmA, dt, esz, w.h, dpad, n, dpad * esz, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = kam_make_tmap_2d(&tmB, dt, esz, w.h, dpad, n, dpad * esz, bk, BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     const size_t smem = (size_t)G_STAGES * STAGE_BYTES + BN * sizeof(RowK) + 1024;
-    auto kern = gram_tcgen05_kernel<I8>;
+    auto kern = gram_tcgen05_kernel<I8, CL>;
     KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t grid = (uint32_t)kam_sm_count();
-    if (grid > n_tiles) grid = (uint32_t)n_tiles;
-    kern<<<grid, G_THREADS, smem, st>>>(tmA, tmB, w.tiles, (uint32_t)n_tiles, (uint32_t)(dpad / bk), n, row_begin,
-                                        row_end, w.rk, go);
-    KAM_CUDA(cudaGetLastError());
+    uint32_t clusters = (uint32_t)kam_sm_count() / CL;
+    if (clusters > n_tiles) clusters = (uint32_t)n_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CL);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const uint2 *tiles = w.tiles;
+    const RowK *rk = w.rk;
+    KAM_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tiles, (uint32_t)n_tiles, (uint32_t)(dpad / bk), n, row_begin,
+                                row_end, rk, go));
     return KAM_OK;
 }
 
@@ -453,26 +488,34 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                            : run_operand<uint32_t>(d_x, n, d, ld, w, use_i8, st);
     if (rc) return rc;
 
-    // upper-triangular tile list, strips of 12 tile-rows, column-major inside a strip so that the
-    // ~148 tiles in flight share about a dozen A panels and a dozen B panels in L2
+    // upper-triangular tile list.  A list entry is (row-tile group, column tile); a group is CL
+    // consecutive 128-row tiles handled by the CL CTAs of a cluster.  Strips of ~12 row tiles,
+    // column-major inside a strip, so the ~148 tiles in flight share about a dozen A panels and a
+    // dozen B panels in L2.
+    const uint32_t CL = g_cluster;
     std::vector<uint2> tiles;
-    const uint32_t tr0 = row_begin / BM, tr1 = (row_end - 1) / BM + 1, tc = (n + BN - 1) / BN;
-    constexpr uint32_t STRIP = 12;
+    const uint32_t GM = BM * CL;
+    const uint32_t tr0 = row_begin / GM, tr1 = (row_end - 1) / GM + 1, tc = (n + BN - 1) / BN;
+    const uint32_t STRIP = 12 / CL;
     for (uint32_t s0 = tr0; s0 < tr1; s0 += STRIP) {
         const uint32_t s1 = s0 + STRIP < tr1 ? s0 + STRIP : tr1;
         for (uint32_t bj = 0; bj < tc; ++bj)
-            for (uint32_t bi = s0; bi < s1; ++bi)
-                if ((uint64_t)bj * BN + BN - 1 > (uint64_t)bi * BM) tiles.push_back(make_uint2(bi, bj));
+            for (uint32_t bg = s0; bg < s1; ++bg)
+                if ((uint64_t)bj * BN + BN - 1 > (uint64_t)bg * GM) tiles.push_back(make_uint2(bg, bj));
     }
     if (tiles.empty()) return KAM_OK;
     KAM_CUDA(cudaMemcpyAsync(w.tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
     KAM_CUDA(cudaStreamSynchronize(st));   // `tiles` is pageable host memory owned by this frame
 
-    return use_i8 ? launch_gram<true>(w, tiles.size(), n, d, row_begin, row_end, go, st)
-                  : launch_gram<false>(w, tiles.size(), n, d, row_begin, row_end, go, st);
+    if (CL == 2)
+        return use_i8 ? launch_gram<true, 2>(w, tiles.size(), n, d, row_begin, row_end, go, st)
+                      : launch_gram<false, 2>(w, tiles.size(), n, d, row_begin, row_end, go, st);
+    return use_i8 ? launch_gram<true, 1>(w, tiles.size(), n, d, row_begin, row_end, go, st)
+                  : launch_gram<false, 1>(w, tiles.size(), n, d, row_begin, row_end, go, st);
 }
 
-// test hook: force the fp16 tensor path even when the uint8 path would apply
+// test hooks: force the fp16 tensor path even when the uint8 path would apply; cluster size 1|2
 void kam_gram_force_f16(int on) { g_force_f16 = on != 0; }
+void kam_gram_set_cluster(int cl) { g_cluster = cl == 1 ? 1u : 2u; }
 
 }  // extern "C"

@@ -90,6 +90,24 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
         ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c_inner), "r"(c_outer), "r"(smem_u32(bar))
         : "memory");
 }
+// multicast load: the box lands at the same CTA-relative smem offset, and signals the mbarrier at
+// the same CTA-relative offset, in every CTA of the cluster selected by cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(void *smem_dst, const CUtensorMap *tm, int32_t c_inner, int32_t c_outer,
+                                               uint64_t *bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c_inner), "r"(c_outer), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
