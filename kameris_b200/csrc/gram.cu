@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
     __shared__ __align__(8) uint64_t full[G_STAGES], empty[G_STAGES], tfull[2], tempty[2];
     __shared__ uint32_t tmem_holder;
 
+    // tile list entries are taken per CLUSTER (blockIdx.x / CL, stride gridDim.x / CL)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (uint32_t t = blockIdx.x / CL; t < n_tiles; t += gridDim.x / CL) {
                 const uint2 tile = tiles[t];
                 const uint32_t bi = tile.x * CL + crank;
                 for (uint32_t kb = 0; kb < k_iters; ++kb) {
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (uint32_t t = blockIdx.x / CL; t < n_tiles; t += gridDim.x / CL) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1u);   // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
         const uint32_t q = (uint32_t)warp & 3u;
         const uint32_t et = threadIdx.x - 64;              // 0..127
         uint32_t acc = 0, acc_phase = 0;
-        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (uint32_t t = blockIdx.x / CL; t < n_tiles; t += gridDim.x / CL) {
             const uint2 tile = tiles[t];
             const uint32_t r0 = (tile.x * CL + crank) * BM, c0 = tile.y * BN;
             asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's colk fully consumed
@@ -261,29 +262,77 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
     }
 }
 
-// ---- pre-pass 1: exact per-row sum and sum of squares, largest count, largest G_ii --------------
-template <typename T>
-__global__ void __launch_bounds__(256) gram_stats_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
-                                                         unsigned long long *__restrict__ S,
-                                                         unsigned long long *__restrict__ G,
-                                                         unsigned long long *__restrict__ flags) {
+// ---- pre-pass: ONE pass over the counts writes the tensor-core operand rows (uint8, saturating, or
+// fp16; zero-padded to dpad) and the exact per-row sum / sum of squares, and records the largest
+// count and the largest G_ii (the exactness envelope).  One CTA per row, 16 elements per thread and
+// step with 16-byte loads and stores.
+template <typename OP>
+__device__ __forceinline__ void store_operand16(OP *dst, const unsigned (&c)[16]) {
+    if constexpr (sizeof(OP) == 1) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            w[i] = min(c[4 * i], 255u) | (min(c[4 * i + 1], 255u) << 8) | (min(c[4 * i + 2], 255u) << 16) |
+                   (min(c[4 * i + 3], 255u) << 24);
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        __half2 h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = __halves2half2(__uint2half_rn(c[2 * i]), __uint2half_rn(c[2 * i + 1]));
+        reinterpret_cast<uint4 *>(dst)[0] = *reinterpret_cast<uint4 *>(&h[0]);
+        reinterpret_cast<uint4 *>(dst)[1] = *reinterpret_cast<uint4 *>(&h[4]);
+    }
+}
+
+template <typename T, typename OP>
+__global__ void __launch_bounds__(256) gram_prepass_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
+                                                           uint64_t dpad, OP *__restrict__ h,
+                                                           unsigned long long *__restrict__ S,
+                                                           unsigned long long *__restrict__ G,
+                                                           unsigned long long *__restrict__ flags, int vec_ok) {
     __shared__ unsigned long long red[3][8];
     const uint32_t row = blockIdx.x;
     const T *xr = x + (uint64_t)row * ld;
-    unsigned long long s = 0, g = 0, mx = 0;
-    for (uint64_t e = threadIdx.x; e < d; e += 256) {
-        const unsigned long long c = (unsigned long long)xr[e];
-        s += c;
-        g += c * c;
-        mx = c > mx ? c : mx;
+    OP *hr = h + (uint64_t)row * dpad;
+    unsigned long long s = 0, g = 0;
+    unsigned mx = 0;
+    if (vec_ok) {   // d % 16 == 0 and 16-byte aligned rows
+        for (uint64_t e = (uint64_t)threadIdx.x * 16; e < dpad; e += 256 * 16) {
+            unsigned c[16];
+            if (e < d) {
+                constexpr int NV = (int)sizeof(T);            // uint4 loads per 16 elements
+                uint4 v[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) v[i] = __ldg(reinterpret_cast<const uint4 *>(xr + e) + i);
+                const T *t = reinterpret_cast<const T *>(v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) c[i] = (unsigned)t[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) c[i] = 0;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                s += c[i];
+                g += (unsigned long long)c[i] * c[i];
+                mx = max(mx, c[i]);
+            }
+            store_operand16<OP>(hr + e, c);
+        }
+    } else {
+        for (uint64_t e = threadIdx.x; e < dpad; e += 256) {
+            const unsigned c = e < d ? (unsigned)xr[e] : 0u;
+            s += c;
+            g += (unsigned long long)c * c;
+            mx = max(mx, c);
+            if constexpr (sizeof(OP) == 1) hr[e] = (OP)min(c, 255u);
+            else hr[e] = __uint2half_rn(c);
+        }
     }
     s = warp_sum64(s);
     g = warp_sum64(g);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long t = __shfl_xor_sync(0xffffffffu, mx, o);
-        mx = t > mx ? t : mx;
-    }
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) {
         red[0][threadIdx.x >> 5] = s;
         red[1][threadIdx.x >> 5] = g;
@@ -291,30 +340,16 @@ __global__ void __launch_bounds__(256) gram_stats_kernel(const T *__restrict__ x
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        s = g = mx = 0;
+        unsigned long long ts = 0, tg = 0, tm = 0;
         for (int w = 0; w < 8; ++w) {
-            s += red[0][w];
-            g += red[1][w];
-            mx = red[2][w] > mx ? red[2][w] : mx;
+            ts += red[0][w];
+            tg += red[1][w];
+            tm = red[2][w] > tm ? red[2][w] : tm;
         }
-        S[row] = s;
-        G[row] = g;
-        atomicMax(&flags[0], mx);
-        atomicMax(&flags[1], g);
-    }
-}
-
-// ---- pre-pass 2: counts -> tensor-core operand rows (uint8 or fp16), zero-padded to dpad ----------
-template <typename T, typename OP>
-__global__ void __launch_bounds__(256) gram_operand_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
-                                                           uint64_t dpad, OP *__restrict__ h) {
-    const uint32_t row = blockIdx.y;
-    const T *xr = x + (uint64_t)row * ld;
-    OP *hr = h + (uint64_t)row * dpad;
-    for (uint64_t e = (uint64_t)blockIdx.x * 256 + threadIdx.x; e < dpad; e += (uint64_t)gridDim.x * 256) {
-        const unsigned c = e < d ? (unsigned)xr[e] : 0u;
-        if constexpr (sizeof(OP) == 1) hr[e] = (OP)c;
-        else hr[e] = __uint2half_rn(c);
+        S[row] = ts;
+        G[row] = tg;
+        atomicMax(&flags[0], tm);
+        atomicMax(&flags[1], tg);
     }
 }
 
@@ -383,21 +418,28 @@ inline size_t gram_layout(uint32_t n, uint64_t d, void *base, GramWs *w) {
 }
 
 template <typename T>
-int run_stats(const void *x, uint32_t n, uint64_t d, uint64_t ld, const GramWs &w, cudaStream_t st) {
-    gram_stats_kernel<T><<<n, 256, 0, st>>>((const T *)x, n, d, ld, w.S, w.G, w.flags);
+int run_prepass(const void *x, uint32_t n, uint64_t d, uint64_t ld, const GramWs &w, bool i8, cudaStream_t st) {
+    const uint64_t dpad = dpad_of(d);
+    const int vec_ok = (d % 16 == 0) && ((ld * sizeof(T)) % 16 == 0) && (((uintptr_t)x & 15) == 0);
+    if (i8)
+        gram_prepass_kernel<T, uint8_t><<<n, 256, 0, st>>>((const T *)x, n, d, ld, dpad, (uint8_t *)w.h, w.S, w.G,
+                                                           w.flags, vec_ok);
+    else
+        gram_prepass_kernel<T, __half><<<n, 256, 0, st>>>((const T *)x, n, d, ld, dpad, (__half *)w.h, w.S, w.G,
+                                                          w.flags, vec_ok);
     KAM_CUDA(cudaGetLastError());
     return KAM_OK;
 }
 
-template <typename T>
-int run_operand(const void *x, uint32_t n, uint64_t d, uint64_t ld, const GramWs &w, bool i8, cudaStream_t st) {
-    const uint64_t dpad = dpad_of(d);
-    uint32_t gx = (uint32_t)((dpad + 256 * 8 - 1) / (256 * 8));
-    if (gx < 1) gx = 1;
-    dim3 grid(gx, n);
-    if (i8) gram_operand_kernel<T, uint8_t><<<grid, 256, 0, st>>>((const T *)x, n, d, ld, dpad, (uint8_t *)w.h);
-    else gram_operand_kernel<T, __half><<<grid, 256, 0, st>>>((const T *)x, n, d, ld, dpad, (__half *)w.h);
-    KAM_CUDA(cudaGetLastError());
+int prepass(const void *x, int elem, uint32_t n, uint64_t d, uint64_t ld, const GramWs &w, bool i8,
+            unsigned long long (&hflags)[2], cudaStream_t st) {
+    KAM_CUDA(cudaMemsetAsync(w.flags, 0, 64, st));
+    int rc = elem == KAM_U8    ? run_prepass<uint8_t>(x, n, d, ld, w, i8, st)
+             : elem == KAM_U16 ? run_prepass<uint16_t>(x, n, d, ld, w, i8, st)
+                               : run_prepass<uint32_t>(x, n, d, ld, w, i8, st);
+    if (rc) return rc;
+    KAM_CUDA(cudaMemcpyAsync(hflags, w.flags, 16, cudaMemcpyDeviceToHost, st));
+    KAM_CUDA(cudaStreamSynchronize(st));
     return KAM_OK;
 }
 
@@ -465,28 +507,27 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     go.cosine = (metrics & KAM_M_COSINE) ? d_tri_cosine : nullptr;
     go.pearson = (metrics & KAM_M_PEARSON) ? d_tri_pearson : nullptr;
 
-    // pass 1: exact row statistics + the envelope flags (largest count, largest G_ii)
-    KAM_CUDA(cudaMemsetAsync(w.flags, 0, 64, st));
-    int rc = elem == KAM_U8    ? run_stats<uint8_t>(d_x, n, d, ld, w, st)
-             : elem == KAM_U16 ? run_stats<uint16_t>(d_x, n, d, ld, w, st)
-                               : run_stats<uint32_t>(d_x, n, d, ld, w, st);
-    if (rc) return rc;
+    // pre-pass: operand rows + exact row statistics + the envelope flags in one sweep.  Operand type:
+    // uint8 x uint8 -> int32 (kind::i8) when every count fits a byte; fp16 -> fp32 (kind::f16) up to
+    // 2048; otherwise the exact integer Gram on the CUDA cores.  The uint8 operand is written
+    // speculatively (the common case); a second sweep rewrites it as fp16 only when it did not fit.
     unsigned long long hflags[2] = {0, 0};
-    KAM_CUDA(cudaMemcpyAsync(hflags, w.flags, 16, cudaMemcpyDeviceToHost, st));
-    KAM_CUDA(cudaStreamSynchronize(st));
+    int rc;
+    bool have_i8 = false;
+    if (!g_force_f16) {
+        if ((rc = prepass(d_x, elem, n, d, ld, w, true, hflags, st))) return rc;
+        have_i8 = hflags[0] <= MAX_I8_COUNT && hflags[1] < MAX_I8_GII;
+    }
+    if (!have_i8) {
+        if (g_force_f16 || (hflags[0] <= MAX_F16_COUNT && hflags[1] < MAX_F16_GII))
+            if ((rc = prepass(d_x, elem, n, d, ld, w, false, hflags, st))) return rc;
+    }
+    const bool use_i8 = have_i8;
+    const bool use_f16 = !use_i8 && hflags[0] <= MAX_F16_COUNT && hflags[1] < MAX_F16_GII;
     rowk_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.S, w.G, n, (double)d, euclid_on_freq, w.rk);
     KAM_CUDA(cudaGetLastError());
-
-    // operand type: uint8 x uint8 -> int32 (kind::i8) when every count fits a byte; fp16 -> fp32
-    // (kind::f16) up to 2048; otherwise the exact integer Gram on the CUDA cores
-    const bool use_i8 = hflags[0] <= MAX_I8_COUNT && hflags[1] < MAX_I8_GII && !g_force_f16;
-    const bool use_f16 = !use_i8 && hflags[0] <= MAX_F16_COUNT && hflags[1] < MAX_F16_GII;
     if (!use_i8 && !use_f16)
         return kam_int_gram_tri(d_x, elem, n, d, ld, row_begin, row_end, w.rk, go, w.xt, st);
-    rc = elem == KAM_U8    ? run_operand<uint8_t>(d_x, n, d, ld, w, use_i8, st)
-         : elem == KAM_U16 ? run_operand<uint16_t>(d_x, n, d, ld, w, use_i8, st)
-                           : run_operand<uint32_t>(d_x, n, d, ld, w, use_i8, st);
-    if (rc) return rc;
 
     // upper-triangular tile list.  A list entry is (row-tile group, column tile); a group is CL
     // consecutive 128-row tiles handled by the CL CTAs of a cluster.  Strips of ~12 row tiles,
