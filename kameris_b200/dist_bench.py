@@ -1,8 +1,9 @@
 """Secondary benchmark lines for bench.py: pairs/s of the distance kernels with their rooflines.
 
   gram      : N=8192 count vectors of D=4^9 (9 kb genomes, k=9): cosine+pearson+euclid from one
-              tcgen05 Gram pass.  Algorithmic flops = 2*D per unique pair; peak =
-              measured bf16 tensor throughput (MEASURED_PEAKS.json).
+              tcgen05 Gram pass.  Algorithmic flops = 2*D per unique pair.  Counts
+              <= 255 run as uint8 x uint8 -> int32 (peak = 2 x the measured bf16 throughput of
+              MEASURED_PEAKS.json); the fp16 path on the same data is reported against the bf16 peak.
   manhattan : BASELINE config 4 shape -- M reads x C=1000 centroids, D=4^6, uint32-exact manhat
               (byte path, VABSDIFF4) ; bound = CUDA-core issue rate, reported as pair-elements/s.
 """
@@ -53,15 +54,28 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
         _lib.check(lib.kam_gram_tri(x.data_ptr(), 1, n, d, x.stride(0), 0, n, 4 | 8 | 16, 1, tri["euclid"].data_ptr(),
                                     tri["cosine"].data_ptr(), tri["pearson"].data_ptr(), ws.data_ptr(), ws.numel(),
                                     stream))
-    t = _time(torch, gram, reps)
-    tflops = 2.0 * d * pairs / t / 1e12
+    t = _time(torch, gram, reps)                  # counts <= 255: uint8 x uint8 -> int32 (tcgen05 kind::i8)
+    lib.kam_gram_force_f16(1)
+    try:
+        t16 = _time(torch, gram, reps)            # same data through the fp16 -> fp32 path (kind::f16)
+    finally:
+        lib.kam_gram_force_f16(0)
+    tflops, tflops16 = 2.0 * d * pairs / t / 1e12, 2.0 * d * pairs / t16 / 1e12
+    i8_peak = 2.0 * tf_peak                       # int8 dense tensor rate is 2x the bf16 rate on B200
     out["gram"] = {"metric": "distance_pairs_per_sec", "value": pairs / t, "unit": "pairs/s",
                    "config": {"workload": "N=%d count vectors, D=4^9, euclid+cosine+pearson from one Gram pass" % n,
-                              "includes": "fp16 conversion + row statistics + tile list + tcgen05 kernel"},
+                              "includes": "operand/statistics pre-pass + tile list + tcgen05 kernel + epilogue",
+                              "path": "uint8 operands, int32 accumulation in TMEM (exact); cluster-2 TMA multicast"},
                    "ms": t * 1e3,
-                   "roofline": {"bound": "tensor", "achieved": tflops, "peak": tf_peak, "unit": "TFLOP/s",
-                                "frac": tflops / tf_peak, "traffic": None,
-                                "algorithmic_flops_per_pair": 2 * d, "kernel": "gram_tcgen05_kernel"}}
+                   "roofline": {"bound": "tensor", "achieved": tflops, "peak": i8_peak, "unit": "TFLOP/s",
+                                "frac": tflops / i8_peak, "traffic": None,
+                                "peak_note": "2 x measured bf16 peak (%.1f): int8 tensor rate; achieved/bf16 peak = %.2f"
+                                             % (tf_peak, tflops / tf_peak),
+                                "algorithmic_flops_per_pair": 2 * d, "kernel": "gram_tcgen05_kernel<i8,cluster2>"},
+                   "fp16_path": {"value": pairs / t16, "unit": "pairs/s", "ms": t16 * 1e3,
+                                 "roofline": {"bound": "tensor", "achieved": tflops16, "peak": tf_peak,
+                                              "unit": "TFLOP/s", "frac": tflops16 / tf_peak,
+                                              "kernel": "gram_tcgen05_kernel<f16,cluster2>"}}}
     del x, tri, ws
 
     # ---- manhattan, config-4 shape ----------------------------------------------------------------------

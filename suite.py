@@ -1,0 +1,264 @@
+#!/usr/bin/env python3
+"""suite.py -- the five BASELINE.json configs end to end on B200s: results checked against the
+oracle (bit-exact counts / manhat, 1e-5 relative for frequencies and Gram metrics), throughput
+reported per config.  One JSON line per config (rank 0).
+
+    python suite.py --config 1 2 4 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29500 suite.py --config 3 5
+
+Large synthetic sets are generated ON DEVICE (torch.Generator seeded per rank and batch); the
+sampled sequences / pairs that are verified are copied back and recomputed by the CPU oracle.
+--scale shrinks configs 3-5 (e.g. --scale 0.1) for quick runs.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from kameris_b200 import dist as D  # noqa: E402
+from kameris_b200 import parallel  # noqa: E402
+from kameris_b200 import repr as R  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+ALPHA = torch.tensor([65, 67, 71, 84], dtype=torch.uint8)     # A C G T
+HIV_P = torch.tensor([0.36, 0.18, 0.24, 0.22])
+
+
+def ctx():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", lr)
+    torch.cuda.set_device(dev)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    return rank, world, dev
+
+
+def gen_chars(dev, n, L, seed, p=None):
+    """n*L ASCII bases on device (+16 B pad for the pack kernel's vector loads)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.zeros(n * L + 16, dtype=torch.uint8, device=dev)
+    alpha = ALPHA.to(dev)
+    step = 1 << 28
+    cdf = torch.cumsum(p.to(dev), 0) if p is not None else None
+    for o in range(0, n * L, step):
+        m = min(step, n * L - o)
+        if cdf is None:
+            idx = torch.randint(0, 4, (m,), generator=g, device=dev)
+        else:
+            idx = torch.bucketize(torch.rand(m, generator=g, device=dev), cdf[:3])
+        out[o:o + m] = alpha[idx]
+    return out
+
+
+def pack(dev, chars, n, L):
+    start = torch.arange(n + 1, dtype=torch.int64, device=dev) * L
+    return R.pack_chars(chars, start, n, n * L)
+
+
+def tmax(x, world, dev):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+def allok(ok, world, dev):
+    t = torch.tensor([1 if ok else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t))
+
+
+def timed(fn, dev, world):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return r, e0.elapsed_time(e1) * 1e-3
+
+
+# ---- config 1 ---------------------------------------------------------------------------------------
+def config1(rank, world, dev, scale):
+    gdir = os.path.join(ROOT, "tests", "golden", "hiv1-genomes")
+    recs = [O.fasta_record0(open(os.path.join(gdir, n), "rb").read()) for n in sorted(os.listdir(gdir))]
+    b = R.pack_records(recs, dev)
+    (c6, t) = timed(lambda: R.kmer_vectors(b, 6, 16, "counts"), dev, 1)
+    x = c6.cpu().numpy()
+    ok = all(np.array_equal(x[i], O.cgr_count(r, 6)) for i, r in enumerate(recs))
+    g = D.gram_tri(c6, ("euclid", "cosine", "pearson"), euclid_on_freq=True)
+    f = x / x.sum(axis=1, keepdims=True)
+    ok &= np.allclose(g["euclid"].cpu().numpy(), O.cdist_triangle(f, "euclid"), rtol=1e-5, atol=0)
+    ok &= np.allclose(g["euclid"].cpu().numpy(), [0.0107171533, 0.0122965513, 0.0118525572, 0.0119359576,
+                                                  0.0116858869, 0.0116338804], rtol=1e-5, atol=0)   # Appendix B
+    man = D.manhattan_tri(c6).cpu().numpy().view(np.uint32)
+    ok &= man.tolist() == [3904, 4791, 4369, 4773, 4455, 4628]
+    return {"config": 1, "what": "demo hiv1 genomes: k=6 counts + euclid(freq)/cosine/pearson/manhat", "ok": bool(ok),
+            "n": 4, "kmers_ms": t * 1e3}
+
+
+# ---- config 2 ---------------------------------------------------------------------------------------
+def config2(rank, world, dev, scale):
+    n, L = 10000, 9000
+    chars = gen_chars(dev, n, L, 20261002 + rank, HIV_P)
+    b = pack(dev, chars, n, L)
+    outs = {k: torch.empty((n, 4 ** k), dtype=torch.float32, device=dev) for k in range(1, 10)}
+    wss = {k: R.kmer_workspace(n, k, dev) for k in range(1, 10)}
+
+    def sweep():
+        for k in range(1, 10):
+            R.kmer_vectors(b, k, 16, "freq32", out_tensor=outs[k], workspace=wss[k])
+    sweep()
+    _, t = timed(sweep, dev, world)
+    rng = np.random.Generator(np.random.PCG64(1))
+    samp = rng.choice(n, 64, replace=False)
+    host = chars.cpu().numpy()
+    ok = True
+    for i in samp:
+        rec = host[i * L:(i + 1) * L].tobytes()
+        for k in range(1, 10):
+            ref = O.frequencies(O.cgr_count(rec, k, 16)).astype(np.float32)
+            ok &= np.allclose(outs[k][i].cpu().numpy(), ref, rtol=1e-6, atol=0)
+    tm = tmax(t, world, dev)
+    byt = ((L + 3) // 4 + 4 * sum(4 ** k for k in range(1, 10))) * n
+    return {"config": 2, "what": "10k x 9 kb per GPU, k=1..9 float32 CGR vectors", "ok": allok(ok, world, dev),
+            "n_gpus": world, "seq_per_s": world * n / tm, "ms": tm * 1e3, "GBps_per_gpu": byt / tm / 1e9,
+            "verified": "64 sequences x 9 k vs oracle (rtol 1e-6)"}
+
+
+# ---- config 3 ---------------------------------------------------------------------------------------
+def config3(rank, world, dev, scale):
+    n_total = int(100000 * scale)
+    n_loc = n_total // world
+    n_total = n_loc * world
+    L, k = 9000, 9
+    chars = gen_chars(dev, n_loc, L, 20261003 + rank, HIV_P)
+    b = pack(dev, chars, n_loc, L)
+    x_loc, t_repr = timed(lambda: R.kmer_vectors(b, k, 16, "counts"), dev, world)
+    del chars, b
+    torch.cuda.empty_cache()
+    (x_full, _), t_ag = timed(lambda: parallel.all_gather_rows(x_loc), dev, world) if world > 1 else ((x_loc, None), 0.0)
+    r0, r1 = D.balanced_row_ranges(n_total, world)[rank]
+    off0, off1 = parallel.tri_row_offset(n_total, r0), parallel.tri_row_offset(n_total, r1)
+
+    def go():
+        return parallel._compute_cuda(x_full, ["cosine", "pearson"], (r0, r1), off0, off1 - off0)
+    res, t_d = timed(go, dev, world)
+    # verify random pairs of this rank's rows against scipy on the gathered counts
+    rng = np.random.Generator(np.random.PCG64(7 + rank))
+    ok = True
+    npairs = 0
+    for _ in range(40):
+        i = int(rng.integers(r0, max(r0 + 1, r1)))
+        if i >= n_total - 1 or i >= r1:
+            continue
+        js = rng.integers(i + 1, n_total, size=32)
+        rows = x_full[torch.from_numpy(np.concatenate([[i], js])).to(dev)].cpu().numpy().astype(np.float64)
+        for m in ("cosine", "pearson"):
+            ref = O.cdist_rect(rows[:1], rows[1:], m)[0]
+            idx = torch.from_numpy(np.array([parallel.tri_row_offset(n_total, i) + (j - i - 1) - off0 for j in js]))
+            got = res[m][idx.to(dev)].cpu().numpy()
+            ok &= np.allclose(got, ref, rtol=1e-5, atol=0)
+        npairs += 64
+    t_dm, t_agm = tmax(t_d, world, dev), tmax(t_ag, world, dev)
+    pairs = n_total * (n_total - 1) // 2
+    return {"config": 3, "what": "N x 9 kb, k=9 counts -> all-gather -> cosine+pearson triangle, row-block sharded",
+            "ok": allok(ok, world, dev), "n_gpus": world, "n": n_total, "pairs": pairs,
+            "pairs_per_s": pairs / t_dm, "dist_ms": t_dm * 1e3, "allgather_ms": t_agm * 1e3,
+            "allgather_GB_received": (n_total - n_loc) * 4 ** k * 2 / 1e9,
+            "tflops_equiv_per_gpu": 2.0 * 4 ** k * pairs / t_dm / world / 1e12,
+            "repr_vec_per_s": world * n_loc / tmax(t_repr, world, dev), "verified": "%d random pairs/rank vs scipy" % npairs}
+
+
+# ---- config 4 ---------------------------------------------------------------------------------------
+def config4(rank, world, dev, scale):
+    m_total, L, k, c = int(1_000_000 * scale), 150, 6, 1000
+    m = m_total // world
+    chars = gen_chars(dev, m, L, 20261004 + rank)
+    b = pack(dev, chars, m, L)
+    x, t_repr = timed(lambda: R.kmer_vectors(b, k, 16, "counts"), dev, world)
+    # centroids: mean of 1000 groups of 1000 reads drawn with a fixed seed (same on every rank)
+    cchars = gen_chars(dev, c * 100, L, 4242)
+    cb = pack(dev, cchars, c * 100, L)
+    cx = R.kmer_vectors(cb, k, 16, "counts").to(torch.float32).view(c, 100, 4 ** k).mean(dim=1).contiguous()
+    out, t_d = timed(lambda: D.manhattan_rect(x, cx), dev, world)
+    rng = np.random.Generator(np.random.PCG64(3 + rank))
+    ii = rng.integers(0, m, size=100)
+    xs = x[torch.from_numpy(ii).to(dev)].cpu().numpy().astype(np.float64)
+    ref = O.cdist_rect(xs, cx.cpu().numpy().astype(np.float64), "cityblock")
+    ok = np.allclose(out[torch.from_numpy(ii).to(dev)].cpu().numpy(), ref, rtol=1e-5, atol=0)
+    host = chars.cpu().numpy()
+    for i in ii[:32]:
+        ok &= np.array_equal(x[int(i)].cpu().numpy(), O.cgr_count(host[i * L:(i + 1) * L].tobytes(), k, 16))
+    t_dm = tmax(t_d, world, dev)
+    return {"config": 4, "what": "short reads x 150 bp, k=6 counts + float32 L1 to 1k centroids", "ok": allok(ok, world, dev),
+            "n_gpus": world, "reads": m * world, "repr_vec_per_s": world * m / tmax(t_repr, world, dev),
+            "pairs_per_s": world * m * c / t_dm, "dist_ms": t_dm * 1e3, "verified": "100 reads x 1000 centroids/rank vs scipy"}
+
+
+# ---- config 5 ---------------------------------------------------------------------------------------
+def config5(rank, world, dev, scale):
+    n_total, L, k = int(5000 * scale), 5_000_000, 9
+    n = max(1, n_total // world)
+    batch = 128
+    ok = True
+    t_sum = 0.0
+    done = 0
+    ws = R.kmer_workspace(batch, k, dev)
+    out = torch.empty((batch, 4 ** k), dtype=torch.float32, device=dev)
+    for b0 in range(0, n, batch):
+        nb = min(batch, n - b0)
+        chars = gen_chars(dev, nb, L, 20261005 + rank * 100003 + b0)
+        pb = pack(dev, chars, nb, L)
+        _, t = timed(lambda: R.kmer_vectors(pb, k, 16, "freq32", out_tensor=out[:nb], workspace=ws), dev, 1)
+        t_sum += t
+        done += nb
+        if b0 == 0:
+            rec = chars[:L].cpu().numpy().tobytes()
+            ref = O.frequencies(O.cgr_count(rec, k, 16)).astype(np.float32)
+            ok &= np.allclose(out[0].cpu().numpy(), ref, rtol=1e-6, atol=0)
+        del chars, pb
+    tm = tmax(t_sum, world, dev)
+    return {"config": 5, "what": "bacterial-scale sequences x 5 Mb, k=9 float32 CGR vectors, sharded by sequence",
+            "ok": allok(ok, world, dev), "n_gpus": world, "n": done * world, "seq_per_s": world * done / tm,
+            "kmers_per_s": world * done * L / tm, "ms": tm * 1e3, "verified": "first sequence of each rank vs oracle"}
+
+
+CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, nargs="+", default=[1, 2, 4, 5])
+    ap.add_argument("--scale", type=float, default=1.0)
+    args = ap.parse_args()
+    rank, world, dev = ctx()
+    for c in args.config:
+        t0 = time.time()
+        r = CONFIGS[c](rank, world, dev, args.scale)
+        torch.cuda.empty_cache()
+        if rank == 0:
+            r["wall_s"] = round(time.time() - t0, 1)
+            print(json.dumps(r), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
