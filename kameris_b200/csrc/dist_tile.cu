@@ -30,8 +30,10 @@ constexpr int STAGES = 4;
 
 template <int OP>
 struct OpT {
-    static constexpr int RM = (OP == OP_JACC || OP == OP_DOT) ? 4 : 8;
-    static constexpr int NACC = (OP == OP_JACC) ? 2 : 1;
+    static constexpr int RM = (OP == OP_JACC || OP == OP_DOT || OP == OP_L1F32) ? 4 : 8;
+    // float L1 keeps a per-stage partial (acc[0]) and the running total (acc[1]): two-level summation
+    // holds the float32 result within ~1e-6 relative over thousands of terms
+    static constexpr int NACC = (OP == OP_JACC || OP == OP_L1F32) ? 2 : 1;
     using acc_t = typename std::conditional<OP == OP_L1F32, float,
                   typename std::conditional<OP == OP_DOT, unsigned long long, uint32_t>::type>::type;
     using out_t = typename std::conditional<OP == OP_JACC || OP == OP_L1F32, float, uint32_t>::type;
@@ -120,6 +122,15 @@ __global__ void __launch_bounds__(DT_THREADS) pair_tile_kernel(const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 8; ++j) pair_op<OP>(acc[i][j], a[i], b[j]);
         }
+        if constexpr (OP == OP_L1F32) {
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc[i][j][NACC - 1] += acc[i][j][0];
+                    acc[i][j][0] = 0;
+                }
+        }
         __syncthreads();   // every thread is done with stage s
         if (tid == 0 && it + STAGES < n_it) {
             const uint32_t nx = it + STAGES;
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(DT_THREADS) pair_tile_kernel(const __grid_cons
                 const uint32_t U = acc[i][j][0], X = acc[i][j][1];
                 out[base + c] = U == 0 ? 0.0f : __fmul_rn(__fdiv_rn(1.0f, (float)U), (float)X);
             } else {
-                out[base + c] = acc[i][j][0];
+                out[base + c] = acc[i][j][NACC - 1];
             }
         }
     }
