@@ -149,6 +149,9 @@ int kam_info_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
  * is not requested) receive float32 triangles.  euclid_on_freq != 0 computes euclidean distance
  * between the frequency vectors x_i/sum(x_i) (what a `frequencies` .mm-repr holds). */
 size_t kam_gram_workspace_bytes(uint32_t n, uint64_t d);
+/* workspace for inputs outside the tensor-exact envelope (integer CUDA-core Gram; 4 B per element).
+ * kam_gram_tri returns KAM_E_WORKSPACE when it needs this size and was given less. */
+size_t kam_gram_workspace_bytes_int(uint32_t n, uint64_t d);
 /* test hook: non-zero forces the fp16 (kind::f16) tensor path where the uint8 (kind::i8) path would
  * be chosen; both are exact inside their envelopes. */
 void kam_gram_force_f16(int on);

@@ -40,6 +40,7 @@ SIGNATURES = {
     "kam_info_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p, c_void_p,
                              c_size_t, c_void_p]),
     "kam_gram_workspace_bytes": (c_size_t, [c_uint32, c_uint64]),
+    "kam_gram_workspace_bytes_int": (c_size_t, [c_uint32, c_uint64]),
     "kam_gram_force_f16": (None, [c_int]),
     "kam_gram_set_cluster": (None, [c_int]),
     "kam_gram_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, ctypes.c_uint,
@@ -69,6 +70,9 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+KAM_E_WORKSPACE = -3
 
 
 def check(rc):

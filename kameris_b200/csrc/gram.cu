@@ -391,7 +391,8 @@ inline size_t max_tiles(uint32_t n) {
     return tr * tc;
 }
 
-inline size_t gram_layout(uint32_t n, uint64_t d, void *base, GramWs *w) {
+// with_int: also reserve room for the integer-fallback operand (4 bytes per element, much larger)
+inline size_t gram_layout(uint32_t n, uint64_t d, void *base, GramWs *w, bool with_int) {
     size_t off = 0;
     auto take = [&](size_t bytes) {
         void *p = base ? (char *)base + off : nullptr;
@@ -403,7 +404,7 @@ inline size_t gram_layout(uint32_t n, uint64_t d, void *base, GramWs *w) {
     void *rk = take((size_t)n * sizeof(RowK));
     void *tiles = take(max_tiles(n) * sizeof(uint2));
     // the fp16 matrix and the integer-fallback operand are never live together: share the space
-    const size_t hb = (size_t)n * dpad_of(d) * 2, ib = kam_int_gram_xt_bytes(n, d);
+    const size_t hb = (size_t)n * dpad_of(d) * 2, ib = with_int ? kam_int_gram_xt_bytes(n, d) : 0;
     void *big = take(hb > ib ? hb : ib);
     if (w) {
         w->flags = (unsigned long long *)flags;
@@ -481,7 +482,8 @@ int launch_gram(const GramWs &w, size_t n_tiles, uint32_t n, uint64_t d, uint32_
 
 extern "C" {
 
-size_t kam_gram_workspace_bytes(uint32_t n, uint64_t d) { return gram_layout(n, d, nullptr, nullptr); }
+size_t kam_gram_workspace_bytes(uint32_t n, uint64_t d) { return gram_layout(n, d, nullptr, nullptr, false); }
+size_t kam_gram_workspace_bytes_int(uint32_t n, uint64_t d) { return gram_layout(n, d, nullptr, nullptr, true); }
 
 int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin, uint32_t row_end,
                  unsigned metrics, int euclid_on_freq, float *d_tri_euclid, float *d_tri_cosine, float *d_tri_pearson,
@@ -501,7 +503,7 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     }
     cudaStream_t st = (cudaStream_t)stream;
     GramWs w;
-    gram_layout(n, d, d_ws, &w);
+    gram_layout(n, d, d_ws, &w, false);
     GramOut go;
     go.euclid = (metrics & KAM_M_EUCLID) ? d_tri_euclid : nullptr;
     go.cosine = (metrics & KAM_M_COSINE) ? d_tri_cosine : nullptr;
@@ -526,8 +528,15 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     const bool use_f16 = !use_i8 && hflags[0] <= MAX_F16_COUNT && hflags[1] < MAX_F16_GII;
     rowk_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.S, w.G, n, (double)d, euclid_on_freq, w.rk);
     KAM_CUDA(cudaGetLastError());
-    if (!use_i8 && !use_f16)
+    if (!use_i8 && !use_f16) {
+        if (ws_bytes < kam_gram_workspace_bytes_int(n, d)) {
+            kam_set_error("kam_gram_tri: counts outside the tensor-exact envelope (max count %llu, max sum of squares "
+                          "%llu) need the integer path: pass a workspace of kam_gram_workspace_bytes_int()",
+                          hflags[0], hflags[1]);
+            return KAM_E_WORKSPACE;
+        }
         return kam_int_gram_tri(d_x, elem, n, d, ld, row_begin, row_end, w.rk, go, w.xt, st);
+    }
 
     // upper-triangular tile list.  A list entry is (row-tile group, column tile); a group is CL
     // consecutive 128-row tiles handled by the CL CTAs of a cluster.  Strips of ~12 row tiles,

@@ -71,7 +71,7 @@ extern "C" int kam_dists_host(const void *h_x, int elem, uint32_t n, uint64_t d,
     const unsigned gm = metrics & (KAM_M_EUCLID | KAM_M_COSINE | KAM_M_PEARSON);
     if (gm) {
         Buf t2, t3;
-        const size_t wb = kam_gram_workspace_bytes(n, d);
+        size_t wb = kam_gram_workspace_bytes(n, d);
         if ((rc = ws.alloc(wb))) return rc;
         float *pe = (float *)tri.p, *pc = nullptr, *pp = nullptr;
         if (gm & KAM_M_COSINE) {
@@ -84,7 +84,15 @@ extern "C" int kam_dists_host(const void *h_x, int elem, uint32_t n, uint64_t d,
         }
         // a `frequencies` file cannot be an input here (integer counts are required), so euclid is
         // the distance between the count vectors, like scipy euclidean on the rows of the file
-        if ((rc = kam_gram_tri(x.p, elem, n, d, d, 0, n, gm, 0, pe, pc, pp, ws.p, wb, st))) return rc;
+        rc = kam_gram_tri(x.p, elem, n, d, d, 0, n, gm, 0, pe, pc, pp, ws.p, wb, st);
+        if (rc == KAM_E_WORKSPACE) {   // outside the tensor-exact envelope: the integer path needs more room
+            cudaFree(ws.p);
+            ws.p = nullptr;
+            wb = kam_gram_workspace_bytes_int(n, d);
+            if ((rc = ws.alloc(wb))) return rc;
+            rc = kam_gram_tri(x.p, elem, n, d, d, 0, n, gm, 0, pe, pc, pp, ws.p, wb, st);
+        }
+        if (rc) return rc;
         if (gm & KAM_M_EUCLID) KAM_CUDA(cudaMemcpyAsync(h_euclid, pe, pairs * 4, cudaMemcpyDeviceToHost, st));
         if (gm & KAM_M_COSINE) KAM_CUDA(cudaMemcpyAsync(h_cosine, pc, pairs * 4, cudaMemcpyDeviceToHost, st));
         if (gm & KAM_M_PEARSON) KAM_CUDA(cudaMemcpyAsync(h_pearson, pp, pairs * 4, cudaMemcpyDeviceToHost, st));

@@ -112,13 +112,18 @@ def gram_tri(x, metrics=("euclid", "cosine", "pearson"), euclid_on_freq=True, ro
     for m in metrics:
         mask |= bits[m]
         outs[m] = torch.zeros(max(tri_len(n), 1), dtype=torch.float32, device=dev)
-    ws = torch.empty(max(lib.kam_gram_workspace_bytes(n, d), 256), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         lib.kam_gram_force_f16(int(force_f16))         # test hook: fp16 tensor path instead of uint8
         try:
-            check(lib.kam_gram_tri(_ptr(x), _ELEM[x.dtype], n, d, x.stride(0), r0, r1, mask, int(euclid_on_freq),
-                                   _ptr(outs.get("euclid")), _ptr(outs.get("cosine")), _ptr(outs.get("pearson")),
-                                   _ptr(ws), ws.numel(), _stream(dev)))
+            for size_fn in (lib.kam_gram_workspace_bytes, lib.kam_gram_workspace_bytes_int):
+                ws = torch.empty(max(size_fn(n, d), 256), dtype=torch.uint8, device=dev)
+                rc = lib.kam_gram_tri(_ptr(x), _ELEM[x.dtype], n, d, x.stride(0), r0, r1, mask, int(euclid_on_freq),
+                                      _ptr(outs.get("euclid")), _ptr(outs.get("cosine")), _ptr(outs.get("pearson")),
+                                      _ptr(ws), ws.numel(), _stream(dev))
+                if rc != _lib.KAM_E_WORKSPACE:     # the integer fallback asks for its (larger) workspace
+                    break
+                del ws
+            check(rc)
         finally:
             lib.kam_gram_force_f16(0)
     return {m: t[:tri_len(n)] for m, t in outs.items()}

@@ -111,10 +111,15 @@ def _compute_cuda(x_full, metrics, rows, tri_offset, slice_len):
                 t, p = sliced(torch.float32)
                 out[m], ptrs[m] = t[:slice_len], p
                 mask |= bits[m]
-            ws = torch.empty(max(lib.kam_gram_workspace_bytes(n, d), 256), dtype=torch.uint8, device=dev)
-            _lib.check(lib.kam_gram_tri(x_full.data_ptr(), elem, n, d, x_full.stride(0), rows[0], rows[1], mask, 1,
-                                        ptrs.get("euclid"), ptrs.get("cosine"), ptrs.get("pearson"), ws.data_ptr(),
-                                        ws.numel(), stream))
+            for size_fn in (lib.kam_gram_workspace_bytes, lib.kam_gram_workspace_bytes_int):
+                ws = torch.empty(max(size_fn(n, d), 256), dtype=torch.uint8, device=dev)
+                rc = lib.kam_gram_tri(x_full.data_ptr(), elem, n, d, x_full.stride(0), rows[0], rows[1], mask, 1,
+                                      ptrs.get("euclid"), ptrs.get("cosine"), ptrs.get("pearson"), ws.data_ptr(),
+                                      ws.numel(), stream)
+                if rc != _lib.KAM_E_WORKSPACE:
+                    break
+                del ws
+            _lib.check(rc)
     return out
 
 
