@@ -232,9 +232,16 @@ __global__ void manhat_serial_kernel(const T *__restrict__ x, uint32_t n, uint64
     const T *a = x + (uint64_t)i * ld, *b = x + (uint64_t)j * ld;
     uint32_t acc = 0;
     for (uint64_t e = 0; e < d; ++e) {
-        if constexpr (std::is_floating_point<T>::value) {
-            const T t = a[e] - b[e];
-            acc = (uint32_t)(long long)((double)acc + (double)(t < 0 ? -t : t));
+        if constexpr (std::is_same<T, float>::value) {
+            // single-precision sum, truncating conversion through int64 (generation_dists T=float,
+            // windows_avx2 VA 0x140027a20: vcvtsi2ss / vsubss / vaddss / vcvttss2si)
+            const float t = __fsub_rn(a[e], b[e]);
+            const float m = b[e] > a[e] ? -t : t;
+            acc = (uint32_t)__float2ll_rz(__fadd_rn(__uint2float_rn(acc), m));
+        } else if constexpr (std::is_same<T, double>::value) {
+            const double t = __dsub_rn(a[e], b[e]);
+            const double m = b[e] > a[e] ? -t : t;
+            acc = (uint32_t)__double2ll_rz(__dadd_rn((double)acc, m));
         } else {
             acc += (uint32_t)(a[e] > b[e] ? a[e] - b[e] : b[e] - a[e]);
         }

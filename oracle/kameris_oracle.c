@@ -18,9 +18,12 @@
  *       The same values reproduce SURVEY.md Appendix B (demo genomes, quirk cases Q1/Q3/Q4).
  *   frequencies: numpy true division as written in backend.py:49 (executed by numpy itself in
  *       oracle.py; the C twin here is checked against it).
- *   manhat / info: PARITY UNPINNED -- the row loops are inlined in non-leaf lambdas of
- *       generation_dists and could not be executed here; restated from disassembly
- *        and checked only against Appendix B values and scipy cityblock / jaccard.
+ *   manhat / info (orc_manhat_*, orc_info_*): PINNED against tests/golden/refcode_dists.json.gz --
+ *       48 cases produced by the reference's OWN machine code: the six per-element-type row lambdas
+ *       of generation_dists_windows_avx2.exe (VA 0x140024610 ... 0x140027d50) mapped at their image
+ *       base and called in-process by oracle/refcode/refdists.c (generator gen_golden_dists.py).
+ *       This corrected the restatement once: for T=float the truncating sum is formed in single
+ *       precision (SURVEY.md A.6 describes the double instance only).
  *   euclid / cosine / pearson: not in the reference at all; defined as scipy cdist (oracle.py).
  *
  * Each function cites the reference location it follows:
@@ -115,8 +118,8 @@ void orc_freq_u32(const uint32_t *count, size_t d, double *out) {
  * A.6  manhat.   dists@0x10001be4e-0x10001bf62 (integer T), dists@0x10001dcd1-0x10001dd71 (fp T)
  *   uint32 acc = 0; for d: acc += (T)|a_d - b_d|   -- difference taken in 32 bits for
  *   8/16/32-bit T (so u32 differences wrap mod 2^32 before the conditional negate), truncated
- *   to T, added mod 2^32.  For float/double T each step is acc = (uint32)((double)acc + |a-b|)
- *   (truncating conversion, quirk Q5).
+ *   to T, added mod 2^32.  For floating T each step is acc = (uint32)(int64)((T)acc + |a-b|) evaluated
+ *   in T's own precision (float: vaddss, double: vaddsd) with a truncating conversion (quirk Q5).
  * ---------------------------------------------------------------------------------------- */
 uint32_t orc_manhat_u8(const uint8_t *a, const uint8_t *b, size_t d) {
     uint32_t acc = 0;
@@ -145,10 +148,15 @@ uint32_t orc_manhat_u64(const uint64_t *a, const uint64_t *b, size_t d) {
     return acc;
 }
 uint32_t orc_manhat_f32(const float *a, const float *b, size_t d) {
+    /* T=float instance (generation_dists_windows_avx2.exe VA 0x140027a20-0x140027ad3): the sum is
+     * formed in SINGLE precision -- vcvtsi2ss (float)acc, vsubss, conditional sign flip, vaddss,
+     * vcvttss2si to int64, low 32 bits kept. */
     uint32_t acc = 0;
     for (size_t i = 0; i < d; i++) {
-        float t = a[i] - b[i];
-        acc = (uint32_t)(int64_t)((double)acc + (double)(t < 0 ? -t : t));
+        volatile float t = a[i] - b[i];
+        volatile float m = (b[i] > a[i]) ? -t : t;
+        volatile float s = (float)acc + m;
+        acc = (uint32_t)(int64_t)s;
     }
     return acc;
 }

@@ -7,8 +7,9 @@ TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's c
 Reference anchors: generation_cgr_mac_avx2 @0x10000d330 (CGR fill),
 generation_dists_mac_avx2 @0x10001b8c0 (row lambda), kameris/job_steps/backend.py:42-56
 (frequencies).  Pinning: CGR counts against tests/golden/refcode_cgr.json.gz (outputs of the
-reference's own machine code, oracle/refcode/); manhat/info have no executable pin
-("parity unpinned" beyond disassembly + SURVEY.md Appendix B values); euclid/cosine/pearson do not
+reference's own machine code, oracle/refcode/); manhat/info against
+tests/golden/refcode_dists.json.gz (outputs of the reference's own row-lambda machine code, all six
+element types); euclid/cosine/pearson do not
 exist in the reference and are defined as scipy.spatial.distance.cdist in float64.
 """
 import ctypes

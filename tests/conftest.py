@@ -33,3 +33,25 @@ def demo_records():
         with open(os.path.join(d, n), "rb") as f:
             out.append((n, O.fasta_record0(f.read())))
     return out
+
+
+@pytest.fixture(scope="session")
+def refcode_dists_cases():
+    """Outputs of the reference's own manhat/info row-loop machine code (oracle/refcode/gen_golden_dists.py)."""
+    import base64
+    import numpy as np
+    from oracle import oracle as O
+    with gzip.open(os.path.join(GOLDEN, "refcode_dists.json.gz")) as f:
+        cases = json.loads(f.read())["cases"]
+    gdir = os.path.join(GOLDEN, "hiv1-genomes")
+    recs = [O.fasta_record0(open(os.path.join(gdir, n), "rb").read()) for n in sorted(os.listdir(gdir))]
+    out = []
+    for c in cases:
+        dt = np.dtype(O.ELEM_DTYPES[c["elem"]])
+        if c["x"] is None:                     # demo genomes: inputs come from the CGR-pinned oracle
+            x = np.stack([O.cgr_count(r, c["demo_k"], 16) for r in recs])
+        else:
+            x = np.frombuffer(base64.b64decode(c["x"]), dtype=dt).reshape(c["shape"]).copy()
+        out.append((c["name"], x, np.array(c["manhat"], dtype=np.uint32),
+                    np.array(c["info_bits"], dtype=np.uint32).view(np.float32)))
+    return out

@@ -33,6 +33,17 @@ def _counts(n, L, k, seed, bits=16):
     return np.stack([O.cgr_count(r, k, bits) for r in recs])
 
 
+def test_golden_reference_machine_code(D, refcode_dists_cases):
+    """CUDA manhat / info == outputs of the reference's own row-lambda machine code (all six element
+    types; wraps, all-zero rows, float truncation quirk)."""
+    for name, x, man, inf in refcode_dists_cases:
+        xd = _dev(x)
+        got_m = D.manhattan_tri(xd).cpu().numpy().view(np.uint32)
+        got_i = D.info_tri(xd).cpu().numpy()
+        assert np.array_equal(got_m, man), name
+        assert np.array_equal(got_i.view(np.uint32), inf.view(np.uint32)), name
+
+
 def test_demo_k6_appendix_b(D, demo_records):
     x = np.stack([O.cgr_count(r, 6) for _, r in demo_records])
     man = D.manhattan_tri(_dev(x)).cpu().numpy().view(np.uint32)

@@ -105,3 +105,16 @@ def test_pyramid_identity(demo_records):
         pooled = hi.reshape(2 ** k, 2, 2 ** k, 2).sum(axis=(1, 3))
         diff = lo - pooled
         assert diff.sum() == 1 and (diff != 0).sum() == 1
+
+
+def test_oracle_dists_match_reference_machine_code(refcode_dists_cases):
+    """manhat (uint32) and info (float32 bit patterns) == outputs of the reference's own row lambdas,
+    for all six element types, every SIMD/scalar code path, uint32 wrap and the float quirk Q5."""
+    assert len(refcode_dists_cases) >= 45
+    seen = set()
+    for name, x, man, inf in refcode_dists_cases:
+        m, f = O.dists_triangle(x, True, True)
+        assert np.array_equal(m, man), name
+        assert np.array_equal(f.view(np.uint32), inf.view(np.uint32)), name
+        seen.add(x.dtype.str)
+    assert len(seen) == 6
