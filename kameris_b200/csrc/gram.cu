@@ -11,17 +11,22 @@
 //             = sqrt(G_ii/S_i^2 + G_jj/S_j^2 - 2 G_ij/(S_i S_j)) on frequencies x/sum(x)
 // with S_i = sum of row i, D = number of bins.
 //
-// Exactness: counts <= 2048 are exact in fp16 and every partial sum of a Gram entry is a
-// non-negative integer bounded by max_i G_ii; when that bound is < 2^24 the fp32 accumulation in
-// TMEM is EXACT, so G is the exact integer Gram matrix and the only rounding is the float64
-// epilogue + the final float32 store.  Inputs outside that envelope (counts > 2048, or
-// max G_ii >= 2^24) take an exact integer CUDA-core Gram kernel instead (dist_tile.cu, OP_DOT).
+// Exactness: every partial sum of a Gram entry is a non-negative integer bounded by max_i G_ii.
+//   kind::i8  : counts <= 255 are exact uint8 operands, int32 accumulation is exact while
+//               max G_ii < 2^31 (the usual case for k-mer counts: half the operand bytes and twice
+//               the MMA rate of fp16);
+//   kind::f16 : counts <= 2048 are exact in fp16, fp32 accumulation is exact while max G_ii < 2^24.
+// Inside its envelope each path produces the exact integer Gram matrix; the only rounding is the
+// float64 epilogue + the final float32 store.  Inputs outside both envelopes take an exact integer
+// CUDA-core Gram kernel instead (dist_tile.cu, OP_DOT).  The pre-pass measures the envelope.
 //
-// Kernel (gram_tcgen05_kernel): persistent, one CTA per SM, 192 threads:
-//   warp 0    TMA producer   : 128x64 (A) and 256x64 (B) fp16 boxes, SWIZZLE_128B, 4-stage ring
-//   warp 1    MMA issuer     : tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, fp32 in TMEM,
-//                              two 256-column accumulators so the epilogue of tile t overlaps the
-//                              MMAs of tile t+1; tcgen05.commit releases smem stages / publishes TMEM
+// Kernel (gram_tcgen05_kernel<I8, CL>): persistent, one CTA per SM in clusters of CL=2, 192 threads:
+//   warp 0    TMA producer   : 128-row A box + its half of the 256-row B panel (multicast to both
+//                              CTAs of the cluster), 128 bytes of K per row, SWIZZLE_128B, 4-stage ring
+//   warp 1    MMA issuer     : tcgen05.mma.cta_group::1.kind::{i8,f16}, M=128 N=256 K=32 bytes, int32 /
+//                              fp32 accumulators in TMEM, two 256-column accumulators so the epilogue
+//                              of tile t overlaps the MMAs of tile t+1; tcgen05.commit (multicast)
+//                              releases smem stages in both CTAs / publishes TMEM
 //   warps 2-5 epilogue       : tcgen05.ld 32x32b -> float64 distance formulas -> packed triangle
 // Only tiles that contain a pair i<j are scheduled (upper triangle).
 #include <vector>
