@@ -163,6 +163,30 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                  float *d_tri_euclid, float *d_tri_cosine, float *d_tri_pearson, void *d_ws,
                  size_t ws_bytes, void *stream);
 
+/* Block interface for multi-GPU runs (kameris_b200/parallel.py): every rank converts ITS rows once
+ * (kam_gram_prepare), the ranks exchange operand rows and row statistics, and each rank computes the
+ * blocks it owns.  operand_kind is global: KAM_GRAM_U8 needs every count <= 255 and every row's sum
+ * of squares < 2^31, KAM_GRAM_F16 needs <= 2048 and < 2^24 (d_flags[0..1] receive, by atomicMax, the
+ * largest count and the largest sum of squares seen; the caller zeroes them and reduces over ranks).
+ * Operand rows are kam_gram_dpad(d) elements long (uint8 or fp16), zero padded. */
+#define KAM_GRAM_U8 0
+#define KAM_GRAM_F16 1
+uint64_t kam_gram_dpad(uint64_t d);
+int kam_gram_prepare(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, int operand_kind,
+                     void *d_operand, uint64_t *d_S, uint64_t *d_G, uint64_t *d_flags, void *stream);
+size_t kam_gram_block_workspace_bytes(uint32_t n_a, uint32_t n_b);
+/* rows [row_begin,row_end) of A against all rows of B.  triangular != 0: A and B are the same
+ * matrix and only pairs j > i are written.  out_ld == 0 (triangular only): packed triangle of n_a;
+ * otherwise dense row-major output, out[i*out_ld + j]. */
+int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_G_a, uint32_t n_a,
+                   const void *d_op_b, const uint64_t *d_S_b, const uint64_t *d_G_b, uint32_t n_b,
+                   int operand_kind, uint64_t d, int triangular, uint32_t row_begin, uint32_t row_end,
+                   unsigned metrics, int euclid_on_freq, float *d_out_euclid, float *d_out_cosine,
+                   float *d_out_pearson, uint64_t out_ld, void *d_ws, size_t ws_bytes, void *stream);
+/* tuning hook: number of SMs the Gram kernel may occupy (0 = all); the rest stay free for
+ * concurrent NCCL transfers. */
+void kam_gram_set_sm_limit(int sms);
+
 /* Host-buffer form of the whole `distances` step: x is the n x d matrix read from a .mm-repr,
  * outputs are packed triangles (NULL = not requested).  euclid is taken between the rows as
  * stored (counts).  Blocking; allocates and frees its device buffers. */

@@ -14,6 +14,7 @@ c_void_p, c_size_t, c_int, c_uint32, c_uint64 = (ctypes.c_void_p, ctypes.c_size_
 KAM_U8, KAM_U16, KAM_U32, KAM_U64, KAM_F32, KAM_F64 = range(6)
 KAM_OUT_COUNTS, KAM_OUT_FREQ_F32, KAM_OUT_FREQ_F64 = 0, 1, 2
 KAM_M_MANHAT, KAM_M_INFO, KAM_M_EUCLID, KAM_M_COSINE, KAM_M_PEARSON = 1, 2, 4, 8, 16
+KAM_GRAM_U8, KAM_GRAM_F16 = 0, 1
 
 # every symbol include/kameris_b200.h declares: (restype, argtypes)
 SIGNATURES = {
@@ -43,6 +44,14 @@ SIGNATURES = {
     "kam_gram_workspace_bytes_int": (c_size_t, [c_uint32, c_uint64]),
     "kam_gram_force_f16": (None, [c_int]),
     "kam_gram_set_cluster": (None, [c_int]),
+    "kam_gram_dpad": (c_uint64, [c_uint64]),
+    "kam_gram_prepare": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
+    "kam_gram_block_workspace_bytes": (c_size_t, [c_uint32, c_uint32]),
+    "kam_gram_block": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_uint32, c_int,
+                               c_uint64, c_int, c_uint32, c_uint32, ctypes.c_uint, c_int, c_void_p, c_void_p, c_void_p,
+                               c_uint64, c_void_p, c_size_t, c_void_p]),
+    "kam_gram_set_sm_limit": (None, [c_int]),
     "kam_gram_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, ctypes.c_uint,
                              c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "kam_dists_host": (c_int, [c_void_p, c_int, c_uint32, c_uint64, ctypes.c_uint, c_void_p, c_void_p, c_void_p,

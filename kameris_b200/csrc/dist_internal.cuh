@@ -16,7 +16,16 @@ struct RowK {
 };
 
 struct GramOut {
-    float *euclid, *cosine, *pearson;   // packed triangles; nullptr = not requested
+    float *euclid, *cosine, *pearson;   // nullptr = not requested
+};
+
+// geometry of one Gram block: rows of matrix A against rows of matrix B
+struct GramGeom {
+    uint32_t n_a, n_b;            // rows of A (block rows) and of B (block columns)
+    uint32_t row_begin, row_end;  // the A rows this launch writes
+    uint32_t tri;                 // 1: A and B are the same matrix, only pairs j > i exist
+    unsigned long long ld;        // 0: packed strict upper triangle of n_a (tri only); else dense row stride
+    const RowK *rk_a, *rk_b;      // per-row constants of A's and B's rows
 };
 
 #ifdef __CUDACC__

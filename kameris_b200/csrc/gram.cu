@@ -116,9 +116,7 @@ template <bool I8, int CL>
 __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const uint2 *__restrict__ tiles, uint32_t n_tiles,
-                                                                    uint32_t k_iters, uint32_t n, uint32_t row_begin,
-                                                                    uint32_t row_end, const RowK *__restrict__ rowk,
-                                                                    GramOut go) {
+                                                                    uint32_t k_iters, GramGeom gg, GramOut go) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B: 1024-B aligned
     RowK *colk = reinterpret_cast<RowK *>(smem + G_STAGES * STAGE_BYTES);                 // [BN]
@@ -171,8 +169,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
                     tma_load_2d(sa, &tmA, kc, (int32_t)(bi * BM), &full[stage]);
                     if constexpr (CL == 1) {
                         tma_load_2d(sa + A_BYTES, &tmB, kc, (int32_t)(tile.y * BN), &full[stage]);
-                    } else {   // my half of the B panel, to both CTAs (tmA's 128-row box)
-                        tma_load_2d_mc(sa + A_BYTES + crank * (B_BYTES / CL), &tmA, kc,
+                    } else {   // my half of the B panel, to both CTAs (tmB has a BN/CL-row box)
+                        tma_load_2d_mc(sa + A_BYTES + crank * (B_BYTES / CL), &tmB, kc,
                                        (int32_t)(tile.y * BN + crank * (BN / CL)), &full[stage], CMASK);
                     }
                     if (++stage == G_STAGES) {
@@ -223,27 +221,29 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
             for (uint32_t c = et; c < (uint32_t)BN; c += 128) {
                 RowK z;
                 z.rn = z.S = z.mu = z.rp = z.a = z.q = 0.0;
-                colk[c] = (c0 + c < n) ? rowk[c0 + c] : z;
+                colk[c] = (c0 + c < gg.n_b) ? gg.rk_b[c0 + c] : z;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t row = r0 + q * 32 + lane;
-            const bool row_ok = row < n && row >= row_begin && row < row_end;
+            const bool row_ok = row < gg.n_a && row >= gg.row_begin && row < gg.row_end;
             RowK ri;
             ri.rn = ri.S = ri.mu = ri.rp = ri.a = ri.q = 0.0;
-            if (row_ok) ri = rowk[row];
-            const long long base = (long long)n * row - (long long)row * (row + 3) / 2 - 1;
+            if (row_ok) ri = gg.rk_a[row];
+            const long long base = gg.ld ? (long long)row * (long long)gg.ld
+                                         : (long long)gg.n_a * row - (long long)row * (row + 3) / 2 - 1;
             for (uint32_t ch = 0; ch < (uint32_t)BN / 32; ++ch) {
                 const uint32_t cb = c0 + ch * 32;
-                if (cb + 31 <= r0 + q * 32) continue;     // whole chunk on or below the diagonal (warp-uniform)
+                if (gg.tri && cb + 31 <= r0 + q * 32) continue;   // whole chunk on or below the diagonal (warp-uniform)
+                if (cb >= gg.n_b) continue;                         // whole chunk past the last column
                 uint32_t v[32];
                 tmem_ld32(tmem_base + acc * BN + ch * 32 + ((q * 32) << 16), v);
                 if (row_ok) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const uint32_t j = cb + c;
-                        if (j <= row || j >= n) continue;
+                        if (j >= gg.n_b || (gg.tri && j <= row)) continue;
                         const double g = I8 ? (double)(int)v[c] : (double)__uint_as_float(v[c]);
                         const RowK cj = colk[ch * 32 + c];
                         gram_store(go, base + j, g, ri, cj);
@@ -380,6 +380,95 @@ __global__ void rowk_kernel(const unsigned long long *__restrict__ S, const unsi
 
 bool g_force_f16 = false;
 uint32_t g_cluster = 2;
+uint32_t g_sm_limit = 0;   // 0 = all SMs; otherwise leave the rest to concurrent work (e.g. NCCL transfers)
+
+inline uint64_t dpad_of(uint64_t d) { return (d + BK_BYTES - 1) / BK_BYTES * BK_BYTES; }   // elements (either width)
+
+inline size_t max_tiles(uint32_t n_a, uint32_t n_b) {
+    return ((size_t)(n_a + BM - 1) / BM + 1) * ((size_t)(n_b + BN - 1) / BN);
+}
+
+template <typename T>
+int run_prepass(const void *x, uint32_t n, uint64_t d, uint64_t ld, bool i8, void *h, unsigned long long *S,
+                unsigned long long *G, unsigned long long *flags, cudaStream_t st) {
+    const uint64_t dpad = dpad_of(d);
+    const int vec_ok = (d % 16 == 0) && ((ld * sizeof(T)) % 16 == 0) && (((uintptr_t)x & 15) == 0);
+    if (i8)
+        gram_prepass_kernel<T, uint8_t><<<n, 256, 0, st>>>((const T *)x, n, d, ld, dpad, (uint8_t *)h, S, G, flags, vec_ok);
+    else
+        gram_prepass_kernel<T, __half><<<n, 256, 0, st>>>((const T *)x, n, d, ld, dpad, (__half *)h, S, G, flags, vec_ok);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+int prepass_dispatch(const void *x, int elem, uint32_t n, uint64_t d, uint64_t ld, bool i8, void *h,
+                     unsigned long long *S, unsigned long long *G, unsigned long long *flags, cudaStream_t st) {
+    return elem == KAM_U8    ? run_prepass<uint8_t>(x, n, d, ld, i8, h, S, G, flags, st)
+           : elem == KAM_U16 ? run_prepass<uint16_t>(x, n, d, ld, i8, h, S, G, flags, st)
+                             : run_prepass<uint32_t>(x, n, d, ld, i8, h, S, G, flags, st);
+}
+
+template <bool I8, int CL>
+int launch_gram(const void *opA, const void *opB, const uint2 *d_tiles, size_t n_tiles, uint64_t d,
+                const GramGeom &gg, GramOut go, cudaStream_t st) {
+    const uint64_t dpad = dpad_of(d);
+    const uint32_t esz = I8 ? 1 : 2, bk = BK_BYTES / esz;
+    const CUtensorMapDataType dt = I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUtensorMap tmA, tmB;
+    int rc;
+    if ((rc = kam_make_tmap_2d(&tmA, dt, esz, opA, dpad, gg.n_a, dpad * esz, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = kam_make_tmap_2d(&tmB, dt, esz, opB, dpad, gg.n_b, dpad * esz, bk, BN / CL, CU_TENSOR_MAP_SWIZZLE_128B)))
+        return rc;
+    const size_t smem = (size_t)G_STAGES * STAGE_BYTES + BN * sizeof(RowK) + 1024;
+    auto kern = gram_tcgen05_kernel<I8, CL>;
+    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t sms = (uint32_t)kam_sm_count();
+    if (g_sm_limit && g_sm_limit < sms) sms = g_sm_limit;
+    uint32_t clusters = sms / CL;
+    if (clusters < 1) clusters = 1;
+    if (clusters > n_tiles) clusters = (uint32_t)n_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CL);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    KAM_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, d_tiles, (uint32_t)n_tiles, (uint32_t)(dpad / bk), gg, go));
+    return KAM_OK;
+}
+
+// tile list of one block + launch.  A list entry is (row-tile group, column tile); a group is CL
+// consecutive 128-row tiles handled by the CL CTAs of a cluster.  Strips of ~12 row tiles,
+// column-major inside a strip, so the ~148 tiles in flight share about a dozen A panels and a
+// dozen B panels in L2.
+int gram_block(const void *opA, const void *opB, bool i8, uint64_t d, const GramGeom &gg, GramOut go, uint2 *d_tiles,
+               cudaStream_t st) {
+    const uint32_t CL = g_cluster;
+    std::vector<uint2> tiles;
+    const uint32_t GM = BM * CL;
+    const uint32_t tr0 = gg.row_begin / GM, tr1 = (gg.row_end - 1) / GM + 1, tc = (gg.n_b + BN - 1) / BN;
+    const uint32_t STRIP = 12 / CL;
+    for (uint32_t s0 = tr0; s0 < tr1; s0 += STRIP) {
+        const uint32_t s1 = s0 + STRIP < tr1 ? s0 + STRIP : tr1;
+        for (uint32_t bj = 0; bj < tc; ++bj)
+            for (uint32_t bg = s0; bg < s1; ++bg)
+                if (!gg.tri || (uint64_t)bj * BN + BN - 1 > (uint64_t)bg * GM) tiles.push_back(make_uint2(bg, bj));
+    }
+    if (tiles.empty()) return KAM_OK;
+    KAM_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    KAM_CUDA(cudaStreamSynchronize(st));   // `tiles` is pageable host memory owned by this frame
+    if (CL == 2)
+        return i8 ? launch_gram<true, 2>(opA, opB, d_tiles, tiles.size(), d, gg, go, st)
+                  : launch_gram<false, 2>(opA, opB, d_tiles, tiles.size(), d, gg, go, st);
+    return i8 ? launch_gram<true, 1>(opA, opB, d_tiles, tiles.size(), d, gg, go, st)
+              : launch_gram<false, 1>(opA, opB, d_tiles, tiles.size(), d, gg, go, st);
+}
 
 struct GramWs {
     void *h;
@@ -388,13 +477,6 @@ struct GramWs {
     uint2 *tiles;
     uint32_t *xt;   // integer fallback operand
 };
-
-inline uint64_t dpad_of(uint64_t d) { return (d + BK_BYTES - 1) / BK_BYTES * BK_BYTES; }   // elements (either width)
-
-inline size_t max_tiles(uint32_t n) {
-    const size_t tr = (n + BM - 1) / BM, tc = (n + BN - 1) / BN;
-    return tr * tc;
-}
 
 // with_int: also reserve room for the integer-fallback operand (4 bytes per element, much larger)
 inline size_t gram_layout(uint32_t n, uint64_t d, void *base, GramWs *w, bool with_int) {
@@ -407,7 +489,7 @@ inline size_t gram_layout(uint32_t n, uint64_t d, void *base, GramWs *w, bool wi
     void *flags = take(64);
     void *S = take((size_t)n * 8), *G = take((size_t)n * 8);
     void *rk = take((size_t)n * sizeof(RowK));
-    void *tiles = take(max_tiles(n) * sizeof(uint2));
+    void *tiles = take(max_tiles(n, n) * sizeof(uint2));
     // the fp16 matrix and the integer-fallback operand are never live together: share the space
     const size_t hb = (size_t)n * dpad_of(d) * 2, ib = with_int ? kam_int_gram_xt_bytes(n, d) : 0;
     void *big = take(hb > ib ? hb : ib);
@@ -423,63 +505,9 @@ inline size_t gram_layout(uint32_t n, uint64_t d, void *base, GramWs *w, bool wi
     return off;
 }
 
-template <typename T>
-int run_prepass(const void *x, uint32_t n, uint64_t d, uint64_t ld, const GramWs &w, bool i8, cudaStream_t st) {
-    const uint64_t dpad = dpad_of(d);
-    const int vec_ok = (d % 16 == 0) && ((ld * sizeof(T)) % 16 == 0) && (((uintptr_t)x & 15) == 0);
-    if (i8)
-        gram_prepass_kernel<T, uint8_t><<<n, 256, 0, st>>>((const T *)x, n, d, ld, dpad, (uint8_t *)w.h, w.S, w.G,
-                                                           w.flags, vec_ok);
-    else
-        gram_prepass_kernel<T, __half><<<n, 256, 0, st>>>((const T *)x, n, d, ld, dpad, (__half *)w.h, w.S, w.G,
-                                                          w.flags, vec_ok);
-    KAM_CUDA(cudaGetLastError());
-    return KAM_OK;
-}
-
-int prepass(const void *x, int elem, uint32_t n, uint64_t d, uint64_t ld, const GramWs &w, bool i8,
-            unsigned long long (&hflags)[2], cudaStream_t st) {
-    KAM_CUDA(cudaMemsetAsync(w.flags, 0, 64, st));
-    int rc = elem == KAM_U8    ? run_prepass<uint8_t>(x, n, d, ld, w, i8, st)
-             : elem == KAM_U16 ? run_prepass<uint16_t>(x, n, d, ld, w, i8, st)
-                               : run_prepass<uint32_t>(x, n, d, ld, w, i8, st);
-    if (rc) return rc;
-    KAM_CUDA(cudaMemcpyAsync(hflags, w.flags, 16, cudaMemcpyDeviceToHost, st));
+int read_flags(const unsigned long long *d_flags, unsigned long long (&h)[2], cudaStream_t st) {
+    KAM_CUDA(cudaMemcpyAsync(h, d_flags, 16, cudaMemcpyDeviceToHost, st));
     KAM_CUDA(cudaStreamSynchronize(st));
-    return KAM_OK;
-}
-
-template <bool I8, int CL>
-int launch_gram(const GramWs &w, size_t n_tiles, uint32_t n, uint64_t d, uint32_t row_begin, uint32_t row_end,
-                GramOut go, cudaStream_t st) {
-    const uint64_t dpad = dpad_of(d);
-    const uint32_t esz = I8 ? 1 : 2, bk = BK_BYTES / esz;
-    const CUtensorMapDataType dt = I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    CUtensorMap tmA, tmB;
-    int rc;
-    if ((rc = kam_make_tmap_2d(&tmA, dt, esz, w.h, dpad, n, dpad * esz, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = kam_make_tmap_2d(&tmB, dt, esz, w.h, dpad, n, dpad * esz, bk, BN, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    const size_t smem = (size_t)G_STAGES * STAGE_BYTES + BN * sizeof(RowK) + 1024;
-    auto kern = gram_tcgen05_kernel<I8, CL>;
-    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t clusters = (uint32_t)kam_sm_count() / CL;
-    if (clusters > n_tiles) clusters = (uint32_t)n_tiles;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(clusters * CL);
-    cfg.blockDim = dim3(G_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const uint2 *tiles = w.tiles;
-    const RowK *rk = w.rk;
-    KAM_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tiles, (uint32_t)n_tiles, (uint32_t)(dpad / bk), n, row_begin,
-                                row_end, rk, go));
     return KAM_OK;
 }
 
@@ -489,6 +517,73 @@ extern "C" {
 
 size_t kam_gram_workspace_bytes(uint32_t n, uint64_t d) { return gram_layout(n, d, nullptr, nullptr, false); }
 size_t kam_gram_workspace_bytes_int(uint32_t n, uint64_t d) { return gram_layout(n, d, nullptr, nullptr, true); }
+uint64_t kam_gram_dpad(uint64_t d) { return dpad_of(d); }
+
+int kam_gram_prepare(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, int operand_kind,
+                     void *d_operand, uint64_t *d_S, uint64_t *d_G, uint64_t *d_flags, void *stream) {
+    KAM_REQUIRE(d_x && d_operand && d_S && d_G && d_flags, "null pointer");
+    KAM_REQUIRE(elem == KAM_U8 || elem == KAM_U16 || elem == KAM_U32, "euclid/cosine/pearson take integer count vectors");
+    KAM_REQUIRE(operand_kind == KAM_GRAM_U8 || operand_kind == KAM_GRAM_F16, "bad operand kind");
+    KAM_REQUIRE(d >= 1 && d < (1ull << 32) && ld >= d, "bad d / ld");
+    KAM_REQUIRE(((uintptr_t)d_operand & 15) == 0, "operand must be 16-byte aligned");
+    if (n == 0) return KAM_OK;
+    return prepass_dispatch(d_x, elem, n, d, ld, operand_kind == KAM_GRAM_U8, d_operand, (unsigned long long *)d_S,
+                            (unsigned long long *)d_G, (unsigned long long *)d_flags, (cudaStream_t)stream);
+}
+
+size_t kam_gram_block_workspace_bytes(uint32_t n_a, uint32_t n_b) {
+    return kam_align_up((size_t)n_a * sizeof(RowK), 1024) + kam_align_up((size_t)n_b * sizeof(RowK), 1024) +
+           kam_align_up(max_tiles(n_a, n_b) * sizeof(uint2), 1024);
+}
+
+int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_G_a, uint32_t n_a, const void *d_op_b,
+                   const uint64_t *d_S_b, const uint64_t *d_G_b, uint32_t n_b, int operand_kind, uint64_t d,
+                   int triangular, uint32_t row_begin, uint32_t row_end, unsigned metrics, int euclid_on_freq,
+                   float *d_out_euclid, float *d_out_cosine, float *d_out_pearson, uint64_t out_ld, void *d_ws,
+                   size_t ws_bytes, void *stream) {
+    KAM_REQUIRE(d_op_a && d_op_b && d_S_a && d_G_a && d_S_b && d_G_b && d_ws, "null pointer");
+    KAM_REQUIRE(operand_kind == KAM_GRAM_U8 || operand_kind == KAM_GRAM_F16, "bad operand kind");
+    KAM_REQUIRE((metrics & ~(KAM_M_EUCLID | KAM_M_COSINE | KAM_M_PEARSON)) == 0 && metrics != 0, "bad metrics mask");
+    KAM_REQUIRE(!(metrics & KAM_M_EUCLID) || d_out_euclid, "null euclid output");
+    KAM_REQUIRE(!(metrics & KAM_M_COSINE) || d_out_cosine, "null cosine output");
+    KAM_REQUIRE(!(metrics & KAM_M_PEARSON) || d_out_pearson, "null pearson output");
+    KAM_REQUIRE(!triangular || (d_op_a == d_op_b && n_a == n_b), "a triangular block needs A == B");
+    KAM_REQUIRE(triangular || out_ld >= n_b, "dense output needs out_ld >= n_b");
+    KAM_REQUIRE(out_ld == 0 || out_ld >= n_b, "out_ld smaller than n_b");
+    if (n_a == 0 || n_b == 0 || row_begin >= row_end) return KAM_OK;
+    if (row_end > n_a) row_end = n_a;
+    if (ws_bytes < kam_gram_block_workspace_bytes(n_a, n_b)) {
+        kam_set_error("kam_gram_block: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    RowK *rk_a = (RowK *)d_ws;
+    RowK *rk_b = (RowK *)((char *)d_ws + kam_align_up((size_t)n_a * sizeof(RowK), 1024));
+    uint2 *tiles = (uint2 *)((char *)rk_b + kam_align_up((size_t)n_b * sizeof(RowK), 1024));
+    rowk_kernel<<<(n_a + 255) / 256, 256, 0, st>>>((const unsigned long long *)d_S_a, (const unsigned long long *)d_G_a,
+                                                   n_a, (double)d, euclid_on_freq, rk_a);
+    if (d_op_b != d_op_a || d_S_b != d_S_a)
+        rowk_kernel<<<(n_b + 255) / 256, 256, 0, st>>>((const unsigned long long *)d_S_b,
+                                                       (const unsigned long long *)d_G_b, n_b, (double)d,
+                                                       euclid_on_freq, rk_b);
+    else
+        rk_b = rk_a;
+    KAM_CUDA(cudaGetLastError());
+    GramOut go;
+    go.euclid = (metrics & KAM_M_EUCLID) ? d_out_euclid : nullptr;
+    go.cosine = (metrics & KAM_M_COSINE) ? d_out_cosine : nullptr;
+    go.pearson = (metrics & KAM_M_PEARSON) ? d_out_pearson : nullptr;
+    GramGeom gg;
+    gg.n_a = n_a;
+    gg.n_b = n_b;
+    gg.row_begin = row_begin;
+    gg.row_end = row_end;
+    gg.tri = triangular ? 1u : 0u;
+    gg.ld = out_ld;
+    gg.rk_a = rk_a;
+    gg.rk_b = rk_b;
+    return gram_block(d_op_a, d_op_b, operand_kind == KAM_GRAM_U8, d, gg, go, tiles, st);
+}
 
 int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin, uint32_t row_end,
                  unsigned metrics, int euclid_on_freq, float *d_tri_euclid, float *d_tri_cosine, float *d_tri_pearson,
@@ -522,12 +617,15 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     int rc;
     bool have_i8 = false;
     if (!g_force_f16) {
-        if ((rc = prepass(d_x, elem, n, d, ld, w, true, hflags, st))) return rc;
+        KAM_CUDA(cudaMemsetAsync(w.flags, 0, 64, st));
+        if ((rc = prepass_dispatch(d_x, elem, n, d, ld, true, w.h, w.S, w.G, w.flags, st))) return rc;
+        if ((rc = read_flags(w.flags, hflags, st))) return rc;
         have_i8 = hflags[0] <= MAX_I8_COUNT && hflags[1] < MAX_I8_GII;
     }
-    if (!have_i8) {
-        if (g_force_f16 || (hflags[0] <= MAX_F16_COUNT && hflags[1] < MAX_F16_GII))
-            if ((rc = prepass(d_x, elem, n, d, ld, w, false, hflags, st))) return rc;
+    if (!have_i8 && (g_force_f16 || (hflags[0] <= MAX_F16_COUNT && hflags[1] < MAX_F16_GII))) {
+        KAM_CUDA(cudaMemsetAsync(w.flags, 0, 64, st));
+        if ((rc = prepass_dispatch(d_x, elem, n, d, ld, false, w.h, w.S, w.G, w.flags, st))) return rc;
+        if ((rc = read_flags(w.flags, hflags, st))) return rc;
     }
     const bool use_i8 = have_i8;
     const bool use_f16 = !use_i8 && hflags[0] <= MAX_F16_COUNT && hflags[1] < MAX_F16_GII;
@@ -542,35 +640,19 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
         }
         return kam_int_gram_tri(d_x, elem, n, d, ld, row_begin, row_end, w.rk, go, w.xt, st);
     }
-
-    // upper-triangular tile list.  A list entry is (row-tile group, column tile); a group is CL
-    // consecutive 128-row tiles handled by the CL CTAs of a cluster.  Strips of ~12 row tiles,
-    // column-major inside a strip, so the ~148 tiles in flight share about a dozen A panels and a
-    // dozen B panels in L2.
-    const uint32_t CL = g_cluster;
-    std::vector<uint2> tiles;
-    const uint32_t GM = BM * CL;
-    const uint32_t tr0 = row_begin / GM, tr1 = (row_end - 1) / GM + 1, tc = (n + BN - 1) / BN;
-    const uint32_t STRIP = 12 / CL;
-    for (uint32_t s0 = tr0; s0 < tr1; s0 += STRIP) {
-        const uint32_t s1 = s0 + STRIP < tr1 ? s0 + STRIP : tr1;
-        for (uint32_t bj = 0; bj < tc; ++bj)
-            for (uint32_t bg = s0; bg < s1; ++bg)
-                if ((uint64_t)bj * BN + BN - 1 > (uint64_t)bg * GM) tiles.push_back(make_uint2(bg, bj));
-    }
-    if (tiles.empty()) return KAM_OK;
-    KAM_CUDA(cudaMemcpyAsync(w.tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
-    KAM_CUDA(cudaStreamSynchronize(st));   // `tiles` is pageable host memory owned by this frame
-
-    if (CL == 2)
-        return use_i8 ? launch_gram<true, 2>(w, tiles.size(), n, d, row_begin, row_end, go, st)
-                      : launch_gram<false, 2>(w, tiles.size(), n, d, row_begin, row_end, go, st);
-    return use_i8 ? launch_gram<true, 1>(w, tiles.size(), n, d, row_begin, row_end, go, st)
-                  : launch_gram<false, 1>(w, tiles.size(), n, d, row_begin, row_end, go, st);
+    GramGeom gg;
+    gg.n_a = gg.n_b = n;
+    gg.row_begin = row_begin;
+    gg.row_end = row_end;
+    gg.tri = 1;
+    gg.ld = 0;
+    gg.rk_a = gg.rk_b = w.rk;
+    return gram_block(w.h, w.h, use_i8, d, gg, go, w.tiles, st);
 }
 
-// test hooks: force the fp16 tensor path even when the uint8 path would apply; cluster size 1|2
+// test / tuning hooks
 void kam_gram_force_f16(int on) { g_force_f16 = on != 0; }
 void kam_gram_set_cluster(int cl) { g_cluster = cl == 1 ? 1u : 2u; }
+void kam_gram_set_sm_limit(int sms) { g_sm_limit = sms > 0 ? (uint32_t)sms : 0u; }
 
 }  // extern "C"

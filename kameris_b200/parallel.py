@@ -142,3 +142,135 @@ def gather_triangle(slice_t, n, group=None, dst=0):
     elif sizes[rank]:
         dist.send(slice_t.contiguous(), dst=dst, group=group)
     return full
+
+
+# ---- Gram metrics with block-cyclic pair ownership (ring exchange overlapped with compute) ------------
+def ring_schedule(world):
+    """Which shard-pair blocks each rank computes.  Rank r owns shard r and, at step s = 0..world//2,
+    works on the block (shard r) x (shard (r+s) % world): s = 0 is its own triangular diagonal block;
+    for even `world` the last step's block is shared by the two ranks that hold both shards, each
+    taking half of the rows of the lower-numbered shard.  Returns, per rank, a list of
+    (step, row_shard, col_shard, part) with part in {'tri', 'full', 'lo', 'hi'}; the global pair set
+    {(a, c): a <= c} is covered exactly once."""
+    plan = []
+    for r in range(world):
+        steps = [(0, r, r, "tri")]
+        for s in range(1, world // 2 + 1):
+            c = (r + s) % world
+            if world % 2 == 0 and s == world // 2:
+                # pair {r, c}: the rank with the smaller index takes the low half of ITS rows, the other
+                # rank takes the high half of those same rows (it holds that shard in its receive buffer)
+                if r < c:
+                    steps.append((s, r, c, "lo"))
+                else:
+                    steps.append((s, c, r, "hi"))
+            else:
+                steps.append((s, r, c, "full"))
+        plan.append(steps)
+    return plan
+
+
+def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group=None, sm_reserve=16):
+    """euclid / cosine / pearson over the rows of all ranks, block-cyclic pair ownership.
+
+    Every rank converts its own rows once (uint8 operands when every count of every rank fits a
+    byte, else fp16), then at step s receives shard (rank+s) % world from its owner while computing
+    the block of step s-1; only world//2 shards reach each rank (half an all-gather) and the first
+    block needs no communication at all.  Returns a list of blocks
+        {"row_shard": a, "col_shard": c, "rows": (r0, r1), "tri": bool, metric: tensor[(r1-r0), n_c]}
+    where entry [i - r0, j] is the distance between row i of shard a and row j of shard c (for a
+    triangular block only j > i is written).
+    """
+    from . import _lib
+    from . import dist as D
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = x_local.device
+    n_loc, d = x_local.shape
+    elem = D._ELEM[x_local.dtype]
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    dpad = int(lib.kam_gram_dpad(d))
+    bits = {"euclid": _lib.KAM_M_EUCLID, "cosine": _lib.KAM_M_COSINE, "pearson": _lib.KAM_M_PEARSON}
+    mask = 0
+    for m in metrics:
+        mask |= bits[m]
+
+    cnt = torch.tensor([n_loc], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+
+    # 1. local operand rows + statistics; the operand kind is a global decision
+    S = torch.zeros(max(n_loc, 1), dtype=torch.int64, device=dev)
+    G = torch.zeros(max(n_loc, 1), dtype=torch.int64, device=dev)
+    kind, esz = _lib.KAM_GRAM_U8, 1
+    for kind, esz in ((_lib.KAM_GRAM_U8, 1), (_lib.KAM_GRAM_F16, 2)):
+        op = torch.empty((max(n_loc, 1), dpad * esz), dtype=torch.uint8, device=dev)
+        flags = torch.zeros(8, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.kam_gram_prepare(x_local.data_ptr(), elem, n_loc, d, x_local.stride(0), kind, op.data_ptr(),
+                                            S.data_ptr(), G.data_ptr(), flags.data_ptr(), stream))
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+        mx, gmax = int(flags[0]), int(flags[1])
+        ok = (mx <= 255 and gmax < 2 ** 31) if kind == _lib.KAM_GRAM_U8 else (mx <= 2048 and gmax < 2 ** 24)
+        if ok:
+            break
+        del op
+    else:
+        raise NotImplementedError("counts outside the tensor-exact envelope: use distances_sharded()")
+
+    # 2. row statistics of every shard (tiny), padded to the largest shard
+    cmax = max(counts)
+    sg = torch.zeros((2, cmax), dtype=torch.int64, device=dev)
+    sg[0, :n_loc], sg[1, :n_loc] = S[:n_loc], G[:n_loc]
+    all_sg = [torch.empty_like(sg) for _ in range(world)]
+    dist.all_gather(all_sg, sg, group=group)
+
+    # 3. post the ring transfers step by step (each pair of ops is its own NCCL group, so they
+    #    complete in order while the compute stream works on earlier blocks)
+    plan = ring_schedule(world)[rank]
+    bufs, works = {}, {}
+    for s in range(1, world // 2 + 1):
+        src, dst = (rank + s) % world, (rank - s) % world
+        bufs[s] = torch.empty((max(counts[src], 1), dpad * esz), dtype=torch.uint8, device=dev)
+        works[s] = dist.batch_isend_irecv([dist.P2POp(dist.isend, op, dst, group),
+                                           dist.P2POp(dist.irecv, bufs[s], src, group)])
+
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    if world > 1 and sm_reserve:
+        lib.kam_gram_set_sm_limit(max(sms - sm_reserve, 2))     # leave SMs to the NCCL transfers
+    out_blocks = []
+    try:
+        for s, a, c, part in plan:
+            if s > 0:
+                for w in works[s]:
+                    w.wait()
+            if part == "hi":            # A = the received shard a (rows of the shared block), B = my shard
+                op_a, sg_a, n_a = bufs[s], all_sg[a], counts[a]
+                op_b, sg_b, n_b = op, all_sg[c], counts[c]
+            else:                        # A = my shard, B = my shard (tri) or the received one
+                op_a, sg_a, n_a = op, all_sg[a], counts[a]
+                op_b, sg_b, n_b = (op, all_sg[c], counts[c]) if s == 0 else (bufs[s], all_sg[c], counts[c])
+            h = n_a // 2
+            r0, r1 = {"tri": (0, n_a), "full": (0, n_a), "lo": (0, h), "hi": (h, n_a)}[part]
+            blk = {"row_shard": a, "col_shard": c, "rows": (r0, r1), "tri": part == "tri"}
+            ptrs = {}
+            for m in metrics:
+                t = torch.zeros((max(r1 - r0, 1), max(n_b, 1)), dtype=torch.float32, device=dev)
+                blk[m] = t[:r1 - r0, :n_b]
+                ptrs[m] = t.data_ptr() - r0 * n_b * 4          # the kernel indexes rows from 0
+            ws = torch.empty(lib.kam_gram_block_workspace_bytes(n_a, n_b), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.kam_gram_block(op_a.data_ptr(), sg_a[0].data_ptr(), sg_a[1].data_ptr(), n_a,
+                                              op_b.data_ptr(), sg_b[0].data_ptr(), sg_b[1].data_ptr(), n_b, kind, d,
+                                              int(part == "tri"), r0, r1, mask, int(euclid_on_freq),
+                                              ptrs.get("euclid"), ptrs.get("cosine"), ptrs.get("pearson"), n_b,
+                                              ws.data_ptr(), ws.numel(), stream))
+            blk["_keep"] = ws
+            out_blocks.append(blk)
+    finally:
+        lib.kam_gram_set_sm_limit(0)
+    torch.cuda.current_stream(dev).synchronize()
+    for b in out_blocks:
+        b.pop("_keep", None)
+    return out_blocks, counts

@@ -82,3 +82,22 @@ def test_distances_sharded_gloo_world2():
         assert p.exitcode == 0
     ref, _ = O.dists_triangle(x, True, False)
     assert np.array_equal(full.view(np.uint32), ref)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8])
+def test_ring_schedule_covers_every_shard_pair_once(world):
+    plan = parallel.ring_schedule(world)
+    cover = {}
+    for r, steps in enumerate(plan):
+        assert steps[0] == (0, r, r, "tri")
+        for s, a, c, part in steps:
+            # the rank holds both shards at that step: its own, and the one received at step s
+            assert r in (a, c) and {a, c} <= {r, (r + s) % world}
+            key = (min(a, c), max(a, c))
+            cover.setdefault(key, []).append(part)
+    want = {(a, c) for a in range(world) for c in range(a, world)}
+    assert set(cover) == want
+    for key, parts in cover.items():
+        assert sorted(parts) in (["tri"], ["full"], ["hi", "lo"]), (key, parts)
+    loads = [sum({"tri": 0.5, "full": 1.0, "lo": 0.5, "hi": 0.5}[p] for _, _, _, p in steps) for steps in plan]
+    assert max(loads) - min(loads) < 1e-9          # perfectly balanced in units of blocks
