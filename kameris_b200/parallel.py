@@ -184,7 +184,8 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
     from . import _lib
     from . import dist as D
     lib = _lib.load()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    multi = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if multi else (0, 1)
     dev = x_local.device
     n_loc, d = x_local.shape
     elem = D._ELEM[x_local.dtype]
@@ -195,10 +196,13 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
     for m in metrics:
         mask |= bits[m]
 
-    cnt = torch.tensor([n_loc], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, cnt, group=group)
-    counts = [int(c.item()) for c in counts]
+    if world > 1:
+        cnt = torch.tensor([n_loc], dtype=torch.int64, device=dev)
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(counts, cnt, group=group)
+        counts = [int(c.item()) for c in counts]
+    else:
+        counts = [n_loc]
 
     # 1. local operand rows + statistics; the operand kind is a global decision
     S = torch.zeros(max(n_loc, 1), dtype=torch.int64, device=dev)
@@ -210,7 +214,8 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
         with torch.cuda.device(dev):
             _lib.check(lib.kam_gram_prepare(x_local.data_ptr(), elem, n_loc, d, x_local.stride(0), kind, op.data_ptr(),
                                             S.data_ptr(), G.data_ptr(), flags.data_ptr(), stream))
-        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+        if world > 1:
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
         mx, gmax = int(flags[0]), int(flags[1])
         ok = (mx <= 255 and gmax < 2 ** 31) if kind == _lib.KAM_GRAM_U8 else (mx <= 2048 and gmax < 2 ** 24)
         if ok:
@@ -223,8 +228,11 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
     cmax = max(counts)
     sg = torch.zeros((2, cmax), dtype=torch.int64, device=dev)
     sg[0, :n_loc], sg[1, :n_loc] = S[:n_loc], G[:n_loc]
-    all_sg = [torch.empty_like(sg) for _ in range(world)]
-    dist.all_gather(all_sg, sg, group=group)
+    if world > 1:
+        all_sg = [torch.empty_like(sg) for _ in range(world)]
+        dist.all_gather(all_sg, sg, group=group)
+    else:
+        all_sg = [sg]
 
     # 3. post the ring transfers step by step (each pair of ops is its own NCCL group, so they
     #    complete in order while the compute stream works on earlier blocks)

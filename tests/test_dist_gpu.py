@@ -200,3 +200,44 @@ def test_gram_row_ranges_compose(D):
         assert not (np.logical_and(acc != 0, part != 0)).any()
         acc += part
     assert np.array_equal(acc, full)
+
+
+def test_gram_ring_single_rank_equals_triangle(D):
+    """parallel.gram_ring without a process group: one triangular block == the packed triangle."""
+    from kameris_b200 import parallel
+    x = _counts(333, 2000, 6, seed=21)
+    xd = _dev(x)
+    blocks, counts = parallel.gram_ring(xd, ("cosine", "euclid"))
+    assert counts == [333] and len(blocks) == 1 and blocks[0]["tri"]
+    ref = D.gram_tri(xd, ("cosine", "euclid"))
+    iu = np.triu_indices(333, 1)
+    for m in ("cosine", "euclid"):
+        assert np.array_equal(blocks[0][m].cpu().numpy()[iu], ref[m].cpu().numpy())
+
+
+def test_gram_block_rectangular(D):
+    """kam_gram_block on two different row sets (dense output) vs scipy."""
+    from kameris_b200 import _lib
+    lib = _lib.load()
+    xa, xb = _counts(150, 2000, 5, seed=31), _counts(70, 2000, 5, seed=32)
+    d = xa.shape[1]
+    dpad = int(lib.kam_gram_dpad(d))
+    st = torch.cuda.current_stream().cuda_stream
+    ops, S, G = [], [], []
+    for x in (xa, xb):
+        xd = _dev(x)
+        op = torch.empty((x.shape[0], dpad), dtype=torch.uint8, device="cuda")
+        s = torch.zeros(x.shape[0], dtype=torch.int64, device="cuda")
+        g = torch.zeros(x.shape[0], dtype=torch.int64, device="cuda")
+        fl = torch.zeros(8, dtype=torch.int64, device="cuda")
+        _lib.check(lib.kam_gram_prepare(xd.data_ptr(), 1, x.shape[0], d, d, 0, op.data_ptr(), s.data_ptr(), g.data_ptr(),
+                                        fl.data_ptr(), st))
+        assert int(fl[0]) == int(x.max()) and int(fl[1]) == int((x.astype(np.int64) ** 2).sum(axis=1).max())
+        assert np.array_equal(s.cpu().numpy(), x.sum(axis=1))
+        ops.append(op), S.append(s), G.append(g)
+    out = torch.zeros((150, 70), dtype=torch.float32, device="cuda")
+    ws = torch.empty(lib.kam_gram_block_workspace_bytes(150, 70), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.kam_gram_block(ops[0].data_ptr(), S[0].data_ptr(), G[0].data_ptr(), 150, ops[1].data_ptr(),
+                                  S[1].data_ptr(), G[1].data_ptr(), 70, 0, d, 0, 0, 150, _lib.KAM_M_PEARSON, 0, None, None,
+                                  out.data_ptr(), 70, ws.data_ptr(), ws.numel(), st))
+    np.testing.assert_allclose(out.cpu().numpy(), O.cdist_rect(xa, xb, "pearson"), rtol=1e-5)
