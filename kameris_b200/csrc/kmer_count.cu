@@ -29,7 +29,6 @@
 
 namespace {
 
-constexpr int A_THREADS = 256;
 constexpr int TILE_BINS_LOG2 = 15;
 constexpr uint32_t TILE_BINS = 1u << TILE_BINS_LOG2;   // 32768 bins: 32 KB of uint8 counters
 constexpr uint64_t A_MAX_LEN = 1ull << 17;              // longer sequences go to path B when tiled
@@ -98,8 +97,10 @@ __device__ __forceinline__ void bump(uint32_t *tab32, uint32_t lb, uint32_t *s_f
     }
 }
 
-template <typename CT, typename OUT>
-__global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__restrict__ planes,
+// THREADS: 256 for genome-length sequences; 64 for short reads, where a sequence gives a CTA only a
+// few dozen k-mer groups and the per-sequence barriers dominate (more, smaller CTAs per SM hide them).
+template <typename CT, typename OUT, int THREADS>
+__global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restrict__ planes,
                                                              const uint64_t *__restrict__ base_start,
                                                              const uint32_t *__restrict__ head_mask, uint32_t n_seqs,
                                                              int k, int count_bits, OUT *__restrict__ out,
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
     uint32_t *tab32 = reinterpret_cast<uint32_t *>(smem_raw);
     __shared__ uint32_t s_seq;
     __shared__ uint32_t s_flag;
-    __shared__ unsigned long long s_red[A_THREADS / 32];
+    __shared__ unsigned long long s_red[THREADS / 32];
     // quotient of every possible uint8 count for the current sequence: the (slow, exact) double
     // division runs 256 times per sequence instead of 4^k times
     __shared__ OUT s_lut[256];
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
     const uint32_t tbits = n_tiles > 1 ? (uint32_t)(2 * k - TILE_BINS_LOG2) : 0u;   // log2(n_tiles)
     constexpr int BPS = 16 / (int)sizeof(OUT);                // bins per 16-byte store
 
-    for (uint32_t i = threadIdx.x; i < tile_words; i += A_THREADS) tab32[i] = 0;
+    for (uint32_t i = threadIdx.x; i < tile_words; i += THREADS) tab32[i] = 0;
 
     for (;;) {
         __syncthreads();   // table is clear; previous s_seq/s_flag/s_lut consumed
@@ -160,11 +161,11 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
         // sum of the counts = number of emitting bases (no wrap on this path unless handled below)
         double sum = (double)(q.n > q.lead ? q.n - q.lead : 0);
         if constexpr (IS_FREQ && sizeof(CT) == 1) {
-            s_lut[threadIdx.x] = convert_count<OUT>(threadIdx.x, 0.0, sum);   // A_THREADS == 256
+            for (uint32_t i = threadIdx.x; i < 256; i += THREADS) s_lut[i] = convert_count<OUT>(i, 0.0, sum);
         }
 
         for (uint32_t t = 0; t < n_tiles; ++t) {
-            for (uint64_t g = g0 + threadIdx.x; g < g1; g += A_THREADS) {
+            for (uint64_t g = g0 + threadIdx.x; g < g1; g += THREADS) {
                 const uint64_t W = g >> 2;                  // word holding the group
                 const uint2 hi = __ldg(planes + W);
                 const uint2 lo = W ? __ldg(planes + W - 1) : make_uint2(0, 0);
@@ -203,13 +204,13 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
                 // frequencies of 16-bit counts that wrapped: the divisor is the sum of the WRAPPED values
                 if (t == 0 && IS_FREQ && count_bits == 16 && q.n > 65535) {
                     unsigned long long part = 0;
-                    for (uint32_t i = threadIdx.x; i < tile_bins; i += A_THREADS) part += tab32[i] & 0xffffu;
+                    for (uint32_t i = threadIdx.x; i < tile_bins; i += THREADS) part += tab32[i] & 0xffffu;
                     part = warp_sum64(part);
                     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
                     __syncthreads();
                     unsigned long long tot = 0;
 #pragma unroll
-                    for (int w = 0; w < A_THREADS / 32; ++w) tot += s_red[w];
+                    for (int w = 0; w < THREADS / 32; ++w) tot += s_red[w];
                     sum = (double)tot;
                 }
             }
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
             const uint32_t wrapmask = (count_bits == 16) ? 0xffffu : 0xffffffffu;
             if (vec_ok) {
                 const uint32_t n_stores = tile_bins / BPS;
-                for (uint32_t c = threadIdx.x; c < n_stores; c += A_THREADS) {
+                for (uint32_t c = threadIdx.x; c < n_stores; c += THREADS) {
                     union {
                         uint4 v;
                         OUT e[BPS];
@@ -260,14 +261,14 @@ __global__ void __launch_bounds__(A_THREADS) cgr_tile_kernel(const uint2 *__rest
                     st_stream16(trow + (uint64_t)c * BPS, u.v);
                 }
             } else {   // tiny or misaligned rows (k=1 with 16-bit counts)
-                for (uint32_t i = threadIdx.x; i < tile_bins; i += A_THREADS) {
+                for (uint32_t i = threadIdx.x; i < tile_bins; i += THREADS) {
                     uint32_t c;
                     if constexpr (sizeof(CT) == 1) c = reinterpret_cast<unsigned char *>(tab32)[i];
                     else c = tab32[i] & wrapmask;
                     trow[i] = convert_count<OUT>(c, 0.0, sum);
                 }
                 __syncthreads();
-                for (uint32_t i = threadIdx.x; i < tile_words; i += A_THREADS) tab32[i] = 0;
+                for (uint32_t i = threadIdx.x; i < tile_words; i += THREADS) tab32[i] = 0;
             }
             __syncthreads();
         }
@@ -391,21 +392,21 @@ inline size_t ws_layout(uint32_t n_seqs, int k, void *base, KmerWs *w) {
     return off;
 }
 
-template <typename CT, typename OUT>
+template <typename CT, typename OUT, int THREADS>
 int launch_tile(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, uint32_t n_seqs, int k,
                 int count_bits, OUT *out, uint64_t out_stride, const KmerWs &w, cudaStream_t st) {
     const uint32_t bins = 1u << (2 * k);
     const uint32_t tile_bins = bins < TILE_BINS ? bins : TILE_BINS;
     size_t smem = (size_t)tile_bins * sizeof(CT);
     if (smem < 16) smem = 16;
-    auto kern = cgr_tile_kernel<CT, OUT>;
+    auto kern = cgr_tile_kernel<CT, OUT, THREADS>;
     KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    KAM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, A_THREADS, smem));
+    KAM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)kam_sm_count() * per_sm;   // persistent: a whole number of CTAs per SM
     if (grid > n_seqs) grid = n_seqs;
-    kern<<<(unsigned)grid, A_THREADS, smem, st>>>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
+    kern<<<(unsigned)grid, THREADS, smem, st>>>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
                                                   out_stride, w.queue, w.spill_count, w.spill_list, w.spill_maxlen);
     KAM_CUDA(cudaGetLastError());
     return KAM_OK;
@@ -415,10 +416,22 @@ template <typename OUT>
 int run_kmer(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, uint32_t n_seqs, int k,
              int count_bits, OUT *out, uint64_t out_stride, const KmerWs &w, cudaStream_t st) {
     KAM_CUDA(cudaMemsetAsync(w.queue, 0, 64, st));
-    int rc = (k <= 6) ? launch_tile<uint32_t, OUT>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
-                                                    out_stride, w, st)
-                      : launch_tile<uint8_t, OUT>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
-                                                   out_stride, w, st);
+    // mean sequence length picks the CTA size (one 8-byte read of the last base offset)
+    unsigned long long total_bases = 0;
+    KAM_CUDA(cudaMemcpyAsync(&total_bases, base_start + n_seqs, 8, cudaMemcpyDeviceToHost, st));
+    KAM_CUDA(cudaStreamSynchronize(st));
+    const bool short_reads = total_bases / n_seqs < 2048;
+    int rc;
+    if (k <= 6)
+        rc = short_reads ? launch_tile<uint32_t, OUT, 64>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
+                                                          out_stride, w, st)
+                         : launch_tile<uint32_t, OUT, 256>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
+                                                           out_stride, w, st);
+    else
+        rc = short_reads ? launch_tile<uint8_t, OUT, 64>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
+                                                         out_stride, w, st)
+                         : launch_tile<uint8_t, OUT, 256>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
+                                                          out_stride, w, st);
     if (rc) return rc;
     if (k <= 6) return KAM_OK;   // uint32 counters, single tile: nothing can spill, no need to look
 

@@ -39,20 +39,27 @@ def list_input_files(directory):
     return sorted(paths, key=lambda p: os.fsencode(p))
 
 
-def read_records(paths):
-    """record[0] of every file (A.1).  A file without a record raises (the reference reads
-    begin() of an empty vector there)."""
+def _read_record(path):
     lib = _lib.load()
-    recs = []
-    for p in paths:
-        with open(p, 'rb') as f:
-            data = f.read()
-        out = ctypes.create_string_buffer(max(len(data), 1))
-        n = lib.kam_fasta_record0(data, len(data), out)
-        if n < 0:
-            raise ValueError('no FASTA record in "%s"' % p)
-        recs.append(out.raw[:n])
-    return recs
+    with open(path, 'rb') as f:
+        data = f.read()
+    out = ctypes.create_string_buffer(max(len(data), 1))
+    n = lib.kam_fasta_record0(data, len(data), out)     # ctypes releases the GIL during the call
+    if n < 0:
+        raise ValueError('no FASTA record in "%s"' % path)
+    return out.raw[:n]
+
+
+def read_records(paths, threads=None):
+    """record[0] of every file (A.1), in the order of `paths`.  A file without a record raises (the
+    reference reads begin() of an empty vector there).  Files are read by a small thread pool: both
+    the file reads and the record extraction run outside the GIL."""
+    if len(paths) < 8:
+        return [_read_record(p) for p in paths]
+    from concurrent.futures import ThreadPoolExecutor
+    workers = threads or min(32, (os.cpu_count() or 4))
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        return list(pool.map(_read_record, paths, chunksize=64))
 
 
 def kmers_from_records(records, k, bits_per_element, mode):
