@@ -95,14 +95,16 @@ int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_
 size_t kam_kmer_workspace_bytes(uint32_t n_seqs, int k);
 
 /* planes -> n_seqs vectors of 4^k bins (row s at d_out + s*out_stride elements).
+ * total_bases_hint: total number of bases (an upper bound such as the character count is fine; it
+ * only selects the CTA size for short reads); 0 = unknown, the library reads it from the device.
  * count_bits: 16|32 (wrap width of the counts, also for the frequencies derived from them).
  * out_kind: KAM_OUT_*.  Element type of d_out: uint16/uint32 for COUNTS, float/double for FREQ.
  * Synchronises `stream` once internally (to learn how many sequences need the long-sequence
  * path); the results are complete on return of the stream's work. */
 int kam_kmer_count(const uint64_t *d_planes, const uint64_t *d_base_start,
-                   const uint32_t *d_head_mask, uint32_t n_seqs, int k, int count_bits,
-                   int out_kind, void *d_out, uint64_t out_stride, void *d_ws, size_t ws_bytes,
-                   void *stream);
+                   const uint32_t *d_head_mask, uint32_t n_seqs, uint64_t total_bases_hint, int k,
+                   int count_bits, int out_kind, void *d_out, uint64_t out_stride, void *d_ws,
+                   size_t ws_bytes, void *stream);
 
 /* Host-buffer form of the whole `kmers` step (what generation_cgr + the numpy pass compute):
  * h_chars/h_char_start are the concatenated FASTA records (record[0] of each file, see

@@ -167,8 +167,8 @@ extern "C" int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_sta
         rc = kam_pack_ascii((const uint8_t *)s.chars.p, (const uint64_t *)s.starts.p, n, nchars, (uint64_t *)s.planes.p,
                             (uint64_t *)s.base.p, (uint32_t *)s.head.p, s.pack_ws.p, s.pack_ws.cap, s.st);
         if (rc) return rc;
-        rc = kam_kmer_count((const uint64_t *)s.planes.p, (const uint64_t *)s.base.p, (const uint32_t *)s.head.p, n, k,
-                            count_bits, out_kind, s.out.p, bins, s.kmer_ws.p, s.kmer_ws.cap, s.st);
+        rc = kam_kmer_count((const uint64_t *)s.planes.p, (const uint64_t *)s.base.p, (const uint32_t *)s.head.p, n,
+                            nchars, k, count_bits, out_kind, s.out.p, bins, s.kmer_ws.p, s.kmer_ws.cap, s.st);
         if (rc) return rc;
         char *dst = (char *)h_out + (size_t)first * row_bytes;
         if (out_pinned) {

@@ -414,12 +414,15 @@ int launch_tile(const uint2 *planes, const uint64_t *base_start, const uint32_t 
 
 template <typename OUT>
 int run_kmer(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, uint32_t n_seqs, int k,
-             int count_bits, OUT *out, uint64_t out_stride, const KmerWs &w, cudaStream_t st) {
+             int count_bits, OUT *out, uint64_t out_stride, const KmerWs &w, uint64_t total_bases_hint,
+             cudaStream_t st) {
     KAM_CUDA(cudaMemsetAsync(w.queue, 0, 64, st));
-    // mean sequence length picks the CTA size (one 8-byte read of the last base offset)
-    unsigned long long total_bases = 0;
-    KAM_CUDA(cudaMemcpyAsync(&total_bases, base_start + n_seqs, 8, cudaMemcpyDeviceToHost, st));
-    KAM_CUDA(cudaStreamSynchronize(st));
+    // mean sequence length picks the CTA size: the caller's hint, else one 8-byte read of the last offset
+    unsigned long long total_bases = total_bases_hint;
+    if (total_bases == 0) {
+        KAM_CUDA(cudaMemcpyAsync(&total_bases, base_start + n_seqs, 8, cudaMemcpyDeviceToHost, st));
+        KAM_CUDA(cudaStreamSynchronize(st));
+    }
     const bool short_reads = total_bases / n_seqs < 2048;
     int rc;
     if (k <= 6)
@@ -474,8 +477,8 @@ size_t kam_kmer_workspace_bytes(uint32_t n_seqs, int k) {
 }
 
 int kam_kmer_count(const uint64_t *d_planes, const uint64_t *d_base_start, const uint32_t *d_head_mask,
-                   uint32_t n_seqs, int k, int count_bits, int out_kind, void *d_out, uint64_t out_stride,
-                   void *d_ws, size_t ws_bytes, void *stream) {
+                   uint32_t n_seqs, uint64_t total_bases_hint, int k, int count_bits, int out_kind, void *d_out,
+                   uint64_t out_stride, void *d_ws, size_t ws_bytes, void *stream) {
     if (k < 1 || 2 * k > 64) {
         kam_set_error("k is too large to fit in the index");   // the reference's message (cgr @0x10000e15f)
         return KAM_E_INVALID;
@@ -499,12 +502,12 @@ int kam_kmer_count(const uint64_t *d_planes, const uint64_t *d_base_start, const
     const uint2 *pl = (const uint2 *)d_planes;
     if (out_kind == KAM_OUT_COUNTS) {
         if (count_bits == 16)
-            return run_kmer<uint16_t>(pl, d_base_start, d_head_mask, n_seqs, k, 16, (uint16_t *)d_out, out_stride, w, st);
-        return run_kmer<uint32_t>(pl, d_base_start, d_head_mask, n_seqs, k, 32, (uint32_t *)d_out, out_stride, w, st);
+            return run_kmer<uint16_t>(pl, d_base_start, d_head_mask, n_seqs, k, 16, (uint16_t *)d_out, out_stride, w, total_bases_hint, st);
+        return run_kmer<uint32_t>(pl, d_base_start, d_head_mask, n_seqs, k, 32, (uint32_t *)d_out, out_stride, w, total_bases_hint, st);
     }
     if (out_kind == KAM_OUT_FREQ_F32)
-        return run_kmer<float>(pl, d_base_start, d_head_mask, n_seqs, k, count_bits, (float *)d_out, out_stride, w, st);
-    return run_kmer<double>(pl, d_base_start, d_head_mask, n_seqs, k, count_bits, (double *)d_out, out_stride, w, st);
+        return run_kmer<float>(pl, d_base_start, d_head_mask, n_seqs, k, count_bits, (float *)d_out, out_stride, w, total_bases_hint, st);
+    return run_kmer<double>(pl, d_base_start, d_head_mask, n_seqs, k, count_bits, (double *)d_out, out_stride, w, total_bases_hint, st);
 }
 
 }  // extern "C"

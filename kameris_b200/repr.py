@@ -97,7 +97,7 @@ def kmer_vectors(batch, k, bits=16, out="counts", out_tensor=None, workspace=Non
     assert out_tensor.dtype == dtype and out_tensor.is_contiguous()
     ws = workspace if workspace is not None else kmer_workspace(batch.n_seqs, k, dev)
     with torch.cuda.device(dev):
-        check(lib.kam_kmer_count(_ptr(batch.planes), _ptr(batch.base_start), _ptr(batch.head_mask), batch.n_seqs, k,
-                                 bits, _OUT_KINDS[out], _ptr(out_tensor), out_tensor.stride(0) if batch.n_seqs else d,
+        check(lib.kam_kmer_count(_ptr(batch.planes), _ptr(batch.base_start), _ptr(batch.head_mask), batch.n_seqs,
+                                 batch.total_chars, k, bits, _OUT_KINDS[out], _ptr(out_tensor), out_tensor.stride(0) if batch.n_seqs else d,
                                  _ptr(ws), ws.numel(), _stream_ptr(dev)))
     return out_tensor

@@ -5,9 +5,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from kameris_b200 import parallel, dist as D
 from kameris_b200.dist_bench import synth_counts
 
-rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); lr = int(os.environ.get("LOCAL_RANK", 0))
 dev = torch.device("cuda", lr); torch.cuda.set_device(dev)
-dist.init_process_group("nccl", device_id=dev)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
 mode = sys.argv[1] if len(sys.argv) > 1 else "check"
 if mode == "check":
     n, k = 1500 * world + 7, 7
@@ -45,14 +46,17 @@ else:
         r = step(); del r; torch.cuda.synchronize()
         times = []
         for _ in range(3):
-            dist.barrier(); torch.cuda.synchronize()
+            if world > 1: dist.barrier()
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); r = step(); e1.record(); torch.cuda.synchronize(); del r
             t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX); times.append(float(t))
+            if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t))
         res[reserve] = min(times)
     if rank == 0:
         n = n_loc * world
         print(json.dumps({"n_gpus": world, "N": n, "D": 4 ** k, "ring_ms_sm_reserve0": res[0], "ring_ms_sm_reserve16": res[16],
                           "pairs_per_s": n * (n - 1) / 2 / (min(res.values()) * 1e-3)}))
-dist.destroy_process_group()
+if world > 1:
+    dist.destroy_process_group()

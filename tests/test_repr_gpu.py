@@ -125,6 +125,16 @@ def test_property_full_size_k9(R):
         assert np.array_equal(out[i].cpu().numpy(), O.cgr_count(recs[i], k, 16))
 
 
+def test_large_k_demo_genomes(R, refcode_cases):
+    """k = 11, 12 (512 shared-memory tiles per vector) on the demo genomes vs the reference-code goldens."""
+    cases = [c for c in refcode_cases if c["name"].startswith("demo-")]
+    recs = [c["record"].encode("latin-1") for c in cases]
+    for k in (11, 12):
+        got = _gpu_counts(R, recs, k, 16)
+        for i, c in enumerate(cases):
+            assert hashlib.sha1(got[i].astype("<u2").tobytes()).hexdigest() == c["k"][str(k)]["sha1"], (c["name"], k)
+
+
 def test_errors(R):
     b = R.pack_records([b"ACGT"])
     with pytest.raises(ValueError):
