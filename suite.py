@@ -166,14 +166,12 @@ def config3(rank, world, dev, scale):
     ok = True
     npairs = 0
     if world > 1:
-        x_all = [torch.empty_like(x_loc.view(torch.int16)) for _ in range(world)]
         # only a sample is checked: gather 64 fixed rows of every shard instead of the whole matrix
         samp_rows = np.sort(np.random.Generator(np.random.PCG64(99)).choice(n_loc, 64, replace=False))
-        mine = torch.from_numpy(rows_of(x_loc, samp_rows, dev).view(np.int16)).to(dev)
+        mine = torch.from_numpy(rows_of(x_loc, samp_rows, dev).view(np.uint8)).to(dev)      # NCCL has no 16-bit ints
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine)
         samp = [p.cpu().numpy().view(np.uint16) for p in parts]
-        del x_all
     else:
         samp_rows = np.sort(np.random.Generator(np.random.PCG64(99)).choice(n_loc, 64, replace=False))
         samp = [rows_of(x_loc, samp_rows, dev)]
