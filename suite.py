@@ -160,6 +160,9 @@ def config3(rank, world, dev, scale):
     del chars, b
     torch.cuda.empty_cache()
     # block-cyclic pair ownership: ring exchange of the uint8 operand rows overlapped with the blocks
+    warm = parallel.gram_ring(x_loc, ("cosine", "pearson"))       # first call sets up the NCCL P2P connections
+    del warm
+    torch.cuda.empty_cache()
     (blocks, counts), t_d = timed(lambda: parallel.gram_ring(x_loc, ("cosine", "pearson")), dev, world)
     # verify random pairs of this rank's blocks against scipy; the column rows are fetched from their owner
     rng = np.random.Generator(np.random.PCG64(7 + rank))
