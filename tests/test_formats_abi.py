@@ -144,3 +144,25 @@ def test_list_input_files_sorted(tmp_path):
         (tmp_path / n).write_text(">x\nACGT\n")
     got = [os.path.basename(p) for p in backend.list_input_files(str(tmp_path))]
     assert got == ["10.fasta", "9.fasta", "A1.fasta", "B.fasta", "a.fasta", "b.fasta"]   # byte-wise
+
+
+def test_abi_argument_validation_without_gpu():
+    """Bad arguments are rejected with an error code and a message before any CUDA call."""
+    import ctypes
+    from kameris_b200 import _lib
+    lib = _lib.load()
+    p = ctypes.c_void_p(16)          # non-null dummy pointers: validation must stop before they are touched
+    assert lib.kam_kmer_count(p, p, p, 1, 0, 33, 16, 0, p, 4, p, 1 << 20, None) == -1
+    assert b"k is too large to fit in the index" in lib.kam_last_error()
+    assert lib.kam_kmer_count(p, p, p, 1, 0, 16, 16, 0, p, 4 ** 16, p, 1 << 20, None) == -4      # k beyond this build
+    assert lib.kam_kmer_count(p, p, p, 1, 0, 4, 8, 0, p, 256, p, 1 << 20, None) == -1
+    assert b"count_bits" in lib.kam_last_error()
+    assert lib.kam_kmer_count(p, p, p, 1, 0, 4, 16, 0, p, 10, p, 1 << 20, None) == -1             # out_stride < 4^k
+    assert lib.kam_kmer_count(p, p, p, 1, 0, 9, 16, 0, p, 4 ** 9, p, 64, None) == -3              # workspace too small
+    assert lib.kam_kmers_host(None, None, 1, 4, 16, 0, None) == -1
+    assert lib.kam_gram_tri(p, 5, 10, 16, 16, 0, 10, 8, 1, None, p, None, p, 1 << 30, None) == -1  # float input
+    assert b"integer count vectors" in lib.kam_last_error()
+    assert lib.kam_gram_tri(p, 1, 10, 16, 16, 0, 10, 8, 1, None, None, None, p, 1 << 30, None) == -1   # missing output
+    assert lib.kam_manhattan_tri(p, 9, 10, 16, 16, 0, 10, p, p, 1 << 30, None) == -1
+    assert lib.kam_dists_host(p, 1, 10, 16, 0, None, None, None, None, None) == -1                 # no metric asked
+    assert lib.kam_gram_dpad(4 ** 9) == 4 ** 9 and lib.kam_gram_dpad(4) == 128
