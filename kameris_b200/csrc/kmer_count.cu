@@ -30,7 +30,7 @@
 namespace {
 
 constexpr int TILE_BINS_LOG2 = 15;
-constexpr uint32_t TILE_BINS = 1u << TILE_BINS_LOG2;   // 32768 bins: 32 KB of uint8 counters
+constexpr uint32_t TILE_BINS = 1u << TILE_BINS_LOG2;   // bins per shared-memory tile (uint8 counters)
 constexpr uint64_t A_MAX_LEN = 1ull << 17;              // longer sequences go to path B when tiled
 constexpr int B_THREADS = 256;
 constexpr uint32_t B_CHUNK = 32768;                     // bases per CTA in path B
