@@ -110,9 +110,11 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
                                                              unsigned long long *__restrict__ spill_maxlen) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *tab32 = reinterpret_cast<uint32_t *>(smem_raw);
-    __shared__ uint32_t s_seq;
+    __shared__ uint32_t s_seq, s_next, s_end;
     __shared__ uint32_t s_flag;
     __shared__ unsigned long long s_red[THREADS / 32];
+    constexpr uint32_t QB = THREADS == 64 ? 8u : 1u;
+    if (threadIdx.x == 0) s_next = s_end = 0;
     // quotient of every possible uint8 count for the current sequence: the (slow, exact) double
     // division runs 256 times per sequence instead of 4^k times
     __shared__ OUT s_lut[256];
@@ -134,7 +136,11 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
     for (;;) {
         __syncthreads();   // table is clear; previous s_seq/s_flag/s_lut consumed
         if (threadIdx.x == 0) {
-            s_seq = atomicAdd(queue, 1u);
+            if (s_next >= s_end) {            // short reads take QB sequences per global atomic
+                s_next = atomicAdd(queue, QB);
+                s_end = s_next + QB;
+            }
+            s_seq = s_next++;
             s_flag = 0;
         }
         __syncthreads();
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
         const uint64_t g0 = pf >> 3, g1 = has_full ? ((pe - 1) >> 3) + 1 : g0;
         // sum of the counts = number of emitting bases (no wrap on this path unless handled below)
         double sum = (double)(q.n > q.lead ? q.n - q.lead : 0);
-        if constexpr (IS_FREQ && sizeof(CT) == 1) {
+        if constexpr (IS_FREQ) {   // (recomputed below when the divisor turns out to be a wrapped sum)
             for (uint32_t i = threadIdx.x; i < 256; i += THREADS) s_lut[i] = convert_count<OUT>(i, 0.0, sum);
         }
 
@@ -212,6 +218,9 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
 #pragma unroll
                     for (int w = 0; w < THREADS / 32; ++w) tot += s_red[w];
                     sum = (double)tot;
+                    __syncthreads();
+                    for (uint32_t i = threadIdx.x; i < 256; i += THREADS) s_lut[i] = convert_count<OUT>(i, 0.0, sum);
+                    __syncthreads();
                 }
             }
 
@@ -251,11 +260,30 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
                             u.v = make_uint4(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu, w0 >> 24);
                         }
                     } else {
+                        // uint32 counters: vector read-and-clear, then quotient LUT for counts < 256
+                        uint32_t cnt[BPS];
+                        if constexpr (BPS == 2) {
+                            const uint2 w = *reinterpret_cast<uint2 *>(&tab32[c * 2]);
+                            *reinterpret_cast<uint2 *>(&tab32[c * 2]) = make_uint2(0, 0);
+                            cnt[0] = w.x & wrapmask, cnt[1] = w.y & wrapmask;
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < BPS; ++i) {
-                            const uint32_t cnt = tab32[c * BPS + i] & wrapmask;
-                            tab32[c * BPS + i] = 0;
-                            u.e[i] = convert_count<OUT>(cnt, 0.0, sum);
+                            for (int q4 = 0; q4 < BPS / 4; ++q4) {
+                                const uint4 w = *reinterpret_cast<uint4 *>(&tab32[c * BPS + 4 * q4]);
+                                *reinterpret_cast<uint4 *>(&tab32[c * BPS + 4 * q4]) = make_uint4(0, 0, 0, 0);
+                                cnt[4 * q4] = w.x & wrapmask, cnt[4 * q4 + 1] = w.y & wrapmask;
+                                cnt[4 * q4 + 2] = w.z & wrapmask, cnt[4 * q4 + 3] = w.w & wrapmask;
+                            }
+                        }
+                        if constexpr (IS_FREQ) {
+#pragma unroll
+                            for (int i = 0; i < BPS; ++i)
+                                u.e[i] = cnt[i] < 256u ? s_lut[cnt[i]] : convert_count<OUT>(cnt[i], 0.0, sum);
+                        } else if constexpr (BPS == 8) {      // uint16 counts: low halves of two counters per PRMT
+                            u.v = make_uint4(__byte_perm(cnt[0], cnt[1], 0x5410), __byte_perm(cnt[2], cnt[3], 0x5410),
+                                             __byte_perm(cnt[4], cnt[5], 0x5410), __byte_perm(cnt[6], cnt[7], 0x5410));
+                        } else {
+                            u.v = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
                         }
                     }
                     st_stream16(trow + (uint64_t)c * BPS, u.v);
