@@ -106,6 +106,17 @@ int kam_kmer_count(const uint64_t *d_planes, const uint64_t *d_base_start,
                    int count_bits, int out_kind, void *d_out, uint64_t out_stride, void *d_ws,
                    size_t ws_bytes, void *stream);
 
+/* Order-(k+1) count tables -> order-k tables by 2x2 sum-pooling of the CGR image plus the one k-mer
+ * that has no (k+1)-mer ending at the same base; exact for dirty heads (quirk Q1) and
+ * for wrapped uint16 counts.  d_in rows hold 4^(k+1) bins, d_out rows 4^k bins, both count_bits wide. */
+int kam_cgr_pool(const uint64_t *d_planes, const uint64_t *d_base_start, const uint32_t *d_head_mask,
+                 uint32_t n_seqs, int k, int count_bits, const void *d_in, uint64_t in_stride,
+                 void *d_out, uint64_t out_stride, void *stream);
+/* counts (uint16/uint32, n rows of d bins) -> frequencies cgr/cgr.sum() (backend.py:49);
+ * out_kind KAM_OUT_FREQ_F32 | KAM_OUT_FREQ_F64.  kam_kmer_count fuses this for fresh tables. */
+int kam_normalize(const void *d_counts, int count_bits, uint32_t n, uint64_t d, uint64_t in_stride,
+                  int out_kind, void *d_out, uint64_t out_stride, void *stream);
+
 /* Host-buffer form of the whole `kmers` step (what generation_cgr + the numpy pass compute):
  * h_chars/h_char_start are the concatenated FASTA records (record[0] of each file, see
  * kam_fasta_record0), h_out receives n_seqs x 4^k elements.  Copies, packing, counting and the

@@ -101,3 +101,28 @@ def kmer_vectors(batch, k, bits=16, out="counts", out_tensor=None, workspace=Non
                                  batch.total_chars, k, bits, _OUT_KINDS[out], _ptr(out_tensor), out_tensor.stride(0) if batch.n_seqs else d,
                                  _ptr(ws), ws.numel(), _stream_ptr(dev)))
     return out_tensor
+
+
+def cgr_pool(batch, counts_k1, k):
+    """order-(k+1) count vectors of `batch` -> order-k count vectors (2x2 pooling + fix-up, A.3)."""
+    lib = _lib.load()
+    bits = {torch.uint16: 16, torch.uint32: 32}[counts_k1.dtype]
+    assert counts_k1.shape == (batch.n_seqs, 4 ** (k + 1)) and counts_k1.is_contiguous()
+    out = torch.empty((batch.n_seqs, 4 ** k), dtype=counts_k1.dtype, device=counts_k1.device)
+    with torch.cuda.device(out.device):
+        check(lib.kam_cgr_pool(_ptr(batch.planes), _ptr(batch.base_start), _ptr(batch.head_mask), batch.n_seqs, k, bits,
+                               _ptr(counts_k1), counts_k1.stride(0) if batch.n_seqs else 4 ** (k + 1), _ptr(out),
+                               4 ** k, _stream_ptr(out.device)))
+    return out
+
+
+def normalize(counts, out="freq64"):
+    """count matrix on the device -> frequencies (each row divided by its sum, backend.py:49)."""
+    lib = _lib.load()
+    bits = {torch.uint16: 16, torch.uint32: 32}[counts.dtype]
+    n, d = counts.shape
+    res = torch.empty((n, d), dtype=torch.float64 if out == "freq64" else torch.float32, device=counts.device)
+    with torch.cuda.device(counts.device):
+        check(lib.kam_normalize(_ptr(counts), bits, n, d, counts.stride(0) if n else d, _OUT_KINDS[out], _ptr(res), d,
+                                _stream_ptr(counts.device)))
+    return res

@@ -135,6 +135,30 @@ def test_large_k_demo_genomes(R, refcode_cases):
             assert hashlib.sha1(got[i].astype("<u2").tobytes()).hexdigest() == c["k"][str(k)]["sha1"], (c["name"], k)
 
 
+@pytest.mark.parametrize("bits", [16, 32])
+def test_cgr_pool_pyramid_and_normalize(R, demo_records, bits):
+    """kam_cgr_pool: counts(k) == pool(counts(k+1)) + fix-up, for clean, dirty (Q1) and wrapping (Q3)
+    records; kam_normalize == numpy true division."""
+    recs = [r for _, r in demo_records] + synth_records(12, 3000, seed=77, dirty=0.02, jitter=500) + \
+        [b"NNACGTACGT", b"N" * 40 + b"ACGTTGCA", b"ACG", b"", b"A" * 70000, b"ACGT" * 20000]
+    b = R.pack_records(recs)
+    hi = R.kmer_vectors(b, 9, bits, "counts")
+    for k in range(8, 0, -1):
+        lo = R.cgr_pool(b, hi, k)
+        assert torch.equal(lo.view(torch.int16 if bits == 16 else torch.int32),
+                           R.kmer_vectors(b, k, bits, "counts").view(torch.int16 if bits == 16 else torch.int32)), k
+        hi = lo
+    c = R.kmer_vectors(b, 5, bits, "counts")
+    f64 = R.normalize(c, "freq64").cpu().numpy()
+    cn = c.cpu().numpy()
+    with np.errstate(all="ignore"):
+        for i in range(len(recs)):
+            assert np.array_equal(f64[i], cn[i] / cn[i].sum(), equal_nan=True)
+    f32 = R.normalize(c, "freq32").cpu().numpy()
+    ok = np.isfinite(f64)
+    np.testing.assert_allclose(f32[ok], f64[ok], rtol=1e-6)
+
+
 def test_errors(R):
     b = R.pack_records([b"ACGT"])
     with pytest.raises(ValueError):
