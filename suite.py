@@ -268,7 +268,82 @@ def config5(rank, world, dev, scale):
             "kmers_per_s": world * done * L / tm, "ms": tm * 1e3, "verified": "first sequence of each rank vs oracle"}
 
 
-CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5}
+# ---- config 6: the drop-in plugin path with FILES (what `kameris run-job` executes) --------------------
+def config6(rank, world, dev, scale):
+    """tests/fixtures/hiv1-lanl-small.yml-like job on a synthetic directory: kmers (frequencies, k=9),
+    kmers (counts, k=6), distances [manhat] -- through run_backend_kmers / run_backend_dists with real
+    files, next to the reference pipeline's port (threaded C counts + the numpy loop of backend.py:45-56
+    + the same file formats), both reading the same directory."""
+    import shutil
+    import tempfile
+    from kameris_b200 import formats
+    from kameris_b200.job_steps import backend
+    if rank != 0:
+        return {}
+    n, L = int(2000 * scale) or 50, 9000
+    root = tempfile.mkdtemp(prefix="kam_suite_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        fdir = os.path.join(root, "fasta")
+        os.mkdir(fdir)
+        rng = np.random.Generator(np.random.PCG64(6))
+        alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+        for i in range(n):
+            seq = alpha[rng.choice(4, size=L, p=[0.36, 0.18, 0.24, 0.22])].tobytes()
+            with open(os.path.join(fdir, "%010d.fasta" % i), "wb") as f:      # selection.py:141-149 naming
+                f.write(b">%d\n" % i + seq + b"\n")
+        t = {}
+        t0 = time.perf_counter()
+        backend.run_backend_kmers({"fasta_output_dir": fdir, "output_file": os.path.join(root, "cgrs.mm-repr"), "k": 9,
+                                   "bits_per_element": 16, "mode": "frequencies", "disable_avx": False}, {})
+        t["ours_kmers_freq_k9_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        backend.run_backend_kmers({"fasta_output_dir": fdir, "output_file": os.path.join(root, "counts.mm-repr"), "k": 6,
+                                   "bits_per_element": 16, "mode": "counts", "disable_avx": False}, {})
+        t["ours_kmers_counts_k6_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        backend.run_backend_dists({"input_file": os.path.join(root, "counts.mm-repr"), "output_prefix": os.path.join(root, "d"),
+                                   "distances": ["manhat"], "disable_avx": False}, {})
+        t["ours_dists_manhat_s"] = time.perf_counter() - t0
+
+        # the reference pipeline (port): read files, threaded counts, numpy frequency loop, write files
+        threads = O.host_threads()
+        paths = backend.list_input_files(fdir)
+        t0 = time.perf_counter()
+        recs = [O.fasta_record0(open(p, "rb").read()) for p in paths]
+        chars = np.frombuffer(b"".join(recs), dtype=np.uint8)
+        start = np.concatenate([[0], np.cumsum([len(r) for r in recs])]).astype(np.uint64)
+        c9 = O.cgr_batch(chars, start, 9, 16, threads)
+        w = formats.repr_writer(os.path.join(root, "ref9.mm-repr"), np.zeros((1, 4 ** 9), np.uint16), n)
+        w.write_all(c9)
+        w.file.close()
+        reader = formats.repr_reader(os.path.join(root, "ref9.mm-repr"))           # backend.py:45-56 verbatim
+        cgrs = []
+        for i in range(reader.count):
+            cgr = reader.read_matrix(i)
+            cgrs.append(cgr / cgr.sum())
+        reader.file.close()
+        writer = formats.repr_writer(os.path.join(root, "ref9.mm-repr"), cgrs[0], len(cgrs), create_file=True)
+        for cgr in cgrs:
+            writer.write_matrix(cgr)
+        writer.file.close()
+        t["port_kmers_freq_k9_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        c6 = O.cgr_batch(chars, start, 6, 16, threads)
+        man, _ = O.dists_triangle(c6, True, False, threads)
+        t["port_counts_k6_plus_manhat_s"] = time.perf_counter() - t0
+
+        ok = open(os.path.join(root, "cgrs.mm-repr"), "rb").read() == open(os.path.join(root, "ref9.mm-repr"), "rb").read()
+        tri, nn = formats.dist_reader.read_triangle(os.path.join(root, "d-manhat.mm-dist"))
+        ok = ok and nn == n and np.array_equal(tri, man)
+        return {"config": 6, "what": "plugin path with files: %d FASTA files x %d bp -> .mm-repr (k=9 float64 frequencies), "
+                                     ".mm-repr (k=6 counts), -manhat.mm-dist" % (n, L),
+                "ok": bool(ok), "files_identical_to_port": bool(ok), "host_cores": threads,
+                **{k: round(v, 3) for k, v in t.items()}}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5, 6: config6}
 
 
 def main():
@@ -281,7 +356,7 @@ def main():
         t0 = time.time()
         r = CONFIGS[c](rank, world, dev, args.scale)
         torch.cuda.empty_cache()
-        if rank == 0:
+        if rank == 0 and r:
             r["wall_s"] = round(time.time() - t0, 1)
             print(json.dumps(r), flush=True)
     if world > 1:
