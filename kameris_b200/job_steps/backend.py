@@ -92,6 +92,65 @@ def kmers_from_records(records, k, bits_per_element, mode):
                          dtype=np_dt).reshape(n, 4 ** k), out
 
 
+CHUNK_BYTES = 256 << 20        # pinned staging per buffer; two buffers alternate
+
+
+def kmers_to_file(records, k, bits_per_element, mode, output_file):
+    """records -> `.mm-repr`, streamed: the batch is cut into chunks of rows; while chunk c is being
+    written to the file from one pinned buffer, chunk c+1 is produced (H2D, kernels, D2H inside
+    kam_kmers_host, which releases the GIL) into the other.  No buffer of the whole result exists."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    lib = _lib.load()
+    if not isinstance(k, int) or k < 1 or 2 * k > 64:
+        raise ValueError('k is too large to fit in the index')
+    if bits_per_element not in (16, 32):
+        raise ValueError('bits per element must be 16 or 32')
+    n, d = len(records), 4 ** k
+    lens = np.fromiter((len(r) for r in records), dtype=np.uint64, count=n)
+    start = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=start[1:])
+    chars = np.frombuffer(b''.join(records), dtype=np.uint8)
+    if mode == 'frequencies':
+        kind, tdt, ndt = _lib.KAM_OUT_FREQ_F64, torch.float64, np.float64
+    else:
+        kind = _lib.KAM_OUT_COUNTS
+        tdt, ndt = (torch.uint16, np.uint16) if bits_per_element == 16 else (torch.uint32, np.uint32)
+    rows = max(1, min(n, CHUNK_BYTES // (d * np.dtype(ndt).itemsize)))
+    bufs = []
+    for _ in range(2 if n > rows else 1):
+        t = torch.empty((rows, d), dtype=tdt)
+        try:
+            t = t.pin_memory()                    # direct DMA target; pageable also works (staged)
+        except RuntimeError:
+            pass
+        bufs.append(t)
+    writer = formats.repr_writer(output_file, np.zeros((1, d), dtype=ndt), n, create_file=True)
+
+    def view(t, m):
+        raw = (ctypes.c_char * (m * d * t.element_size())).from_address(t.data_ptr())
+        return np.frombuffer(raw, dtype=ndt).reshape(m, d)
+
+    try:
+        with ThreadPoolExecutor(max_workers=1) as wpool:
+            futs = [None, None]
+            for c, i0 in enumerate(range(0, n, rows)):
+                i1 = min(i0 + rows, n)
+                slot = c % len(bufs)
+                if futs[slot] is not None:
+                    futs[slot].result()           # the write that used this buffer has finished
+                sub = (start[i0:i1 + 1] - start[i0]).copy()
+                base = chars.ctypes.data + int(start[i0]) if chars.size else None
+                _lib.check(lib.kam_kmers_host(base, sub.ctypes.data, i1 - i0, k, bits_per_element, kind,
+                                              bufs[slot].data_ptr()))
+                futs[slot] = wpool.submit(lambda a=view(bufs[slot], i1 - i0): a.tofile(writer.file))
+            for f in futs:
+                if f is not None:
+                    f.result()
+    finally:
+        writer.file.close()
+
+
 def run_backend_kmers(options, exp_options):
     log = _log()
     t0 = time.time()
@@ -99,12 +158,7 @@ def run_backend_kmers(options, exp_options):
         paths = list_input_files(options['fasta_output_dir'])
         log.info('%d files, using B200 backend', len(paths))
         records = read_records(paths)
-        vecs, _keep = kmers_from_records(records, options['k'], options['bits_per_element'], options['mode'])
-        k = options['k']
-        example = np.zeros((1, 4 ** k), dtype=vecs.dtype)
-        writer = formats.repr_writer(options['output_file'], example, len(records), create_file=True)
-        writer.write_all(vecs)
-        writer.file.close()
+        kmers_to_file(records, options['k'], options['bits_per_element'], options['mode'], options['output_file'])
     except (_lib.KamError, ValueError, OSError) as e:
         log.error('kmers step failed: %s', e)
         raise subprocess.CalledProcessError(1, 'generation_cgr (kameris_b200)', str(e))

@@ -292,6 +292,8 @@ def config6(rank, world, dev, scale):
             with open(os.path.join(fdir, "%010d.fasta" % i), "wb") as f:      # selection.py:141-149 naming
                 f.write(b">%d\n" % i + seq + b"\n")
         t = {}
+        backend.run_backend_kmers({"fasta_output_dir": fdir, "output_file": os.path.join(root, "warm.mm-repr"), "k": 3,
+                                   "bits_per_element": 16, "mode": "counts", "disable_avx": False}, {})   # CUDA context, library
         t0 = time.perf_counter()
         backend.run_backend_kmers({"fasta_output_dir": fdir, "output_file": os.path.join(root, "cgrs.mm-repr"), "k": 9,
                                    "bits_per_element": 16, "mode": "frequencies", "disable_avx": False}, {})
