@@ -106,6 +106,16 @@ int kam_kmer_count(const uint64_t *d_planes, const uint64_t *d_base_start,
                    int count_bits, int out_kind, void *d_out, uint64_t out_stride, void *d_ws,
                    size_t ws_bytes, void *stream);
 
+/* Every order k_lo..k_hi in one call (BASELINE config 2: k = 1..9).  h_outs is a HOST array of
+ * k_hi-k_lo+1 device pointers (order k at index k-k_lo), each a dense n_seqs x 4^k matrix.  For
+ * 8 <= k_hi <= 10 and genome-length sequences (<= 65535 bases) this is ONE fused kernel: the sequence
+ * is scanned once per shared-memory tile of the largest table and every lower order is obtained by
+ * 2x2 pooling of that tile; otherwise it runs kam_kmer_count once per order.
+ * Workspace: kam_kmer_workspace_bytes(n_seqs, k_hi). */
+int kam_kmer_sweep(const uint64_t *d_planes, const uint64_t *d_base_start, const uint32_t *d_head_mask,
+                   uint32_t n_seqs, uint64_t total_bases_hint, int k_lo, int k_hi, int count_bits,
+                   int out_kind, void *const *h_outs, void *d_ws, size_t ws_bytes, void *stream);
+
 /* Order-(k+1) count tables -> order-k tables by 2x2 sum-pooling of the CGR image plus the one k-mer
  * that has no (k+1)-mer ending at the same base; exact for dirty heads (quirk Q1) and
  * for wrapped uint16 counts.  d_in rows hold 4^(k+1) bins, d_out rows 4^k bins, both count_bits wide. */

@@ -28,6 +28,8 @@ SIGNATURES = {
     "kam_kmer_workspace_bytes": (c_size_t, [c_uint32, c_int]),
     "kam_kmer_count": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint64, c_int, c_int, c_int, c_void_p,
                                c_uint64, c_void_p, c_size_t, c_void_p]),
+    "kam_kmer_sweep": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint64, c_int, c_int, c_int, c_int, c_void_p,
+                               c_void_p, c_size_t, c_void_p]),
     "kam_cgr_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_int, c_void_p, c_uint64, c_void_p,
                              c_uint64, c_void_p]),
     "kam_normalize": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_int, c_void_p, c_uint64, c_void_p]),

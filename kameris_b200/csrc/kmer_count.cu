@@ -307,6 +307,286 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
     }
 }
 
+// ---- fused sweep: every order k_lo..k_hi from ONE scan at k_hi ---------------------
+// The 2^k x 2^k CGR image of order k is the 2x2 sum-pool of the order-(k+1) image plus the one k-mer
+// that ends at base k-1 (it has no (k+1)-mer ending there).  A shared-memory tile of the k_hi table
+// holds whole rows, so each tile can be pooled down level by level inside the CTA and every level's
+// slice streamed out while the tile is resident: the sequence is scanned once per tile of the
+// LARGEST table only, and the lower orders cost their output bytes.  Levels that shrink below one
+// row per tile (k < 2*k_hi - 15) are accumulated across tiles in a small table and finished at the
+// end of the sequence.  Dirty heads (quirk Q1): the partial k-mers of a level are added just before
+// that level is written and removed again before it is pooled.  Sequences longer than 65535 bases
+// (pooled uint16 counters) or with a uint8 overflow go to the spill list and are redone per order.
+constexpr int SW_THREADS = 256;
+constexpr int SW_MAX_K = 10;            // the table of the first order below one row per tile stays <= 256 bins
+constexpr uint32_t SW_NONE = 0xffffffffu;
+
+struct SweepPtrs {
+    void *out[16];                      // indexed by k
+};
+
+template <typename OUT>
+__device__ __forceinline__ OUT sweep_convert(uint32_t c, const OUT *lut, double sum) {
+    if constexpr (std::is_integral<OUT>::value) return (OUT)c;
+    else return c < 256u ? lut[c] : convert_count<OUT>(c, 0.0, sum);
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(SW_THREADS) cgr_sweep_kernel(const uint2 *__restrict__ planes,
+                                                               const uint64_t *__restrict__ base_start,
+                                                               const uint32_t *__restrict__ head_mask, uint32_t n_seqs,
+                                                               int k_hi, int k_lo, SweepPtrs so,
+                                                               uint32_t *__restrict__ queue,
+                                                               uint32_t *__restrict__ spill_count,
+                                                               uint32_t *__restrict__ spill_list,
+                                                               unsigned long long *__restrict__ spill_maxlen) {
+    constexpr bool IS_FREQ = !std::is_integral<OUT>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *tab32 = reinterpret_cast<uint32_t *>(smem_raw);                                  // TILE_BINS uint8
+    unsigned short *bufA = reinterpret_cast<unsigned short *>(smem_raw + TILE_BINS);           // TILE_BINS/4 uint16
+    unsigned short *bufB = bufA + TILE_BINS / 4;                                               // TILE_BINS/16 uint16
+    uint32_t *deepA = reinterpret_cast<uint32_t *>(bufB + TILE_BINS / 16);                     // 256
+    uint32_t *deepB = deepA + 256;                                                             // 64
+    OUT *lut = reinterpret_cast<OUT *>(deepB + 64);                                            // [levels][256]
+    __shared__ uint32_t s_seq, s_flag;
+    __shared__ uint32_t s_fix[16], s_lead[16];
+    __shared__ double s_sum[16];
+
+    const uint32_t bins_hi = 1u << (2 * k_hi);
+    const uint32_t n_tiles = bins_hi / TILE_BINS;                 // k_hi >= 8
+    const uint32_t tbits = (uint32_t)(2 * k_hi - TILE_BINS_LOG2);
+    const int k1 = (int)tbits;                                    // order at which a tile holds exactly one row
+    const uint32_t mask = (1u << k_hi) - 1u;
+    const uint32_t ysh = (uint32_t)(TILE_BINS_LOG2 - k_hi), ylow = (1u << ysh) - 1u;
+
+    for (uint32_t i = threadIdx.x; i < TILE_BINS / 4; i += SW_THREADS) tab32[i] = 0;
+    for (uint32_t i = threadIdx.x; i < 256 + 64; i += SW_THREADS) deepA[i] = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_seq = atomicAdd(queue, 1u);
+            s_flag = 0;
+        }
+        __syncthreads();
+        const uint32_t s = s_seq;
+        if (s >= n_seqs) break;
+        const uint64_t p0 = base_start[s], n = base_start[s + 1] - p0;
+        const uint32_t hm = head_mask[s];
+        if (n > 65535) {
+            if (threadIdx.x == 0) {
+                spill_list[atomicAdd(spill_count, 1u)] = s;
+                atomicMax(spill_maxlen, (unsigned long long)n);
+            }
+            continue;
+        }
+        // per-level constants: emit threshold, divisor, the k-mer ending at base k-1, quotient LUT
+        if (threadIdx.x >= (uint32_t)k_lo && threadIdx.x <= (uint32_t)k_hi) {
+            const int kk = (int)threadIdx.x;
+            const uint32_t lead = __popc(hm & ((kk > 1 ? (1u << (kk - 1)) : 1u) - 1u));
+            s_lead[kk] = lead;
+            s_sum[kk] = (double)(n > lead ? n - lead : 0);
+            uint32_t fix = SW_NONE;
+            if (kk < k_hi && n >= (uint64_t)kk) {
+                uint32_t x = 0, y = 0;                           // full kk-mer of bases 0..kk-1, oldest in bit 0
+                for (int t = 0; t < kk; ++t) {
+                    const uint64_t p = p0 + t;
+                    const uint2 w = planes[p >> 5];
+                    const uint32_t b = (uint32_t)(p & 31);
+                    x |= ((w.x >> b) & 1u) << t;
+                    y |= ((w.y >> b) & 1u) << t;
+                }
+                fix = (y << kk) | x;
+            }
+            s_fix[kk] = fix;
+        }
+        __syncthreads();
+        if constexpr (IS_FREQ) {
+            for (int kk = k_lo; kk <= k_hi; ++kk)
+                lut[(kk - k_lo) * 256 + threadIdx.x] = convert_count<OUT>(threadIdx.x, 0.0, s_sum[kk]);
+        }
+        SeqInfo q;
+        q.p0 = p0;
+        q.n = n;
+
+        const uint64_t pf = p0 + (uint64_t)(k_hi - 1), pe = p0 + n;
+        const bool has_full = n >= (uint64_t)k_hi;
+        const uint64_t g0 = pf >> 3, g1 = has_full ? ((pe - 1) >> 3) + 1 : g0;
+
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+            // ---- scan: full k_hi-mers that fall into tile t
+            for (uint64_t g = g0 + threadIdx.x; g < g1; g += SW_THREADS) {
+                const uint64_t W = g >> 2;
+                const uint2 hi = __ldg(planes + W);
+                const uint2 lo = W ? __ldg(planes + W - 1) : make_uint2(0, 0);
+                const uint32_t sh0 = 8u * (uint32_t)(g & 3) + 32u - (uint32_t)(k_hi - 1);
+                const uint32_t gx = (uint32_t)((((unsigned long long)hi.x << 32) | lo.x) >> sh0);
+                const uint32_t gy = (uint32_t)((((unsigned long long)hi.y << 32) | lo.y) >> sh0);
+                const uint64_t pbase = g << 3;
+                uint32_t m = 0xffu;
+                if (pbase < pf) m &= 0xffu << (uint32_t)(pf - pbase);
+                if (pbase + 8 > pe) m &= 0xffu >> (uint32_t)(pbase + 8 - pe);
+#pragma unroll 1
+                for (uint32_t i = 0; i < tbits; ++i) {
+                    const uint32_t want = 0u - ((t >> (tbits - 1 - i)) & 1u);
+                    m &= ~((gy >> (uint32_t)(k_hi - 1 - i)) ^ want);
+                }
+                while (m) {
+                    const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                    m &= m - 1u;
+                    const uint32_t yw = (gy >> b) & mask, xw = (gx >> b) & mask;
+                    bump<uint8_t>(tab32, ((yw & ylow) << k_hi) | xw, &s_flag);
+                }
+            }
+            __syncthreads();
+
+            // ---- level chain: kk = k_hi (the uint8 tile itself), then pooled uint16 levels down to
+            //      max(k_lo, k1); `cur` holds the slice [t*cur_bins, (t+1)*cur_bins) of level kk
+            unsigned short *cur16 = nullptr;
+            uint32_t cur_bins = TILE_BINS;
+            for (int kk = k_hi; kk >= k_lo && kk >= k1; --kk) {
+                if (kk < k_hi) {
+                    const uint32_t nb = cur_bins >> 2, ncols_log = (uint32_t)kk;        // destination: 2^kk columns
+                    unsigned short *dst = ((k_hi - kk) & 1) ? bufA : bufB;
+                    if (kk == k_hi - 1) {                                                 // from the uint8 tile
+                        const unsigned char *P = reinterpret_cast<const unsigned char *>(tab32);
+                        for (uint32_t i = threadIdx.x; i < nb; i += SW_THREADS) {
+                            const uint32_t y = i >> ncols_log, x = i & ((1u << ncols_log) - 1u);
+                            const uint32_t a = *reinterpret_cast<const unsigned short *>(P + ((2 * y) << (kk + 1)) + 2 * x);
+                            const uint32_t b = *reinterpret_cast<const unsigned short *>(P + ((2 * y + 1) << (kk + 1)) + 2 * x);
+                            dst[i] = (unsigned short)((a & 0xffu) + (a >> 8) + (b & 0xffu) + (b >> 8));
+                        }
+                    } else {
+                        const unsigned short *P = cur16;
+                        for (uint32_t i = threadIdx.x; i < nb; i += SW_THREADS) {
+                            const uint32_t y = i >> ncols_log, x = i & ((1u << ncols_log) - 1u);
+                            const uint32_t a = *reinterpret_cast<const uint32_t *>(P + ((2 * y) << (kk + 1)) + 2 * x);
+                            const uint32_t b = *reinterpret_cast<const uint32_t *>(P + ((2 * y + 1) << (kk + 1)) + 2 * x);
+                            dst[i] = (unsigned short)((a & 0xffffu) + (a >> 16) + (b & 0xffffu) + (b >> 16));
+                        }
+                    }
+                    cur16 = dst;
+                    cur_bins = nb;
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        const uint32_t fix = s_fix[kk];
+                        if (fix != SW_NONE && fix / cur_bins == t) cur16[fix % cur_bins] += 1;   // the k-mer ending at base kk-1
+                    }
+                }
+                const bool dirty = s_lead[kk] < (uint32_t)(kk - 1);
+                if (dirty && threadIdx.x == 0) {
+                    q.lead = s_lead[kk];
+                    head_partials(planes, q, kk, [&](uint32_t bin) {
+                        if (bin / cur_bins != t) return;
+                        const uint32_t lb = bin % cur_bins;
+                        if (kk == k_hi) bump<uint8_t>(tab32, lb, &s_flag);
+                        else cur16[lb] += 1;
+                    });
+                }
+                __syncthreads();
+                // ---- write this level's slice
+                OUT *dstrow = reinterpret_cast<OUT *>(so.out[kk]) + (uint64_t)s * ((uint64_t)1 << (2 * kk)) + (uint64_t)t * cur_bins;
+                const OUT *lk = lut + (kk - k_lo) * 256;
+                const double sum = s_sum[kk];
+                if (kk == k_hi) {
+                    constexpr int BPS = 16 / (int)sizeof(OUT);
+                    const uint32_t n_stores = cur_bins / BPS;
+                    for (uint32_t c = threadIdx.x; c < n_stores; c += SW_THREADS) {
+                        union {
+                            uint4 v;
+                            OUT e[BPS];
+                        } u;
+                        uint32_t w0 = 0, w1 = 0;
+                        if constexpr (BPS == 8) {
+                            const uint2 w = *reinterpret_cast<uint2 *>(&tab32[c * 2]);
+                            w0 = w.x, w1 = w.y;
+                        } else if constexpr (BPS == 4) {
+                            w0 = tab32[c];
+                        } else {
+                            w0 = reinterpret_cast<unsigned short *>(tab32)[c];
+                        }
+                        if constexpr (IS_FREQ) {
+#pragma unroll
+                            for (int i = 0; i < BPS; ++i) u.e[i] = lk[((i < 4 ? w0 : w1) >> (8 * (i & 3))) & 0xffu];
+                        } else if constexpr (BPS == 8) {
+                            u.v = make_uint4(__byte_perm(w0, 0, 0x4140), __byte_perm(w0, 0, 0x4342),
+                                             __byte_perm(w1, 0, 0x4140), __byte_perm(w1, 0, 0x4342));
+                        } else {
+                            u.v = make_uint4(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu, w0 >> 24);
+                        }
+                        st_stream16(dstrow + (uint64_t)c * BPS, u.v);
+                    }
+                } else {
+                    for (uint32_t i = threadIdx.x; i < cur_bins; i += SW_THREADS)
+                        __stcs(dstrow + i, sweep_convert<OUT>(cur16[i], lk, sum));
+                }
+                __syncthreads();
+                if (dirty && threadIdx.x == 0) {                 // remove the partial k-mers before pooling further
+                    q.lead = s_lead[kk];
+                    head_partials(planes, q, kk, [&](uint32_t bin) {
+                        if (bin / cur_bins != t) return;
+                        const uint32_t lb = bin % cur_bins;
+                        if (kk == k_hi) atomicSub(&tab32[lb >> 2], 1u << ((lb & 3u) * 8u));
+                        else cur16[lb] -= 1;
+                    });
+                }
+                __syncthreads();
+            }
+            // ---- below one row per tile: add this tile's order-k1 row into the order-(k1-1) table
+            if (k_lo < k1) {
+                // cur16 holds order k1: 2^k1 bins (one row, y = t); k1 < k_hi always (k_hi <= 14)
+                const uint32_t cols = 1u << k1;
+                for (uint32_t x = threadIdx.x; x < cols; x += SW_THREADS)
+                    atomicAdd(&deepA[(t >> 1) * (cols >> 1) + (x >> 1)], (uint32_t)cur16[x]);
+            }
+            for (uint32_t i = threadIdx.x; i < TILE_BINS / 4; i += SW_THREADS) tab32[i] = 0;
+            __syncthreads();
+        }
+
+        // ---- orders below k1: tiny tables, pooled sequentially
+        if (k_lo < k1) {
+            uint32_t *tbl = deepA, *oth = deepB;
+            for (int kk = k1 - 1; kk >= k_lo; --kk) {
+                const uint32_t nb = 1u << (2 * kk);
+                if (threadIdx.x == 0 && s_fix[kk] != SW_NONE) tbl[s_fix[kk]] += 1;
+                const bool dirty = s_lead[kk] < (uint32_t)(kk - 1);
+                if (dirty && threadIdx.x == 0) {
+                    q.lead = s_lead[kk];
+                    head_partials(planes, q, kk, [&](uint32_t bin) { tbl[bin] += 1; });
+                }
+                __syncthreads();
+                OUT *dstrow = reinterpret_cast<OUT *>(so.out[kk]) + (uint64_t)s * nb;
+                for (uint32_t i = threadIdx.x; i < nb; i += SW_THREADS)
+                    dstrow[i] = sweep_convert<OUT>(tbl[i], lut + (kk - k_lo) * 256, s_sum[kk]);
+                __syncthreads();
+                if (dirty && threadIdx.x == 0) {
+                    q.lead = s_lead[kk];
+                    head_partials(planes, q, kk, [&](uint32_t bin) { tbl[bin] -= 1; });
+                }
+                __syncthreads();
+                if (kk > k_lo) {
+                    const uint32_t nd = nb >> 2;
+                    for (uint32_t i = threadIdx.x; i < nd; i += SW_THREADS) {
+                        const uint32_t y = i >> (kk - 1), x = i & ((1u << (kk - 1)) - 1u);
+                        oth[i] = tbl[((2 * y) << kk) + 2 * x] + tbl[((2 * y) << kk) + 2 * x + 1] +
+                                 tbl[((2 * y + 1) << kk) + 2 * x] + tbl[((2 * y + 1) << kk) + 2 * x + 1];
+                    }
+                    __syncthreads();
+                    uint32_t *tmp = tbl;
+                    tbl = oth;
+                    oth = tmp;
+                }
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < 256 + 64; i += SW_THREADS) deepA[i] = 0;
+        }
+        if (threadIdx.x == 0 && s_flag) {
+            spill_list[atomicAdd(spill_count, 1u)] = s;
+            atomicMax(spill_maxlen, (unsigned long long)n);
+        }
+    }
+}
+
 // ---- path B ------------------------------------------------------------------------------------
 // grid (chunks, batch): CTA (c, b) counts bases [c*B_CHUNK, (c+1)*B_CHUNK) of sequence
 // spill_list[first + b] into tables[b] (4^k uint32, zeroed beforehand) with RED.ADD.
@@ -406,7 +686,7 @@ inline size_t ws_layout(uint32_t n_seqs, int k, void *base, KmerWs *w) {
     const uint32_t batch = spill_batch(k);
     void *hdr = take(64);
     void *list = take((size_t)(n_seqs ? n_seqs : 1) * 4);
-    void *sums = take((size_t)batch * 8);
+    void *sums = take((size_t)1024 * 8);   // spill_batch() never exceeds 1024 (any k: the sweep reuses this layout)
     void *tables = take((size_t)batch * (((size_t)1 << (2 * k)) * 4));
     if (w) {
         w->queue = (uint32_t *)hdr;
@@ -440,6 +720,43 @@ int launch_tile(const uint2 *planes, const uint64_t *base_start, const uint32_t 
     return KAM_OK;
 }
 
+struct SpillInfo {
+    uint32_t queue, count;
+    unsigned long long maxlen;
+};
+
+inline int read_spill(const KmerWs &w, SpillInfo *h, cudaStream_t st) {
+    KAM_CUDA(cudaMemcpyAsync(h, w.queue, 16, cudaMemcpyDeviceToHost, st));
+    KAM_CUDA(cudaStreamSynchronize(st));
+    return KAM_OK;
+}
+
+// path B over the spill list, `batch` sequences at a time so the live tables stay in L2
+template <typename OUT>
+int run_spill(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, int k, int count_bits,
+              OUT *out, uint64_t out_stride, const KmerWs &w, const SpillInfo &h, cudaStream_t st) {
+    if (h.count == 0) return KAM_OK;
+    const uint32_t bins = 1u << (2 * k);
+    const uint32_t wrapmask = count_bits == 16 ? 0xffffu : 0xffffffffu;
+    const uint32_t chunks = (uint32_t)((h.maxlen + B_CHUNK - 1) / B_CHUNK);
+    uint32_t fin_blocks = bins / 256 / 8;
+    if (fin_blocks < 1) fin_blocks = 1;
+    if (fin_blocks > 1024) fin_blocks = 1024;
+    const uint32_t batch = spill_batch(k);
+    for (uint32_t first = 0; first < h.count; first += batch) {
+        const uint32_t nb = h.count - first < batch ? h.count - first : batch;
+        KAM_CUDA(cudaMemsetAsync(w.tables, 0, (size_t)nb * bins * 4, st));
+        KAM_CUDA(cudaMemsetAsync(w.sums, 0, (size_t)nb * 8, st));
+        cgr_spill_count_kernel<<<dim3(chunks ? chunks : 1, nb), B_THREADS, 0, st>>>(
+            planes, base_start, head_mask, w.spill_list, first, k, w.tables, bins);
+        cgr_spill_sum_kernel<<<dim3(fin_blocks, nb), 256, 0, st>>>(w.tables, bins, bins, wrapmask, w.sums);
+        cgr_spill_finalize_kernel<OUT><<<dim3(fin_blocks, nb), 256, 0, st>>>(w.tables, bins, bins, wrapmask, w.sums,
+                                                                             w.spill_list, first, out, out_stride);
+        KAM_CUDA(cudaGetLastError());
+    }
+    return KAM_OK;
+}
+
 template <typename OUT>
 int run_kmer(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, uint32_t n_seqs, int k,
              int count_bits, OUT *out, uint64_t out_stride, const KmerWs &w, uint64_t total_bases_hint,
@@ -466,32 +783,38 @@ int run_kmer(const uint2 *planes, const uint64_t *base_start, const uint32_t *he
     if (rc) return rc;
     if (k <= 6) return KAM_OK;   // uint32 counters, single tile: nothing can spill, no need to look
 
-    struct {
-        uint32_t queue, count;
-        unsigned long long maxlen;
-    } h;
-    KAM_CUDA(cudaMemcpyAsync(&h, w.queue, 16, cudaMemcpyDeviceToHost, st));
-    KAM_CUDA(cudaStreamSynchronize(st));
-    if (h.count == 0) return KAM_OK;
+    SpillInfo h;
+    if ((rc = read_spill(w, &h, st))) return rc;
+    return run_spill<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, h, st);
+}
 
-    // path B over the spill list, `batch` sequences at a time so the live tables stay in L2
-    const uint32_t bins = 1u << (2 * k);
-    const uint32_t wrapmask = count_bits == 16 ? 0xffffu : 0xffffffffu;
-    const uint32_t chunks = (uint32_t)((h.maxlen + B_CHUNK - 1) / B_CHUNK);
-    uint32_t fin_blocks = bins / 256 / 8;
-    if (fin_blocks < 1) fin_blocks = 1;
-    if (fin_blocks > 1024) fin_blocks = 1024;
-    for (uint32_t first = 0; first < h.count; first += w.batch) {
-        const uint32_t nb = h.count - first < w.batch ? h.count - first : w.batch;
-        KAM_CUDA(cudaMemsetAsync(w.tables, 0, (size_t)nb * bins * 4, st));
-        KAM_CUDA(cudaMemsetAsync(w.sums, 0, (size_t)nb * 8, st));
-        cgr_spill_count_kernel<<<dim3(chunks ? chunks : 1, nb), B_THREADS, 0, st>>>(
-            planes, base_start, head_mask, w.spill_list, first, k, w.tables, bins);
-        cgr_spill_sum_kernel<<<dim3(fin_blocks, nb), 256, 0, st>>>(w.tables, bins, bins, wrapmask, w.sums);
-        cgr_spill_finalize_kernel<OUT><<<dim3(fin_blocks, nb), 256, 0, st>>>(w.tables, bins, bins, wrapmask, w.sums,
-                                                                             w.spill_list, first, out, out_stride);
-        KAM_CUDA(cudaGetLastError());
-    }
+template <typename OUT>
+int run_sweep(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, uint32_t n_seqs, int k_lo,
+              int k_hi, int count_bits, void *const *outs, const KmerWs &w, cudaStream_t st) {
+    SweepPtrs so;
+    for (int i = 0; i < 16; ++i) so.out[i] = nullptr;
+    for (int k = k_lo; k <= k_hi; ++k) so.out[k] = outs[k - k_lo];
+    KAM_CUDA(cudaMemsetAsync(w.queue, 0, 64, st));
+    const bool is_freq = !std::is_integral<OUT>::value;
+    const size_t smem = TILE_BINS + TILE_BINS / 2 + TILE_BINS / 8 + 320 * 4 +
+                        (is_freq ? (size_t)(k_hi - k_lo + 1) * 256 * sizeof(OUT) : 16);
+    auto kern = cgr_sweep_kernel<OUT>;
+    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    KAM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SW_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)kam_sm_count() * per_sm;
+    if (grid > n_seqs) grid = n_seqs;
+    kern<<<(unsigned)grid, SW_THREADS, smem, st>>>(planes, base_start, head_mask, n_seqs, k_hi, k_lo, so, w.queue,
+                                                   w.spill_count, w.spill_list, w.spill_maxlen);
+    KAM_CUDA(cudaGetLastError());
+    SpillInfo h;
+    int rc = read_spill(w, &h, st);
+    if (rc) return rc;
+    for (int k = k_lo; k <= k_hi && h.count; ++k)      // sequences the fused kernel declined: every order, path B
+        if ((rc = run_spill<OUT>(planes, base_start, head_mask, k, count_bits, (OUT *)outs[k - k_lo],
+                                 (uint64_t)1 << (2 * k), w, h, st)))
+            return rc;
     return KAM_OK;
 }
 
@@ -536,6 +859,46 @@ int kam_kmer_count(const uint64_t *d_planes, const uint64_t *d_base_start, const
     if (out_kind == KAM_OUT_FREQ_F32)
         return run_kmer<float>(pl, d_base_start, d_head_mask, n_seqs, k, count_bits, (float *)d_out, out_stride, w, total_bases_hint, st);
     return run_kmer<double>(pl, d_base_start, d_head_mask, n_seqs, k, count_bits, (double *)d_out, out_stride, w, total_bases_hint, st);
+}
+
+int kam_kmer_sweep(const uint64_t *d_planes, const uint64_t *d_base_start, const uint32_t *d_head_mask,
+                   uint32_t n_seqs, uint64_t total_bases_hint, int k_lo, int k_hi, int count_bits, int out_kind,
+                   void *const *h_outs, void *d_ws, size_t ws_bytes, void *stream) {
+    KAM_REQUIRE(k_lo >= 1 && k_lo <= k_hi, "need 1 <= k_lo <= k_hi");
+    if (2 * k_hi > 64) {
+        kam_set_error("k is too large to fit in the index");
+        return KAM_E_INVALID;
+    }
+    KAM_REQUIRE(k_hi <= 15, "k > 15 not supported by this build");
+    KAM_REQUIRE(count_bits == 16 || count_bits == 32, "count_bits must be 16 or 32");
+    KAM_REQUIRE(out_kind >= KAM_OUT_COUNTS && out_kind <= KAM_OUT_FREQ_F64, "bad out_kind");
+    KAM_REQUIRE(d_planes && d_base_start && d_head_mask && h_outs && d_ws, "null pointer");
+    for (int k = k_lo; k <= k_hi; ++k) KAM_REQUIRE(h_outs[k - k_lo], "null output pointer");
+    if (ws_bytes < kam_kmer_workspace_bytes(n_seqs, k_hi)) {
+        kam_set_error("kam_kmer_sweep: workspace too small (needs kam_kmer_workspace_bytes(n_seqs, k_hi))");
+        return KAM_E_WORKSPACE;
+    }
+    if (n_seqs == 0) return KAM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool fused = k_hi >= 8 && k_hi <= SW_MAX_K && k_lo < k_hi &&
+                       (total_bases_hint == 0 || total_bases_hint / n_seqs <= 65535);
+    if (!fused) {   // one ordinary pass per order
+        for (int k = k_lo; k <= k_hi; ++k) {
+            int rc = kam_kmer_count(d_planes, d_base_start, d_head_mask, n_seqs, total_bases_hint, k, count_bits, out_kind,
+                                    h_outs[k - k_lo], (uint64_t)1 << (2 * k), d_ws, ws_bytes, stream);
+            if (rc) return rc;
+        }
+        return KAM_OK;
+    }
+    KmerWs w;
+    ws_layout(n_seqs, k_hi, d_ws, &w);
+    const uint2 *pl = (const uint2 *)d_planes;
+    if (out_kind == KAM_OUT_COUNTS)
+        return count_bits == 16 ? run_sweep<uint16_t>(pl, d_base_start, d_head_mask, n_seqs, k_lo, k_hi, 16, h_outs, w, st)
+                                : run_sweep<uint32_t>(pl, d_base_start, d_head_mask, n_seqs, k_lo, k_hi, 32, h_outs, w, st);
+    if (out_kind == KAM_OUT_FREQ_F32)
+        return run_sweep<float>(pl, d_base_start, d_head_mask, n_seqs, k_lo, k_hi, count_bits, h_outs, w, st);
+    return run_sweep<double>(pl, d_base_start, d_head_mask, n_seqs, k_lo, k_hi, count_bits, h_outs, w, st);
 }
 
 }  // extern "C"

@@ -126,3 +126,22 @@ def normalize(counts, out="freq64"):
         check(lib.kam_normalize(_ptr(counts), bits, n, d, counts.stride(0) if n else d, _OUT_KINDS[out], _ptr(res), d,
                                 _stream_ptr(counts.device)))
     return res
+
+
+def kmer_sweep(batch, k_lo, k_hi, bits=16, out="counts", out_tensors=None, workspace=None):
+    """CGR vectors of every order k_lo..k_hi: dict k -> tensor (n_seqs, 4^k); one fused kernel for
+    8 <= k_hi <= 10 (scan once, 2x2 pooling for the lower orders), see kam_kmer_sweep."""
+    import ctypes
+    lib = _lib.load()
+    dev = batch.device
+    dtype = {"counts": torch.uint16 if bits == 16 else torch.uint32, "freq32": torch.float32,
+             "freq64": torch.float64}[out]
+    if out_tensors is None:
+        out_tensors = {k: torch.empty((batch.n_seqs, 4 ** k), dtype=dtype, device=dev) for k in range(k_lo, k_hi + 1)}
+    ptrs = (ctypes.c_void_p * (k_hi - k_lo + 1))(*[out_tensors[k].data_ptr() for k in range(k_lo, k_hi + 1)])
+    ws = workspace if workspace is not None else kmer_workspace(batch.n_seqs, k_hi, dev)
+    with torch.cuda.device(dev):
+        check(lib.kam_kmer_sweep(_ptr(batch.planes), _ptr(batch.base_start), _ptr(batch.head_mask), batch.n_seqs,
+                                 batch.total_chars, k_lo, k_hi, bits, _OUT_KINDS[out], ptrs, _ptr(ws), ws.numel(),
+                                 _stream_ptr(dev)))
+    return out_tensors

@@ -159,6 +159,33 @@ def test_cgr_pool_pyramid_and_normalize(R, demo_records, bits):
     np.testing.assert_allclose(f32[ok], f64[ok], rtol=1e-6)
 
 
+@pytest.mark.parametrize("out,bits", [("counts", 16), ("counts", 32), ("freq32", 16), ("freq64", 16)])
+@pytest.mark.parametrize("k_hi", [8, 9, 10])
+def test_fused_sweep_vs_oracle(R, demo_records, out, bits, k_hi):
+    """kam_kmer_sweep (one scan at k_hi, every lower order by in-kernel 2x2 pooling) == the oracle at
+    every order, for clean and dirty records (Q1 partial k-mers at each level), records shorter than
+    k, and records the fused kernel declines (> 65535 bases, uint8 overflow) and redoes per order."""
+    recs = [r for _, r in demo_records] + synth_records(20, 9000, seed=400 + k_hi, dirty=0.003, p=HIV_P, jitter=2000) + \
+        [b"NNACGTACGTAC", b"N" * 40 + b"ACGTTGCAAC", b"ACG", b"", b"ACGTAC", b"A" * 70000, b"ACGT" * 300,
+         b"T" * 3000, synth_records(1, 90000, seed=9)[0]]
+    b = R.pack_records(recs)
+    res = R.kmer_sweep(b, 1, k_hi, bits, out)
+    for k in range(1, k_hi + 1):
+        got = res[k].cpu().numpy()
+        for i, r in enumerate(recs):
+            c = O.cgr_count(r, k, bits)
+            if out == "counts":
+                assert np.array_equal(got[i], c), (k, i)
+            else:
+                with np.errstate(all="ignore"):
+                    ref = O.frequencies(c)
+                if out == "freq64":
+                    assert np.array_equal(got[i], ref, equal_nan=True), (k, i)
+                else:
+                    ok = np.isfinite(ref)
+                    np.testing.assert_allclose(got[i][ok], ref[ok], rtol=1e-6, atol=0, err_msg=str((k, i)))
+
+
 def test_errors(R):
     b = R.pack_records([b"ACGT"])
     with pytest.raises(ValueError):
