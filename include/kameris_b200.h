@@ -107,14 +107,17 @@ int kam_kmer_count(const uint64_t *d_planes, const uint64_t *d_base_start,
                    size_t ws_bytes, void *stream);
 
 /* Every order k_lo..k_hi in one call (BASELINE config 2: k = 1..9).  h_outs is a HOST array of
- * k_hi-k_lo+1 device pointers (order k at index k-k_lo), each a dense n_seqs x 4^k matrix.  For
- * 8 <= k_hi <= 10 and genome-length sequences (<= 65535 bases) this is ONE fused kernel: the sequence
- * is scanned once per shared-memory tile of the largest table and every lower order is obtained by
- * 2x2 pooling of that tile; otherwise it runs kam_kmer_count once per order.
- * Workspace: kam_kmer_workspace_bytes(n_seqs, k_hi). */
+ * k_hi-k_lo+1 device pointers (order k at index k-k_lo), each a dense n_seqs x 4^k matrix.  Orders
+ * >= 8 run the ordinary tiled kernel (they are output-bound); for genome-length sequences (<= 65535
+ * bases) the orders <= 7 come from ONE fused kernel: a single scan at order 7, whose table fits one
+ * shared-memory tile, and every lower order by 2x2 pooling of that tile inside the CTA (SURVEY.md
+ * A.3), so orders 1..6 cost only their output bytes.  Workspace: kam_kmer_workspace_bytes(n_seqs, k_hi). */
 int kam_kmer_sweep(const uint64_t *d_planes, const uint64_t *d_base_start, const uint32_t *d_head_mask,
                    uint32_t n_seqs, uint64_t total_bases_hint, int k_lo, int k_hi, int count_bits,
                    int out_kind, void *const *h_outs, void *d_ws, size_t ws_bytes, void *stream);
+
+/* tuning / test hook: top order of the fused part of kam_kmer_sweep (6..10, default 7). */
+void kam_kmer_sweep_set_fused_top(int k);
 
 /* Order-(k+1) count tables -> order-k tables by 2x2 sum-pooling of the CGR image plus the one k-mer
  * that has no (k+1)-mer ending at the same base; exact for dirty heads (quirk Q1) and

@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
 // that level is written and removed again before it is pooled.  Sequences longer than 65535 bases
 // (pooled uint16 counters) or with a uint8 overflow go to the spill list and are redone per order.
 constexpr int SW_THREADS = 256;
-constexpr int SW_MAX_K = 10;            // the table of the first order below one row per tile stays <= 256 bins
+constexpr int SW_MAX_K = 10;            // fused top order limit: the first order below one row per tile stays <= 256 bins
+int g_sweep_top = 7;                    // top order of the fused part (tuning / test hook)
 constexpr uint32_t SW_NONE = 0xffffffffu;
 
 struct SweepPtrs {
@@ -341,25 +342,29 @@ __global__ void __launch_bounds__(SW_THREADS) cgr_sweep_kernel(const uint2 *__re
                                                                uint32_t *__restrict__ spill_list,
                                                                unsigned long long *__restrict__ spill_maxlen) {
     constexpr bool IS_FREQ = !std::is_integral<OUT>::value;
+    constexpr int BPS = 16 / (int)sizeof(OUT);
+    // tile geometry: the whole table when it has <= 32768 bins (k_hi <= 7), else 32768-bin row blocks
+    const uint32_t bins_hi = 1u << (2 * k_hi);
+    const uint32_t tile_log2 = 2 * k_hi < TILE_BINS_LOG2 ? (uint32_t)(2 * k_hi) : (uint32_t)TILE_BINS_LOG2;
+    const uint32_t tile_bins = 1u << tile_log2;
+    const uint32_t n_tiles = bins_hi / tile_bins;
+    const uint32_t tbits = (uint32_t)(2 * k_hi) - tile_log2;     // log2(n_tiles)
+    const int k1 = (int)tbits;                                    // order at which a tile holds exactly one row
+    const uint32_t mask = (1u << k_hi) - 1u;
+    const uint32_t ysh = tile_log2 - (uint32_t)k_hi, ylow = (1u << ysh) - 1u;
+
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *tab32 = reinterpret_cast<uint32_t *>(smem_raw);                                  // TILE_BINS uint8
-    unsigned short *bufA = reinterpret_cast<unsigned short *>(smem_raw + TILE_BINS);           // TILE_BINS/4 uint16
-    unsigned short *bufB = bufA + TILE_BINS / 4;                                               // TILE_BINS/16 uint16
-    uint32_t *deepA = reinterpret_cast<uint32_t *>(bufB + TILE_BINS / 16);                     // 256
+    uint32_t *tab32 = reinterpret_cast<uint32_t *>(smem_raw);                                  // tile_bins uint8
+    unsigned short *bufA = reinterpret_cast<unsigned short *>(smem_raw + tile_bins);           // tile_bins/4 uint16
+    unsigned short *bufB = bufA + tile_bins / 4;                                               // tile_bins/16 uint16
+    uint32_t *deepA = reinterpret_cast<uint32_t *>(smem_raw + tile_bins + tile_bins / 2 + tile_bins / 8);   // 256
     uint32_t *deepB = deepA + 256;                                                             // 64
     OUT *lut = reinterpret_cast<OUT *>(deepB + 64);                                            // [levels][256]
     __shared__ uint32_t s_seq, s_flag;
     __shared__ uint32_t s_fix[16], s_lead[16];
     __shared__ double s_sum[16];
 
-    const uint32_t bins_hi = 1u << (2 * k_hi);
-    const uint32_t n_tiles = bins_hi / TILE_BINS;                 // k_hi >= 8
-    const uint32_t tbits = (uint32_t)(2 * k_hi - TILE_BINS_LOG2);
-    const int k1 = (int)tbits;                                    // order at which a tile holds exactly one row
-    const uint32_t mask = (1u << k_hi) - 1u;
-    const uint32_t ysh = (uint32_t)(TILE_BINS_LOG2 - k_hi), ylow = (1u << ysh) - 1u;
-
-    for (uint32_t i = threadIdx.x; i < TILE_BINS / 4; i += SW_THREADS) tab32[i] = 0;
+    for (uint32_t i = threadIdx.x; i < tile_bins / 4; i += SW_THREADS) tab32[i] = 0;
     for (uint32_t i = threadIdx.x; i < 256 + 64; i += SW_THREADS) deepA[i] = 0;
 
     for (;;) {
@@ -408,6 +413,8 @@ __global__ void __launch_bounds__(SW_THREADS) cgr_sweep_kernel(const uint2 *__re
         SeqInfo q;
         q.p0 = p0;
         q.n = n;
+        bool any_dirty = false;
+        for (int kk = k_lo; kk <= k_hi; ++kk) any_dirty |= s_lead[kk] < (uint32_t)(kk - 1);
 
         const uint64_t pf = p0 + (uint64_t)(k_hi - 1), pe = p0 + n;
         const bool has_full = n >= (uint64_t)k_hi;
@@ -441,20 +448,24 @@ __global__ void __launch_bounds__(SW_THREADS) cgr_sweep_kernel(const uint2 *__re
             __syncthreads();
 
             // ---- level chain: kk = k_hi (the uint8 tile itself), then pooled uint16 levels down to
-            //      max(k_lo, k1); `cur` holds the slice [t*cur_bins, (t+1)*cur_bins) of level kk
+            //      max(k_lo, k1); `cur` holds the slice [t*cur_bins, (t+1)*cur_bins) of level kk.
+            //      One barrier per level: level kk-1 is pooled (into the other buffer) by threads that
+            //      may still be overtaken by threads writing level kk out -- both only READ level kk.
             unsigned short *cur16 = nullptr;
-            uint32_t cur_bins = TILE_BINS;
+            uint32_t cur_bins = tile_bins;
             for (int kk = k_hi; kk >= k_lo && kk >= k1; --kk) {
                 if (kk < k_hi) {
                     const uint32_t nb = cur_bins >> 2, ncols_log = (uint32_t)kk;        // destination: 2^kk columns
                     unsigned short *dst = ((k_hi - kk) & 1) ? bufA : bufB;
+                    const uint32_t fix = s_fix[kk];
+                    const uint32_t fix_l = (fix != SW_NONE && fix / nb == t) ? fix % nb : SW_NONE;   // the k-mer ending at base kk-1
                     if (kk == k_hi - 1) {                                                 // from the uint8 tile
                         const unsigned char *P = reinterpret_cast<const unsigned char *>(tab32);
                         for (uint32_t i = threadIdx.x; i < nb; i += SW_THREADS) {
                             const uint32_t y = i >> ncols_log, x = i & ((1u << ncols_log) - 1u);
                             const uint32_t a = *reinterpret_cast<const unsigned short *>(P + ((2 * y) << (kk + 1)) + 2 * x);
                             const uint32_t b = *reinterpret_cast<const unsigned short *>(P + ((2 * y + 1) << (kk + 1)) + 2 * x);
-                            dst[i] = (unsigned short)((a & 0xffu) + (a >> 8) + (b & 0xffu) + (b >> 8));
+                            dst[i] = (unsigned short)((a & 0xffu) + (a >> 8) + (b & 0xffu) + (b >> 8) + (i == fix_l ? 1u : 0u));
                         }
                     } else {
                         const unsigned short *P = cur16;
@@ -462,34 +473,32 @@ __global__ void __launch_bounds__(SW_THREADS) cgr_sweep_kernel(const uint2 *__re
                             const uint32_t y = i >> ncols_log, x = i & ((1u << ncols_log) - 1u);
                             const uint32_t a = *reinterpret_cast<const uint32_t *>(P + ((2 * y) << (kk + 1)) + 2 * x);
                             const uint32_t b = *reinterpret_cast<const uint32_t *>(P + ((2 * y + 1) << (kk + 1)) + 2 * x);
-                            dst[i] = (unsigned short)((a & 0xffffu) + (a >> 16) + (b & 0xffffu) + (b >> 16));
+                            dst[i] = (unsigned short)((a & 0xffffu) + (a >> 16) + (b & 0xffffu) + (b >> 16) + (i == fix_l ? 1u : 0u));
                         }
                     }
                     cur16 = dst;
                     cur_bins = nb;
                     __syncthreads();
+                }
+                const bool dirty = any_dirty && s_lead[kk] < (uint32_t)(kk - 1);   // CTA-uniform
+                if (dirty) {
                     if (threadIdx.x == 0) {
-                        const uint32_t fix = s_fix[kk];
-                        if (fix != SW_NONE && fix / cur_bins == t) cur16[fix % cur_bins] += 1;   // the k-mer ending at base kk-1
+                        q.lead = s_lead[kk];
+                        head_partials(planes, q, kk, [&](uint32_t bin) {
+                            if (bin / cur_bins != t) return;
+                            const uint32_t lb = bin % cur_bins;
+                            if (kk == k_hi) bump<uint8_t>(tab32, lb, &s_flag);
+                            else cur16[lb] += 1;
+                        });
                     }
+                    __syncthreads();
                 }
-                const bool dirty = s_lead[kk] < (uint32_t)(kk - 1);
-                if (dirty && threadIdx.x == 0) {
-                    q.lead = s_lead[kk];
-                    head_partials(planes, q, kk, [&](uint32_t bin) {
-                        if (bin / cur_bins != t) return;
-                        const uint32_t lb = bin % cur_bins;
-                        if (kk == k_hi) bump<uint8_t>(tab32, lb, &s_flag);
-                        else cur16[lb] += 1;
-                    });
-                }
-                __syncthreads();
                 // ---- write this level's slice
                 OUT *dstrow = reinterpret_cast<OUT *>(so.out[kk]) + (uint64_t)s * ((uint64_t)1 << (2 * kk)) + (uint64_t)t * cur_bins;
                 const OUT *lk = lut + (kk - k_lo) * 256;
                 const double sum = s_sum[kk];
-                if (kk == k_hi) {
-                    constexpr int BPS = 16 / (int)sizeof(OUT);
+                const bool vec_ok = cur_bins % BPS == 0 && ((reinterpret_cast<uintptr_t>(dstrow) & 15) == 0);
+                if (kk == k_hi && vec_ok) {
                     const uint32_t n_stores = cur_bins / BPS;
                     for (uint32_t c = threadIdx.x; c < n_stores; c += SW_THREADS) {
                         union {
@@ -516,30 +525,45 @@ __global__ void __launch_bounds__(SW_THREADS) cgr_sweep_kernel(const uint2 *__re
                         }
                         st_stream16(dstrow + (uint64_t)c * BPS, u.v);
                     }
+                } else if (kk < k_hi && vec_ok) {
+                    const uint32_t n_stores = cur_bins / BPS;
+                    for (uint32_t c = threadIdx.x; c < n_stores; c += SW_THREADS) {
+                        union {
+                            uint4 v;
+                            OUT e[BPS];
+                        } u;
+#pragma unroll
+                        for (int i = 0; i < BPS; ++i) u.e[i] = sweep_convert<OUT>(cur16[c * BPS + i], lk, sum);
+                        st_stream16(dstrow + (uint64_t)c * BPS, u.v);
+                    }
                 } else {
-                    for (uint32_t i = threadIdx.x; i < cur_bins; i += SW_THREADS)
-                        __stcs(dstrow + i, sweep_convert<OUT>(cur16[i], lk, sum));
+                    for (uint32_t i = threadIdx.x; i < cur_bins; i += SW_THREADS) {
+                        const uint32_t c = kk == k_hi ? reinterpret_cast<const unsigned char *>(tab32)[i] : cur16[i];
+                        dstrow[i] = sweep_convert<OUT>(c, lk, sum);
+                    }
                 }
-                __syncthreads();
-                if (dirty && threadIdx.x == 0) {                 // remove the partial k-mers before pooling further
-                    q.lead = s_lead[kk];
-                    head_partials(planes, q, kk, [&](uint32_t bin) {
-                        if (bin / cur_bins != t) return;
-                        const uint32_t lb = bin % cur_bins;
-                        if (kk == k_hi) atomicSub(&tab32[lb >> 2], 1u << ((lb & 3u) * 8u));
-                        else cur16[lb] -= 1;
-                    });
+                if (dirty) {                                      // remove the partial k-mers before pooling further
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        q.lead = s_lead[kk];
+                        head_partials(planes, q, kk, [&](uint32_t bin) {
+                            if (bin / cur_bins != t) return;
+                            const uint32_t lb = bin % cur_bins;
+                            if (kk == k_hi) atomicSub(&tab32[lb >> 2], 1u << ((lb & 3u) * 8u));
+                            else cur16[lb] -= 1;
+                        });
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
             // ---- below one row per tile: add this tile's order-k1 row into the order-(k1-1) table
             if (k_lo < k1) {
-                // cur16 holds order k1: 2^k1 bins (one row, y = t); k1 < k_hi always (k_hi <= 14)
-                const uint32_t cols = 1u << k1;
+                const uint32_t cols = 1u << k1;                  // cur16 holds order k1: one row, y = t
                 for (uint32_t x = threadIdx.x; x < cols; x += SW_THREADS)
                     atomicAdd(&deepA[(t >> 1) * (cols >> 1) + (x >> 1)], (uint32_t)cur16[x]);
             }
-            for (uint32_t i = threadIdx.x; i < TILE_BINS / 4; i += SW_THREADS) tab32[i] = 0;
+            __syncthreads();                                      // every reader of the tile is done
+            for (uint32_t i = threadIdx.x; i < tile_bins / 4; i += SW_THREADS) tab32[i] = 0;
             __syncthreads();
         }
 
@@ -548,18 +572,19 @@ __global__ void __launch_bounds__(SW_THREADS) cgr_sweep_kernel(const uint2 *__re
             uint32_t *tbl = deepA, *oth = deepB;
             for (int kk = k1 - 1; kk >= k_lo; --kk) {
                 const uint32_t nb = 1u << (2 * kk);
-                if (threadIdx.x == 0 && s_fix[kk] != SW_NONE) tbl[s_fix[kk]] += 1;
-                const bool dirty = s_lead[kk] < (uint32_t)(kk - 1);
-                if (dirty && threadIdx.x == 0) {
-                    q.lead = s_lead[kk];
-                    head_partials(planes, q, kk, [&](uint32_t bin) { tbl[bin] += 1; });
+                if (threadIdx.x == 0) {
+                    if (s_fix[kk] != SW_NONE) tbl[s_fix[kk]] += 1;
+                    if (s_lead[kk] < (uint32_t)(kk - 1)) {
+                        q.lead = s_lead[kk];
+                        head_partials(planes, q, kk, [&](uint32_t bin) { tbl[bin] += 1; });
+                    }
                 }
                 __syncthreads();
                 OUT *dstrow = reinterpret_cast<OUT *>(so.out[kk]) + (uint64_t)s * nb;
                 for (uint32_t i = threadIdx.x; i < nb; i += SW_THREADS)
                     dstrow[i] = sweep_convert<OUT>(tbl[i], lut + (kk - k_lo) * 256, s_sum[kk]);
                 __syncthreads();
-                if (dirty && threadIdx.x == 0) {
+                if (threadIdx.x == 0 && s_lead[kk] < (uint32_t)(kk - 1)) {
                     q.lead = s_lead[kk];
                     head_partials(planes, q, kk, [&](uint32_t bin) { tbl[bin] -= 1; });
                 }
@@ -796,7 +821,8 @@ int run_sweep(const uint2 *planes, const uint64_t *base_start, const uint32_t *h
     for (int k = k_lo; k <= k_hi; ++k) so.out[k] = outs[k - k_lo];
     KAM_CUDA(cudaMemsetAsync(w.queue, 0, 64, st));
     const bool is_freq = !std::is_integral<OUT>::value;
-    const size_t smem = TILE_BINS + TILE_BINS / 2 + TILE_BINS / 8 + 320 * 4 +
+    const size_t tile_bins = (size_t)1 << (2 * k_hi < TILE_BINS_LOG2 ? 2 * k_hi : TILE_BINS_LOG2);
+    const size_t smem = tile_bins + tile_bins / 2 + tile_bins / 8 + 320 * 4 +
                         (is_freq ? (size_t)(k_hi - k_lo + 1) * 256 * sizeof(OUT) : 16);
     auto kern = cgr_sweep_kernel<OUT>;
     KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -880,16 +906,19 @@ int kam_kmer_sweep(const uint64_t *d_planes, const uint64_t *d_base_start, const
     }
     if (n_seqs == 0) return KAM_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fused = k_hi >= 8 && k_hi <= SW_MAX_K && k_lo < k_hi &&
-                       (total_bases_hint == 0 || total_bases_hint / n_seqs <= 65535);
-    if (!fused) {   // one ordinary pass per order
-        for (int k = k_lo; k <= k_hi; ++k) {
-            int rc = kam_kmer_count(d_planes, d_base_start, d_head_mask, n_seqs, total_bases_hint, k, count_bits, out_kind,
-                                    h_outs[k - k_lo], (uint64_t)1 << (2 * k), d_ws, ws_bytes, stream);
-            if (rc) return rc;
-        }
-        return KAM_OK;
+    // orders >= 8 (a vector is >= 256 KB: output-bound) run the ordinary tiled kernel; the orders below
+    // come from ONE scan at order min(k_hi, 7) whose table fits a single shared-memory tile, pooled down
+    // inside the CTA.  The fused part needs genome-length sequences (pooled uint16 counters, uint8 top).
+    const int top = g_sweep_top < 6 ? 6 : (g_sweep_top > SW_MAX_K ? SW_MAX_K : g_sweep_top);
+    const int kf = k_hi < top ? k_hi : top;                   // top order of the fused part
+    const bool fused = kf >= 6 && k_lo < kf && (total_bases_hint == 0 || total_bases_hint / n_seqs <= 65535);
+    for (int k = k_hi; k >= k_lo && (k > kf || !fused); --k) {
+        int rc = kam_kmer_count(d_planes, d_base_start, d_head_mask, n_seqs, total_bases_hint, k, count_bits, out_kind,
+                                h_outs[k - k_lo], (uint64_t)1 << (2 * k), d_ws, ws_bytes, stream);
+        if (rc) return rc;
     }
+    if (!fused) return KAM_OK;
+    k_hi = kf;
     KmerWs w;
     ws_layout(n_seqs, k_hi, d_ws, &w);
     const uint2 *pl = (const uint2 *)d_planes;
@@ -900,5 +929,9 @@ int kam_kmer_sweep(const uint64_t *d_planes, const uint64_t *d_base_start, const
         return run_sweep<float>(pl, d_base_start, d_head_mask, n_seqs, k_lo, k_hi, count_bits, h_outs, w, st);
     return run_sweep<double>(pl, d_base_start, d_head_mask, n_seqs, k_lo, k_hi, count_bits, h_outs, w, st);
 }
+
+// tuning / test hook: top order of the fused part of kam_kmer_sweep (default 7; 8..10 fuse the tiled
+// orders too, which was measured slower: fewer CTAs fit per SM next to the pooling buffers)
+void kam_kmer_sweep_set_fused_top(int k) { g_sweep_top = k; }
 
 }  // extern "C"

@@ -127,9 +127,8 @@ def config2(rank, world, dev, scale):
     outs = {k: torch.empty((n, 4 ** k), dtype=torch.float32, device=dev) for k in range(1, 10)}
     wss = {k: R.kmer_workspace(n, k, dev) for k in range(1, 10)}
 
-    def sweep():
-        for k in range(1, 10):
-            R.kmer_vectors(b, k, 16, "freq32", out_tensor=outs[k], workspace=wss[k])
+    def sweep():      # one fused kernel: scan at k=9, orders 8..1 by in-kernel 2x2 pooling
+        R.kmer_sweep(b, 1, 9, 16, "freq32", out_tensors=outs, workspace=wss[9])
     sweep()
     _, t = timed(sweep, dev, world)
     rng = np.random.Generator(np.random.PCG64(1))

@@ -160,8 +160,8 @@ def test_cgr_pool_pyramid_and_normalize(R, demo_records, bits):
 
 
 @pytest.mark.parametrize("out,bits", [("counts", 16), ("counts", 32), ("freq32", 16), ("freq64", 16)])
-@pytest.mark.parametrize("k_hi", [8, 9, 10])
-def test_fused_sweep_vs_oracle(R, demo_records, out, bits, k_hi):
+@pytest.mark.parametrize("k_hi,top", [(7, 7), (9, 7), (9, 9), (10, 10), (8, 8), (6, 6)])
+def test_fused_sweep_vs_oracle(R, demo_records, out, bits, k_hi, top):
     """kam_kmer_sweep (one scan at k_hi, every lower order by in-kernel 2x2 pooling) == the oracle at
     every order, for clean and dirty records (Q1 partial k-mers at each level), records shorter than
     k, and records the fused kernel declines (> 65535 bases, uint8 overflow) and redoes per order."""
@@ -169,7 +169,12 @@ def test_fused_sweep_vs_oracle(R, demo_records, out, bits, k_hi):
         [b"NNACGTACGTAC", b"N" * 40 + b"ACGTTGCAAC", b"ACG", b"", b"ACGTAC", b"A" * 70000, b"ACGT" * 300,
          b"T" * 3000, synth_records(1, 90000, seed=9)[0]]
     b = R.pack_records(recs)
-    res = R.kmer_sweep(b, 1, k_hi, bits, out)
+    from kameris_b200 import _lib
+    _lib.load().kam_kmer_sweep_set_fused_top(top)      # 7 = default hybrid; 8..10 also fuse the tiled orders
+    try:
+        res = R.kmer_sweep(b, 1, k_hi, bits, out)
+    finally:
+        _lib.load().kam_kmer_sweep_set_fused_top(7)
     for k in range(1, k_hi + 1):
         got = res[k].cpu().numpy()
         for i, r in enumerate(recs):
