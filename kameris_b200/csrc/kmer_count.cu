@@ -307,6 +307,171 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
     }
 }
 
+// ---- path A for short reads at k <= 6: one WARP per read ---------------------------------------------
+// A 150 bp read has ~18 groups of 8 k-mers and a 4096-bin table: a CTA per read spends its time in
+// barriers and dependent global-load latencies, and uint32 counters cost 32 KB of shared-memory
+// traffic per read for the read-out alone.  Here every warp owns a private table of 4^k uint8 counters
+// (4 KB at k=6; a read of <= 255 bases cannot overflow them), grabs QB reads per global atomic, fetches
+// the QB+1 offsets and head masks with ONE coalesced load (lane i <- read s0+i) and only ever needs
+// __syncwarp.  The read-out is 16-byte streaming stores in the output type, exactly one write per byte
+// of the output.  Longer reads in the batch: counters are checked for the 255 -> 256 carry and the read
+// is redone on path B.
+constexpr int WK_WARPS = 8;
+constexpr uint32_t WK_QB = 8;
+int g_warp_path = 1;                    // test hook: 0 = short reads at k <= 6 use the CTA-per-read kernel
+
+template <bool CHECK>
+__device__ __forceinline__ uint32_t warp_scan_read(const uint2 *__restrict__ planes, const SeqInfo &q, int k,
+                                                   uint32_t *tab32, uint32_t lane) {
+    const uint32_t mask = (1u << k) - 1u;
+    const uint64_t pf = q.p0 + (uint64_t)(k - 1), pe = q.p0 + q.n;
+    uint32_t over = 0;
+    if (q.n >= (uint64_t)k) {
+        const uint64_t g0 = pf >> 3, g1 = ((pe - 1) >> 3) + 1;
+        for (uint64_t g = g0 + lane; g < g1; g += 32) {
+            const uint64_t W = g >> 2;
+            const uint2 hi = __ldg(planes + W);
+            const uint2 lo = W ? __ldg(planes + W - 1) : make_uint2(0, 0);
+            const uint32_t sh0 = 8u * (uint32_t)(g & 3) + 32u - (uint32_t)(k - 1);
+            const uint32_t gx = (uint32_t)((((unsigned long long)hi.x << 32) | lo.x) >> sh0);
+            const uint32_t gy = (uint32_t)((((unsigned long long)hi.y << 32) | lo.y) >> sh0);
+            const uint64_t pbase = g << 3;
+            uint32_t m = 0xffu;
+            if (pbase < pf) m &= 0xffu << (uint32_t)(pf - pbase);
+            if (pbase + 8 > pe) m &= 0xffu >> (uint32_t)(pbase + 8 - pe);
+            while (m) {
+                const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                const uint32_t lb = (((gy >> b) & mask) << k) | ((gx >> b) & mask);
+                const uint32_t bsh = (lb & 3u) * 8u;
+                if constexpr (CHECK) {
+                    const uint32_t old = atomicAdd(&tab32[lb >> 2], 1u << bsh);
+                    over |= (((old >> bsh) & 0xffu) == 0xffu);
+                } else {
+                    atomicAdd(&tab32[lb >> 2], 1u << bsh);   // result unused
+                }
+            }
+        }
+    }
+    if (lane == 0 && q.lead < (uint32_t)(k - 1)) {   // dirty head (rare)
+        head_partials(planes, q, k, [&](uint32_t bin) {
+            const uint32_t bsh = (bin & 3u) * 8u;
+            const uint32_t old = atomicAdd(&tab32[bin >> 2], 1u << bsh);
+            over |= (((old >> bsh) & 0xffu) == 0xffu);
+        });
+    }
+    return over;
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(WK_WARPS * 32) cgr_warp_kernel(const uint2 *__restrict__ planes,
+                                                                 const uint64_t *__restrict__ base_start,
+                                                                 const uint32_t *__restrict__ head_mask,
+                                                                 uint32_t n_seqs, int k, OUT *__restrict__ out,
+                                                                 uint64_t out_stride, uint32_t *__restrict__ queue,
+                                                                 uint32_t *__restrict__ spill_count,
+                                                                 uint32_t *__restrict__ spill_list,
+                                                                 unsigned long long *__restrict__ spill_maxlen) {
+    constexpr bool IS_FREQ = !std::is_integral<OUT>::value;
+    constexpr int BPS = 16 / (int)sizeof(OUT);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t bins = 1u << (2 * k);
+    const uint32_t tab_bytes = bins < 16u ? 16u : bins;
+    const uint32_t per_warp = tab_bytes + (IS_FREQ ? 256u * (uint32_t)sizeof(OUT) : 0u);
+    uint32_t *tab32 = reinterpret_cast<uint32_t *>(smem_raw + (size_t)warp * per_warp);
+    OUT *lut = reinterpret_cast<OUT *>(smem_raw + (size_t)warp * per_warp + tab_bytes);
+    (void)lut;
+    for (uint32_t i = lane; i < tab_bytes / 4; i += 32) tab32[i] = 0;
+    __syncwarp();
+
+    for (;;) {
+        uint32_t s0 = 0;
+        if (lane == 0) s0 = atomicAdd(queue, WK_QB);
+        s0 = __shfl_sync(0xffffffffu, s0, 0);
+        if (s0 >= n_seqs) break;
+        const uint32_t nb = n_seqs - s0 < WK_QB ? n_seqs - s0 : WK_QB;
+        const unsigned long long bs_l = lane <= nb ? base_start[s0 + lane] : 0ull;
+        const uint32_t hm_l = lane < nb ? head_mask[s0 + lane] : 0u;
+        for (uint32_t r = 0; r < nb; ++r) {
+            const uint32_t s = s0 + r;
+            SeqInfo q;
+            q.p0 = __shfl_sync(0xffffffffu, bs_l, (int)r);
+            q.n = __shfl_sync(0xffffffffu, bs_l, (int)r + 1) - q.p0;
+            q.lead = __popc(__shfl_sync(0xffffffffu, hm_l, (int)r) & ((k > 1 ? (1u << (k - 1)) : 1u) - 1u));
+            OUT *row = out + (uint64_t)s * out_stride;
+            if (q.n > 64ull * bins && q.n > 255) {   // mean count > 64: uint8 would overflow, straight to path B
+                if (lane == 0) {
+                    spill_list[atomicAdd(spill_count, 1u)] = s;
+                    atomicMax(spill_maxlen, (unsigned long long)q.n);
+                }
+                continue;
+            }
+            const double sum = (double)(q.n > q.lead ? q.n - q.lead : 0);
+            uint32_t maxc = 255u;
+            if constexpr (IS_FREQ) {   // quotient of every count this read can produce (<= its number of k-mers)
+                if (sum < 255.0) maxc = (uint32_t)sum;
+                for (uint32_t i = lane; i <= maxc; i += 32) lut[i] = convert_count<OUT>(i, 0.0, sum);
+            }
+            uint32_t over = q.n <= 255 ? warp_scan_read<false>(planes, q, k, tab32, lane)
+                                       : warp_scan_read<true>(planes, q, k, tab32, lane);
+            over = __any_sync(0xffffffffu, over);
+            __syncwarp();                            // table / LUT writes visible to every lane before the read-out
+            if (over && lane == 0) {
+                spill_list[atomicAdd(spill_count, 1u)] = s;
+                atomicMax(spill_maxlen, (unsigned long long)q.n);
+            }
+            // read-out (and clear); a row that path B will redo is still written, then overwritten
+            const bool vec_ok = (bins % BPS == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+            if (vec_ok) {
+                const uint32_t n_stores = bins / BPS;
+                for (uint32_t c = lane; c < n_stores; c += 32) {
+                    union {
+                        uint4 v;
+                        OUT e[BPS];
+                    } u;
+                    uint32_t w0 = 0, w1 = 0;
+                    if constexpr (BPS == 8) {
+                        const uint2 w = *reinterpret_cast<uint2 *>(&tab32[c * 2]);
+                        w0 = w.x, w1 = w.y;
+                        if (w0 | w1) *reinterpret_cast<uint2 *>(&tab32[c * 2]) = make_uint2(0, 0);
+                    } else if constexpr (BPS == 4) {
+                        w0 = tab32[c];
+                        if (w0) tab32[c] = 0;
+                    } else {
+                        unsigned short *t16 = reinterpret_cast<unsigned short *>(tab32);
+                        w0 = t16[c];
+                        if (w0) t16[c] = 0;
+                    }
+                    if constexpr (IS_FREQ) {
+#pragma unroll
+                        for (int i = 0; i < BPS; ++i) {
+                            const uint32_t cnt = ((i < 4 ? w0 : w1) >> (8 * (i & 3))) & 0xffu;
+                            u.e[i] = lut[cnt < maxc ? cnt : maxc];   // cnt > maxc only on an overflowed (redone) row
+                        }
+                    } else if constexpr (BPS == 8) {
+                        u.v = make_uint4(__byte_perm(w0, 0, 0x4140), __byte_perm(w0, 0, 0x4342),
+                                         __byte_perm(w1, 0, 0x4140), __byte_perm(w1, 0, 0x4342));
+                    } else {
+                        u.v = make_uint4(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu, w0 >> 24);
+                    }
+                    st_stream16(row + (uint64_t)c * BPS, u.v);
+                }
+            } else {   // tiny or misaligned rows (k = 1, or odd strides)
+                unsigned char *t8 = reinterpret_cast<unsigned char *>(tab32);
+                for (uint32_t i = lane; i < bins; i += 32) {
+                    const uint32_t cnt = t8[i];
+                    if constexpr (IS_FREQ) row[i] = lut[cnt < maxc ? cnt : maxc];
+                    else row[i] = (OUT)cnt;
+                }
+                __syncwarp();
+                for (uint32_t i = lane; i < tab_bytes / 4; i += 32) tab32[i] = 0;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // ---- fused sweep: every order k_lo..k_hi from ONE scan at k_hi ---------------------
 // The 2^k x 2^k CGR image of order k is the 2x2 sum-pool of the order-(k+1) image plus the one k-mer
 // that ends at base k-1 (it has no (k+1)-mer ending there).  A shared-memory tile of the k_hi table
@@ -745,6 +910,26 @@ int launch_tile(const uint2 *planes, const uint64_t *base_start, const uint32_t 
     return KAM_OK;
 }
 
+template <typename OUT>
+int launch_warp(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, uint32_t n_seqs, int k,
+                OUT *out, uint64_t out_stride, const KmerWs &w, cudaStream_t st) {
+    const uint32_t bins = 1u << (2 * k);
+    const size_t per_warp = (bins < 16u ? 16u : bins) + (std::is_integral<OUT>::value ? 0 : 256 * sizeof(OUT));
+    const size_t smem = per_warp * WK_WARPS;
+    auto kern = cgr_warp_kernel<OUT>;
+    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    KAM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WK_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)kam_sm_count() * per_sm;   // persistent: a whole number of CTAs per SM
+    const uint64_t need = ((uint64_t)n_seqs + WK_QB * WK_WARPS - 1) / (WK_QB * WK_WARPS);
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, WK_WARPS * 32, smem, st>>>(planes, base_start, head_mask, n_seqs, k, out, out_stride, w.queue,
+                                                      w.spill_count, w.spill_list, w.spill_maxlen);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
 struct SpillInfo {
     uint32_t queue, count;
     unsigned long long maxlen;
@@ -795,7 +980,9 @@ int run_kmer(const uint2 *planes, const uint64_t *base_start, const uint32_t *he
     }
     const bool short_reads = total_bases / n_seqs < 2048;
     int rc;
-    if (k <= 6)
+    if (k <= 6 && short_reads && g_warp_path)
+        rc = launch_warp<OUT>(planes, base_start, head_mask, n_seqs, k, out, out_stride, w, st);
+    else if (k <= 6)
         rc = short_reads ? launch_tile<uint32_t, OUT, 64>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
                                                           out_stride, w, st)
                          : launch_tile<uint32_t, OUT, 256>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
@@ -806,7 +993,7 @@ int run_kmer(const uint2 *planes, const uint64_t *base_start, const uint32_t *he
                          : launch_tile<uint8_t, OUT, 256>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
                                                           out_stride, w, st);
     if (rc) return rc;
-    if (k <= 6) return KAM_OK;   // uint32 counters, single tile: nothing can spill, no need to look
+    if (k <= 6 && !(short_reads && g_warp_path)) return KAM_OK;   // uint32 counters, single tile: nothing can spill
 
     SpillInfo h;
     if ((rc = read_spill(w, &h, st))) return rc;
@@ -933,5 +1120,6 @@ int kam_kmer_sweep(const uint64_t *d_planes, const uint64_t *d_base_start, const
 // tuning / test hook: top order of the fused part of kam_kmer_sweep (default 7; 8..10 fuse the tiled
 // orders too, which was measured slower: fewer CTAs fit per SM next to the pooling buffers)
 void kam_kmer_sweep_set_fused_top(int k) { g_sweep_top = k; }
+void kam_kmer_set_warp_path(int on) { g_warp_path = on; }
 
 }  // extern "C"

@@ -89,6 +89,39 @@ def test_short_reads_k6(R):
     assert np.array_equal(got, O.cgr_batch(chars, start, 6, 16))
 
 
+@pytest.mark.parametrize("out,bits", [("counts", 16), ("counts", 32), ("freq32", 16), ("freq64", 16), ("freq64", 32)])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
+def test_short_reads_warp_kernel(R, k, out, bits):
+    """The warp-per-read kernel (short reads, k <= 6): ragged and dirty reads, empty reads, reads
+    shorter than k, reads past 255 bases (checked uint8 counters), reads whose counters overflow and
+    are redone on the spill path, a read long enough to go there directly; every output kind.  The
+    CTA-per-read kernel (warp path off) must give the same bytes."""
+    recs = synth_records(700, 150, seed=31 + k, jitter=40, dirty=0.01) + \
+        [b"", b"ACG", b"NNNNNN", b"ACGTAC", b"NNACGTACGTAC", b"N" * 40 + b"ACGTTGCAAC", b"A" * 400, b"ACGT" * 200,
+         synth_records(1, 300, seed=5)[0], synth_records(1, 3000, seed=6)[0], b"AC" * 600, b"T" * 255, b"T" * 256,
+         b"G" * 261, synth_records(1, 70000 if k < 4 else 9000, seed=8)[0]] + synth_records(300, 100, seed=9, jitter=30)
+    from kameris_b200 import _lib
+    got = _gpu_counts(R, recs, k, bits, out)
+    _lib.load().kam_kmer_set_warp_path(0)
+    try:
+        alt = _gpu_counts(R, recs, k, bits, out)
+    finally:
+        _lib.load().kam_kmer_set_warp_path(1)
+    assert got.tobytes() == alt.tobytes()
+    for i, r in enumerate(recs):
+        c = O.cgr_count(r, k, bits)
+        if out == "counts":
+            assert np.array_equal(got[i], c), (k, i)
+        else:
+            with np.errstate(all="ignore"):
+                ref = O.frequencies(c)
+            if out == "freq64":
+                assert np.array_equal(got[i], ref, equal_nan=True), (k, i)
+            else:
+                ok = np.isfinite(ref)
+                np.testing.assert_allclose(got[i][ok], ref[ok], rtol=1e-6, atol=0, err_msg=str((k, i)))
+
+
 @pytest.mark.parametrize("k,bits", [(9, 16), (9, 32), (8, 16), (7, 16), (2, 16), (12, 16)])
 def test_long_sequences_spill_path(R, k, bits):
     """Sequences beyond the shared-memory path (length, or uint8 overflow) take the RED.ADD spill."""
