@@ -121,6 +121,9 @@ void kam_kmer_sweep_set_fused_top(int k);
 /* test hook: 0 sends short reads at k <= 6 through the CTA-per-read kernel instead of the warp-per-read
  * kernel (default 1); both produce identical vectors. */
 void kam_kmer_set_warp_path(int on);
+/* test hook: 0 sends long sequences (and uint8-counter overflows) straight to the global-memory RED.ADD
+ * path instead of the shared-memory uint16 tile kernel (default 1); identical vectors either way. */
+void kam_kmer_set_long_path(int on);
 
 /* Order-(k+1) count tables -> order-k tables by 2x2 sum-pooling of the CGR image plus the one k-mer
  * that has no (k+1)-mer ending at the same base; exact for dirty heads (quirk Q1) and

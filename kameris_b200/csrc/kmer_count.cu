@@ -777,6 +777,187 @@ __global__ void __launch_bounds__(SW_THREADS) cgr_sweep_kernel(const uint2 *__re
     }
 }
 
+
+// ---- path L: long sequences, shared-memory tiles of packed uint16 counters ----------------------------
+// Measured on B200 (scratch/atoms_bench.cu): shared-memory atomic increments on random bins run at
+// ~12 per clock per SM (3.5e12/s per GPU), global RED.ADD at 0.66 (1.9e11/s) -- 18x apart.  So a
+// megabase sequence is counted in shared memory too, even though its table does not fit: work item =
+// (sequence, tile of 65536 bins = 128 KB of uint16 counters packed two to a word); the CTA scans the
+// WHOLE sequence and increments the k-mers of its tile (4 passes over the planes at k=9, which cost
+// 1.25 MB of L2 reads each against 5e6 increments).  Per thread: one plane word = 32 k-mer end
+// positions; the in-tile mask of all 32 is formed with a few whole-word ops (the tile index is the
+// y-bits of the newest bases), then one atomic per set bit.  Overflow of a uint16 counter is caught
+// without looking at the atomics' results: the sum of the counters read out must equal the number of
+// increments issued (every wrap lowers the sum by 65535 or 65536), else the sequence is redone on
+// path B.  The tile is converted and streamed out with 16-byte stores exactly once.
+constexpr int LG_THREADS = 1024;
+constexpr int LG_TILE_LOG2 = 16;
+constexpr int LG_MAX_K = 11;            // 64 passes at k=11 still beat RED.ADD; beyond that path B
+int g_long_path = 1;                    // test hook: 0 = everything path A declines goes straight to path B
+
+template <typename OUT>
+__global__ void __launch_bounds__(LG_THREADS, 1) cgr_long_kernel(const uint2 *__restrict__ planes,
+                                                                 const uint64_t *__restrict__ base_start,
+                                                                 const uint32_t *__restrict__ head_mask,
+                                                                 const uint32_t *__restrict__ list, uint32_t n_list,
+                                                                 int k, OUT *__restrict__ out, uint64_t out_stride,
+                                                                 uint32_t *__restrict__ queue2,
+                                                                 uint32_t *__restrict__ ovf_flag,
+                                                                 uint32_t *__restrict__ spill2_count,
+                                                                 uint32_t *__restrict__ spill2_list,
+                                                                 unsigned long long *__restrict__ spill2_maxlen) {
+    constexpr bool IS_FREQ = !std::is_integral<OUT>::value;
+    constexpr int BPS = 16 / (int)sizeof(OUT);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw);
+    __shared__ uint32_t s_item;
+    __shared__ unsigned long long s_diff;
+    __shared__ OUT s_lut[256];
+    (void)s_lut;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tile_log2 = 2 * k < LG_TILE_LOG2 ? (uint32_t)(2 * k) : (uint32_t)LG_TILE_LOG2;
+    const uint32_t tile_bins = 1u << tile_log2;
+    const uint32_t tbits = (uint32_t)(2 * k) - tile_log2;            // log2(number of tiles)
+    const uint32_t n_tiles = 1u << tbits;
+    const uint32_t ylow = (1u << (tile_log2 - (uint32_t)k)) - 1u;    // y bits that index inside a tile
+    const uint32_t tile_words = tile_bins >> 1;                      // k >= 2 here
+    const uint32_t n_items = n_list * n_tiles;
+
+    for (uint32_t i = threadIdx.x; i < tile_words; i += LG_THREADS) tab[i] = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_item = atomicAdd(queue2, 1u);
+            s_diff = 0;
+        }
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_items) break;
+        const uint32_t li = item >> tbits, t = item & (n_tiles - 1u);
+        const uint32_t s = list[li];
+        const SeqInfo q = seq_info(base_start, head_mask, s, k);
+        const double sum = (double)(q.n > q.lead ? q.n - q.lead : 0);
+        if constexpr (IS_FREQ) {
+            if (threadIdx.x < 256) s_lut[threadIdx.x] = convert_count<OUT>(threadIdx.x, 0.0, sum);
+        }
+        unsigned long long issued = 0;
+        if (q.n >= (uint64_t)k) {
+            const uint64_t pa = q.p0 + (uint64_t)(k - 1), pe = q.p0 + q.n;   // k-mer end positions [pa, pe)
+            const uint64_t W0 = pa >> 5, W1 = ((pe - 1) >> 5) + 1;
+            const uint32_t shc = 32u - (uint32_t)(k - 1);
+            uint32_t cnt = 0;
+            const uint32_t shc1 = shc - 1u;
+            const uint32_t xm4 = ((1u << (k - 1)) - 1u) << 2;          // x bits 1..k-1 of the window, as a byte offset
+            const uint32_t ym4 = ylow << (k + 1);                      // in-tile y bits above them
+            for (uint64_t Wb = W0 + (threadIdx.x & ~31u); Wb < W1; Wb += LG_THREADS) {   // warp-uniform trip count
+                const uint64_t W = Wb + lane;
+                uint2 hi = make_uint2(0, 0);
+                if (W < W1) hi = __ldg(planes + W);
+                uint2 lo;
+                lo.x = __shfl_up_sync(0xffffffffu, hi.x, 1);
+                lo.y = __shfl_up_sync(0xffffffffu, hi.y, 1);
+                if (lane == 0) lo = Wb ? __ldg(planes + Wb - 1) : make_uint2(0, 0);
+                if (W < W1) {
+                    const unsigned long long vx = ((unsigned long long)hi.x << 32) | lo.x;
+                    const unsigned long long vy = ((unsigned long long)hi.y << 32) | lo.y;
+                    const uint64_t pbase = W << 5;
+                    uint32_t m = 0xffffffffu;
+                    if (pbase < pa) m &= 0xffffffffu << (uint32_t)(pa - pbase);
+                    if (pbase + 32 > pe) m &= 0xffffffffu >> (uint32_t)(pbase + 32 - pe);
+                    // tile index = top tbits bits of the y window = y-bits of the newest tbits bases
+#pragma unroll 1
+                    for (uint32_t i = 0; i < tbits; ++i) {
+                        const uint32_t want = 0u - ((t >> (tbits - 1 - i)) & 1u);
+                        m &= ~((uint32_t)(vy >> (32u - i)) ^ want);
+                    }
+                    cnt += __popc(m);
+                    // bin = (y window << k) | x window; counter word = bin >> 1, half = bin & 1 = x-bit of the
+                    // OLDEST base of the k-mer, which for end position b is bit b of selw
+                    const uint32_t selw = (uint32_t)(vx >> shc);
+                    const unsigned long long vy2 = vy >> 1;
+                    while (m) {
+                        uint32_t b;
+                        asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(m));
+                        const uint32_t bit = 1u << b;
+                        const uint32_t s1 = b + shc1;
+                        const uint32_t off = ((uint32_t)(vx >> s1) & xm4) | (((uint32_t)(vy2 >> s1) << (k + 1)) & ym4);
+                        const uint32_t inc = (selw & bit) ? 0x10000u : 1u;
+                        m ^= bit;
+                        atomicAdd(reinterpret_cast<uint32_t *>(smem_raw + off), inc);   // result unused
+                    }
+                }
+                __syncwarp();   // lanes leave the bit loop at different times: reconverge before the next shuffle
+            }
+            issued = cnt;
+        }
+        if (threadIdx.x == 0 && q.lead < (uint32_t)(k - 1)) {   // dirty head (rare)
+            head_partials(planes, q, k, [&](uint32_t bin) {
+                if ((bin >> tile_log2) != t) return;
+                const uint32_t lb = bin & (tile_bins - 1u);
+                atomicAdd(&tab[lb >> 1], (lb & 1u) ? 0x10000u : 1u);
+                issued += 1;
+            });
+        }
+        __syncthreads();
+
+        // ---- read-out: convert, stream, clear, and add up what the counters hold
+        OUT *trow = out + (uint64_t)s * out_stride + (uint64_t)t * tile_bins;
+        unsigned long long held = 0;
+        const bool vec_ok = (tile_bins % BPS == 0) && ((reinterpret_cast<uintptr_t>(trow) & 15) == 0);
+        if (vec_ok) {
+            const uint32_t n_stores = tile_bins / BPS;
+            for (uint32_t c = threadIdx.x; c < n_stores; c += LG_THREADS) {
+                union {
+                    uint4 v;
+                    OUT e[BPS];
+                } u;
+                uint32_t cn[BPS];
+                if constexpr (BPS == 8) {
+                    const uint4 w = *reinterpret_cast<uint4 *>(&tab[c * 4]);
+                    if (w.x | w.y | w.z | w.w) *reinterpret_cast<uint4 *>(&tab[c * 4]) = make_uint4(0, 0, 0, 0);
+                    cn[0] = w.x & 0xffffu, cn[1] = w.x >> 16, cn[2] = w.y & 0xffffu, cn[3] = w.y >> 16;
+                    cn[4] = w.z & 0xffffu, cn[5] = w.z >> 16, cn[6] = w.w & 0xffffu, cn[7] = w.w >> 16;
+                    u.v = w;                                     // uint16 counts: the packed counters as they are
+                } else if constexpr (BPS == 4) {
+                    const uint2 w = *reinterpret_cast<uint2 *>(&tab[c * 2]);
+                    if (w.x | w.y) *reinterpret_cast<uint2 *>(&tab[c * 2]) = make_uint2(0, 0);
+                    cn[0] = w.x & 0xffffu, cn[1] = w.x >> 16, cn[2] = w.y & 0xffffu, cn[3] = w.y >> 16;
+                } else {
+                    const uint32_t w = tab[c];
+                    if (w) tab[c] = 0;
+                    cn[0] = w & 0xffffu, cn[1] = w >> 16;
+                }
+#pragma unroll
+                for (int i = 0; i < BPS; ++i) held += cn[i];
+                if constexpr (IS_FREQ) {
+#pragma unroll
+                    for (int i = 0; i < BPS; ++i) u.e[i] = cn[i] < 256u ? s_lut[cn[i]] : convert_count<OUT>(cn[i], 0.0, sum);
+                } else if constexpr (BPS == 4) {
+                    u.v = make_uint4(cn[0], cn[1], cn[2], cn[3]);
+                }
+                st_stream16(trow + (uint64_t)c * BPS, u.v);
+            }
+        } else {   // misaligned rows (odd strides)
+            for (uint32_t i = threadIdx.x; i < tile_bins; i += LG_THREADS) {
+                const uint32_t c = (tab[i >> 1] >> (16u * (i & 1u))) & 0xffffu;
+                held += c;
+                trow[i] = IS_FREQ ? (c < 256u ? s_lut[c] : convert_count<OUT>(c, 0.0, sum)) : convert_count<OUT>(c, 0.0, sum);
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < tile_words; i += LG_THREADS) tab[i] = 0;
+        }
+        // a wrapped counter makes held < issued: redo the sequence on path B (once, whichever tile sees it)
+        const unsigned long long d = warp_sum64(issued - held);
+        if (lane == 0 && d) atomicAdd(&s_diff, d);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_diff != 0 && atomicExch(&ovf_flag[li], 1u) == 0u) {
+            spill2_list[atomicAdd(spill2_count, 1u)] = s;
+            atomicMax(spill2_maxlen, (unsigned long long)q.n);
+        }
+    }
+}
+
 // ---- path B ------------------------------------------------------------------------------------
 // grid (chunks, batch): CTA (c, b) counts bases [c*B_CHUNK, (c+1)*B_CHUNK) of sequence
 // spill_list[first + b] into tables[b] (4^k uint32, zeroed beforehand) with RED.ADD.
@@ -851,6 +1032,11 @@ struct KmerWs {
     uint32_t *spill_count;           // [1]
     unsigned long long *spill_maxlen;// [1]
     uint32_t *spill_list;            // [n_seqs]
+    uint32_t *queue2;                // [1]   path L: work-item queue, and the list of sequences it hands to path B
+    uint32_t *spill2_count;          // [1]
+    unsigned long long *spill2_maxlen;// [1]
+    uint32_t *spill2_list;           // [n_seqs]
+    uint32_t *ovf_flag;              // [n_seqs]
     unsigned long long *sums;        // [batch]
     uint32_t *tables;                // [batch][4^k]
     uint32_t batch;
@@ -876,6 +1062,8 @@ inline size_t ws_layout(uint32_t n_seqs, int k, void *base, KmerWs *w) {
     const uint32_t batch = spill_batch(k);
     void *hdr = take(64);
     void *list = take((size_t)(n_seqs ? n_seqs : 1) * 4);
+    void *list2 = take((size_t)(n_seqs ? n_seqs : 1) * 4);
+    void *flags = take((size_t)(n_seqs ? n_seqs : 1) * 4);
     void *sums = take((size_t)1024 * 8);   // spill_batch() never exceeds 1024 (any k: the sweep reuses this layout)
     void *tables = take((size_t)batch * (((size_t)1 << (2 * k)) * 4));
     if (w) {
@@ -883,6 +1071,11 @@ inline size_t ws_layout(uint32_t n_seqs, int k, void *base, KmerWs *w) {
         w->spill_count = (uint32_t *)hdr + 1;
         w->spill_maxlen = (unsigned long long *)((char *)hdr + 8);
         w->spill_list = (uint32_t *)list;
+        w->queue2 = (uint32_t *)hdr + 4;
+        w->spill2_count = (uint32_t *)hdr + 5;
+        w->spill2_maxlen = (unsigned long long *)((char *)hdr + 24);
+        w->spill2_list = (uint32_t *)list2;
+        w->ovf_flag = (uint32_t *)flags;
         w->sums = (unsigned long long *)sums;
         w->tables = (uint32_t *)tables;
         w->batch = batch;
@@ -944,7 +1137,8 @@ inline int read_spill(const KmerWs &w, SpillInfo *h, cudaStream_t st) {
 // path B over the spill list, `batch` sequences at a time so the live tables stay in L2
 template <typename OUT>
 int run_spill(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, int k, int count_bits,
-              OUT *out, uint64_t out_stride, const KmerWs &w, const SpillInfo &h, cudaStream_t st) {
+              OUT *out, uint64_t out_stride, const KmerWs &w, const uint32_t *list, const SpillInfo &h,
+              cudaStream_t st) {
     if (h.count == 0) return KAM_OK;
     const uint32_t bins = 1u << (2 * k);
     const uint32_t wrapmask = count_bits == 16 ? 0xffffu : 0xffffffffu;
@@ -958,13 +1152,40 @@ int run_spill(const uint2 *planes, const uint64_t *base_start, const uint32_t *h
         KAM_CUDA(cudaMemsetAsync(w.tables, 0, (size_t)nb * bins * 4, st));
         KAM_CUDA(cudaMemsetAsync(w.sums, 0, (size_t)nb * 8, st));
         cgr_spill_count_kernel<<<dim3(chunks ? chunks : 1, nb), B_THREADS, 0, st>>>(
-            planes, base_start, head_mask, w.spill_list, first, k, w.tables, bins);
+            planes, base_start, head_mask, list, first, k, w.tables, bins);
         cgr_spill_sum_kernel<<<dim3(fin_blocks, nb), 256, 0, st>>>(w.tables, bins, bins, wrapmask, w.sums);
         cgr_spill_finalize_kernel<OUT><<<dim3(fin_blocks, nb), 256, 0, st>>>(w.tables, bins, bins, wrapmask, w.sums,
-                                                                             w.spill_list, first, out, out_stride);
+                                                                             list, first, out, out_stride);
         KAM_CUDA(cudaGetLastError());
     }
     return KAM_OK;
+}
+
+// the sequences path A declined (too long for its tiles, or a uint8 counter overflowed): path L where
+// its tiles apply, and path B for whatever overflows even uint16 counters (one more 16-byte read-back)
+template <typename OUT>
+int run_overflow(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, int k, int count_bits,
+                 OUT *out, uint64_t out_stride, const KmerWs &w, const SpillInfo &h, cudaStream_t st) {
+    if (h.count == 0) return KAM_OK;
+    if (k < 7 || k > LG_MAX_K || !g_long_path)
+        return run_spill<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, w.spill_list, h, st);
+    KAM_CUDA(cudaMemsetAsync(w.queue2, 0, 16, st));
+    KAM_CUDA(cudaMemsetAsync(w.ovf_flag, 0, (size_t)h.count * 4, st));
+    const uint32_t tile_log2 = 2 * k < LG_TILE_LOG2 ? 2 * k : LG_TILE_LOG2;
+    const size_t smem = ((size_t)1 << tile_log2) * 2;
+    const uint64_t items = (uint64_t)h.count << (2 * k - tile_log2);
+    auto kern = cgr_long_kernel<OUT>;
+    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t grid = (uint64_t)kam_sm_count();   // 128 KB of counters: one CTA per SM, persistent over the item queue
+    if (grid > items) grid = items;
+    kern<<<(unsigned)grid, LG_THREADS, smem, st>>>(planes, base_start, head_mask, w.spill_list, h.count, k, out,
+                                                   out_stride, w.queue2, w.ovf_flag, w.spill2_count, w.spill2_list,
+                                                   w.spill2_maxlen);
+    KAM_CUDA(cudaGetLastError());
+    SpillInfo h2;
+    KAM_CUDA(cudaMemcpyAsync(&h2, w.queue2, 16, cudaMemcpyDeviceToHost, st));
+    KAM_CUDA(cudaStreamSynchronize(st));
+    return run_spill<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, w.spill2_list, h2, st);
 }
 
 template <typename OUT>
@@ -997,7 +1218,7 @@ int run_kmer(const uint2 *planes, const uint64_t *base_start, const uint32_t *he
 
     SpillInfo h;
     if ((rc = read_spill(w, &h, st))) return rc;
-    return run_spill<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, h, st);
+    return run_overflow<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, h, st);
 }
 
 template <typename OUT>
@@ -1025,7 +1246,7 @@ int run_sweep(const uint2 *planes, const uint64_t *base_start, const uint32_t *h
     int rc = read_spill(w, &h, st);
     if (rc) return rc;
     for (int k = k_lo; k <= k_hi && h.count; ++k)      // sequences the fused kernel declined: every order, path B
-        if ((rc = run_spill<OUT>(planes, base_start, head_mask, k, count_bits, (OUT *)outs[k - k_lo],
+        if ((rc = run_overflow<OUT>(planes, base_start, head_mask, k, count_bits, (OUT *)outs[k - k_lo],
                                  (uint64_t)1 << (2 * k), w, h, st)))
             return rc;
     return KAM_OK;
@@ -1121,5 +1342,6 @@ int kam_kmer_sweep(const uint64_t *d_planes, const uint64_t *d_base_start, const
 // orders too, which was measured slower: fewer CTAs fit per SM next to the pooling buffers)
 void kam_kmer_sweep_set_fused_top(int k) { g_sweep_top = k; }
 void kam_kmer_set_warp_path(int on) { g_warp_path = on; }
+void kam_kmer_set_long_path(int on) { g_long_path = on; }
 
 }  // extern "C"

@@ -246,7 +246,7 @@ def config4(rank, world, dev, scale):
 def config5(rank, world, dev, scale):
     n_total, L, k = int(5000 * scale), 5_000_000, 9
     n = max(1, n_total // world)
-    batch = 128
+    batch = 148        # one batch = 148 x 4 tile work items of the long-sequence kernel: four full waves
     ok = True
     t_sum = 0.0
     done = 0

@@ -122,14 +122,39 @@ def test_short_reads_warp_kernel(R, k, out, bits):
                 np.testing.assert_allclose(got[i][ok], ref[ok], rtol=1e-6, atol=0, err_msg=str((k, i)))
 
 
-@pytest.mark.parametrize("k,bits", [(9, 16), (9, 32), (8, 16), (7, 16), (2, 16), (12, 16)])
-def test_long_sequences_spill_path(R, k, bits):
-    """Sequences beyond the shared-memory path (length, or uint8 overflow) take the RED.ADD spill."""
+@pytest.mark.parametrize("long_path", [1, 0])
+@pytest.mark.parametrize("k,bits", [(9, 16), (9, 32), (8, 16), (7, 16), (2, 16), (10, 16), (11, 32), (12, 16)])
+def test_long_sequences_spill_path(R, k, bits, long_path):
+    """Sequences beyond path A (length, or uint8 overflow) take the shared-memory uint16 tile kernel
+    (path L, 7 <= k <= 11) and, when even a uint16 counter overflows (70 000 x 'A'), the RED.ADD path B;
+    long_path=0 sends all of them to path B directly.  Dirty heads included."""
     recs = synth_records(3, 400000, seed=11 + k, dirty=0.001) + [b"ACGT" * 3000, b"A" * 70000,
-                                                                 synth_records(1, 9000, seed=2)[0]]
-    got = _gpu_counts(R, recs, k, bits)
+                                                                 synth_records(1, 9000, seed=2)[0],
+                                                                 b"NNA" + synth_records(1, 200000, seed=3)[0],
+                                                                 b"AC" * 140000]
+    from kameris_b200 import _lib
+    _lib.load().kam_kmer_set_long_path(long_path)
+    try:
+        got = _gpu_counts(R, recs, k, bits)
+    finally:
+        _lib.load().kam_kmer_set_long_path(1)
     for i, r in enumerate(recs):
         assert np.array_equal(got[i], O.cgr_count(r, k, bits)), (i, k, bits)
+
+
+@pytest.mark.parametrize("out", ["freq32", "freq64"])
+def test_long_sequences_frequencies(R, out):
+    """path L with the fused frequency division (BASELINE config 5 shape, scaled down)."""
+    recs = synth_records(2, 600000, seed=77, dirty=0.0005) + [b"A" * 70000, b"AC" * 140000]
+    for bits in (16, 32):
+        got = _gpu_counts(R, recs, 9, bits, out)
+        for i, r in enumerate(recs):
+            with np.errstate(all="ignore"):
+                ref = O.frequencies(O.cgr_count(r, 9, bits))
+            if out == "freq64":
+                assert np.array_equal(got[i], ref, equal_nan=True), (i, bits)
+            else:
+                np.testing.assert_allclose(got[i], ref, rtol=1e-6, atol=0)
 
 
 def test_wrap_and_wrapped_frequencies(R):
