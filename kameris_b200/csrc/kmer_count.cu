@@ -876,15 +876,21 @@ __global__ void __launch_bounds__(LG_THREADS, 1) cgr_long_kernel(const uint2 *__
                     // OLDEST base of the k-mer, which for end position b is bit b of selw
                     const uint32_t selw = (uint32_t)(vx >> shc);
                     const unsigned long long vy2 = vy >> 1;
-                    while (m) {
-                        uint32_t b;
-                        asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(m));
-                        const uint32_t bit = 1u << b;
+                    auto bin_off = [&](uint32_t b) {
                         const uint32_t s1 = b + shc1;
-                        const uint32_t off = ((uint32_t)(vx >> s1) & xm4) | (((uint32_t)(vy2 >> s1) << (k + 1)) & ym4);
-                        const uint32_t inc = (selw & bit) ? 0x10000u : 1u;
-                        m ^= bit;
-                        atomicAdd(reinterpret_cast<uint32_t *>(smem_raw + off), inc);   // result unused
+                        return ((uint32_t)(vx >> s1) & xm4) | (((uint32_t)(vy2 >> s1) << (k + 1)) & ym4);
+                    };
+                    while (m) {   // two independent increments per trip: the highest and the lowest set bit
+                        uint32_t b1, b2;
+                        asm("bfind.u32 %0, %1;" : "=r"(b1) : "r"(m));
+                        const uint32_t bit1 = 1u << b1, bit2 = m & (0u - m);
+                        asm("bfind.u32 %0, %1;" : "=r"(b2) : "r"(bit2));
+                        m &= ~(bit1 | bit2);
+                        const uint32_t off1 = bin_off(b1), off2 = bin_off(b2);
+                        const uint32_t inc1 = (selw & bit1) ? 0x10000u : 1u;
+                        const uint32_t inc2 = bit2 == bit1 ? 0u : ((selw & bit2) ? 0x10000u : 1u);   // one bit left: adds 0
+                        atomicAdd(reinterpret_cast<uint32_t *>(smem_raw + off1), inc1);   // results unused
+                        atomicAdd(reinterpret_cast<uint32_t *>(smem_raw + off2), inc2);
                     }
                 }
                 __syncwarp();   // lanes leave the bit loop at different times: reconverge before the next shuffle
