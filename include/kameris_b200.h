@@ -190,6 +190,10 @@ void kam_gram_force_f16(int on);
 /* tuning/test hook: thread-block cluster size of the Gram kernel (2 = B panel multicast between the
  * two CTAs of a cluster, default; 1 = no cluster). */
 void kam_gram_set_cluster(int cl);
+/* tuning/test hook: non-zero (default) runs the CTA-pair kernel (tcgen05.mma.cta_group::2, one 256 x 256
+ * tile per cluster of two CTAs, B split between them); 0 the cluster-multicast cta_group::1 kernel.  Needs
+ * cluster 2.  Both produce the exact integer Gram matrix, hence identical outputs. */
+void kam_gram_set_pair(int on);
 int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                  uint32_t row_begin, uint32_t row_end, unsigned metrics, int euclid_on_freq,
                  float *d_tri_euclid, float *d_tri_cosine, float *d_tri_pearson, void *d_ws,

@@ -267,6 +267,216 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
     }
 }
 
+
+// ---- CTA-pair variant: tcgen05.mma.cta_group::2, M256 x N256 per instruction --------------------------
+// The two CTAs of a cluster (one TPC) form ONE 256 x 256 tile: CTA r stages the A rows [128r, 128r+128)
+// and the B rows [128r, 128r+128) of the tile -- 32 KB per stage and CTA, against 48 KB for the
+// multicast variant above, so the shared-memory port carries 64 B/clk of TMA writes plus 64 B/clk of
+// operand reads instead of 96 + 96 (the port moves 128 B/clk: the cta_group::1 kernel is bound by it at
+// ~75 % tensor-pipe activity).  Only the leader CTA (rank 0) issues MMAs; the hardware reads the other
+// half of B from the peer's shared memory and writes each CTA's 128 accumulator rows into its own TMEM.
+// Both CTAs run a TMA producer (their loads complete on the LEADER's `full` barrier, address bit 24
+// cleared) and four epilogue warps (which release the accumulator on the leader's `tempty` barrier).
+constexpr int P_STAGES = 6;
+constexpr uint32_t PB_BYTES = (BN / 2) * BK_BYTES, P_STAGE_BYTES = A_BYTES + PB_BYTES;
+constexpr uint32_t IDESC2_F16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr uint32_t IDESC2_I8 = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even (leader) CTA
+
+template <bool I8>
+__device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    if constexpr (I8) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC2_I8), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC2_F16), "r"(accumulate)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+// TMA load whose completion is counted on the leader CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *tm, int32_t c_inner, int32_t c_outer,
+                                                 uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c_inner), "r"(c_outer), "r"(smem_u32(bar) & PEER_MASK)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+
+template <bool I8>
+__global__ void __launch_bounds__(G_THREADS, 1) gram_pair_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const uint2 *__restrict__ tiles, uint32_t n_tiles,
+                                                                 uint32_t k_iters, GramGeom gg, GramOut go) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    RowK *colk = reinterpret_cast<RowK *>(smem + P_STAGES * P_STAGE_BYTES);   // [BN]
+    __shared__ __align__(8) uint64_t full[P_STAGES], empty[P_STAGES], tfull[2], tempty[2];
+    __shared__ uint32_t tmem_holder;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < P_STAGES; ++s) {
+            mbar_init(&full[s], 1);    // leader only: its producer's arrive.expect_tx (bytes of BOTH CTAs)
+            mbar_init(&empty[s], 1);   // one multicast commit from the leader's MMA thread
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);   // one multicast commit
+            mbar_init(&tempty[a], 8);  // leader only: four epilogue warps of each CTA
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {   // the same warp of both CTAs allocates (and later frees) the pair's TMEM
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_holder;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = blockIdx.x / 2; t < n_tiles; t += gridDim.x / 2) {
+                const uint2 tile = tiles[t];
+                const int32_t arow = (int32_t)((tile.x * 2 + crank) * BM);
+                const int32_t brow = (int32_t)(tile.y * BN + crank * (BN / 2));
+                for (uint32_t kb = 0; kb < k_iters; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    if (leader) mbar_arrive_expect_tx(&full[stage], 2 * P_STAGE_BYTES);
+                    unsigned char *sa = smem + stage * P_STAGE_BYTES;
+                    const int32_t kc = (int32_t)(kb * (I8 ? BK_BYTES : BK_BYTES / 2));
+                    tma_load_2d_pair(sa, &tmA, kc, arow, &full[stage]);
+                    tma_load_2d_pair(sa + A_BYTES, &tmB, kc, brow, &full[stage]);
+                    if (++stage == P_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA, for both CTAs =====
+        if (leader && lane == 0) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t t = blockIdx.x / 2; t < n_tiles; t += gridDim.x / 2) {
+                mbar_wait_cluster(&tempty[acc], acc_phase ^ 1u);   // both epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (uint32_t kb = 0; kb < k_iters; ++kb) {
+                    mbar_wait(&full[stage], phase);                // both CTAs' TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * P_STAGE_BYTES);
+                    const uint64_t a_desc = umma_desc(sa), b_desc = umma_desc(sa + A_BYTES);
+#pragma unroll
+                    for (uint32_t k = 0; k < BK_BYTES / 32; ++k)
+                        umma2<I8>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+                    umma2_commit_mc(&empty[stage], 3);             // frees the stage in both CTAs
+                    if (++stage == P_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma2_commit_mc(&tfull[acc], 3);                   // accumulator complete, both epilogues
+                acc ^= 1u;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps per CTA, CTA r owns rows [128r, 128r+128) of the tile =====
+        const uint32_t q = (uint32_t)warp & 3u;
+        const uint32_t et = threadIdx.x - 64;
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t t = blockIdx.x / 2; t < n_tiles; t += gridDim.x / 2) {
+            const uint2 tile = tiles[t];
+            const uint32_t r0 = (tile.x * 2 + crank) * BM, c0 = tile.y * BN;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (uint32_t c = et; c < (uint32_t)BN; c += 128) {
+                RowK z;
+                z.rn = z.S = z.mu = z.rp = z.a = z.q = 0.0;
+                colk[c] = (c0 + c < gg.n_b) ? gg.rk_b[c0 + c] : z;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t row = r0 + q * 32 + lane;
+            const bool row_ok = row < gg.n_a && row >= gg.row_begin && row < gg.row_end;
+            RowK ri;
+            ri.rn = ri.S = ri.mu = ri.rp = ri.a = ri.q = 0.0;
+            if (row_ok) ri = gg.rk_a[row];
+            const long long base = gg.ld ? (long long)row * (long long)gg.ld
+                                         : (long long)gg.n_a * row - (long long)row * (row + 3) / 2 - 1;
+            for (uint32_t ch = 0; ch < (uint32_t)BN / 32; ++ch) {
+                const uint32_t cb = c0 + ch * 32;
+                if (gg.tri && cb + 31 <= r0 + q * 32) continue;
+                if (cb >= gg.n_b) continue;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + acc * BN + ch * 32 + ((q * 32) << 16), v);
+                if (row_ok) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const uint32_t j = cb + c;
+                        if (j >= gg.n_b || (gg.tri && j <= row)) continue;
+                        const double g = I8 ? (double)(int)v[c] : (double)__uint_as_float(v[c]);
+                        const RowK cj = colk[ch * 32 + c];
+                        gram_store(go, base + j, g, ri, cj);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---- pre-pass: ONE pass over the counts writes the tensor-core operand rows (uint8, saturating, or
 // fp16; zero-padded to dpad) and the exact per-row sum / sum of squares, and records the largest
 // count and the largest G_ii (the exactness envelope).  One CTA per row, 16 elements per thread and
@@ -379,6 +589,7 @@ __global__ void rowk_kernel(const unsigned long long *__restrict__ S, const unsi
 }
 
 bool g_force_f16 = false;
+bool g_pair = true;        // cta_group::2 kernel (gram_pair_kernel, default) or the cluster-multicast one
 uint32_t g_cluster = 2;
 uint32_t g_sm_limit = 0;   // 0 = all SMs; otherwise leave the rest to concurrent work (e.g. NCCL transfers)
 
@@ -408,7 +619,7 @@ int prepass_dispatch(const void *x, int elem, uint32_t n, uint64_t d, uint64_t l
                              : run_prepass<uint32_t>(x, n, d, ld, i8, h, S, G, flags, st);
 }
 
-template <bool I8, int CL>
+template <bool I8, int CL, bool PAIR = false>
 int launch_gram(const void *opA, const void *opB, const uint2 *d_tiles, size_t n_tiles, uint64_t d,
                 const GramGeom &gg, GramOut go, cudaStream_t st) {
     const uint64_t dpad = dpad_of(d);
@@ -419,8 +630,8 @@ int launch_gram(const void *opA, const void *opB, const uint2 *d_tiles, size_t n
     if ((rc = kam_make_tmap_2d(&tmA, dt, esz, opA, dpad, gg.n_a, dpad * esz, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = kam_make_tmap_2d(&tmB, dt, esz, opB, dpad, gg.n_b, dpad * esz, bk, BN / CL, CU_TENSOR_MAP_SWIZZLE_128B)))
         return rc;
-    const size_t smem = (size_t)G_STAGES * STAGE_BYTES + BN * sizeof(RowK) + 1024;
-    auto kern = gram_tcgen05_kernel<I8, CL>;
+    const size_t smem = (PAIR ? (size_t)P_STAGES * P_STAGE_BYTES : (size_t)G_STAGES * STAGE_BYTES) + BN * sizeof(RowK) + 1024;
+    auto kern = PAIR ? gram_pair_kernel<I8> : gram_tcgen05_kernel<I8, CL>;
     KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t sms = (uint32_t)kam_sm_count();
     if (g_sm_limit && g_sm_limit < sms) sms = g_sm_limit;
@@ -463,6 +674,9 @@ int gram_block(const void *opA, const void *opB, bool i8, uint64_t d, const Gram
     if (tiles.empty()) return KAM_OK;
     KAM_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
     KAM_CUDA(cudaStreamSynchronize(st));   // `tiles` is pageable host memory owned by this frame
+    if (CL == 2 && g_pair)
+        return i8 ? launch_gram<true, 2, true>(opA, opB, d_tiles, tiles.size(), d, gg, go, st)
+                  : launch_gram<false, 2, true>(opA, opB, d_tiles, tiles.size(), d, gg, go, st);
     if (CL == 2)
         return i8 ? launch_gram<true, 2>(opA, opB, d_tiles, tiles.size(), d, gg, go, st)
                   : launch_gram<false, 2>(opA, opB, d_tiles, tiles.size(), d, gg, go, st);
@@ -653,6 +867,7 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
 // test / tuning hooks
 void kam_gram_force_f16(int on) { g_force_f16 = on != 0; }
 void kam_gram_set_cluster(int cl) { g_cluster = cl == 1 ? 1u : 2u; }
+void kam_gram_set_pair(int on) { g_pair = on != 0; }
 void kam_gram_set_sm_limit(int sms) { g_sm_limit = sms > 0 ? (uint32_t)sms : 0u; }
 
 }  // extern "C"

@@ -65,17 +65,17 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
     out["gram"] = {"metric": "distance_pairs_per_sec", "value": pairs / t, "unit": "pairs/s",
                    "config": {"workload": "N=%d count vectors, D=4^9, euclid+cosine+pearson from one Gram pass" % n,
                               "includes": "operand/statistics pre-pass + tile list + tcgen05 kernel + epilogue",
-                              "path": "uint8 operands, int32 accumulation in TMEM (exact); cluster-2 TMA multicast"},
+                              "path": "uint8 operands, int32 accumulation in TMEM (exact); CTA pairs, tcgen05.mma.cta_group::2 (M256 x N256)"},
                    "ms": t * 1e3,
                    "roofline": {"bound": "tensor", "achieved": tflops, "peak": i8_peak, "unit": "TFLOP/s",
                                 "frac": tflops / i8_peak, "traffic": None,
                                 "peak_note": "2 x measured bf16 peak (%.1f): int8 tensor rate; achieved/bf16 peak = %.2f"
                                              % (tf_peak, tflops / tf_peak),
-                                "algorithmic_flops_per_pair": 2 * d, "kernel": "gram_tcgen05_kernel<i8,cluster2>"},
+                                "algorithmic_flops_per_pair": 2 * d, "kernel": "gram_pair_kernel<i8>"},
                    "fp16_path": {"value": pairs / t16, "unit": "pairs/s", "ms": t16 * 1e3,
                                  "roofline": {"bound": "tensor", "achieved": tflops16, "peak": tf_peak,
                                               "unit": "TFLOP/s", "frac": tflops16 / tf_peak,
-                                              "kernel": "gram_tcgen05_kernel<f16,cluster2>"}}}
+                                              "kernel": "gram_pair_kernel<f16>"}}}
     del x, tri, ws
 
     # ---- manhattan, config-4 shape ----------------------------------------------------------------------

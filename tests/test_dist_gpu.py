@@ -159,6 +159,28 @@ def test_gram_vs_scipy(D, n, L, k):
     _check_gram(D, x, force_f16=True)      # fp16 -> fp32 tensor path
 
 
+@pytest.mark.parametrize("n,L,k", [(3, 500, 3), (257, 1000, 7), (700, 4000, 6), (520, 9000, 8)])
+def test_gram_kernel_variants_agree_exactly(D, n, L, k):
+    """cta_group::2 pair kernel (default), cluster-multicast cta_group::1 kernel and the no-cluster kernel
+    all produce the exact integer Gram matrix: identical float32 outputs, both operand kinds."""
+    from kameris_b200 import _lib
+    lib = _lib.load()
+    x = _dev(_counts(n, L, k, seed=n + k))
+    res = []
+    try:
+        for pair, cl in ((1, 2), (0, 2), (0, 1)):
+            lib.kam_gram_set_pair(pair)
+            lib.kam_gram_set_cluster(cl)
+            for f16 in (False, True):
+                res.append(D.gram_tri(x, ("euclid", "cosine", "pearson"), euclid_on_freq=True, force_f16=f16))
+    finally:
+        lib.kam_gram_set_pair(1)
+        lib.kam_gram_set_cluster(2)
+    for r in res[1:]:
+        for m in r:
+            assert torch.equal(r[m], res[0][m])
+
+
 def test_gram_i8_and_f16_paths_agree_exactly(D):
     """both tensor paths produce the exact integer Gram matrix, hence identical float32 outputs."""
     x = _dev(_counts(300, 5000, 6, seed=5))
