@@ -41,6 +41,22 @@ def main_dists(argv):
     return 0
 
 
+def _maybe_init_process_group():
+    """Under `python -m torch.distributed.run --nproc-per-node N -m kameris_b200.cli ...` (one process per
+    GPU) the steps shard over the ranks: bind this rank to its GPU and join the NCCL group."""
+    import os
+    if int(os.environ.get('WORLD_SIZE', '1')) <= 1:
+        return False
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return False
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    dist.init_process_group('nccl', device_id=dev)
+    return True
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     logging.basicConfig(level=logging.INFO, format='%(message)s', stream=sys.stdout)
@@ -48,11 +64,17 @@ def main(argv=None):
         print(USAGE_CGR)
         print(USAGE_DISTS)
         return 1
+    joined = False
     try:
+        joined = _maybe_init_process_group()
         return (main_cgr if argv[0] == 'generation_cgr' else main_dists)(argv[1:])
     except Exception as e:  # noqa: BLE001 -- the executables die with a message and a non-zero code
         print('error: %s' % e)
         return 1
+    finally:
+        if joined:
+            import torch.distributed as dist
+            dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -66,6 +66,18 @@ class repr_reader(object):
             raise ValueError("truncated .mm-repr file")
         return m.reshape(self.count, n)
 
+    def read_rows(self, begin, end):
+        """Matrices [begin, end) as one (end-begin, rows*cols) array (a rank's shard in multi-GPU runs)."""
+        self._require_dense()
+        if not 0 <= begin <= end <= self.count:
+            raise IndexError((begin, end))
+        n = self.rows * self.cols
+        self.file.seek(REPR_HEADER + begin * n * self.dtype.itemsize)
+        m = np.fromfile(self.file, dtype=self.dtype, count=(end - begin) * n)
+        if m.size != (end - begin) * n:
+            raise ValueError("truncated .mm-repr file")
+        return m.reshape(end - begin, n)
+
     def close(self):
         self.file.close()
 
@@ -109,6 +121,20 @@ class repr_writer(object):
             raise ValueError("matrix block does not match the header")
         mats.tofile(self.file)
         self.written = self.count
+
+    def close(self):
+        self.file.close()
+
+
+class repr_appender(object):
+    """An existing `.mm-repr` opened in place (no header rewrite, no truncation): ranks of a multi-GPU
+    run write their own rows into the file rank 0 created."""
+
+    def __init__(self, filename):
+        r = repr_reader(filename)
+        self.count, self.rows, self.cols, self.dtype, self.value_type = r.count, r.rows, r.cols, r.dtype, r.value_type
+        r.close()
+        self.file = open(filename, "r+b")
 
     def close(self):
         self.file.close()

@@ -95,10 +95,14 @@ def kmers_from_records(records, k, bits_per_element, mode):
 CHUNK_BYTES = 256 << 20        # pinned staging per buffer; two buffers alternate
 
 
-def kmers_to_file(records, k, bits_per_element, mode, output_file):
+def kmers_to_file(records, k, bits_per_element, mode, output_file, row_offset=0, total_rows=None, create=True):
     """records -> `.mm-repr`, streamed: the batch is cut into chunks of rows; while chunk c is being
     written to the file from one pinned buffer, chunk c+1 is produced (H2D, kernels, D2H inside
-    kam_kmers_host, which releases the GIL) into the other.  No buffer of the whole result exists."""
+    kam_kmers_host, which releases the GIL) into the other.  No buffer of the whole result exists.
+
+    Multi-GPU runs (run_backend_kmers under torch.distributed): `records` is this rank's shard of the
+    file list; its rows go to rows [row_offset, row_offset + len(records)) of a file of `total_rows`
+    matrices that rank 0 created (create=False: open in place, write nothing but the rows)."""
     import torch
     from concurrent.futures import ThreadPoolExecutor
     lib = _lib.load()
@@ -125,7 +129,12 @@ def kmers_to_file(records, k, bits_per_element, mode, output_file):
         except RuntimeError:
             pass
         bufs.append(t)
-    writer = formats.repr_writer(output_file, np.zeros((1, d), dtype=ndt), n, create_file=True)
+    if create:
+        writer = formats.repr_writer(output_file, np.zeros((1, d), dtype=ndt), n if total_rows is None else total_rows,
+                                     create_file=True)
+    else:
+        writer = formats.repr_appender(output_file)
+    writer.file.seek(formats.REPR_HEADER + row_offset * d * np.dtype(ndt).itemsize)
 
     def view(t, m):
         raw = (ctypes.c_char * (m * d * t.element_size())).from_address(t.data_ptr())
@@ -151,12 +160,65 @@ def kmers_to_file(records, k, bits_per_element, mode, output_file):
         writer.file.close()
 
 
+def _world():
+    """(torch.distributed module, rank, world) when the step runs under an initialised process group
+    with more than one rank (one process per GPU), else (None, 0, 1)."""
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return None, 0, 1
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def _value_dtype(bits_per_element, mode):
+    if mode == 'frequencies':
+        return np.dtype(np.float64)
+    return np.dtype(np.uint16 if bits_per_element == 16 else np.uint32)
+
+
+def kmers_to_file_sharded(paths, k, bits_per_element, mode, output_file, dist, produce=None):
+    """The `kmers` step on all ranks of a process group: the sorted file list is cut into
+    contiguous shards with nearly equal numbers of input bytes, every rank turns ITS files into vectors
+    and writes them straight into its row range of the one `.mm-repr` (no gather, no data-path
+    collective; two barriers order the header before and the close after the row writes).
+
+    `produce(records, row_offset, total_rows)` defaults to the CUDA streaming writer; the CPU tests inject
+    a host function to exercise the sharding and the file offsets under gloo."""
+    from ..parallel import shard_by_bases
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sizes = [os.path.getsize(p) for p in paths]
+    b, e = shard_by_bases(sizes, world)[rank]
+    n, d = len(paths), 4 ** k
+    if rank == 0:
+        w = formats.repr_writer(output_file, np.zeros((1, d), dtype=_value_dtype(bits_per_element, mode)), n,
+                                create_file=True)
+        w.file.truncate(formats.REPR_HEADER + n * d * w.dtype.itemsize)
+        w.file.close()
+    dist.barrier()
+    records = read_records(paths[b:e])
+    if produce is None:
+        kmers_to_file(records, k, bits_per_element, mode, output_file, row_offset=b, total_rows=n, create=False)
+    else:
+        produce(records, b, n)
+    dist.barrier()
+    return b, e
+
+
 def run_backend_kmers(options, exp_options):
     log = _log()
     t0 = time.time()
     try:
         paths = list_input_files(options['fasta_output_dir'])
         log.info('%d files, using B200 backend', len(paths))
+        dist, rank, world = _world()
+        if dist is not None:
+            b, e = kmers_to_file_sharded(paths, options['k'], options['bits_per_element'], options['mode'],
+                                         options['output_file'], dist)
+            log.info('kmers: rank %d/%d wrote vectors [%d, %d) of %d in %.2f seconds', rank, world, b, e, len(paths),
+                     time.time() - t0)
+            return
         records = read_records(paths)
         kmers_to_file(records, options['k'], options['bits_per_element'], options['mode'], options['output_file'])
     except (_lib.KamError, ValueError, OSError) as e:
@@ -198,11 +260,58 @@ def dists_from_matrix(x, metrics):
     return out
 
 
+def dists_to_files_sharded(input_file, output_prefix, metrics, dist, device=None, compute=None):
+    """The `distances` step on all ranks of a process group: every rank reads a contiguous
+    block of rows of the `.mm-repr`, the rows are all-gathered (the one exchange step), rank r computes
+    the block of triangle rows that holds 1/world of the pairs -- a CONTIGUOUS byte range of every
+    `.mm-dist` -- and writes it in place into the files rank 0 created.  `compute` as in
+    parallel.distances_sharded (CPU tests)."""
+    import torch
+    from .. import parallel
+    rank, world = dist.get_rank(), dist.get_world_size()
+    with formats.repr_reader(input_file) as reader:
+        n = reader.count
+        b, e = rank * n // world, (rank + 1) * n // world
+        x = reader.read_rows(b, e)
+    if any(m in GRAM_METRICS for m in metrics) and formats.element_type_of(x.dtype) > 2:
+        raise ValueError('euclid/cosine/pearson need integer count vectors (mode: counts)')
+    t = torch.from_numpy(x)
+    if device is not None:
+        t = t.to(device)
+    slices, (r0, r1), n_all = parallel.distances_sharded(t, metrics, compute=compute)
+    assert n_all == n
+    off0 = parallel.tri_row_offset(n, r0)
+    for m in metrics:
+        path = '%s-%s.mm-dist' % (output_prefix, m)
+        ndt = np.dtype(np.uint32 if m == 'manhat' else np.float32)
+        if rank == 0:
+            w = formats.dist_writer(path, ndt, n)
+            w.file.truncate(formats.DIST_HEADER + (n * (n - 1) // 2) * 4)
+            w.close()
+        dist.barrier()
+        part = slices[m].cpu().numpy()
+        part = part.view(np.uint32) if m == 'manhat' else part
+        if part.size:
+            with open(path, 'r+b') as f:
+                f.seek(formats.DIST_HEADER + off0 * 4)
+                np.ascontiguousarray(part, dtype=ndt).tofile(f)
+        dist.barrier()
+    return n, (r0, r1)
+
+
 def run_backend_dists(options, exp_options):
     log = _log()
     t0 = time.time()
     try:
         metrics = requested_metrics(options['distances'])
+        dist, rank, world = _world()
+        if dist is not None:
+            import torch
+            n, rows = dists_to_files_sharded(options['input_file'], options['output_prefix'], metrics, dist,
+                                             device=torch.device('cuda', torch.cuda.current_device()))
+            log.info('distances: rank %d/%d wrote triangle rows [%d, %d) of %d (%s) in %.2f seconds', rank, world,
+                     rows[0], rows[1], n, ','.join(metrics), time.time() - t0)
+            return
         with formats.repr_reader(options['input_file']) as reader:
             x = reader.read_all()                 # raises "Sparse matrices are not supported"
         n = x.shape[0]

@@ -101,3 +101,75 @@ def test_ring_schedule_covers_every_shard_pair_once(world):
         assert sorted(parts) in (["tri"], ["full"], ["hi", "lo"]), (key, parts)
     loads = [sum({"tri": 0.5, "full": 1.0, "lo": 0.5, "hi": 0.5}[p] for _, _, _, p in steps) for steps in plan]
     assert max(loads) - min(loads) < 1e-9          # perfectly balanced in units of blocks
+
+
+# ---- the two job steps under a process group: every rank writes its part of ONE output file ------------
+def _host_compute_all(x_full, metrics, rows, tri_offset, slice_len):
+    from oracle import oracle as O
+    x = x_full.numpy()
+    man, info = O.dists_triangle(x, True, True, threads=1)
+    out = {}
+    if "manhat" in metrics:
+        out["manhat"] = torch.from_numpy(man[tri_offset:tri_offset + slice_len].view(np.int32).copy())
+    if "info" in metrics:
+        out["info"] = torch.from_numpy(info[tri_offset:tri_offset + slice_len].copy())
+    return out
+
+
+def _steps_worker(rank, world, port, root):
+    from kameris_b200 import formats
+    from kameris_b200.job_steps import backend
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        paths = backend.list_input_files(os.path.join(root, "fasta"))
+        out = os.path.join(root, "counts.mm-repr")
+
+        def produce(records, row_offset, total_rows):      # host stand-in for the CUDA streaming writer
+            w = formats.repr_appender(out)
+            assert w.count == total_rows
+            w.file.seek(formats.REPR_HEADER + row_offset * 4 ** 3 * 2)
+            for r in records:
+                O.cgr_count(r, 3, 16).astype("<u2").tofile(w.file)
+            w.close()
+        backend.kmers_to_file_sharded(paths, 3, 16, "counts", out, dist, produce=produce)
+        backend.dists_to_files_sharded(out, os.path.join(root, "d"), ["manhat", "info"], dist,
+                                       compute=_host_compute_all)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_job_steps_sharded_files_gloo_world2(tmp_path):
+    """kmers + distances steps on 2 ranks (gloo, host stand-ins for the kernels): the `.mm-repr` and
+    `.mm-dist` files assembled from per-rank writes equal the single-process files byte for byte."""
+    from kameris_b200 import formats
+    from oracle import oracle as O
+    from tests.helpers import synth_records
+    root = str(tmp_path)
+    os.mkdir(os.path.join(root, "fasta"))
+    recs = synth_records(11, 300, seed=3, jitter=250, dirty=0.01)
+    for i, r in enumerate(recs):
+        with open(os.path.join(root, "fasta", "%04d.fasta" % i), "wb") as f:
+            f.write(b">x\n" + r + b"\n")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_steps_worker, args=(r, 2, port, root)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    x = np.stack([O.cgr_count(r, 3, 16) for r in recs])
+    with formats.repr_reader(os.path.join(root, "counts.mm-repr")) as rd:
+        assert rd.count == 11 and rd.cols == 64 and np.array_equal(rd.read_all(), x)
+        assert np.array_equal(rd.read_rows(3, 7), x[3:7])
+    man, info = O.dists_triangle(x, True, True)
+    tri, n = formats.dist_reader.read_triangle(os.path.join(root, "d-manhat.mm-dist"))
+    assert n == 11 and np.array_equal(tri, man)
+    tri, n = formats.dist_reader.read_triangle(os.path.join(root, "d-info.mm-dist"))
+    assert n == 11 and np.array_equal(tri, info)
