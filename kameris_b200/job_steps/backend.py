@@ -278,7 +278,7 @@ def dists_to_files_sharded(input_file, output_prefix, metrics, dist, device=None
     t = torch.from_numpy(x)
     if device is not None:
         t = t.to(device)
-    slices, (r0, r1), n_all = parallel.distances_sharded(t, metrics, compute=compute)
+    slices, (r0, r1), n_all = parallel.distances_sharded(t, metrics, compute=compute, euclid_on_freq=False)
     assert n_all == n
     off0 = parallel.tri_row_offset(n, r0)
     for m in metrics:

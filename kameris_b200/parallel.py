@@ -61,22 +61,26 @@ def all_gather_rows(x_local, group=None):
     return full.view(x_local.dtype).view(sum(counts), d), counts
 
 
-def distances_sharded(x_local, metrics, group=None, compute=None):
+def distances_sharded(x_local, metrics, group=None, compute=None, euclid_on_freq=True):
     """x_local: this rank's rows (count vectors).  Returns (slices, (r0, r1), n) where slices maps
     each metric to this rank's contiguous piece of the packed triangle (rows r0..r1-1).
 
     `compute(x_full, metric_names, (r0, r1), tri_offset, slice_len)` defaults to the CUDA kernels;
-    the CPU tests inject a host function to exercise the plumbing under gloo."""
+    the CPU tests inject a host function to exercise the plumbing under gloo.  euclid_on_freq: euclid
+    between the frequency vectors x/sum(x) (default) or between the rows as stored (the file-based job
+    step, like kam_dists_host)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     x_full, _ = all_gather_rows(x_local, group)
     n = x_full.shape[0]
     r0, r1 = balanced_row_ranges(n, world)[rank]
     off0, off1 = tri_row_offset(n, r0), tri_row_offset(n, r1)
-    fn = compute or _compute_cuda
-    return fn(x_full, list(metrics), (r0, r1), off0, off1 - off0), (r0, r1), n
+    if compute is None:
+        def compute(*a):
+            return _compute_cuda(*a, euclid_on_freq=euclid_on_freq)
+    return compute(x_full, list(metrics), (r0, r1), off0, off1 - off0), (r0, r1), n
 
 
-def _compute_cuda(x_full, metrics, rows, tri_offset, slice_len):
+def _compute_cuda(x_full, metrics, rows, tri_offset, slice_len, euclid_on_freq=True):
     from . import _lib
     from . import dist as D
     lib = _lib.load()
@@ -113,7 +117,8 @@ def _compute_cuda(x_full, metrics, rows, tri_offset, slice_len):
                 mask |= bits[m]
             for size_fn in (lib.kam_gram_workspace_bytes, lib.kam_gram_workspace_bytes_int):
                 ws = torch.empty(max(size_fn(n, d), 256), dtype=torch.uint8, device=dev)
-                rc = lib.kam_gram_tri(x_full.data_ptr(), elem, n, d, x_full.stride(0), rows[0], rows[1], mask, 1,
+                rc = lib.kam_gram_tri(x_full.data_ptr(), elem, n, d, x_full.stride(0), rows[0], rows[1], mask,
+                                      int(euclid_on_freq),
                                       ptrs.get("euclid"), ptrs.get("cosine"), ptrs.get("pearson"), ws.data_ptr(),
                                       ws.numel(), stream)
                 if rc != _lib.KAM_E_WORKSPACE:
