@@ -19,6 +19,7 @@ One step = one pass of the `kmers` hot path over the whole batch.
           reference's own single-threaded numpy pass (backend.py:45-49), on a bounded sample.  The
           all-threads float32 C variant is reported beside it as `threaded_c_f32`.
   distances : secondary lines -- pairs/s of the distance kernels on vectors of the same shape
+  kmers_other_shapes : secondary lines -- the short-read (configs[3]) and megabase (configs[4]) shapes
 
 With --gpus N (torchrun, one rank per GPU) every rank processes its own 10 000-sequence shard
 (sequences are independent: no data-path collective, weak scaling); value = all ranks' vectors /
@@ -191,6 +192,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-distances", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short-read / long-sequence kmers lines")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -333,6 +335,15 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+        del out, batch
+        torch.cuda.empty_cache()
+        if world == 1 and not args.no_extra:
+            try:
+                from kameris_b200 import repr_bench
+                line["kmers_other_shapes"] = repr_bench.run(dev, hbm_peak)
+            except Exception as e:  # must not hide the headline
+                line["kmers_other_shapes"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            torch.cuda.empty_cache()
         if world == 1 and not args.no_distances:
             d = distance_lines(torch, dev, hbm_peak, tf_peak)
             if d is not None:

@@ -7,9 +7,14 @@
 // head_mask preserves.
 //
 // Three launches over tiles of 4096 characters:
-//   pack_count_kernel   valid bases per tile
+//   pack_count_kernel   classifies every character ONCE, four at a time inside a 32-bit word (a
+//                       byte-permute perfect hash gives the letter each byte would have to be; an exact
+//                       zero-byte test and three multiply "movemasks" give 4-bit valid / x / y masks),
+//                       stores the three 16-bit masks of each thread's 16 characters (8 B) and the
+//                       valid bases per tile
 //   pack_scan_kernel    exclusive scan of the tile counts (one CTA), grand total
-//   pack_scatter_kernel compaction: x/y bits land at their flat position; per-sequence starts
+//   pack_scatter_kernel compaction from the stored masks (the characters are not read again): x/y
+//                       bits land at their flat position; per-sequence starts
 // HBM-bound byte work: 16-byte loads, one uint2 store per 32 bases.
 #include "common.cuh"
 
@@ -29,37 +34,80 @@ struct Cls {
     uint32_t cnt, x, y, vmask;   // compacted x/y bits (cnt of them), validity of the 16 raw chars
 };
 
-__device__ __forceinline__ void cls_byte(uint32_t c, Cls &r, int i) {
-    const uint32_t sel = c & 31u;
-    const uint32_t v = ((c & 0xE0u) == 0x40u) ? ((LUT_VALID >> sel) & 1u) : 0u;
-    r.x |= (v & (LUT_X >> sel)) << r.cnt;
-    r.y |= (v & (LUT_Y >> sel)) << r.cnt;
-    r.vmask |= v << i;
-    r.cnt += v;
+// 4 characters in one word -> 4-bit masks (bit i = character i): valid, x-bit (G,T), y-bit (A,T).
+// (c >> 1) & 3 is a perfect hash of the four letters (A:0 C:1 T:2 G:3); a byte permute looks up the
+// letter each byte would have to be, and the byte is a base iff it equals that letter.  For bases,
+// x = bit 2 of the character and y = the complement of bit 1.
+__device__ __forceinline__ void cls_word(uint32_t w, uint32_t &v4, uint32_t &x4, uint32_t &y4) {
+    const uint32_t h4 = (w >> 1) & 0x03030303u;
+    const uint32_t t = h4 | (h4 >> 4);                                  // byte 0: h0 | h1<<4, byte 2: h2 | h3<<4
+    const uint32_t expect = __byte_perm(0x47544341u, 0u, __byte_perm(t, 0u, 0x4420u));
+    const uint32_t z = w ^ expect;
+    const uint32_t nz = ((z & 0x7f7f7f7fu) + 0x7f7f7f7fu) | z;          // bit 7 of each byte: byte != 0 (no cross-byte carry)
+    const uint32_t v1 = (~nz >> 7) & 0x01010101u;                       // bit 0 of each byte: valid
+    constexpr uint32_t GATHER = 0x01020408u;                            // bits 0, 8, 16, 24 -> bits 24..27
+    v4 = (v1 * GATHER) >> 24;
+    x4 = (((w >> 2) & v1) * GATHER) >> 24;
+    y4 = (((~w >> 1) & v1) * GATHER) >> 24;
 }
 
-// classify the 16 characters at chars[pos .. pos+16) (those at or beyond `total` are invalid)
-__device__ __forceinline__ Cls classify16(const uint8_t *__restrict__ chars, uint64_t pos, uint64_t total) {
-    Cls r{0, 0, 0, 0};
+__device__ __forceinline__ void cls_byte(uint32_t c, uint32_t &vm, uint32_t &xm, uint32_t &ym, int i) {
+    const uint32_t sel = c & 31u;
+    const uint32_t v = ((c & 0xE0u) == 0x40u) ? ((LUT_VALID >> sel) & 1u) : 0u;
+    vm |= v << i;
+    xm |= (v & (LUT_X >> sel)) << i;
+    ym |= (v & (LUT_Y >> sel)) << i;
+}
+
+// masks of the 16 characters at chars[pos .. pos+16) (those at or beyond `total` are invalid):
+// .x = valid | x << 16, .y = y
+__device__ __forceinline__ uint2 classify16(const uint8_t *__restrict__ chars, uint64_t pos, uint64_t total) {
+    uint32_t vm = 0, xm = 0, ym = 0;
     if (pos + PACK_CPT <= total) {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(chars + pos));
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) cls_byte((w[q] >> (8 * b)) & 0xFFu, r, q * 4 + b);
+        for (int q = 0; q < 4; ++q) {
+            uint32_t v4, x4, y4;
+            cls_word(w[q], v4, x4, y4);
+            vm |= v4 << (4 * q);
+            xm |= x4 << (4 * q);
+            ym |= y4 << (4 * q);
+        }
     } else {
         for (int i = 0; i < PACK_CPT; ++i)
-            if (pos + i < total) cls_byte(chars[pos + i], r, i);
+            if (pos + i < total) cls_byte(chars[pos + i], vm, xm, ym, i);
+    }
+    return make_uint2(vm | (xm << 16), ym);
+}
+
+// stored masks -> compacted x/y bits: drop the bit positions of the non-base characters (usually none,
+// or one IUPAC symbol), from the top so that the positions below stay put
+__device__ __forceinline__ Cls compact16(uint2 m) {
+    Cls r;
+    r.vmask = m.x & 0xffffu;
+    r.x = m.x >> 16;
+    r.y = m.y;
+    r.cnt = __popc(r.vmask);
+    uint32_t inv = ~r.vmask & 0xffffu;
+    while (inv) {
+        const uint32_t p = 31u - (uint32_t)__clz((int)inv);
+        const uint32_t low = (1u << p) - 1u;
+        r.x = (r.x & low) | ((r.x >> (p + 1)) << p);
+        r.y = (r.y & low) | ((r.y >> (p + 1)) << p);
+        inv ^= 1u << p;
     }
     return r;
 }
 
 __global__ void __launch_bounds__(PACK_THREADS) pack_count_kernel(const uint8_t *__restrict__ chars,
-                                                                  uint64_t total, uint32_t *__restrict__ tile_count) {
+                                                                  uint64_t total, uint32_t *__restrict__ tile_count,
+                                                                  uint2 *__restrict__ masks) {
     __shared__ uint32_t wsum[PACK_THREADS / 32];
     const uint64_t pos = (uint64_t)blockIdx.x * PACK_TILE + (uint64_t)threadIdx.x * PACK_CPT;
-    uint32_t c = pos < total ? classify16(chars, pos, total).cnt : 0;
+    const uint2 m = pos < total ? classify16(chars, pos, total) : make_uint2(0, 0);
+    masks[(uint64_t)blockIdx.x * PACK_THREADS + threadIdx.x] = m;
+    uint32_t c = __popc(m.x & 0xffffu);
     c = warp_sum(c);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -106,7 +154,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(const uint32_t 
     }
 }
 
-__global__ void __launch_bounds__(PACK_THREADS) pack_scatter_kernel(const uint8_t *__restrict__ chars, uint64_t total,
+__global__ void __launch_bounds__(PACK_THREADS) pack_scatter_kernel(const uint2 *__restrict__ masks, uint64_t total,
                                                                     const uint64_t *__restrict__ tile_off,
                                                                     const uint64_t *__restrict__ char_start,
                                                                     uint32_t n_seqs, uint2 *__restrict__ planes,
@@ -139,8 +187,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_scatter_kernel(const uint8_
         first_seq = lo;
     }
 
-    const uint64_t pos = tile_begin + (uint64_t)threadIdx.x * PACK_CPT;
-    Cls r = pos < total ? classify16(chars, pos, total) : Cls{0, 0, 0, 0};
+    const Cls r = compact16(__ldg(masks + (uint64_t)blockIdx.x * PACK_THREADS + threadIdx.x));
 
     // block exclusive scan of r.cnt
     uint32_t inc = r.cnt;
@@ -220,7 +267,8 @@ size_t kam_planes_words(uint64_t total_chars) { return (size_t)(total_chars / 32
 size_t kam_pack_workspace_bytes(uint64_t total_chars, uint32_t n_seqs) {
     (void)n_seqs;
     const uint64_t nt = n_tiles_of(total_chars);
-    return kam_align_up((nt + 1) * sizeof(uint32_t), 256) + kam_align_up((nt + 1) * sizeof(uint64_t), 256);
+    return kam_align_up((nt + 1) * sizeof(uint32_t), 256) + kam_align_up((nt + 1) * sizeof(uint64_t), 256) +
+           kam_align_up(nt * PACK_THREADS * sizeof(uint2), 256);
 }
 
 int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_t n_seqs, uint64_t total_chars,
@@ -238,13 +286,14 @@ int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_
     KAM_REQUIRE(nt < (1ull << 31), "input too large for one call");
     uint32_t *tile_count = (uint32_t *)d_ws;
     uint64_t *tile_off = (uint64_t *)((char *)d_ws + kam_align_up((nt + 1) * sizeof(uint32_t), 256));
+    uint2 *masks = (uint2 *)((char *)tile_off + kam_align_up((nt + 1) * sizeof(uint64_t), 256));
 
     KAM_CUDA(cudaMemsetAsync(d_planes, 0, kam_planes_words(total_chars) * sizeof(uint64_t), st));
-    if (nt) pack_count_kernel<<<(unsigned)nt, PACK_THREADS, 0, st>>>(d_chars, total_chars, tile_count);
+    if (nt) pack_count_kernel<<<(unsigned)nt, PACK_THREADS, 0, st>>>(d_chars, total_chars, tile_count, masks);
     pack_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_count, nt, tile_off, d_char_start, n_seqs, total_chars,
                                                  d_base_start);
     if (nt)
-        pack_scatter_kernel<<<(unsigned)nt, PACK_THREADS, 0, st>>>(d_chars, total_chars, tile_off, d_char_start,
+        pack_scatter_kernel<<<(unsigned)nt, PACK_THREADS, 0, st>>>(masks, total_chars, tile_off, d_char_start,
                                                                    n_seqs, (uint2 *)d_planes, d_base_start);
     if (n_seqs) head_mask_kernel<<<(n_seqs + 255) / 256, 256, 0, st>>>(d_chars, d_char_start, n_seqs, d_head_mask);
     KAM_CUDA(cudaGetLastError());
