@@ -177,14 +177,24 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_scatter_kernel(const uint2 
         sx[i] = 0;
         sy[i] = 0;
     }
-    if (threadIdx.x == 0) {
-        // lower_bound(char_start, tile_begin) over [0, n_seqs)
+    if (threadIdx.x < 32) {
+        // lower_bound(char_start, tile_begin) over [0, n_seqs), 32 probes per round (one per lane): a
+        // few dependent L2 round trips instead of log2(n_seqs) of them on one thread
         uint32_t lo = 0, hi = n_seqs;
         while (lo < hi) {
-            const uint32_t mid = lo + (hi - lo) / 2;
-            if (char_start[mid] < tile_begin) lo = mid + 1; else hi = mid;
+            const uint32_t step = (hi - lo + 31u) / 32u;
+            const uint64_t i = (uint64_t)lo + (uint64_t)threadIdx.x * step;
+            const bool less = i < hi && char_start[i] < tile_begin;
+            const uint32_t c = __popc(__ballot_sync(0xffffffffu, less));   // probes are monotone: 1..1 0..0
+            if (c == 0) {
+                hi = lo;
+            } else {
+                const uint64_t nh = (uint64_t)lo + (uint64_t)c * step;
+                lo = lo + (c - 1u) * step + 1u;
+                if (nh < hi) hi = (uint32_t)nh;
+            }
         }
-        first_seq = lo;
+        if (threadIdx.x == 0) first_seq = lo;
     }
 
     const Cls r = compact16(__ldg(masks + (uint64_t)blockIdx.x * PACK_THREADS + threadIdx.x));
