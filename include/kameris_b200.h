@@ -230,6 +230,19 @@ int kam_dists_host(const void *h_x, int elem, uint32_t n, uint64_t d, unsigned m
                    uint32_t *h_manhat, float *h_info, float *h_euclid, float *h_cosine,
                    float *h_pearson);
 
+/* ---------------------------------------------------------------------------------------------
+ * mds job step (kameris/job_steps/mds.py:10-35): classical multidimensional scaling.
+ * kam_mds_center replaces the numpy double-centring of mds.py:14-24 (same operation order, float64):
+ * packed `.mm-dist` triangle of n points (elem KAM_U32 or KAM_F32) -> d_B, n x n row-major.
+ * kam_symm_block is the n^2 product of the block subspace iteration that replaces
+ * scipy.sparse.linalg.eigsh(B, k=dim) of mds.py:26: d_Y = d_B * d_Q with d_Q, d_Y n x 16 row-major
+ * (a narrower block is zero-padded by the caller).  Both asynchronous on `stream`.
+ * ------------------------------------------------------------------------------------------- */
+#define KAM_MDS_BLOCK 16
+size_t kam_mds_workspace_bytes(uint32_t n);
+int kam_mds_center(const void *d_tri, int elem, uint32_t n, double *d_B, void *d_ws, size_t ws_bytes, void *stream);
+int kam_symm_block(const double *d_B, uint32_t n, const double *d_Q, double *d_Y, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,210 @@
+// mds.cu -- the n^2 parts of the `mds` job step (kameris/job_steps/mds.py:10-35: classical
+// multidimensional scaling of a distance matrix) as HBM-bound float64 kernels:
+//
+//   kam_mds_center   packed `.mm-dist` triangle (uint32 manhat, float32 others) ->
+//                    B = -0.5 (D^2 - colmean_j - rowmean_i + mean), n x n float64 (mds.py:14-24, same
+//                    operation order), in three sweeps: expand+square (each 32x32 tile of the triangle
+//                    is read once, coalesced, and written to both (i,j) and, transposed through shared
+//                    memory, (j,i)), row sums, centring in place
+//   kam_symm_block   Y = B Q for the symmetric B and a block of 16 column vectors: the matrix-block
+//                    product of the subspace iteration that replaces scipy's eigsh(B, k=dim) (mds.py:26).
+//                    B is streamed from HBM exactly once per call (n^2 x 8 bytes -- the roofline);
+//                    the 16-column block is staged through shared memory in 128-row slabs and shared by
+//                    the 16 rows of a CTA; each warp owns two rows of B, lanes stride the columns, 8
+//                    independent 256-byte row loads are in flight per warp.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MT = 32;                     // tile edge of the expand kernel
+constexpr int SB = 16;                     // columns of the vector block
+constexpr int SY_WARPS = 8, SY_ROWS = 2;   // rows of B per warp
+constexpr int SY_SLAB = 128;               // rows of Q staged per step (4 chunks of 32 columns of B)
+
+template <typename T>
+__global__ void __launch_bounds__(MT * 8) mds_expand_sq_kernel(const T *__restrict__ tri, uint32_t n,
+                                                               double *__restrict__ B) {
+    __shared__ double tile[MT][MT + 1];
+    // blockIdx.x enumerates the tile pairs (bi <= bj) of the upper triangle row by row
+    const uint32_t nt = (n + MT - 1) / MT;
+    uint32_t bi = 0, rem = blockIdx.x;
+    while (rem >= nt - bi) {               // at most nt steps; nt is small next to the tile work
+        rem -= nt - bi;
+        ++bi;
+    }
+    const uint32_t bj = bi + rem;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (uint32_t r = ty; r < MT; r += 8) {
+        const uint64_t i = (uint64_t)bi * MT + r, j = (uint64_t)bj * MT + tx;
+        double v = 0.0;
+        if (i < n && j < n && j > i) {
+            const double d = (double)tri[(uint64_t)n * i - i * (i + 3) / 2 + j - 1];
+            v = d * d;
+        } else if (i < n && j < n && j < i) {                      // only inside diagonal tiles
+            const double d = (double)tri[(uint64_t)n * j - j * (j + 3) / 2 + i - 1];
+            v = d * d;
+        }
+        tile[r][tx] = v;
+        if (i < n && j < n) B[i * n + j] = v;
+    }
+    if (bi == bj) return;                                          // diagonal tile: both halves written above
+    __syncthreads();
+    for (uint32_t r = ty; r < MT; r += 8) {
+        const uint64_t j = (uint64_t)bj * MT + r, i = (uint64_t)bi * MT + tx;   // row j of B, column i
+        if (i < n && j < n) B[j * n + i] = tile[tx][r];
+    }
+}
+
+// tot[i] = (sum of row i) / n  (== numpy's column means: B is symmetric).  One warp per row.
+__global__ void __launch_bounds__(256) mds_rowmean_kernel(const double *__restrict__ B, uint32_t n,
+                                                          double *__restrict__ tot) {
+    const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double *r = B + (uint64_t)row * n;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    uint32_t j = lane;
+    for (; j + 96 < n; j += 128) {
+        s0 += r[j];
+        s1 += r[j + 32];
+        s2 += r[j + 64];
+        s3 += r[j + 96];
+    }
+    for (; j < n; j += 32) s0 += r[j];
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) tot[row] = s / (double)n;
+}
+
+// mean[0] = (sum of tot) / n; one CTA
+__global__ void __launch_bounds__(1024) mds_mean_kernel(const double *__restrict__ tot, uint32_t n,
+                                                        double *__restrict__ mean) {
+    __shared__ double red[32];
+    double s = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += 1024) s += tot[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) mean[0] = s / (double)n;
+    }
+}
+
+// B_ij = ((B_ij - tot_j) - tot_i + mean) * -0.5, the operation order of mds.py:19-24
+__global__ void __launch_bounds__(256) mds_center_kernel(double *__restrict__ B, uint32_t n,
+                                                         const double *__restrict__ tot,
+                                                         const double *__restrict__ mean) {
+    const uint32_t i = blockIdx.y;
+    const double ti = tot[i], m = mean[0];
+    double *r = B + (uint64_t)i * n;
+    for (uint32_t j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256)
+        r[j] = ((r[j] - tot[j]) - ti + m) * -0.5;
+}
+
+// Y[n x 16] = B[n x n] * Q[n x 16]
+__global__ void __launch_bounds__(SY_WARPS * 32) symm_block_kernel(const double *__restrict__ B, uint32_t n,
+                                                                   const double *__restrict__ Q,
+                                                                   double *__restrict__ Y) {
+    __shared__ double qs[SB][SY_SLAB];                       // transposed slab: lane-consecutive reads
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t row0 = (blockIdx.x * SY_WARPS + warp) * SY_ROWS;
+    const double *r0 = B + (uint64_t)(row0 < n ? row0 : 0) * n;
+    const double *r1 = B + (uint64_t)(row0 + 1 < n ? row0 + 1 : 0) * n;
+    double acc[SY_ROWS][SB];
+#pragma unroll
+    for (int r = 0; r < SY_ROWS; ++r)
+#pragma unroll
+        for (int c = 0; c < SB; ++c) acc[r][c] = 0.0;
+
+    for (uint32_t j0 = 0; j0 < n; j0 += SY_SLAB) {
+        // the row loads of this slab first (independent, in flight while the Q slab is staged)
+        double b0[SY_SLAB / 32], b1[SY_SLAB / 32];
+#pragma unroll
+        for (int q = 0; q < SY_SLAB / 32; ++q) {
+            const uint32_t j = j0 + q * 32 + lane;
+            b0[q] = j < n ? __ldg(r0 + j) : 0.0;
+            b1[q] = j < n ? __ldg(r1 + j) : 0.0;
+        }
+        __syncthreads();                                     // previous slab consumed
+        for (uint32_t e = threadIdx.x; e < SY_SLAB * SB; e += SY_WARPS * 32) {
+            const uint32_t jj = e / SB, c = e % SB;          // coalesced read of Q rows
+            qs[c][jj] = j0 + jj < n ? __ldg(Q + (uint64_t)(j0 + jj) * SB + c) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < SY_SLAB / 32; ++q) {
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+                const double qv = qs[c][q * 32 + lane];
+                acc[0][c] = fma(b0[q], qv, acc[0][c]);
+                acc[1][c] = fma(b1[q], qv, acc[1][c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < SY_ROWS; ++r)
+#pragma unroll
+        for (int c = 0; c < SB; ++c) {
+            double v = acc[r][c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            acc[r][c] = v;
+        }
+    if (lane < SB) {
+#pragma unroll
+        for (int r = 0; r < SY_ROWS; ++r) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < SB; ++c)
+                if ((int)lane == c) v = acc[r][c];
+            if (row0 + r < n) Y[(uint64_t)(row0 + r) * SB + lane] = v;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t kam_mds_workspace_bytes(uint32_t n) { return kam_align_up((size_t)n * 8, 256) + 256; }
+
+int kam_mds_center(const void *d_tri, int elem, uint32_t n, double *d_B, void *d_ws, size_t ws_bytes, void *stream) {
+    KAM_REQUIRE(d_B && d_ws && (d_tri || n < 2), "null pointer");
+    KAM_REQUIRE(elem == KAM_U32 || elem == KAM_F32, "a .mm-dist triangle holds uint32 (manhat) or float32 values");
+    KAM_REQUIRE(n >= 1, "empty matrix");
+    if (ws_bytes < kam_mds_workspace_bytes(n)) {
+        kam_set_error("kam_mds_center: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double *tot = (double *)d_ws;
+    double *mean = (double *)((char *)d_ws + kam_align_up((size_t)n * 8, 256));
+    const uint64_t nt = (n + MT - 1) / MT, pairs = nt * (nt + 1) / 2;
+    KAM_REQUIRE(pairs < (1ull << 31), "matrix too large for one call");
+    if (elem == KAM_U32)
+        mds_expand_sq_kernel<uint32_t><<<(unsigned)pairs, MT * 8, 0, st>>>((const uint32_t *)d_tri, n, d_B);
+    else
+        mds_expand_sq_kernel<float><<<(unsigned)pairs, MT * 8, 0, st>>>((const float *)d_tri, n, d_B);
+    mds_rowmean_kernel<<<(n + 7) / 8, 256, 0, st>>>(d_B, n, tot);
+    mds_mean_kernel<<<1, 1024, 0, st>>>(tot, n, mean);
+    unsigned gx = (n + 255) / 256;
+    if (gx > 64) gx = 64;
+    mds_center_kernel<<<dim3(gx, n), 256, 0, st>>>(d_B, n, tot, mean);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+int kam_symm_block(const double *d_B, uint32_t n, const double *d_Q, double *d_Y, void *stream) {
+    KAM_REQUIRE(d_B && d_Q && d_Y, "null pointer");
+    KAM_REQUIRE(n >= 1, "empty matrix");
+    const unsigned grid = (n + SY_WARPS * SY_ROWS - 1) / (SY_WARPS * SY_ROWS);
+    symm_block_kernel<<<grid, SY_WARPS * 32, 0, (cudaStream_t)stream>>>(d_B, n, d_Q, d_Y);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+}  // extern "C"

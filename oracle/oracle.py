@@ -240,3 +240,47 @@ def cdist_triangle(x: np.ndarray, metric: str) -> np.ndarray:
 def cdist_rect(x: np.ndarray, y: np.ndarray, metric: str) -> np.ndarray:
     from scipy.spatial.distance import cdist
     return cdist(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64), _SCIPY[metric])
+
+
+# ---- mds job step (kameris/job_steps/mds.py:10-35) ------------------------------------------------------
+def full_from_triangle(tri: np.ndarray, n: int) -> np.ndarray:
+    """what kameris_formats.dist_reader.read_matrix hands to mds (mds.py:39): the symmetric N x N matrix."""
+    m = np.zeros((n, n), dtype=tri.dtype)
+    iu = np.triu_indices(n, 1)
+    m[iu] = tri
+    m.T[iu] = tri
+    return m
+
+
+def mds_reference(delta: np.ndarray, dim: int) -> np.ndarray:
+    """Restatement of mds(delta, dim), kameris/job_steps/mds.py:10-35: classical MDS.
+    B = -0.5 (D^2 - colmean - rowmean + mean) (mds.py:14-24); the `dim` eigenpairs of largest magnitude
+    (scipy eigsh default which='LM', mds.py:26), in DEscending algebraic order after the fliplr of
+    mds.py:32; points = V sqrt(lambda); columns with a negative eigenvalue become NaN and are dropped
+    (mds.py:34).  Deterministic (full symmetric eigendecomposition instead of ARPACK); eigenvector signs
+    are arbitrary in both.  Pinned against tests/golden/ref_mds.npz (outputs of the reference function
+    itself, oracle/refpy/gen_golden_mds.py)."""
+    delta = np.asarray(delta).astype(float)
+    n = delta.shape[0]
+    sq = delta ** 2
+    tot = sq.sum(axis=0) / n
+    b = -0.5 * (sq - tot[None, :] - tot[:, None] + tot.sum() / n)
+    w, v = np.linalg.eigh((b + b.T) / 2)
+    pick = np.argsort(-np.abs(w), kind="stable")[:dim]
+    pick = pick[np.argsort(-w[pick], kind="stable")]              # descending algebraic order
+    with np.errstate(invalid="ignore"):
+        pts = v[:, pick] * np.sqrt(w[pick])[None, :]
+    return pts[:, ~np.isnan(pts).any(axis=0)]
+
+
+def same_up_to_column_signs(a: np.ndarray, b: np.ndarray, rtol: float) -> bool:
+    """eigenvector signs are arbitrary: compare column by column with the better of the two signs;
+    the tolerance is relative to the column's largest entry."""
+    if a.shape != b.shape:
+        return False
+    for j in range(a.shape[1]):
+        scale = np.abs(b[:, j]).max()
+        err = min(np.abs(a[:, j] - b[:, j]).max(), np.abs(a[:, j] + b[:, j]).max())
+        if not err <= rtol * scale:
+            return False
+    return True
