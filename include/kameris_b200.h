@@ -241,7 +241,9 @@ int kam_dists_host(const void *h_x, int elem, uint32_t n, uint64_t d, unsigned m
 #define KAM_MDS_BLOCK 16
 size_t kam_mds_workspace_bytes(uint32_t n);
 int kam_mds_center(const void *d_tri, int elem, uint32_t n, double *d_B, void *d_ws, size_t ws_bytes, void *stream);
-int kam_symm_block(const double *d_B, uint32_t n, const double *d_Q, double *d_Y, void *stream);
+size_t kam_symm_workspace_bytes(uint32_t n);
+int kam_symm_block(const double *d_B, uint32_t n, const double *d_Q, double *d_Y, void *d_ws, size_t ws_bytes,
+                   void *stream);
 
 #ifdef __cplusplus
 }

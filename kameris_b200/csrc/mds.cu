@@ -18,7 +18,7 @@ namespace {
 
 constexpr int MT = 32;                     // tile edge of the expand kernel
 constexpr int SB = 16;                     // columns of the vector block
-constexpr int SY_WARPS = 8, SY_ROWS = 2;   // rows of B per warp
+constexpr int SY_WARPS = 8, SY_ROWS = 4;   // rows of B per warp
 constexpr int SY_SLAB = 128;               // rows of Q staged per step (4 chunks of 32 columns of B)
 
 template <typename T>
@@ -105,65 +105,124 @@ __global__ void __launch_bounds__(256) mds_center_kernel(double *__restrict__ B,
         r[j] = ((r[j] - tot[j]) - ti + m) * -0.5;
 }
 
-// Y[n x 16] = B[n x n] * Q[n x 16]
-__global__ void __launch_bounds__(SY_WARPS * 32) symm_block_kernel(const double *__restrict__ B, uint32_t n,
-                                                                   const double *__restrict__ Q,
-                                                                   double *__restrict__ Y) {
-    __shared__ double qs[SB][SY_SLAB];                       // transposed slab: lane-consecutive reads
+// Ypart[split][n x 16] = B[:, j range of the split] * Q[j range, :].  CTA = 8 warps x 4 rows of B, lanes
+// stride the columns j; grid = (row blocks, column splits) so that the number of work items fills the SMs
+// evenly (n = 10 000: 313 row blocks alone would be 2.1 waves).  Software pipeline over slabs of 128
+// columns: the 16 row loads of slab s+1 (4 rows x 4 chunks, independent 256-byte warp requests) and the
+// thread's share of the next 128 x 16 slab of Q are issued BEFORE the multiply of slab s, so HBM/L2
+// latency hides behind 256 DFMA per lane.  Q slabs live in shared memory with a row stride of 18 doubles
+// (the 16-byte reads of a quarter-warp fall into distinct banks), double-buffered: one barrier per slab.
+constexpr int SY_QLD = SB + 2;
+constexpr int SY_QPT = SY_SLAB * SB / (SY_WARPS * 32);   // Q elements staged per thread and slab (8)
+
+__global__ void __launch_bounds__(SY_WARPS * 32, 1) symm_block_kernel(const double *__restrict__ B, uint32_t n,
+                                                                      const double *__restrict__ Q,
+                                                                      double *__restrict__ Ypart,
+                                                                      uint32_t cols_per_split) {
+    __shared__ __align__(16) double qs[2][SY_SLAB][SY_QLD];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t row0 = (blockIdx.x * SY_WARPS + warp) * SY_ROWS;
-    const double *r0 = B + (uint64_t)(row0 < n ? row0 : 0) * n;
-    const double *r1 = B + (uint64_t)(row0 + 1 < n ? row0 + 1 : 0) * n;
+    const uint32_t jbeg = blockIdx.y * cols_per_split;
+    const uint32_t jend = jbeg + cols_per_split < n ? jbeg + cols_per_split : n;
+    const double *rp[SY_ROWS];
+#pragma unroll
+    for (int r = 0; r < SY_ROWS; ++r) rp[r] = B + (uint64_t)(row0 + r < n ? row0 + r : 0) * n;
     double acc[SY_ROWS][SB];
 #pragma unroll
     for (int r = 0; r < SY_ROWS; ++r)
 #pragma unroll
         for (int c = 0; c < SB; ++c) acc[r][c] = 0.0;
 
-    for (uint32_t j0 = 0; j0 < n; j0 += SY_SLAB) {
-        // the row loads of this slab first (independent, in flight while the Q slab is staged)
-        double b0[SY_SLAB / 32], b1[SY_SLAB / 32];
+    double bv[SY_ROWS][SY_SLAB / 32], qreg[SY_QPT];
+    auto load_slab = [&](uint32_t j0) {
 #pragma unroll
         for (int q = 0; q < SY_SLAB / 32; ++q) {
             const uint32_t j = j0 + q * 32 + lane;
-            b0[q] = j < n ? __ldg(r0 + j) : 0.0;
-            b1[q] = j < n ? __ldg(r1 + j) : 0.0;
+#pragma unroll
+            for (int r = 0; r < SY_ROWS; ++r) bv[r][q] = j < jend ? __ldg(rp[r] + j) : 0.0;
         }
-        __syncthreads();                                     // previous slab consumed
-        for (uint32_t e = threadIdx.x; e < SY_SLAB * SB; e += SY_WARPS * 32) {
-            const uint32_t jj = e / SB, c = e % SB;          // coalesced read of Q rows
-            qs[c][jj] = j0 + jj < n ? __ldg(Q + (uint64_t)(j0 + jj) * SB + c) : 0.0;
+#pragma unroll
+        for (int i = 0; i < SY_QPT; ++i) {
+            const uint32_t e = threadIdx.x + i * SY_WARPS * 32, jj = e / SB;
+            qreg[i] = j0 + jj < jend ? __ldg(Q + (uint64_t)(j0 + jj) * SB + e % SB) : 0.0;
         }
-        __syncthreads();
+    };
+    auto store_q = [&](uint32_t buf) {
+#pragma unroll
+        for (int i = 0; i < SY_QPT; ++i) {
+            const uint32_t e = threadIdx.x + i * SY_WARPS * 32;
+            qs[buf][e / SB][e % SB] = qreg[i];
+        }
+    };
+
+    load_slab(jbeg);
+    store_q(0);
+    __syncthreads();
+    uint32_t buf = 0;
+    for (uint32_t j0 = jbeg; j0 < jend; j0 += SY_SLAB, buf ^= 1u) {
+        double bc[SY_ROWS][SY_SLAB / 32];
+#pragma unroll
+        for (int r = 0; r < SY_ROWS; ++r)
+#pragma unroll
+            for (int q = 0; q < SY_SLAB / 32; ++q) bc[r][q] = bv[r][q];
+        const bool more = j0 + SY_SLAB < jend;
+        if (more) load_slab(j0 + SY_SLAB);                     // in flight during the multiply below
 #pragma unroll
         for (int q = 0; q < SY_SLAB / 32; ++q) {
+            const double2 *qrow = reinterpret_cast<const double2 *>(&qs[buf][q * 32 + lane][0]);
 #pragma unroll
-            for (int c = 0; c < SB; ++c) {
-                const double qv = qs[c][q * 32 + lane];
-                acc[0][c] = fma(b0[q], qv, acc[0][c]);
-                acc[1][c] = fma(b1[q], qv, acc[1][c]);
+            for (int c2 = 0; c2 < SB / 2; ++c2) {
+                const double2 qv = qrow[c2];
+#pragma unroll
+                for (int r = 0; r < SY_ROWS; ++r) {
+                    acc[r][2 * c2] = fma(bc[r][q], qv.x, acc[r][2 * c2]);
+                    acc[r][2 * c2 + 1] = fma(bc[r][q], qv.y, acc[r][2 * c2 + 1]);
+                }
             }
         }
+        if (more) store_q(buf ^ 1u);                           // that buffer was last read one slab ago
+        __syncthreads();
     }
+    double *Yp = Ypart + (uint64_t)blockIdx.y * n * SB;
 #pragma unroll
-    for (int r = 0; r < SY_ROWS; ++r)
+    for (int r = 0; r < SY_ROWS; ++r) {
+        double mine = 0.0;
 #pragma unroll
         for (int c = 0; c < SB; ++c) {
             double v = acc[r][c];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            acc[r][c] = v;
+            if ((int)lane == c) mine = v;
         }
-    if (lane < SB) {
-#pragma unroll
-        for (int r = 0; r < SY_ROWS; ++r) {
-            double v = 0.0;
-#pragma unroll
-            for (int c = 0; c < SB; ++c)
-                if ((int)lane == c) v = acc[r][c];
-            if (row0 + r < n) Y[(uint64_t)(row0 + r) * SB + lane] = v;
+        if (lane < SB && row0 + r < n) Yp[(uint64_t)(row0 + r) * SB + lane] = mine;
+    }
+}
+
+// Y = sum over the column splits (fixed order: deterministic)
+__global__ void __launch_bounds__(256) symm_reduce_kernel(const double *__restrict__ Ypart, uint32_t n, uint32_t splits,
+                                                          double *__restrict__ Y) {
+    const uint64_t e = (uint64_t)blockIdx.x * 256 + threadIdx.x, tot = (uint64_t)n * SB;
+    if (e >= tot) return;
+    double s = Ypart[e];
+    for (uint32_t k = 1; k < splits; ++k) s += Ypart[(uint64_t)k * tot + e];
+    Y[e] = s;
+}
+
+// number of column splits: fill whole waves of SMs (one CTA per SM), at least 4 slabs per split
+inline uint32_t symm_splits(uint32_t n) {
+    const uint32_t rb = (n + SY_WARPS * SY_ROWS - 1) / (SY_WARPS * SY_ROWS), sms = (uint32_t)kam_sm_count();
+    uint32_t best = 1;
+    double best_eff = 0.0;
+    for (uint32_t s = 1; s <= 8; ++s) {
+        if (s > 1 && n / s < 4 * SY_SLAB) break;
+        const double waves = (double)rb * s / sms;
+        const double eff = waves / (double)(uint64_t)(waves + 0.999999);
+        if (eff > best_eff + 0.02) {
+            best_eff = eff;
+            best = s;
         }
     }
+    return best;
 }
 
 }  // namespace
@@ -198,11 +257,23 @@ int kam_mds_center(const void *d_tri, int elem, uint32_t n, double *d_B, void *d
     return KAM_OK;
 }
 
-int kam_symm_block(const double *d_B, uint32_t n, const double *d_Q, double *d_Y, void *stream) {
-    KAM_REQUIRE(d_B && d_Q && d_Y, "null pointer");
+size_t kam_symm_workspace_bytes(uint32_t n) { return (size_t)symm_splits(n) * n * SB * sizeof(double) + 256; }
+
+int kam_symm_block(const double *d_B, uint32_t n, const double *d_Q, double *d_Y, void *d_ws, size_t ws_bytes,
+                   void *stream) {
+    KAM_REQUIRE(d_B && d_Q && d_Y && d_ws, "null pointer");
     KAM_REQUIRE(n >= 1, "empty matrix");
-    const unsigned grid = (n + SY_WARPS * SY_ROWS - 1) / (SY_WARPS * SY_ROWS);
-    symm_block_kernel<<<grid, SY_WARPS * 32, 0, (cudaStream_t)stream>>>(d_B, n, d_Q, d_Y);
+    if (ws_bytes < kam_symm_workspace_bytes(n)) {
+        kam_set_error("kam_symm_block: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t splits = symm_splits(n);
+    const uint32_t cps = ((n + splits - 1) / splits + SY_SLAB - 1) / SY_SLAB * SY_SLAB;   // whole slabs per split
+    const unsigned rb = (n + SY_WARPS * SY_ROWS - 1) / (SY_WARPS * SY_ROWS);
+    double *part = splits == 1 ? d_Y : (double *)d_ws;
+    symm_block_kernel<<<dim3(rb, splits), SY_WARPS * 32, 0, st>>>(d_B, n, d_Q, part, cps);
+    if (splits > 1) symm_reduce_kernel<<<(unsigned)(((uint64_t)n * SB + 255) / 256), 256, 0, st>>>(part, n, splits, d_Y);
     KAM_CUDA(cudaGetLastError());
     return KAM_OK;
 }

@@ -158,14 +158,14 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_scatter_kernel(const uint2 
                                                                     const uint64_t *__restrict__ tile_off,
                                                                     const uint64_t *__restrict__ char_start,
                                                                     uint32_t n_seqs, uint2 *__restrict__ planes,
-                                                                    uint64_t *__restrict__ base_start) {
+                                                                    uint64_t *__restrict__ base_start,
+                                                                    const uint32_t *__restrict__ tile_first_seq) {
     constexpr int NW = PACK_THREADS / 32;
     constexpr int SW = PACK_TILE / 32 + 2;   // words a tile's compacted bases can touch
     __shared__ uint32_t sx[SW], sy[SW];
     __shared__ uint32_t wsum[NW];
     __shared__ uint32_t pref[PACK_THREADS];
     __shared__ uint32_t vmask[PACK_THREADS];
-    __shared__ uint32_t first_seq;
 
     const uint64_t tile_begin = (uint64_t)blockIdx.x * PACK_TILE;
     const uint64_t tile_end = tile_begin + PACK_TILE < total ? tile_begin + PACK_TILE : total;
@@ -177,26 +177,6 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_scatter_kernel(const uint2 
         sx[i] = 0;
         sy[i] = 0;
     }
-    if (threadIdx.x < 32) {
-        // lower_bound(char_start, tile_begin) over [0, n_seqs), 32 probes per round (one per lane): a
-        // few dependent L2 round trips instead of log2(n_seqs) of them on one thread
-        uint32_t lo = 0, hi = n_seqs;
-        while (lo < hi) {
-            const uint32_t step = (hi - lo + 31u) / 32u;
-            const uint64_t i = (uint64_t)lo + (uint64_t)threadIdx.x * step;
-            const bool less = i < hi && char_start[i] < tile_begin;
-            const uint32_t c = __popc(__ballot_sync(0xffffffffu, less));   // probes are monotone: 1..1 0..0
-            if (c == 0) {
-                hi = lo;
-            } else {
-                const uint64_t nh = (uint64_t)lo + (uint64_t)c * step;
-                lo = lo + (c - 1u) * step + 1u;
-                if (nh < hi) hi = (uint32_t)nh;
-            }
-        }
-        if (threadIdx.x == 0) first_seq = lo;
-    }
-
     const Cls r = compact16(__ldg(masks + (uint64_t)blockIdx.x * PACK_THREADS + threadIdx.x));
 
     // block exclusive scan of r.cnt
@@ -242,13 +222,29 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_scatter_kernel(const uint2 
     }
 
     // sequences that start inside this tile
-    for (uint32_t s = first_seq + threadIdx.x; s < n_seqs; s += PACK_THREADS) {
+    for (uint32_t s = tile_first_seq[blockIdx.x] + threadIdx.x; s < n_seqs; s += PACK_THREADS) {
         const uint64_t c0 = char_start[s];
         if (c0 >= tile_end) break;             // char_start is non-decreasing
         const uint32_t rel = (uint32_t)(c0 - tile_begin);
         const uint32_t th = rel / PACK_CPT, o = rel % PACK_CPT;
         base_start[s] = goff + pref[th] + __popc(vmask[th] & ((1u << o) - 1u));
     }
+}
+
+// tile_first_seq[t] = first sequence whose first character lies at or after the start of tile t
+// (lower_bound of char_start): thread s fills the tiles (tile of sequence s-1, tile of sequence s];
+// the thread of the last sequence also fills the tiles behind it with n_seqs.
+__global__ void tile_first_seq_kernel(const uint64_t *__restrict__ char_start, uint32_t n_seqs, uint64_t n_tiles,
+                                      uint32_t *__restrict__ tile_first_seq) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seqs) return;
+    const uint64_t c = char_start[s];
+    // tiles i with char_start[s-1] < i * TILE <= char_start[s]  (equal starts: the first sequence takes them)
+    const uint64_t lo = s ? char_start[s - 1] / PACK_TILE + 1 : 0;
+    const uint64_t hi = c / PACK_TILE;
+    for (uint64_t i = lo; i <= hi && i < n_tiles; ++i) tile_first_seq[i] = s;
+    if (s == n_seqs - 1)
+        for (uint64_t i = hi + 1; i < n_tiles; ++i) tile_first_seq[i] = n_seqs;
 }
 
 __global__ void head_mask_kernel(const uint8_t *__restrict__ chars, const uint64_t *__restrict__ char_start,
@@ -278,7 +274,7 @@ size_t kam_pack_workspace_bytes(uint64_t total_chars, uint32_t n_seqs) {
     (void)n_seqs;
     const uint64_t nt = n_tiles_of(total_chars);
     return kam_align_up((nt + 1) * sizeof(uint32_t), 256) + kam_align_up((nt + 1) * sizeof(uint64_t), 256) +
-           kam_align_up(nt * PACK_THREADS * sizeof(uint2), 256);
+           kam_align_up(nt * PACK_THREADS * sizeof(uint2), 256) + kam_align_up((nt + 1) * sizeof(uint32_t), 256);
 }
 
 int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_t n_seqs, uint64_t total_chars,
@@ -297,14 +293,17 @@ int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_
     uint32_t *tile_count = (uint32_t *)d_ws;
     uint64_t *tile_off = (uint64_t *)((char *)d_ws + kam_align_up((nt + 1) * sizeof(uint32_t), 256));
     uint2 *masks = (uint2 *)((char *)tile_off + kam_align_up((nt + 1) * sizeof(uint64_t), 256));
+    uint32_t *tile_first = (uint32_t *)((char *)masks + kam_align_up(nt * PACK_THREADS * sizeof(uint2), 256));
 
     KAM_CUDA(cudaMemsetAsync(d_planes, 0, kam_planes_words(total_chars) * sizeof(uint64_t), st));
     if (nt) pack_count_kernel<<<(unsigned)nt, PACK_THREADS, 0, st>>>(d_chars, total_chars, tile_count, masks);
     pack_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_count, nt, tile_off, d_char_start, n_seqs, total_chars,
                                                  d_base_start);
+    if (nt && n_seqs)
+        tile_first_seq_kernel<<<(n_seqs + 255) / 256, 256, 0, st>>>(d_char_start, n_seqs, nt, tile_first);
     if (nt)
         pack_scatter_kernel<<<(unsigned)nt, PACK_THREADS, 0, st>>>(masks, total_chars, tile_off, d_char_start,
-                                                                   n_seqs, (uint2 *)d_planes, d_base_start);
+                                                                   n_seqs, (uint2 *)d_planes, d_base_start, tile_first);
     if (n_seqs) head_mask_kernel<<<(n_seqs + 255) / 256, 256, 0, st>>>(d_chars, d_char_start, n_seqs, d_head_mask);
     KAM_CUDA(cudaGetLastError());
     return KAM_OK;

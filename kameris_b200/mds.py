@@ -33,7 +33,11 @@ def center(tri, n):
     return B
 
 
-def symm_block(B, Q, out=None):
+def symm_workspace(n, device):
+    return torch.empty(_lib.load().kam_symm_workspace_bytes(n), dtype=torch.uint8, device=device)
+
+
+def symm_block(B, Q, out=None, workspace=None):
     """Y = B Q for symmetric B (n, n) float64 and Q (n, 16) float64, both contiguous on the device."""
     lib = _lib.load()
     n = B.shape[0]
@@ -41,8 +45,9 @@ def symm_block(B, Q, out=None):
     assert B.is_contiguous() and Q.is_contiguous()
     if out is None:
         out = torch.empty_like(Q)
+    ws = workspace if workspace is not None else symm_workspace(n, B.device)
     with torch.cuda.device(B.device):
-        check(lib.kam_symm_block(B.data_ptr(), n, Q.data_ptr(), out.data_ptr(),
+        check(lib.kam_symm_block(B.data_ptr(), n, Q.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                  torch.cuda.current_stream(B.device).cuda_stream))
     return out
 
@@ -66,9 +71,10 @@ def top_eigenpairs(B, dim, tol=1e-12, max_iter=5000, seed=0, stats=None):
     Q = torch.zeros((n, BLOCK), dtype=torch.float64, device=dev)
     Q[:, :b] = torch.linalg.qr(torch.randn((n, b), dtype=torch.float64, device=dev, generator=g))[0]
     Y = torch.empty_like(Q)
+    ws = symm_workspace(n, dev)
     it = 0
     while True:
-        symm_block(B, Q, out=Y)
+        symm_block(B, Q, out=Y, workspace=ws)
         it += 1
         T = Q[:, :b].T @ Y[:, :b]
         theta, S = torch.linalg.eigh((T + T.T) * 0.5)

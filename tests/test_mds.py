@@ -66,7 +66,7 @@ def test_center_kernel_vs_numpy(M):
         tot = sq.sum(axis=0) / n
         ref = (sq - tot[None, :] - tot[:, None] + tot.sum() / n) * -0.5
         np.testing.assert_allclose(B, ref, rtol=0, atol=1e-12 * np.abs(ref).max(), err_msg=name)
-        assert np.array_equal(B, B.T)
+        np.testing.assert_allclose(B, B.T, rtol=0, atol=1e-12 * np.abs(ref).max())   # the operation order of mds.py:19-24 is not symmetric in the last bit
 
 
 @pytest.mark.gpu
