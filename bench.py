@@ -213,6 +213,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep NCCL's version banner off stdout (ONE JSON line)
         dist_pg.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     hbm_peak, tf_peak, peak_src = load_peaks()

@@ -127,7 +127,7 @@ def config2(rank, world, dev, scale):
     outs = {k: torch.empty((n, 4 ** k), dtype=torch.float32, device=dev) for k in range(1, 10)}
     wss = {k: R.kmer_workspace(n, k, dev) for k in range(1, 10)}
 
-    def sweep():      # one fused kernel: scan at k=9, orders 8..1 by in-kernel 2x2 pooling
+    def sweep():      # orders 9, 8: the tiled kernel; orders 7..1: one fused scan at k=7 pooled down in the CTA
         R.kmer_sweep(b, 1, 9, 16, "freq32", out_tensors=outs, workspace=wss[9])
     sweep()
     _, t = timed(sweep, dev, world)
