@@ -20,6 +20,9 @@
  *                         scipy.spatial.distance {euclidean, cosine, correlation}
  *   kam_dists_host        `generation_dists <in> <prefix> <names>` as invoked by
  *                         kameris/job_steps/backend.py:59-66, minus file I/O
+ *   kam_mds_center        the numpy double-centring of kameris/job_steps/mds.py:14-24
+ *   kam_symm_block        the matrix-block product of the eigen-solve that replaces
+ *                         scipy.sparse.linalg.eigsh(B, k=dim), kameris/job_steps/mds.py:26
  *
  * Conventions: every function returns 0 on success and a negative KAM_E_* code on failure;
  * kam_last_error() returns a thread-local message.  No exceptions and no ownership cross the ABI:

@@ -119,39 +119,91 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_count_kernel(const uint8_t 
     }
 }
 
-// one CTA: tile_off[t] = sum of tile_count[0..t); base_start[s] = grand total for every trailing
-// sequence that starts at `total` (they own no tile); base_start[n_seqs] likewise.
+// one CTA: tile_off[t] = sum of tile_count[0..t) (here: over the chunk totals of the two-level scan below);
+// base_start[s] = grand total for every trailing sequence that starts at `total` (they own no tile);
+// base_start[n_seqs] likewise.  The counts are walked in chunks of 1024 consecutive entries (coalesced
+// loads and stores), each chunk scanned with warp shuffles + one shared-memory pass over the 32 warp
+// totals, the running total carried along.
 __global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(const uint32_t *__restrict__ tile_count,
                                                                  uint64_t n_tiles, uint64_t *__restrict__ tile_off,
                                                                  const uint64_t *__restrict__ char_start,
                                                                  uint32_t n_seqs, uint64_t total,
                                                                  uint64_t *__restrict__ base_start) {
-    __shared__ unsigned long long part[SCAN_THREADS];
-    const uint64_t per = (n_tiles + SCAN_THREADS - 1) / SCAN_THREADS;
-    const uint64_t b = (uint64_t)threadIdx.x * per;
-    const uint64_t e = b + per < n_tiles ? b + per : n_tiles;
-    unsigned long long s = 0;
-    for (uint64_t i = b; i < e; ++i) s += tile_count[i];
-    part[threadIdx.x] = s;
+    __shared__ unsigned long long wtot[SCAN_THREADS / 32];
+    __shared__ unsigned long long carry;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (int o = 1; o < SCAN_THREADS; o <<= 1) {
-        unsigned long long v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    for (uint64_t c0 = 0; c0 < n_tiles; c0 += SCAN_THREADS) {
+        const uint64_t i = c0 + threadIdx.x;
+        const unsigned long long v = i < n_tiles ? tile_count[i] : 0u;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += u;
+        }
+        if (lane == 31) wtot[warp] = inc;
         __syncthreads();
-        part[threadIdx.x] += v;
+        unsigned long long woff = 0, chunk_total = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+            const unsigned long long t = wtot[w];
+            if (w < (int)warp) woff += t;
+            chunk_total += t;
+        }
+        const unsigned long long base = carry;
+        if (i < n_tiles) tile_off[i] = base + woff + inc - v;
+        __syncthreads();                                           // everyone has read wtot and carry
+        if (threadIdx.x == 0) carry = base + chunk_total;
         __syncthreads();
-    }
-    unsigned long long run = threadIdx.x ? part[threadIdx.x - 1] : 0;
-    for (uint64_t i = b; i < e; ++i) {
-        tile_off[i] = run;
-        run += tile_count[i];
     }
     if (threadIdx.x == 0) {
-        const unsigned long long grand = part[SCAN_THREADS - 1];
+        const unsigned long long grand = carry;
         tile_off[n_tiles] = grand;
         base_start[n_seqs] = grand;
         for (int64_t q = (int64_t)n_seqs - 1; q >= 0 && char_start[q] >= total; --q) base_start[q] = grand;
     }
+}
+
+// two-level scan of the tile counts: chunk totals (one CTA per 1024 tiles), pack_scan_kernel over the chunk
+// totals, then every chunk scans its own 1024 tiles on top of its chunk offset -- three short launches
+// instead of one CTA walking all the tiles.
+__global__ void __launch_bounds__(SCAN_THREADS) chunk_sum_kernel(const uint32_t *__restrict__ tile_count,
+                                                                 uint64_t n_tiles, uint32_t *__restrict__ chunk_tot) {
+    __shared__ uint32_t wtot[SCAN_THREADS / 32];
+    const uint64_t i = (uint64_t)blockIdx.x * SCAN_THREADS + threadIdx.x;
+    uint32_t v = warp_sum(i < n_tiles ? tile_count[i] : 0u);
+    if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = warp_sum(wtot[threadIdx.x]);
+        if (threadIdx.x == 0) chunk_tot[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) tile_off_kernel(const uint32_t *__restrict__ tile_count,
+                                                                uint64_t n_tiles,
+                                                                const uint64_t *__restrict__ chunk_off,
+                                                                uint64_t *__restrict__ tile_off) {
+    __shared__ uint32_t wtot[SCAN_THREADS / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t i = (uint64_t)blockIdx.x * SCAN_THREADS + threadIdx.x;
+    const uint32_t v = i < n_tiles ? tile_count[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += u;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w)
+        if (w < (int)warp) woff += wtot[w];
+    if (i < n_tiles) tile_off[i] = chunk_off[blockIdx.x] + woff + inc - v;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) tile_off[n_tiles] = chunk_off[gridDim.x];
 }
 
 __global__ void __launch_bounds__(PACK_THREADS) pack_scatter_kernel(const uint2 *__restrict__ masks, uint64_t total,
@@ -274,7 +326,9 @@ size_t kam_pack_workspace_bytes(uint64_t total_chars, uint32_t n_seqs) {
     (void)n_seqs;
     const uint64_t nt = n_tiles_of(total_chars);
     return kam_align_up((nt + 1) * sizeof(uint32_t), 256) + kam_align_up((nt + 1) * sizeof(uint64_t), 256) +
-           kam_align_up(nt * PACK_THREADS * sizeof(uint2), 256) + kam_align_up((nt + 1) * sizeof(uint32_t), 256);
+           kam_align_up(nt * PACK_THREADS * sizeof(uint2), 256) + kam_align_up((nt + 1) * sizeof(uint32_t), 256) +
+           kam_align_up((nt / SCAN_THREADS + 2) * sizeof(uint32_t), 256) +
+           kam_align_up((nt / SCAN_THREADS + 2) * sizeof(uint64_t), 256);
 }
 
 int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_t n_seqs, uint64_t total_chars,
@@ -294,11 +348,16 @@ int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_
     uint64_t *tile_off = (uint64_t *)((char *)d_ws + kam_align_up((nt + 1) * sizeof(uint32_t), 256));
     uint2 *masks = (uint2 *)((char *)tile_off + kam_align_up((nt + 1) * sizeof(uint64_t), 256));
     uint32_t *tile_first = (uint32_t *)((char *)masks + kam_align_up(nt * PACK_THREADS * sizeof(uint2), 256));
+    uint32_t *chunk_tot = (uint32_t *)((char *)tile_first + kam_align_up((nt + 1) * sizeof(uint32_t), 256));
+    uint64_t *chunk_off = (uint64_t *)((char *)chunk_tot + kam_align_up((nt / SCAN_THREADS + 2) * sizeof(uint32_t), 256));
+    const uint64_t n_chunks = (nt + SCAN_THREADS - 1) / SCAN_THREADS;
 
     KAM_CUDA(cudaMemsetAsync(d_planes, 0, kam_planes_words(total_chars) * sizeof(uint64_t), st));
     if (nt) pack_count_kernel<<<(unsigned)nt, PACK_THREADS, 0, st>>>(d_chars, total_chars, tile_count, masks);
-    pack_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_count, nt, tile_off, d_char_start, n_seqs, total_chars,
+    if (n_chunks) chunk_sum_kernel<<<(unsigned)n_chunks, SCAN_THREADS, 0, st>>>(tile_count, nt, chunk_tot);
+    pack_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(chunk_tot, n_chunks, chunk_off, d_char_start, n_seqs, total_chars,
                                                  d_base_start);
+    if (n_chunks) tile_off_kernel<<<(unsigned)n_chunks, SCAN_THREADS, 0, st>>>(tile_count, nt, chunk_off, tile_off);
     if (nt && n_seqs)
         tile_first_seq_kernel<<<(n_seqs + 255) / 256, 256, 0, st>>>(d_char_start, n_seqs, nt, tile_first);
     if (nt)
