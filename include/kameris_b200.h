@@ -247,6 +247,9 @@ int kam_mds_center(const void *d_tri, int elem, uint32_t n, double *d_B, void *d
 size_t kam_symm_workspace_bytes(uint32_t n);
 int kam_symm_block(const double *d_B, uint32_t n, const double *d_Q, double *d_Y, void *d_ws, size_t ws_bytes,
                    void *stream);
+/* test hook: 0 = always the register-pipelined product kernel; default 1 = TMA-fed shared-memory tiles
+ * whenever n is even (16-byte-aligned rows); identical results up to the summation order. */
+void kam_symm_set_tma(int on);
 
 #ifdef __cplusplus
 }

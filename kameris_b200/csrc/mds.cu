@@ -13,6 +13,7 @@
 //                    the 16 rows of a CTA; each warp owns two rows of B, lanes stride the columns, 8
 //                    independent 256-byte row loads are in flight per warp.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -198,6 +199,120 @@ __global__ void __launch_bounds__(SY_WARPS * 32, 1) symm_block_kernel(const doub
     }
 }
 
+
+// ---- the same product with TMA-fed shared-memory tiles ---------------------------------------------------
+// symm_block_kernel keeps its operands in flight in REGISTERS (16 row loads per lane), and its 64
+// replicated accumulators per lane leave room for no more: ~32 KB in flight per SM, a third of what
+// HBM latency x bandwidth asks for.  Here one elected thread streams B tiles (32 rows x 128 columns,
+// 32 KB) and the matching Q slab (128 x 16, 16 KB, SWIZZLE_128B so that the eight 16-byte chunks a
+// quarter-warp reads from eight consecutive rows fall into distinct banks) through a 4-stage
+// cp.async.bulk.tensor + mbarrier ring: 128 KB of B in flight per SM, independent of the register
+// file; out-of-range rows / columns are zero-filled by the TMA unit, so the body has no bounds checks.
+// The eight consumer warps keep the lanes-stride-columns mapping (conflict-free, coalesced reads of B).
+constexpr int TY_STAGES = 4;
+constexpr int TY_ROWS = SY_WARPS * SY_ROWS;                                  // 32 rows of B per CTA
+constexpr uint32_t TY_B_BYTES = TY_ROWS * SY_SLAB * 8, TY_Q_BYTES = SY_SLAB * SB * 8;
+constexpr uint32_t TY_STAGE_BYTES = TY_B_BYTES + TY_Q_BYTES;                 // 48 KB
+
+__global__ void __launch_bounds__(SY_WARPS * 32 + 32, 1) symm_tma_kernel(const __grid_constant__ CUtensorMap tmB,
+                                                                         const __grid_constant__ CUtensorMap tmQ,
+                                                                         uint32_t n, double *__restrict__ Ypart,
+                                                                         uint32_t cols_per_split) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full[TY_STAGES], empty[TY_STAGES];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t jbeg = blockIdx.y * cols_per_split;
+    const uint32_t jend = jbeg + cols_per_split < n ? jbeg + cols_per_split : n;
+    const uint32_t n_slabs = jbeg < jend ? (jend - jbeg + SY_SLAB - 1) / SY_SLAB : 0;
+    const uint32_t row_base = blockIdx.x * TY_ROWS;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmQ);
+        for (int s = 0; s < TY_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], SY_WARPS);   // one arrive per consumer warp
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == SY_WARPS) {
+        // ===== producer: one thread =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t sl = 0; sl < n_slabs; ++sl) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                mbar_arrive_expect_tx(&full[stage], TY_STAGE_BYTES);
+                unsigned char *sb = smem + stage * TY_STAGE_BYTES;
+                const int32_t j0 = (int32_t)(jbeg + sl * SY_SLAB);
+                tma_load_2d(sb, &tmB, j0, (int32_t)row_base, &full[stage]);          // [32 rows][128 cols]
+                tma_load_2d(sb + TY_B_BYTES, &tmQ, 0, j0, &full[stage]);             // [128 rows][16 cols], swizzled
+                if (++stage == TY_STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: warp w owns rows row_base + 4w .. +3, lanes stride the columns =====
+    double acc[SY_ROWS][SB];
+#pragma unroll
+    for (int r = 0; r < SY_ROWS; ++r)
+#pragma unroll
+        for (int c = 0; c < SB; ++c) acc[r][c] = 0.0;
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t sl = 0; sl < n_slabs; ++sl) {
+        mbar_wait(&full[stage], phase);
+        const unsigned char *sb = smem + stage * TY_STAGE_BYTES;
+        const double *bs = reinterpret_cast<const double *>(sb) + (warp * SY_ROWS) * SY_SLAB;
+        // columns of this slab beyond jend belong to the next split (the TMA box does not stop there)
+        const uint32_t valid = jend - (jbeg + sl * SY_SLAB);
+#pragma unroll
+        for (int q = 0; q < SY_SLAB / 32; ++q) {
+            const uint32_t jj = q * 32 + lane;
+            double bv[SY_ROWS];
+#pragma unroll
+            for (int r = 0; r < SY_ROWS; ++r) bv[r] = jj < valid ? bs[r * SY_SLAB + jj] : 0.0;
+            const unsigned char *qrow = sb + TY_B_BYTES + jj * 128u;
+#pragma unroll
+            for (int c2 = 0; c2 < SB / 2; ++c2) {
+                const double2 qv = *reinterpret_cast<const double2 *>(qrow + ((uint32_t)(c2 ^ (jj & 7u)) << 4));
+#pragma unroll
+                for (int r = 0; r < SY_ROWS; ++r) {
+                    acc[r][2 * c2] = fma(bv[r], qv.x, acc[r][2 * c2]);
+                    acc[r][2 * c2 + 1] = fma(bv[r], qv.y, acc[r][2 * c2 + 1]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == TY_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+    const uint32_t row0 = row_base + warp * SY_ROWS;
+    double *Yp = Ypart + (uint64_t)blockIdx.y * n * SB;
+#pragma unroll
+    for (int r = 0; r < SY_ROWS; ++r) {
+        double mine = 0.0;
+#pragma unroll
+        for (int c = 0; c < SB; ++c) {
+            double v = acc[r][c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((int)lane == c) mine = v;
+        }
+        if (lane < SB && row0 + r < n) Yp[(uint64_t)(row0 + r) * SB + lane] = mine;
+    }
+}
+
+bool g_symm_tma = true;   // test hook: false = register-pipelined kernel for every n
+
 // Y = sum over the column splits (fixed order: deterministic)
 __global__ void __launch_bounds__(256) symm_reduce_kernel(const double *__restrict__ Ypart, uint32_t n, uint32_t splits,
                                                           double *__restrict__ Y) {
@@ -272,10 +387,28 @@ int kam_symm_block(const double *d_B, uint32_t n, const double *d_Q, double *d_Y
     const uint32_t cps = ((n + splits - 1) / splits + SY_SLAB - 1) / SY_SLAB * SY_SLAB;   // whole slabs per split
     const unsigned rb = (n + SY_WARPS * SY_ROWS - 1) / (SY_WARPS * SY_ROWS);
     double *part = splits == 1 ? d_Y : (double *)d_ws;
-    symm_block_kernel<<<dim3(rb, splits), SY_WARPS * 32, 0, st>>>(d_B, n, d_Q, part, cps);
+    // TMA needs 16-byte-aligned rows (n even) and bases; everything else takes the register-pipelined kernel
+    const bool tma_ok = g_symm_tma && n % 2 == 0 && n >= 64 && ((uintptr_t)d_B & 15) == 0 && ((uintptr_t)d_Q & 15) == 0;
+    if (tma_ok) {
+        CUtensorMap tmB, tmQ;
+        int rc;
+        if ((rc = kam_make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, d_B, n, n, (uint64_t)n * 8, SY_SLAB, TY_ROWS,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE)) ||
+            (rc = kam_make_tmap_2d(&tmQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, d_Q, SB, n, (uint64_t)SB * 8, SB, SY_SLAB,
+                                   CU_TENSOR_MAP_SWIZZLE_128B)))
+            return rc;
+        const size_t smem = (size_t)TY_STAGES * TY_STAGE_BYTES + 1024;
+        KAM_CUDA(cudaFuncSetAttribute(symm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        symm_tma_kernel<<<dim3(rb, splits), SY_WARPS * 32 + 32, smem, st>>>(tmB, tmQ, n, part, cps);
+    } else {
+        symm_block_kernel<<<dim3(rb, splits), SY_WARPS * 32, 0, st>>>(d_B, n, d_Q, part, cps);
+    }
     if (splits > 1) symm_reduce_kernel<<<(unsigned)(((uint64_t)n * SB + 255) / 256), 256, 0, st>>>(part, n, splits, d_Y);
     KAM_CUDA(cudaGetLastError());
     return KAM_OK;
 }
+
+/* test hook: 0 = always the register-pipelined product kernel (default 1: TMA-fed tiles when n is even) */
+void kam_symm_set_tma(int on) { g_symm_tma = on != 0; }
 
 }  // extern "C"

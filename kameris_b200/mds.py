@@ -73,11 +73,34 @@ def top_eigenpairs(B, dim, tol=1e-12, max_iter=5000, seed=0, stats=None, check_e
     Q[:, :b] = torch.linalg.qr(torch.randn((n, b), dtype=torch.float64, device=dev, generator=g))[0]
     Y = torch.empty_like(Q)
     ws = symm_workspace(n, dev)
+    # orthonormalisation of B Q: Cholesky QR twice (three small launches each, no host round trip); a
+    # rank-deficient block (B of rank < 16: exactly embeddable inputs) makes the factorisation fail, which
+    # is noticed at the next convergence check and answered by Householder QR from the last good block
+    householder = False
+    bad = torch.zeros((), dtype=torch.int32, device=dev)
+    Q_good = Q.clone()
+
+    def orth(Yb):
+        nonlocal bad
+        if householder:
+            return torch.linalg.qr(Yb)[0]
+        Z = Yb
+        for _ in range(2):
+            L, info = torch.linalg.cholesky_ex(Z.T @ Z)
+            bad = bad | (info != 0).to(torch.int32)
+            Z = torch.linalg.solve_triangular(L, Z.T, upper=False).T
+        return Z
+
     it = 0
     while True:
         symm_block(B, Q, out=Y, workspace=ws)
         it += 1
         if b == n or it % check_every == 0 or it >= max_iter:
+            if not householder and (int(bad) != 0 or not bool(torch.isfinite(Y).all())):
+                householder = True                         # redo the last sweeps from the last good block
+                Q.copy_(Q_good)
+                bad.zero_()
+                symm_block(B, Q, out=Y, workspace=ws)
             T = Q[:, :b].T @ Y[:, :b]
             theta, S = torch.linalg.eigh((T + T.T) * 0.5)
             order = torch.argsort(theta.abs(), descending=True)[:dim]
@@ -87,9 +110,11 @@ def top_eigenpairs(B, dim, tol=1e-12, max_iter=5000, seed=0, stats=None, check_e
             scale = theta.abs().max().clamp_min(1e-300)
             if bool((res <= tol * scale).all()) or b == n or it >= max_iter:
                 break
-        Q[:, :b] = torch.linalg.qr(Y[:, :b])[0]
+            Q_good.copy_(Q)
+        Q[:, :b] = orth(Y[:, :b])
     if stats is not None:
-        stats.update({"iterations": it, "residual": float((res / scale).max()), "block": b})
+        stats.update({"iterations": it, "residual": float((res / scale).max()), "block": b,
+                      "orthonormalisation": "householder" if householder else "cholesky-qr2"})
     w = theta[order]
     desc = torch.argsort(w, descending=True)
     return w[desc], X[:, desc]

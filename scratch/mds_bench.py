@@ -21,9 +21,13 @@ def ev(fn, reps=3):
 t_c, B = ev(lambda: M.center(tri, n))
 Q = torch.randn((n, 16), dtype=torch.float64, device=dev, generator=g)
 t_s, _ = ev(lambda: M.symm_block(B, Q), 10)
+from kameris_b200 import _lib
+_lib.load().kam_symm_set_tma(0)
+t_s_reg, _ = ev(lambda: M.symm_block(B, Q), 10)
+_lib.load().kam_symm_set_tma(1)
 t_mm, _ = ev(lambda: B @ Q, 10)
 stats = {}
 t0 = time.perf_counter(); w, X = M.top_eigenpairs(B, dim, stats=stats); torch.cuda.synchronize(); t_e = time.perf_counter() - t0
 print(json.dumps({"n": n, "center_ms": t_c, "center_GBps": (n * n * 8 * 4 + tri.numel() * 4) / t_c / 1e6,
-                  "symm_block_ms": t_s, "symm_GBps": n * n * 8 / t_s / 1e6, "torch_matmul_ms": t_mm,
+                  "symm_block_ms": t_s, "symm_regs_kernel_ms": t_s_reg, "symm_GBps": n * n * 8 / t_s / 1e6, "torch_matmul_ms": t_mm,
                   "eig_s": t_e, **stats, "w": [float(x) for x in w[:4]]}))

@@ -70,16 +70,25 @@ def test_center_kernel_vs_numpy(M):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [1, 5, 16, 33, 257, 1000])
+@pytest.mark.parametrize("n", [1, 5, 16, 33, 64, 66, 257, 1000, 2050, 4098])
 def test_symm_block_vs_fp64_matmul(M, n):
+    """both product kernels (TMA-fed tiles for even n >= 64, register-pipelined otherwise / on request)
+    against a float64 matmul; same summation order, so the two kernels agree bit for bit."""
+    from kameris_b200 import _lib
     g = torch.Generator(device="cuda")
     g.manual_seed(n)
     A = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g)
     B = (A + A.T).contiguous()
     Q = torch.randn((n, M.BLOCK), dtype=torch.float64, device="cuda", generator=g)
-    Y = M.symm_block(B, Q)
     ref = B @ Q
+    Y = M.symm_block(B, Q)
     assert float((Y - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+    _lib.load().kam_symm_set_tma(0)
+    try:
+        Y2 = M.symm_block(B, Q)
+    finally:
+        _lib.load().kam_symm_set_tma(1)
+    assert torch.equal(Y, Y2)
 
 
 @pytest.mark.gpu
