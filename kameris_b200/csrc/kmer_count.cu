@@ -18,11 +18,21 @@
 // the output type, fusing the frequency division.  The output (4^k * sizeof(out) per sequence,
 // >96% zeros for 9 kb genomes at k=9) is written exactly once and never read: HBM-write-bound.
 // A uint8 counter that would pass 255, or a sequence too long for this path, puts the sequence
-// on the spill list.
+// on the overflow list.
 //
-// Path B (spill): uint32 tables in global memory (L2-resident: a few sequences at a time),
-// RED.ADD increments from many CTAs per sequence, then a finalize pass (wrap to 16 bits,
-// normalise).  This is the "global-atomic spill" for long sequences (5 Mb genomes at k=9).
+// Path A for short reads at k <= 6 (cgr_warp_kernel): one WARP per read, private uint8 table.
+//
+// Path L (cgr_long_kernel): the overflow list of path A -- megabase sequences, uint8 overflows --
+// counted in shared-memory tiles of 65536 packed uint16 counters, one CTA per (sequence, tile);
+// shared-memory atomics are ~18x faster than global RED.ADD on B200, so scanning a sequence once
+// per tile is the cheaper trade.
+//
+// Path B (cgr_spill_*): whatever overflows even uint16 counters (and k >= 12): uint32 tables in
+// global memory (L2-resident: a few sequences at a time), RED.ADD increments from many CTAs per
+// sequence, then a finalize pass (wrap to 16 bits, normalise).
+//
+// Sweep (cgr_sweep_kernel): every order k_lo..k_hi of a batch; orders <= 7 from one scan at k=7 and
+// 2x2 pooling of the shared-memory tile.
 #include <type_traits>
 
 #include "common.cuh"
