@@ -47,6 +47,49 @@ def test_pack_layout(R):
         pos += len(valid)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_pack_random_layouts(R, seed):
+    """pack kernels against a numpy restatement of the planes layout: random record lengths including
+    empty records (leading, trailing, consecutive), records that start exactly on 4096-character tile
+    boundaries, records spanning many tiles, dirty characters, totals that are not multiples of 16."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    alpha = np.frombuffer(b"ACGTNacgtRY-", dtype=np.uint8)
+    p = np.array([0.24, 0.24, 0.24, 0.24] + [0.005] * 8)
+    p /= p.sum()
+    lens = []
+    for _ in range(int(rng.integers(1, 200))):
+        kind = rng.integers(0, 6)
+        lens.append(int({0: 0, 1: rng.integers(1, 40), 2: rng.integers(100, 300), 3: 4096 * rng.integers(1, 4),
+                         4: rng.integers(5000, 30000), 5: 4096 - 7}[int(kind)]))
+    if seed == 1:
+        lens = [0, 0, 4096, 0, 8192, 1, 0] + lens + [0, 0]
+    if seed == 2:
+        lens = lens + [4096 * 3 - sum(lens) % 4096]             # total a multiple of the tile size
+    recs = [alpha[rng.choice(len(alpha), size=n, p=p)].tobytes() for n in lens]
+    b = R.pack_records(recs)
+    base = b.base_start.cpu().numpy()
+    planes = b.planes.cpu().numpy().view(np.uint64)
+    head = b.head_mask.cpu().numpy().view(np.uint32)
+    allc = np.frombuffer(b"".join(recs), dtype=np.uint8)
+    valid = np.isin(allc, np.frombuffer(b"ACGT", dtype=np.uint8))
+    starts = np.concatenate([[0], np.cumsum(lens)])
+    cum = np.concatenate([[0], np.cumsum(valid)])
+    assert np.array_equal(base, cum[starts])
+    vb = allc[valid]
+    xbits = np.isin(vb, np.frombuffer(b"GT", dtype=np.uint8)).astype(np.uint64)
+    ybits = np.isin(vb, np.frombuffer(b"AT", dtype=np.uint8)).astype(np.uint64)
+    nw = (len(vb) + 31) // 32
+    pad = nw * 32 - len(vb)
+    xw = np.concatenate([xbits, np.zeros(pad, np.uint64)]).reshape(nw, 32)
+    yw = np.concatenate([ybits, np.zeros(pad, np.uint64)]).reshape(nw, 32)
+    sh = np.arange(32, dtype=np.uint64)
+    want = (xw << sh).sum(axis=1) | ((yw << sh).sum(axis=1) << np.uint64(32))
+    assert np.array_equal(planes[:nw], want)
+    for s_i, rec in enumerate(recs):
+        hm = sum(1 << i for i, c in enumerate(rec[:32]) if c in b"ACGT")
+        assert head[s_i] == hm, s_i
+
+
 def test_golden_reference_machine_code(R, refcode_cases):
     """Every golden case (quirks Q1/Q3/Q4, demo genomes, random dirty records), k <= 10."""
     ks = sorted({int(k) for c in refcode_cases for k in c["k"] if int(k) <= 10})
