@@ -20,6 +20,7 @@ One step = one pass of the `kmers` hot path over the whole batch.
           all-threads float32 C variant is reported beside it as `threaded_c_f32`.
   distances : secondary lines -- pairs/s of the distance kernels on vectors of the same shape
   kmers_other_shapes : secondary lines -- the short-read (configs[3]) and megabase (configs[4]) shapes
+  mds : secondary line -- the mds step at n = 10 000 with the reference's numpy/ARPACK mds() beside it
 
 With --gpus N (torchrun, one rank per GPU) every rank processes its own 10 000-sequence shard
 (sequences are independent: no data-path collective, weak scaling); value = all ranks' vectors /
@@ -349,6 +350,15 @@ def main():
             d = distance_lines(torch, dev, hbm_peak, tf_peak)
             if d is not None:
                 line["distances"] = d
+        if world == 1 and not args.no_extra:
+            try:                                   # the first consumer of the matrices
+                from kameris_b200 import mds_bench
+                torch.cuda.empty_cache()
+                line["mds"], tri_sample = mds_bench.run(dev, hbm_peak)
+                if not args.no_cpu_baseline:
+                    line["mds"]["cpu_baseline"] = mds_bench.cpu_baseline(tri_sample, 10000, 10)
+            except Exception as e:
+                line["mds"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
     if world > 1:
         dist_pg.destroy_process_group()

@@ -284,3 +284,25 @@ def same_up_to_column_signs(a: np.ndarray, b: np.ndarray, rtol: float) -> bool:
         if not err <= rtol * scale:
             return False
     return True
+
+
+def mds_reference_arpack(delta: np.ndarray, dim: int) -> np.ndarray:
+    """The reference's own algorithm for timing (bench.py's cpu_baseline of the mds line): the
+    statements of kameris/job_steps/mds.py:10-35 with scipy's ARPACK eigsh, as the reference runs them."""
+    import scipy.sparse.linalg as linalg
+    delta = delta.astype(float)
+    n = delta.shape[0]
+    deltasq = delta ** 2
+    deltatotals = np.sum(deltasq, axis=0) / n
+    total = np.sum(deltatotals) / n
+    b = deltasq
+    b -= deltatotals
+    b = b.transpose()
+    b -= deltatotals
+    b = b.transpose()
+    b += total
+    b *= -0.5
+    vals, vecs = linalg.eigsh(b, k=dim)
+    with np.errstate(invalid="ignore"):
+        pts = np.fliplr(np.dot(vecs, np.diag(np.sqrt(vals))))
+    return pts[:, ~np.isnan(pts).any(axis=0)]
