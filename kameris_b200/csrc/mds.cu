@@ -258,31 +258,36 @@ __global__ void __launch_bounds__(SY_WARPS * 32 + 32, 1) symm_tma_kernel(const _
         return;
     }
 
-    // ===== consumers: warp w owns rows row_base + 4w .. +3, lanes stride the columns =====
-    double acc[SY_ROWS][SB];
+    // ===== consumers: warp = (row group g of 8 rows, column half h of 8 columns); lanes stride the
+    // columns j.  A lane needs R values of B and C values of Q per column for R x C FMAs, i.e.
+    // shared-memory wavefronts per FMA ~ 1/(16R) + 1/(16C): the square 8 x 8 block needs 20 % fewer than 4 x 16.
+    constexpr int TR = 8, TC = 8;
+    const uint32_t g = warp >> 1, h = warp & 1u;
+    double acc[TR][TC];
 #pragma unroll
-    for (int r = 0; r < SY_ROWS; ++r)
+    for (int r = 0; r < TR; ++r)
 #pragma unroll
-        for (int c = 0; c < SB; ++c) acc[r][c] = 0.0;
+        for (int c = 0; c < TC; ++c) acc[r][c] = 0.0;
     uint32_t stage = 0, phase = 0;
     for (uint32_t sl = 0; sl < n_slabs; ++sl) {
         mbar_wait(&full[stage], phase);
         const unsigned char *sb = smem + stage * TY_STAGE_BYTES;
-        const double *bs = reinterpret_cast<const double *>(sb) + (warp * SY_ROWS) * SY_SLAB;
+        const double *bs = reinterpret_cast<const double *>(sb) + (g * TR) * SY_SLAB;
         // columns of this slab beyond jend belong to the next split (the TMA box does not stop there)
         const uint32_t valid = jend - (jbeg + sl * SY_SLAB);
 #pragma unroll
         for (int q = 0; q < SY_SLAB / 32; ++q) {
             const uint32_t jj = q * 32 + lane;
-            double bv[SY_ROWS];
+            double bv[TR];
 #pragma unroll
-            for (int r = 0; r < SY_ROWS; ++r) bv[r] = jj < valid ? bs[r * SY_SLAB + jj] : 0.0;
+            for (int r = 0; r < TR; ++r) bv[r] = jj < valid ? bs[r * SY_SLAB + jj] : 0.0;
             const unsigned char *qrow = sb + TY_B_BYTES + jj * 128u;
 #pragma unroll
-            for (int c2 = 0; c2 < SB / 2; ++c2) {
-                const double2 qv = *reinterpret_cast<const double2 *>(qrow + ((uint32_t)(c2 ^ (jj & 7u)) << 4));
+            for (int c2 = 0; c2 < TC / 2; ++c2) {
+                const uint32_t chunk = h * (TC / 2) + c2;
+                const double2 qv = *reinterpret_cast<const double2 *>(qrow + ((chunk ^ (jj & 7u)) << 4));
 #pragma unroll
-                for (int r = 0; r < SY_ROWS; ++r) {
+                for (int r = 0; r < TR; ++r) {
                     acc[r][2 * c2] = fma(bv[r], qv.x, acc[r][2 * c2]);
                     acc[r][2 * c2 + 1] = fma(bv[r], qv.y, acc[r][2 * c2 + 1]);
                 }
@@ -295,19 +300,19 @@ __global__ void __launch_bounds__(SY_WARPS * 32 + 32, 1) symm_tma_kernel(const _
             phase ^= 1u;
         }
     }
-    const uint32_t row0 = row_base + warp * SY_ROWS;
+    const uint32_t row0 = row_base + g * TR;
     double *Yp = Ypart + (uint64_t)blockIdx.y * n * SB;
 #pragma unroll
-    for (int r = 0; r < SY_ROWS; ++r) {
+    for (int r = 0; r < TR; ++r) {
         double mine = 0.0;
 #pragma unroll
-        for (int c = 0; c < SB; ++c) {
+        for (int c = 0; c < TC; ++c) {
             double v = acc[r][c];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if ((int)lane == c) mine = v;
         }
-        if (lane < SB && row0 + r < n) Yp[(uint64_t)(row0 + r) * SB + lane] = mine;
+        if (lane < TC && row0 + r < n) Yp[(uint64_t)(row0 + r) * SB + h * TC + lane] = mine;
     }
 }
 
