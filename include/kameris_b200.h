@@ -95,6 +95,10 @@ int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_
                    uint64_t total_chars, uint64_t *d_planes, uint64_t *d_base_start,
                    uint32_t *d_head_mask, void *d_ws, size_t ws_bytes, void *stream);
 
+/* test hook: 0 = three-launch packer (count / scan / scatter); default 1 = single pass (classification,
+ * chained scan with decoupled look-back, compaction in one kernel); identical outputs. */
+void kam_pack_set_fused(int on);
+
 size_t kam_kmer_workspace_bytes(uint32_t n_seqs, int k);
 
 /* planes -> n_seqs vectors of 4^k bins (row s at d_out + s*out_stride elements).

@@ -25,6 +25,7 @@ SIGNATURES = {
     "kam_pack_workspace_bytes": (c_size_t, [c_uint64, c_uint32]),
     "kam_pack_ascii": (c_int, [c_void_p, c_void_p, c_uint32, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_size_t, c_void_p]),
+    "kam_pack_set_fused": (None, [c_int]),
     "kam_kmer_workspace_bytes": (c_size_t, [c_uint32, c_int]),
     "kam_kmer_count": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_uint64, c_int, c_int, c_int, c_void_p,
                                c_uint64, c_void_p, c_size_t, c_void_p]),

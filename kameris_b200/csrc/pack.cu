@@ -283,6 +283,175 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_scatter_kernel(const uint2 
     }
 }
 
+
+// ---- single pass: classify, chained scan with decoupled look-back, compaction --------------------------
+// The three-launch version above writes 8 bytes of masks per 16 characters and reads them back; here a
+// tile is classified once and scattered by the same CTA: 1 byte read + 1/4 byte written per character.
+// Chunks of 8 tiles (32 768 characters) are handed out by an atomic ticket (so every lower-numbered chunk
+// is already running).  A CTA classifies its chunk (8 independent 16-byte loads per thread, masks kept
+// in 16 KB of shared memory), publishes the chunk's base count, then warp 0 walks back over the published
+// words -- 32 predecessors per step -- summing `aggregate` entries until it meets an `inclusive prefix`
+// entry, and publishes its own inclusive prefix.  The chunk's tiles are then compacted one after the
+// other: x/y bit streams built in shared memory at bit offset 0, funnel-shifted to the tile's flat
+// position on the way out.  state word: bits 63..62 = 0 empty / 1 aggregate / 2 inclusive prefix,
+// bits 61..0 = bases.
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_PREFIX = 2ull << 62, ST_VAL = (1ull << 62) - 1ull;
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+constexpr int PF_SUB = 8;                               // tiles per CTA ("chunk": 32 768 characters)
+
+__global__ void __launch_bounds__(PACK_THREADS) pack_fused_kernel(const uint8_t *__restrict__ chars, uint64_t total,
+                                                                  uint64_t n_tiles, const uint64_t *__restrict__ char_start,
+                                                                  uint32_t n_seqs, uint2 *__restrict__ planes,
+                                                                  uint64_t *__restrict__ base_start,
+                                                                  const uint32_t *__restrict__ tile_first_seq,
+                                                                  unsigned long long *__restrict__ state,
+                                                                  unsigned int *__restrict__ ticket) {
+    constexpr int NW = PACK_THREADS / 32;
+    constexpr int SW = PACK_TILE / 32 + 1;   // words of a tile's compacted bases, plus a zero word behind them
+    __shared__ uint2 smask[PF_SUB][PACK_THREADS];          // the classification of the whole chunk (16 KB)
+    __shared__ uint32_t sx[SW], sy[SW];
+    __shared__ uint32_t wcnt[NW][PF_SUB];                  // bases per warp segment (512 characters) and tile
+    __shared__ uint32_t sub_cnt[PF_SUB];
+    __shared__ uint32_t pref[PACK_THREADS];
+    __shared__ uint32_t s_chunk;
+    __shared__ unsigned long long s_goff;
+
+    if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint64_t chunk = s_chunk;
+    const uint64_t n_chunks = (n_tiles + PF_SUB - 1) / PF_SUB;
+    const uint64_t tile0 = chunk * PF_SUB;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- phase A: classify the chunk (8 independent 16-byte loads per thread), count its bases
+#pragma unroll
+    for (int i = 0; i < PF_SUB; ++i) {
+        const uint64_t pos = (tile0 + i) * PACK_TILE + (uint64_t)threadIdx.x * PACK_CPT;
+        const uint2 m = pos < total ? classify16(chars, pos, total) : make_uint2(0, 0);
+        smask[i][threadIdx.x] = m;
+        const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(m.x & 0xffffu));   // REDUX.SUM
+        if (lane == 0) wcnt[warp][i] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // ---- per-tile and chunk counts, publication, decoupled look-back (warp 0)
+        uint32_t t = 0;
+        if (lane < PF_SUB) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) t += wcnt[w][lane];
+            sub_cnt[lane] = t;
+        }
+        const uint32_t chunk_cnt = __reduce_add_sync(0xffffffffu, t);
+        if (threadIdx.x == 0 && chunk > 0) st_state(&state[chunk], ST_AGG | chunk_cnt);
+        unsigned long long before = 0;
+        if (chunk > 0) {
+            int64_t p = (int64_t)chunk - 1;
+            for (uint32_t spin = 0;;) {
+                const int64_t idx = p - (int64_t)threadIdx.x;
+                const unsigned long long v = idx >= 0 ? ld_state(&state[idx]) : ST_PREFIX;
+                const uint32_t flag = (uint32_t)(v >> 62);
+                if (__any_sync(0xffffffffu, flag == 0)) {          // a predecessor has not published yet
+                    if (++spin > (1u << 24)) __trap();
+                    continue;
+                }
+                const uint32_t isp = __ballot_sync(0xffffffffu, flag == 2);
+                const uint32_t upto = isp ? (uint32_t)__ffs((int)isp) - 1u : 31u;   // closest inclusive prefix
+                unsigned long long part = threadIdx.x <= upto ? (v & ST_VAL) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                before += part;
+                if (isp) break;
+                p -= 32;
+            }
+        }
+        if (threadIdx.x == 0) {
+            st_state(&state[chunk], ST_PREFIX | (before + chunk_cnt));
+            s_goff = before;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: compaction of the chunk's tiles from the stored masks
+    uint64_t goff = s_goff;                                  // flat base index of the current tile's first base
+#pragma unroll 1
+    for (int i = 0; i < PF_SUB; ++i) {
+        const uint64_t tile = tile0 + i;
+        if (tile >= n_tiles) break;
+        const uint64_t tile_begin = tile * PACK_TILE;
+        const uint64_t tile_end = tile_begin + PACK_TILE < total ? tile_begin + PACK_TILE : total;
+        const uint32_t tile_cnt = sub_cnt[i];
+        for (int w = threadIdx.x; w < SW; w += PACK_THREADS) {
+            sx[w] = 0;
+            sy[w] = 0;
+        }
+        const Cls r = compact16(smask[i][threadIdx.x]);
+        uint32_t inc = r.cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += v;
+        }
+        uint32_t woff = 0;                                   // bases of the warps before (phase A counted them)
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+            if (w < (int)warp) woff += wcnt[w][i];
+        const uint32_t excl = woff + inc - r.cnt;
+        pref[threadIdx.x] = excl;
+        __syncthreads();                                     // streams cleared
+        if (r.cnt) {                                         // bit streams at offset 0
+            const uint32_t lw = excl >> 5, sh = excl & 31;
+            atomicOr(&sx[lw], r.x << sh);
+            atomicOr(&sy[lw], r.y << sh);
+            if (sh + r.cnt > 32) {
+                atomicOr(&sx[lw + 1], r.x >> (32 - sh));
+                atomicOr(&sy[lw + 1], r.y >> (32 - sh));
+            }
+        }
+        __syncthreads();
+        const uint32_t bit0 = (uint32_t)(goff & 31);
+        const uint64_t word0 = goff >> 5;
+        const uint32_t nwords = (bit0 + tile_cnt + 31) >> 5;   // words touched (0 when the tile has no base)
+        for (uint32_t w = threadIdx.x; w < nwords; w += PACK_THREADS) {
+            // word w of the output = bits [32 w - bit0, 32 w - bit0 + 32) of the offset-0 stream
+            const uint32_t hx = w < (uint32_t)SW ? sx[w] : 0u, hy = w < (uint32_t)SW ? sy[w] : 0u;
+            const uint32_t lx = w ? sx[w - 1] : 0u, ly = w ? sy[w - 1] : 0u;
+            const uint32_t ox = __funnelshift_l(lx, hx, bit0), oy = __funnelshift_l(ly, hy, bit0);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(planes + word0 + w);
+            if (w == 0 || w == nwords - 1) {     // may be shared with a neighbouring tile (planes pre-zeroed)
+                if (ox) atomicOr(dst, ox);
+                if (oy) atomicOr(dst + 1, oy);
+            } else {
+                planes[word0 + w] = make_uint2(ox, oy);
+            }
+        }
+        // sequences that start inside this tile
+        for (uint32_t s = tile_first_seq[tile] + threadIdx.x; s < n_seqs; s += PACK_THREADS) {
+            const uint64_t c0 = char_start[s];
+            if (c0 >= tile_end) break;           // char_start is non-decreasing
+            const uint32_t rel = (uint32_t)(c0 - tile_begin);
+            const uint32_t th = rel / PACK_CPT, o = rel % PACK_CPT;
+            base_start[s] = goff + pref[th] + __popc(smask[i][th].x & 0xffffu & ((1u << o) - 1u));
+        }
+        goff += tile_cnt;
+        __syncthreads();                                     // pref / streams consumed before the next tile
+    }
+    if (chunk == n_chunks - 1 && threadIdx.x == 0) {         // grand total: the end marker and trailing empty sequences
+        base_start[n_seqs] = goff;
+        for (int64_t q = (int64_t)n_seqs - 1; q >= 0 && char_start[q] >= total; --q) base_start[q] = goff;
+    }
+}
+
+int g_pack_fused = 1;   // test hook: 0 = the three-launch count / scan / scatter version
+
 // tile_first_seq[t] = first sequence whose first character lies at or after the start of tile t
 // (lower_bound of char_start): thread s fills the tiles (tile of sequence s-1, tile of sequence s];
 // the thread of the last sequence also fills the tiles behind it with n_seqs.
@@ -353,6 +522,25 @@ int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_
     const uint64_t n_chunks = (nt + SCAN_THREADS - 1) / SCAN_THREADS;
 
     KAM_CUDA(cudaMemsetAsync(d_planes, 0, kam_planes_words(total_chars) * sizeof(uint64_t), st));
+    if (g_pack_fused) {
+        // single pass; `state` (one word per tile) and the ticket live where the masks of the other version do
+        unsigned long long *state = (unsigned long long *)masks;
+        unsigned int *ticket = (unsigned int *)tile_count;
+        if (nt == 0) {
+            KAM_CUDA(cudaMemsetAsync(d_base_start, 0, ((size_t)n_seqs + 1) * 8, st));
+        } else {
+            const uint64_t n_chunks_f = (nt + PF_SUB - 1) / PF_SUB;
+            KAM_CUDA(cudaMemsetAsync(state, 0, n_chunks_f * 8, st));
+            KAM_CUDA(cudaMemsetAsync(ticket, 0, 4, st));
+            if (n_seqs) tile_first_seq_kernel<<<(n_seqs + 255) / 256, 256, 0, st>>>(d_char_start, n_seqs, nt, tile_first);
+            pack_fused_kernel<<<(unsigned)n_chunks_f, PACK_THREADS, 0, st>>>(d_chars, total_chars, nt, d_char_start, n_seqs,
+                                                                     (uint2 *)d_planes, d_base_start, tile_first, state,
+                                                                     ticket);
+        }
+        if (n_seqs) head_mask_kernel<<<(n_seqs + 255) / 256, 256, 0, st>>>(d_chars, d_char_start, n_seqs, d_head_mask);
+        KAM_CUDA(cudaGetLastError());
+        return KAM_OK;
+    }
     if (nt) pack_count_kernel<<<(unsigned)nt, PACK_THREADS, 0, st>>>(d_chars, total_chars, tile_count, masks);
     if (n_chunks) chunk_sum_kernel<<<(unsigned)n_chunks, SCAN_THREADS, 0, st>>>(tile_count, nt, chunk_tot);
     pack_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(chunk_tot, n_chunks, chunk_off, d_char_start, n_seqs, total_chars,
@@ -367,5 +555,8 @@ int kam_pack_ascii(const uint8_t *d_chars, const uint64_t *d_char_start, uint32_
     KAM_CUDA(cudaGetLastError());
     return KAM_OK;
 }
+
+/* test hook: 0 = three-launch pack (count / scan / scatter), default 1 = single pass with decoupled look-back */
+void kam_pack_set_fused(int on) { g_pack_fused = on; }
 
 }  // extern "C"

@@ -47,8 +47,40 @@ def test_pack_layout(R):
         pos += len(valid)
 
 
+@pytest.fixture(params=[1, 0], ids=["single-pass", "three-launch"])
+def pack_mode(request):
+    from kameris_b200 import _lib
+    _lib.load().kam_pack_set_fused(request.param)
+    yield request.param
+    _lib.load().kam_pack_set_fused(1)
+
+
+def test_pack_large_many_tiles(R, pack_mode):
+    """40 MB of characters (10 000 tiles: the chained scan's look-back crosses many waves of CTAs) against
+    numpy: per-sequence base offsets and a checksum of the planes."""
+    rng = np.random.Generator(np.random.PCG64(9))
+    n, L = 4000, 10000
+    alpha = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    allc = alpha[rng.choice(5, size=n * L, p=[0.245, 0.245, 0.245, 0.245, 0.02])]
+    chars = torch.zeros(n * L + 16, dtype=torch.uint8, device="cuda")
+    chars[:n * L] = torch.from_numpy(allc).cuda()
+    start = torch.arange(n + 1, dtype=torch.int64, device="cuda") * L
+    b = R.pack_chars(chars, start, n, n * L)
+    valid = allc != ord("N")
+    cum = np.concatenate([[0], np.cumsum(valid)])
+    assert np.array_equal(b.base_start.cpu().numpy(), cum[np.arange(n + 1) * L])
+    vb = allc[valid]
+    nw = len(vb) // 32
+    xb = np.isin(vb[:nw * 32], np.frombuffer(b"GT", dtype=np.uint8)).reshape(nw, 32)
+    yb = np.isin(vb[:nw * 32], np.frombuffer(b"AT", dtype=np.uint8)).reshape(nw, 32)
+    want = np.packbits(xb, axis=1, bitorder="little").view(np.uint32)[:, 0].astype(np.uint64) | \
+        (np.packbits(yb, axis=1, bitorder="little").view(np.uint32)[:, 0].astype(np.uint64) << np.uint64(32))
+    got = b.planes.cpu().numpy().view(np.uint64)[:nw]
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
-def test_pack_random_layouts(R, seed):
+def test_pack_random_layouts(R, seed, pack_mode):
     """pack kernels against a numpy restatement of the planes layout: random record lengths including
     empty records (leading, trailing, consecutive), records that start exactly on 4096-character tile
     boundaries, records spanning many tiles, dirty characters, totals that are not multiples of 16."""
