@@ -131,6 +131,9 @@ void kam_kmer_set_warp_path(int on);
 /* test hook: 0 sends long sequences (and uint8-counter overflows) straight to the global-memory RED.ADD
  * path instead of the shared-memory uint16 tile kernel (default 1); identical vectors either way. */
 void kam_kmer_set_long_path(int on);
+/* test hook: 0 makes the CTA-per-sequence kernel scan 8 k-mer end positions per thread and trip (the first
+ * version) instead of one whole plane word of 32 (default 1); identical vectors either way. */
+void kam_kmer_set_word_scan(int on);
 
 /* Order-(k+1) count tables -> order-k tables by 2x2 sum-pooling of the CGR image plus the one k-mer
  * that has no (k+1)-mer ending at the same base; exact for dirty heads (quirk Q1) and

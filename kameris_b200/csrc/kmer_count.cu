@@ -107,6 +107,44 @@ __device__ __forceinline__ void bump(uint32_t *tab32, uint32_t lb, uint32_t *s_f
     }
 }
 
+
+// Scan of one sequence for one shared-memory tile, 32 k-mer end positions (one plane word) per thread
+// and trip: the in-tile mask of all 32 positions is formed with whole-word operations (the tile index is
+// the top `tbits` bits of the y window = the y-bits of the newest tbits bases), then one increment per set
+// bit.  Replaces a scan that handled 8 positions per thread and trip (4x the per-position overhead);
+// genome-length sequences only -- a 150 bp read has too few words to occupy a CTA this way.
+template <typename CT, int THREADS>
+__device__ __forceinline__ void scan_tile_words(const uint2 *__restrict__ planes, uint64_t pf, uint64_t pe, int k,
+                                                uint32_t t, uint32_t tbits, uint32_t ylow, uint32_t *tab32,
+                                                uint32_t *s_flag) {
+    const uint32_t mask = (1u << k) - 1u;
+    const uint32_t shc = 32u - (uint32_t)(k - 1);
+    const uint64_t W0 = pf >> 5, W1 = ((pe - 1) >> 5) + 1;
+    for (uint64_t W = W0 + threadIdx.x; W < W1; W += THREADS) {
+        const uint2 hi = __ldg(planes + W);
+        const uint2 lo = W ? __ldg(planes + W - 1) : make_uint2(0, 0);
+        const unsigned long long vx = ((unsigned long long)hi.x << 32) | lo.x;
+        const unsigned long long vy = ((unsigned long long)hi.y << 32) | lo.y;
+        const uint64_t pbase = W << 5;
+        uint32_t m = 0xffffffffu;
+        if (pbase < pf) m &= 0xffffffffu << (uint32_t)(pf - pbase);
+        if (pbase + 32 > pe) m &= 0xffffffffu >> (uint32_t)(pbase + 32 - pe);
+#pragma unroll 1
+        for (uint32_t i = 0; i < tbits; ++i) {
+            const uint32_t want = 0u - ((t >> (tbits - 1 - i)) & 1u);
+            m &= ~((uint32_t)(vy >> (32u - i)) ^ want);
+        }
+        while (m) {
+            uint32_t b;
+            asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(m));
+            m ^= 1u << b;
+            const uint32_t sh = b + shc;
+            const uint32_t xw = (uint32_t)(vx >> sh) & mask, yw = (uint32_t)(vy >> sh) & ylow;
+            bump<CT>(tab32, (yw << k) | xw, s_flag);
+        }
+    }
+}
+
 // THREADS: 256 for genome-length sequences; 64 for short reads, where a sequence gives a CTA only a
 // few dozen k-mer groups and the per-sequence barriers dominate (more, smaller CTAs per SM hide them).
 template <typename CT, typename OUT, int THREADS>
@@ -117,7 +155,8 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
                                                              uint64_t out_stride, uint32_t *__restrict__ queue,
                                                              uint32_t *__restrict__ spill_count,
                                                              uint32_t *__restrict__ spill_list,
-                                                             unsigned long long *__restrict__ spill_maxlen) {
+                                                             unsigned long long *__restrict__ spill_maxlen,
+                                                             int word_scan) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *tab32 = reinterpret_cast<uint32_t *>(smem_raw);
     __shared__ uint32_t s_seq, s_next, s_end;
@@ -181,6 +220,9 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
         }
 
         for (uint32_t t = 0; t < n_tiles; ++t) {
+            if (THREADS == 256 && has_full && word_scan) {
+                scan_tile_words<CT, THREADS>(planes, pf, pe, k, t, tbits, ylow, tab32, &s_flag);
+            } else
             for (uint64_t g = g0 + threadIdx.x; g < g1; g += THREADS) {
                 const uint64_t W = g >> 2;                  // word holding the group
                 const uint2 hi = __ldg(planes + W);
@@ -328,6 +370,7 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
 // is redone on path B.
 constexpr int WK_WARPS = 8;
 constexpr uint32_t WK_QB = 8;
+int g_word_scan = 1;                    // test hook: 0 = path A scans 8 positions per thread and trip (the first version)
 int g_warp_path = 1;                    // test hook: 0 = short reads at k <= 6 use the CTA-per-read kernel
 
 template <bool CHECK>
@@ -1114,7 +1157,8 @@ int launch_tile(const uint2 *planes, const uint64_t *base_start, const uint32_t 
     uint64_t grid = (uint64_t)kam_sm_count() * per_sm;   // persistent: a whole number of CTAs per SM
     if (grid > n_seqs) grid = n_seqs;
     kern<<<(unsigned)grid, THREADS, smem, st>>>(planes, base_start, head_mask, n_seqs, k, count_bits, out,
-                                                  out_stride, w.queue, w.spill_count, w.spill_list, w.spill_maxlen);
+                                                  out_stride, w.queue, w.spill_count, w.spill_list, w.spill_maxlen,
+                                                  g_word_scan);
     KAM_CUDA(cudaGetLastError());
     return KAM_OK;
 }
@@ -1358,6 +1402,7 @@ int kam_kmer_sweep(const uint64_t *d_planes, const uint64_t *d_base_start, const
 // orders too, which was measured slower: fewer CTAs fit per SM next to the pooling buffers)
 void kam_kmer_sweep_set_fused_top(int k) { g_sweep_top = k; }
 void kam_kmer_set_warp_path(int on) { g_warp_path = on; }
+void kam_kmer_set_word_scan(int on) { g_word_scan = on; }
 void kam_kmer_set_long_path(int on) { g_long_path = on; }
 
 }  // extern "C"

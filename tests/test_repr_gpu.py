@@ -197,6 +197,34 @@ def test_short_reads_warp_kernel(R, k, out, bits):
                 np.testing.assert_allclose(got[i][ok], ref[ok], rtol=1e-6, atol=0, err_msg=str((k, i)))
 
 
+@pytest.mark.parametrize("out,bits", [("counts", 16), ("counts", 32), ("freq64", 16)])
+@pytest.mark.parametrize("k", [2, 5, 6, 7, 8, 9, 10])
+def test_tile_kernel_scan_variants(R, k, out, bits):
+    """The CTA-per-sequence kernel scans a whole plane word (32 k-mer end positions) per thread and trip;
+    the first version (8 positions, kam_kmer_set_word_scan(0)) must give the same bytes, and both the
+    oracle's.  Ragged genome lengths around the word / tile boundaries, dirty heads, sequences shorter
+    than k and empty ones in between so every sequence starts at a different bit of a plane word."""
+    recs = synth_records(40, 9000, seed=70 + k, jitter=700, dirty=0.002) + \
+        [b"", b"ACG", b"ACGTACGTAC", b"N" * 5 + b"ACGTTGCAACGT", b"T" * 31, b"G" * 32, b"C" * 33, b"A" * 64,
+         b"NNA" + synth_records(1, 20000, seed=3)[0], synth_records(1, 100000, seed=4)[0], b"ACGT" * 16 + b"A"] + \
+        synth_records(20, 2500, seed=71, jitter=31)
+    from kameris_b200 import _lib
+    got = _gpu_counts(R, recs, k, bits, out)
+    _lib.load().kam_kmer_set_word_scan(0)
+    try:
+        alt = _gpu_counts(R, recs, k, bits, out)
+    finally:
+        _lib.load().kam_kmer_set_word_scan(1)
+    assert got.tobytes() == alt.tobytes()
+    for i, r in enumerate(recs):
+        c = O.cgr_count(r, k, bits)
+        if out == "counts":
+            assert np.array_equal(got[i], c), (k, i)
+        else:
+            with np.errstate(all="ignore"):
+                assert np.array_equal(got[i], O.frequencies(c), equal_nan=True), (k, i)
+
+
 @pytest.mark.parametrize("long_path", [1, 0])
 @pytest.mark.parametrize("k,bits", [(9, 16), (9, 32), (8, 16), (7, 16), (2, 16), (10, 16), (11, 32), (12, 16)])
 def test_long_sequences_spill_path(R, k, bits, long_path):
