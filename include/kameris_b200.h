@@ -184,12 +184,19 @@ int kam_info_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                  uint32_t row_begin, uint32_t row_end, float *d_tri, void *d_ws, size_t ws_bytes,
                  void *stream);
 
-/* Gram-matrix metrics on count vectors (uint16/uint32): G = X X^T on the tcgen05 tensor cores
+/* Gram-matrix metrics on count vectors (uint8/uint16/uint32): G = X X^T on the tcgen05 tensor cores
  * with exact operands: uint8 x uint8 -> int32 (kind::i8) when every count <= 255, integer-valued
  * fp16 -> fp32 (kind::f16) up to 2048, exact uint64 CUDA-core Gram beyond; fused float64 epilogue.
  * metrics: any of KAM_M_EUCLID|KAM_M_COSINE|KAM_M_PEARSON; d_tri[m] (may be NULL when the metric
  * is not requested) receive float32 triangles.  euclid_on_freq != 0 computes euclidean distance
- * between the frequency vectors x_i/sum(x_i) (what a `frequencies` .mm-repr holds). */
+ * between the frequency vectors x_i/sum(x_i) (what a `frequencies` .mm-repr holds).
+ *
+ * elem KAM_F32 / KAM_F64 -- the rows of a `mode: frequencies` .mm-repr (backend.py:45-56: cgr / cgr.sum()):
+ * the pre-pass recovers, row by row, the integer counts behind the quotients and accepts them only when
+ * they reproduce every stored element bit for bit and sum to the divisor; the exact integer Gram of the
+ * recovered counts then runs on the tensor cores as above, with euclid between the rows as stored (the
+ * frequency vectors; euclid_on_freq is ignored).  If any row is not a frequency vector (or the recovered
+ * counts leave the tensor envelopes) the whole matrix takes a float64 Gram on the CUDA cores instead. */
 size_t kam_gram_workspace_bytes(uint32_t n, uint64_t d);
 /* workspace for inputs outside the tensor-exact envelope (integer CUDA-core Gram; 4 B per element).
  * kam_gram_tri returns KAM_E_WORKSPACE when it needs this size and was given less. */
@@ -197,6 +204,9 @@ size_t kam_gram_workspace_bytes_int(uint32_t n, uint64_t d);
 /* test hook: non-zero forces the fp16 (kind::f16) tensor path where the uint8 (kind::i8) path would
  * be chosen; both are exact inside their envelopes. */
 void kam_gram_force_f16(int on);
+/* test hook: 0 sends floating-point rows straight to the float64 CUDA-core Gram (no integer recovery);
+ * default 1. */
+void kam_gram_set_float_recover(int on);
 /* tuning/test hook: thread-block cluster size of the Gram kernel (2 = B panel multicast between the
  * two CTAs of a cluster, default; 1 = no cluster). */
 void kam_gram_set_cluster(int cl);
@@ -214,7 +224,10 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
  * blocks it owns.  operand_kind is global: KAM_GRAM_U8 needs every count <= 255 and every row's sum
  * of squares < 2^31, KAM_GRAM_F16 needs <= 2048 and < 2^24 (d_flags[0..1] receive, by atomicMax, the
  * largest count and the largest sum of squares seen; the caller zeroes them and reduces over ranks).
- * Operand rows are kam_gram_dpad(d) elements long (uint8 or fp16), zero padded. */
+ * Operand rows are kam_gram_dpad(d) elements long (uint8 or fp16), zero padded.  Floating-point rows
+ * (KAM_F32 / KAM_F64 frequency vectors) are converted through the integer recovery described above;
+ * d_flags[2] receives the number of rows that could not be recovered (the block interface has no
+ * float64 path: the caller must treat a non-zero count as an error).  d_flags holds >= 3 words. */
 #define KAM_GRAM_U8 0
 #define KAM_GRAM_F16 1
 uint64_t kam_gram_dpad(uint64_t d);
@@ -235,7 +248,8 @@ void kam_gram_set_sm_limit(int sms);
 
 /* Host-buffer form of the whole `distances` step: x is the n x d matrix read from a .mm-repr,
  * outputs are packed triangles (NULL = not requested).  euclid is taken between the rows as
- * stored (counts).  Blocking; allocates and frees its device buffers. */
+ * stored (count vectors of a `counts` file, frequency vectors of a `frequencies` file).  Blocking;
+ * allocates and frees its device buffers. */
 int kam_dists_host(const void *h_x, int elem, uint32_t n, uint64_t d, unsigned metrics,
                    uint32_t *h_manhat, float *h_info, float *h_euclid, float *h_cosine,
                    float *h_pearson);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "kam_gram_workspace_bytes": (c_size_t, [c_uint32, c_uint64]),
     "kam_gram_workspace_bytes_int": (c_size_t, [c_uint32, c_uint64]),
     "kam_gram_force_f16": (None, [c_int]),
+    "kam_gram_set_float_recover": (None, [c_int]),
     "kam_gram_set_cluster": (None, [c_int]),
     "kam_gram_set_pair": (None, [c_int]),
     "kam_gram_dpad": (c_uint64, [c_uint64]),

@@ -35,10 +35,39 @@ __device__ __forceinline__ void gram_store(const GramOut &go, long long idx, dou
     if (go.pearson) go.pearson[idx] = (float)(1.0 - (g - ri.S * cj.mu) * ri.rp * cj.rp);
     if (go.euclid) {
         const double e2 = ri.a + cj.a - 2.0 * g * ri.q * cj.q;
-        go.euclid[idx] = sqrtf((float)(e2 > 0.0 ? e2 : 0.0));
+        go.euclid[idx] = sqrtf((float)(e2 < 0.0 ? 0.0 : e2));   // cancellation below zero -> 0; NaN (an empty row) stays NaN
     }
 }
 #endif
+
+#ifdef __CUDACC__
+// 16 counts -> 16 tensor-core operand elements (uint8, saturating, or integer-valued fp16), one or two
+// 16-byte stores
+template <typename OP>
+__device__ __forceinline__ void store_operand16(OP *dst, const unsigned (&c)[16]) {
+    if constexpr (sizeof(OP) == 1) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            w[i] = min(c[4 * i], 255u) | (min(c[4 * i + 1], 255u) << 8) | (min(c[4 * i + 2], 255u) << 16) |
+                   (min(c[4 * i + 3], 255u) << 24);
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        __half2 h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = __halves2half2(__uint2half_rn(c[2 * i]), __uint2half_rn(c[2 * i + 1]));
+        reinterpret_cast<uint4 *>(dst)[0] = *reinterpret_cast<uint4 *>(&h[0]);
+        reinterpret_cast<uint4 *>(dst)[1] = *reinterpret_cast<uint4 *>(&h[4]);
+    }
+}
+#endif
+
+// floating-point rows (freq_gram.cu): operand pre-pass with integer recovery (flags[2] counts the rows
+// that are not frequency vectors), and the float64 CUDA-core Gram between the rows as stored
+int kam_float_prepass(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint64_t dpad, bool i8, void *h,
+                      unsigned long long *S, unsigned long long *G, unsigned long long *flags, cudaStream_t st);
+int kam_float_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,
+                       uint32_t row_end, RowK *rk, GramOut go, cudaStream_t st);
 
 size_t kam_int_gram_xt_bytes(uint32_t n, uint64_t d);
 int kam_int_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,

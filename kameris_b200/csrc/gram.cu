@@ -481,24 +481,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_pair_kernel(const __grid_co
 // fp16; zero-padded to dpad) and the exact per-row sum / sum of squares, and records the largest
 // count and the largest G_ii (the exactness envelope).  One CTA per row, 16 elements per thread and
 // step with 16-byte loads and stores.
-template <typename OP>
-__device__ __forceinline__ void store_operand16(OP *dst, const unsigned (&c)[16]) {
-    if constexpr (sizeof(OP) == 1) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            w[i] = min(c[4 * i], 255u) | (min(c[4 * i + 1], 255u) << 8) | (min(c[4 * i + 2], 255u) << 16) |
-                   (min(c[4 * i + 3], 255u) << 24);
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-    } else {
-        __half2 h[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = __halves2half2(__uint2half_rn(c[2 * i]), __uint2half_rn(c[2 * i + 1]));
-        reinterpret_cast<uint4 *>(dst)[0] = *reinterpret_cast<uint4 *>(&h[0]);
-        reinterpret_cast<uint4 *>(dst)[1] = *reinterpret_cast<uint4 *>(&h[4]);
-    }
-}
-
 template <typename T, typename OP>
 __global__ void __launch_bounds__(256) gram_prepass_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
                                                            uint64_t dpad, OP *__restrict__ h,
@@ -589,6 +571,7 @@ __global__ void rowk_kernel(const unsigned long long *__restrict__ S, const unsi
 }
 
 bool g_force_f16 = false;
+bool g_float_recover = true;   // test hook: false = floating-point rows always take the float64 CUDA-core Gram
 bool g_pair = true;        // cta_group::2 kernel (gram_pair_kernel, default) or the cluster-multicast one
 uint32_t g_cluster = 2;
 uint32_t g_sm_limit = 0;   // 0 = all SMs; otherwise leave the rest to concurrent work (e.g. NCCL transfers)
@@ -614,6 +597,8 @@ int run_prepass(const void *x, uint32_t n, uint64_t d, uint64_t ld, bool i8, voi
 
 int prepass_dispatch(const void *x, int elem, uint32_t n, uint64_t d, uint64_t ld, bool i8, void *h,
                      unsigned long long *S, unsigned long long *G, unsigned long long *flags, cudaStream_t st) {
+    if (elem == KAM_F32 || elem == KAM_F64)   // frequency rows: integer recovery fused into the sweep (freq_gram.cu)
+        return kam_float_prepass(x, elem, n, d, ld, dpad_of(d), i8, h, S, G, flags, st);
     return elem == KAM_U8    ? run_prepass<uint8_t>(x, n, d, ld, i8, h, S, G, flags, st)
            : elem == KAM_U16 ? run_prepass<uint16_t>(x, n, d, ld, i8, h, S, G, flags, st)
                              : run_prepass<uint32_t>(x, n, d, ld, i8, h, S, G, flags, st);
@@ -719,8 +704,8 @@ inline size_t gram_layout(uint32_t n, uint64_t d, void *base, GramWs *w, bool wi
     return off;
 }
 
-int read_flags(const unsigned long long *d_flags, unsigned long long (&h)[2], cudaStream_t st) {
-    KAM_CUDA(cudaMemcpyAsync(h, d_flags, 16, cudaMemcpyDeviceToHost, st));
+int read_flags(const unsigned long long *d_flags, unsigned long long (&h)[3], cudaStream_t st) {
+    KAM_CUDA(cudaMemcpyAsync(h, d_flags, 24, cudaMemcpyDeviceToHost, st));
     KAM_CUDA(cudaStreamSynchronize(st));
     return KAM_OK;
 }
@@ -736,7 +721,8 @@ uint64_t kam_gram_dpad(uint64_t d) { return dpad_of(d); }
 int kam_gram_prepare(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, int operand_kind,
                      void *d_operand, uint64_t *d_S, uint64_t *d_G, uint64_t *d_flags, void *stream) {
     KAM_REQUIRE(d_x && d_operand && d_S && d_G && d_flags, "null pointer");
-    KAM_REQUIRE(elem == KAM_U8 || elem == KAM_U16 || elem == KAM_U32, "euclid/cosine/pearson take integer count vectors");
+    KAM_REQUIRE(elem == KAM_U8 || elem == KAM_U16 || elem == KAM_U32 || elem == KAM_F32 || elem == KAM_F64,
+                "euclid/cosine/pearson take count vectors (uint8/16/32) or frequency vectors (float32/64)");
     KAM_REQUIRE(operand_kind == KAM_GRAM_U8 || operand_kind == KAM_GRAM_F16, "bad operand kind");
     KAM_REQUIRE(d >= 1 && d < (1ull << 32) && ld >= d, "bad d / ld");
     KAM_REQUIRE(((uintptr_t)d_operand & 15) == 0, "operand must be 16-byte aligned");
@@ -803,7 +789,8 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                  unsigned metrics, int euclid_on_freq, float *d_tri_euclid, float *d_tri_cosine, float *d_tri_pearson,
                  void *d_ws, size_t ws_bytes, void *stream) {
     KAM_REQUIRE(d_x && d_ws, "null pointer");
-    KAM_REQUIRE(elem == KAM_U8 || elem == KAM_U16 || elem == KAM_U32, "euclid/cosine/pearson take integer count vectors");
+    KAM_REQUIRE(elem == KAM_U8 || elem == KAM_U16 || elem == KAM_U32 || elem == KAM_F32 || elem == KAM_F64,
+                "euclid/cosine/pearson take count vectors (uint8/16/32) or frequency vectors (float32/64)");
     KAM_REQUIRE(d >= 1 && d < (1ull << 32) && ld >= d, "bad d / ld");
     KAM_REQUIRE((metrics & ~(KAM_M_EUCLID | KAM_M_COSINE | KAM_M_PEARSON)) == 0 && metrics != 0, "bad metrics mask");
     KAM_REQUIRE(!(metrics & KAM_M_EUCLID) || d_tri_euclid, "null euclid output");
@@ -827,9 +814,16 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     // uint8 x uint8 -> int32 (kind::i8) when every count fits a byte; fp16 -> fp32 (kind::f16) up to
     // 2048; otherwise the exact integer Gram on the CUDA cores.  The uint8 operand is written
     // speculatively (the common case); a second sweep rewrites it as fp16 only when it did not fit.
-    unsigned long long hflags[2] = {0, 0};
+    // Floating-point rows (a `frequencies` file): the same sweep recovers the integer counts behind the
+    // quotients, row by row, and accepts them only when they reproduce every element bit for bit
+    // (freq_gram.cu); euclid is then the distance between the rows as stored, i.e. between frequency
+    // vectors.  Rows that are not frequency vectors send the whole matrix to the float64 CUDA-core Gram.
+    const bool is_float = elem == KAM_F32 || elem == KAM_F64;
+    if (is_float) euclid_on_freq = 1;
+    unsigned long long hflags[3] = {0, 0, 0};
     int rc;
     bool have_i8 = false;
+    if (is_float && !g_float_recover) return kam_float_gram_tri(d_x, elem, n, d, ld, row_begin, row_end, w.rk, go, st);
     if (!g_force_f16) {
         KAM_CUDA(cudaMemsetAsync(w.flags, 0, 64, st));
         if ((rc = prepass_dispatch(d_x, elem, n, d, ld, true, w.h, w.S, w.G, w.flags, st))) return rc;
@@ -843,6 +837,8 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     }
     const bool use_i8 = have_i8;
     const bool use_f16 = !use_i8 && hflags[0] <= MAX_F16_COUNT && hflags[1] < MAX_F16_GII;
+    if (is_float && (hflags[2] != 0 || (!use_i8 && !use_f16)))
+        return kam_float_gram_tri(d_x, elem, n, d, ld, row_begin, row_end, w.rk, go, st);
     rowk_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.S, w.G, n, (double)d, euclid_on_freq, w.rk);
     KAM_CUDA(cudaGetLastError());
     if (!use_i8 && !use_f16) {
@@ -866,6 +862,7 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
 
 // test / tuning hooks
 void kam_gram_force_f16(int on) { g_force_f16 = on != 0; }
+void kam_gram_set_float_recover(int on) { g_float_recover = on != 0; }
 void kam_gram_set_cluster(int cl) { g_cluster = cl == 1 ? 1u : 2u; }
 void kam_gram_set_pair(int on) { g_pair = on != 0; }
 void kam_gram_set_sm_limit(int sms) { g_sm_limit = sms > 0 ? (uint32_t)sms : 0u; }

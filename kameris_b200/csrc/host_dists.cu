@@ -82,8 +82,9 @@ extern "C" int kam_dists_host(const void *h_x, int elem, uint32_t n, uint64_t d,
             if ((rc = t3.alloc(pairs * 4))) return rc;
             pp = (float *)t3.p;
         }
-        // a `frequencies` file cannot be an input here (integer counts are required), so euclid is
-        // the distance between the count vectors, like scipy euclidean on the rows of the file
+        // euclid is the distance between the rows as stored, like scipy euclidean on the rows of the
+        // file: count vectors (euclid_on_freq = 0), or the frequency vectors of a `frequencies` file
+        // (floating-point rows: kam_gram_tri recovers the counts and sets euclid_on_freq itself)
         rc = kam_gram_tri(x.p, elem, n, d, d, 0, n, gm, 0, pe, pc, pp, ws.p, wb, st);
         if (rc == KAM_E_WORKSPACE) {   // outside the tensor-exact envelope: the integer path needs more room
             cudaFree(ws.p);

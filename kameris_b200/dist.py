@@ -100,7 +100,9 @@ def info_tri(x, rows=None, out=None):
 
 def gram_tri(x, metrics=("euclid", "cosine", "pearson"), euclid_on_freq=True, rows=None, force_f16=False):
     """euclid / cosine / pearson of every pair i<j from one tensor-core Gram pass: dict of float32
-    packed triangles.  x: uint16/uint32 count vectors."""
+    packed triangles.  x: uint8/uint16/uint32 count vectors, or float32/float64 frequency vectors (the
+    counts behind them are recovered and verified on the device; euclid is then always between the
+    frequency vectors)."""
     lib = _lib.load()
     x = _prep(x)
     n, d = x.shape

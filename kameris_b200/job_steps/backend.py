@@ -6,7 +6,8 @@ with the two executables replaced by libkameris_b200.so (no subprocess, no CPU f
                  mode ('counts'|'frequencies'), disable_avx (ignored)
     run_backend_dists(options, exp_options)   backend.py:59-66
         options: input_file, output_prefix, distances (list), disable_avx (ignored)
-        distances: 'manhat', 'info' (reference) and 'euclid', 'cosine', 'pearson' (new).
+        distances: 'manhat', 'info' (reference) and 'euclid', 'cosine', 'pearson' (new; on a `counts`
+        file between the count vectors, on a `frequencies` file between the frequency vectors).
 
 Outputs: `.mm-repr` (uint16/uint32 counts, or float64 frequencies shaped 1 x 4^k exactly like the
 numpy rewrite of backend.py:45-56) and `<prefix>-<name>.mm-dist`.  Failures raise
@@ -250,8 +251,8 @@ def dists_from_matrix(x, metrics):
     for m in metrics:
         out[m] = np.zeros(pairs, dtype=np.uint32 if m == 'manhat' else np.float32)
         mask |= bits[m]
-    if any(m in GRAM_METRICS for m in metrics) and elem > 2:
-        raise ValueError('euclid/cosine/pearson need integer count vectors (mode: counts)')
+    if any(m in GRAM_METRICS for m in metrics) and elem == 3:
+        raise ValueError('euclid/cosine/pearson are not defined for 64-bit integer vectors')
 
     def p(m):
         return out[m].ctypes.data if m in out else None
@@ -273,8 +274,8 @@ def dists_to_files_sharded(input_file, output_prefix, metrics, dist, device=None
         n = reader.count
         b, e = rank * n // world, (rank + 1) * n // world
         x = reader.read_rows(b, e)
-    if any(m in GRAM_METRICS for m in metrics) and formats.element_type_of(x.dtype) > 2:
-        raise ValueError('euclid/cosine/pearson need integer count vectors (mode: counts)')
+    if any(m in GRAM_METRICS for m in metrics) and formats.element_type_of(x.dtype) == 3:
+        raise ValueError('euclid/cosine/pearson are not defined for 64-bit integer vectors')
     t = torch.from_numpy(x)
     if device is not None:
         t = t.to(device)

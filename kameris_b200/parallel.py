@@ -222,6 +222,9 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
         if world > 1:
             dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
         mx, gmax = int(flags[0]), int(flags[1])
+        if int(flags[2]):
+            raise ValueError("%d floating-point row(s) are not frequency vectors (count / sum): "
+                             "use distances_sharded()" % int(flags[2]))
         ok = (mx <= 255 and gmax < 2 ** 31) if kind == _lib.KAM_GRAM_U8 else (mx <= 2048 and gmax < 2 ** 24)
         if ok:
             break

@@ -115,10 +115,33 @@ def test_dists_gram_metrics_files(backend, genomes, tmp_path):
         np.testing.assert_allclose(tri, O.cdist_triangle(x, m), rtol=1e-5)
     tri, _ = formats.dist_reader.read_triangle(prefix + "-manhat.mm-dist")
     assert tri.tolist() == [3904, 4791, 4369, 4773, 4455, 4628]
-    # a frequencies file is rejected for the Gram metrics (integer counts required)
-    frq = str(tmp_path / "f.mm-repr")
-    backend.run_backend_kmers({"fasta_output_dir": genomes, "output_file": frq, "k": 4, "bits_per_element": 16,
-                               "mode": "frequencies", "disable_avx": True}, {})
+    # a uint64 file has no Gram metrics
+    w = formats.repr_writer(str(tmp_path / "u64.mm-repr"), np.zeros((1, 16), dtype=np.uint64), 3, create_file=True)
+    for i in range(3):
+        w.write_matrix(np.arange(16, dtype=np.uint64).reshape(1, 16) + i)
+    w.file.close()
     with pytest.raises(subprocess.CalledProcessError):
-        backend.run_backend_dists({"input_file": frq, "output_prefix": prefix, "distances": ["cosine"],
-                                   "disable_avx": True}, {})
+        backend.run_backend_dists({"input_file": str(tmp_path / "u64.mm-repr"), "output_prefix": prefix,
+                                   "distances": ["cosine"], "disable_avx": True}, {})
+
+
+@pytest.mark.parametrize("k", [3, 6, 8])
+def test_dists_gram_metrics_on_frequencies_file(backend, genomes, tmp_path, k):
+    """`mode: frequencies` (the reference's default, demo/hiv1-lanl.yml:30) writes float64 cgr / cgr.sum()
+    (backend.py:45-56); the distances step takes that file too: euclid / cosine / pearson between the
+    frequency vectors as stored, = scipy on the rows of the file.  k=6, 8: the counts behind the quotients
+    are recovered and verified on the device and the tensor-core Gram runs; k=3: smallest count > 8,
+    float64 CUDA-core Gram."""
+    frq = str(tmp_path / "f.mm-repr")
+    backend.run_backend_kmers({"fasta_output_dir": genomes, "output_file": frq, "k": k, "bits_per_element": 16,
+                               "mode": "frequencies", "disable_avx": True}, {})
+    prefix = str(tmp_path / "fq")
+    backend.run_backend_dists({"input_file": frq, "output_prefix": prefix,
+                               "distances": ["cosine", "pearson", "euclid"], "disable_avx": True}, {})
+    with formats.repr_reader(frq) as r:
+        x = r.read_all()
+    assert x.dtype == np.float64
+    for m in ("cosine", "pearson", "euclid"):
+        tri, n = formats.dist_reader.read_triangle("%s-%s.mm-dist" % (prefix, m))
+        assert n == 4 and tri.dtype == np.float32
+        np.testing.assert_allclose(tri, O.cdist_triangle(x, m), rtol=1e-5, err_msg=m)

@@ -263,3 +263,108 @@ def test_gram_block_rectangular(D):
                                   S[1].data_ptr(), G[1].data_ptr(), 70, 0, d, 0, 0, 150, _lib.KAM_M_PEARSON, 0, None, None,
                                   out.data_ptr(), 70, ws.data_ptr(), ws.numel(), st))
     np.testing.assert_allclose(out.cpu().numpy(), O.cdist_rect(xa, xb, "pearson"), rtol=1e-5)
+
+
+# ---- Gram metrics on floating-point rows (a `frequencies` .mm-repr) ----------------------------------
+def _freq(x, dtype):
+    """cgr / cgr.sum() as backend.py:49 computes it (float64); float32 as kmer_count.cu's freq32 kind."""
+    with np.errstate(all="ignore"):
+        f = x / x.sum(axis=1, keepdims=True).astype(np.float64)
+    return f.astype(dtype)
+
+
+def _set_recover(on):
+    from kameris_b200 import _lib
+    _lib.load().kam_gram_set_float_recover(on)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,L,k", [(37, 3000, 5), (130, 9000, 6), (257, 1000, 7), (40, 9000, 9), (65, 2000, 4)])
+def test_gram_on_frequency_rows_recovers_counts(D, n, L, k, dtype):
+    """float rows f = c / sum(c): the pre-pass recovers the integer counts (verified bit for bit), so the
+    tensor-core path gives exactly the triangles of the count matrix with euclid on frequencies; the
+    float64 CUDA-core kernel (recovery off) agrees to rounding; both match scipy on the stored rows."""
+    x = _counts(n, L, k, seed=300 + n + k)
+    f = _freq(x, dtype)
+    got = D.gram_tri(_dev(f), ("euclid", "cosine", "pearson"))
+    ref = D.gram_tri(_dev(x), ("euclid", "cosine", "pearson"), euclid_on_freq=True)
+    recovered = all(int(r[r > 0].min()) <= 8 for r in x)
+    if recovered:
+        for m in got:
+            assert torch.equal(got[m], ref[m]), m
+    _set_recover(0)
+    try:
+        alt = D.gram_tri(_dev(f), ("euclid", "cosine", "pearson"))
+    finally:
+        _set_recover(1)
+    f64 = f.astype(np.float64)
+    for m in ("euclid", "cosine", "pearson"):
+        want = O.cdist_triangle(f64, m)
+        tol = 1e-5 if dtype == np.float64 else 2e-4      # float32 rows: the INPUT is only good to 6e-8 per element
+        np.testing.assert_allclose(alt[m].cpu().numpy(), want, rtol=tol, err_msg=m)
+        np.testing.assert_allclose(got[m].cpu().numpy(), want, rtol=tol, err_msg=m)
+
+
+def test_gram_on_float_rows_general(D):
+    """rows that are not frequency vectors (arbitrary positive / signed floats, ragged d), an all-NaN row
+    (the 0/0 of an empty sequence) and an all-zero row: the float64 Gram between the rows as stored."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    for n, d in ((5, 7), (70, 100), (130, 1000), (64, 64)):
+        x = rng.standard_normal((n, d))
+        got = D.gram_tri(_dev(x), ("euclid", "cosine", "pearson"))
+        for m in got:
+            np.testing.assert_allclose(got[m].cpu().numpy(), O.cdist_triangle(x, m), rtol=1e-5, atol=1e-6, err_msg=m)
+        x32 = np.abs(x).astype(np.float32)
+        got = D.gram_tri(_dev(x32), ("euclid", "cosine", "pearson"))
+        for m in got:
+            np.testing.assert_allclose(got[m].cpu().numpy(), O.cdist_triangle(x32.astype(np.float64), m), rtol=1e-5,
+                                       atol=1e-6, err_msg=m)
+    # frequency rows + one row of NaN: still recovered; pairs with the NaN row are NaN like scipy's
+    c = _counts(20, 3000, 7, seed=9)
+    f = _freq(c, np.float64)
+    f[3] = np.nan
+    got = D.gram_tri(_dev(f), ("euclid", "cosine", "pearson"))
+    with np.errstate(all="ignore"):
+        for m in got:
+            want = O.cdist_triangle(f, m)
+            g = got[m].cpu().numpy()
+            assert np.array_equal(np.isnan(g), np.isnan(want)), m
+            ok = ~np.isnan(want)
+            np.testing.assert_allclose(g[ok], want[ok], rtol=1e-5, err_msg=m)
+    # a mixed row (some NaN) or a zero row is not a frequency vector: float64 path, same NaN pattern as scipy
+    f = _freq(c, np.float64)
+    f[5, :10] = np.nan
+    f[7] = 0.0
+    got = D.gram_tri(_dev(f), ("euclid", "cosine"))
+    with np.errstate(all="ignore"):
+        for m in got:
+            want = O.cdist_triangle(f, m)
+            g = got[m].cpu().numpy()
+            assert np.array_equal(np.isnan(g), np.isnan(want)), m
+            ok = ~np.isnan(want)
+            np.testing.assert_allclose(g[ok], want[ok], rtol=1e-5, err_msg=m)
+
+
+def test_gram_on_frequency_rows_row_ranges_and_f16(D):
+    """row blocks compose on both float paths; counts above 255 take the fp16 operand after recovery."""
+    c = _counts(150, 9000, 6, seed=41)
+    f = _freq(c, np.float64)
+    whole = D.gram_tri(_dev(f), ("cosine", "euclid"))
+    for rec in (1, 0):
+        _set_recover(rec)
+        try:
+            full = D.gram_tri(_dev(f), ("cosine", "euclid"))
+            parts = [D.gram_tri(_dev(f), ("cosine", "euclid"), rows=r) for r in ((0, 40), (40, 97), (97, 150))]
+        finally:
+            _set_recover(1)
+        for m in full:
+            assert torch.equal(sum(p[m] for p in parts), full[m]), (rec, m)
+            np.testing.assert_allclose(full[m].cpu().numpy(), whole[m].cpu().numpy(), rtol=1e-6)
+    rng = np.random.Generator(np.random.PCG64(5))
+    c = rng.integers(0, 600, size=(90, 48)).astype(np.uint16)
+    c[:, 0] = 1                                           # smallest positive count 1: recoverable
+    f = _freq(c, np.float64)
+    got = D.gram_tri(_dev(f), ("euclid", "cosine", "pearson"))
+    ref = D.gram_tri(_dev(c), ("euclid", "cosine", "pearson"), euclid_on_freq=True)
+    for m in got:
+        assert torch.equal(got[m], ref[m]), m

@@ -160,8 +160,8 @@ def test_abi_argument_validation_without_gpu():
     assert lib.kam_kmer_count(p, p, p, 1, 0, 4, 16, 0, p, 10, p, 1 << 20, None) == -1             # out_stride < 4^k
     assert lib.kam_kmer_count(p, p, p, 1, 0, 9, 16, 0, p, 4 ** 9, p, 64, None) == -3              # workspace too small
     assert lib.kam_kmers_host(None, None, 1, 4, 16, 0, None) == -1
-    assert lib.kam_gram_tri(p, 5, 10, 16, 16, 0, 10, 8, 1, None, p, None, p, 1 << 30, None) == -1  # float input
-    assert b"integer count vectors" in lib.kam_last_error()
+    assert lib.kam_gram_tri(p, 3, 10, 16, 16, 0, 10, 8, 1, None, p, None, p, 1 << 30, None) == -1  # uint64 input
+    assert b"count vectors" in lib.kam_last_error()
     assert lib.kam_gram_tri(p, 1, 10, 16, 16, 0, 10, 8, 1, None, None, None, p, 1 << 30, None) == -1   # missing output
     assert lib.kam_manhattan_tri(p, 9, 10, 16, 16, 0, 10, p, p, 1 << 30, None) == -1
     assert lib.kam_dists_host(p, 1, 10, 16, 0, None, None, None, None, None) == -1                 # no metric asked
