@@ -88,55 +88,47 @@ __global__ void __launch_bounds__(FP_THREADS) gram_prepass_float_kernel(const T 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr bool F32 = std::is_same<T, float>::value;
 
-    // pass 1: smallest positive element; what else is in the row
-    double fm = INFINITY;
-    unsigned long long npos = 0, nnan = 0, nbad = 0;
-    for (uint64_t e = (uint64_t)threadIdx.x * 16; e < d; e += FP_THREADS * 16) {
-        T v[16];
-        load16<T>(xr, e, d, vec_ok, v);
+    // smallest positive element of the first `limit` elements, and what else is there
+    auto scan = [&](uint64_t limit) {
+        double fm = INFINITY;
+        unsigned long long npos = 0, nnan = 0, nbad = 0;
+        for (uint64_t e = (uint64_t)threadIdx.x * 16; e < limit; e += FP_THREADS * 16) {
+            T v[16];
+            load16<T>(xr, e, d, vec_ok, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const double f = (double)v[i];
-            if (f != f) ++nnan;
-            else if (f < 0.0 || f == INFINITY) ++nbad;
-            else if (f > 0.0) {
-                ++npos;
-                fm = fmin(fm, f);
+            for (int i = 0; i < 16; ++i) {
+                const double f = (double)v[i];
+                if (f != f) ++nnan;
+                else if (f < 0.0 || f == INFINITY) ++nbad;
+                else if (f > 0.0) {
+                    ++npos;
+                    fm = fmin(fm, f);
+                }
             }
         }
-    }
-    fm = warp_min_d(fm);
-    npos = warp_sum64(npos), nnan = warp_sum64(nnan), nbad = warp_sum64(nbad);
-    if (lane == 0) red_d[warp] = fm, red_u[0][warp] = npos, red_u[1][warp] = nnan, red_u[2][warp] = nbad;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double m = INFINITY;
-        unsigned long long p = 0, q = 0, b = 0;
-        for (int w = 0; w < FP_THREADS / 32; ++w) m = fmin(m, red_d[w]), p += red_u[0][w], q += red_u[1][w], b += red_u[2][w];
-        s_fmin = m;
-        // NaN in every bin: the 0/0 of an empty sequence.  (The zero-padded tail of the last chunk is not counted:
-        // nnan counts elements < d only.)
-        s_mode = (q == d) ? 1 : (b == 0 && q == 0 && p > 0) ? 2 : 0;
-    }
-    __syncthreads();
-    const int mode = s_mode;
-    const double fmin_row = s_fmin;
-
-    bool done = false;
-    unsigned long long fs = 0, fg = 0, fmx = 0;
-    if (mode == 1) {
-        for (uint64_t e = (uint64_t)threadIdx.x * 16; e < dpad; e += FP_THREADS * 16) {
-            unsigned c[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) c[i] = 0;
-            store_operand16<OP>(hr + e, c);
+        fm = warp_min_d(fm);
+        npos = warp_sum64(npos), nnan = warp_sum64(nnan), nbad = warp_sum64(nbad);
+        if (lane == 0) red_d[warp] = fm, red_u[0][warp] = npos, red_u[1][warp] = nnan, red_u[2][warp] = nbad;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = INFINITY;
+            unsigned long long p = 0, q = 0, b = 0;
+            for (int w = 0; w < FP_THREADS / 32; ++w)
+                m = fmin(m, red_d[w]), p += red_u[0][w], q += red_u[1][w], b += red_u[2][w];
+            s_fmin = m;
+            // NaN in every bin: the 0/0 of an empty sequence (the zero fill past d is not counted)
+            s_mode = (q == limit) ? 1 : (b == 0 && q == 0 && p > 0) ? 2 : 0;
         }
-        done = true;
-    } else if (mode == 2) {
+        __syncthreads();
+    };
+
+    unsigned long long fs = 0, fg = 0, fmx = 0;
+    // proposals S = rint(c_min / fm), c_min = 1..N_CMIN: verify every element, write the operand row
+    auto try_proposals = [&](double fm) -> bool {
         constexpr int N_DELTA = F32 ? 3 : 1;   // a float32 quotient pins S only to within 2^-24
-        for (int prop = 0; prop < N_CMIN * N_DELTA && !done; ++prop) {
+        for (int prop = 0; prop < N_CMIN * N_DELTA; ++prop) {
             const int cmin = prop / N_DELTA + 1, dl = prop % N_DELTA;
-            const double Sd = rint((double)cmin / fmin_row) + (dl == 0 ? 0.0 : dl == 1 ? -1.0 : 1.0);
+            const double Sd = rint((double)cmin / fm) + (dl == 0 ? 0.0 : dl == 1 ? -1.0 : 1.0);
             if (!(Sd >= 1.0 && Sd < 4503599627370496.0)) continue;   // uniform: same value in every thread
             unsigned long long s = 0, g = 0;
             unsigned mx = 0, bad = 0;
@@ -154,7 +146,7 @@ __global__ void __launch_bounds__(FP_THREADS) gram_prepass_float_kernel(const T 
                 store_operand16<OP>(hr + e, c);
             }
             s = warp_sum64(s), g = warp_sum64(g);
-            unsigned long long mb = ((unsigned long long)bad << 32) | mx;   // max() keeps both: bad flag and largest count
+            unsigned long long mb = ((unsigned long long)bad << 32) | mx;   // bad flag and largest count in one word
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const unsigned long long t = __shfl_xor_sync(0xffffffffu, mb, o);
@@ -175,9 +167,40 @@ __global__ void __launch_bounds__(FP_THREADS) gram_prepass_float_kernel(const T 
             }
             __syncthreads();
             if (s_tot[3] == 0) {
-                done = true;
                 fs = s_tot[0], fg = s_tot[1], fmx = s_tot[2];
+                return true;
             }
+        }
+        return false;
+    };
+
+    bool done = false;
+    double tried = 0.0;
+    // Long rows: the smallest positive element of a short prefix is nearly always a count of 1 already, so
+    // the proposals are formed after reading 1/16 of the row or less and the row is swept ONCE (verification
+    // does not depend on where the proposal came from); only if they fail is the whole row scanned.
+    constexpr uint64_t PREFIX = 16384;
+    if (d >= 16 * PREFIX) {
+        scan(PREFIX);
+        if (s_mode == 2) {
+            tried = s_fmin;
+            done = try_proposals(tried);
+        }
+    }
+    if (!done) {
+        scan(d);
+        const int mode = s_mode;
+        const double fm = s_fmin;
+        if (mode == 1) {
+            for (uint64_t e = (uint64_t)threadIdx.x * 16; e < dpad; e += FP_THREADS * 16) {
+                unsigned c[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) c[i] = 0;
+                store_operand16<OP>(hr + e, c);
+            }
+            done = true;
+        } else if (mode == 2 && fm != tried) {
+            done = try_proposals(fm);
         }
     }
     if (threadIdx.x == 0) {

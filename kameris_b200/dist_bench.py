@@ -22,8 +22,8 @@ def _time(torch, fn, reps):
     return e0.elapsed_time(e1) / reps * 1e-3
 
 
-def synth_counts(torch, dev, n, L, k, seed):
-    """count vectors of n synthetic genomes, produced by the repr path itself."""
+def synth_counts(torch, dev, n, L, k, seed, kind="counts"):
+    """count (or frequency) vectors of n synthetic genomes, produced by the repr path itself."""
     from . import repr as R
     rng = np.random.Generator(np.random.PCG64(seed))
     alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
@@ -32,7 +32,7 @@ def synth_counts(torch, dev, n, L, k, seed):
     d_chars = torch.zeros(len(chars) + 16, dtype=torch.uint8, device=dev)
     d_chars[:len(chars)] = torch.from_numpy(chars.copy()).to(dev)
     batch = R.pack_chars(d_chars, torch.from_numpy(start).to(dev), n, len(chars))
-    return R.kmer_vectors(batch, k, 16, "counts")
+    return R.kmer_vectors(batch, k, 16, kind)
 
 
 def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
@@ -76,7 +76,45 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
                                  "roofline": {"bound": "tensor", "achieved": tflops16, "peak": tf_peak,
                                               "unit": "TFLOP/s", "frac": tflops16 / tf_peak,
                                               "kernel": "gram_pair_kernel<f16>"}}}
-    del x, tri, ws
+    del x
+
+    # ---- the same metrics on a `frequencies` matrix (float64 cgr / cgr.sum(), what backend.py:45-56 writes) ----
+    # integer recovery fused into the pre-pass (freq_gram.cu), then the same tensor-core Gram
+    xf = synth_counts(torch, dev, n, 9000, k, 20261003, kind="freq64")
+
+    def gram_f():
+        _lib.check(lib.kam_gram_tri(xf.data_ptr(), 5, n, d, xf.stride(0), 0, n, 4 | 8 | 16, 1, tri["euclid"].data_ptr(),
+                                    tri["cosine"].data_ptr(), tri["pearson"].data_ptr(), ws.data_ptr(), ws.numel(),
+                                    stream))
+    tf = _time(torch, gram_f, reps)
+    out["gram"]["frequencies_input"] = {
+        "value": pairs / tf, "unit": "pairs/s", "ms": tf * 1e3,
+        "what": "float64 frequency rows: counts recovered and verified bit for bit in the pre-pass "
+                "(1/16 + 1 sweeps of %.1f GB), then the uint8 tensor-core Gram" % (n * d * 8 / 1e9),
+        "extra_ms_vs_counts_input": (tf - t) * 1e3,
+        "prepass_read_GBps_lower_bound": (1.0 + 1.0 / 16) * n * d * 8 / max(tf - t, 1e-9) / 1e9}
+    del xf
+    # rows that are not frequency vectors: float64 Gram on the CUDA cores (DFMA-bound)
+    nf, df = 4096, 4096
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    xr = torch.rand((nf, df), dtype=torch.float64, device=dev, generator=g)
+    pf = nf * (nf - 1) // 2
+    wsf = torch.empty(lib.kam_gram_workspace_bytes(nf, df), dtype=torch.uint8, device=dev)
+
+    def gram_r():
+        _lib.check(lib.kam_gram_tri(xr.data_ptr(), 5, nf, df, xr.stride(0), 0, nf, 4 | 8 | 16, 1,
+                                    tri["euclid"].data_ptr(), tri["cosine"].data_ptr(), tri["pearson"].data_ptr(),
+                                    wsf.data_ptr(), wsf.numel(), stream))
+    tr = _time(torch, gram_r, reps)
+    dfma_peak = 148 * 58.8 * 1.965e9              # measured FP64 rate (scratch/dfma_bench.cu): 58.8 FMA/clk/SM
+    out["gram"]["float64_fallback"] = {
+        "value": pf / tr, "unit": "pairs/s", "ms": tr * 1e3,
+        "config": {"workload": "N=%d arbitrary float64 rows, D=%d" % (nf, df),
+                   "includes": "failed recovery pre-pass + row statistics + gram_f64_kernel"},
+        "roofline": {"bound": "fp64 issue", "achieved": pf * df / tr / 1e12, "peak": dfma_peak / 1e12,
+                     "unit": "T DFMA/s", "frac": pf * df / tr / dfma_peak, "kernel": "gram_f64_kernel<double>"}}
+    del xr, wsf, tri, ws
 
     # ---- manhattan, config-4 shape ----------------------------------------------------------------------
     m, c, k6 = 131072, 1000, 6
