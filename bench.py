@@ -14,10 +14,12 @@ One step = one pass of the `kmers` hot path over the whole batch.
           .mm-repr value type, bit-exact cgr/cgr.sum()) into pinned host memory
   roofline : HBM; algorithmic bytes/vector = ceil(L/4) + 4^k*4 over the CUDA-event
           time of the kam_kmer_count launches, against MEASURED_PEAKS.json
-  cpu_baseline : the reference `kmers` step (`kind: port`; its executables cannot run here): the
-          oracle's threaded restatement of generation_cgr on all host cores followed by the
-          reference's own single-threaded numpy pass (backend.py:45-49), on a bounded sample.  The
-          all-threads float32 C variant is reported beside it as `threaded_c_f32`.
+  cpu_baseline : the reference `kmers` step on all host cores, on a bounded sample: generation_cgr's
+          per-file CGR fill -- the reference's OWN machine code (`kind: reference`: the leaf function of
+          generation_cgr_windows_avx2.exe, extracted into oracle/_ref by the build where /root/reference
+          is mounted and run in-process, oracle/refcode/refcode.c) or, without it, the oracle's threaded
+          restatement (`kind: port`) -- followed by the reference's own single-threaded numpy pass
+          (backend.py:45-49).  The all-threads float32 C variant is reported beside it as `threaded_c_f32`.
   distances : secondary lines -- pairs/s of the distance kernels on vectors of the same shape
   kmers_other_shapes : secondary lines -- the short-read (configs[3]) and megabase (configs[4]) shapes
   mds : secondary line -- the mds step at n = 10 000 with the reference's numpy/ARPACK mds() beside it
@@ -103,10 +105,28 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def reference_kmers_step(O, chars, start, n, counts, threads):
-    """The reference `kmers` step, mode=frequencies, minus file I/O: generation_cgr (threaded port,
-    uint16 counts) then the numpy loop of kameris/job_steps/backend.py:45-49 verbatim."""
-    O.lib().orc_cgr_batch(chars.ctypes.data, start.ctypes.data, n, K, 16, counts.ctypes.data, threads)
+def reference_fill(O):
+    """The reference's own CGR-fill machine code when oracle/_ref holds it (built in the container where
+    /root/reference is mounted; see oracle/refcode/refcode.c), checked here against the port on a few
+    records; None -> the port is timed instead."""
+    if O.refcode() is None:
+        return None
+    chars, start = synth_chars(8, SEQ_LEN, SEED + 1)
+    got = np.zeros((8, BINS), dtype=np.uint16)
+    O.refcode_cgr_batch(chars, start, K, got, threads=2)
+    if not np.array_equal(got, O.cgr_batch(chars, start, K, 16)):
+        raise RuntimeError("the reference's machine code and its port disagree")
+    return O.refcode_cgr_batch
+
+
+def reference_kmers_step(O, chars, start, n, counts, threads, fill=None):
+    """The reference `kmers` step, mode=frequencies, minus file I/O: generation_cgr's per-file CGR fill on
+    all host threads (the reference's own machine code when available, else the threaded port; uint16
+    counts) then the numpy loop of kameris/job_steps/backend.py:45-49 verbatim."""
+    if fill is not None:
+        fill(chars, start, K, counts, threads=threads)
+    else:
+        O.lib().orc_cgr_batch(chars.ctypes.data, start.ctypes.data, n, K, 16, counts.ctypes.data, threads)
     cgrs = []
     for i in range(n):
         cgr = counts[i].reshape(1, -1)          # reader.read_matrix(i)
@@ -114,17 +134,32 @@ def reference_kmers_step(O, chars, start, n, counts, threads):
     return cgrs
 
 
+def _baseline_kind(fill, threads):
+    if fill is not None:
+        return "reference", ("the reference's own CGR-fill machine code (generation_cgr_windows_avx2.exe VA "
+                             "0x140016040, mapped from oracle/_ref) on %d threads" % threads)
+    return "port", "threaded uint16 counts (port of generation_cgr, %d threads)" % threads
+
+
 def cpu_baseline(sample_n=1500, reps=2):
     from oracle import oracle as O
     threads = O.host_threads()
+    fill = reference_fill(O)
+    kind, what = _baseline_kind(fill, threads)
     n = sample_n
     chars, start = synth_chars(n, SEQ_LEN, SEED)
     counts = np.zeros((n, BINS), dtype=np.uint16)
     best = float("inf")
     for _ in range(reps):
         t0 = time.perf_counter()
-        reference_kmers_step(O, chars, start, n, counts, threads)
+        reference_kmers_step(O, chars, start, n, counts, threads, fill)
         best = min(best, time.perf_counter() - t0)
+    t0 = time.perf_counter()                          # the counting part alone (no numpy pass), warm buffers
+    if fill is not None:
+        fill(chars, start, K, counts, threads=threads)
+    else:
+        O.lib().orc_cgr_batch(chars.ctypes.data, start.ctypes.data, n, K, 16, counts.ctypes.data, threads)
+    t_fill = time.perf_counter() - t0
     n2 = max(64, 250 * threads)
     chars2, start2 = synth_chars(n2, SEQ_LEN, SEED)
     out = np.zeros((n2, BINS), dtype=np.float32)     # pre-touched
@@ -133,40 +168,44 @@ def cpu_baseline(sample_n=1500, reps=2):
         t0 = time.perf_counter()
         O.cgr_freq_batch(chars2, start2, K, 16, f64=False, threads=threads, out=out)
         best2 = min(best2, time.perf_counter() - t0)
-    return {"value": n / best, "unit": "vectors/s", "cores": threads, "kind": "port",
-            "sample": "%d of the %d sequences x %d bp, k=%d: threaded uint16 counts (port of generation_cgr, %d "
-                      "threads) + the reference's single-threaded numpy float64 pass (backend.py:45-49), best of %d"
-                      % (n, N_SEQS, SEQ_LEN, K, threads, reps),
+    return {"value": n / best, "unit": "vectors/s", "cores": threads, "kind": kind,
+            "sample": "%d of the %d sequences x %d bp, k=%d: %s + the reference's single-threaded numpy float64 "
+                      "pass (backend.py:45-49), best of %d" % (n, N_SEQS, SEQ_LEN, K, what, reps),
+            "counts_only": {"value": n / t_fill, "unit": "vectors/s",
+                            "what": "the uint16 counting part alone (%s), no frequency pass" % kind},
             "threaded_c_f32": {"value": n2 / best2, "unit": "vectors/s",
                                "what": "counts + float32 normalisation fused in C on all %d threads, output "
                                        "pre-touched (NOT what the reference does; upper bound for a CPU)" % threads}}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle port: its executables cannot run here)."""
+    """--impl reference: the reference's CPU path on the host cores -- its own CGR-fill machine code from
+    oracle/_ref when the build container extracted it, else the oracle port -- plus its numpy pass."""
     if rank != 0:
         return
     from oracle import oracle as O
     threads = O.host_threads()
+    fill = reference_fill(O)
+    kind, what = _baseline_kind(fill, threads)
     n = 500
     chars, start = synth_chars(n, SEQ_LEN, SEED)
     counts = np.zeros((n, BINS), dtype=np.uint16)
     for _ in range(args.warmup):
-        reference_kmers_step(O, chars, start, n, counts, threads)
+        reference_kmers_step(O, chars, start, n, counts, threads, fill)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        reference_kmers_step(O, chars, start, n, counts, threads)
+        reference_kmers_step(O, chars, start, n, counts, threads, fill)
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
-    sample = ("%d sequences x %d bp per step (bounded sample of the %d-sequence workload): threaded uint16 counts "
-              "(%d threads) + single-threaded numpy float64 pass (backend.py:45-49)" % (n, SEQ_LEN, N_SEQS, threads))
+    sample = ("%d sequences x %d bp per step (bounded sample of the %d-sequence workload): %s + single-threaded "
+              "numpy float64 pass (backend.py:45-49)" % (n, SEQ_LEN, N_SEQS, what))
     print(json.dumps({
         "impl": "reference", "metric": "cgr_vectors_per_sec_k9", "value": v, "unit": "vectors/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic HIV-1-like 10k x 9 kb, k=9 CGR frequency vectors (configs[1])",
                    "n_seqs_per_step": n, "seq_len": SEQ_LEN, "k": K, "out": "float64"},
-        "cpu_baseline": {"value": v, "unit": "vectors/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "vectors/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))

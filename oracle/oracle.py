@@ -88,6 +88,73 @@ def lib():
     return _lib
 
 
+# ---- the reference's own machine code (oracle/refcode/refcode.c) -----------------------------------------
+_REF_SO = os.path.join(_HERE, "_ref", "librefcode.so")
+REF_BLOB = os.path.join(_HERE, "_ref", "cgr_fill_u16.bin")
+REF_PE = "/root/reference/kameris/scripts/generation_cgr_windows_avx2.exe"
+_ref = False
+
+
+def _has_bmi2():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " bmi2" in line
+    except OSError:
+        pass
+    return False
+
+
+def refcode_extract_blob():
+    """Build step (container with /root/reference): write the CGR fill function's 0x168 bytes + the order
+    string into oracle/_ref/cgr_fill_u16.bin, a build output that travels to the GPU box like the .so files."""
+    lib = ctypes.CDLL(_REF_SO)
+    rc = lib.refcode_extract(REF_PE.encode(), REF_BLOB.encode())
+    if rc != 0:
+        raise RuntimeError("refcode_extract failed: %d" % rc)
+    return REF_BLOB
+
+
+def refcode():
+    """Runner for the reference's own CGR-fill machine code: loaded from the reference executable where
+    /root/reference is mounted, else from the blob the build extracted into oracle/_ref/.  None when
+    neither is there (or the host has no BMI2: the code uses shlx)."""
+    global _ref
+    if _ref is False:
+        _ref = None
+        if os.path.exists(_REF_SO) and _has_bmi2():
+            lib = ctypes.CDLL(_REF_SO)
+            if os.path.exists(REF_PE):
+                rc = lib.refcode_load(REF_PE.encode())
+            elif os.path.exists(REF_BLOB):
+                rc = lib.refcode_load_blob(REF_BLOB.encode())
+            else:
+                rc = -1
+            if rc == 0:
+                lib.refcode_order.restype = ctypes.c_char_p
+                lib.refcode_cgr_u16_batch.restype = ctypes.c_int
+                lib.refcode_cgr_u16_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                                      ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int]
+                if lib.refcode_order() == b"ACGT":
+                    _ref = lib
+    return _ref
+
+
+def refcode_cgr_batch(chars, start, k, out, threads=0):
+    """uint16 CGR count vectors of a batch of records by the REFERENCE'S machine code on `threads` host
+    threads (what generation_cgr's executor does per file, minus the file reads)."""
+    lib = refcode()
+    if lib is None:
+        raise RuntimeError("the reference's machine code is not available here")
+    n = len(start) - 1
+    assert out.dtype == np.uint16 and out.shape == (n, 4 ** k) and out.flags.c_contiguous
+    rc = lib.refcode_cgr_u16_batch(_ptr(chars), _ptr(start), n, k, _ptr(out), threads or host_threads())
+    if rc != 0:
+        raise RuntimeError("refcode_cgr_u16_batch failed: %d" % rc)
+    return out
+
+
 def host_threads():
     """std::thread::hardware_concurrency() of the reference (cgr@0x100015641, dists@0x1000017ae)."""
     try:

@@ -118,3 +118,21 @@ def test_oracle_dists_match_reference_machine_code(refcode_dists_cases):
         assert np.array_equal(f.view(np.uint32), inf.view(np.uint32)), name
         seen.add(x.dtype.str)
     assert len(seen) == 6
+
+
+def test_reference_machine_code_batch_equals_port():
+    """bench.py's `kind: reference` CPU baseline runs the reference's own CGR-fill machine code (loaded from
+    the reference executable here, from the blob under oracle/_ref on the GPU box) on host threads: same
+    vectors as the port, clean and dirty records, several k."""
+    if O.refcode() is None:
+        pytest.skip("oracle/_ref holds no reference machine code on this host")
+    from tests.helpers import synth_records
+    recs = synth_records(24, 3000, seed=4, jitter=400, dirty=0.01) + [b"", b"ACG", b"NNACGTNACGT"]
+    lens = np.array([len(r) for r in recs], dtype=np.uint64)
+    start = np.zeros(len(recs) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=start[1:])
+    chars = np.frombuffer(b"".join(recs), dtype=np.uint8)
+    for k in (3, 6, 9):
+        got = np.zeros((len(recs), 4 ** k), dtype=np.uint16)
+        O.refcode_cgr_batch(chars, start, k, got, threads=3)
+        assert np.array_equal(got, O.cgr_batch(chars, start, k, 16)), k
