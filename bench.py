@@ -211,6 +211,49 @@ def run_reference(args, rank, world):
     }))
 
 
+def mds_cpu_baseline(tri, n, dim, sample_n=3000):
+    """the reference's mds() (numpy + ARPACK, oracle port of mds.py:10-35) on the first sample_n points of the
+    set the GPU line used"""
+    from oracle import oracle as O
+    m = min(sample_n, n)
+    # pairs (i, j) with i < j < m: the first m-1-i entries of row i of the packed triangle
+    sub = np.concatenate([tri[i * n - i * (i + 1) // 2: i * n - i * (i + 1) // 2 + (m - 1 - i)] for i in range(m - 1)])
+    delta = O.full_from_triangle(sub, m)
+    t0 = time.perf_counter()
+    O.mds_reference_arpack(delta, dim)
+    dt = time.perf_counter() - t0
+    return {"value": m / dt, "unit": "points/s", "kind": "port", "sample": "first %d of the %d points: numpy centring + "
+            "scipy eigsh (mds.py:10-35)" % (m, n), "ms": dt * 1e3}
+
+
+def distances_cpu_baseline(n=4096, k=6, length=9000):
+    """generation_dists' row tasks on all host threads (`kind: port`: the threaded restatement of the manhat /
+    info row lambda, generation_dists_mac_avx2 @0x10001b8c0; its machine code needs the whole executable image
+    and stays in the build container), on n count vectors of D = 4^k; and scipy's pdist for the metrics the
+    reference does not have."""
+    from oracle import oracle as O
+    threads = O.host_threads()
+    chars, start = synth_chars(n, length, SEED + 7)
+    x = O.cgr_batch(chars, start, k, 16)
+    pairs = n * (n - 1) // 2
+    t0 = time.perf_counter()
+    O.dists_triangle(x, True, False, threads=threads)
+    tm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.dists_triangle(x, False, True, threads=threads)
+    ti = time.perf_counter() - t0
+    m = 256
+    t0 = time.perf_counter()
+    O.cdist_triangle(x[:m], "cosine")
+    tc = time.perf_counter() - t0
+    sample = "%d count vectors (%d bp, k=%d, D=%d): %d pairs" % (n, length, k, 4 ** k, pairs)
+    return {"manhat": {"value": pairs / tm, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+            "info": {"value": pairs / ti, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+            "cosine_scipy_pdist": {"value": m * (m - 1) // 2 / tc, "unit": "pairs/s", "cores": 1, "kind": "port",
+                                   "sample": "scipy.spatial.distance.pdist(cosine) on %d of those vectors (the "
+                                             "definition of the metric; not in the reference)" % m}}
+
+
 def distance_lines(torch, dev, hbm_peak, tf_peak):
     """Secondary measurements: pairs/s of the distance kernels (filled in as they are built)."""
     try:
@@ -389,13 +432,15 @@ def main():
             d = distance_lines(torch, dev, hbm_peak, tf_peak)
             if d is not None:
                 line["distances"] = d
+                if not args.no_cpu_baseline and "error" not in d:
+                    d["cpu_baseline"] = distances_cpu_baseline()
         if world == 1 and not args.no_extra:
             try:                                   # the first consumer of the matrices
                 from kameris_b200 import mds_bench
                 torch.cuda.empty_cache()
                 line["mds"], tri_sample = mds_bench.run(dev, hbm_peak)
                 if not args.no_cpu_baseline:
-                    line["mds"]["cpu_baseline"] = mds_bench.cpu_baseline(tri_sample, 10000, 10)
+                    line["mds"]["cpu_baseline"] = mds_cpu_baseline(tri_sample, 10000, 10)
             except Exception as e:
                 line["mds"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))

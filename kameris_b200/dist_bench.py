@@ -137,6 +137,39 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
                         "roofline": {"bound": "cuda-core issue", "achieved": m * c * d6 / t / 1e12,
                                      "peak": lane_peak / 1e12, "unit": "T pair-elements/s (peak: 1 lane-op each)",
                                      "frac": m * c * d6 / t / lane_peak, "kernel": "pair_tile_kernel<SAD8X4>"}}
+    del reads, cent, o, ws
+    torch.cuda.empty_cache()
+
+    # ---- e2e: the whole `distances` step on HOST buffers through kam_dists_host ---------------------------
+    # (what run_backend_dists calls between reading the .mm-repr and writing the .mm-dist files): H2D of the
+    # count vectors, kernels, D2H of the packed triangles, device buffers allocated and freed inside the call
+    import time
+    ne, ke = 16384, 6
+    de = 4 ** ke
+    xe = synth_counts(torch, dev, ne, 9000, ke, 20261006).cpu().pin_memory()
+    pe = ne * (ne - 1) // 2
+    h_man = torch.empty(pe, dtype=torch.int32).pin_memory()
+    h_f = [torch.empty(pe, dtype=torch.float32).pin_memory() for _ in range(3)]
+
+    def host_step(mask):
+        _lib.check(lib.kam_dists_host(xe.data_ptr(), 1, ne, de, mask,
+                                      h_man.data_ptr() if mask & 1 else None, None,
+                                      h_f[0].data_ptr() if mask & 4 else None,
+                                      h_f[1].data_ptr() if mask & 8 else None,
+                                      h_f[2].data_ptr() if mask & 16 else None))
+
+    e2e = {}
+    for name, mask, n_out in (("manhat", 1, 1), ("euclid+cosine+pearson", 4 | 8 | 16, 3)):
+        host_step(mask)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            host_step(mask)
+        dt = (time.perf_counter() - t0) / reps
+        e2e[name] = {"value": pe / dt, "unit": "pairs/s", "ms": dt * 1e3,
+                     "h2d_bytes_per_step": ne * de * 2, "d2h_bytes_per_step": pe * 4 * n_out}
+    out["e2e"] = {"api": "kam_dists_host (C ABI, pinned host buffers)",
+                  "config": {"workload": "%d count vectors (9 kb genomes, k=%d, D=%d, uint16): %d pairs" % (ne, ke, de, pe)},
+                  **e2e}
     return out
 
 

@@ -54,18 +54,3 @@ def run(dev, hbm_peak, n=10000, dim=10):
                        "frac": (4 * n * n * 8 + tri.numel() * 4) / t_c / 1e9 / hbm_peak},
             "symm_block": {"ms": t_s * 1e3, "GBps": n * n * 8 / t_s / 1e9, "frac": n * n * 8 / t_s / 1e9 / hbm_peak,
                            "dfma_per_clk_per_sm": n * n * 16 / t_s / 148 / 1.965e9, "cublas_dgemm_ms": t_mm * 1e3}}, sample
-
-
-def cpu_baseline(tri, n, dim, sample_n=3000):
-    """the reference's mds() (numpy + ARPACK, oracle port) on the first sample_n points of the same set"""
-    import numpy as np
-    from oracle import oracle as O
-    m = min(sample_n, n)
-    # pairs (i, j) with i < j < m: the first m-1-i entries of row i of the packed triangle
-    sub = np.concatenate([tri[i * n - i * (i + 1) // 2: i * n - i * (i + 1) // 2 + (m - 1 - i)] for i in range(m - 1)])
-    delta = O.full_from_triangle(sub, m)
-    t0 = time.perf_counter()
-    O.mds_reference_arpack(delta, dim)
-    dt = time.perf_counter() - t0
-    return {"value": m / dt, "unit": "points/s", "kind": "port", "sample": "first %d of the %d points: numpy centring + "
-            "scipy eigsh (mds.py:10-35)" % (m, n), "ms": dt * 1e3}
