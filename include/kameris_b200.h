@@ -272,6 +272,20 @@ int kam_symm_block(const double *d_B, uint32_t n, const double *d_Q, double *d_Y
  * whenever n is even (16-byte-aligned rows); identical results up to the summation order. */
 void kam_symm_set_tma(int on);
 
+/* ---------------------------------------------------------------------------------------------
+ * classify pre-processing (kameris/job_steps/classify.py:29-50): the column statistics and
+ * the transform of sklearn's StandardScaler(with_mean=False) on a row-major n x d feature matrix (elem
+ * KAM_U8/U16/U32 count vectors or KAM_F32/F64 frequency vectors), float64 results:
+ *   mean_c = sum x_ic / n_c,  var_c = (sum (x_ic - mean_c)^2 - (sum (x_ic - mean_c))^2 / n_c) / n_c
+ * over the n_c non-NaN entries of column c (sklearn/utils/extmath.py _incremental_mean_and_var), and
+ * out_ic = x_ic / scale_c.  Asynchronous on `stream`.
+ * ------------------------------------------------------------------------------------------- */
+size_t kam_colstats_workspace_bytes(uint32_t n, uint64_t d);
+int kam_col_stats(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, double *d_mean, double *d_var,
+                  int64_t *d_count, void *d_ws, size_t ws_bytes, void *stream);
+int kam_col_scale(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, const double *d_scale,
+                  double *d_out, uint64_t out_ld, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

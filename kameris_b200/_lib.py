@@ -71,6 +71,10 @@ SIGNATURES = {
     "kam_symm_workspace_bytes": (c_size_t, [c_uint32]),
     "kam_symm_set_tma": (None, [c_int]),
     "kam_symm_block": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kam_colstats_workspace_bytes": (c_size_t, [c_uint32, c_uint64]),
+    "kam_col_stats": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_size_t, c_void_p]),
+    "kam_col_scale": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_void_p, c_void_p, c_uint64, c_void_p]),
     "kam_dists_host": (c_int, [c_void_p, c_int, c_uint32, c_uint64, ctypes.c_uint, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
 }
