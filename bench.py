@@ -23,6 +23,8 @@ One step = one pass of the `kmers` hot path over the whole batch.
   distances : secondary lines -- pairs/s of the distance kernels on vectors of the same shape
   kmers_other_shapes : secondary lines -- the short-read (configs[3]) and megabase (configs[4]) shapes
   mds : secondary line -- the mds step at n = 10 000 with the reference's numpy/ARPACK mds() beside it
+  classify_preprocess : secondary line -- StandardScaler + TruncatedSVD (classify.py:29-50) on 10 000 count
+          vectors of 4^6 bins, with scikit-learn on the host cores beside it
 
 With --gpus N (torchrun, one rank per GPU) every rank processes its own 10 000-sequence shard
 (sequences are independent: no data-path collective, weak scaling); value = all ranks' vectors /
@@ -254,6 +256,22 @@ def distances_cpu_baseline(n=4096, k=6, length=9000):
                                              "definition of the metric; not in the reference)" % m}}
 
 
+def preprocess_cpu_baseline(host, sample_n=2000):
+    """the reference's two normalisers (classify.py:29-50) as scikit-learn runs them on the host cores
+    (`kind: reference`: scikit-learn IS the reference's implementation of this arithmetic), on the first
+    sample_n vectors of the set the GPU line used"""
+    from sklearn.decomposition import TruncatedSVD
+    from sklearn.preprocessing import StandardScaler
+    x = host[:sample_n].astype(np.float64)
+    ncomp = int(np.ceil(sum(np.count_nonzero(f) for f in x[:256]) / 256 * 0.1))
+    t0 = time.perf_counter()
+    TruncatedSVD(n_components=ncomp, random_state=0).fit_transform(StandardScaler(with_mean=False).fit_transform(x))
+    dt = time.perf_counter() - t0
+    return {"value": len(x) / dt, "unit": "vectors/s", "kind": "reference", "cores": len(os.sched_getaffinity(0)),
+            "ms": dt * 1e3, "sample": "first %d of the %d vectors: sklearn StandardScaler(with_mean=False) + "
+            "TruncatedSVD(n_components=%d) fit_transform" % (len(x), len(host), ncomp)}
+
+
 def distance_lines(torch, dev, hbm_peak, tf_peak):
     """Secondary measurements: pairs/s of the distance kernels (filled in as they are built)."""
     try:
@@ -443,6 +461,14 @@ def main():
                     line["mds"]["cpu_baseline"] = mds_cpu_baseline(tri_sample, 10000, 10)
             except Exception as e:
                 line["mds"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            try:                                   # classify pre-processing
+                from kameris_b200 import preprocess_bench
+                torch.cuda.empty_cache()
+                line["classify_preprocess"], host = preprocess_bench.run(torch, dev, hbm_peak)
+                if not args.no_cpu_baseline:
+                    line["classify_preprocess"]["cpu_baseline"] = preprocess_cpu_baseline(host)
+            except Exception as e:
+                line["classify_preprocess"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
     if world > 1:
         dist_pg.destroy_process_group()

@@ -254,7 +254,7 @@ constexpr int FT = 64, FK = 16, FPAD = 2;
 __device__ __forceinline__ long long tri_base_f(long long n, long long i) { return n * i - i * (i + 3) / 2 - 1; }
 
 template <typename T>
-__global__ void __launch_bounds__(256) gram_f64_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
+__global__ void __launch_bounds__(256, 3) gram_f64_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
                                                        uint32_t row_begin, uint32_t row_end,
                                                        const RowK *__restrict__ rk, GramOut go) {
     const uint32_t bi = blockIdx.y, bj = blockIdx.x;
@@ -264,24 +264,28 @@ __global__ void __launch_bounds__(256) gram_f64_kernel(const T *__restrict__ x, 
     __shared__ __align__(16) double As[2][FK][FT + FPAD];
     __shared__ __align__(16) double Bs[2][FK][FT + FPAD];
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;   // this thread stages 4 consecutive k of one row
-    const bool a_ok = r0 + lr < n, b_ok = c0 + lr < n;
-    const T *pa = x + (uint64_t)(a_ok ? r0 + lr : 0) * ld;
-    const T *pb = x + (uint64_t)(b_ok ? c0 + lr : 0) * ld;
+    // staging: thread (lk, lr) loads element k0 + lk of rows lr, lr + 16, lr + 32, lr + 48 -- a half-warp reads
+    // 16 consecutive elements of one row
+    const int lk = threadIdx.x & 15, lr = threadIdx.x >> 4;
     T ra[4], rb[4];
+    const T *pa = x + (uint64_t)(r0 + lr) * ld + lk, *pb = x + (uint64_t)(c0 + lr) * ld + lk;
+    const uint64_t ld16 = 16 * ld;
+    uint32_t ok = 0;   // bit i: row lr + 16 i of the A tile exists; bit 4 + i: of the B tile
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ok |= (r0 + lr + 16 * i < n ? 1u << i : 0u) | (c0 + lr + 16 * i < n ? 16u << i : 0u);
     auto gload = [&](uint64_t k0) {
+        const bool kin = k0 + lk < d;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const uint64_t k = k0 + lk + i;
-            ra[i] = (a_ok && k < d) ? __ldg(pa + k) : (T)0;
-            rb[i] = (b_ok && k < d) ? __ldg(pb + k) : (T)0;
+            ra[i] = (kin && (ok >> i & 1u)) ? __ldg(pa + k0 + i * ld16) : (T)0;
+            rb[i] = (kin && (ok >> (4 + i) & 1u)) ? __ldg(pb + k0 + i * ld16) : (T)0;
         }
     };
     auto sstore = [&](int buf) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            As[buf][lk + i][lr] = (double)ra[i];
-            Bs[buf][lk + i][lr] = (double)rb[i];
+            As[buf][lk][lr + 16 * i] = (double)ra[i];
+            Bs[buf][lk][lr + 16 * i] = (double)rb[i];
         }
     };
     double acc[4][4];
@@ -290,6 +294,8 @@ __global__ void __launch_bounds__(256) gram_f64_kernel(const T *__restrict__ x, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
+    // thread (ty, tx) owns rows ty*4 .. ty*4+3 and columns tx*2, tx*2+1, 32+tx*2, 32+tx*2+1: the 16 lanes of a
+    // half-warp read 16 consecutive 16-byte pieces of a B row (no bank conflicts), the A values are broadcasts
     const uint64_t nk = (d + FK - 1) / FK;
     gload(0);
     sstore(0);
@@ -301,8 +307,8 @@ __global__ void __launch_bounds__(256) gram_f64_kernel(const T *__restrict__ x, 
         for (int k = 0; k < FK; ++k) {
             const double2 a01 = *reinterpret_cast<const double2 *>(&As[buf][k][ty * 4]);
             const double2 a23 = *reinterpret_cast<const double2 *>(&As[buf][k][ty * 4 + 2]);
-            const double2 b01 = *reinterpret_cast<const double2 *>(&Bs[buf][k][tx * 4]);
-            const double2 b23 = *reinterpret_cast<const double2 *>(&Bs[buf][k][tx * 4 + 2]);
+            const double2 b01 = *reinterpret_cast<const double2 *>(&Bs[buf][k][tx * 2]);
+            const double2 b23 = *reinterpret_cast<const double2 *>(&Bs[buf][k][32 + tx * 2]);
             const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(256) gram_f64_kernel(const T *__restrict__ x, 
         const RowK ri = rk[gi];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t gj = c0 + tx * 4 + j;
+            const uint32_t gj = c0 + (j < 2 ? tx * 2 + j : 32 + tx * 2 + (j - 2));
             if (gj >= n || gj <= gi) continue;
             gram_store(go, base + gj, acc[i][j], ri, rk[gj]);
         }
