@@ -300,8 +300,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # ONE JSON line on stdout: libraries that print to file descriptor 1 (MAGMA / NCCL banners) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         run_reference(args, rank, world)
+        sys.stdout.flush()
         return
 
     import torch
@@ -470,6 +476,7 @@ def main():
             except Exception as e:
                 line["classify_preprocess"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist_pg.destroy_process_group()
 

@@ -99,8 +99,14 @@ def svd_flip_v(u, vt):
 
 
 def _lu_normalizer(y):
-    """scipy.linalg.lu(y, permute_l=True)[0] = P L"""
-    p, l, _ = torch.linalg.lu(y)
+    """scipy.linalg.lu(y, permute_l=True)[0] = P L  (cuSOLVER getrf: MAGMA's batched LU prints a banner on
+    stdout for matrices of this size)"""
+    prev = torch.backends.cuda.preferred_linalg_library()
+    torch.backends.cuda.preferred_linalg_library("cusolver")
+    try:
+        p, l, _ = torch.linalg.lu(y)
+    finally:
+        torch.backends.cuda.preferred_linalg_library(prev)
     return p @ l
 
 
