@@ -29,28 +29,42 @@ __device__ __forceinline__ bool is_nan_elem(T v) {
     else return false;
 }
 
+// VEC adjacent columns per thread, fetched with one VEC*sizeof(T)-byte load (uint16: 2, uint8: 4), so that a
+// warp reads 128 bytes of a row per instruction
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) ColPack {
+    T v[VEC];
+};
+
 // pass 1: per-slab column sums and non-NaN counts
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(CS_THREADS) col_sum_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
                                                              uint32_t rows_per_slab, double *__restrict__ psum,
                                                              uint32_t *__restrict__ pcnt) {
-    const uint64_t c = (uint64_t)blockIdx.x * CS_THREADS + threadIdx.x;
+    const uint64_t c = ((uint64_t)blockIdx.x * CS_THREADS + threadIdx.x) * VEC;
     if (c >= d) return;
     const uint32_t r0 = blockIdx.y * rows_per_slab;
     const uint32_t r1 = min(n, r0 + rows_per_slab);
-    double s = 0.0;
-    uint32_t cnt = 0;
+    double s[VEC];
+    uint32_t cnt[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s[j] = 0.0, cnt[j] = 0;
     const T *p = x + (uint64_t)r0 * ld + c;
-#pragma unroll 4
+#pragma unroll 8
     for (uint32_t r = r0; r < r1; ++r, p += ld) {
-        const T v = __ldg(p);
-        if (!is_nan_elem<T>(v)) {
-            s += (double)v;
-            ++cnt;
-        }
+        const ColPack<T, VEC> w = *reinterpret_cast<const ColPack<T, VEC> *>(p);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+            if (!is_nan_elem<T>(w.v[j])) {
+                s[j] += (double)w.v[j];
+                ++cnt[j];
+            }
     }
-    psum[(uint64_t)blockIdx.y * d + c] = s;
-    pcnt[(uint64_t)blockIdx.y * d + c] = cnt;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        psum[(uint64_t)blockIdx.y * d + c + j] = s[j];
+        pcnt[(uint64_t)blockIdx.y * d + c + j] = cnt[j];
+    }
 }
 
 __global__ void col_mean_kernel(const double *__restrict__ psum, const uint32_t *__restrict__ pcnt, uint32_t slabs,
@@ -68,28 +82,34 @@ __global__ void col_mean_kernel(const double *__restrict__ psum, const uint32_t 
 }
 
 // pass 2: per-slab sums of (x - T) and (x - T)^2
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(CS_THREADS) col_dev_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
                                                              uint32_t rows_per_slab, const double *__restrict__ mean,
                                                              double *__restrict__ pcorr, double *__restrict__ psq) {
-    const uint64_t c = (uint64_t)blockIdx.x * CS_THREADS + threadIdx.x;
+    const uint64_t c = ((uint64_t)blockIdx.x * CS_THREADS + threadIdx.x) * VEC;
     if (c >= d) return;
     const uint32_t r0 = blockIdx.y * rows_per_slab;
     const uint32_t r1 = min(n, r0 + rows_per_slab);
-    const double m = mean[c];
-    double corr = 0.0, sq = 0.0;
+    double m[VEC], corr[VEC], sq[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) m[j] = mean[c + j], corr[j] = 0.0, sq[j] = 0.0;
     const T *p = x + (uint64_t)r0 * ld + c;
-#pragma unroll 4
+#pragma unroll 8
     for (uint32_t r = r0; r < r1; ++r, p += ld) {
-        const T v = __ldg(p);
-        if (!is_nan_elem<T>(v)) {
-            const double t = (double)v - m;
-            corr += t;
-            sq = __dadd_rn(sq, __dmul_rn(t, t));   // temp **= 2 is a rounded product: no fused multiply-add
-        }
+        const ColPack<T, VEC> w = *reinterpret_cast<const ColPack<T, VEC> *>(p);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+            if (!is_nan_elem<T>(w.v[j])) {
+                const double t = (double)w.v[j] - m[j];
+                corr[j] += t;
+                sq[j] = __dadd_rn(sq[j], __dmul_rn(t, t));   // temp **= 2 is a rounded product: no fused multiply-add
+            }
     }
-    pcorr[(uint64_t)blockIdx.y * d + c] = corr;
-    psq[(uint64_t)blockIdx.y * d + c] = sq;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        pcorr[(uint64_t)blockIdx.y * d + c + j] = corr[j];
+        psq[(uint64_t)blockIdx.y * d + c + j] = sq[j];
+    }
 }
 
 __global__ void col_var_kernel(const double *__restrict__ pcorr, const double *__restrict__ psq, uint32_t slabs, uint64_t d,
@@ -105,7 +125,7 @@ __global__ void col_var_kernel(const double *__restrict__ pcorr, const double *_
     var[c] = (sq - corr * corr / nn) / nn;
 }
 
-// transform: out = x / scale, float64
+// transform: out = x / scale, float64.  Four rows per trip: the loads are issued before the (long) divisions
 template <typename T>
 __global__ void __launch_bounds__(CS_THREADS) col_scale_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
                                                                const double *__restrict__ scale, double *__restrict__ out,
@@ -113,11 +133,36 @@ __global__ void __launch_bounds__(CS_THREADS) col_scale_kernel(const T *__restri
     const uint64_t c = (uint64_t)blockIdx.x * CS_THREADS + threadIdx.x;
     if (c >= d) return;
     const double s = scale[c];
-    for (uint32_t r = blockIdx.y; r < n; r += gridDim.y) out[(uint64_t)r * out_ld + c] = (double)__ldg(x + (uint64_t)r * ld + c) / s;
+    // x / s, correctly rounded, without the general division sequence (the kernel was issue-bound on it): with
+    // rc = RN(1/s), q = RN(x rc), the exact remainder e = x - q s (one FMA) and q' = RN(q + e rc) is the
+    // correctly rounded quotient (Markstein's final step; what the hardware-assisted sequence ends with too).
+    // Only for a normal divisor and finite operands well inside the exponent range -- anything else divides.
+    const double rc = __drcp_rn(s);
+    const bool fast = s > 1e-100 && s < 1e100;
+    const uint32_t gy = gridDim.y;
+    for (uint32_t r = blockIdx.y; r < n; r += 4 * gy) {
+        T v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = r + i * gy < n ? __ldg(x + (uint64_t)(r + i * gy) * ld + c) : (T)0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (r + i * gy >= n) continue;
+            const double a = (double)v[i];
+            double q;
+            if (fast && (a == 0.0 || (fabs(a) > 1e-100 && fabs(a) < 1e100))) {
+                q = __dmul_rn(a, rc);
+                const double e = __fma_rn(-q, s, a);
+                q = __fma_rn(e, rc, q);
+            } else {
+                q = a / s;          // NaN, infinities, extreme magnitudes
+            }
+            __stcs(out + (uint64_t)(r + i * gy) * out_ld + c, q);
+        }
+    }
 }
 
 inline uint32_t slab_count(uint32_t n, uint64_t d) {
-    const uint64_t col_blocks = (d + CS_THREADS - 1) / CS_THREADS;
+    const uint64_t col_blocks = (d + CS_THREADS - 1) / CS_THREADS;   // (an upper bound when columns are vectorised)
     uint64_t s = ((uint64_t)kam_sm_count() * 8 + col_blocks - 1) / col_blocks;   // ~8 CTAs per SM in flight
     if (s > n) s = n;
     if (s > 4096) s = 4096;
@@ -125,23 +170,35 @@ inline uint32_t slab_count(uint32_t n, uint64_t d) {
     return (uint32_t)s;
 }
 
-template <typename T>
-int run_stats(const void *x, uint32_t n, uint64_t d, uint64_t ld, double *mean, double *var, long long *count, void *ws,
-              cudaStream_t st) {
+template <typename T, int VEC>
+int run_stats_v(const void *x, uint32_t n, uint64_t d, uint64_t ld, double *mean, double *var, long long *count, void *ws,
+                cudaStream_t st) {
     const uint32_t slabs = slab_count(n, d);
     const uint32_t rps = (n + slabs - 1) / slabs;
     const uint32_t used = (n + rps - 1) / rps;          // slabs that hold rows
     double *pa = (double *)ws;
     double *pb = pa + (size_t)slabs * d;
     uint32_t *pc = (uint32_t *)(pb + (size_t)slabs * d);
-    const dim3 grid((unsigned)((d + CS_THREADS - 1) / CS_THREADS), used);
+    const uint64_t threads = (d + VEC - 1) / VEC;
+    const dim3 grid((unsigned)((threads + CS_THREADS - 1) / CS_THREADS), used);
     const unsigned cb = (unsigned)((d + 255) / 256);
-    col_sum_kernel<T><<<grid, CS_THREADS, 0, st>>>((const T *)x, n, d, ld, rps, pa, pc);
+    col_sum_kernel<T, VEC><<<grid, CS_THREADS, 0, st>>>((const T *)x, n, d, ld, rps, pa, pc);
     col_mean_kernel<<<cb, 256, 0, st>>>(pa, pc, used, d, mean, count);
-    col_dev_kernel<T><<<grid, CS_THREADS, 0, st>>>((const T *)x, n, d, ld, rps, mean, pa, pb);
+    col_dev_kernel<T, VEC><<<grid, CS_THREADS, 0, st>>>((const T *)x, n, d, ld, rps, mean, pa, pb);
     col_var_kernel<<<cb, 256, 0, st>>>(pa, pb, used, d, count, var);
     KAM_CUDA(cudaGetLastError());
     return KAM_OK;
+}
+
+template <typename T>
+int run_stats(const void *x, uint32_t n, uint64_t d, uint64_t ld, double *mean, double *var, long long *count, void *ws,
+              cudaStream_t st) {
+    constexpr int VEC = sizeof(T) < 4 ? 4 / (int)sizeof(T) : 1;
+    if constexpr (VEC > 1) {
+        if (d % VEC == 0 && ld % VEC == 0 && ((uintptr_t)x % (VEC * sizeof(T))) == 0)
+            return run_stats_v<T, VEC>(x, n, d, ld, mean, var, count, ws, st);
+    }
+    return run_stats_v<T, 1>(x, n, d, ld, mean, var, count, ws, st);
 }
 
 template <typename T>

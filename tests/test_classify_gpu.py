@@ -67,7 +67,8 @@ def C():
 
 
 @needs_gpu
-@pytest.mark.parametrize("case", ["u16_k6", "u32_k4", "f64_freq_k5", "f32_freq_k5", "f64_nan_const", "tall_thin", "one_row"])
+@pytest.mark.parametrize("case", ["u16_k6", "u32_k4", "f64_freq_k5", "f32_freq_k5", "f64_nan_const", "tall_thin", "one_row",
+                                  "u8_vec4", "u8_odd"])
 def test_standard_scaler_vs_sklearn(C, case):
     rng = np.random.Generator(np.random.PCG64(5))
     if case == "u16_k6":
@@ -83,6 +84,8 @@ def test_standard_scaler_vs_sklearn(C, case):
         x[:, 5] = 2.5                              # constant column: scale 1
         x[:, 6] = 0.0
         x[:, 8] = 1e9 + rng.standard_normal(70) * 1e-9      # indistinguishable from a constant: scale 1
+    elif case in ("u8_vec4", "u8_odd"):            # 4 columns per thread / the one-column fallback
+        x = rng.integers(0, 200, size=(777, 1028 if case == "u8_vec4" else 1027)).astype(np.uint8)
     elif case == "tall_thin":
         x = rng.integers(0, 50, size=(5000, 3)).astype(np.uint16)
     else:
@@ -173,3 +176,36 @@ def test_scaler_full_size_property(C):
     torch.testing.assert_close(t.var(dim=0, unbiased=False), torch.ones(4096, dtype=torch.float64, device="cuda"),
                                rtol=1e-10, atol=0)
     torch.testing.assert_close(t.mean(dim=0), mean / scale, rtol=1e-10, atol=0)
+
+
+@needs_gpu
+@pytest.mark.parametrize("dtype", ["u16", "f64", "f32"])
+def test_scale_columns_is_a_correctly_rounded_division(C, dtype):
+    """kam_col_scale forms x / scale from a reciprocal and one exact-remainder correction: the results must be
+    the IEEE quotients bit for bit (checked against the device's own division), including zeros, NaN,
+    infinities, denormal and huge operands and scales."""
+    from kameris_b200 import preprocess as P
+    g = torch.Generator(device="cuda")
+    g.manual_seed(9)
+    n, d = 3000, 515
+    if dtype == "u16":
+        x = torch.randint(0, 65536, (n, d), device="cuda", generator=g, dtype=torch.int32).to(torch.uint16)
+        xd = x.to(torch.int32).to(torch.float64)
+    else:
+        x = torch.randn((n, d), device="cuda", generator=g, dtype=torch.float64) * 10 ** torch.randint(
+            -12, 12, (n, d), device="cuda", generator=g).to(torch.float64)
+        x[5, :] = 0.0
+        x[6, 3] = float("nan")
+        x[7, 4] = float("inf")
+        x[8, 5] = 1e-310
+        x[9, 6] = 1e300
+        if dtype == "f32":
+            x = x.to(torch.float32)
+        xd = x.to(torch.float64)
+    scale = torch.rand(d, device="cuda", generator=g, dtype=torch.float64) * 10 ** torch.randint(
+        -6, 6, (d,), device="cuda", generator=g).to(torch.float64) + 1e-9
+    scale[0], scale[1], scale[2] = 1.0, 1e-200, 1e200
+    got = P.scale_columns(x, scale)
+    want = xd / scale
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
