@@ -80,7 +80,10 @@ class StandardScaler(TransformerMixin, BaseEstimator):
         if x.shape[1] != self.n_features_in_:
             raise ValueError("X has %d features, but StandardScaler is expecting %d features as input."
                              % (x.shape[1], self.n_features_in_))
-        scale = self.scale_device_ if self.scale_device_.device == x.device else self.scale_device_.to(x.device)
+        scale = getattr(self, "scale_device_", None)
+        if scale is None or scale.device != x.device:      # unpickled model, or another GPU: upload once
+            import torch
+            scale = self.scale_device_ = torch.from_numpy(np.asarray(self.scale_, dtype=np.float64)).to(x.device)
         out = P.scale_columns(x, scale)
         return out if self.device_output else out.cpu().numpy()
 
@@ -89,11 +92,6 @@ class StandardScaler(TransformerMixin, BaseEstimator):
         state.pop("scale_device_", None)
         return state
 
-    def __setstate__(self, state):
-        self.__dict__.update(state)
-        if "scale_" in state:
-            import torch
-            self.scale_device_ = torch.from_numpy(np.asarray(state["scale_"], dtype=np.float64)).cuda()
 
 
 class TruncatedSVD(TransformerMixin, BaseEstimator):
@@ -135,7 +133,12 @@ class TruncatedSVD(TransformerMixin, BaseEstimator):
         if x.shape[1] != self.n_features_in_:
             raise ValueError("X has %d features, but TruncatedSVD is expecting %d features as input."
                              % (x.shape[1], self.n_features_in_))
-        return (x @ self.components_device_.T).cpu().numpy()
+        comp = getattr(self, "components_device_", None)
+        if comp is None or comp.device != x.device:          # unpickled model, or another GPU: upload once
+            import torch
+            comp = self.components_device_ = torch.from_numpy(
+                np.asarray(self.components_, dtype=np.float64)).to(x.device)
+        return (x @ comp.T).cpu().numpy()
 
     def inverse_transform(self, X):
         return np.dot(X, self.components_)
@@ -145,28 +148,17 @@ class TruncatedSVD(TransformerMixin, BaseEstimator):
         state.pop("components_device_", None)
         return state
 
-    def __setstate__(self, state):
-        self.__dict__.update(state)
-        if "components_" in state:
-            import torch
-            self.components_device_ = torch.from_numpy(np.asarray(state["components_"], dtype=np.float64)).cuda()
 
 
 def build_pipeline(classifier_factory, num_features, options):
-    """classify.py:29-50 with the two normalisers on the device."""
-    normalize_features = not options.get('skip_normalization', False)
-    dim_reduce_fraction = options.get('dim_reduce_fraction', 0.1)
-
-    normalizers = []
-    if normalize_features:
-        # scale each feature dimension to unit variance (no mean scaling: classify.py:37-40)
-        normalizers.append(('scaler', StandardScaler(with_mean=False, device_output=True)))
-        # reduce dimensionality to some fraction of its original
-        normalizers.append(
-            ('dim_reducer',
-             TruncatedSVD(n_components=int(
-                np.ceil(num_features * dim_reduce_fraction)
-             )))
-        )
-
-    return Pipeline(normalizers + [('classifier', classifier_factory())])
+    """Same contract as classify.py:29-50: options `skip_normalization` (default False) and
+    `dim_reduce_fraction` (default 0.1); unless normalisation is skipped, the classifier is preceded by the
+    unit-variance scaler (no centring) and by a truncated SVD keeping ceil(num_features * fraction)
+    components, here both on the device with the scaled matrix handed over without leaving it."""
+    steps = []
+    if not options.get('skip_normalization', False):
+        keep = int(np.ceil(num_features * options.get('dim_reduce_fraction', 0.1)))
+        steps += [('scaler', StandardScaler(with_mean=False, device_output=True)),
+                  ('dim_reducer', TruncatedSVD(n_components=keep))]
+    steps.append(('classifier', classifier_factory()))
+    return Pipeline(steps)
