@@ -828,6 +828,8 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
         KAM_CUDA(cudaMemsetAsync(w.flags, 0, 64, st));
         if ((rc = prepass_dispatch(d_x, elem, n, d, ld, true, w.h, w.S, w.G, w.flags, st))) return rc;
         if ((rc = read_flags(w.flags, hflags, st))) return rc;
+        if (is_float && hflags[2] != 0)   // not frequency vectors: no second sweep, straight to the float64 Gram
+            return kam_float_gram_tri(d_x, elem, n, d, ld, row_begin, row_end, w.rk, go, st);
         have_i8 = hflags[0] <= MAX_I8_COUNT && hflags[1] < MAX_I8_GII;
     }
     if (!have_i8 && (g_force_f16 || (hflags[0] <= MAX_F16_COUNT && hflags[1] < MAX_F16_GII))) {

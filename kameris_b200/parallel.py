@@ -194,6 +194,8 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
     dev = x_local.device
     n_loc, d = x_local.shape
     elem = D._ELEM[x_local.dtype]
+    if x_local.dtype in (torch.float32, torch.float64):
+        euclid_on_freq = True       # frequency rows: euclid between the rows as stored (kam_gram_tri does the same)
     stream = torch.cuda.current_stream(dev).cuda_stream
     dpad = int(lib.kam_gram_dpad(d))
     bits = {"euclid": _lib.KAM_M_EUCLID, "cosine": _lib.KAM_M_COSINE, "pearson": _lib.KAM_M_PEARSON}

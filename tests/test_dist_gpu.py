@@ -368,3 +368,20 @@ def test_gram_on_frequency_rows_row_ranges_and_f16(D):
     ref = D.gram_tri(_dev(c), ("euclid", "cosine", "pearson"), euclid_on_freq=True)
     for m in got:
         assert torch.equal(got[m], ref[m]), m
+
+
+def test_gram_ring_on_frequency_rows(D):
+    """the block interface (kam_gram_prepare) recovers the counts of float64 frequency rows too: the ring's
+    block equals the packed triangle of the count matrix (euclid between frequency vectors whatever the
+    caller's flag); rows that are not frequency vectors are an error there (no float64 block kernel)."""
+    from kameris_b200 import parallel
+    x = _counts(150, 3000, 7, seed=23)
+    f = _dev(_freq(x, np.float64))
+    blocks, counts = parallel.gram_ring(f, ("cosine", "euclid"), euclid_on_freq=False)
+    ref = D.gram_tri(_dev(x), ("cosine", "euclid"), euclid_on_freq=True)
+    iu = np.triu_indices(150, 1)
+    for m in ("cosine", "euclid"):
+        assert np.array_equal(blocks[0][m].cpu().numpy()[iu], ref[m].cpu().numpy())
+    bad = np.abs(np.random.Generator(np.random.PCG64(1)).standard_normal((20, 64)))
+    with pytest.raises(ValueError):
+        parallel.gram_ring(_dev(bad), ("cosine",))
