@@ -156,6 +156,15 @@ int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_
 /* A.1: first FASTA record of a file image (generation_cgr @0x10000d691-0x10000d83e).  Writes at
  * most n bytes to out; returns the record length or -1 when the file holds no record. */
 int64_t kam_fasta_record0(const char *buf, size_t n, char *out);
+/* The same for a whole directory listing, on `threads` host threads (0 = all; the task scheme of
+ * mmg::ParallelExecutor @0x10001a6f0): kam_fasta_file_sizes stats every path (a non-regular entry has
+ * size 0); with file_offsets = the exclusive prefix sum of those sizes (n+1 entries) kam_fasta_read_files
+ * reads the files and leaves record[0] of file i at h_chars[start[i] .. start[i+1]) -- contiguous, in path
+ * order, ready for kam_kmers_host.  h_chars needs file_offsets[n] bytes.  A path that cannot be read, is not
+ * a regular file or holds no record fails the call (KAM_E_INVALID, *bad_index = the first such path). */
+int kam_fasta_file_sizes(const char *const *paths, uint32_t n, uint64_t *h_sizes, int threads);
+int kam_fasta_read_files(const char *const *paths, uint32_t n, const uint64_t *file_offsets, uint8_t *h_chars,
+                         uint64_t *h_start, int threads, uint32_t *bad_index);
 
 /* ---------------------------------------------------------------------------------------------
  * Distances.  x is a row-major n x d matrix (row stride `ld` elements) of element type `elem`.

@@ -40,6 +40,8 @@ SIGNATURES = {
     "kam_normalize": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_int, c_void_p, c_uint64, c_void_p]),
     "kam_kmers_host": (c_int, [c_void_p, c_void_p, c_uint32, c_int, c_int, c_int, c_void_p]),
     "kam_fasta_record0": (ctypes.c_int64, [c_void_p, c_size_t, c_void_p]),
+    "kam_fasta_file_sizes": (c_int, [c_void_p, c_uint32, c_void_p, c_int]),
+    "kam_fasta_read_files": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "kam_manhattan_workspace_bytes": (c_size_t, [c_uint32, c_uint64]),
     "kam_manhattan_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),

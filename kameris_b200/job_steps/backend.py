@@ -40,27 +40,47 @@ def list_input_files(directory):
     return sorted(paths, key=lambda p: os.fsencode(p))
 
 
-def _read_record(path):
+def read_records_packed(paths, threads=0):
+    """record[0] of every file (A.1), in the order of `paths`, as ONE buffer: (chars uint8[total], start
+    uint64[n+1]) with record i at chars[start[i]:start[i+1]] -- the layout kam_kmers_host takes.  The files are
+    read and the records extracted by the library's host thread pool (kam_fasta_read_files, all cores by
+    default), not by Python.  A file without a record raises (the reference reads begin() of an empty vector
+    there), and so does an entry that is not a readable regular file."""
     lib = _lib.load()
-    with open(path, 'rb') as f:
-        data = f.read()
-    out = ctypes.create_string_buffer(max(len(data), 1))
-    n = lib.kam_fasta_record0(data, len(data), out)     # ctypes releases the GIL during the call
-    if n < 0:
-        raise ValueError('no FASTA record in "%s"' % path)
-    return out.raw[:n]
+    n = len(paths)
+    start = np.zeros(n + 1, dtype=np.uint64)
+    if n == 0:
+        return np.zeros(0, dtype=np.uint8), start
+    enc = [os.fsencode(p) for p in paths]
+    arr = (ctypes.c_char_p * n)(*enc)
+    sizes = np.zeros(n, dtype=np.uint64)
+    if lib.kam_fasta_file_sizes(arr, n, sizes.ctypes.data, threads) != 0:
+        raise OSError(lib.kam_last_error().decode(errors='replace'))
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(sizes, out=offs[1:])
+    chars = np.empty(int(offs[-1]) + 16, dtype=np.uint8)
+    bad = ctypes.c_uint32(0)
+    if lib.kam_fasta_read_files(arr, n, offs.ctypes.data, chars.ctypes.data, start.ctypes.data, threads,
+                                ctypes.byref(bad)) != 0:
+        msg = lib.kam_last_error().decode(errors='replace')
+        raise (ValueError if msg.startswith('no FASTA record') else OSError)(msg)
+    return chars[:int(start[-1])], start
 
 
-def read_records(paths, threads=None):
-    """record[0] of every file (A.1), in the order of `paths`.  A file without a record raises (the
-    reference reads begin() of an empty vector there).  Files are read by a small thread pool: both
-    the file reads and the record extraction run outside the GIL."""
-    if len(paths) < 8:
-        return [_read_record(p) for p in paths]
-    from concurrent.futures import ThreadPoolExecutor
-    workers = threads or min(32, (os.cpu_count() or 4))
-    with ThreadPoolExecutor(max_workers=workers) as pool:
-        return list(pool.map(_read_record, paths, chunksize=64))
+def read_records(paths, threads=0):
+    """record[0] of every file as a list of bytes objects (see read_records_packed)."""
+    chars, start = read_records_packed(paths, threads)
+    raw = chars.tobytes()
+    return [raw[int(start[i]):int(start[i + 1])] for i in range(len(paths))]
+
+
+def _pack_records(records):
+    """list of bytes -> (chars, start) like read_records_packed"""
+    n = len(records)
+    lens = np.fromiter((len(r) for r in records), dtype=np.uint64, count=n)
+    start = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=start[1:])
+    return np.frombuffer(b''.join(records), dtype=np.uint8), start
 
 
 def kmers_from_records(records, k, bits_per_element, mode):
@@ -73,10 +93,7 @@ def kmers_from_records(records, k, bits_per_element, mode):
     if bits_per_element not in (16, 32):
         raise ValueError('bits per element must be 16 or 32')
     n = len(records)
-    lens = np.fromiter((len(r) for r in records), dtype=np.uint64, count=n)
-    start = np.zeros(n + 1, dtype=np.uint64)
-    np.cumsum(lens, out=start[1:])
-    chars = np.frombuffer(b''.join(records), dtype=np.uint8)
+    chars, start = _pack_records(records)
     if mode == 'frequencies':
         kind, dt = _lib.KAM_OUT_FREQ_F64, torch.float64
     else:
@@ -97,7 +114,7 @@ CHUNK_BYTES = 256 << 20        # pinned staging per buffer; two buffers alternat
 
 
 def kmers_to_file(records, k, bits_per_element, mode, output_file, row_offset=0, total_rows=None, create=True):
-    """records -> `.mm-repr`, streamed: the batch is cut into chunks of rows; while chunk c is being
+    """records (a list of bytes, or the (chars, start) pair of read_records_packed) -> `.mm-repr`, streamed: the batch is cut into chunks of rows; while chunk c is being
     written to the file from one pinned buffer, chunk c+1 is produced (H2D, kernels, D2H inside
     kam_kmers_host, which releases the GIL) into the other.  No buffer of the whole result exists.
 
@@ -111,11 +128,8 @@ def kmers_to_file(records, k, bits_per_element, mode, output_file, row_offset=0,
         raise ValueError('k is too large to fit in the index')
     if bits_per_element not in (16, 32):
         raise ValueError('bits per element must be 16 or 32')
-    n, d = len(records), 4 ** k
-    lens = np.fromiter((len(r) for r in records), dtype=np.uint64, count=n)
-    start = np.zeros(n + 1, dtype=np.uint64)
-    np.cumsum(lens, out=start[1:])
-    chars = np.frombuffer(b''.join(records), dtype=np.uint8)
+    chars, start = records if isinstance(records, tuple) else _pack_records(records)
+    n, d = len(start) - 1, 4 ** k
     if mode == 'frequencies':
         kind, tdt, ndt = _lib.KAM_OUT_FREQ_F64, torch.float64, np.float64
     else:
@@ -198,11 +212,11 @@ def kmers_to_file_sharded(paths, k, bits_per_element, mode, output_file, dist, p
         w.file.truncate(formats.REPR_HEADER + n * d * w.dtype.itemsize)
         w.file.close()
     dist.barrier()
-    records = read_records(paths[b:e])
     if produce is None:
-        kmers_to_file(records, k, bits_per_element, mode, output_file, row_offset=b, total_rows=n, create=False)
+        kmers_to_file(read_records_packed(paths[b:e]), k, bits_per_element, mode, output_file, row_offset=b,
+                      total_rows=n, create=False)
     else:
-        produce(records, b, n)
+        produce(read_records(paths[b:e]), b, n)
     dist.barrier()
     return b, e
 
@@ -220,12 +234,12 @@ def run_backend_kmers(options, exp_options):
             log.info('kmers: rank %d/%d wrote vectors [%d, %d) of %d in %.2f seconds', rank, world, b, e, len(paths),
                      time.time() - t0)
             return
-        records = read_records(paths)
+        records = read_records_packed(paths)
         kmers_to_file(records, options['k'], options['bits_per_element'], options['mode'], options['output_file'])
     except (_lib.KamError, ValueError, OSError) as e:
         log.error('kmers step failed: %s', e)
         raise subprocess.CalledProcessError(1, 'generation_cgr (kameris_b200)', str(e))
-    log.info('kmers: %d vectors of %d bins in %.2f seconds', len(records), 4 ** options['k'], time.time() - t0)
+    log.info('kmers: %d vectors of %d bins in %.2f seconds', len(paths), 4 ** options['k'], time.time() - t0)
 
 
 def requested_metrics(names):

@@ -166,3 +166,40 @@ def test_abi_argument_validation_without_gpu():
     assert lib.kam_manhattan_tri(p, 9, 10, 16, 16, 0, 10, p, p, 1 << 30, None) == -1
     assert lib.kam_dists_host(p, 1, 10, 16, 0, None, None, None, None, None) == -1                 # no metric asked
     assert lib.kam_gram_dpad(4 ** 9) == 4 ** 9 and lib.kam_gram_dpad(4) == 128
+
+
+def test_native_fasta_ingest_matches_record0_semantics(tmp_path):
+    """kam_fasta_read_files (host thread pool, no GPU): record[0] of every file exactly as the per-file A.1
+    restatement extracts it -- CRLF, blank lines, several records, header-less files, inner whitespace kept,
+    leading / trailing whitespace trimmed, no trailing newline, lower case kept -- contiguous, in path order."""
+    from kameris_b200.job_steps import backend
+    from oracle import oracle as O
+    from tests.helpers import synth_records
+    bodies = [b">a desc\nACGT\nACGT\n", b">a\r\nACGTN\r\nNNAC\r\n\r\n>b\r\nTTTT\r\n", b"ACGT\nAC GT\n", b"\n\n>x\n  acgtRY \t\nGG\n>y\nAA",
+              b">only\nA", b">h1\n>h2\nCCCC\n", b"  \t\n>z\n\nGATTACA\n\nTTTT\n", b"A" * 100000 + b"\n" + b"C" * 7]
+    bodies += [b">r%d\n" % i + b"\n".join(r[j:j + 61] for j in range(0, len(r), 61)) + b"\n"
+               for i, r in enumerate(synth_records(300, 700, seed=2, jitter=300, dirty=0.01))]
+    d = tmp_path / "fa"
+    d.mkdir()
+    for i, b in enumerate(bodies):
+        (d / ("s%04d.fasta" % i)).write_bytes(b)
+    paths = backend.list_input_files(str(d))
+    for threads in (0, 1, 3):
+        chars, start = backend.read_records_packed(paths, threads)
+        assert start[0] == 0 and len(start) == len(paths) + 1 and chars.size == start[-1]
+        for i, p in enumerate(paths):
+            with open(p, "rb") as f:
+                want = O.fasta_record0(f.read())
+            assert chars[int(start[i]):int(start[i + 1])].tobytes() == want, (threads, p)
+    assert backend.read_records(paths[:5]) == [O.fasta_record0(b) for b in bodies[:5]]
+    assert backend.read_records_packed([])[1].tolist() == [0]
+    # a file without a record, a missing file and a directory entry fail loudly, naming the first offender
+    (d / "s0003a.fasta").write_bytes(b">header only\n\n")
+    with pytest.raises(ValueError, match="s0003a.fasta"):
+        backend.read_records_packed(backend.list_input_files(str(d)))
+    (d / "s0003a.fasta").unlink()
+    with pytest.raises(OSError):
+        backend.read_records_packed(paths + [str(d / "missing.fasta")])
+    (d / "zdir").mkdir()
+    with pytest.raises(OSError, match="zdir"):
+        backend.read_records_packed(backend.list_input_files(str(d)))
