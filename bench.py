@@ -111,14 +111,19 @@ def reference_fill(O):
     """The reference's own CGR-fill machine code when oracle/_ref holds it (built in the container where
     /root/reference is mounted; see oracle/refcode/refcode.c), checked here against the port on a few
     records; None -> the port is timed instead."""
-    if O.refcode() is None:
+    try:
+        if O.refcode() is None:
+            return None
+        chars, start = synth_chars(8, SEQ_LEN, SEED + 1)
+        got = np.zeros((8, BINS), dtype=np.uint16)
+        O.refcode_cgr_batch(chars, start, K, got, threads=2)
+        if not np.array_equal(got, O.cgr_batch(chars, start, K, 16)):
+            print("bench: the reference's machine code and its port disagree; timing the port", file=sys.stderr)
+            return None
+        return O.refcode_cgr_batch
+    except (OSError, RuntimeError) as e:      # a baseline problem must not cost the bench line
+        print("bench: reference machine code unavailable (%s); timing the port" % e, file=sys.stderr)
         return None
-    chars, start = synth_chars(8, SEQ_LEN, SEED + 1)
-    got = np.zeros((8, BINS), dtype=np.uint16)
-    O.refcode_cgr_batch(chars, start, K, got, threads=2)
-    if not np.array_equal(got, O.cgr_batch(chars, start, K, 16)):
-        raise RuntimeError("the reference's machine code and its port disagree")
-    return O.refcode_cgr_batch
 
 
 def reference_kmers_step(O, chars, start, n, counts, threads, fill=None):
@@ -229,47 +234,44 @@ def mds_cpu_baseline(tri, n, dim, sample_n=3000):
 
 
 def distances_cpu_baseline(n=4096, k=6, length=9000):
-    """generation_dists' row tasks on all host threads (`kind: port`: the threaded restatement of the manhat /
-    info row lambda, generation_dists_mac_avx2 @0x10001b8c0; its machine code needs the whole executable image
-    and stays in the build container), on n count vectors of D = 4^k; and scipy's pdist for the metrics the
-    reference does not have."""
+    """generation_dists' row tasks on all host threads, on n count vectors of D = 4^k: the reference's OWN
+    row-lambda machine code (`kind: reference`: generation_dists_windows_avx2.exe VA 0x1400253c0, run from the
+    image the build extracted into oracle/_ref, oracle/refcode/refdists.c; checked here against the port) or,
+    without it, the threaded restatement (`kind: port`); and scipy's pdist for the metrics the reference does
+    not have."""
     from oracle import oracle as O
     threads = O.host_threads()
     chars, start = synth_chars(n, length, SEED + 7)
     x = O.cgr_batch(chars, start, k, 16)
     pairs = n * (n - 1) // 2
+    kind, run = "port", lambda m, i: O.dists_triangle(x, m, i, threads=threads)
+    try:
+        if O.refdists() is not None:
+            a = O.refdists_triangle(x[:64], True, True, threads=2)
+            b = O.dists_triangle(x[:64], True, True)
+            if np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)):
+                kind, run = "reference", lambda m, i: O.refdists_triangle(x, m, i, threads=threads)
+            else:
+                print("bench: the reference's row-task machine code and its port disagree; timing the port",
+                      file=sys.stderr)
+    except (OSError, RuntimeError) as e:      # a baseline problem must not cost the bench line
+        print("bench: reference machine code unavailable (%s); timing the port" % e, file=sys.stderr)
     t0 = time.perf_counter()
-    O.dists_triangle(x, True, False, threads=threads)
+    run(True, False)
     tm = time.perf_counter() - t0
     t0 = time.perf_counter()
-    O.dists_triangle(x, False, True, threads=threads)
+    run(False, True)
     ti = time.perf_counter() - t0
     m = 256
     t0 = time.perf_counter()
     O.cdist_triangle(x[:m], "cosine")
     tc = time.perf_counter() - t0
     sample = "%d count vectors (%d bp, k=%d, D=%d): %d pairs" % (n, length, k, 4 ** k, pairs)
-    return {"manhat": {"value": pairs / tm, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
-            "info": {"value": pairs / ti, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+    return {"manhat": {"value": pairs / tm, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
+            "info": {"value": pairs / ti, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
             "cosine_scipy_pdist": {"value": m * (m - 1) // 2 / tc, "unit": "pairs/s", "cores": 1, "kind": "port",
                                    "sample": "scipy.spatial.distance.pdist(cosine) on %d of those vectors (the "
                                              "definition of the metric; not in the reference)" % m}}
-
-
-def preprocess_cpu_baseline(host, sample_n=2000):
-    """the reference's two normalisers (classify.py:29-50) as scikit-learn runs them on the host cores
-    (`kind: reference`: scikit-learn IS the reference's implementation of this arithmetic), on the first
-    sample_n vectors of the set the GPU line used"""
-    from sklearn.decomposition import TruncatedSVD
-    from sklearn.preprocessing import StandardScaler
-    x = host[:sample_n].astype(np.float64)
-    ncomp = int(np.ceil(sum(np.count_nonzero(f) for f in x[:256]) / 256 * 0.1))
-    t0 = time.perf_counter()
-    TruncatedSVD(n_components=ncomp, random_state=0).fit_transform(StandardScaler(with_mean=False).fit_transform(x))
-    dt = time.perf_counter() - t0
-    return {"value": len(x) / dt, "unit": "vectors/s", "kind": "reference", "cores": len(os.sched_getaffinity(0)),
-            "ms": dt * 1e3, "sample": "first %d of the %d vectors: sklearn StandardScaler(with_mean=False) + "
-            "TruncatedSVD(n_components=%d) fit_transform" % (len(x), len(host), ncomp)}
 
 
 def distance_lines(torch, dev, hbm_peak, tf_peak):
@@ -442,7 +444,10 @@ def main():
             "host": {"cores": len(os.sched_getaffinity(0))},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+            try:
+                line["cpu_baseline"] = cpu_baseline()
+            except Exception as e:  # must not hide the headline
+                line["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
         del out, batch
         torch.cuda.empty_cache()
         if world == 1 and not args.no_extra:
@@ -457,7 +462,10 @@ def main():
             if d is not None:
                 line["distances"] = d
                 if not args.no_cpu_baseline and "error" not in d:
-                    d["cpu_baseline"] = distances_cpu_baseline()
+                    try:
+                        d["cpu_baseline"] = distances_cpu_baseline()
+                    except Exception as e:  # must not hide the headline
+                        d["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if world == 1 and not args.no_extra:
             try:                                   # the first consumer of the matrices
                 from kameris_b200 import mds_bench

@@ -141,6 +141,76 @@ def refcode():
     return _ref
 
 
+_REFD_SO = os.path.join(_HERE, "_ref", "librefdists.so")
+REFD_BLOB = os.path.join(_HERE, "_ref", "dists_image.bin")
+REFD_PE = "/root/reference/kameris/scripts/generation_dists_windows_avx2.exe"
+_refd = False
+
+
+def refdists_extract_blob():
+    """Build step (container with /root/reference): the loaded image of generation_dists_windows_avx2.exe
+    (sections at their virtual addresses) -> oracle/_ref/dists_image.bin, a build output that travels to the
+    GPU box like the .so files."""
+    lib = ctypes.CDLL(_REFD_SO)
+    rc = lib.refdists_extract(REFD_PE.encode(), REFD_BLOB.encode())
+    if rc != 0:
+        raise RuntimeError("refdists_extract failed: %d" % rc)
+    return REFD_BLOB
+
+
+def _has_avx2():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " avx2" in line
+    except OSError:
+        pass
+    return False
+
+
+def refdists():
+    """Runner for the reference's own manhat / info row-task machine code (oracle/refcode/refdists.c), from the
+    executable where /root/reference is mounted, else from the image the build extracted into oracle/_ref/.
+    None when neither is there, the host has no AVX2, or the image's preferred address range is taken."""
+    global _refd
+    if _refd is False:
+        _refd = None
+        if os.path.exists(_REFD_SO) and _has_avx2():
+            lib = ctypes.CDLL(_REFD_SO)
+            if os.path.exists(REFD_PE):
+                rc = lib.refdists_load(REFD_PE.encode())
+            elif os.path.exists(REFD_BLOB):
+                rc = lib.refdists_load_blob(REFD_BLOB.encode())
+            else:
+                rc = -1
+            if rc == 0:
+                lib.refdists_run_threaded.restype = ctypes.c_int
+                lib.refdists_run_threaded.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64,
+                                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+                _refd = lib
+    return _refd
+
+
+def refdists_triangle(x, want_manhat=True, want_info=False, threads=0):
+    """(manhat uint32 triangle | None, info float32 triangle | None) of the rows of x by the REFERENCE'S row-task
+    machine code on `threads` host threads (what generation_dists' executor runs)."""
+    lib = refdists()
+    if lib is None:
+        raise RuntimeError("the reference's machine code is not available here")
+    x = np.ascontiguousarray(x)
+    n, d = x.shape
+    elem = [np.dtype(t) for t in ELEM_DTYPES].index(x.dtype)
+    pairs = n * (n - 1) // 2
+    man = np.zeros(pairs, dtype=np.uint32) if want_manhat else None
+    inf = np.zeros(pairs, dtype=np.float32) if want_info else None
+    rc = lib.refdists_run_threaded(elem, _ptr(x), n, d, _ptr(man) if want_manhat else None,
+                                   _ptr(inf) if want_info else None, threads or host_threads())
+    if rc != 0:
+        raise RuntimeError("refdists_run_threaded failed: %d" % rc)
+    return man, inf
+
+
 def refcode_cgr_batch(chars, start, k, out, threads=0):
     """uint16 CGR count vectors of a batch of records by the REFERENCE'S machine code on `threads` host
     threads (what generation_cgr's executor does per file, minus the file reads)."""

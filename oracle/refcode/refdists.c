@@ -26,6 +26,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 #include <sys/mman.h>
 
 #define IMAGE_BASE 0x140000000ull
@@ -65,41 +66,92 @@ struct closure {
 
 static int g_loaded = 0;
 
-int refdists_load(const char *pe_path) {
-    if (g_loaded) return 0;
+/* the PE's sections laid out as the Windows loader would (no relocations needed at the preferred base):
+ * returns a calloc'ed image of *image_size bytes, or NULL with *err set */
+static unsigned char *build_image(const char *pe_path, uint32_t *image_size, int *err) {
     FILE *f = fopen(pe_path, "rb");
-    if (!f) return -1;
+    if (!f) return *err = -1, (unsigned char *)NULL;
     fseek(f, 0, SEEK_END);
     long fsz = ftell(f);
     fseek(f, 0, SEEK_SET);
     unsigned char *img = (unsigned char *)malloc((size_t)fsz);
     if (fread(img, 1, (size_t)fsz, f) != (size_t)fsz) {
         fclose(f);
-        return -2;
+        free(img);
+        return *err = -2, (unsigned char *)NULL;
     }
     fclose(f);
     uint32_t pe = *(uint32_t *)(img + 0x3c);
-    if (memcmp(img + pe, "PE\0\0", 4) != 0) return -3;
+    if (memcmp(img + pe, "PE\0\0", 4) != 0) return free(img), *err = -3, (unsigned char *)NULL;
     uint16_t nsec = *(uint16_t *)(img + pe + 6), optsz = *(uint16_t *)(img + pe + 20);
     uint64_t base = *(uint64_t *)(img + pe + 24 + 24);
-    uint32_t image_size = *(uint32_t *)(img + pe + 24 + 56);
-    if (base != IMAGE_BASE) return -4;
-    void *m = mmap((void *)IMAGE_BASE, image_size, PROT_READ | PROT_WRITE | PROT_EXEC,
-                   MAP_PRIVATE | MAP_ANONYMOUS | MAP_FIXED_NOREPLACE, -1, 0);
-    if (m != (void *)IMAGE_BASE) return -5;
+    *image_size = *(uint32_t *)(img + pe + 24 + 56);
+    if (base != IMAGE_BASE) return free(img), *err = -4, (unsigned char *)NULL;
+    unsigned char *out = (unsigned char *)calloc(*image_size, 1);
     unsigned char *sh = img + pe + 24 + optsz;
     for (int s = 0; s < nsec; ++s, sh += 40) {
         uint32_t vsize = *(uint32_t *)(sh + 8), va = *(uint32_t *)(sh + 12), rawsz = *(uint32_t *)(sh + 16),
                  rawp = *(uint32_t *)(sh + 20);
         uint32_t n = rawsz < vsize ? rawsz : vsize;
-        if ((uint64_t)va + n > image_size || (long)(rawp + n) > fsz) return -6;
-        memcpy((char *)IMAGE_BASE + va, img + rawp, n);
+        if ((uint64_t)va + n > *image_size || (long)(rawp + n) > fsz) return free(img), free(out), *err = -6, (unsigned char *)NULL;
+        memcpy(out + va, img + rawp, n);
     }
     free(img);
+    return out;
+}
+
+static int map_image(const unsigned char *image, uint32_t image_size) {
+    void *m = mmap((void *)IMAGE_BASE, image_size, PROT_READ | PROT_WRITE | PROT_EXEC,
+                   MAP_PRIVATE | MAP_ANONYMOUS | MAP_FIXED_NOREPLACE, -1, 0);
+    if (m != (void *)IMAGE_BASE) return -5;
+    memcpy(m, image, image_size);
     for (int e = 0; e < 6; ++e)
         if (memcmp((void *)LAMBDA_VA[e], PROLOGUE, 3) != 0) return -7;
     g_loaded = 1;
     return 0;
+}
+
+int refdists_load(const char *pe_path) {
+    if (g_loaded) return 0;
+    uint32_t image_size = 0;
+    int err = 0;
+    unsigned char *image = build_image(pe_path, &image_size, &err);
+    if (!image) return err;
+    err = map_image(image, image_size);
+    free(image);
+    return err;
+}
+
+/* build step (container with /root/reference): the loaded image -> a file under oracle/_ref/, so that
+ * bench.py's distances CPU baseline can run the reference's row tasks on the GPU box ("kind": "reference") */
+int refdists_extract(const char *pe_path, const char *blob_path) {
+    uint32_t image_size = 0;
+    int err = 0;
+    unsigned char *image = build_image(pe_path, &image_size, &err);
+    if (!image) return err;
+    FILE *f = fopen(blob_path, "wb");
+    if (!f) return free(image), -8;
+    err = (fwrite(&image_size, 4, 1, f) == 1 && fwrite(image, 1, image_size, f) == image_size) ? 0 : -9;
+    fclose(f);
+    free(image);
+    return err;
+}
+
+int refdists_load_blob(const char *blob_path) {
+    if (g_loaded) return 0;
+    FILE *f = fopen(blob_path, "rb");
+    if (!f) return -1;
+    uint32_t image_size = 0;
+    if (fread(&image_size, 4, 1, f) != 1 || image_size == 0 || image_size > (64u << 20)) {
+        fclose(f);
+        return -2;
+    }
+    unsigned char *image = (unsigned char *)malloc(image_size);
+    const size_t got = fread(image, 1, image_size, f);
+    fclose(f);
+    int err = got == image_size ? map_image(image, image_size) : -2;
+    free(image);
+    return err;
 }
 
 /* x: n matrices of d elements of element type `elem` (row-major).  manhat_tri / info_tri: packed strict
@@ -136,6 +188,72 @@ int refdists_run(int elem, const void *x, uint64_t n, uint64_t d, uint32_t *manh
         c.i = i;
         fn(&c);
     }
+    free(vars);
+    free(ptrs);
+    return 0;
+}
+
+/* ---- all rows on host threads: the executor of generation_dists (mmg::ParallelExecutor @0x10001a6f0) hands
+ * row indices to hardware_concurrency workers through one atomic counter; the row tasks write disjoint
+ * entries of the packed triangles ---- */
+struct rows_job {
+    int elem;
+    struct closure proto;   /* everything but i */
+    uint64_t n;
+    uint64_t next;
+};
+
+static void *rows_worker(void *arg) {
+    struct rows_job *j = (struct rows_job *)arg;
+    struct closure c = j->proto;
+    row_fn fn = (row_fn)LAMBDA_VA[j->elem];
+    for (;;) {
+        const uint64_t i = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (i >= j->n) break;
+        c.i = i;
+        fn(&c);
+    }
+    return NULL;
+}
+
+int refdists_run_threaded(int elem, const void *x, uint64_t n, uint64_t d, uint32_t *manhat_tri, float *info_tri,
+                          int threads) {
+    static const size_t esz[6] = {1, 2, 4, 8, 4, 8};
+    if (!g_loaded || elem < 0 || elem > 5) return -1;
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    struct variant *vars = (struct variant *)calloc(n, sizeof *vars);
+    void **ptrs = (void **)calloc(n, sizeof *ptrs);
+    for (uint64_t r = 0; r < n; ++r) {
+        vars[r].which = elem;
+        vars[r].data = (char *)x + r * d * esz[elem];
+        vars[r].rows = 1;
+        vars[r].cols = d;
+        ptrs[r] = &vars[r];
+    }
+    struct vec v = {ptrs, ptrs + n, ptrs + n};
+    uint8_t do_m = manhat_tri != NULL, do_i = info_tri != NULL;
+    uint32_t dummy_m = 0;
+    float dummy_i = 0;
+    struct sym_adapter am = {manhat_tri ? (void *)manhat_tri : (void *)&dummy_m, n, 0, 0, {0, 0}};
+    struct sym_adapter ai = {info_tri ? (void *)info_tri : (void *)&dummy_i, n, 0, 0, {0, 0}};
+    uint64_t nn = n;
+    struct rows_job job;
+    memset(&job, 0, sizeof job);
+    job.elem = elem;
+    job.n = n;
+    job.proto.n = &nn;
+    job.proto.do_manhat = &do_m;
+    job.proto.manhat = &am;
+    job.proto.mats = &v;
+    job.proto.do_info = &do_i;
+    job.proto.info = &ai;
+    pthread_t th[256];
+    int made = 0;
+    for (; made < threads; made++)
+        if (pthread_create(&th[made], NULL, rows_worker, &job)) break;
+    if (made == 0) rows_worker(&job);
+    for (int t = 0; t < made; t++) pthread_join(th[t], NULL);
     free(vars);
     free(ptrs);
     return 0;

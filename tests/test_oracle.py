@@ -136,3 +136,18 @@ def test_reference_machine_code_batch_equals_port():
         got = np.zeros((len(recs), 4 ** k), dtype=np.uint16)
         O.refcode_cgr_batch(chars, start, k, got, threads=3)
         assert np.array_equal(got, O.cgr_batch(chars, start, k, 16)), k
+
+
+def test_reference_row_task_machine_code_threaded_equals_port():
+    """bench.py's `kind: reference` distances baseline: the reference's own manhat / info row tasks (loaded from
+    the executable here, from the image under oracle/_ref on the GPU box) on host threads == the port, for every
+    element type."""
+    if O.refdists() is None:
+        pytest.skip("oracle/_ref holds no reference machine code on this host")
+    rng = np.random.Generator(np.random.PCG64(3))
+    for dt in O.ELEM_DTYPES:
+        x = (rng.random((33, 257)) * 40).astype(dt)
+        x[4] = 0
+        man, inf = O.refdists_triangle(x, True, True, threads=3)
+        pm, pi = O.dists_triangle(x, True, True)
+        assert np.array_equal(man, pm) and np.array_equal(inf.view(np.uint32), pi.view(np.uint32)), dt
