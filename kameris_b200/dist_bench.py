@@ -37,7 +37,6 @@ def synth_counts(torch, dev, n, L, k, seed, kind="counts"):
 
 def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
     from . import _lib
-    from . import dist as D
     lib = _lib.load()
     out = {}
 
