@@ -6,6 +6,8 @@ subcommands/classify.py:51-54) and the C++ twins inside the executables (mmg::re
 generation_cgr @0x100009fc0, mmg::repr_reader generation_dists @0x100019c10, mmg::dist_writer
 @0x100019720).  Layouts: SURVEY.md A.4 / A.5 (little-endian, no padding).
 """
+import os
+
 import numpy as np
 
 ELEMENT_TYPES = [np.dtype("<u1"), np.dtype("<u2"), np.dtype("<u4"), np.dtype("<u8"), np.dtype("<f4"),
@@ -14,6 +16,64 @@ REPR_MAGIC = b"MMREPR\0"
 DIST_MAGIC = b"MMDIST\0"
 REPR_HEADER = 34
 DIST_HEADER = 16
+
+
+# ---- bulk file I/O ------------------------------------------------------------------------------------------
+# numpy's fromfile / tofile move ~1 GB/s through one thread (and fault in a fresh buffer on the way); the
+# matrices here are gigabytes.  Positional reads / writes of disjoint slices from a few threads (the system
+# calls release the GIL) reach the page cache's bandwidth instead (20 GB/s for a 2 GB read on 8 cores).
+PARALLEL_IO_MIN_BYTES = 32 << 20
+PARALLEL_IO_THREADS = 8
+
+
+def _io_slices(nbytes, threads):
+    chunk = -(-nbytes // threads)
+    chunk = -(-chunk // 4096) * 4096                      # page-aligned pieces
+    return [(o, min(chunk, nbytes - o)) for o in range(0, nbytes, chunk)]
+
+
+def pread_into(fd, arr, offset, threads=None):
+    """fill the C-contiguous ndarray `arr` from file descriptor `fd` at byte `offset`; returns bytes read
+    (short only at end of file)."""
+    nbytes = arr.nbytes
+    if nbytes == 0:
+        return 0
+    mv = memoryview(arr.reshape(-1).view(np.uint8))
+
+    def one(o, ln):
+        got = 0
+        while got < ln:
+            r = os.preadv(fd, [mv[o + got:o + ln]], offset + o + got)
+            if r <= 0:
+                break
+            got += r
+        return got
+    t = min(threads or PARALLEL_IO_THREADS, os.cpu_count() or 1)
+    if nbytes < PARALLEL_IO_MIN_BYTES or t < 2:
+        return one(0, nbytes)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=t) as pool:
+        return sum(pool.map(lambda s: one(*s), _io_slices(nbytes, t)))
+
+
+def pwrite_from(fd, arr, offset, threads=None):
+    """write the C-contiguous ndarray `arr` to file descriptor `fd` at byte `offset` (the file grows as needed)."""
+    nbytes = arr.nbytes
+    if nbytes == 0:
+        return
+    mv = memoryview(arr.reshape(-1).view(np.uint8))
+
+    def one(o, ln):
+        done = 0
+        while done < ln:
+            done += os.pwritev(fd, [mv[o + done:o + ln]], offset + o + done)
+    t = min(threads or PARALLEL_IO_THREADS, os.cpu_count() or 1)
+    if nbytes < PARALLEL_IO_MIN_BYTES or t < 2:
+        one(0, nbytes)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=t) as pool:
+        list(pool.map(lambda s: one(*s), _io_slices(nbytes, t)))
 
 
 def element_type_of(dtype):
@@ -58,13 +118,7 @@ class repr_reader(object):
 
     def read_all(self):
         """All matrices as one (count, rows*cols) array (what generation_dists loads into RAM)."""
-        self._require_dense()
-        n = self.rows * self.cols
-        self.file.seek(REPR_HEADER)
-        m = np.fromfile(self.file, dtype=self.dtype, count=self.count * n)
-        if m.size != self.count * n:
-            raise ValueError("truncated .mm-repr file")
-        return m.reshape(self.count, n)
+        return self.read_rows(0, self.count)
 
     def read_rows(self, begin, end):
         """Matrices [begin, end) as one (end-begin, rows*cols) array (a rank's shard in multi-GPU runs)."""
@@ -72,11 +126,10 @@ class repr_reader(object):
         if not 0 <= begin <= end <= self.count:
             raise IndexError((begin, end))
         n = self.rows * self.cols
-        self.file.seek(REPR_HEADER + begin * n * self.dtype.itemsize)
-        m = np.fromfile(self.file, dtype=self.dtype, count=(end - begin) * n)
-        if m.size != (end - begin) * n:
+        m = np.empty((end - begin, n), dtype=self.dtype)
+        if pread_into(self.file.fileno(), m, REPR_HEADER + begin * n * self.dtype.itemsize) != m.nbytes:
             raise ValueError("truncated .mm-repr file")
-        return m.reshape(end - begin, n)
+        return m
 
     def close(self):
         self.file.close()
@@ -106,6 +159,7 @@ class repr_writer(object):
             np.array([self.count, self.rows, self.cols], dtype="<u8").tobytes()
         assert len(head) == REPR_HEADER
         self.file.write(head)
+        self.file.flush()                                  # positional writes (pwrite_from) may follow
 
     def write_matrix(self, m):
         m = np.ascontiguousarray(m, dtype=self.dtype)
@@ -119,7 +173,9 @@ class repr_writer(object):
         mats = np.ascontiguousarray(mats, dtype=self.dtype)
         if mats.size != self.count * self.rows * self.cols:
             raise ValueError("matrix block does not match the header")
-        mats.tofile(self.file)
+        self.file.flush()
+        pwrite_from(self.file.fileno(), mats, REPR_HEADER)
+        self.file.seek(REPR_HEADER + mats.nbytes)
         self.written = self.count
 
     def close(self):
@@ -159,7 +215,9 @@ class dist_writer(object):
         tri = np.ascontiguousarray(tri, dtype=self.dtype)
         if tri.size != self.size * (self.size - 1) // 2:
             raise ValueError("triangle length does not match the header")
-        tri.tofile(self.file)
+        self.file.flush()
+        pwrite_from(self.file.fileno(), tri, DIST_HEADER)
+        self.file.seek(DIST_HEADER + tri.nbytes)
 
     def write_next_row(self, row):
         np.ascontiguousarray(row, dtype=self.dtype).tofile(self.file)
@@ -180,11 +238,10 @@ class dist_reader(object):
     @staticmethod
     def read_triangle(filename):
         dt, n = dist_reader.read_header(filename)
+        tri = np.empty(n * (n - 1) // 2, dtype=dt)
         with open(filename, "rb") as f:
-            f.seek(DIST_HEADER)
-            tri = np.fromfile(f, dtype=dt, count=n * (n - 1) // 2)
-        if tri.size != n * (n - 1) // 2:
-            raise ValueError("truncated .mm-dist file")
+            if pread_into(f.fileno(), tri, DIST_HEADER) != tri.nbytes:
+                raise ValueError("truncated .mm-dist file")
         return tri, n
 
     @staticmethod

@@ -149,7 +149,9 @@ def kmers_to_file(records, k, bits_per_element, mode, output_file, row_offset=0,
                                      create_file=True)
     else:
         writer = formats.repr_appender(output_file)
-    writer.file.seek(formats.REPR_HEADER + row_offset * d * np.dtype(ndt).itemsize)
+    writer.file.flush()
+    fd, row_bytes = writer.file.fileno(), d * np.dtype(ndt).itemsize
+    base_off = formats.REPR_HEADER + row_offset * row_bytes
 
     def view(t, m):
         raw = (ctypes.c_char * (m * d * t.element_size())).from_address(t.data_ptr())
@@ -167,7 +169,8 @@ def kmers_to_file(records, k, bits_per_element, mode, output_file, row_offset=0,
                 base = chars.ctypes.data + int(start[i0]) if chars.size else None
                 _lib.check(lib.kam_kmers_host(base, sub.ctypes.data, i1 - i0, k, bits_per_element, kind,
                                               bufs[slot].data_ptr()))
-                futs[slot] = wpool.submit(lambda a=view(bufs[slot], i1 - i0): a.tofile(writer.file))
+                # positional, multi-threaded write of the chunk's rows (formats.pwrite_from)
+                futs[slot] = wpool.submit(formats.pwrite_from, fd, view(bufs[slot], i1 - i0), base_off + i0 * row_bytes)
             for f in futs:
                 if f is not None:
                     f.result()
@@ -308,8 +311,7 @@ def dists_to_files_sharded(input_file, output_prefix, metrics, dist, device=None
         part = part.view(np.uint32) if m == 'manhat' else part
         if part.size:
             with open(path, 'r+b') as f:
-                f.seek(formats.DIST_HEADER + off0 * 4)
-                np.ascontiguousarray(part, dtype=ndt).tofile(f)
+                formats.pwrite_from(f.fileno(), np.ascontiguousarray(part, dtype=ndt), formats.DIST_HEADER + off0 * 4)
         dist.barrier()
     return n, (r0, r1)
 

@@ -203,3 +203,48 @@ def test_native_fasta_ingest_matches_record0_semantics(tmp_path):
     (d / "zdir").mkdir()
     with pytest.raises(OSError, match="zdir"):
         backend.read_records_packed(backend.list_input_files(str(d)))
+
+
+def test_parallel_positional_io(tmp_path, monkeypatch):
+    """formats.pread_into / pwrite_from (threaded positional I/O behind read_rows / write_all / write_triangle and
+    the kmers step's chunk writes): byte-identical files and arrays whatever the slice boundaries, offsets that
+    are not page-aligned, short reads at end of file, empty arrays."""
+    monkeypatch.setattr(formats, "PARALLEL_IO_MIN_BYTES", 1 << 12)          # force the threaded path
+    rng = np.random.Generator(np.random.PCG64(4))
+    mats = rng.integers(0, 65536, size=(37, 4 ** 5), dtype=np.uint16)
+    seq, par, chunked = (str(tmp_path / n) for n in ("seq.mm-repr", "par.mm-repr", "chunked.mm-repr"))
+    w = formats.repr_writer(seq, mats[:1], len(mats), create_file=True)
+    for m in mats:
+        w.write_matrix(m)
+    w.close()
+    w = formats.repr_writer(par, mats[:1], len(mats), create_file=True)
+    w.write_all(mats)
+    w.close()
+    # the kmers step's pattern: header, then chunks of rows written at their offsets, out of order
+    w = formats.repr_writer(chunked, mats[:1], len(mats), create_file=True)
+    row_bytes = mats.shape[1] * 2
+    for i0, i1 in ((20, 37), (0, 7), (7, 20)):
+        formats.pwrite_from(w.file.fileno(), np.ascontiguousarray(mats[i0:i1]), formats.REPR_HEADER + i0 * row_bytes,
+                            threads=3)
+    w.close()
+    ref = open(seq, "rb").read()
+    assert open(par, "rb").read() == ref and open(chunked, "rb").read() == ref
+    with formats.repr_reader(seq) as r:
+        assert np.array_equal(r.read_all(), mats)
+        assert np.array_equal(r.read_rows(5, 23), mats[5:23])
+        assert r.read_rows(9, 9).shape == (0, 4 ** 5)
+        assert np.array_equal(r.read_matrix(36, flatten=True), mats[36])
+    with open(seq, "r+b") as f:
+        f.truncate(len(ref) - 100)
+    with formats.repr_reader(seq) as r, pytest.raises(ValueError, match="truncated"):
+        r.read_all()
+    tri = rng.random(300 * 299 // 2).astype(np.float32)
+    dw = formats.dist_writer(str(tmp_path / "t.mm-dist"), np.float32, 300)
+    dw.write_triangle(tri)
+    dw.close()
+    got, n = formats.dist_reader.read_triangle(str(tmp_path / "t.mm-dist"))
+    assert n == 300 and np.array_equal(got, tri)
+    assert os.path.getsize(str(tmp_path / "t.mm-dist")) == formats.DIST_HEADER + tri.nbytes
+    buf = np.zeros(1000, dtype=np.uint8)
+    with open(str(tmp_path / "t.mm-dist"), "rb") as f:
+        assert formats.pread_into(f.fileno(), buf, formats.DIST_HEADER + tri.nbytes - 10) == 10   # short at EOF

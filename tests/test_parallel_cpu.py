@@ -173,3 +173,53 @@ def test_job_steps_sharded_files_gloo_world2(tmp_path):
     assert n == 11 and np.array_equal(tri, man)
     tri, n = formats.dist_reader.read_triangle(os.path.join(root, "d-info.mm-dist"))
     assert n == 11 and np.array_equal(tri, info)
+
+
+def test_kmers_to_file_streaming_writer_with_host_stand_in(tmp_path, monkeypatch):
+    """The streaming `.mm-repr` writer of the kmers step (chunks produced into alternating buffers, written at
+    their offsets by positional multi-threaded writes) with a host stand-in for kam_kmers_host: several chunks,
+    a row offset into a larger file, packed and list inputs -> byte-identical to the file written row by row."""
+    import ctypes
+    from kameris_b200 import _lib, formats
+    from kameris_b200.job_steps import backend
+    from oracle import oracle as O
+    from tests.helpers import synth_records
+    k, bits = 4, 16
+    d = 4 ** k
+    recs = synth_records(23, 300, seed=12, jitter=100, dirty=0.01)
+    real = _lib.load()
+
+    class Fake(object):
+        def __getattr__(self, name):
+            return getattr(real, name)
+
+        @staticmethod
+        def kam_kmers_host(base, starts, n, kk, b, kind, out_ptr):
+            st = np.ctypeslib.as_array(ctypes.cast(starts, ctypes.POINTER(ctypes.c_uint64)), shape=(n + 1,))
+            raw = ctypes.string_at(base, int(st[n])) if base else b""
+            out = np.ctypeslib.as_array(ctypes.cast(out_ptr, ctypes.POINTER(ctypes.c_uint16)), shape=(n, d))
+            for i in range(n):
+                out[i] = O.cgr_count(raw[int(st[i]):int(st[i + 1])], kk, b)
+            return 0
+    monkeypatch.setattr(_lib, "load", lambda: Fake())
+    monkeypatch.setattr(backend, "CHUNK_BYTES", 5 * d * 2)                  # 5 rows per chunk -> 5 chunks
+    monkeypatch.setattr(formats, "PARALLEL_IO_MIN_BYTES", 256)              # threaded positional writes
+    want = str(tmp_path / "want.mm-repr")
+    w = formats.repr_writer(want, np.zeros((1, d), dtype=np.uint16), len(recs), create_file=True)
+    for r in recs:
+        w.write_matrix(O.cgr_count(r, k, bits))
+    w.close()
+    got = str(tmp_path / "got.mm-repr")
+    backend.kmers_to_file(recs, k, bits, "counts", got)
+    assert open(got, "rb").read() == open(want, "rb").read()
+    got2 = str(tmp_path / "got2.mm-repr")
+    backend.kmers_to_file(backend._pack_records(recs), k, bits, "counts", got2)
+    assert open(got2, "rb").read() == open(want, "rb").read()
+    # a shard written in place into a file another rank created (rows 10..22 of 23)
+    got3 = str(tmp_path / "got3.mm-repr")
+    w = formats.repr_writer(got3, np.zeros((1, d), dtype=np.uint16), len(recs), create_file=True)
+    w.file.truncate(formats.REPR_HEADER + len(recs) * d * 2)
+    w.close()
+    backend.kmers_to_file(recs[10:], k, bits, "counts", got3, row_offset=10, total_rows=len(recs), create=False)
+    backend.kmers_to_file(recs[:10], k, bits, "counts", got3, row_offset=0, total_rows=len(recs), create=False)
+    assert open(got3, "rb").read() == open(want, "rb").read()
