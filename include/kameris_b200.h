@@ -17,9 +17,18 @@
  *   kam_info_tri          info row lambda   (generation_dists @0x10001bab5-0x10001bcb0)
  *   kam_gram_*            euclid / cosine / pearson -- NOT in the reference (schema enum
  *                         kameris/schemas/job_options.json:97 has only manhat, info); defined as
- *                         scipy.spatial.distance {euclidean, cosine, correlation}
+ *                         scipy.spatial.distance {euclidean, cosine, correlation} on the rows as stored:
+ *                         count vectors, or the float64 cgr / cgr.sum() rows of a `frequencies` file
+ *                         (kameris/job_steps/backend.py:45-56)
  *   kam_dists_host        `generation_dists <in> <prefix> <names>` as invoked by
  *                         kameris/job_steps/backend.py:59-66, minus file I/O
+ *   kam_fasta_record0 /   the front half of the per-file task: ifstream + getline + trim + first-record
+ *   kam_fasta_read_files  selection (generation_cgr @0x10000d691-0x10000d83e), for one file image / for a whole
+ *                         listing on the host threads of mmg::ParallelExecutor (@0x10001a6f0)
+ *   kam_cgr_pool,         device forms of what the reference gets by re-running generation_cgr at another k
+ *   kam_normalize          and of the numpy pass backend.py:45-49 on existing count tables
+ *   kam_col_stats /       sklearn StandardScaler(with_mean=False).fit / .transform as used by
+ *   kam_col_scale         kameris/job_steps/classify.py:29-50 (build_pipeline)
  *   kam_mds_center        the numpy double-centring of kameris/job_steps/mds.py:14-24
  *   kam_symm_block        the matrix-block product of the eigen-solve that replaces
  *                         scipy.sparse.linalg.eigsh(B, k=dim), kameris/job_steps/mds.py:26
