@@ -248,3 +248,18 @@ def test_parallel_positional_io(tmp_path, monkeypatch):
     buf = np.zeros(1000, dtype=np.uint8)
     with open(str(tmp_path / "t.mm-dist"), "rb") as f:
         assert formats.pread_into(f.fileno(), buf, formats.DIST_HEADER + tri.nbytes - 10) == 10   # short at EOF
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under kameris_b200/ (nor suite-independent product entry points)
+    may import, load or execute it."""
+    pkg = os.path.join(ROOT, "kameris_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")) or "." not in fn:
+                with open(os.path.join(dirpath, fn), "rb") as f:
+                    txt = f.read().decode(errors="replace")
+                if re.search(r"^\s*(from|import)\s+oracle\b|libkameris_oracle|oracle/_ref|librefcode|librefdists", txt, re.M):
+                    offenders.append(os.path.relpath(os.path.join(dirpath, fn), ROOT))
+    assert offenders == []
