@@ -3,7 +3,7 @@ import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from kameris_b200 import repr as R, _lib
-from suite import gen_chars, pack
+from tests.suite import gen_chars, pack
 dev = torch.device("cuda:0")
 n, L, k = int(os.environ.get("N", "148")), int(os.environ.get("L", "5000000")), int(os.environ.get("K", "9"))
 chars = gen_chars(dev, n, L, 20261005)

@@ -3,7 +3,7 @@ import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from kameris_b200 import repr as R
-from suite import gen_chars
+from tests.suite import gen_chars
 dev = torch.device("cuda:0")
 res = {}
 for name, n, L, dirty in (("genomes_clean", 40000, 9000, 0.0), ("genomes_dirty0.2%", 40000, 9000, 0.002), ("reads", 2_000_000, 150, 0.0)):

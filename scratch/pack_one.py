@@ -2,7 +2,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from kameris_b200 import repr as R
-from suite import gen_chars
+from tests.suite import gen_chars
 dev = torch.device("cuda:0")
 n, L = 200000, 9000
 chars = gen_chars(dev, n, L, 7)

@@ -3,7 +3,7 @@ import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from kameris_b200 import repr as R, _lib
-from suite import gen_chars, pack
+from tests.suite import gen_chars, pack
 dev = torch.device("cuda:0")
 m, L = 1_000_000, 150
 chars = gen_chars(dev, m, L, 20261004)

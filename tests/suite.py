@@ -1,11 +1,12 @@
 #!/usr/bin/env python3
-"""suite.py -- the five BASELINE.json configs end to end on B200s: results checked against the
+"""tests/suite.py -- the five BASELINE.json configs end to end on B200s: results checked against the
 oracle (bit-exact counts / manhat, 1e-5 relative for frequencies and Gram metrics), throughput
-reported per config.  One JSON line per config (rank 0).
+reported per config.  One JSON line per config (rank 0).  A verification harness (it uses the oracle as
+the checker), hence under tests/.
 
-    python suite.py --config 1 2 4 5
+    python tests/suite.py --config 1 2 4 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-        --master-port 29500 suite.py --config 3 5
+        --master-port 29500 tests/suite.py --config 3 5
 
 Large synthetic sets are generated ON DEVICE (torch.Generator seeded per rank and batch); the
 sampled sequences / pairs that are verified are copied back and recomputed by the CPU oracle.
@@ -19,7 +20,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
