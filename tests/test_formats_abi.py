@@ -250,16 +250,24 @@ def test_parallel_positional_io(tmp_path, monkeypatch):
         assert formats.pread_into(f.fileno(), buf, formats.DIST_HEADER + tri.nbytes - 10) == 10   # short at EOF
 
 
-def test_product_never_imports_the_oracle():
-    """oracle/ is test infrastructure: nothing under kameris_b200/ (nor suite-independent product entry points)
-    may import, load or execute it."""
-    pkg = os.path.join(ROOT, "kameris_b200")
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """oracle/ is test infrastructure: outside oracle/ itself, only tests/, __graft_entry__.py (build of the
+    checker + smoke()) and bench.py (cpu_baseline / --impl reference) may import, load or execute it -- in
+    particular nothing under kameris_b200/."""
+    allowed = {"bench.py", "__graft_entry__.py"}
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|libkameris_oracle|oracle/_ref|librefcode|librefdists", re.M)
     offenders = []
-    for dirpath, _, files in os.walk(pkg):
+    for dirpath, dirs, files in os.walk(ROOT):
+        rel = os.path.relpath(dirpath, ROOT)
+        dirs[:] = [d for d in dirs if not d.startswith(".") and d not in ("gpurun_out", "__pycache__")]
+        if rel.split(os.sep)[0] in ("oracle", "tests"):
+            continue
         for fn in files:
-            if fn.endswith((".py", ".cu", ".cuh", ".h")) or "." not in fn:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")) or (rel.endswith("scripts") and "." not in fn):
+                path = os.path.relpath(os.path.join(dirpath, fn), ROOT)
+                if path in allowed:
+                    continue
                 with open(os.path.join(dirpath, fn), "rb") as f:
-                    txt = f.read().decode(errors="replace")
-                if re.search(r"^\s*(from|import)\s+oracle\b|libkameris_oracle|oracle/_ref|librefcode|librefdists", txt, re.M):
-                    offenders.append(os.path.relpath(os.path.join(dirpath, fn), ROOT))
+                    if pat.search(f.read().decode(errors="replace")):
+                        offenders.append(path)
     assert offenders == []
