@@ -69,7 +69,7 @@ def main(argv=None):
         joined = _maybe_init_process_group()
         return (main_cgr if argv[0] == 'generation_cgr' else main_dists)(argv[1:])
     except Exception as e:  # noqa: BLE001 -- the executables die with a message and a non-zero code
-        print('error: %s' % e)
+        print('error: %s' % (getattr(e, 'output', None) or e))     # CalledProcessError carries the cause in .output
         return 1
     finally:
         if joined:

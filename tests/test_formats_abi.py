@@ -271,3 +271,24 @@ def test_only_tests_smoke_and_bench_touch_the_oracle():
                     if pat.search(f.read().decode(errors="replace")):
                         offenders.append(path)
     assert offenders == []
+
+
+def test_cli_usage_and_errors_without_gpu(tmp_path, capsys):
+    """the argv-compatible shims (backend.py:36-39, :61-65): usage / bad input end with a non-zero code and a
+    message on stdout (the reference aborts; _command.py:17-18 turns that into CalledProcessError) before any
+    device work."""
+    from kameris_b200 import cli
+    assert cli.main([]) == 1
+    assert cli.main(["generation_cgr", "cgr"]) == 1
+    assert "Usage: generation_cgr" in capsys.readouterr().out
+    assert cli.main(["generation_cgr", "twocgr", str(tmp_path), str(tmp_path / "o"), "4", "16"]) == 1
+    assert cli.main(["generation_dists", "a", "b"]) == 1
+    assert cli.main(["generation_dists", "a", "b", "chebyshev"]) == 1
+    assert "Usage: generation_dists" in capsys.readouterr().out
+    assert cli.main(["generation_dists", str(tmp_path / "missing.mm-repr"), str(tmp_path / "p"), "manhat,info"]) == 1
+    assert cli.main(["generation_cgr", "cgr", str(tmp_path / "no such dir"), str(tmp_path / "o"), "4", "16"]) == 1
+    empty = tmp_path / "fa"
+    empty.mkdir()
+    (empty / "x.fasta").write_text(">header only\n")
+    assert cli.main(["generation_cgr", "cgr", str(empty), str(tmp_path / "o"), "4", "16"]) == 1
+    assert "no FASTA record" in capsys.readouterr().out
