@@ -292,3 +292,21 @@ def test_cli_usage_and_errors_without_gpu(tmp_path, capsys):
     (empty / "x.fasta").write_text(">header only\n")
     assert cli.main(["generation_cgr", "cgr", str(empty), str(tmp_path / "o"), "4", "16"]) == 1
     assert "no FASTA record" in capsys.readouterr().out
+
+
+def test_header_is_plain_c_and_the_example_links(tmp_path):
+    """include/kameris_b200.h is a C header (C99, -pedantic -Werror) and examples/kmers_host.c -- the plain-C
+    caller INTEGRATION.md shows -- compiles and links against the shared library (no compute call here)."""
+    import shutil
+    import subprocess
+    from kameris_b200 import build
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    build.build()
+    exe = str(tmp_path / "kmers_host")
+    libdir = os.path.dirname(build.LIB)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "kmers_host.c"), "-L", libdir, "-lkameris_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"usage:" in r.stderr
