@@ -274,6 +274,22 @@ def distances_cpu_baseline(n=4096, k=6, length=9000):
                                              "definition of the metric; not in the reference)" % m}}
 
 
+def preprocess_cpu_baseline(host, sample_n=2000):
+    """the reference's two normalisers (classify.py:29-50) as scikit-learn runs them on the host cores
+    (`kind: reference`: scikit-learn IS the reference's implementation of this arithmetic), on the first
+    sample_n vectors of the set the GPU line used"""
+    from sklearn.decomposition import TruncatedSVD
+    from sklearn.preprocessing import StandardScaler
+    x = host[:sample_n].astype(np.float64)
+    ncomp = int(np.ceil(sum(np.count_nonzero(f) for f in x[:256]) / 256 * 0.1))
+    t0 = time.perf_counter()
+    TruncatedSVD(n_components=ncomp, random_state=0).fit_transform(StandardScaler(with_mean=False).fit_transform(x))
+    dt = time.perf_counter() - t0
+    return {"value": len(x) / dt, "unit": "vectors/s", "kind": "reference", "cores": len(os.sched_getaffinity(0)),
+            "ms": dt * 1e3, "sample": "first %d of the %d vectors: sklearn StandardScaler(with_mean=False) + "
+            "TruncatedSVD(n_components=%d) fit_transform" % (len(x), len(host), ncomp)}
+
+
 def distance_lines(torch, dev, hbm_peak, tf_peak):
     """Secondary measurements: pairs/s of the distance kernels (filled in as they are built)."""
     try:

@@ -122,6 +122,22 @@ int kam_kmer_count(const uint64_t *d_planes, const uint64_t *d_base_start,
                    int count_bits, int out_kind, void *d_out, uint64_t out_stride, void *d_ws,
                    size_t ws_bytes, void *stream);
 
+/* The same fill with a SPARSE result, for vectors that are mostly zeros (a 9 kb genome touches <= 8992 of
+ * the 262144 bins of k = 9): vector s becomes d_nnz[s] packed entries (bin << 8 | count), in ascending bin
+ * order, at d_entries + d_entry_start[s].  An entry list never has more entries than the sequence has
+ * characters, so d_entry_start may simply be the character offsets of the batch (d_char_start of
+ * kam_pack_ascii) and d_entries hold total_chars words.  7 <= k <= 12.  A sequence this path cannot take
+ * (longer than 131072 bases, or a bin count above 255) gets d_nnz[s] = KAM_SPARSE_DECLINED; the caller
+ * recomputes it with kam_kmer_count.  The dense vector (generation_cgr @0x10000d330) is the expansion of the
+ * list over zeros; wrap width and output type are applied by whoever expands.  Fully asynchronous on
+ * `stream` (no internal synchronisation).  Workspace: kam_kmer_workspace_bytes(n_seqs, k). */
+#define KAM_SPARSE_MIN_K 7
+#define KAM_SPARSE_MAX_K 12
+#define KAM_SPARSE_DECLINED 0xffffffffu
+int kam_kmer_count_sparse(const uint64_t *d_planes, const uint64_t *d_base_start, const uint32_t *d_head_mask,
+                          uint32_t n_seqs, int k, const uint64_t *d_entry_start, uint32_t *d_entries,
+                          uint32_t *d_nnz, void *d_ws, size_t ws_bytes, void *stream);
+
 /* Every order k_lo..k_hi in one call (BASELINE config 2: k = 1..9).  h_outs is a HOST array of
  * k_hi-k_lo+1 device pointers (order k at index k-k_lo), each a dense n_seqs x 4^k matrix.  Orders
  * >= 8 run the ordinary tiled kernel (they are output-bound); for genome-length sequences (<= 65535
@@ -161,6 +177,22 @@ int kam_normalize(const void *d_counts, int count_bits, uint32_t n, uint64_t d, 
  * copy back are pipelined over chunks on internal streams; blocking. */
 int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_t n_seqs, int k,
                    int count_bits, int out_kind, void *h_out);
+/* How kam_kmers_host brings the vectors back: 0 = always dense (kernel writes the rows, the copy engine moves
+ * them), 1 = default: chunks whose vectors are mostly zeros (k >= 7 and entry lists <= 1/4 of the dense bytes)
+ * return as kam_kmer_count_sparse lists and are expanded into h_out by the host threads, 2 = sparse whenever
+ * 7 <= k <= 12 (test hook).  The rows written are identical either way.  Calls of kam_kmers_host are
+ * serialised by the library (one pipeline per device); it may be called from any thread. */
+void kam_kmers_host_set_sparse(int mode);
+/* Host worker threads of the library (list expansion): default = the cores of the process' affinity mask,
+ * divided by LOCAL_WORLD_SIZE under torchrun; KAM_HOST_THREADS in the environment or this call override. */
+void kam_host_set_threads(int threads);
+int kam_host_threads(void);
+/* Host-side expansion of kam_kmer_count_sparse lists (copied back by the caller) into n_seqs dense rows of
+ * 4^k elements: uint16/uint32 counts (count_bits) or float/double frequencies count/sum per out_kind, the sum
+ * being that of the list -- i.e. exactly what kam_kmer_count would have written.  Every cache line of a row
+ * is written once with non-temporal stores, on the library's host threads.  No GPU involved. */
+int kam_sparse_expand(const uint32_t *h_entries, const uint64_t *h_entry_start, const uint32_t *h_nnz,
+                      uint32_t n_seqs, int k, int count_bits, int out_kind, void *h_out);
 
 /* A.1: first FASTA record of a file image (generation_cgr @0x10000d691-0x10000d83e).  Writes at
  * most n bytes to out; returns the record length or -1 when the file holds no record. */

@@ -15,6 +15,7 @@ KAM_U8, KAM_U16, KAM_U32, KAM_U64, KAM_F32, KAM_F64 = range(6)
 KAM_OUT_COUNTS, KAM_OUT_FREQ_F32, KAM_OUT_FREQ_F64 = 0, 1, 2
 KAM_M_MANHAT, KAM_M_INFO, KAM_M_EUCLID, KAM_M_COSINE, KAM_M_PEARSON = 1, 2, 4, 8, 16
 KAM_GRAM_U8, KAM_GRAM_F16 = 0, 1
+KAM_SPARSE_DECLINED = 0xffffffff
 
 # every symbol include/kameris_b200.h declares: (restype, argtypes)
 SIGNATURES = {
@@ -39,6 +40,12 @@ SIGNATURES = {
                              c_uint64, c_void_p]),
     "kam_normalize": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_int, c_void_p, c_uint64, c_void_p]),
     "kam_kmers_host": (c_int, [c_void_p, c_void_p, c_uint32, c_int, c_int, c_int, c_void_p]),
+    "kam_kmers_host_set_sparse": (None, [c_int]),
+    "kam_host_set_threads": (None, [c_int]),
+    "kam_host_threads": (c_int, []),
+    "kam_sparse_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_int, c_int, c_void_p]),
+    "kam_kmer_count_sparse": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_size_t, c_void_p]),
     "kam_fasta_record0": (ctypes.c_int64, [c_void_p, c_size_t, c_void_p]),
     "kam_fasta_file_sizes": (c_int, [c_void_p, c_uint32, c_void_p, c_int]),
     "kam_fasta_read_files": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

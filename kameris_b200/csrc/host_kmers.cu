@@ -4,13 +4,33 @@
 // kameris/job_steps/backend.py:34-56 (file reading/writing stays with the caller): ASCII records
 // in host memory -> count / frequency vectors in host memory.  The batch is cut into chunks of
 // sequences; each chunk goes H2D -> pack -> k-mer count -> D2H on one of NSLOT streams with its
-// own device buffers, so the (dominant) device-to-host copy of chunk c overlaps the kernels and
-// the host-to-device copy of chunk c+1.  Pinned caller buffers are copied directly; pageable
-// ones go through internal pinned staging.
+// own device buffers, so the device-to-host copy of chunk c overlaps the kernels and the
+// host-to-device copy of chunk c+1.
+//
+// Two ways back to the host:
+//   dense   the kernel writes the vectors, the copy engine moves them (PCIe: ~57 GB/s measured).  Pinned
+//           caller buffers are copied directly; pageable ones go through internal pinned staging.
+//   sparse  (k >= 7, chunks whose vectors are mostly zeros -- 9 kb genomes at k = 9 are 96.6 % zeros):
+//           the kernel emits sorted (bin, count) lists (kam_kmer_count_sparse, 4 B per non-zero bin
+//           instead of 2-8 B per bin), only those cross PCIe, and a pool of host threads expands each list
+//           into the caller's dense row with non-temporal stores, writing every cache line of the row
+//           exactly once (zero lines and composed lines alike; ~200 GB/s on 8+ cores of the GPU box against
+//           57 GB/s for the copy engine, scratch/hostbw.cu).  The frequency division (backend.py:49) runs
+//           on the host in IEEE double precision -- the same operation numpy performs -- once per distinct
+//           count of a vector.  A chunk in which the sparse kernel declined a sequence is redone densely.
+#include <immintrin.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
+
+#include <sched.h>
 
 #include "common.cuh"
 
@@ -19,23 +39,222 @@ namespace {
 constexpr int NSLOT = 3;
 constexpr size_t OUT_CHUNK_BYTES = 128ull << 20;
 constexpr size_t CHAR_CHUNK_BYTES = 256ull << 20;
+constexpr size_t SPARSE_CHAR_CHUNK = 8ull << 20;      // 4 B of entry space per character: 32 MB of staging per slot
+constexpr uint32_t SPARSE_MAX_ROWS = 1024;
+constexpr int MAX_DEVICES = 64;
 
+// ---- host thread pool (the expansion's workers; the calling thread takes part) --------------------------
+class HostPool {
+   public:
+    ~HostPool() { stop(); }
+    int threads() {
+        std::lock_guard<std::mutex> g(cfg_);
+        return want();
+    }
+    void set_threads(int n) {
+        std::lock_guard<std::mutex> g(cfg_);
+        override_ = n > 0 ? n : 0;
+    }
+    // fn(i) for every i in [0, n), on the pool's threads and the caller
+    void parallel_for(uint32_t n, const std::function<void(uint32_t)> &fn) {
+        if (n == 0) return;
+        std::lock_guard<std::mutex> g(cfg_);
+        const int t = want();
+        if (t <= 1 || n == 1) {
+            for (uint32_t i = 0; i < n; ++i) fn(i);
+            return;
+        }
+        ensure(t - 1);
+        {
+            std::lock_guard<std::mutex> l(m_);
+            fn_ = &fn;
+            n_ = n;
+            next_.store(0);
+            active_ = (int)workers_.size();
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (uint32_t i; (i = next_.fetch_add(1)) < n;) fn(i);
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [&] { return active_ == 0; });
+        fn_ = nullptr;
+    }
+
+   private:
+    int want() {
+        if (override_) return override_;
+        if (const char *e = getenv("KAM_HOST_THREADS")) {
+            const int v = atoi(e);
+            if (v > 0) return v;
+        }
+        cpu_set_t set;
+        int cores = 0;
+        if (sched_getaffinity(0, sizeof set, &set) == 0) cores = CPU_COUNT(&set);
+        if (cores <= 0) cores = (int)std::thread::hardware_concurrency();
+        if (cores <= 0) cores = 1;
+        // one process per GPU (torchrun): the ranks of a box share its cores
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+            const int lw = atoi(e);
+            if (lw > 1) cores = std::max(2, cores / lw);
+        }
+        return std::min(cores, 64);
+    }
+    void ensure(int n) {
+        if ((int)workers_.size() == n) return;
+        stop();
+        quit_ = false;
+        const uint64_t g0 = gen_;            // no generation is published while cfg_ is held by our caller
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this, g0] { work(g0); });
+    }
+    void stop() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            quit_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+        workers_.clear();
+    }
+    void work(uint64_t seen) {
+        for (;;) {
+            const std::function<void(uint32_t)> *fn;
+            uint32_t n;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (quit_) return;
+                fn = fn_;
+                n = n_;
+            }
+            if (fn)
+                for (uint32_t i; (i = next_.fetch_add(1)) < n;) (*fn)(i);
+            {
+                std::lock_guard<std::mutex> l(m_);
+                if (--active_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::mutex cfg_, m_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> workers_;
+    const std::function<void(uint32_t)> *fn_ = nullptr;
+    std::atomic<uint32_t> next_{0};
+    uint32_t n_ = 0;
+    int active_ = 0, override_ = 0;
+    uint64_t gen_ = 0;
+    bool quit_ = false;
+};
+
+HostPool &pool() {
+    static HostPool *p = new HostPool();   // never destroyed: worker threads must not be joined at exit
+    return *p;
+}
+
+// ---- expansion of one entry list into one dense row ------------------------------------------------------
+template <typename OUT>
+struct Conv {
+    double sum;
+    OUT lut[256];
+    bool have[256];
+    int kind;
+    Conv(double s, int out_kind) : sum(s), kind(out_kind) { memset(have, 0, sizeof have); }
+    inline OUT operator()(uint32_t c) {
+        if (!have[c]) {
+            if (kind == KAM_OUT_FREQ_F64) lut[c] = (OUT)((double)c / sum);          // numpy true division
+            else if (kind == KAM_OUT_FREQ_F32) lut[c] = (OUT)(float)((double)c / sum);
+            else lut[c] = (OUT)c;
+            have[c] = true;
+        }
+        return lut[c];
+    }
+};
+
+inline void stream_zero_lines(char *p, size_t lines) {
+    const __m128i z = _mm_setzero_si128();
+    for (size_t i = 0; i < lines; ++i, p += 64) {
+        _mm_stream_si128((__m128i *)p, z);
+        _mm_stream_si128((__m128i *)(p + 16), z);
+        _mm_stream_si128((__m128i *)(p + 32), z);
+        _mm_stream_si128((__m128i *)(p + 48), z);
+    }
+}
+
+template <typename OUT>
+void expand_row(OUT *row, size_t bins, const uint32_t *ent, uint32_t nnz, int out_kind) {
+    unsigned long long s = 0;
+    for (uint32_t e = 0; e < nnz; ++e) s += ent[e] & 0xffu;
+    Conv<OUT> conv((double)s, out_kind);
+    if (((uintptr_t)row & 15) != 0 || (bins * sizeof(OUT)) % 64 != 0) {   // odd placement: plain stores
+        // an empty sequence in a frequencies file is 0/0 = NaN everywhere, like numpy
+        const OUT zero = conv(0);
+        for (size_t i = 0; i < bins; ++i) row[i] = zero;
+        for (uint32_t e = 0; e < nnz; ++e) row[ent[e] >> 8] = conv(ent[e] & 0xffu);
+        return;
+    }
+    constexpr uint32_t EPL = 64 / sizeof(OUT);    // elements per 64-byte line
+    char *p = (char *)row;
+    const size_t nlines = bins / EPL;
+    alignas(64) OUT tmp[EPL];
+    const OUT zero = conv(0);
+    const bool plain_zero = out_kind == KAM_OUT_COUNTS || s != 0;   // 0/0: the "zero" is NaN
+    alignas(64) OUT zline[EPL];
+    for (uint32_t i = 0; i < EPL; ++i) zline[i] = zero;
+    auto fill = [&](size_t l0, size_t l1) {
+        if (plain_zero) {
+            stream_zero_lines(p + l0 * 64, l1 - l0);
+        } else {
+            for (size_t l = l0; l < l1; ++l)
+                for (int q = 0; q < 4; ++q)
+                    _mm_stream_si128((__m128i *)(p + l * 64 + 16 * q), *(const __m128i *)((const char *)zline + 16 * q));
+        }
+    };
+    size_t line = 0;
+    uint32_t e = 0;
+    while (e < nnz) {
+        const size_t l = (ent[e] >> 8) / EPL;
+        fill(line, l);
+        for (uint32_t i = 0; i < EPL; ++i) tmp[i] = zero;
+        do {
+            tmp[(ent[e] >> 8) % EPL] = conv(ent[e] & 0xffu);
+            ++e;
+        } while (e < nnz && (ent[e] >> 8) / EPL == l);
+        for (int q = 0; q < 4; ++q)
+            _mm_stream_si128((__m128i *)(p + l * 64 + 16 * q), *(const __m128i *)((const char *)tmp + 16 * q));
+        line = l + 1;
+    }
+    fill(line, nlines);
+}
+
+void expand_dispatch(void *row, size_t bins, const uint32_t *ent, uint32_t nnz, int count_bits, int out_kind) {
+    if (out_kind == KAM_OUT_FREQ_F64) expand_row<double>((double *)row, bins, ent, nnz, out_kind);
+    else if (out_kind == KAM_OUT_FREQ_F32) expand_row<float>((float *)row, bins, ent, nnz, out_kind);
+    else if (count_bits == 16) expand_row<uint16_t>((uint16_t *)row, bins, ent, nnz, out_kind);
+    else expand_row<uint32_t>((uint32_t *)row, bins, ent, nnz, out_kind);
+}
+
+// ---- device / pinned buffers, pipeline slots --------------------------------------------------------------
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return KAM_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
+        release();
         size_t want = kam_align_up(bytes + bytes / 8, 1 << 20);
         if (cudaMalloc(&p, want) != cudaSuccess) {
             cudaGetLastError();
+            p = nullptr;
             kam_set_error("cudaMalloc(%zu) failed", want);
             return KAM_E_NOMEM;
         }
         cap = want;
         return KAM_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
     }
 };
 
@@ -44,46 +263,63 @@ struct PinBuf {
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return KAM_OK;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
+        release();
         size_t want = kam_align_up(bytes + bytes / 8, 1 << 20);
         if (cudaMallocHost(&p, want) != cudaSuccess) {
             cudaGetLastError();
+            p = nullptr;
             kam_set_error("cudaMallocHost(%zu) failed", want);
             return KAM_E_NOMEM;
         }
         cap = want;
         return KAM_OK;
     }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
 };
 
 struct Slot {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;   // D2H of the chunk last issued on this slot
-    DevBuf chars, starts, planes, base, head, pack_ws, kmer_ws, out;
-    PinBuf h_starts, h_chars, h_out;
-    // pending copy-out from pinned staging to a pageable caller buffer
-    void *pend_dst = nullptr;
+    DevBuf chars, starts, planes, base, head, pack_ws, kmer_ws, out, entries, nnz;
+    PinBuf h_starts, h_chars, h_out, h_entries, h_nnz;
+    bool busy = false;            // a chunk is in flight
+    // what the in-flight chunk still owes the caller once `done` has fired
+    bool sparse = false;
+    uint32_t first = 0, n = 0;
+    uint64_t nchars = 0;
+    void *pend_dst = nullptr;     // dense, pageable caller buffer: copy out of h_out
     size_t pend_bytes = 0;
 };
 
 struct HostCtx {
-    int device = -1;
+    bool ready = false;
     Slot slot[NSLOT];
 };
 
-HostCtx g_ctx;
+std::mutex g_call;                 // kam_kmers_host calls are serialised (one pipeline per device)
+HostCtx g_ctx[MAX_DEVICES];
+int g_sparse_mode = 1;             // 0 = never, 1 = when the vectors are sparse enough (default), 2 = whenever k allows
 
-int ctx_init() {
+int ctx_get(HostCtx **out) {
     int dev = 0;
     KAM_CUDA(cudaGetDevice(&dev));
-    if (g_ctx.device == dev && g_ctx.slot[0].st) return KAM_OK;
-    for (auto &s : g_ctx.slot) {
-        if (!s.st) KAM_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-        if (!s.done) KAM_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (dev < 0 || dev >= MAX_DEVICES) {
+        kam_set_error("device index %d out of range", dev);
+        return KAM_E_INVALID;
     }
-    g_ctx.device = dev;
+    HostCtx &c = g_ctx[dev];
+    if (!c.ready) {
+        for (auto &s : c.slot) {
+            if (!s.st) KAM_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+            if (!s.done) KAM_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        }
+        c.ready = true;
+    }
+    *out = &c;
     return KAM_OK;
 }
 
@@ -96,68 +332,121 @@ bool is_pinned(const void *p) {
     return a.type == cudaMemoryTypeHost;
 }
 
-int slot_drain(Slot &s) {
+struct Job {
+    const uint8_t *h_chars;
+    const uint64_t *h_char_start;
+    int k, count_bits, out_kind;
+    void *h_out;
+    size_t bins, row_bytes;
+    bool out_pinned, in_pinned;
+};
+
+// the chunk's vectors, densely, straight into the caller's rows (also the redo of a declined sparse chunk)
+int issue_dense(Slot &s, const Job &j) {
+    int rc;
+    if ((rc = s.kmer_ws.ensure(kam_kmer_workspace_bytes(s.n, j.k))) || (rc = s.out.ensure((size_t)s.n * j.row_bytes)))
+        return rc;
+    rc = kam_kmer_count((const uint64_t *)s.planes.p, (const uint64_t *)s.base.p, (const uint32_t *)s.head.p, s.n,
+                        s.nchars, j.k, j.count_bits, j.out_kind, s.out.p, j.bins, s.kmer_ws.p, s.kmer_ws.cap, s.st);
+    if (rc) return rc;
+    char *dst = (char *)j.h_out + (size_t)s.first * j.row_bytes;
+    if (j.out_pinned) {
+        KAM_CUDA(cudaMemcpyAsync(dst, s.out.p, (size_t)s.n * j.row_bytes, cudaMemcpyDeviceToHost, s.st));
+    } else {
+        if ((rc = s.h_out.ensure((size_t)s.n * j.row_bytes))) return rc;
+        KAM_CUDA(cudaMemcpyAsync(s.h_out.p, s.out.p, (size_t)s.n * j.row_bytes, cudaMemcpyDeviceToHost, s.st));
+        s.pend_dst = dst;
+        s.pend_bytes = (size_t)s.n * j.row_bytes;
+    }
+    s.sparse = false;
+    KAM_CUDA(cudaEventRecord(s.done, s.st));
+    return KAM_OK;
+}
+
+int slot_drain(Slot &s, const Job &j) {
+    if (!s.busy) return KAM_OK;
     KAM_CUDA(cudaEventSynchronize(s.done));
+    if (s.sparse) {
+        const uint32_t *nnz = (const uint32_t *)s.h_nnz.p;
+        bool declined = false;
+        for (uint32_t i = 0; i < s.n; ++i) declined |= nnz[i] == KAM_SPARSE_DECLINED;
+        if (declined) {                       // rare: a sequence too long for the tiles or a count above 255
+            int rc = issue_dense(s, j);
+            if (rc) return rc;
+            KAM_CUDA(cudaEventSynchronize(s.done));
+        } else {
+            const uint32_t *ent = (const uint32_t *)s.h_entries.p;
+            const uint64_t *hs = (const uint64_t *)s.h_starts.p;
+            char *dst = (char *)j.h_out + (size_t)s.first * j.row_bytes;
+            pool().parallel_for(s.n, [&](uint32_t i) {
+                expand_dispatch(dst + (size_t)i * j.row_bytes, j.bins, ent + hs[i], nnz[i], j.count_bits, j.out_kind);
+                _mm_sfence();
+            });
+        }
+    }
     if (s.pend_dst) {
         memcpy(s.pend_dst, s.h_out.p, s.pend_bytes);
         s.pend_dst = nullptr;
     }
+    s.busy = false;
     return KAM_OK;
 }
 
-}  // namespace
-
-extern "C" int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_t n_seqs, int k,
-                              int count_bits, int out_kind, void *h_out) {
-    if (k < 1 || 2 * k > 64) {
-        kam_set_error("k is too large to fit in the index");
-        return KAM_E_INVALID;
+// after an error: nothing of this call may still be writing into the caller's buffers when it returns
+void abandon(HostCtx &c) {
+    for (auto &s : c.slot) {
+        if (s.st) cudaStreamSynchronize(s.st);
+        s.busy = false;
+        s.pend_dst = nullptr;
     }
-    KAM_REQUIRE(k <= 15, "k > 15 not supported by this build");
-    KAM_REQUIRE(count_bits == 16 || count_bits == 32, "count_bits must be 16 or 32");
-    KAM_REQUIRE(out_kind >= KAM_OUT_COUNTS && out_kind <= KAM_OUT_FREQ_F64, "bad out_kind");
-    KAM_REQUIRE(h_char_start && h_out, "null pointer");
-    if (n_seqs == 0) return KAM_OK;
-    int rc = ctx_init();
-    if (rc) return rc;
+    cudaGetLastError();
+}
 
-    const size_t bins = (size_t)1 << (2 * k);
-    const size_t esz = out_kind == KAM_OUT_COUNTS ? (size_t)count_bits / 8 : (out_kind == KAM_OUT_FREQ_F32 ? 4 : 8);
-    const size_t row_bytes = bins * esz;
-    const bool out_pinned = is_pinned(h_out);
-    const bool in_pinned = h_chars && is_pinned(h_chars);
-
-    uint32_t max_rows = (uint32_t)std::max<size_t>(1, OUT_CHUNK_BYTES / row_bytes);
+int kmers_host_locked(HostCtx &ctx, const Job &j, uint32_t n_seqs) {
+    int rc;
+    const bool sparse_k = j.k >= KAM_SPARSE_MIN_K && j.k <= KAM_SPARSE_MAX_K && g_sparse_mode != 0;
+    const uint32_t dense_rows = (uint32_t)std::max<size_t>(1, OUT_CHUNK_BYTES / j.row_bytes);
     uint32_t first = 0;
     int turn = 0;
-    bool used[NSLOT] = {false, false, false};
     while (first < n_seqs) {
-        // chunk [first, last): bounded by rows and by characters
+        // a run of sequences is expanded on the host when its entry lists (4 B per character at most) are at
+        // most a quarter of the dense bytes; decided per chunk from the first sequences' lengths
+        const uint64_t c0 = j.h_char_start[first];
+        bool sparse = false;
+        if (sparse_k) {
+            const uint32_t probe = std::min<uint32_t>(n_seqs - first, SPARSE_MAX_ROWS);
+            const uint64_t pc = j.h_char_start[first + probe] - c0;
+            sparse = g_sparse_mode == 2 || pc * 4 * 4 <= (uint64_t)probe * j.row_bytes;
+        }
+        const uint32_t max_rows = sparse ? SPARSE_MAX_ROWS : dense_rows;
+        const uint64_t max_chars = sparse ? SPARSE_CHAR_CHUNK : CHAR_CHUNK_BYTES;
         uint32_t last = first;
-        const uint64_t c0 = h_char_start[first];
         while (last < n_seqs && last - first < max_rows &&
-               (last == first || h_char_start[last + 1] - c0 <= CHAR_CHUNK_BYTES))
+               (last == first || j.h_char_start[last + 1] - c0 <= max_chars))
             ++last;
         const uint32_t n = last - first;
-        const uint64_t nchars = h_char_start[last] - c0;
+        const uint64_t nchars = j.h_char_start[last] - c0;
 
-        Slot &s = g_ctx.slot[turn];
-        if (used[turn] && (rc = slot_drain(s))) return rc;
-        used[turn] = true;
+        Slot &s = ctx.slot[turn];
+        if ((rc = slot_drain(s, j))) return rc;
+        s.first = first;
+        s.n = n;
+        s.nchars = nchars;
+        s.sparse = sparse;
 
         if ((rc = s.chars.ensure(nchars + 32)) || (rc = s.starts.ensure((size_t)(n + 1) * 8)) ||
             (rc = s.planes.ensure(kam_planes_words(nchars) * 8)) || (rc = s.base.ensure((size_t)(n + 1) * 8)) ||
             (rc = s.head.ensure((size_t)n * 4)) || (rc = s.pack_ws.ensure(kam_pack_workspace_bytes(nchars, n))) ||
-            (rc = s.kmer_ws.ensure(kam_kmer_workspace_bytes(n, k))) || (rc = s.out.ensure((size_t)n * row_bytes)) ||
             (rc = s.h_starts.ensure((size_t)(n + 1) * 8)))
             return rc;
 
         uint64_t *hs = (uint64_t *)s.h_starts.p;
-        for (uint32_t i = 0; i <= n; ++i) hs[i] = h_char_start[first + i] - c0;
+        for (uint32_t i = 0; i <= n; ++i) hs[i] = j.h_char_start[first + i] - c0;
         KAM_CUDA(cudaMemcpyAsync(s.starts.p, hs, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s.st));
+        s.busy = true;
         if (nchars) {
-            const void *src = h_chars + c0;
-            if (!in_pinned) {
+            const void *src = j.h_chars + c0;
+            if (!j.in_pinned) {
                 if ((rc = s.h_chars.ensure(nchars))) return rc;
                 memcpy(s.h_chars.p, src, nchars);
                 src = s.h_chars.p;
@@ -167,23 +456,97 @@ extern "C" int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_sta
         rc = kam_pack_ascii((const uint8_t *)s.chars.p, (const uint64_t *)s.starts.p, n, nchars, (uint64_t *)s.planes.p,
                             (uint64_t *)s.base.p, (uint32_t *)s.head.p, s.pack_ws.p, s.pack_ws.cap, s.st);
         if (rc) return rc;
-        rc = kam_kmer_count((const uint64_t *)s.planes.p, (const uint64_t *)s.base.p, (const uint32_t *)s.head.p, n,
-                            nchars, k, count_bits, out_kind, s.out.p, bins, s.kmer_ws.p, s.kmer_ws.cap, s.st);
-        if (rc) return rc;
-        char *dst = (char *)h_out + (size_t)first * row_bytes;
-        if (out_pinned) {
-            KAM_CUDA(cudaMemcpyAsync(dst, s.out.p, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, s.st));
-        } else {
-            if ((rc = s.h_out.ensure((size_t)n * row_bytes))) return rc;
-            KAM_CUDA(cudaMemcpyAsync(s.h_out.p, s.out.p, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, s.st));
-            s.pend_dst = dst;
-            s.pend_bytes = (size_t)n * row_bytes;
+        if (sparse) {
+            const size_t eb = (size_t)(nchars ? nchars : 1) * 4;
+            if ((rc = s.kmer_ws.ensure(kam_kmer_workspace_bytes(n, j.k))) || (rc = s.entries.ensure(eb)) ||
+                (rc = s.nnz.ensure((size_t)n * 4)) || (rc = s.h_entries.ensure(eb)) || (rc = s.h_nnz.ensure((size_t)n * 4)))
+                return rc;
+            rc = kam_kmer_count_sparse((const uint64_t *)s.planes.p, (const uint64_t *)s.base.p, (const uint32_t *)s.head.p,
+                                       n, j.k, (const uint64_t *)s.starts.p, (uint32_t *)s.entries.p, (uint32_t *)s.nnz.p,
+                                       s.kmer_ws.p, s.kmer_ws.cap, s.st);
+            if (rc) return rc;
+            KAM_CUDA(cudaMemcpyAsync(s.h_nnz.p, s.nnz.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s.st));
+            if (nchars)
+                KAM_CUDA(cudaMemcpyAsync(s.h_entries.p, s.entries.p, (size_t)nchars * 4, cudaMemcpyDeviceToHost, s.st));
+            KAM_CUDA(cudaEventRecord(s.done, s.st));
+        } else if ((rc = issue_dense(s, j))) {
+            return rc;
         }
-        KAM_CUDA(cudaEventRecord(s.done, s.st));
         first = last;
         turn = (turn + 1) % NSLOT;
     }
-    for (int i = 0; i < NSLOT; ++i)
-        if (used[i] && (rc = slot_drain(g_ctx.slot[i]))) return rc;
+    for (int i = 0; i < NSLOT; ++i) {   // oldest first
+        if ((rc = slot_drain(ctx.slot[turn], j))) return rc;
+        turn = (turn + 1) % NSLOT;
+    }
     return KAM_OK;
 }
+
+}  // namespace
+
+extern "C" {
+
+int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_t n_seqs, int k, int count_bits,
+                   int out_kind, void *h_out) {
+    if (k < 1 || 2 * k > 64) {
+        kam_set_error("k is too large to fit in the index");
+        return KAM_E_INVALID;
+    }
+    KAM_REQUIRE(k <= 15, "k > 15 not supported by this build");
+    KAM_REQUIRE(count_bits == 16 || count_bits == 32, "count_bits must be 16 or 32");
+    KAM_REQUIRE(out_kind >= KAM_OUT_COUNTS && out_kind <= KAM_OUT_FREQ_F64, "bad out_kind");
+    KAM_REQUIRE(h_char_start && h_out, "null pointer");
+    if (n_seqs == 0) return KAM_OK;
+    KAM_REQUIRE(h_chars || h_char_start[n_seqs] == h_char_start[0], "null character buffer");
+    std::lock_guard<std::mutex> lock(g_call);
+    HostCtx *ctx = nullptr;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    Job j;
+    j.h_chars = h_chars;
+    j.h_char_start = h_char_start;
+    j.k = k;
+    j.count_bits = count_bits;
+    j.out_kind = out_kind;
+    j.h_out = h_out;
+    j.bins = (size_t)1 << (2 * k);
+    const size_t esz = out_kind == KAM_OUT_COUNTS ? (size_t)count_bits / 8 : (out_kind == KAM_OUT_FREQ_F32 ? 4 : 8);
+    j.row_bytes = j.bins * esz;
+    j.out_pinned = is_pinned(h_out);
+    j.in_pinned = h_chars && is_pinned(h_chars);
+    rc = kmers_host_locked(*ctx, j, n_seqs);
+    if (rc) abandon(*ctx);
+    return rc;
+}
+
+void kam_kmers_host_set_sparse(int mode) { g_sparse_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+void kam_host_set_threads(int threads) { pool().set_threads(threads); }
+int kam_host_threads(void) { return pool().threads(); }
+
+int kam_sparse_expand(const uint32_t *h_entries, const uint64_t *h_entry_start, const uint32_t *h_nnz, uint32_t n_seqs,
+                      int k, int count_bits, int out_kind, void *h_out) {
+    KAM_REQUIRE(k >= 1 && k <= KAM_SPARSE_MAX_K, "need 1 <= k <= 12");
+    KAM_REQUIRE(count_bits == 16 || count_bits == 32, "count_bits must be 16 or 32");
+    KAM_REQUIRE(out_kind >= KAM_OUT_COUNTS && out_kind <= KAM_OUT_FREQ_F64, "bad out_kind");
+    KAM_REQUIRE(h_entry_start && h_nnz && h_out, "null pointer");
+    if (n_seqs == 0) return KAM_OK;
+    const size_t bins = (size_t)1 << (2 * k);
+    const size_t esz = out_kind == KAM_OUT_COUNTS ? (size_t)count_bits / 8 : (out_kind == KAM_OUT_FREQ_F32 ? 4 : 8);
+    for (uint32_t i = 0; i < n_seqs; ++i) {
+        KAM_REQUIRE(h_nnz[i] != KAM_SPARSE_DECLINED, "a declined vector has no entry list");
+        KAM_REQUIRE(h_nnz[i] == 0 || h_entries, "null entry buffer");
+        for (uint32_t e = 0; e < h_nnz[i]; ++e) {
+            const uint32_t v = h_entries[h_entry_start[i] + e];
+            KAM_REQUIRE((v >> 8) < bins && (v & 0xffu) != 0, "entry out of range");
+            KAM_REQUIRE(e == 0 || (h_entries[h_entry_start[i] + e - 1] >> 8) < (v >> 8), "entries must ascend by bin");
+        }
+    }
+    pool().parallel_for(n_seqs, [&](uint32_t i) {
+        expand_dispatch((char *)h_out + (size_t)i * bins * esz, bins, h_entries ? h_entries + h_entry_start[i] : nullptr,
+                        h_nnz[i], count_bits, out_kind);
+        _mm_sfence();
+    });
+    return KAM_OK;
+}
+
+}  // extern "C"

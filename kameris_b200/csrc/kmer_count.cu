@@ -359,6 +359,116 @@ __global__ void __launch_bounds__(THREADS) cgr_tile_kernel(const uint2 *__restri
     }
 }
 
+// ---- path A with a SPARSE read-out ---------------------------------------------------------------------
+// A 9 kb genome at k=9 touches <= 8992 of 262144 bins: as a dense float64 row it is 2 MB of which 96.6 % are
+// zeros, and the host-buffer form of the step (kam_kmers_host) used to spend 99.6 % of its time moving those
+// zeros over PCIe.  Here the same shared-memory tiles are read out as a list of packed entries
+// (bin << 8 | count), in ascending bin order, <= one entry per emitting base: the CTA's warps own consecutive
+// runs of counter words, a first sweep counts the non-zero counters per warp, a second writes them at the
+// warp's offset (ballot to skip all-zero groups, shuffle scan inside a group) and clears the tile.  The host
+// expands a list into the caller's dense row with non-temporal stores (host_kmers.cu).  A sequence this path
+// declines (too long for the tiles, or a uint8 counter overflowed) gets nnz = KAM_SPARSE_DECLINED.
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v) {   // 0x80 in every non-zero byte
+    return (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) cgr_sparse_kernel(const uint2 *__restrict__ planes,
+                                                               const uint64_t *__restrict__ base_start,
+                                                               const uint32_t *__restrict__ head_mask, uint32_t n_seqs,
+                                                               int k, const uint64_t *__restrict__ entry_start,
+                                                               uint32_t *__restrict__ entries,
+                                                               uint32_t *__restrict__ nnz_out,
+                                                               uint32_t *__restrict__ queue) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *tab32 = reinterpret_cast<uint32_t *>(smem_raw);
+    __shared__ uint32_t s_seq, s_flag;
+    __shared__ uint32_t s_wtot[THREADS / 32];
+    constexpr uint32_t WARPS = THREADS / 32;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t bins = 1u << (2 * k);
+    const uint32_t tile_bins = bins < TILE_BINS ? bins : TILE_BINS;
+    const uint32_t n_tiles = bins / tile_bins;
+    const uint32_t tile_words = tile_bins / 4;                 // uint8 counters, four to a word
+    const uint32_t wpw = tile_words / WARPS;                   // words per warp (k >= 7: a multiple of 32)
+    const uint32_t ysh = n_tiles > 1 ? (uint32_t)(TILE_BINS_LOG2 - k) : (uint32_t)k;
+    const uint32_t ylow = (1u << ysh) - 1u;
+    const uint32_t tbits = n_tiles > 1 ? (uint32_t)(2 * k - TILE_BINS_LOG2) : 0u;
+
+    for (uint32_t i = threadIdx.x; i < tile_words; i += THREADS) tab32[i] = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_seq = atomicAdd(queue, 1u);
+            s_flag = 0;
+        }
+        __syncthreads();
+        const uint32_t s = s_seq;
+        if (s >= n_seqs) break;
+        const SeqInfo q = seq_info(base_start, head_mask, s, k);
+        if (q.n > A_MAX_LEN || (q.n > 64ull * bins && q.n > 255)) {
+            if (threadIdx.x == 0) nnz_out[s] = KAM_SPARSE_DECLINED;
+            continue;
+        }
+        uint32_t *ent = entries + entry_start[s];
+        const uint64_t pf = q.p0 + (uint64_t)(k - 1), pe = q.p0 + q.n;
+        const bool has_full = q.n >= (uint64_t)k;
+        uint32_t total = 0;                                    // CTA-uniform
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+            if (has_full) scan_tile_words<uint8_t, THREADS>(planes, pf, pe, k, t, tbits, ylow, tab32, &s_flag);
+            if (threadIdx.x == 0 && q.lead < (uint32_t)(k - 1)) {   // dirty head (rare)
+                head_partials(planes, q, k, [&](uint32_t bin) {
+                    if (n_tiles > 1 && (bin >> TILE_BINS_LOG2) != t) return;
+                    bump<uint8_t>(tab32, bin & (tile_bins - 1), &s_flag);
+                });
+            }
+            __syncthreads();
+            const uint32_t w0 = warp * wpw;
+            uint32_t c = 0;
+            for (uint32_t it = 0; it < wpw; it += 32) c += __popc(nonzero_bytes(tab32[w0 + it + lane]));
+            c = warp_sum(c);
+            if (lane == 0) s_wtot[warp] = c;
+            __syncthreads();
+            uint32_t base = total, tile_total = 0;
+#pragma unroll
+            for (uint32_t w = 0; w < WARPS; ++w) {
+                const uint32_t x = s_wtot[w];
+                if (w < warp) base += x;
+                tile_total += x;
+            }
+            if (c) {
+                for (uint32_t it = 0; it < wpw; it += 32) {
+                    const uint32_t widx = w0 + it + lane;
+                    const uint32_t v = tab32[widx];
+                    const uint32_t cnt = __popc(nonzero_bytes(v));
+                    if (__ballot_sync(0xffffffffu, cnt != 0) == 0u) continue;   // > 85 % of the groups at k=9
+                    uint32_t incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= (uint32_t)o) incl += y;
+                    }
+                    if (cnt) {
+                        tab32[widx] = 0;
+                        uint32_t pos = base + incl - cnt;
+                        const uint32_t bin0 = t * tile_bins + widx * 4u;
+#pragma unroll
+                        for (uint32_t b = 0; b < 4; ++b) {
+                            const uint32_t byte = (v >> (8u * b)) & 0xffu;
+                            if (byte) ent[pos++] = ((bin0 + b) << 8) | byte;
+                        }
+                    }
+                    base += __shfl_sync(0xffffffffu, incl, 31);
+                }
+            }
+            total += tile_total;
+            __syncthreads();   // tile clear again, s_wtot consumed
+        }
+        if (threadIdx.x == 0) nnz_out[s] = s_flag ? KAM_SPARSE_DECLINED : total;
+    }
+}
+
 // ---- path A for short reads at k <= 6: one WARP per read ---------------------------------------------
 // A 150 bp read has ~18 groups of 8 k-mers and a 4096-bin table: a CTA per read spends its time in
 // barriers and dependent global-load latencies, and uint32 counters cost 32 KB of shared-memory
@@ -1353,6 +1463,35 @@ int kam_kmer_count(const uint64_t *d_planes, const uint64_t *d_base_start, const
     if (out_kind == KAM_OUT_FREQ_F32)
         return run_kmer<float>(pl, d_base_start, d_head_mask, n_seqs, k, count_bits, (float *)d_out, out_stride, w, total_bases_hint, st);
     return run_kmer<double>(pl, d_base_start, d_head_mask, n_seqs, k, count_bits, (double *)d_out, out_stride, w, total_bases_hint, st);
+}
+
+int kam_kmer_count_sparse(const uint64_t *d_planes, const uint64_t *d_base_start, const uint32_t *d_head_mask,
+                          uint32_t n_seqs, int k, const uint64_t *d_entry_start, uint32_t *d_entries, uint32_t *d_nnz,
+                          void *d_ws, size_t ws_bytes, void *stream) {
+    KAM_REQUIRE(k >= KAM_SPARSE_MIN_K && k <= KAM_SPARSE_MAX_K, "sparse vectors need 7 <= k <= 12");
+    KAM_REQUIRE(d_planes && d_base_start && d_head_mask && d_entry_start && d_entries && d_nnz && d_ws, "null pointer");
+    if (ws_bytes < kam_kmer_workspace_bytes(n_seqs, k)) {
+        kam_set_error("kam_kmer_count_sparse: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    if (n_seqs == 0) return KAM_OK;
+    KmerWs w;
+    ws_layout(n_seqs, k, d_ws, &w);
+    cudaStream_t st = (cudaStream_t)stream;
+    KAM_CUDA(cudaMemsetAsync(w.queue, 0, 64, st));
+    const uint32_t bins = 1u << (2 * k);
+    const size_t smem = bins < TILE_BINS ? bins : TILE_BINS;
+    auto kern = cgr_sparse_kernel<256>;
+    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    KAM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)kam_sm_count() * per_sm;
+    if (grid > n_seqs) grid = n_seqs;
+    kern<<<(unsigned)grid, 256, smem, st>>>((const uint2 *)d_planes, d_base_start, d_head_mask, n_seqs, k, d_entry_start,
+                                            d_entries, d_nnz, w.queue);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
 }
 
 int kam_kmer_sweep(const uint64_t *d_planes, const uint64_t *d_base_start, const uint32_t *d_head_mask,

@@ -145,3 +145,33 @@ def kmer_sweep(batch, k_lo, k_hi, bits=16, out="counts", out_tensors=None, works
                                  batch.total_chars, k_lo, k_hi, bits, _OUT_KINDS[out], ptrs, _ptr(ws), ws.numel(),
                                  _stream_ptr(dev)))
     return out_tensors
+
+
+def kmer_sparse(batch, k, char_start_dev, workspace=None):
+    """Sparse form of kmer_vectors (kam_kmer_count_sparse): (entries int32[total_chars], nnz int32[n_seqs]);
+    vector s is entries[char_start[s] : char_start[s] + nnz[s]], each (bin << 8 | count), ascending by bin.
+    nnz == -1 (KAM_SPARSE_DECLINED as int32): the sequence needs kmer_vectors."""
+    lib = _lib.load()
+    dev = batch.device
+    entries = torch.empty(max(batch.total_chars, 1), dtype=torch.int32, device=dev)
+    nnz = torch.empty(max(batch.n_seqs, 1), dtype=torch.int32, device=dev)
+    ws = workspace if workspace is not None else kmer_workspace(batch.n_seqs, k, dev)
+    with torch.cuda.device(dev):
+        check(lib.kam_kmer_count_sparse(_ptr(batch.planes), _ptr(batch.base_start), _ptr(batch.head_mask),
+                                        batch.n_seqs, k, _ptr(char_start_dev), _ptr(entries), _ptr(nnz), _ptr(ws),
+                                        ws.numel(), _stream_ptr(dev)))
+    return entries, nnz[:batch.n_seqs]
+
+
+def sparse_expand(entries, entry_start, nnz, k, bits=16, out="counts"):
+    """Host expansion of kmer_sparse lists (numpy arrays) into a dense (n, 4^k) ndarray (kam_sparse_expand)."""
+    lib = _lib.load()
+    n = len(nnz)
+    dt = {"counts": np.uint16 if bits == 16 else np.uint32, "freq32": np.float32, "freq64": np.float64}[out]
+    res = np.empty((n, 4 ** k), dtype=dt)
+    entries = np.ascontiguousarray(entries, dtype=np.uint32)
+    entry_start = np.ascontiguousarray(entry_start, dtype=np.uint64)
+    nnz = np.ascontiguousarray(nnz, dtype=np.uint32)
+    check(lib.kam_sparse_expand(entries.ctypes.data if entries.size else None, entry_start.ctypes.data,
+                                nnz.ctypes.data, n, k, bits, _OUT_KINDS[out], res.ctypes.data))
+    return res

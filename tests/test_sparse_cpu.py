@@ -1,0 +1,71 @@
+"""Host half of the sparse return path of kam_kmers_host (no GPU): kam_sparse_expand turns sorted
+(bin << 8 | count) lists into the dense rows generation_cgr + the numpy pass (backend.py:45-49) produce.
+The lists here are made from the oracle's count vectors."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import synth_records
+
+
+def _lists(vectors):
+    ent, start, nnz = [], [0], []
+    for v in vectors:
+        b = np.nonzero(v)[0].astype(np.uint32)
+        ent.append((b << np.uint32(8)) | v[b].astype(np.uint32))
+        nnz.append(len(b))
+        start.append(start[-1] + len(b) + 3)          # slack between lists, like the character offsets
+        ent.append(np.zeros(3, dtype=np.uint32))
+    return np.concatenate(ent), np.array(start[:-1], dtype=np.uint64), np.array(nnz, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("k", [7, 9])
+@pytest.mark.parametrize("threads", [1, 5])
+def test_expand_matches_oracle_and_numpy(k, threads):
+    from kameris_b200 import _lib, repr as R
+    lib = _lib.load()
+    recs = synth_records(9, 3000, seed=k, dirty=0.002, jitter=2500) + [b"", b"NNNN", b"ACGTACGTAC", b"T" * 200]
+    counts = np.stack([O.cgr_count(r, k, 16) for r in recs])
+    assert counts.max() <= 255
+    ent, start, nnz = _lists(counts)
+    lib.kam_host_set_threads(threads)
+    try:
+        assert lib.kam_host_threads() == threads
+        got16 = R.sparse_expand(ent, start, nnz, k, 16, "counts")
+        got32 = R.sparse_expand(ent, start, nnz, k, 32, "counts")
+        f64 = R.sparse_expand(ent, start, nnz, k, 16, "freq64")
+        f32 = R.sparse_expand(ent, start, nnz, k, 16, "freq32")
+    finally:
+        lib.kam_host_set_threads(0)
+    assert np.array_equal(got16, counts) and np.array_equal(got32, counts.astype(np.uint32))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i, c in enumerate(counts):
+            want = c.reshape(1, -1) / c.reshape(1, -1).sum()          # backend.py:49, executed by numpy
+            assert np.array_equal(f64[i], want[0], equal_nan=True), i
+            assert np.array_equal(f32[i], want[0].astype(np.float32), equal_nan=True), i
+    assert np.isnan(f64[len(recs) - 4]).all()                          # empty record: 0/0 everywhere, like numpy
+
+
+def test_expand_misaligned_rows_and_small_k():
+    """rows that are not 64-byte multiples / 16-byte aligned take the plain-store path"""
+    from kameris_b200 import repr as R
+    recs = [b"ACGTTGCAAC", b"GATTACA" * 30]
+    for k in (1, 2, 3, 5):
+        counts = np.stack([O.cgr_count(r, k, 16) for r in recs])
+        ent, start, nnz = _lists(counts)
+        assert np.array_equal(R.sparse_expand(ent, start, nnz, k, 16, "counts"), counts)
+        f = R.sparse_expand(ent, start, nnz, k, 16, "freq64")
+        assert np.array_equal(f, counts / counts.sum(axis=1, keepdims=True))
+
+
+def test_expand_rejects_bad_lists():
+    from kameris_b200 import _lib, repr as R
+    bad = np.array([(5 << 8) | 1, (5 << 8) | 2], dtype=np.uint32)              # not ascending
+    with pytest.raises(_lib.KamError):
+        R.sparse_expand(bad, np.array([0], dtype=np.uint64), np.array([2], dtype=np.uint32), 7)
+    with pytest.raises(_lib.KamError):
+        R.sparse_expand(np.array([(4 ** 7) << 8 | 1], dtype=np.uint32), np.array([0], dtype=np.uint64),
+                        np.array([1], dtype=np.uint32), 7)                      # bin out of range
+    with pytest.raises(_lib.KamError):
+        R.sparse_expand(np.zeros(1, dtype=np.uint32), np.array([0], dtype=np.uint64),
+                        np.array([0xffffffff], dtype=np.uint32), 7)             # a declined vector
