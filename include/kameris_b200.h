@@ -286,15 +286,17 @@ int kam_gram_prepare(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t
 size_t kam_gram_block_workspace_bytes(uint32_t n_a, uint32_t n_b);
 /* rows [row_begin,row_end) of A against all rows of B.  triangular != 0: A and B are the same
  * matrix and only pairs j > i are written.  out_ld == 0 (triangular only): packed triangle of n_a;
- * otherwise dense row-major output, out[i*out_ld + j]. */
+ * otherwise dense row-major output, out[i*out_ld + j].  sm_limit: number of SMs the kernel may occupy
+ * (0 = all; a multi-GPU caller leaves a few to the concurrent NCCL transfers).  Asynchronous on `stream`:
+ * the tile schedule of a geometry is built once and cached on the device by the library. */
 int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_G_a, uint32_t n_a,
                    const void *d_op_b, const uint64_t *d_S_b, const uint64_t *d_G_b, uint32_t n_b,
                    int operand_kind, uint64_t d, int triangular, uint32_t row_begin, uint32_t row_end,
                    unsigned metrics, int euclid_on_freq, float *d_out_euclid, float *d_out_cosine,
-                   float *d_out_pearson, uint64_t out_ld, void *d_ws, size_t ws_bytes, void *stream);
-/* tuning hook: number of SMs the Gram kernel may occupy (0 = all); the rest stay free for
- * concurrent NCCL transfers. */
-void kam_gram_set_sm_limit(int sms);
+                   float *d_out_pearson, uint64_t out_ld, int sm_limit, void *d_ws, size_t ws_bytes, void *stream);
+/* tuning hook: row tiles (of 128 rows) per strip of the tile schedule (default 12); larger strips re-use the
+ * column panels longer in L2 at the price of more row panels in flight. */
+void kam_gram_set_strip(int row_tiles);
 
 /* Host-buffer form of the whole `distances` step: x is the n x d matrix read from a .mm-repr,
  * outputs are packed triangles (NULL = not requested).  euclid is taken between the rows as

@@ -71,8 +71,8 @@ SIGNATURES = {
     "kam_gram_block_workspace_bytes": (c_size_t, [c_uint32, c_uint32]),
     "kam_gram_block": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_uint32, c_int,
                                c_uint64, c_int, c_uint32, c_uint32, ctypes.c_uint, c_int, c_void_p, c_void_p, c_void_p,
-                               c_uint64, c_void_p, c_size_t, c_void_p]),
-    "kam_gram_set_sm_limit": (None, [c_int]),
+                               c_uint64, c_int, c_void_p, c_size_t, c_void_p]),
+    "kam_gram_set_strip": (None, [c_int]),
     "kam_gram_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, ctypes.c_uint,
                              c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "kam_mds_workspace_bytes": (c_size_t, [c_uint32]),

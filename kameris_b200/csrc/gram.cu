@@ -29,6 +29,9 @@
 //                              releases smem stages in both CTAs / publishes TMEM
 //   warps 2-5 epilogue       : tcgen05.ld 32x32b -> float64 distance formulas -> packed triangle
 // Only tiles that contain a pair i<j are scheduled (upper triangle).
+#include <string.h>
+
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -574,7 +577,7 @@ bool g_force_f16 = false;
 bool g_float_recover = true;   // test hook: false = floating-point rows always take the float64 CUDA-core Gram
 bool g_pair = true;        // cta_group::2 kernel (gram_pair_kernel, default) or the cluster-multicast one
 uint32_t g_cluster = 2;
-uint32_t g_sm_limit = 0;   // 0 = all SMs; otherwise leave the rest to concurrent work (e.g. NCCL transfers)
+uint32_t g_strip = 12;      // row tiles (of 128) per strip of the tile order (tuning hook)
 
 inline uint64_t dpad_of(uint64_t d) { return (d + BK_BYTES - 1) / BK_BYTES * BK_BYTES; }   // elements (either width)
 
@@ -606,7 +609,7 @@ int prepass_dispatch(const void *x, int elem, uint32_t n, uint64_t d, uint64_t l
 
 template <bool I8, int CL, bool PAIR = false>
 int launch_gram(const void *opA, const void *opB, const uint2 *d_tiles, size_t n_tiles, uint64_t d,
-                const GramGeom &gg, GramOut go, cudaStream_t st) {
+                const GramGeom &gg, GramOut go, uint32_t sm_limit, cudaStream_t st) {
     const uint64_t dpad = dpad_of(d);
     const uint32_t esz = I8 ? 1 : 2, bk = BK_BYTES / esz;
     const CUtensorMapDataType dt = I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -619,7 +622,7 @@ int launch_gram(const void *opA, const void *opB, const uint2 *d_tiles, size_t n
     auto kern = PAIR ? gram_pair_kernel<I8> : gram_tcgen05_kernel<I8, CL>;
     KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t sms = (uint32_t)kam_sm_count();
-    if (g_sm_limit && g_sm_limit < sms) sms = g_sm_limit;
+    if (sm_limit && sm_limit < sms) sms = sm_limit;
     uint32_t clusters = sms / CL;
     if (clusters < 1) clusters = 1;
     if (clusters > n_tiles) clusters = (uint32_t)n_tiles;
@@ -639,34 +642,103 @@ int launch_gram(const void *opA, const void *opB, const uint2 *d_tiles, size_t n
     return KAM_OK;
 }
 
-// tile list of one block + launch.  A list entry is (row-tile group, column tile); a group is CL
-// consecutive 128-row tiles handled by the CL CTAs of a cluster.  Strips of ~12 row tiles,
-// column-major inside a strip, so the ~148 tiles in flight share about a dozen A panels and a
-// dozen B panels in L2.
-int gram_block(const void *opA, const void *opB, bool i8, uint64_t d, const GramGeom &gg, GramOut go, uint2 *d_tiles,
-               cudaStream_t st) {
-    const uint32_t CL = g_cluster;
-    std::vector<uint2> tiles;
+// Tile lists are cached per geometry: the list of a block depends only on (first row group, last row group,
+// column tiles, triangular?, cluster size), it lives in device memory owned by the library next to the pinned
+// host copy it was uploaded from, so a launch neither waits for the upload nor re-builds the list (the first
+// version built a std::vector per call and synchronised the stream before it went out of scope).
+struct TileList {
+    int dev = -1;
+    uint32_t tr0 = 0, tr1 = 0, tc = 0, tri = 0, cl = 0, strip = 0;
+    uint2 *d = nullptr, *h = nullptr;
+    cudaEvent_t up = nullptr;   // the upload; launches on other streams wait for it
+    size_t n = 0;
+    uint64_t stamp = 0;
+};
+constexpr int TILE_CACHE = 32;
+TileList g_tiles[TILE_CACHE];
+uint64_t g_tile_stamp = 0;
+std::mutex g_tile_mu;
+
+// a list entry is (row-tile group, column tile); a group is CL consecutive 128-row tiles handled by the CL
+// CTAs of a cluster.  Strips of ~12 row tiles, column-major inside a strip, so the ~148 tiles in flight share
+// about a dozen A panels and a dozen B panels in L2.
+int tile_list(const GramGeom &gg, uint32_t CL, cudaStream_t st, const uint2 **d_list, size_t *n_list) {
     const uint32_t GM = BM * CL;
     const uint32_t tr0 = gg.row_begin / GM, tr1 = (gg.row_end - 1) / GM + 1, tc = (gg.n_b + BN - 1) / BN;
-    const uint32_t STRIP = 12 / CL;
+    int dev = 0;
+    KAM_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tile_mu);
+    TileList *slot = &g_tiles[0];
+    for (auto &t : g_tiles) {
+        if (t.d && t.dev == dev && t.tr0 == tr0 && t.tr1 == tr1 && t.tc == tc && t.tri == gg.tri && t.cl == CL &&
+            t.strip == g_strip) {
+            KAM_CUDA(cudaStreamWaitEvent(st, t.up, 0));
+            t.stamp = ++g_tile_stamp;
+            *d_list = t.d;
+            *n_list = t.n;
+            return KAM_OK;
+        }
+        if (t.stamp < slot->stamp) slot = &t;
+    }
+    std::vector<uint2> tiles;
+    const uint32_t STRIP = g_strip / CL ? g_strip / CL : 1;
     for (uint32_t s0 = tr0; s0 < tr1; s0 += STRIP) {
         const uint32_t s1 = s0 + STRIP < tr1 ? s0 + STRIP : tr1;
         for (uint32_t bj = 0; bj < tc; ++bj)
             for (uint32_t bg = s0; bg < s1; ++bg)
                 if (!gg.tri || (uint64_t)bj * BN + BN - 1 > (uint64_t)bg * GM) tiles.push_back(make_uint2(bg, bj));
     }
+    if (slot->d) {   // evict: earlier launches that read this list were enqueued on streams we do not know
+        int cur = dev;
+        if (slot->dev != dev) cudaSetDevice(slot->dev);
+        cudaDeviceSynchronize();
+        cudaFree(slot->d);
+        cudaFreeHost(slot->h);
+        cudaEventDestroy(slot->up);
+        if (slot->dev != cur) cudaSetDevice(cur);
+        slot->d = slot->h = nullptr;
+        slot->up = nullptr;
+    }
+    slot->n = tiles.size();
+    *d_list = nullptr;
+    *n_list = 0;
     if (tiles.empty()) return KAM_OK;
-    KAM_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
-    KAM_CUDA(cudaStreamSynchronize(st));   // `tiles` is pageable host memory owned by this frame
+    KAM_CUDA(cudaMalloc(&slot->d, tiles.size() * sizeof(uint2)));
+    if (cudaMallocHost(&slot->h, tiles.size() * sizeof(uint2)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(slot->d);
+        slot->d = nullptr;
+        kam_set_error("cudaMallocHost failed for a Gram tile list");
+        return KAM_E_NOMEM;
+    }
+    memcpy(slot->h, tiles.data(), tiles.size() * sizeof(uint2));
+    KAM_CUDA(cudaMemcpyAsync(slot->d, slot->h, tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+    KAM_CUDA(cudaEventCreateWithFlags(&slot->up, cudaEventDisableTiming));
+    KAM_CUDA(cudaEventRecord(slot->up, st));
+    slot->dev = dev;
+    slot->tr0 = tr0, slot->tr1 = tr1, slot->tc = tc, slot->tri = gg.tri, slot->cl = CL, slot->strip = g_strip;
+    slot->stamp = ++g_tile_stamp;
+    *d_list = slot->d;
+    *n_list = slot->n;
+    return KAM_OK;
+}
+
+int gram_block(const void *opA, const void *opB, bool i8, uint64_t d, const GramGeom &gg, GramOut go, uint32_t sm_limit,
+               cudaStream_t st) {
+    const uint32_t CL = g_cluster;
+    const uint2 *d_tiles = nullptr;
+    size_t n_tiles = 0;
+    int rc = tile_list(gg, CL, st, &d_tiles, &n_tiles);
+    if (rc) return rc;
+    if (n_tiles == 0) return KAM_OK;
     if (CL == 2 && g_pair)
-        return i8 ? launch_gram<true, 2, true>(opA, opB, d_tiles, tiles.size(), d, gg, go, st)
-                  : launch_gram<false, 2, true>(opA, opB, d_tiles, tiles.size(), d, gg, go, st);
+        return i8 ? launch_gram<true, 2, true>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st)
+                  : launch_gram<false, 2, true>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st);
     if (CL == 2)
-        return i8 ? launch_gram<true, 2>(opA, opB, d_tiles, tiles.size(), d, gg, go, st)
-                  : launch_gram<false, 2>(opA, opB, d_tiles, tiles.size(), d, gg, go, st);
-    return i8 ? launch_gram<true, 1>(opA, opB, d_tiles, tiles.size(), d, gg, go, st)
-              : launch_gram<false, 1>(opA, opB, d_tiles, tiles.size(), d, gg, go, st);
+        return i8 ? launch_gram<true, 2>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st)
+                  : launch_gram<false, 2>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st);
+    return i8 ? launch_gram<true, 1>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st)
+              : launch_gram<false, 1>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st);
 }
 
 struct GramWs {
@@ -739,8 +811,8 @@ size_t kam_gram_block_workspace_bytes(uint32_t n_a, uint32_t n_b) {
 int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_G_a, uint32_t n_a, const void *d_op_b,
                    const uint64_t *d_S_b, const uint64_t *d_G_b, uint32_t n_b, int operand_kind, uint64_t d,
                    int triangular, uint32_t row_begin, uint32_t row_end, unsigned metrics, int euclid_on_freq,
-                   float *d_out_euclid, float *d_out_cosine, float *d_out_pearson, uint64_t out_ld, void *d_ws,
-                   size_t ws_bytes, void *stream) {
+                   float *d_out_euclid, float *d_out_cosine, float *d_out_pearson, uint64_t out_ld, int sm_limit,
+                   void *d_ws, size_t ws_bytes, void *stream) {
     KAM_REQUIRE(d_op_a && d_op_b && d_S_a && d_G_a && d_S_b && d_G_b && d_ws, "null pointer");
     KAM_REQUIRE(operand_kind == KAM_GRAM_U8 || operand_kind == KAM_GRAM_F16, "bad operand kind");
     KAM_REQUIRE((metrics & ~(KAM_M_EUCLID | KAM_M_COSINE | KAM_M_PEARSON)) == 0 && metrics != 0, "bad metrics mask");
@@ -759,7 +831,6 @@ int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_
     cudaStream_t st = (cudaStream_t)stream;
     RowK *rk_a = (RowK *)d_ws;
     RowK *rk_b = (RowK *)((char *)d_ws + kam_align_up((size_t)n_a * sizeof(RowK), 1024));
-    uint2 *tiles = (uint2 *)((char *)rk_b + kam_align_up((size_t)n_b * sizeof(RowK), 1024));
     rowk_kernel<<<(n_a + 255) / 256, 256, 0, st>>>((const unsigned long long *)d_S_a, (const unsigned long long *)d_G_a,
                                                    n_a, (double)d, euclid_on_freq, rk_a);
     if (d_op_b != d_op_a || d_S_b != d_S_a)
@@ -782,7 +853,7 @@ int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_
     gg.ld = out_ld;
     gg.rk_a = rk_a;
     gg.rk_b = rk_b;
-    return gram_block(d_op_a, d_op_b, operand_kind == KAM_GRAM_U8, d, gg, go, tiles, st);
+    return gram_block(d_op_a, d_op_b, operand_kind == KAM_GRAM_U8, d, gg, go, sm_limit > 0 ? (uint32_t)sm_limit : 0u, st);
 }
 
 int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin, uint32_t row_end,
@@ -859,7 +930,7 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     gg.tri = 1;
     gg.ld = 0;
     gg.rk_a = gg.rk_b = w.rk;
-    return gram_block(w.h, w.h, use_i8, d, gg, go, w.tiles, st);
+    return gram_block(w.h, w.h, use_i8, d, gg, go, 0, st);
 }
 
 // test / tuning hooks
@@ -867,6 +938,6 @@ void kam_gram_force_f16(int on) { g_force_f16 = on != 0; }
 void kam_gram_set_float_recover(int on) { g_float_recover = on != 0; }
 void kam_gram_set_cluster(int cl) { g_cluster = cl == 1 ? 1u : 2u; }
 void kam_gram_set_pair(int on) { g_pair = on != 0; }
-void kam_gram_set_sm_limit(int sms) { g_sm_limit = sms > 0 ? (uint32_t)sms : 0u; }
+void kam_gram_set_strip(int row_tiles) { g_strip = row_tiles >= 2 ? (uint32_t)row_tiles : 2u; }
 
 }  // extern "C"

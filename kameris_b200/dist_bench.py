@@ -169,6 +169,11 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
         dt = sorted(ts)[2]              # median of 5 (cudaMalloc / cudaFree inside the call make single calls noisy)
         e2e[name] = {"value": pe / dt, "unit": "pairs/s", "ms": dt * 1e3, "ms_min_max": [min(ts) * 1e3, max(ts) * 1e3],
                      "h2d_bytes_per_step": ne * de * 2, "d2h_bytes_per_step": pe * 4 * n_out}
+    out["rooflines"] = {"gram_i8": dict(out["gram"]["roofline"], value=out["gram"]["value"], ms=out["gram"]["ms"]),
+                        "gram_f16": dict(out["gram"]["fp16_path"]["roofline"], value=out["gram"]["fp16_path"]["value"],
+                                         ms=out["gram"]["fp16_path"]["ms"]),
+                        "manhattan_u8": dict(out["manhattan"]["roofline"], value=out["manhattan"]["value"],
+                                             ms=out["manhattan"]["ms"])}
     out["e2e"] = {"api": "kam_dists_host (C ABI, pinned host buffers)",
                   "config": {"workload": "%d count vectors (9 kb genomes, k=%d, D=%d, uint16): %d pairs" % (ne, ke, de, pe)},
                   **e2e}

@@ -196,53 +196,95 @@ def _value_dtype(bits_per_element, mode):
     return np.dtype(np.uint16 if bits_per_element == 16 else np.uint32)
 
 
+def _agree(dist, err, what):
+    """Every rank learns here whether ANY rank failed, instead of a bare barrier: a rank that raised between
+    two collectives would leave the others waiting until the NCCL timeout.  Re-raises the local error, or an
+    OSError on the ranks that were fine."""
+    import torch
+    dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+    flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag.item()):
+        if err is not None:
+            raise err
+        raise OSError('%s failed on another rank' % what)
+
+
+def _unlink_quietly(paths):
+    for p in paths:
+        try:
+            os.unlink(p)
+        except OSError:
+            pass
+
+
 def kmers_to_file_sharded(paths, k, bits_per_element, mode, output_file, dist, produce=None):
     """The `kmers` step on all ranks of a process group: the sorted file list is cut into
     contiguous shards with nearly equal numbers of input bytes, every rank turns ITS files into vectors
     and writes them straight into its row range of the one `.mm-repr` (no gather, no data-path
-    collective; two barriers order the header before and the close after the row writes).
+    collective; two agreement points order the header before and the close after the row writes, and make
+    every rank fail -- and rank 0 remove the partial file -- when any rank failed).
 
     `produce(records, row_offset, total_rows)` defaults to the CUDA streaming writer; the CPU tests inject
     a host function to exercise the sharding and the file offsets under gloo."""
     from ..parallel import shard_by_bases
     rank, world = dist.get_rank(), dist.get_world_size()
-    sizes = [os.path.getsize(p) for p in paths]
-    b, e = shard_by_bases(sizes, world)[rank]
     n, d = len(paths), 4 ** k
-    if rank == 0:
-        w = formats.repr_writer(output_file, np.zeros((1, d), dtype=_value_dtype(bits_per_element, mode)), n,
-                                create_file=True)
-        w.file.truncate(formats.REPR_HEADER + n * d * w.dtype.itemsize)
-        w.file.close()
-    dist.barrier()
-    if produce is None:
-        kmers_to_file(read_records_packed(paths[b:e]), k, bits_per_element, mode, output_file, row_offset=b,
-                      total_rows=n, create=False)
-    else:
-        produce(read_records(paths[b:e]), b, n)
-    dist.barrier()
+    err, b, e = None, 0, 0
+    try:
+        sizes = [os.path.getsize(p) for p in paths]
+        b, e = shard_by_bases(sizes, world)[rank]
+        if rank == 0:
+            w = formats.repr_writer(output_file, np.zeros((1, d), dtype=_value_dtype(bits_per_element, mode)), n,
+                                    create_file=True)
+            w.file.truncate(formats.REPR_HEADER + n * d * w.dtype.itemsize)
+            w.file.close()
+    except Exception as ex:   # noqa: BLE001 -- whatever it is, the other ranks must hear of it
+        err = ex
+    try:
+        _agree(dist, err, 'kmers step (creating %s)' % output_file)
+        try:
+            if produce is None:
+                kmers_to_file(read_records_packed(paths[b:e]), k, bits_per_element, mode, output_file, row_offset=b,
+                              total_rows=n, create=False)
+            else:
+                produce(read_records(paths[b:e]), b, n)
+        except Exception as ex:   # noqa: BLE001
+            err = ex
+        _agree(dist, err, 'kmers step (vectors of a shard)')
+    except Exception:
+        if rank == 0:
+            _unlink_quietly([output_file])
+        raise
     return b, e
+
+
+def _kmers_single(options):
+    """the step in one process (what run_backend_kmers does outside a process group)"""
+    paths = list_input_files(options['fasta_output_dir'])
+    records = read_records_packed(paths)
+    kmers_to_file(records, options['k'], options['bits_per_element'], options['mode'], options['output_file'])
+    return len(paths)
 
 
 def run_backend_kmers(options, exp_options):
     log = _log()
     t0 = time.time()
     try:
-        paths = list_input_files(options['fasta_output_dir'])
-        log.info('%d files, using B200 backend', len(paths))
         dist, rank, world = _world()
         if dist is not None:
+            paths = list_input_files(options['fasta_output_dir'])
+            log.info('%d files, using B200 backend', len(paths))
             b, e = kmers_to_file_sharded(paths, options['k'], options['bits_per_element'], options['mode'],
                                          options['output_file'], dist)
             log.info('kmers: rank %d/%d wrote vectors [%d, %d) of %d in %.2f seconds', rank, world, b, e, len(paths),
                      time.time() - t0)
             return
-        records = read_records_packed(paths)
-        kmers_to_file(records, options['k'], options['bits_per_element'], options['mode'], options['output_file'])
+        n = _kmers_single(options)
     except (_lib.KamError, ValueError, OSError) as e:
         log.error('kmers step failed: %s', e)
         raise subprocess.CalledProcessError(1, 'generation_cgr (kameris_b200)', str(e))
-    log.info('kmers: %d vectors of %d bins in %.2f seconds', len(paths), 4 ** options['k'], time.time() - t0)
+    log.info('kmers: %d vectors of %d bins in %.2f seconds', n, 4 ** options['k'], time.time() - t0)
 
 
 def requested_metrics(names):
@@ -278,42 +320,119 @@ def dists_from_matrix(x, metrics):
     return out
 
 
+def _write_ring_blocks(blocks, counts, metrics, paths, n):
+    """Dense blocks of parallel.gram_ring -> their places in the packed `.mm-dist` triangles (A.5 order,
+    generation_dists @0x10001bf7e).  Row i of a block covers a run of consecutive columns j > i, i.e. ONE
+    contiguous segment of the file; a block whose column shard lies before its row shard is the transposed
+    case (its pairs are stored under the column's row).  Segments of different blocks are disjoint, so all ranks
+    write into the same files without coordination."""
+    from concurrent.futures import ThreadPoolExecutor
+    from ..parallel import tri_row_offset
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        for blk in blocks:
+            a, c = blk['row_shard'], blk['col_shard']
+            r0, r1 = blk['rows']
+            for m in metrics:
+                host = blk[m].cpu().numpy()
+                if blk['tri']:
+                    segs = [(int(offs[a]) + r, int(offs[a]) + r + 1, host[r - r0, r + 1:]) for r in range(r0, r1)]
+                elif a < c:
+                    segs = [(int(offs[a]) + r, int(offs[c]), host[r - r0]) for r in range(r0, r1)]
+                else:            # pairs (i in shard a, j in shard c < a) live in row j of the triangle
+                    ht = np.ascontiguousarray(host.T)
+                    segs = [(int(offs[c]) + j, int(offs[a]) + r0, ht[j]) for j in range(ht.shape[0])]
+                with open(paths[m], 'r+b') as f:
+                    fd = f.fileno()
+
+                    def put(seg):
+                        i, j0, vals = seg
+                        if vals.size:
+                            os.pwrite(fd, np.ascontiguousarray(vals, dtype=np.float32).data,
+                                      formats.DIST_HEADER + 4 * (tri_row_offset(n, i) + j0 - i - 1))
+                    list(pool.map(put, segs))
+
+
 def dists_to_files_sharded(input_file, output_prefix, metrics, dist, device=None, compute=None):
-    """The `distances` step on all ranks of a process group: every rank reads a contiguous
-    block of rows of the `.mm-repr`, the rows are all-gathered (the one exchange step), rank r computes
-    the block of triangle rows that holds 1/world of the pairs -- a CONTIGUOUS byte range of every
-    `.mm-dist` -- and writes it in place into the files rank 0 created.  `compute` as in
-    parallel.distances_sharded (CPU tests)."""
+    """The `distances` step on all ranks of a process group: every rank reads a contiguous block
+    of rows of the `.mm-repr`.
+      * euclid / cosine / pearson: parallel.gram_ring -- block-cyclic pair ownership, shards of tensor-core
+        operand rows travel around the ring while the block before is computed; every rank writes the rows of
+        its dense blocks into their (disjoint) segments of the `.mm-dist` files;
+      * manhat / info (and Gram metrics outside the tensor-exact envelope, or with an injected `compute`): the
+        rows are all-gathered, rank r computes the triangle rows that hold 1/world of the pairs -- a CONTIGUOUS
+        byte range of every `.mm-dist` -- and writes it in place.
+    Rank 0 creates the files; agreement points replace bare barriers so that a failure on any rank fails every
+    rank and removes the partial outputs.  `compute` as in parallel.distances_sharded (CPU tests)."""
     import torch
     from .. import parallel
     rank, world = dist.get_rank(), dist.get_world_size()
-    with formats.repr_reader(input_file) as reader:
-        n = reader.count
-        b, e = rank * n // world, (rank + 1) * n // world
-        x = reader.read_rows(b, e)
-    if any(m in GRAM_METRICS for m in metrics) and formats.element_type_of(x.dtype) == 3:
-        raise ValueError('euclid/cosine/pearson are not defined for 64-bit integer vectors')
-    t = torch.from_numpy(x)
-    if device is not None:
-        t = t.to(device)
-    slices, (r0, r1), n_all = parallel.distances_sharded(t, metrics, compute=compute, euclid_on_freq=False)
-    assert n_all == n
-    off0 = parallel.tri_row_offset(n, r0)
-    for m in metrics:
-        path = '%s-%s.mm-dist' % (output_prefix, m)
-        ndt = np.dtype(np.uint32 if m == 'manhat' else np.float32)
+    paths = {m: '%s-%s.mm-dist' % (output_prefix, m) for m in metrics}
+    err, n, x = None, 0, None
+    try:
+        with formats.repr_reader(input_file) as reader:
+            n = reader.count
+            b, e = rank * n // world, (rank + 1) * n // world
+            x = reader.read_rows(b, e)
+        if any(m in GRAM_METRICS for m in metrics) and formats.element_type_of(x.dtype) == 3:
+            raise ValueError('euclid/cosine/pearson are not defined for 64-bit integer vectors')
         if rank == 0:
-            w = formats.dist_writer(path, ndt, n)
-            w.file.truncate(formats.DIST_HEADER + (n * (n - 1) // 2) * 4)
-            w.close()
-        dist.barrier()
-        part = slices[m].cpu().numpy()
-        part = part.view(np.uint32) if m == 'manhat' else part
-        if part.size:
-            with open(path, 'r+b') as f:
-                formats.pwrite_from(f.fileno(), np.ascontiguousarray(part, dtype=ndt), formats.DIST_HEADER + off0 * 4)
-        dist.barrier()
-    return n, (r0, r1)
+            for m in metrics:
+                w = formats.dist_writer(paths[m], np.dtype(np.uint32 if m == 'manhat' else np.float32), n)
+                w.file.truncate(formats.DIST_HEADER + (n * (n - 1) // 2) * 4)
+                w.close()
+    except Exception as ex:   # noqa: BLE001 -- the other ranks must hear of it
+        err = ex
+    rows = (0, 0)
+    try:
+        _agree(dist, err, 'distances step (reading %s / creating the outputs)' % input_file)
+        try:
+            t = torch.from_numpy(x)
+            if device is not None:
+                t = t.to(device)
+            rest = list(metrics)
+            gram = [m for m in metrics if m in GRAM_METRICS]
+            if gram and compute is None and t.is_cuda and x.dtype != np.uint64:
+                try:
+                    blocks, counts = parallel.gram_ring(t, gram, euclid_on_freq=False)
+                    _write_ring_blocks(blocks, counts, gram, paths, n)
+                    del blocks
+                    rest = [m for m in metrics if m not in gram]
+                except (NotImplementedError, ValueError):
+                    pass          # decided from all-reduced flags: every rank takes the all-gather path below
+            if rest:
+                slices, rows, n_all = parallel.distances_sharded(t, rest, compute=compute, euclid_on_freq=False)
+                assert n_all == n
+                off0 = parallel.tri_row_offset(n, rows[0])
+                for m in rest:
+                    ndt = np.dtype(np.uint32 if m == 'manhat' else np.float32)
+                    part = slices[m].cpu().numpy()
+                    part = part.view(np.uint32) if m == 'manhat' else part
+                    if part.size:
+                        with open(paths[m], 'r+b') as f:
+                            formats.pwrite_from(f.fileno(), np.ascontiguousarray(part, dtype=ndt),
+                                                formats.DIST_HEADER + off0 * 4)
+        except Exception as ex:   # noqa: BLE001
+            err = ex
+        _agree(dist, err, 'distances step (a rank\'s share of the pairs)')
+    except Exception:
+        if rank == 0:
+            _unlink_quietly(paths.values())
+        raise
+    return n, rows
+
+
+def _dists_single(options, metrics):
+    """the step in one process (what run_backend_dists does outside a process group)"""
+    with formats.repr_reader(options['input_file']) as reader:
+        x = reader.read_all()                 # raises "Sparse matrices are not supported"
+    n = x.shape[0]
+    res = dists_from_matrix(x, metrics)
+    for m in metrics:
+        w = formats.dist_writer('%s-%s.mm-dist' % (options['output_prefix'], m), res[m].dtype, n)
+        w.write_triangle(res[m])
+        w.close()
+    return n
 
 
 def run_backend_dists(options, exp_options):
@@ -326,17 +445,10 @@ def run_backend_dists(options, exp_options):
             import torch
             n, rows = dists_to_files_sharded(options['input_file'], options['output_prefix'], metrics, dist,
                                              device=torch.device('cuda', torch.cuda.current_device()))
-            log.info('distances: rank %d/%d wrote triangle rows [%d, %d) of %d (%s) in %.2f seconds', rank, world,
-                     rows[0], rows[1], n, ','.join(metrics), time.time() - t0)
+            log.info('distances: rank %d/%d wrote its share of the pairs of %d vectors (%s) in %.2f seconds', rank,
+                     world, n, ','.join(metrics), time.time() - t0)
             return
-        with formats.repr_reader(options['input_file']) as reader:
-            x = reader.read_all()                 # raises "Sparse matrices are not supported"
-        n = x.shape[0]
-        res = dists_from_matrix(x, metrics)
-        for m in metrics:
-            w = formats.dist_writer('%s-%s.mm-dist' % (options['output_prefix'], m), res[m].dtype, n)
-            w.write_triangle(res[m])
-            w.close()
+        n = _dists_single(options, metrics)
     except (_lib.KamError, ValueError, OSError, TypeError) as e:
         log.error('distances step failed: %s', e)
         raise subprocess.CalledProcessError(1, 'generation_dists (kameris_b200)', str(e))

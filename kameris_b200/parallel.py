@@ -175,7 +175,7 @@ def ring_schedule(world):
     return plan
 
 
-def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group=None, sm_reserve=16):
+def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group=None, sm_reserve=16, timing=None):
     """euclid / cosine / pearson over the rows of all ranks, block-cyclic pair ownership.
 
     Every rank converts its own rows once (uint8 operands when every count of every rank fits a
@@ -184,7 +184,11 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
     block needs no communication at all.  Returns a list of blocks
         {"row_shard": a, "col_shard": c, "rows": (r0, r1), "tri": bool, metric: tensor[(r1-r0), n_c]}
     where entry [i - r0, j] is the distance between row i of shard a and row j of shard c (for a
-    triangular block only j > i is written).
+    triangular block only j > i is meaningful).
+
+    timing: a dict that receives, in milliseconds on this rank's compute stream, `prepare_ms` (operand
+    conversion + statistics), `block_ms` (the Gram kernels) and `exposed_comm_ms` (time the compute stream
+    sat waiting for a shard that had not arrived yet -- the non-overlapped part of the exchange).
     """
     from . import _lib
     from . import dist as D
@@ -196,12 +200,20 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
     elem = D._ELEM[x_local.dtype]
     if x_local.dtype in (torch.float32, torch.float64):
         euclid_on_freq = True       # frequency rows: euclid between the rows as stored (kam_gram_tri does the same)
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    cur = torch.cuda.current_stream(dev)
+    stream = cur.cuda_stream
     dpad = int(lib.kam_gram_dpad(d))
     bits = {"euclid": _lib.KAM_M_EUCLID, "cosine": _lib.KAM_M_COSINE, "pearson": _lib.KAM_M_PEARSON}
     mask = 0
     for m in metrics:
         mask |= bits[m]
+    marks = []                      # (label, event) on the compute stream
+
+    def mark(label):
+        if timing is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(cur)
+            marks.append((label, e))
 
     if world > 1:
         cnt = torch.tensor([n_loc], dtype=torch.int64, device=dev)
@@ -212,6 +224,7 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
         counts = [n_loc]
 
     # 1. local operand rows + statistics; the operand kind is a global decision
+    mark("start")
     S = torch.zeros(max(n_loc, 1), dtype=torch.int64, device=dev)
     G = torch.zeros(max(n_loc, 1), dtype=torch.int64, device=dev)
     kind, esz = _lib.KAM_GRAM_U8, 1
@@ -233,6 +246,7 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
         del op
     else:
         raise NotImplementedError("counts outside the tensor-exact envelope: use distances_sharded()")
+    mark("prepared")
 
     # 2. row statistics of every shard (tiny), padded to the largest shard
     cmax = max(counts)
@@ -255,40 +269,52 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
                                            dist.P2POp(dist.irecv, bufs[s], src, group)])
 
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    if world > 1 and sm_reserve:
-        lib.kam_gram_set_sm_limit(max(sms - sm_reserve, 2))     # leave SMs to the NCCL transfers
+    sm_limit = max(sms - sm_reserve, 2) if (world > 1 and sm_reserve) else 0    # leave SMs to the NCCL transfers
     out_blocks = []
-    try:
-        for s, a, c, part in plan:
-            if s > 0:
-                for w in works[s]:
-                    w.wait()
-            if part == "hi":            # A = the received shard a (rows of the shared block), B = my shard
-                op_a, sg_a, n_a = bufs[s], all_sg[a], counts[a]
-                op_b, sg_b, n_b = op, all_sg[c], counts[c]
-            else:                        # A = my shard, B = my shard (tri) or the received one
-                op_a, sg_a, n_a = op, all_sg[a], counts[a]
-                op_b, sg_b, n_b = (op, all_sg[c], counts[c]) if s == 0 else (bufs[s], all_sg[c], counts[c])
-            h = n_a // 2
-            r0, r1 = {"tri": (0, n_a), "full": (0, n_a), "lo": (0, h), "hi": (h, n_a)}[part]
-            blk = {"row_shard": a, "col_shard": c, "rows": (r0, r1), "tri": part == "tri"}
-            ptrs = {}
-            for m in metrics:
-                t = torch.zeros((max(r1 - r0, 1), max(n_b, 1)), dtype=torch.float32, device=dev)
-                blk[m] = t[:r1 - r0, :n_b]
-                ptrs[m] = t.data_ptr() - r0 * n_b * 4          # the kernel indexes rows from 0
-            ws = torch.empty(lib.kam_gram_block_workspace_bytes(n_a, n_b), dtype=torch.uint8, device=dev)
-            with torch.cuda.device(dev):
-                _lib.check(lib.kam_gram_block(op_a.data_ptr(), sg_a[0].data_ptr(), sg_a[1].data_ptr(), n_a,
-                                              op_b.data_ptr(), sg_b[0].data_ptr(), sg_b[1].data_ptr(), n_b, kind, d,
-                                              int(part == "tri"), r0, r1, mask, int(euclid_on_freq),
-                                              ptrs.get("euclid"), ptrs.get("cosine"), ptrs.get("pearson"), n_b,
-                                              ws.data_ptr(), ws.numel(), stream))
-            blk["_keep"] = ws
-            out_blocks.append(blk)
-    finally:
-        lib.kam_gram_set_sm_limit(0)
-    torch.cuda.current_stream(dev).synchronize()
+    for s, a, c, part in plan:
+        if s > 0:
+            mark("wait%d" % s)
+            for w in works[s]:
+                w.wait()            # the compute stream waits for the transfer, the host does not
+        mark("block%d" % s)
+        if part == "hi":            # A = the received shard a (rows of the shared block), B = my shard
+            op_a, sg_a, n_a = bufs[s], all_sg[a], counts[a]
+            op_b, sg_b, n_b = op, all_sg[c], counts[c]
+        else:                        # A = my shard, B = my shard (tri) or the received one
+            op_a, sg_a, n_a = op, all_sg[a], counts[a]
+            op_b, sg_b, n_b = (op, all_sg[c], counts[c]) if s == 0 else (bufs[s], all_sg[c], counts[c])
+        h = n_a // 2
+        r0, r1 = {"tri": (0, n_a), "full": (0, n_a), "lo": (0, h), "hi": (h, n_a)}[part]
+        blk = {"row_shard": a, "col_shard": c, "rows": (r0, r1), "tri": part == "tri"}
+        ptrs = {}
+        for m in metrics:
+            # every entry of a rectangular block is written by the kernel; a triangular block keeps zeros
+            # on and below its diagonal
+            alloc = torch.zeros if part == "tri" else torch.empty
+            t = alloc((max(r1 - r0, 1), max(n_b, 1)), dtype=torch.float32, device=dev)
+            blk[m] = t[:r1 - r0, :n_b]
+            ptrs[m] = t.data_ptr() - r0 * n_b * 4          # the kernel indexes rows from 0
+        ws = torch.empty(lib.kam_gram_block_workspace_bytes(n_a, n_b), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.kam_gram_block(op_a.data_ptr(), sg_a[0].data_ptr(), sg_a[1].data_ptr(), n_a,
+                                          op_b.data_ptr(), sg_b[0].data_ptr(), sg_b[1].data_ptr(), n_b, kind, d,
+                                          int(part == "tri"), r0, r1, mask, int(euclid_on_freq),
+                                          ptrs.get("euclid"), ptrs.get("cosine"), ptrs.get("pearson"), n_b, sm_limit,
+                                          ws.data_ptr(), ws.numel(), stream))
+        blk["_keep"] = ws
+        out_blocks.append(blk)
+    mark("end")
+    cur.synchronize()
     for b in out_blocks:
         b.pop("_keep", None)
+    if timing is not None:
+        t = {"prepare_ms": 0.0, "block_ms": 0.0, "exposed_comm_ms": 0.0, "other_ms": 0.0}
+        for (la, ea), (_, eb) in zip(marks[:-1], marks[1:]):
+            dt = ea.elapsed_time(eb)
+            key = "prepare_ms" if la == "start" else "block_ms" if la.startswith("block") else \
+                "exposed_comm_ms" if la.startswith("wait") else "other_ms"
+            t[key] += dt
+        t["operand"] = "uint8" if kind == _lib.KAM_GRAM_U8 else "fp16"
+        t["recv_bytes"] = int(sum(b.numel() for b in bufs.values()))
+        timing.update(t)
     return out_blocks, counts

@@ -1,0 +1,124 @@
+"""Multi-GPU `distances` legs of bench.py (the only path with an exchange step).
+
+  gram_ring   STRONG scaling: a fixed set of N_total = 40 000 count vectors of D = 4^9 bins (9 kb genomes,
+              k = 9; 21 GB of uint16 counts), cosine + pearson of all N(N-1)/2 = 8.0e8 pairs with
+              parallel.gram_ring: every rank converts its shard to uint8 tensor-core operands, shards travel
+              around the ring with NCCL send/recv while the tcgen05 Gram kernel works on the block before.
+              The set is generated in 8 seeded blocks of 5000 sequences, so it is the SAME set at 1, 2, 4
+              and 8 ranks.  Reported: whole-call time (max over ranks), pairs/s, the kernel time and the
+              exposed (non-overlapped) wait for shards on the compute stream.
+  manhat      STRONG scaling: 32 768 count vectors of D = 4^6 through parallel.distances_sharded (NCCL
+              all-gather of the rows, then contiguous triangle row blocks with equal pair counts).
+"""
+import torch
+
+N_TOTAL, SEQ_LEN, K, BLOCKS = 40000, 9000, 9, 8
+HIV_CDF = (0.36, 0.54, 0.78)
+
+
+def gen_counts(dev, n, length, k, seed, out=None):
+    """count vectors (uint16) of n synthetic HIV-1-like sequences, generated and counted on the device"""
+    from . import repr as R
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    chars = torch.zeros(n * length + 16, dtype=torch.uint8, device=dev)
+    alpha = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
+    cdf = torch.tensor(HIV_CDF, device=dev)
+    step = 1 << 27
+    for o in range(0, n * length, step):
+        m = min(step, n * length - o)
+        chars[o:o + m] = alpha[torch.bucketize(torch.rand(m, generator=g, device=dev), cdf)]
+    start = torch.arange(n + 1, dtype=torch.int64, device=dev) * length
+    b = R.pack_chars(chars, start, n, n * length)
+    return R.kmer_vectors(b, k, 16, "counts", out_tensor=out)
+
+
+def _max_over_ranks(dist_pg, dev, world, vals):
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist_pg.all_reduce(t, op=dist_pg.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def _barrier(dist_pg, dev, world):
+    if world > 1:
+        dist_pg.barrier()
+    torch.cuda.synchronize(dev)
+
+
+def gen_shard(dev, rank, world, n_total, k, seed_base):
+    """this rank's rows of a fixed set of n_total sequences (the same set at every world size that divides
+    BLOCKS: it is generated in BLOCKS seeded blocks)"""
+    if BLOCKS % world == 0:
+        per = n_total // BLOCKS
+        mine = range(rank * BLOCKS // world, (rank + 1) * BLOCKS // world)
+    else:                                   # other world sizes: equal shards, per-rank seeds
+        per = n_total // world
+        mine = [1000 + rank]
+    x = torch.empty((per * len(mine), 4 ** k), dtype=torch.uint16, device=dev)
+    for i, b in enumerate(mine):
+        gen_counts(dev, per, SEQ_LEN, k, seed_base + b, out=x[i * per:(i + 1) * per])
+    torch.cuda.empty_cache()
+    return x
+
+
+def run_gram_ring(dist_pg, dev, rank, world, tf_peak, reps=2, n_total=N_TOTAL):
+    from . import parallel
+    x = gen_shard(dev, rank, world, n_total, K, 2026100300)
+    n_loc, d = x.shape
+    n_all = n_loc * world
+    pairs = n_all * (n_all - 1) // 2
+    parallel.gram_ring(x, ("cosine", "pearson"))                  # warm-up: NCCL P2P set-up, tile schedules
+    torch.cuda.empty_cache()
+    best, tim = None, None
+    for _ in range(reps):
+        t = {}
+        _barrier(dist_pg, dev, world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        blocks, _ = parallel.gram_ring(x, ("cosine", "pearson"), timing=t)
+        e1.record()
+        _barrier(dist_pg, dev, world)
+        ms = e0.elapsed_time(e1)
+        chk = float(blocks[0]["cosine"][0, 1]) if blocks and blocks[0]["cosine"].numel() > 1 else 0.0
+        del blocks
+        torch.cuda.empty_cache()
+        ms, blk, exp, prep = _max_over_ranks(dist_pg, dev, world, [ms, t["block_ms"], t["exposed_comm_ms"], t["prepare_ms"]])
+        if best is None or ms < best:
+            best, tim = ms, {"block_ms": blk, "exposed_comm_ms": exp, "prepare_ms": prep, "operand": t["operand"],
+                             "recv_bytes_per_rank": t["recv_bytes"]}
+    flops = 2.0 * d * pairs
+    i8_peak = 2.0 * tf_peak
+    return {"value": pairs / (best * 1e-3), "unit": "pairs/s", "ms": best, "n_gpus": world, "scaling": "strong",
+            "n_total": n_all, "d": d, "pairs": pairs, "metrics": "cosine+pearson", "check_cosine_0_1": chk,
+            "achieved": flops / (best * 1e-3) / 1e12 / world, "peak": i8_peak, "unit_roofline": "TFLOP/s per GPU",
+            "frac": flops / (best * 1e-3) / 1e12 / world / i8_peak,
+            "kernel": "gram_pair_kernel<i8> (tcgen05 cta_group::2) + NCCL send/recv ring",
+            "includes": "operand pre-pass, statistics all-gather, ring send/recv, every block's kernel", **tim}
+
+
+def run_manhat_sharded(dist_pg, dev, rank, world, reps=2, n_total=32768, k=6):
+    from . import parallel
+    x = gen_shard(dev, rank, world, n_total, k, 2026100400)
+    n_all = x.shape[0] * world
+    pairs = n_all * (n_all - 1) // 2
+    if world > 1:
+        run = lambda: parallel.distances_sharded(x, ["manhat"])            # noqa: E731
+    else:
+        from . import dist as D
+        run = lambda: D.manhattan_tri(x)                                   # noqa: E731
+    run()
+    best = None
+    for _ in range(reps):
+        _barrier(dist_pg, dev, world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = run()
+        e1.record()
+        _barrier(dist_pg, dev, world)
+        del r
+        ms = _max_over_ranks(dist_pg, dev, world, [e0.elapsed_time(e1)])[0]
+        best = ms if best is None else min(best, ms)
+    return {"value": pairs / (best * 1e-3), "unit": "pairs/s", "ms": best, "n_gpus": world, "scaling": "strong",
+            "n_total": n_all, "d": 4 ** k, "pairs": pairs,
+            "kernel": "NCCL all-gather + pair_tile_kernel<SAD8X4> on balanced triangle row blocks"}

@@ -261,7 +261,7 @@ def test_gram_block_rectangular(D):
     ws = torch.empty(lib.kam_gram_block_workspace_bytes(150, 70), dtype=torch.uint8, device="cuda")
     _lib.check(lib.kam_gram_block(ops[0].data_ptr(), S[0].data_ptr(), G[0].data_ptr(), 150, ops[1].data_ptr(),
                                   S[1].data_ptr(), G[1].data_ptr(), 70, 0, d, 0, 0, 150, _lib.KAM_M_PEARSON, 0, None, None,
-                                  out.data_ptr(), 70, ws.data_ptr(), ws.numel(), st))
+                                  out.data_ptr(), 70, 0, ws.data_ptr(), ws.numel(), st))
     np.testing.assert_allclose(out.cpu().numpy(), O.cdist_rect(xa, xb, "pearson"), rtol=1e-5)
 
 

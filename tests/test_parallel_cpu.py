@@ -223,3 +223,68 @@ def test_kmers_to_file_streaming_writer_with_host_stand_in(tmp_path, monkeypatch
     backend.kmers_to_file(recs[10:], k, bits, "counts", got3, row_offset=10, total_rows=len(recs), create=False)
     backend.kmers_to_file(recs[:10], k, bits, "counts", got3, row_offset=0, total_rows=len(recs), create=False)
     assert open(got3, "rb").read() == open(want, "rb").read()
+
+
+# ---- a failure on ONE rank must fail EVERY rank (no rank left waiting in a collective), and remove the output ----
+def _failing_worker(rank, world, port, root, which, ret):
+    from kameris_b200 import formats
+    from kameris_b200.job_steps import backend
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        paths = backend.list_input_files(os.path.join(root, "fasta"))
+        out = os.path.join(root, "bad.mm-repr")
+        msg = "no error"
+        try:
+            if which == "kmers":
+                def produce(records, row_offset, total_rows):
+                    if rank == 1:
+                        raise ValueError("no FASTA record in a file of this shard")
+                backend.kmers_to_file_sharded(paths, 3, 16, "counts", out, dist, produce=produce)
+            else:
+                def compute(x_full, metrics, rows, tri_offset, slice_len):
+                    if rank == 1:
+                        raise RuntimeError("device out of memory (injected)")
+                    return _host_compute_all(x_full, metrics, rows, tri_offset, slice_len)
+                backend.dists_to_files_sharded(os.path.join(root, "good.mm-repr"), os.path.join(root, "bad"), ["manhat"],
+                                               dist, compute=compute)
+        except Exception as e:   # noqa: BLE001
+            msg = "%s: %s" % (type(e).__name__, e)
+        ret.put((rank, msg))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("which", ["kmers", "dists"])
+def test_sharded_steps_agree_on_failure(tmp_path, which):
+    from kameris_b200 import formats
+    from oracle import oracle as O
+    from tests.helpers import synth_records
+    root = str(tmp_path)
+    os.mkdir(os.path.join(root, "fasta"))
+    recs = synth_records(6, 200, seed=4)
+    for i, r in enumerate(recs):
+        with open(os.path.join(root, "fasta", "%04d.fasta" % i), "wb") as f:
+            f.write(b">x\n" + r + b"\n")
+    w = formats.repr_writer(os.path.join(root, "good.mm-repr"), np.zeros((1, 64), dtype=np.uint16), 6)
+    for r in recs:
+        w.write_matrix(O.cgr_count(r, 3, 16))
+    w.close()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_failing_worker, args=(r, 2, port, root, which, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(ret.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert "failed on another rank" in got[0], got          # the healthy rank is told, it does not hang
+    assert ("no FASTA record" in got[1]) if which == "kmers" else ("injected" in got[1]), got
+    assert not os.path.exists(os.path.join(root, "bad.mm-repr"))
+    assert not os.path.exists(os.path.join(root, "bad-manhat.mm-dist"))
