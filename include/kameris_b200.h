@@ -298,6 +298,23 @@ int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_
  * column panels longer in L2 at the price of more row panels in flight. */
 void kam_gram_set_strip(int row_tiles);
 
+/* ---------------------------------------------------------------------------------------------
+ * Peer memory (one process per GPU on one NVLink / NVSwitch box).  kam_peer_alloc gives device memory that
+ * kam_peer_export turns into a KAM_PEER_HANDLE_BYTES handle; another process passes the handle (sent through
+ * any channel, e.g. a torch.distributed all-gather) to kam_peer_open and gets a pointer it can READ with
+ * kam_peer_copy -- a copy-engine transfer over NVLink that occupies no SM, unlike NCCL send/recv kernels, so
+ * it does not disturb a persistent kernel that owns every SM (the Gram kernel whose next block's operand rows
+ * it fetches).  Opened handles are cached by the library; kam_peer_close unmaps one.  The owner must keep the
+ * buffer alive and unmodified until its readers are done (the callers use a barrier).
+ * ------------------------------------------------------------------------------------------- */
+#define KAM_PEER_HANDLE_BYTES 64
+int kam_peer_alloc(size_t bytes, void **d_ptr);
+int kam_peer_free(void *d_ptr);
+int kam_peer_export(const void *d_ptr, unsigned char *handle);
+int kam_peer_open(const unsigned char *handle, void **d_mapped);
+int kam_peer_close(void *d_mapped);
+int kam_peer_copy(void *d_dst, const void *d_src, size_t bytes, void *stream);
+
 /* Host-buffer form of the whole `distances` step: x is the n x d matrix read from a .mm-repr,
  * outputs are packed triangles (NULL = not requested).  euclid is taken between the rows as
  * stored (count vectors of a `counts` file, frequency vectors of a `frequencies` file).  Blocking;

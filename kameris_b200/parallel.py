@@ -7,6 +7,8 @@
              the triangle that holds 1/world of the pairs.  Rows [r0, r1) are CONTIGUOUS in the
              packed `.mm-dist` triangle, so each rank allocates only its slice; nothing is reduced.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -175,16 +177,71 @@ def ring_schedule(world):
     return plan
 
 
-def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group=None, sm_reserve=16, timing=None):
+_PEER = {}      # device index -> this rank's exported operand buffer and the peers' buffers it has opened
+
+
+def _peer_state(dev):
+    return _PEER.setdefault(dev.index, {"ptr": 0, "bytes": 0, "handle": b"", "opened": {}})
+
+
+def _peer_buffer(lib, dev, nbytes):
+    """this rank's exportable device buffer (kam_peer_alloc), grown when needed; (pointer, 64-byte handle)"""
+    import ctypes
+    from . import _lib
+    st = _peer_state(dev)
+    if st["bytes"] < nbytes:
+        if st["ptr"]:
+            torch.cuda.synchronize(dev)
+            _lib.check(lib.kam_peer_free(st["ptr"]))
+            st["ptr"], st["bytes"] = 0, 0
+        want = nbytes + nbytes // 8 + 4096
+        p = ctypes.c_void_p()
+        _lib.check(lib.kam_peer_alloc(want, ctypes.byref(p)))
+        h = ctypes.create_string_buffer(_lib.KAM_PEER_HANDLE_BYTES)
+        _lib.check(lib.kam_peer_export(p, h))
+        st["ptr"], st["bytes"], st["handle"] = p.value, want, h.raw
+    return st["ptr"], st["handle"]
+
+
+def _peer_open(lib, dev, src_rank, handle):
+    """pointer through which this rank reads the exported buffer of `src_rank` (cached per handle)"""
+    import ctypes
+    from . import _lib
+    st = _peer_state(dev)
+    old = st["opened"].get(src_rank)
+    if old is not None and old[0] == handle:
+        return old[1]
+    if old is not None:
+        lib.kam_peer_close(old[1])            # the owner re-allocated: drop the stale mapping
+    p = ctypes.c_void_p()
+    _lib.check(lib.kam_peer_open(handle, ctypes.byref(p)))
+    st["opened"][src_rank] = (handle, p.value)
+    return p.value
+
+
+def _align(x, a=256):
+    return (x + a - 1) // a * a
+
+
+def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group=None, sm_reserve=None, timing=None,
+              transport=None):
     """euclid / cosine / pearson over the rows of all ranks, block-cyclic pair ownership.
 
     Every rank converts its own rows once (uint8 operands when every count of every rank fits a
-    byte, else fp16), then at step s receives shard (rank+s) % world from its owner while computing
+    byte, else fp16), then at step s fetches shard (rank+s) % world from its owner while computing
     the block of step s-1; only world//2 shards reach each rank (half an all-gather) and the first
     block needs no communication at all.  Returns a list of blocks
         {"row_shard": a, "col_shard": c, "rows": (r0, r1), "tri": bool, metric: tensor[(r1-r0), n_c]}
     where entry [i - r0, j] is the distance between row i of shard a and row j of shard c (for a
     triangular block only j > i is meaningful).
+
+    transport: how a shard reaches the rank that needs it.
+      "peer" (default; ranks of one NVLink box): the owner keeps its operand rows and row statistics in a
+          buffer exported over CUDA IPC (kam_peer_*), the reader PULLS them with a copy-engine transfer on a
+          side stream -- no SM is involved, so the persistent cluster kernel keeps all 148 SMs;
+      "nccl": isend/irecv pairs; their kernels need SMs, `sm_reserve` of which (default 16) the Gram kernel
+          leaves free while transfers are in flight.
+    KAM_RING_TRANSPORT / KAM_RING_SM_RESERVE in the environment override the defaults.
 
     timing: a dict that receives, in milliseconds on this rank's compute stream, `prepare_ms` (operand
     conversion + statistics), `block_ms` (the Gram kernels) and `exposed_comm_ms` (time the compute stream
@@ -200,6 +257,10 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
     elem = D._ELEM[x_local.dtype]
     if x_local.dtype in (torch.float32, torch.float64):
         euclid_on_freq = True       # frequency rows: euclid between the rows as stored (kam_gram_tri does the same)
+    if transport is None:
+        transport = os.environ.get("KAM_RING_TRANSPORT", "peer")
+    if world == 1:
+        transport = "local"
     cur = torch.cuda.current_stream(dev)
     stream = cur.cuda_stream
     dpad = int(lib.kam_gram_dpad(d))
@@ -215,74 +276,105 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
             e.record(cur)
             marks.append((label, e))
 
-    if world > 1:
-        cnt = torch.tensor([n_loc], dtype=torch.int64, device=dev)
-        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(counts, cnt, group=group)
-        counts = [int(c.item()) for c in counts]
-    else:
-        counts = [n_loc]
-
-    # 1. local operand rows + statistics; the operand kind is a global decision
+    # 1. local operand rows + statistics, laid out [rows | S | G] in one buffer; the operand kind is a global
+    #    decision (all-reduced envelope flags)
     mark("start")
-    S = torch.zeros(max(n_loc, 1), dtype=torch.int64, device=dev)
-    G = torch.zeros(max(n_loc, 1), dtype=torch.int64, device=dev)
-    kind, esz = _lib.KAM_GRAM_U8, 1
+    keep = []
     for kind, esz in ((_lib.KAM_GRAM_U8, 1), (_lib.KAM_GRAM_F16, 2)):
-        op = torch.empty((max(n_loc, 1), dpad * esz), dtype=torch.uint8, device=dev)
+        rows_b = _align(max(n_loc, 1) * dpad * esz)
+        total_b = rows_b + 2 * max(n_loc, 1) * 8
+        if transport == "peer":
+            base, handle = _peer_buffer(lib, dev, total_b)
+        else:
+            own = torch.empty(total_b, dtype=torch.uint8, device=dev)
+            keep.append(own)
+            base, handle = own.data_ptr(), b""
         flags = torch.zeros(8, dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.kam_gram_prepare(x_local.data_ptr(), elem, n_loc, d, x_local.stride(0), kind, op.data_ptr(),
-                                            S.data_ptr(), G.data_ptr(), flags.data_ptr(), stream))
+            _lib.check(lib.kam_gram_prepare(x_local.data_ptr(), elem, n_loc, d, x_local.stride(0), kind, base,
+                                            base + rows_b, base + rows_b + max(n_loc, 1) * 8, flags.data_ptr(), stream))
         if world > 1:
             dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
-        mx, gmax = int(flags[0]), int(flags[1])
-        if int(flags[2]):
+        mx, gmax, bad = (int(v) for v in flags[:3].tolist())     # (host sync: every rank's rows are complete now)
+        if bad:
             raise ValueError("%d floating-point row(s) are not frequency vectors (count / sum): "
-                             "use distances_sharded()" % int(flags[2]))
+                             "use distances_sharded()" % bad)
         ok = (mx <= 255 and gmax < 2 ** 31) if kind == _lib.KAM_GRAM_U8 else (mx <= 2048 and gmax < 2 ** 24)
         if ok:
             break
-        del op
     else:
         raise NotImplementedError("counts outside the tensor-exact envelope: use distances_sharded()")
     mark("prepared")
 
-    # 2. row statistics of every shard (tiny), padded to the largest shard
-    cmax = max(counts)
-    sg = torch.zeros((2, cmax), dtype=torch.int64, device=dev)
-    sg[0, :n_loc], sg[1, :n_loc] = S[:n_loc], G[:n_loc]
+    # 2. who holds how many rows (and, for the peer transport, where)
     if world > 1:
-        all_sg = [torch.empty_like(sg) for _ in range(world)]
-        dist.all_gather(all_sg, sg, group=group)
+        info = torch.zeros(_lib.KAM_PEER_HANDLE_BYTES + 8, dtype=torch.uint8)
+        if handle:
+            info[:_lib.KAM_PEER_HANDLE_BYTES] = torch.frombuffer(bytearray(handle), dtype=torch.uint8)
+        info[_lib.KAM_PEER_HANDLE_BYTES:] = torch.tensor([n_loc], dtype=torch.int64).view(torch.uint8)
+        infos = torch.empty((world, info.numel()), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(infos, info.to(dev), group=group)
+        infos = infos.cpu()
+        counts = [int(infos[r, _lib.KAM_PEER_HANDLE_BYTES:].view(torch.int64)[0]) for r in range(world)]
+        handles = [bytes(infos[r, :_lib.KAM_PEER_HANDLE_BYTES].tolist()) for r in range(world)]
     else:
-        all_sg = [sg]
+        counts, handles = [n_loc], [handle]
 
-    # 3. post the ring transfers step by step (each pair of ops is its own NCCL group, so they
-    #    complete in order while the compute stream works on earlier blocks)
+    def layout(n):                  # offsets of S and G behind n operand rows, and the buffer's size
+        rb = _align(max(n, 1) * dpad * esz)
+        return rb, rb + max(n, 1) * 8, rb + 2 * max(n, 1) * 8
+
+    # 3. start fetching the shards of the later steps, in the order they are needed
     plan = ring_schedule(world)[rank]
-    bufs, works = {}, {}
-    for s in range(1, world // 2 + 1):
-        src, dst = (rank + s) % world, (rank - s) % world
-        bufs[s] = torch.empty((max(counts[src], 1), dpad * esz), dtype=torch.uint8, device=dev)
-        works[s] = dist.batch_isend_irecv([dist.P2POp(dist.isend, op, dst, group),
-                                           dist.P2POp(dist.irecv, bufs[s], src, group)])
+    bufs, ready = {}, {}
+    if transport == "peer":
+        side = _peer_state(dev).get("stream")
+        if side is None:
+            side = _peer_state(dev)["stream"] = torch.cuda.Stream(dev)
+        for s in range(1, world // 2 + 1):
+            src = (rank + s) % world
+            nb = layout(counts[src])[2]
+            bufs[s] = torch.empty(nb, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.kam_peer_copy(bufs[s].data_ptr(), _peer_open(lib, dev, src, handles[src]), nb,
+                                             side.cuda_stream))
+            ready[s] = torch.cuda.Event()
+            ready[s].record(side)
+    elif transport == "nccl":
+        # each pair of ops is its own NCCL group, so they complete in order while the compute stream works
+        for s in range(1, world // 2 + 1):
+            src, dst = (rank + s) % world, (rank - s) % world
+            bufs[s] = torch.empty(layout(counts[src])[2], dtype=torch.uint8, device=dev)
+            ready[s] = dist.batch_isend_irecv([dist.P2POp(dist.isend, keep[-1][:layout(n_loc)[2]], dst, group),
+                                               dist.P2POp(dist.irecv, bufs[s], src, group)])
+    elif world > 1:
+        raise ValueError("unknown ring transport %r" % transport)
 
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    sm_limit = max(sms - sm_reserve, 2) if (world > 1 and sm_reserve) else 0    # leave SMs to the NCCL transfers
+    if sm_reserve is None:
+        sm_reserve = int(os.environ.get("KAM_RING_SM_RESERVE", "16"))
+    if transport != "nccl":
+        sm_reserve = 0              # copy-engine transfers need no SM
+    last_step = world // 2
     out_blocks = []
     for s, a, c, part in plan:
+        # NCCL transport: SMs are left to the send/recv kernels only while transfers are still in flight
+        sm_limit = max(sms - sm_reserve, 2) if (sm_reserve and s < last_step) else 0
         if s > 0:
             mark("wait%d" % s)
-            for w in works[s]:
-                w.wait()            # the compute stream waits for the transfer, the host does not
+            if transport == "peer":
+                cur.wait_event(ready[s])
+            else:
+                for w in ready[s]:
+                    w.wait()        # the compute stream waits for the transfer, the host does not
         mark("block%d" % s)
+        mine, theirs = (base, n_loc), ((bufs[s].data_ptr(), counts[(rank + s) % world]) if s > 0 else (base, n_loc))
         if part == "hi":            # A = the received shard a (rows of the shared block), B = my shard
-            op_a, sg_a, n_a = bufs[s], all_sg[a], counts[a]
-            op_b, sg_b, n_b = op, all_sg[c], counts[c]
+            (pa, n_a), (pb, n_b) = theirs, mine
         else:                        # A = my shard, B = my shard (tri) or the received one
-            op_a, sg_a, n_a = op, all_sg[a], counts[a]
-            op_b, sg_b, n_b = (op, all_sg[c], counts[c]) if s == 0 else (bufs[s], all_sg[c], counts[c])
+            (pa, n_a), (pb, n_b) = mine, theirs
+        sa, ga, _ = layout(n_a)
+        sb, gb, _ = layout(n_b)
         h = n_a // 2
         r0, r1 = {"tri": (0, n_a), "full": (0, n_a), "lo": (0, h), "hi": (h, n_a)}[part]
         blk = {"row_shard": a, "col_shard": c, "rows": (r0, r1), "tri": part == "tri"}
@@ -296,8 +388,7 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
             ptrs[m] = t.data_ptr() - r0 * n_b * 4          # the kernel indexes rows from 0
         ws = torch.empty(lib.kam_gram_block_workspace_bytes(n_a, n_b), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.kam_gram_block(op_a.data_ptr(), sg_a[0].data_ptr(), sg_a[1].data_ptr(), n_a,
-                                          op_b.data_ptr(), sg_b[0].data_ptr(), sg_b[1].data_ptr(), n_b, kind, d,
+            _lib.check(lib.kam_gram_block(pa, pa + sa, pa + ga, n_a, pb, pb + sb, pb + gb, n_b, kind, d,
                                           int(part == "tri"), r0, r1, mask, int(euclid_on_freq),
                                           ptrs.get("euclid"), ptrs.get("cosine"), ptrs.get("pearson"), n_b, sm_limit,
                                           ws.data_ptr(), ws.numel(), stream))
@@ -305,15 +396,22 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
         out_blocks.append(blk)
     mark("end")
     cur.synchronize()
+    if transport == "peer":
+        torch.cuda.current_stream(dev).wait_stream(side)
+        dist.barrier(group)         # nobody overwrites or frees its exported rows while a peer still reads them
     for b in out_blocks:
         b.pop("_keep", None)
     if timing is not None:
-        t = {"prepare_ms": 0.0, "block_ms": 0.0, "exposed_comm_ms": 0.0, "other_ms": 0.0}
+        t = {"prepare_ms": 0.0, "block_ms": 0.0, "exposed_comm_ms": 0.0, "other_ms": 0.0, "blocks_ms": []}
         for (la, ea), (_, eb) in zip(marks[:-1], marks[1:]):
             dt = ea.elapsed_time(eb)
             key = "prepare_ms" if la == "start" else "block_ms" if la.startswith("block") else \
                 "exposed_comm_ms" if la.startswith("wait") else "other_ms"
             t[key] += dt
+            if la.startswith("block"):
+                t["blocks_ms"].append(round(dt, 3))
+        t["sm_reserve"] = sm_reserve
+        t["transport"] = transport
         t["operand"] = "uint8" if kind == _lib.KAM_GRAM_U8 else "fp16"
         t["recv_bytes"] = int(sum(b.numel() for b in bufs.values()))
         timing.update(t)
