@@ -1143,7 +1143,9 @@ __global__ void __launch_bounds__(LG_THREADS, 1) cgr_long_kernel(const uint2 *__
 //   * the read-out un-permutes: a warp's lanes walk the low word-index bits (conflict-free), each lane gathers the
 //     words of one 16-byte store for both halves and writes two vectors 2^k bins apart.
 // Per increment: 7 ALU-pipe + 4 FMA-pipe instructions + ATOMS + branch, one bit per trip.
-template <typename OUT>
+constexpr uint32_t LG2_QUEUE = 4;      // groups a thread prepares per round (16 B each)
+
+template <typename OUT, bool NESTED>
 __global__ void __launch_bounds__(LG_THREADS, 1) cgr_long2_kernel(const uint2 *__restrict__ planes,
                                                                   const uint64_t *__restrict__ base_start,
                                                                   const uint32_t *__restrict__ head_mask,
@@ -1160,10 +1162,13 @@ __global__ void __launch_bounds__(LG_THREADS, 1) cgr_long2_kernel(const uint2 *_
     constexpr uint32_t LB = BPS == 8 ? 3u : (BPS == 4 ? 2u : 1u);     // log2(BPS)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw);           // 32768 words: two uint16 counters each
+    uint4 *lq = reinterpret_cast<uint4 *>(smem_raw + 131072);          // [LQ][LG_THREADS] prepared groups
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
     __shared__ uint32_t s_item;
     __shared__ unsigned long long s_diff;
     __shared__ OUT s_lut[256];
     (void)s_lut;
+    constexpr uint32_t LQ = LG2_QUEUE;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t K = (uint32_t)k;
     const uint32_t tbits = 2u * K - 16u, n_tiles = 1u << tbits;      // tile = 65536 bins
@@ -1204,35 +1209,77 @@ __global__ void __launch_bounds__(LG_THREADS, 1) cgr_long2_kernel(const uint2 *_
         unsigned long long issued = 0;
         if (q.n >= (uint64_t)k) {
             // group g covers end positions [pa + G g, pa + G g + G): the windows of these positions are the bits
-            // [p0 + G g, p0 + G g + 32) of the stream
-            const uint64_t n_pos = q.n - (uint64_t)(k - 1);
-            const uint32_t n_groups = (uint32_t)((n_pos + G - 1) / G);
+            // [p0 + G g, p0 + G g + 32) of the stream.  (sequences on this path have < 2^31 bases)
+            const uint32_t n_pos = (uint32_t)(q.n - (uint64_t)(k - 1));
+            const uint32_t n_groups = (n_pos + G - 1) / G;
             const uint2 *wbase = planes + (q.p0 >> 5);
             const uint32_t bit0 = (uint32_t)(q.p0 & 31);
-            // per tile bit i: all-ones when bit (tbits-1-i) of t is set
             uint32_t cnt = 0;
-            for (uint32_t g = threadIdx.x; g < n_groups; g += LG_THREADS) {
-                const uint32_t bp = bit0 + G * g;          // < 2^32: sequences on this path are < 2^31 bases
-                const uint32_t w = bp >> 5, sh = bp & 31u;
-                const uint2 a = __ldg(wbase + w), b = __ldg(wbase + w + 1);
-                const uint32_t X = __funnelshift_r(a.x, b.x, sh), Y = __funnelshift_r(a.y, b.y, sh);
-                const uint64_t left = n_pos - (uint64_t)G * g;
-                uint32_t m = left >= G ? gmask : ((1u << (uint32_t)left) - 1u);
+            // Lanes find different numbers of in-tile k-mers in their groups.  The hardware runs the bit loop
+            // below with whatever lanes are at it (independent thread scheduling): a lane that has finished a
+            // group fetches its next one and re-joins, so the loop body itself stays ~93 % full -- but everything
+            // between two visits of the loop runs for a handful of lanes at a time (measured: 4.9 of 32).  So
+            // that part is kept to one 16-byte shared-memory load: the groups of LQ rounds are prepared by the
+            // whole warp in lock step (loads, funnel shifts, in-tile mask, bit reversal) into a per-thread queue.
+            for (uint32_t g0 = 0; g0 < n_groups; g0 += LQ * LG_THREADS) {
+#pragma unroll
+                for (uint32_t i = 0; i < LQ; ++i) {
+                    const uint32_t g = g0 + i * LG_THREADS + threadIdx.x;
+                    uint4 e = make_uint4(0, 0, 0, 0);
+                    if (g < n_groups) {
+                        const uint32_t bp = bit0 + G * g;
+                        const uint32_t w = bp >> 5, sh = bp & 31u;
+                        const uint2 a = __ldg(wbase + w), b = __ldg(wbase + w + 1);
+                        const uint32_t X = __funnelshift_r(a.x, b.x, sh), Y = __funnelshift_r(a.y, b.y, sh);
+                        const uint32_t left = n_pos - G * g;
+                        uint32_t m = left >= G ? gmask : ((1u << left) - 1u);
 #pragma unroll 1
-                for (uint32_t i = 0; i < tbits; ++i) {
-                    const uint32_t want = 0u - ((t >> (tbits - 1u - i)) & 1u);
-                    m &= ~((Y >> (K - 1u - i)) ^ want);
+                        for (uint32_t j = 0; j < tbits; ++j) {
+                            const uint32_t want = 0u - ((t >> (tbits - 1u - j)) & 1u);
+                            m &= ~((Y >> (K - 1u - j)) ^ want);
+                        }
+                        cnt += __popc(m);
+                        e = make_uint4(m, __brev(X), __brev(Y), 0);
+                    }
+                    lq[i * LG_THREADS + threadIdx.x] = e;
                 }
-                cnt += __popc(m);
-                const uint32_t RX = __brev(X), RY = __brev(Y);
-                while (m) {
-                    const uint32_t low = m & (0u - m);
-                    m ^= low;
-                    const uint32_t T = RX * low, U = RY * low;            // windows of this position at the top
-                    const uint32_t off = ((T >> shT) & MT) | ((U >> 14) & MU);
-                    const uint32_t inc = (uint32_t)((int)U >> 31) * 0xffff0001u + 1u;   // sign set: 0x10000, else 1
-                    atomicAdd(reinterpret_cast<uint32_t *>(smem_raw + off), inc);         // result unused
+                if constexpr (NESTED) {
+                    const uint4 *qp = lq + threadIdx.x;
+#pragma unroll 1
+                    for (uint32_t i = 0; i < LQ; ++i, qp += LG_THREADS) {
+                        const uint4 e = *qp;
+                        uint32_t m = e.x;
+                        const uint32_t RX = e.y, RY = e.z;
+                        while (m) {
+                            const uint32_t low = m & (0u - m);
+                            m ^= low;
+                            const uint32_t T = RX * low, U = RY * low;        // windows of this position at the top
+                            const uint32_t off = ((T >> shT) & MT) | ((U >> 14) & MU);
+                            const uint32_t inc = (uint32_t)((int)U >> 31) * 0xffff0001u + 1u;   // sign set: 0x10000, else 1
+                            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sbase + off), "r"(inc) : "memory");
+                        }
+                    }
+                } else {
+                    uint32_t i = 0;
+                    uint4 e = lq[threadIdx.x];
+                    uint32_t m = e.x, RX = e.y, RY = e.z;
+                    for (;;) {
+                        while (m == 0) {
+                            if (++i == LQ) break;
+                            e = lq[i * LG_THREADS + threadIdx.x];
+                            m = e.x, RX = e.y, RY = e.z;
+                        }
+                        if (m == 0) break;
+                        const uint32_t low = m & (0u - m);
+                        m ^= low;
+                        const uint32_t T = RX * low, U = RY * low;
+                        const uint32_t off = ((T >> shT) & MT) | ((U >> 14) & MU);
+                        const uint32_t inc = (uint32_t)((int)U >> 31) * 0xffff0001u + 1u;
+                        atomicAdd(reinterpret_cast<uint32_t *>(smem_raw + off), inc);
+                    }
                 }
+                __syncwarp();   // lanes leave the bit loops at different times and would stay apart (measured: the
+                                // next round's preparation then ran with 1.8 lanes per instruction)
             }
             issued = cnt;
         }
@@ -1529,10 +1576,11 @@ int run_overflow(const uint2 *planes, const uint64_t *base_start, const uint32_t
     const uint64_t items = (uint64_t)h.count << (2 * k - tile_log2);
     uint64_t grid = (uint64_t)kam_sm_count();   // 128 KB of counters: one CTA per SM, persistent over the item queue
     if (grid > items) grid = items;
-    if (k >= 9 && g_long_path == 1 && h.maxlen < (1ull << 31)) {
-        auto kern = cgr_long2_kernel<OUT>;
-        KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)grid, LG_THREADS, smem, st>>>(planes, base_start, head_mask, w.spill_list, w.spill_count, k, out,
+    if (k >= 9 && (g_long_path == 1 || g_long_path == 3) && h.maxlen < (1ull << 31)) {
+        auto kern = g_long_path == 1 ? cgr_long2_kernel<OUT, true> : cgr_long2_kernel<OUT, false>;
+        const size_t smem2 = smem + (size_t)LG2_QUEUE * LG_THREADS * 16;
+        KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        kern<<<(unsigned)grid, LG_THREADS, smem2, st>>>(planes, base_start, head_mask, w.spill_list, w.spill_count, k, out,
                                                        out_stride, w.queue2, w.ovf_flag, w.spill2_count, w.spill2_list,
                                                        w.spill2_maxlen);
     } else {
