@@ -956,7 +956,7 @@ __global__ void __launch_bounds__(SW_THREADS) cgr_sweep_kernel(const uint2 *__re
 constexpr int LG_THREADS = 1024;
 constexpr int LG_TILE_LOG2 = 16;
 constexpr int LG_MAX_K = 11;            // 64 passes at k=11 still beat RED.ADD; beyond that path B
-int g_long_path = 1;                    // test hook: 0 = everything path A declines goes straight to path B; 2 = first version of path L
+int g_long_path = 1;                    // test hook: 0 = everything path A declines goes straight to path B
 
 template <typename OUT>
 __global__ void __launch_bounds__(LG_THREADS, 1) cgr_long_kernel(const uint2 *__restrict__ planes,
@@ -1115,236 +1115,6 @@ __global__ void __launch_bounds__(LG_THREADS, 1) cgr_long_kernel(const uint2 *__
             }
             __syncthreads();
             for (uint32_t i = threadIdx.x; i < tile_words; i += LG_THREADS) tab[i] = 0;
-        }
-        // a wrapped counter makes held < issued: redo the sequence on path B (once, whichever tile sees it)
-        const unsigned long long d = warp_sum64(issued - held);
-        if (lane == 0 && d) atomicAdd(&s_diff, d);
-        __syncthreads();
-        if (threadIdx.x == 0 && s_diff != 0 && atomicExch(&ovf_flag[li], 1u) == 0u) {
-            spill2_list[atomicAdd(spill2_count, 1u)] = s;
-            atomicMax(spill2_maxlen, (unsigned long long)q.n);
-        }
-    }
-}
-
-// ---- path L, second version (k = 9..11) ---------------------------------------------------------------
-// The first version above is bound by the ALU pipe, not by the atomics: per increment it issues 13 ALU-pipe
-// instructions (64-bit funnel shifts for the two windows, masks, the half-word select) plus two FLO on the
-// quarter-rate pipe, and a warp instruction occupies the 16-lane ALU pipe for two cycles.  Here the work per
-// set bit is re-formulated so that most of it runs on the FMA pipe instead:
-//   * a thread takes G = 33 - k k-mer end positions whose windows all lie inside ONE 32-bit register per plane
-//     (bits [s, s+32) of the stream, fetched with one funnel shift);
-//   * the register is kept BIT-REVERSED (one BREV per plane and group): then `R * low`, with low = m & -m the
-//     isolated lowest set bit of the in-tile mask, is the register shifted so that the window of that position
-//     sits at the TOP of the product -- a plain IMAD replaces find-first-set + variable funnel shift;
-//   * the top bits of the two products ARE the counter address: the table is simply laid out in the bit-reversed
-//     order they come in (word = [reversed in-tile y bits above the oldest one][reversed x window], upper or lower
-//     16-bit half chosen by the sign of the y product = the oldest base's y bit), 2 shifts + 2 LOP3;
-//   * the read-out un-permutes: a warp's lanes walk the low word-index bits (conflict-free), each lane gathers the
-//     words of one 16-byte store for both halves and writes two vectors 2^k bins apart.
-// Per increment: 7 ALU-pipe + 4 FMA-pipe instructions + ATOMS + branch, one bit per trip.
-constexpr uint32_t LG2_QUEUE = 4;      // groups a thread prepares per round (16 B each)
-
-template <typename OUT, bool NESTED>
-__global__ void __launch_bounds__(LG_THREADS, 1) cgr_long2_kernel(const uint2 *__restrict__ planes,
-                                                                  const uint64_t *__restrict__ base_start,
-                                                                  const uint32_t *__restrict__ head_mask,
-                                                                  const uint32_t *__restrict__ list,
-                                                                  const uint32_t *__restrict__ n_list_ptr, int k,
-                                                                  OUT *__restrict__ out, uint64_t out_stride,
-                                                                  uint32_t *__restrict__ queue2,
-                                                                  uint32_t *__restrict__ ovf_flag,
-                                                                  uint32_t *__restrict__ spill2_count,
-                                                                  uint32_t *__restrict__ spill2_list,
-                                                                  unsigned long long *__restrict__ spill2_maxlen) {
-    constexpr bool IS_FREQ = !std::is_integral<OUT>::value;
-    constexpr int BPS = 16 / (int)sizeof(OUT);
-    constexpr uint32_t LB = BPS == 8 ? 3u : (BPS == 4 ? 2u : 1u);     // log2(BPS)
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw);           // 32768 words: two uint16 counters each
-    uint4 *lq = reinterpret_cast<uint4 *>(smem_raw + 131072);          // [LQ][LG_THREADS] prepared groups
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    __shared__ uint32_t s_item;
-    __shared__ unsigned long long s_diff;
-    __shared__ OUT s_lut[256];
-    (void)s_lut;
-    constexpr uint32_t LQ = LG2_QUEUE;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t K = (uint32_t)k;
-    const uint32_t tbits = 2u * K - 16u, n_tiles = 1u << tbits;      // tile = 65536 bins
-    const uint32_t G = 33u - K;                                       // end positions per thread and trip
-    const uint32_t gmask = (1u << G) - 1u;
-    const uint32_t ybits = 15u - K;                                   // in-tile y bits above the oldest one
-    const uint32_t MT = ((1u << K) - 1u) << 2, MU = ((1u << ybits) - 1u) << (K + 2u);
-    const uint32_t shT = 30u - K;
-    const uint32_t n_items = n_list_ptr[0] * n_tiles;
-
-    for (uint32_t i = threadIdx.x; i < 32768u; i += LG_THREADS) tab[i] = 0;
-
-    // (bin inside the tile) -> byte offset of its counter word and the increment that selects the half
-    auto slot_of = [&](uint32_t b, uint32_t &off, uint32_t &inc) {
-        const uint32_t x = b & ((1u << K) - 1u), yl = b >> K;
-        const uint32_t xr = __brev(x) >> (32u - K);
-        const uint32_t yr = ybits ? (__brev(yl >> 1) >> (32u - ybits)) : 0u;
-        off = ((yr << K) | xr) << 2;
-        inc = (yl & 1u) ? 0x10000u : 1u;
-    };
-
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            s_item = atomicAdd(queue2, 1u);
-            s_diff = 0;
-        }
-        __syncthreads();
-        const uint32_t item = s_item;
-        if (item >= n_items) break;
-        const uint32_t li = item >> tbits, t = item & (n_tiles - 1u);
-        const uint32_t s = list[li];
-        const SeqInfo q = seq_info(base_start, head_mask, s, k);
-        const double sum = (double)(q.n > q.lead ? q.n - q.lead : 0);
-        if constexpr (IS_FREQ) {
-            if (threadIdx.x < 256) s_lut[threadIdx.x] = convert_count<OUT>(threadIdx.x, 0.0, sum);
-        }
-        unsigned long long issued = 0;
-        if (q.n >= (uint64_t)k) {
-            // group g covers end positions [pa + G g, pa + G g + G): the windows of these positions are the bits
-            // [p0 + G g, p0 + G g + 32) of the stream.  (sequences on this path have < 2^31 bases)
-            const uint32_t n_pos = (uint32_t)(q.n - (uint64_t)(k - 1));
-            const uint32_t n_groups = (n_pos + G - 1) / G;
-            const uint2 *wbase = planes + (q.p0 >> 5);
-            const uint32_t bit0 = (uint32_t)(q.p0 & 31);
-            uint32_t cnt = 0;
-            // Lanes find different numbers of in-tile k-mers in their groups.  The hardware runs the bit loop
-            // below with whatever lanes are at it (independent thread scheduling): a lane that has finished a
-            // group fetches its next one and re-joins, so the loop body itself stays ~93 % full -- but everything
-            // between two visits of the loop runs for a handful of lanes at a time (measured: 4.9 of 32).  So
-            // that part is kept to one 16-byte shared-memory load: the groups of LQ rounds are prepared by the
-            // whole warp in lock step (loads, funnel shifts, in-tile mask, bit reversal) into a per-thread queue.
-            for (uint32_t g0 = 0; g0 < n_groups; g0 += LQ * LG_THREADS) {
-#pragma unroll
-                for (uint32_t i = 0; i < LQ; ++i) {
-                    const uint32_t g = g0 + i * LG_THREADS + threadIdx.x;
-                    uint4 e = make_uint4(0, 0, 0, 0);
-                    if (g < n_groups) {
-                        const uint32_t bp = bit0 + G * g;
-                        const uint32_t w = bp >> 5, sh = bp & 31u;
-                        const uint2 a = __ldg(wbase + w), b = __ldg(wbase + w + 1);
-                        const uint32_t X = __funnelshift_r(a.x, b.x, sh), Y = __funnelshift_r(a.y, b.y, sh);
-                        const uint32_t left = n_pos - G * g;
-                        uint32_t m = left >= G ? gmask : ((1u << left) - 1u);
-#pragma unroll 1
-                        for (uint32_t j = 0; j < tbits; ++j) {
-                            const uint32_t want = 0u - ((t >> (tbits - 1u - j)) & 1u);
-                            m &= ~((Y >> (K - 1u - j)) ^ want);
-                        }
-                        cnt += __popc(m);
-                        e = make_uint4(m, __brev(X), __brev(Y), 0);
-                    }
-                    lq[i * LG_THREADS + threadIdx.x] = e;
-                }
-                if constexpr (NESTED) {
-                    const uint4 *qp = lq + threadIdx.x;
-#pragma unroll 1
-                    for (uint32_t i = 0; i < LQ; ++i, qp += LG_THREADS) {
-                        const uint4 e = *qp;
-                        uint32_t m = e.x;
-                        const uint32_t RX = e.y, RY = e.z;
-                        while (m) {
-                            const uint32_t low = m & (0u - m);
-                            m ^= low;
-                            const uint32_t T = RX * low, U = RY * low;        // windows of this position at the top
-                            const uint32_t off = ((T >> shT) & MT) | ((U >> 14) & MU);
-                            const uint32_t inc = (uint32_t)((int)U >> 31) * 0xffff0001u + 1u;   // sign set: 0x10000, else 1
-                            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sbase + off), "r"(inc) : "memory");
-                        }
-                    }
-                } else {
-                    uint32_t i = 0;
-                    uint4 e = lq[threadIdx.x];
-                    uint32_t m = e.x, RX = e.y, RY = e.z;
-                    for (;;) {
-                        while (m == 0) {
-                            if (++i == LQ) break;
-                            e = lq[i * LG_THREADS + threadIdx.x];
-                            m = e.x, RX = e.y, RY = e.z;
-                        }
-                        if (m == 0) break;
-                        const uint32_t low = m & (0u - m);
-                        m ^= low;
-                        const uint32_t T = RX * low, U = RY * low;
-                        const uint32_t off = ((T >> shT) & MT) | ((U >> 14) & MU);
-                        const uint32_t inc = (uint32_t)((int)U >> 31) * 0xffff0001u + 1u;
-                        atomicAdd(reinterpret_cast<uint32_t *>(smem_raw + off), inc);
-                    }
-                }
-                __syncwarp();   // lanes leave the bit loops at different times and would stay apart (measured: the
-                                // next round's preparation then ran with 1.8 lanes per instruction)
-            }
-            issued = cnt;
-        }
-        if (threadIdx.x == 0 && q.lead < (uint32_t)(k - 1)) {   // dirty head (rare)
-            head_partials(planes, q, k, [&](uint32_t bin) {
-                if ((bin >> 16) != t) return;
-                uint32_t off, inc;
-                slot_of(bin & 0xffffu, off, inc);
-                atomicAdd(reinterpret_cast<uint32_t *>(smem_raw + off), inc);
-                issued += 1;
-            });
-        }
-        __syncthreads();
-
-        // ---- read-out.  Word index = [yr (ybits)][xr (K bits)] with xr bit (K-1-i) = bin bit i.  A lane owns
-        // the low 5 word-index bits (conflict-free); one work item fixes yr and the middle xr bits [5, K-LB); the
-        // BPS words of a 16-byte store differ in the top LB bits of xr.
-        OUT *trow = out + (uint64_t)s * out_stride + (uint64_t)t * 65536u;
-        unsigned long long held = 0;
-        const uint32_t mid_bits = K - LB - 5u;
-        const uint32_t n_work = 1u << (ybits + mid_bits);
-        const bool vec_ok = (reinterpret_cast<uintptr_t>(trow) & 15) == 0;
-        for (uint32_t wi = warp; wi < n_work; wi += LG_THREADS / 32) {
-            const uint32_t yr = wi >> mid_bits, mid = wi & ((1u << mid_bits) - 1u);
-            const uint32_t jw0 = (yr << K) | (mid << 5) | lane;
-            uint32_t lo[BPS], hi[BPS];
-#pragma unroll
-            for (uint32_t e = 0; e < (uint32_t)BPS; ++e) {
-                const uint32_t er = __brev(e) >> (32u - LB);                 // bin bit i of e -> xr bit K-1-i
-                const uint32_t jw = jw0 | (er << (K - LB));
-                const uint32_t wv = tab[jw];
-                if (wv) tab[jw] = 0;
-                lo[e] = wv & 0xffffu;
-                hi[e] = wv >> 16;
-                held += lo[e] + hi[e];
-            }
-            // output bin of e = 0, lower half: x = rev_K(xr without the e bits), y_low = rev(yr) << 1
-            const uint32_t xr0 = (mid << 5) | lane;
-            const uint32_t x0 = __brev(xr0) >> (32u - K);
-            const uint32_t yl0 = ybits ? ((__brev(yr) >> (32u - ybits)) << 1) : 0u;
-            OUT *p0 = trow + ((uint64_t)yl0 << K) + x0, *p1 = p0 + ((uint64_t)1 << K);
-            union {
-                uint4 v;
-                OUT e[BPS];
-            } u0, u1;
-#pragma unroll
-            for (int e = 0; e < BPS; ++e) {
-                if constexpr (IS_FREQ) {
-                    u0.e[e] = lo[e] < 256u ? s_lut[lo[e]] : convert_count<OUT>(lo[e], 0.0, sum);
-                    u1.e[e] = hi[e] < 256u ? s_lut[hi[e]] : convert_count<OUT>(hi[e], 0.0, sum);
-                } else {
-                    u0.e[e] = (OUT)lo[e];
-                    u1.e[e] = (OUT)hi[e];
-                }
-            }
-            if (vec_ok) {
-                st_stream16(p0, u0.v);
-                st_stream16(p1, u1.v);
-            } else {
-#pragma unroll
-                for (int e = 0; e < BPS; ++e) {
-                    p0[e] = u0.e[e];
-                    p1[e] = u1.e[e];
-                }
-            }
         }
         // a wrapped counter makes held < issued: redo the sequence on path B (once, whichever tile sees it)
         const unsigned long long d = warp_sum64(issued - held);
@@ -1576,20 +1346,11 @@ int run_overflow(const uint2 *planes, const uint64_t *base_start, const uint32_t
     const uint64_t items = (uint64_t)h.count << (2 * k - tile_log2);
     uint64_t grid = (uint64_t)kam_sm_count();   // 128 KB of counters: one CTA per SM, persistent over the item queue
     if (grid > items) grid = items;
-    if (k >= 9 && (g_long_path == 1 || g_long_path == 3) && h.maxlen < (1ull << 31)) {
-        auto kern = g_long_path == 1 ? cgr_long2_kernel<OUT, true> : cgr_long2_kernel<OUT, false>;
-        const size_t smem2 = smem + (size_t)LG2_QUEUE * LG_THREADS * 16;
-        KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        kern<<<(unsigned)grid, LG_THREADS, smem2, st>>>(planes, base_start, head_mask, w.spill_list, w.spill_count, k, out,
-                                                       out_stride, w.queue2, w.ovf_flag, w.spill2_count, w.spill2_list,
-                                                       w.spill2_maxlen);
-    } else {
-        auto kern = cgr_long_kernel<OUT>;
-        KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)grid, LG_THREADS, smem, st>>>(planes, base_start, head_mask, w.spill_list, h.count, k, out,
-                                                       out_stride, w.queue2, w.ovf_flag, w.spill2_count, w.spill2_list,
-                                                       w.spill2_maxlen);
-    }
+    auto kern = cgr_long_kernel<OUT>;
+    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, LG_THREADS, smem, st>>>(planes, base_start, head_mask, w.spill_list, h.count, k, out,
+                                                   out_stride, w.queue2, w.ovf_flag, w.spill2_count, w.spill2_list,
+                                                   w.spill2_maxlen);
     KAM_CUDA(cudaGetLastError());
     SpillInfo h2;
     KAM_CUDA(cudaMemcpyAsync(&h2, w.queue2, 16, cudaMemcpyDeviceToHost, st));

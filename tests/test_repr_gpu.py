@@ -225,14 +225,12 @@ def test_tile_kernel_scan_variants(R, k, out, bits):
                 assert np.array_equal(got[i], O.frequencies(c), equal_nan=True), (k, i)
 
 
-@pytest.mark.parametrize("long_path", [1, 2, 0])
+@pytest.mark.parametrize("long_path", [1, 0])
 @pytest.mark.parametrize("k,bits", [(9, 16), (9, 32), (8, 16), (7, 16), (2, 16), (10, 16), (11, 32), (12, 16)])
 def test_long_sequences_spill_path(R, k, bits, long_path):
     """Sequences beyond path A (length, or uint8 overflow) take the shared-memory uint16 tile kernel
-    (path L, 7 <= k <= 11: long_path=1 is its second version -- bit-reversed planes, multiply instead of
-    find-first-set + funnel shift, permuted table -- for k >= 9, long_path=2 the first version for every k)
-    and, when even a uint16 counter overflows (70 000 x 'A'), the RED.ADD path B; long_path=0 sends all of
-    them to path B directly.  Dirty heads included."""
+    (path L, 7 <= k <= 11) and, when even a uint16 counter overflows (70 000 x 'A'), the RED.ADD path B;
+    long_path=0 sends all of them to path B directly.  Dirty heads included."""
     recs = synth_records(3, 400000, seed=11 + k, dirty=0.001) + [b"ACGT" * 3000, b"A" * 70000,
                                                                  synth_records(1, 9000, seed=2)[0],
                                                                  b"NNA" + synth_records(1, 200000, seed=3)[0],
