@@ -385,3 +385,112 @@ def test_gram_ring_on_frequency_rows(D):
     bad = np.abs(np.random.Generator(np.random.PCG64(1)).standard_normal((20, 64)))
     with pytest.raises(ValueError):
         parallel.gram_ring(_dev(bad), ("cosine",))
+
+
+# ---- Gram kernels past one tile per CTA pair: the persistent loop, TMEM double buffering, stage-ring wrap ----
+def _ref_metrics_f64(xd64):
+    """float64 reference of all pairs on the device: exact Gram (sums < 2^53) + the scipy formulas"""
+    g = xd64 @ xd64.T
+    s = xd64.sum(dim=1)
+    d = xd64.shape[1]
+    gii = torch.diagonal(g)
+    cos = 1.0 - g / torch.sqrt(gii[:, None] * gii[None, :])
+    cov = g - s[:, None] * s[None, :] / d
+    var = gii - s * s / d
+    pea = 1.0 - cov / torch.sqrt(var[:, None] * var[None, :])
+    f2 = gii / (s * s)
+    euc = torch.sqrt(torch.clamp(f2[:, None] + f2[None, :] - 2.0 * g / (s[:, None] * s[None, :]), min=0.0))
+    return {"euclid": euc, "cosine": cos, "pearson": pea}
+
+
+def test_gram_many_waves_every_pair_every_variant(D):
+    """N = 6450, D = 4096: 26 x 26 / 2 = 351 tiles of 256 x 256 on 74 CTA pairs (4.7 waves) -- every CTA pair
+    runs the persistent loop several times, so the TMEM accumulator hand-over (tfull / tempty phases), the
+    wrap of the shared-memory stage ring across tiles and the strip schedule are all exercised.  EVERY pair is
+    compared with a float64 Gram (exact) + the scipy formulas, for the three kernel variants and both operand
+    kinds; the variants must also agree bit for bit."""
+    from kameris_b200 import _lib
+    lib = _lib.load()
+    n, d = 6450, 4096
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    x = torch.poisson(torch.full((n, d), 2.2, device="cuda"), generator=g)      # counts 0..~14
+    x[17] *= 9                                                                   # a row with larger counts (<= 255)
+    xd = x.to(torch.int32).to(torch.uint16)
+    ref = _ref_metrics_f64(x.to(torch.float64))
+    iu = torch.triu_indices(n, n, 1, device="cuda")
+    want = {m: ref[m][iu[0], iu[1]] for m in ref}
+    del ref
+    first = None
+    try:
+        for pair, cl in ((1, 2), (0, 2), (0, 1)):
+            lib.kam_gram_set_pair(pair)
+            lib.kam_gram_set_cluster(cl)
+            for f16 in (False, True):
+                got = D.gram_tri(xd, ("euclid", "cosine", "pearson"), euclid_on_freq=True, force_f16=f16)
+                for m in got:
+                    err = ((got[m].double() - want[m]).abs() / want[m].abs().clamp(min=1e-30)).max().item()
+                    assert err < 2e-6, (pair, cl, f16, m, err)
+                if first is None:
+                    first = got
+                else:
+                    for m in got:
+                        assert torch.equal(got[m], first[m]), (pair, cl, f16, m)
+    finally:
+        lib.kam_gram_set_pair(1)
+        lib.kam_gram_set_cluster(2)
+
+
+def test_gram_block_halves_and_rectangles_many_waves(D):
+    """kam_gram_block as the ring uses it, at sizes with several waves of tiles: a full rectangular block, its
+    `lo` / `hi` row halves (they must tile the full block exactly) and a triangular block with dense output,
+    every entry against the float64 reference."""
+    from kameris_b200 import _lib
+    lib = _lib.load()
+    na, nb, d = 3300, 3100, 4096
+    g = torch.Generator(device="cuda")
+    g.manual_seed(6)
+    xa = torch.poisson(torch.full((na, d), 1.7, device="cuda"), generator=g)
+    xb = torch.poisson(torch.full((nb, d), 2.9, device="cuda"), generator=g)
+    ref = _ref_metrics_f64(torch.cat([xa, xb]).to(torch.float64))
+    st = torch.cuda.current_stream().cuda_stream
+    dpad = int(lib.kam_gram_dpad(d))
+    ops = []
+    for x in (xa, xb):
+        xd = x.to(torch.int32).to(torch.uint16)
+        op = torch.empty((x.shape[0], dpad), dtype=torch.uint8, device="cuda")
+        s = torch.zeros(x.shape[0], dtype=torch.int64, device="cuda")
+        gg = torch.zeros(x.shape[0], dtype=torch.int64, device="cuda")
+        fl = torch.zeros(8, dtype=torch.int64, device="cuda")
+        _lib.check(lib.kam_gram_prepare(xd.data_ptr(), 1, x.shape[0], d, d, 0, op.data_ptr(), s.data_ptr(), gg.data_ptr(),
+                                        fl.data_ptr(), st))
+        ops.append((op, s, gg, x.shape[0]))
+
+    def block(a, b, tri, r0, r1, metric_bit):
+        (oa, sa, ga, n_a), (ob, sb, gb, n_b) = ops[a], ops[b]
+        out = torch.full((n_a, n_b), -7.0, dtype=torch.float32, device="cuda")
+        ws = torch.empty(lib.kam_gram_block_workspace_bytes(n_a, n_b), dtype=torch.uint8, device="cuda")
+        p = out.data_ptr()
+        _lib.check(lib.kam_gram_block(oa.data_ptr(), sa.data_ptr(), ga.data_ptr(), n_a, ob.data_ptr(), sb.data_ptr(),
+                                      gb.data_ptr(), n_b, 0, d, int(tri), r0, r1, metric_bit, 1,
+                                      p if metric_bit == 4 else None, p if metric_bit == 8 else None,
+                                      p if metric_bit == 16 else None, n_b, 0, ws.data_ptr(), ws.numel(), st))
+        torch.cuda.synchronize()
+        return out
+
+    def close(got, want):
+        return ((got.double() - want).abs() / want.abs().clamp(min=1e-30)).max().item() < 2e-6
+
+    for name, bit in (("cosine", 8), ("pearson", 16), ("euclid", 4)):
+        want = ref[name][:na, na:]
+        full = block(0, 1, False, 0, na, bit)
+        assert close(full, want), name
+        h = na // 2
+        lo, hi = block(0, 1, False, 0, h, bit), block(0, 1, False, h, na, bit)
+        assert torch.equal(lo[:h], full[:h]) and torch.equal(hi[h:], full[h:]), name
+        assert bool((lo[h:] == -7.0).all()) and bool((hi[:h] == -7.0).all()), "rows outside the range were written"
+    tri = block(1, 1, True, 0, nb, 8)
+    iu = torch.triu_indices(nb, nb, 1, device="cuda")
+    assert close(tri[iu[0], iu[1]], ref["cosine"][na:, na:][iu[0], iu[1]])
+    il = torch.tril_indices(nb, nb, 0, device="cuda")
+    assert bool((tri[il[0], il[1]] == -7.0).all()), "a triangular block wrote on or below its diagonal"
