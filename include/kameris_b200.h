@@ -264,6 +264,10 @@ void kam_gram_set_cluster(int cl);
  * tile per cluster of two CTAs, B split between them); 0 the cluster-multicast cta_group::1 kernel.  Needs
  * cluster 2.  Both produce the exact integer Gram matrix, hence identical outputs. */
 void kam_gram_set_pair(int on);
+/* test hook: 0 sends count vectors outside the uint8 / fp16 envelopes straight to the integer CUDA-core Gram;
+ * default 1 tries the limb-split tensor path first (counts <= 65535: c = 256 hi + lo, three kind::i8 Grams
+ * combined exactly in float64; taken when the byte limbs keep every int32 accumulator below 2^31). */
+void kam_gram_set_limb(int on);
 int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                  uint32_t row_begin, uint32_t row_end, unsigned metrics, int euclid_on_freq,
                  float *d_tri_euclid, float *d_tri_cosine, float *d_tri_pearson, void *d_ws,

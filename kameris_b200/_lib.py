@@ -66,6 +66,7 @@ SIGNATURES = {
     "kam_gram_set_float_recover": (None, [c_int]),
     "kam_gram_set_cluster": (None, [c_int]),
     "kam_gram_set_pair": (None, [c_int]),
+    "kam_gram_set_limb": (None, [c_int]),
     "kam_gram_dpad": (c_uint64, [c_uint64]),
     "kam_gram_prepare": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),

@@ -17,6 +17,8 @@ struct RowK {
 
 struct GramOut {
     float *euclid, *cosine, *pearson;   // nullptr = not requested
+    int *raw = nullptr;                 // when set: the exact int32 Gram entry itself, dense [row * ld + col]
+                                        // (limb-split path: three partial Grams are combined afterwards)
 };
 
 // geometry of one Gram block: rows of matrix A against rows of matrix B

@@ -31,6 +31,7 @@
 // Only tiles that contain a pair i<j are scheduled (upper triangle).
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -247,6 +248,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
                     for (int c = 0; c < 32; ++c) {
                         const uint32_t j = cb + c;
                         if (j >= gg.n_b || (gg.tri && j <= row)) continue;
+                        if (I8 && go.raw) {
+                            go.raw[base + j] = (int)v[c];
+                            continue;
+                        }
                         const double g = I8 ? (double)(int)v[c] : (double)__uint_as_float(v[c]);
                         const RowK cj = colk[ch * 32 + c];
                         gram_store(go, base + j, g, ri, cj);
@@ -458,6 +463,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_pair_kernel(const __grid_co
                     for (int c = 0; c < 32; ++c) {
                         const uint32_t j = cb + c;
                         if (j >= gg.n_b || (gg.tri && j <= row)) continue;
+                        if (I8 && go.raw) {
+                            go.raw[base + j] = (int)v[c];
+                            continue;
+                        }
                         const double g = I8 ? (double)(int)v[c] : (double)__uint_as_float(v[c]);
                         const RowK cj = colk[ch * 32 + c];
                         gram_store(go, base + j, g, ri, cj);
@@ -553,6 +562,91 @@ __global__ void __launch_bounds__(256) gram_prepass_kernel(const T *__restrict__
     }
 }
 
+// ---- limb-split path: counts up to 65535 and sums of squares far beyond 2^31 on the integer tensor cores ---
+// c = 256 hi + lo  =>  G_ij = LL_ij + 256 (LH_ij + HL_ij) + 65536 HH_ij with LL = lo lo^T, ... : three
+// kind::i8 Grams.  Every int32 accumulator stays exact as long as its FINAL value does (all terms are
+// non-negative, so partial sums never exceed it), and by Cauchy-Schwarz LL_ij <= max_r sum lo_r^2 etc.; the
+// pre-pass measures those maxima (flags[3], flags[4]).  Operand rows: XA = [lo | hi], XB = [hi | lo] (2 dpad
+// bytes each): LL and HH are Grams of the two halves of XA, and LH + HL is ONE Gram of XA against XB over the
+// doubled K.  The three int32 results of a block of rows go to scratch and a combine kernel applies the metric
+// formulas to LL + 256 MID + 65536 HH in float64 (< 2^49: exact).
+template <typename T>
+__global__ void __launch_bounds__(256) gram_prepass_limb_kernel(const T *__restrict__ x, uint32_t n, uint64_t d,
+                                                                uint64_t ld, uint64_t dpad, uint8_t *__restrict__ xa,
+                                                                uint8_t *__restrict__ xb,
+                                                                unsigned long long *__restrict__ S,
+                                                                unsigned long long *__restrict__ G,
+                                                                unsigned long long *__restrict__ flags) {
+    __shared__ unsigned long long red[5][8];
+    const uint32_t row = blockIdx.x;
+    const T *xr = x + (uint64_t)row * ld;
+    uint8_t *ra = xa + (uint64_t)row * 2 * dpad, *rb = xb + (uint64_t)row * 2 * dpad;
+    unsigned long long s = 0, g = 0, ll = 0, hh = 0;
+    unsigned mx = 0;
+    for (uint64_t e = (uint64_t)threadIdx.x * 4; e < dpad; e += 256 * 4) {   // dpad is a multiple of 128
+        uint32_t lo4 = 0, hi4 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const unsigned c = e + i < d ? (unsigned)xr[e + i] : 0u;
+            const unsigned lo = c & 0xffu, hi = (c >> 8) & 0xffu;
+            s += c;
+            g += (unsigned long long)c * c;
+            ll += lo * lo;
+            hh += hi * hi;
+            mx = max(mx, c);
+            lo4 |= lo << (8 * i);
+            hi4 |= hi << (8 * i);
+        }
+        *reinterpret_cast<uint32_t *>(ra + e) = lo4;
+        *reinterpret_cast<uint32_t *>(ra + dpad + e) = hi4;
+        *reinterpret_cast<uint32_t *>(rb + e) = hi4;
+        *reinterpret_cast<uint32_t *>(rb + dpad + e) = lo4;
+    }
+    s = warp_sum64(s);
+    g = warp_sum64(g);
+    ll = warp_sum64(ll);
+    hh = warp_sum64(hh);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s;
+        red[1][threadIdx.x >> 5] = g;
+        red[2][threadIdx.x >> 5] = mx;
+        red[3][threadIdx.x >> 5] = ll;
+        red[4][threadIdx.x >> 5] = hh;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t[5] = {0, 0, 0, 0, 0};
+        for (int w = 0; w < 8; ++w) {
+            t[0] += red[0][w];
+            t[1] += red[1][w];
+            t[2] = red[2][w] > t[2] ? red[2][w] : t[2];
+            t[3] += red[3][w];
+            t[4] += red[4][w];
+        }
+        S[row] = t[0];
+        G[row] = t[1];
+        atomicMax(&flags[0], t[2]);
+        atomicMax(&flags[1], t[1]);
+        atomicMax(&flags[3], t[3]);
+        atomicMax(&flags[4], t[4]);
+    }
+}
+
+// one thread per (row, column) of the row block [r0, r1): exact G from the three partial Grams -> metrics
+__global__ void __launch_bounds__(256) gram_limb_combine_kernel(const int *__restrict__ ll, const int *__restrict__ mid,
+                                                                const int *__restrict__ hh, uint32_t n, uint32_t r0,
+                                                                uint32_t r1, const RowK *__restrict__ rk, GramOut go) {
+    const uint32_t row = r0 + blockIdx.y;
+    const uint32_t j = blockIdx.x * 256 + threadIdx.x;
+    if (row >= r1 || j >= n || j <= row) return;
+    const size_t at = (size_t)(row - r0) * n + j;
+    const double g = (double)ll[at] + 256.0 * (double)mid[at] + 65536.0 * (double)hh[at];
+    const long long idx = (long long)n * row - (long long)row * (row + 3) / 2 - 1 + j;
+    gram_store(go, idx, g, rk[row], rk[j]);
+}
+
 __global__ void rowk_kernel(const unsigned long long *__restrict__ S, const unsigned long long *__restrict__ G,
                             uint32_t n, double D, int euclid_on_freq, RowK *__restrict__ rk) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -575,6 +669,7 @@ __global__ void rowk_kernel(const unsigned long long *__restrict__ S, const unsi
 
 bool g_force_f16 = false;
 bool g_float_recover = true;   // test hook: false = floating-point rows always take the float64 CUDA-core Gram
+bool g_limb = true;        // test hook: false = inputs outside the uint8 / fp16 envelopes skip the limb-split tensor path
 bool g_pair = true;        // cta_group::2 kernel (gram_pair_kernel, default) or the cluster-multicast one
 uint32_t g_cluster = 2;
 uint32_t g_strip = 12;      // row tiles (of 128) per strip of the tile order (tuning hook)
@@ -607,16 +702,20 @@ int prepass_dispatch(const void *x, int elem, uint32_t n, uint64_t d, uint64_t l
                              : run_prepass<uint32_t>(x, n, d, ld, i8, h, S, G, flags, st);
 }
 
+// kext: K extent of the operand rows in elements (0 = dpad_of(d)); pitch: their row pitch in bytes (0 = packed).
+// The limb-split path runs on sub-ranges of rows that hold [low bytes | high bytes] side by side.
 template <bool I8, int CL, bool PAIR = false>
 int launch_gram(const void *opA, const void *opB, const uint2 *d_tiles, size_t n_tiles, uint64_t d,
-                const GramGeom &gg, GramOut go, uint32_t sm_limit, cudaStream_t st) {
-    const uint64_t dpad = dpad_of(d);
+                const GramGeom &gg, GramOut go, uint32_t sm_limit, cudaStream_t st, uint64_t kext = 0,
+                uint64_t pitch = 0) {
     const uint32_t esz = I8 ? 1 : 2, bk = BK_BYTES / esz;
+    const uint64_t dpad = kext ? kext : dpad_of(d);
+    if (!pitch) pitch = dpad * esz;
     const CUtensorMapDataType dt = I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap tmA, tmB;
     int rc;
-    if ((rc = kam_make_tmap_2d(&tmA, dt, esz, opA, dpad, gg.n_a, dpad * esz, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = kam_make_tmap_2d(&tmB, dt, esz, opB, dpad, gg.n_b, dpad * esz, bk, BN / CL, CU_TENSOR_MAP_SWIZZLE_128B)))
+    if ((rc = kam_make_tmap_2d(&tmA, dt, esz, opA, dpad, gg.n_a, pitch, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = kam_make_tmap_2d(&tmB, dt, esz, opB, dpad, gg.n_b, pitch, bk, BN / CL, CU_TENSOR_MAP_SWIZZLE_128B)))
         return rc;
     const size_t smem = (PAIR ? (size_t)P_STAGES * P_STAGE_BYTES : (size_t)G_STAGES * STAGE_BYTES) + BN * sizeof(RowK) + 1024;
     auto kern = PAIR ? gram_pair_kernel<I8> : gram_tcgen05_kernel<I8, CL>;
@@ -724,7 +823,7 @@ int tile_list(const GramGeom &gg, uint32_t CL, cudaStream_t st, const uint2 **d_
 }
 
 int gram_block(const void *opA, const void *opB, bool i8, uint64_t d, const GramGeom &gg, GramOut go, uint32_t sm_limit,
-               cudaStream_t st) {
+               cudaStream_t st, uint64_t kext = 0, uint64_t pitch = 0) {
     const uint32_t CL = g_cluster;
     const uint2 *d_tiles = nullptr;
     size_t n_tiles = 0;
@@ -732,13 +831,25 @@ int gram_block(const void *opA, const void *opB, bool i8, uint64_t d, const Gram
     if (rc) return rc;
     if (n_tiles == 0) return KAM_OK;
     if (CL == 2 && g_pair)
-        return i8 ? launch_gram<true, 2, true>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st)
-                  : launch_gram<false, 2, true>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st);
+        return i8 ? launch_gram<true, 2, true>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st, kext, pitch)
+                  : launch_gram<false, 2, true>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st, kext, pitch);
     if (CL == 2)
-        return i8 ? launch_gram<true, 2>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st)
-                  : launch_gram<false, 2>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st);
-    return i8 ? launch_gram<true, 1>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st)
-              : launch_gram<false, 1>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st);
+        return i8 ? launch_gram<true, 2>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st, kext, pitch)
+                  : launch_gram<false, 2>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st, kext, pitch);
+    return i8 ? launch_gram<true, 1>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st, kext, pitch)
+              : launch_gram<false, 1>(opA, opB, d_tiles, n_tiles, d, gg, go, sm_limit, st, kext, pitch);
+}
+
+// limb-split path: rows per scratch block (a multiple of 256) and the bytes it needs next to the operands
+inline uint32_t limb_rows(uint32_t n) {
+    uint64_t r = (256ull << 20) / ((uint64_t)n * 12) / 256 * 256;
+    const uint64_t nup = ((uint64_t)n + 255) / 256 * 256;
+    if (r < 256) r = 256;
+    if (r > nup) r = nup;
+    return (uint32_t)r;
+}
+inline size_t limb_bytes(uint32_t n, uint64_t d) {
+    return kam_align_up((size_t)n * dpad_of(d) * 4, 1024) + (size_t)3 * limb_rows(n) * n * 4 + 1024;
 }
 
 struct GramWs {
@@ -763,7 +874,8 @@ inline size_t gram_layout(uint32_t n, uint64_t d, void *base, GramWs *w, bool wi
     void *tiles = take(max_tiles(n, n) * sizeof(uint2));
     // the fp16 matrix and the integer-fallback operand are never live together: share the space
     const size_t hb = (size_t)n * dpad_of(d) * 2, ib = with_int ? kam_int_gram_xt_bytes(n, d) : 0;
-    void *big = take(hb > ib ? hb : ib);
+    const size_t lb = with_int ? limb_bytes(n, d) : 0;
+    void *big = take(std::max(hb, std::max(ib, lb)));
     if (w) {
         w->flags = (unsigned long long *)flags;
         w->S = (unsigned long long *)S;
@@ -921,6 +1033,50 @@ int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
                           hflags[0], hflags[1]);
             return KAM_E_WORKSPACE;
         }
+        // counts up to 65535 whose byte limbs keep every int32 partial Gram exact: limb-split tensor path
+        if (g_limb && !is_float && hflags[0] <= 65535) {
+            uint8_t *xa = (uint8_t *)w.h, *xb = xa + (size_t)n * dpad_of(d) * 2;
+            int *scratch = (int *)((char *)w.h + kam_align_up((size_t)n * dpad_of(d) * 4, 1024));
+            KAM_CUDA(cudaMemsetAsync(w.flags, 0, 64, st));
+            if (elem == KAM_U8)
+                gram_prepass_limb_kernel<uint8_t><<<n, 256, 0, st>>>((const uint8_t *)d_x, n, d, ld, dpad_of(d), xa, xb, w.S, w.G, w.flags);
+            else if (elem == KAM_U16)
+                gram_prepass_limb_kernel<uint16_t><<<n, 256, 0, st>>>((const uint16_t *)d_x, n, d, ld, dpad_of(d), xa, xb, w.S, w.G, w.flags);
+            else
+                gram_prepass_limb_kernel<uint32_t><<<n, 256, 0, st>>>((const uint32_t *)d_x, n, d, ld, dpad_of(d), xa, xb, w.S, w.G, w.flags);
+            KAM_CUDA(cudaGetLastError());
+            unsigned long long lf[5] = {0, 0, 0, 0, 0};
+            KAM_CUDA(cudaMemcpyAsync(lf, w.flags, 40, cudaMemcpyDeviceToHost, st));
+            KAM_CUDA(cudaStreamSynchronize(st));
+            const double lim = 2147483647.0;
+            if ((double)lf[3] <= lim && (double)lf[4] <= lim && 2.0 * sqrt((double)lf[3] * (double)lf[4]) <= lim) {
+                const uint64_t dp = dpad_of(d);
+                const uint32_t R = limb_rows(n);
+                int *sll = scratch, *smid = scratch + (size_t)R * n, *shh = scratch + (size_t)2 * R * n;
+                for (uint32_t rb = row_begin / 256 * 256; rb < row_end; rb += R) {
+                    GramGeom gg;
+                    gg.n_a = gg.n_b = n;
+                    gg.row_begin = rb > row_begin ? rb : row_begin;
+                    gg.row_end = rb + R < row_end ? rb + R : row_end;
+                    gg.tri = 1;
+                    gg.ld = n;
+                    gg.rk_a = gg.rk_b = w.rk;
+                    const size_t shift = (size_t)gg.row_begin * n;     // scratch row 0 = row gg.row_begin
+                    GramOut gr;
+                    gr.euclid = gr.cosine = gr.pearson = nullptr;
+                    gr.raw = sll - shift;
+                    if ((rc = gram_block(xa, xa, true, d, gg, gr, 0, st, dp, 2 * dp))) return rc;
+                    gr.raw = shh - shift;
+                    if ((rc = gram_block(xa + dp, xa + dp, true, d, gg, gr, 0, st, dp, 2 * dp))) return rc;
+                    gr.raw = smid - shift;
+                    if ((rc = gram_block(xa, xb, true, d, gg, gr, 0, st, 2 * dp, 2 * dp))) return rc;
+                    gram_limb_combine_kernel<<<dim3((n + 255) / 256, gg.row_end - gg.row_begin), 256, 0, st>>>(
+                        sll, smid, shh, n, gg.row_begin, gg.row_end, w.rk, go);
+                    KAM_CUDA(cudaGetLastError());
+                }
+                return KAM_OK;
+            }
+        }
         return kam_int_gram_tri(d_x, elem, n, d, ld, row_begin, row_end, w.rk, go, w.xt, st);
     }
     GramGeom gg;
@@ -938,6 +1094,7 @@ void kam_gram_force_f16(int on) { g_force_f16 = on != 0; }
 void kam_gram_set_float_recover(int on) { g_float_recover = on != 0; }
 void kam_gram_set_cluster(int cl) { g_cluster = cl == 1 ? 1u : 2u; }
 void kam_gram_set_pair(int on) { g_pair = on != 0; }
+void kam_gram_set_limb(int on) { g_limb = on != 0; }
 void kam_gram_set_strip(int row_tiles) { g_strip = row_tiles >= 2 ? (uint32_t)row_tiles : 2u; }
 
 }  // extern "C"

@@ -203,13 +203,61 @@ def test_gram_ragged_d_and_u32(D):
     _check_gram(D, x[:, :4].copy() + 1)                                 # k=1-like: d=4
 
 
-def test_gram_integer_fallback_outside_fp16_envelope(D):
-    """counts > 2048 or sum of squares >= 2^24: exact integer Gram on the CUDA cores."""
+@pytest.mark.parametrize("limb", [1, 0])
+def test_gram_outside_fp16_envelope(D, limb):
+    """counts > 2048 or sum of squares >= 2^24: the limb-split tensor path (c = 256 hi + lo, three uint8 Grams
+    combined exactly; limb=1) or the exact integer Gram on the CUDA cores (limb=0) -- same results."""
+    from kameris_b200 import _lib
+    lib = _lib.load()
     rng = np.random.Generator(np.random.PCG64(9))
-    x = rng.integers(0, 60000, size=(70, 300)).astype(np.uint16)
-    _check_gram(D, x)
-    x2 = rng.integers(100, 2000, size=(50, 4096)).astype(np.uint16)     # <= 2048 but G_ii ~ 5e9 >= 2^24
-    _check_gram(D, x2)
+    lib.kam_gram_set_limb(limb)
+    try:
+        x = rng.integers(0, 60000, size=(70, 300)).astype(np.uint16)
+        _check_gram(D, x)
+        x2 = rng.integers(100, 2000, size=(50, 4096)).astype(np.uint16)     # <= 2048 but G_ii ~ 5e9 >= 2^24
+        _check_gram(D, x2)
+        x3 = rng.integers(0, 70000, size=(33, 500)).astype(np.uint32)       # above 65535: never the limb path
+        _check_gram(D, x3)
+    finally:
+        lib.kam_gram_set_limb(1)
+
+
+def test_gram_limb_path_many_tiles_and_its_limit(D):
+    """limb-split path on a config-5-like shape (mean count ~19 with a heavy tail above 255, D = 4^9: the sum of
+    squares of a row is ~1e8, far beyond the fp16 envelope) over several tiles and row blocks, against a float64
+    Gram; identical bits to the CUDA-core integer Gram; and rows whose low bytes alone would overflow an int32
+    accumulator (all 255 over 65536 bins) must fall through to the integer path and still be right."""
+    from kameris_b200 import _lib
+    lib = _lib.load()
+    n, d = 900, 4 ** 9
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    x = torch.poisson(torch.full((n, d), 19.0, device="cuda"), generator=g)
+    x[:, ::977] *= 40                                     # ~270 bins per row with counts ~760: hi limbs in use
+    assert float(x.max()) > 255 and float(x.max()) < 65536
+    xd = x.to(torch.int32).to(torch.uint16)
+    ref = _ref_metrics_f64(x.to(torch.float64))
+    iu = torch.triu_indices(n, n, 1, device="cuda")
+    got = D.gram_tri(xd, ("euclid", "cosine", "pearson"), euclid_on_freq=True)
+    for m in got:
+        want = ref[m][iu[0], iu[1]]
+        err = ((got[m].double() - want).abs() / want.abs().clamp(min=1e-30)).max().item()
+        assert err < 2e-6, (m, err)
+    part = D.gram_tri(xd, ("cosine",), rows=(300, 601))["cosine"]           # a row range that starts inside a tile
+    lo, hi = 300 * n - 300 * 301 // 2, 601 * n - 601 * 602 // 2
+    assert torch.equal(part[lo:hi], got["cosine"][lo:hi])
+    lib.kam_gram_set_limb(0)
+    try:
+        slow = D.gram_tri(xd[:200], ("euclid", "cosine", "pearson"), euclid_on_freq=True)
+    finally:
+        lib.kam_gram_set_limb(1)
+    fast = D.gram_tri(xd[:200], ("euclid", "cosine", "pearson"), euclid_on_freq=True)
+    for m in slow:
+        assert torch.equal(slow[m], fast[m]), m
+    y = np.full((40, 65536), 255, dtype=np.uint16)         # sum lo^2 = 4.26e9 >= 2^31: limb path must decline
+    y[:, ::3] = 300
+    y[np.arange(40), np.arange(40)] = 7
+    _check_gram(D, y)
 
 
 def test_gram_row_ranges_compose(D):
