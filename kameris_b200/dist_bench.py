@@ -115,7 +115,71 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
                      "unit": "T DFMA/s", "frac": pf * df / tr / dfma_peak, "kernel": "gram_f64_kernel<double>"}}
     del xr, wsf, tri, ws
 
-    # ---- manhattan, config-4 shape ----------------------------------------------------------------------
+    # ---- Gram at D = 4096 (configs[0] / [3] shape): 32 K-steps per tile, bound by the epilogue and its stores ----
+    ng, kg = 32768, 6
+    dg = 4 ** kg
+    xg = synth_counts(torch, dev, ng, 9000, kg, 20261008)
+    pg = ng * (ng - 1) // 2
+    trig = {m: torch.empty(pg, dtype=torch.float32, device=dev) for m in ("euclid", "cosine", "pearson")}
+    wsg = torch.empty(lib.kam_gram_workspace_bytes(ng, dg), dtype=torch.uint8, device=dev)
+
+    def gram_small(mask):
+        _lib.check(lib.kam_gram_tri(xg.data_ptr(), 1, ng, dg, xg.stride(0), 0, ng, mask, 1, trig["euclid"].data_ptr(),
+                                    trig["cosine"].data_ptr(), trig["pearson"].data_ptr(), wsg.data_ptr(), wsg.numel(),
+                                    stream))
+    t3 = _time(torch, lambda: gram_small(4 | 8 | 16), reps)
+    t1 = _time(torch, lambda: gram_small(8), reps)
+    out["gram_d4096"] = {
+        "metric": "distance_pairs_per_sec", "value": pg / t3, "unit": "pairs/s", "ms": t3 * 1e3,
+        "config": {"workload": "N=%d count vectors (9 kb genomes, k=6, D=4096), euclid+cosine+pearson, packed triangles "
+                               "on the device" % ng},
+        "roofline": {"bound": "hbm (writes)", "achieved": 12.0 * pg / t3 / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": 12.0 * pg / t3 / 1e9 / hbm_peak, "algorithmic_bytes_per_pair": 12,
+                     "kernel": "gram_pair_kernel<i8> (K = 32 steps: float64 epilogue + triangle stores dominate)",
+                     "tensor_TFLOPs": 2.0 * dg * pg / t3 / 1e12},
+        "cosine_only": {"value": pg / t1, "unit": "pairs/s", "ms": t1 * 1e3, "GBps": 4.0 * pg / t1 / 1e9}}
+    del xg, trig, wsg
+    torch.cuda.empty_cache()
+
+    # ---- limb-split path (counts above 255 / sums of squares beyond the fp16 envelope: configs[4]-like vectors) ----
+    nl, dl = 4096, 4 ** 9
+    gl = torch.Generator(device=dev)
+    gl.manual_seed(3)
+    xl = torch.poisson(torch.full((nl, dl), 19.0, device=dev), generator=gl)
+    xl[:, ::977] *= 40
+    xl = xl.to(torch.int32).to(torch.uint16)
+    pl = nl * (nl - 1) // 2
+    tril = {m: torch.empty(pl, dtype=torch.float32, device=dev) for m in ("cosine", "pearson")}
+    wsl = torch.empty(lib.kam_gram_workspace_bytes_int(nl, dl), dtype=torch.uint8, device=dev)
+
+    def gram_limb():
+        _lib.check(lib.kam_gram_tri(xl.data_ptr(), 1, nl, dl, xl.stride(0), 0, nl, 8 | 16, 1, None,
+                                    tril["cosine"].data_ptr(), tril["pearson"].data_ptr(), wsl.data_ptr(), wsl.numel(),
+                                    stream))
+    tl = _time(torch, gram_limb, reps)
+    lib.kam_gram_set_limb(0)
+    try:
+        tl0 = _time(torch, gram_limb, 1)
+    finally:
+        lib.kam_gram_set_limb(1)
+    out["gram_limb"] = {
+        "metric": "distance_pairs_per_sec", "value": pl / tl, "unit": "pairs/s", "ms": tl * 1e3,
+        "config": {"workload": "N=%d count vectors of a 5 Mb genome at k=9 (Poisson(19) + a tail to ~760, D=4^9): "
+                               "sum of squares ~1e8 per row, outside the uint8 and fp16 envelopes" % nl,
+                   "path": "c = 256 hi + lo: three kind::i8 Grams (4x the MMA work of the uint8 path), float64 combine"},
+        "roofline": {"bound": "tensor", "achieved": 2.0 * dl * pl / tl / 1e12, "peak": 2.0 * tf_peak, "unit": "TFLOP/s",
+                     "frac": 2.0 * dl * pl / tl / 1e12 / (2.0 * tf_peak), "kernel": "gram_pair_kernel<i8> x3 + combine",
+                     "issued_TFLOPs": 4 * 2.0 * dl * pl / tl / 1e12},
+        "cuda_core_integer_path": {"value": pl / tl0, "unit": "pairs/s", "ms": tl0 * 1e3,
+                                   "what": "the path these vectors took in round 1 (IMAD.WIDE Gram, kam_gram_set_limb(0))"}}
+    del xl, tril, wsl
+    torch.cuda.empty_cache()
+
+    # ---- manhattan / info / float L1, config-4 shape ---------------------------------------------------------
+    # peaks: the issue rate of each kernel's inner operation, measured with scratch/pairop_bench.cu on this GPU
+    # type (profiles/r2_pairop_microbench.log), in pair-elements per clock and SM
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    op_peak = {"u8": 199.5, "u32": 50.4, "info": 243.9, "f32": 50.6}
     m, c, k6 = 131072, 1000, 6
     d6 = 4 ** k6
     reads = synth_counts(torch, dev, m, 150, k6, 20261004)
@@ -124,19 +188,51 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
     ws = torch.empty(lib.kam_manhattan_workspace_bytes(m, d6) + lib.kam_manhattan_workspace_bytes(c, d6),
                      dtype=torch.uint8, device=dev)
 
-    def manh():
-        _lib.check(lib.kam_manhattan_rect(reads.data_ptr(), cent.data_ptr(), 1, m, c, d6, reads.stride(0),
-                                          cent.stride(0), o.data_ptr(), ws.data_ptr(), ws.numel(), stream))
-    t = _time(torch, manh, reps)
-    lane_peak = 148 * 128 * 1.965e9            # nominal FP32/INT32 lane-ops per second
-    out["manhattan"] = {"metric": "distance_pairs_per_sec", "value": m * c / t, "unit": "pairs/s",
-                        "config": {"workload": "%d reads (150 bp, k=6 counts) x %d centroids, D=4096, uint32 manhat"
-                                               % (m, c), "includes": "operand transposition pre-pass + tile kernel"},
-                        "ms": t * 1e3,
-                        "roofline": {"bound": "cuda-core issue", "achieved": m * c * d6 / t / 1e12,
-                                     "peak": lane_peak / 1e12, "unit": "T pair-elements/s (peak: 1 lane-op each)",
-                                     "frac": m * c * d6 / t / lane_peak, "kernel": "pair_tile_kernel<SAD8X4>"}}
-    del reads, cent, o, ws
+    def manh(x, y):
+        _lib.check(lib.kam_manhattan_rect(x.data_ptr(), y.data_ptr(), 1, m, c, d6, x.stride(0), y.stride(0),
+                                          o.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+
+    def pair_line(t, pairs, dd, key, kernel, workload, includes="operand transposition pre-pass + tile kernel"):
+        peak = op_peak[key] * sms * 1.965e9
+        return {"metric": "distance_pairs_per_sec", "value": pairs / t, "unit": "pairs/s", "ms": t * 1e3,
+                "config": {"workload": workload, "includes": includes},
+                "roofline": {"bound": "cuda-core issue (%s)" % kernel.split(":")[1].strip(),
+                             "achieved": pairs * dd / t / 1e12, "peak": peak / 1e12, "unit": "T pair-elements/s",
+                             "frac": pairs * dd / t / peak, "kernel": kernel.split(":")[0],
+                             "peak_source": "measured issue rate of the inner op (scratch/pairop_bench.cu): %.1f "
+                                            "pair-elements per clk and SM" % op_peak[key]}}
+    t = _time(torch, lambda: manh(reads, cent), reps)
+    out["manhattan"] = pair_line(t, m * c, d6, "u8", "pair_tile_kernel<SAD8X4>: VABSDIFF4.U8.ACC",
+                                 "%d reads (150 bp, k=6 counts) x %d centroids, D=4096, uint32 manhat" % (m, c))
+    big = cent.clone()
+    big.view(torch.int16)[0, 0] = 300                 # one count above 255 -> the exact 32-bit path
+    t = _time(torch, lambda: manh(reads, big), reps)
+    out["manhattan_u32"] = pair_line(t, m * c, d6, "u32", "pair_tile_kernel<SAD32>: VABSDIFF.U32",
+                                     "same shape with a count above 255: exact mod 2^32 path")
+    centf = cent.to(torch.float32) / 145.0
+    of = torch.empty((m, c), dtype=torch.float32, device=dev)
+
+    def l1f():
+        _lib.check(lib.kam_manhattan_rect_f32(reads.data_ptr(), 1, centf.data_ptr(), m, c, d6, reads.stride(0),
+                                              centf.stride(0), of.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+    t = _time(torch, l1f, reps)
+    out["manhattan_f32_centroids"] = pair_line(t, m * c, d6, "f32", "pair_tile_kernel<L1F32>: 2 x FADD",
+                                               "configs[3]'s real workload: uint16 count rows x float32 centroids, float L1")
+    del reads, cent, o, of, big, centf
+    ni = 32768
+    xi = synth_counts(torch, dev, ni, 9000, k6, 20261009)
+    pi_ = ni * (ni - 1) // 2
+    ti_ = torch.empty(pi_, dtype=torch.float32, device=dev)
+    wsi = torch.empty(lib.kam_info_workspace_bytes(ni, d6), dtype=torch.uint8, device=dev)
+
+    def info():
+        _lib.check(lib.kam_info_tri(xi.data_ptr(), 1, ni, d6, xi.stride(0), 0, ni, ti_.data_ptr(), wsi.data_ptr(),
+                                    wsi.numel(), stream))
+    t = _time(torch, info, reps)
+    out["info"] = pair_line(t, pi_, d6, "info", "pair_tile_kernel<JACC>: LOP3 + POPC",
+                            "N=%d count vectors (9 kb genomes, k=6, D=4096), reference `info` triangle" % ni,
+                            "presence-bitmap pre-pass + tile kernel")
+    del xi, ti_, wsi, ws
     torch.cuda.empty_cache()
 
     # ---- e2e: the whole `distances` step on HOST buffers through kam_dists_host ---------------------------
@@ -169,11 +265,12 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
         dt = sorted(ts)[2]              # median of 5 (cudaMalloc / cudaFree inside the call make single calls noisy)
         e2e[name] = {"value": pe / dt, "unit": "pairs/s", "ms": dt * 1e3, "ms_min_max": [min(ts) * 1e3, max(ts) * 1e3],
                      "h2d_bytes_per_step": ne * de * 2, "d2h_bytes_per_step": pe * 4 * n_out}
-    out["rooflines"] = {"gram_i8": dict(out["gram"]["roofline"], value=out["gram"]["value"], ms=out["gram"]["ms"]),
-                        "gram_f16": dict(out["gram"]["fp16_path"]["roofline"], value=out["gram"]["fp16_path"]["value"],
-                                         ms=out["gram"]["fp16_path"]["ms"]),
-                        "manhattan_u8": dict(out["manhattan"]["roofline"], value=out["manhattan"]["value"],
-                                             ms=out["manhattan"]["ms"])}
+    def flat(line):
+        return dict(line["roofline"], value=line["value"], ms=line["ms"])
+    out["rooflines"] = {"gram_i8": flat(out["gram"]), "gram_f16": flat(out["gram"]["fp16_path"]),
+                        "gram_d4096": flat(out["gram_d4096"]), "gram_limb": flat(out["gram_limb"]),
+                        "manhattan_u8": flat(out["manhattan"]), "manhattan_u32": flat(out["manhattan_u32"]),
+                        "manhattan_f32_centroids": flat(out["manhattan_f32_centroids"]), "info": flat(out["info"])}
     out["e2e"] = {"api": "kam_dists_host (C ABI, pinned host buffers)",
                   "config": {"workload": "%d count vectors (9 kb genomes, k=%d, D=%d, uint16): %d pairs" % (ne, ke, de, pe)},
                   **e2e}
