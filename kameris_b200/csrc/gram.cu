@@ -27,7 +27,8 @@
 //                              fp32 accumulators in TMEM, two 256-column accumulators so the epilogue
 //                              of tile t overlaps the MMAs of tile t+1; tcgen05.commit (multicast)
 //                              releases smem stages in both CTAs / publishes TMEM
-//   warps 2-5 epilogue       : tcgen05.ld 32x32b -> float64 distance formulas -> packed triangle
+//   warps 2-9 epilogue       : tcgen05.ld 32x32b -> float64 distance formulas -> shared-memory transpose ->
+//                              row-contiguous stores into the packed triangle
 // Only tiles that contain a pair i<j are scheduled (upper triangle).
 #include <string.h>
 
@@ -44,7 +45,8 @@ namespace {
 constexpr int BM = 128, BN = 256;
 constexpr int BK_BYTES = 128;                        // one SWIZZLE_128B row of K per stage: 64 fp16 or 128 uint8
 constexpr int G_STAGES = 4;
-constexpr int G_THREADS = 192;
+constexpr int EP_WARPS = 8;                           // epilogue warps: two per TMEM lane quarter
+constexpr int G_THREADS = 64 + 32 * EP_WARPS;
 constexpr uint32_t A_BYTES = BM * BK_BYTES, B_BYTES = BN * BK_BYTES, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
 // exactness envelopes (see the header comment)
@@ -113,6 +115,86 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Epilogue stores.  A TMEM lane is a ROW of the tile: after tcgen05.ld every lane of an epilogue warp holds 32
+// consecutive columns of its own row, so storing straight from the registers makes one warp-wide store touch
+// 32 different rows -- 32 separate 32-byte sectors for 128 bytes of payload.  At D = 4096 (32 K-steps per tile)
+// that, not the MMAs, bounded the kernel (14.4 ms for 5.4e8 pairs x 3 metrics; cosine alone took 4.3 ms).  So
+// each 32 x 32 chunk goes through a padded shared-memory tile per warp and leaves as 32 row-contiguous
+// 128-byte stores.
+constexpr int EP_PITCH = 33;
+constexpr int EP_ROWS = 16;                                            // rows per staging round (half a warp's 32)
+constexpr uint32_t EP_TILE_BYTES = 8 * EP_ROWS * EP_PITCH * 4;         // eight epilogue warps
+
+template <bool I8>
+__device__ __forceinline__ void gram_store_chunk(const GramGeom &gg, const GramOut &go, float *stile,
+                                                 const uint32_t (&v)[32], const RowK &ri, const RowK *colk, uint32_t cb,
+                                                 uint32_t row_first, uint32_t lane) {
+    const uint32_t j = cb + lane;                       // the column this lane stores
+    const bool j_ok = j < gg.n_b;
+    float *mine = stile + (lane & (EP_ROWS - 1)) * EP_PITCH;
+    // the lanes' 32 values each -> global memory, 16 rows at a time through the warp's staging tile
+    auto put = [&](float *dst, const float (&val)[32]) {
+#pragma unroll
+        for (uint32_t h = 0; h < 32 / EP_ROWS; ++h) {
+            if (lane / EP_ROWS == h) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) mine[c] = val[c];
+            }
+            __syncwarp();
+            // rows of this round that this launch writes; the address of row r+1 follows from that of row r
+            const uint32_t first = row_first + h * EP_ROWS;
+            const uint32_t lo = first > gg.row_begin ? first : gg.row_begin;
+            uint32_t hi = first + EP_ROWS < gg.row_end ? first + EP_ROWS : gg.row_end;
+            hi = hi < gg.n_a ? hi : gg.n_a;
+            if (lo < hi && j_ok) {
+                const long long base = gg.ld ? (long long)lo * (long long)gg.ld
+                                             : (long long)gg.n_a * lo - (long long)lo * (lo + 3) / 2 - 1;
+                float *p = dst + base + j;
+                const float *sp = stile + (lo - first) * EP_PITCH + lane;
+#pragma unroll 8
+                for (uint32_t row = lo; row < hi; ++row) {
+                    if (!gg.tri || j > row) *p = *sp;
+                    p += gg.ld ? (long long)gg.ld : (long long)gg.n_a - (long long)row - 2;
+                    sp += EP_PITCH;
+                }
+            }
+            __syncwarp();
+        }
+    };
+    float val[32];
+    if (I8 && go.raw) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) val[c] = __uint_as_float(v[c]);
+        put(reinterpret_cast<float *>(go.raw), val);
+        return;
+    }
+    if (go.cosine) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const double g = I8 ? (double)(int)v[c] : (double)__uint_as_float(v[c]);
+            val[c] = (float)(1.0 - g * ri.rn * colk[c].rn);
+        }
+        put(go.cosine, val);
+    }
+    if (go.pearson) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const double g = I8 ? (double)(int)v[c] : (double)__uint_as_float(v[c]);
+            val[c] = (float)(1.0 - (g - ri.S * colk[c].mu) * ri.rp * colk[c].rp);
+        }
+        put(go.pearson, val);
+    }
+    if (go.euclid) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const double g = I8 ? (double)(int)v[c] : (double)__uint_as_float(v[c]);
+            const double e2 = ri.a + colk[c].a - 2.0 * g * ri.q * colk[c].q;
+            val[c] = sqrtf((float)(e2 < 0.0 ? 0.0 : e2));   // cancellation below zero -> 0; NaN (an empty row) stays NaN
+        }
+        put(go.euclid, val);
+    }
+}
+
 // CL = cluster size along M (1 or 2).  With CL == 2 the two CTAs of a cluster work on the tiles
 // (2p, bj) and (2p+1, bj): they need the same B panel, so each CTA fetches half of it and TMA
 // multicasts it into both shared memories -- 32 KB instead of 48 KB of L2 traffic per CTA and stage.
@@ -124,6 +206,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B: 1024-B aligned
     RowK *colk = reinterpret_cast<RowK *>(smem + G_STAGES * STAGE_BYTES);                 // [BN]
+    float *stile = reinterpret_cast<float *>(colk + BN) + (((threadIdx.x >> 5) + 6) & 7) * EP_ROWS * EP_PITCH;   // per epilogue warp (warps 2..9)
     __shared__ __align__(8) uint64_t full[G_STAGES], empty[G_STAGES], tfull[2], tempty[2];
     __shared__ uint32_t tmem_holder;
 
@@ -141,7 +224,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);   // one arrive per epilogue warp
+            mbar_init(&tempty[a], EP_WARPS);   // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -214,20 +297,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
             }
         }
     } else {
-        // ===== epilogue: 4 warps, warp w may touch TMEM lanes [32*(w%4), +32) =====
-        const uint32_t q = (uint32_t)warp & 3u;
-        const uint32_t et = threadIdx.x - 64;              // 0..127
+        // ===== epilogue: 8 warps, warp w may touch TMEM lanes [32*(w%4), +32); the two warps of a lane quarter
+        // take alternate 32-column chunks =====
+        const uint32_t q = (uint32_t)warp & 3u, half = ((uint32_t)warp - 2u) >> 2;
+        const uint32_t et = threadIdx.x - 64;              // 0..255
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = blockIdx.x / CL; t < n_tiles; t += gridDim.x / CL) {
             const uint2 tile = tiles[t];
             const uint32_t r0 = (tile.x * CL + crank) * BM, c0 = tile.y * BN;
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's colk fully consumed
-            for (uint32_t c = et; c < (uint32_t)BN; c += 128) {
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EP_WARPS) : "memory");   // previous tile's colk fully consumed
+            for (uint32_t c = et; c < (uint32_t)BN; c += 32 * EP_WARPS) {
                 RowK z;
                 z.rn = z.S = z.mu = z.rp = z.a = z.q = 0.0;
                 colk[c] = (c0 + c < gg.n_b) ? gg.rk_b[c0 + c] : z;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EP_WARPS) : "memory");
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t row = r0 + q * 32 + lane;
@@ -235,28 +319,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
             RowK ri;
             ri.rn = ri.S = ri.mu = ri.rp = ri.a = ri.q = 0.0;
             if (row_ok) ri = gg.rk_a[row];
-            const long long base = gg.ld ? (long long)row * (long long)gg.ld
-                                         : (long long)gg.n_a * row - (long long)row * (row + 3) / 2 - 1;
-            for (uint32_t ch = 0; ch < (uint32_t)BN / 32; ++ch) {
+            for (uint32_t ch = half; ch < (uint32_t)BN / 32; ch += 2) {
                 const uint32_t cb = c0 + ch * 32;
                 if (gg.tri && cb + 31 <= r0 + q * 32) continue;   // whole chunk on or below the diagonal (warp-uniform)
                 if (cb >= gg.n_b) continue;                         // whole chunk past the last column
                 uint32_t v[32];
                 tmem_ld32(tmem_base + acc * BN + ch * 32 + ((q * 32) << 16), v);
-                if (row_ok) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const uint32_t j = cb + c;
-                        if (j >= gg.n_b || (gg.tri && j <= row)) continue;
-                        if (I8 && go.raw) {
-                            go.raw[base + j] = (int)v[c];
-                            continue;
-                        }
-                        const double g = I8 ? (double)(int)v[c] : (double)__uint_as_float(v[c]);
-                        const RowK cj = colk[ch * 32 + c];
-                        gram_store(go, base + j, g, ri, cj);
-                    }
-                }
+                gram_store_chunk<I8>(gg, go, stile, v, ri, colk + ch * 32, cb, r0 + q * 32, (uint32_t)lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -348,6 +417,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_pair_kernel(const __grid_co
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     RowK *colk = reinterpret_cast<RowK *>(smem + P_STAGES * P_STAGE_BYTES);   // [BN]
+    float *stile = reinterpret_cast<float *>(colk + BN) + (((threadIdx.x >> 5) + 6) & 7) * EP_ROWS * EP_PITCH;   // per epilogue warp (warps 2..9)
     __shared__ __align__(8) uint64_t full[P_STAGES], empty[P_STAGES], tfull[2], tempty[2];
     __shared__ uint32_t tmem_holder;
 
@@ -364,7 +434,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_pair_kernel(const __grid_co
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);   // one multicast commit
-            mbar_init(&tempty[a], 8);  // leader only: four epilogue warps of each CTA
+            mbar_init(&tempty[a], 2 * EP_WARPS);  // leader only: the epilogue warps of both CTAs
         }
         fence_mbar_init();
     }
@@ -429,20 +499,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_pair_kernel(const __grid_co
             }
         }
     } else {
-        // ===== epilogue: 4 warps per CTA, CTA r owns rows [128r, 128r+128) of the tile =====
-        const uint32_t q = (uint32_t)warp & 3u;
+        // ===== epilogue: 8 warps per CTA, CTA r owns rows [128r, 128r+128) of the tile; the two warps of a TMEM
+        // lane quarter take alternate 32-column chunks =====
+        const uint32_t q = (uint32_t)warp & 3u, half = ((uint32_t)warp - 2u) >> 2;
         const uint32_t et = threadIdx.x - 64;
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = blockIdx.x / 2; t < n_tiles; t += gridDim.x / 2) {
             const uint2 tile = tiles[t];
             const uint32_t r0 = (tile.x * 2 + crank) * BM, c0 = tile.y * BN;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (uint32_t c = et; c < (uint32_t)BN; c += 128) {
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EP_WARPS) : "memory");
+            for (uint32_t c = et; c < (uint32_t)BN; c += 32 * EP_WARPS) {
                 RowK z;
                 z.rn = z.S = z.mu = z.rp = z.a = z.q = 0.0;
                 colk[c] = (c0 + c < gg.n_b) ? gg.rk_b[c0 + c] : z;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EP_WARPS) : "memory");
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t row = r0 + q * 32 + lane;
@@ -450,28 +521,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_pair_kernel(const __grid_co
             RowK ri;
             ri.rn = ri.S = ri.mu = ri.rp = ri.a = ri.q = 0.0;
             if (row_ok) ri = gg.rk_a[row];
-            const long long base = gg.ld ? (long long)row * (long long)gg.ld
-                                         : (long long)gg.n_a * row - (long long)row * (row + 3) / 2 - 1;
-            for (uint32_t ch = 0; ch < (uint32_t)BN / 32; ++ch) {
+            for (uint32_t ch = half; ch < (uint32_t)BN / 32; ch += 2) {
                 const uint32_t cb = c0 + ch * 32;
                 if (gg.tri && cb + 31 <= r0 + q * 32) continue;
                 if (cb >= gg.n_b) continue;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + acc * BN + ch * 32 + ((q * 32) << 16), v);
-                if (row_ok) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const uint32_t j = cb + c;
-                        if (j >= gg.n_b || (gg.tri && j <= row)) continue;
-                        if (I8 && go.raw) {
-                            go.raw[base + j] = (int)v[c];
-                            continue;
-                        }
-                        const double g = I8 ? (double)(int)v[c] : (double)__uint_as_float(v[c]);
-                        const RowK cj = colk[ch * 32 + c];
-                        gram_store(go, base + j, g, ri, cj);
-                    }
-                }
+                gram_store_chunk<I8>(gg, go, stile, v, ri, colk + ch * 32, cb, r0 + q * 32, (uint32_t)lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -717,7 +773,8 @@ int launch_gram(const void *opA, const void *opB, const uint2 *d_tiles, size_t n
     if ((rc = kam_make_tmap_2d(&tmA, dt, esz, opA, dpad, gg.n_a, pitch, bk, BM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = kam_make_tmap_2d(&tmB, dt, esz, opB, dpad, gg.n_b, pitch, bk, BN / CL, CU_TENSOR_MAP_SWIZZLE_128B)))
         return rc;
-    const size_t smem = (PAIR ? (size_t)P_STAGES * P_STAGE_BYTES : (size_t)G_STAGES * STAGE_BYTES) + BN * sizeof(RowK) + 1024;
+    const size_t smem = (PAIR ? (size_t)P_STAGES * P_STAGE_BYTES : (size_t)G_STAGES * STAGE_BYTES) + BN * sizeof(RowK) +
+                        EP_TILE_BYTES + 1024;
     auto kern = PAIR ? gram_pair_kernel<I8> : gram_tcgen05_kernel<I8, CL>;
     KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t sms = (uint32_t)kam_sm_count();
