@@ -51,7 +51,7 @@ void ingest_worker(Ingest *gp) {
         if (i >= g.n) break;
         g.len[i] = 0;
         const uint64_t cap = g.off[i + 1] - g.off[i];
-        const int fd = open(g.paths[i], O_RDONLY | O_CLOEXEC);
+        const int fd = open(g.paths[i], O_RDONLY | O_CLOEXEC | O_NONBLOCK)   /* a FIFO in the directory must not block the step */;
         if (fd < 0) {
             note_bad(g, i, errno);
             continue;

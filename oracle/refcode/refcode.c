@@ -11,7 +11,12 @@
  *     VA 0x140016040 .. 0x1400161a8   (file offset 0x15440, 0x168 bytes)
  *     void fill(std::vector<uint16_t>& count, const std::string& record, unsigned k,
  *               const char* const& order)          -- Windows x64 ABI (rcx, rdx, r8d, r9)
- * called from VA 0x14001564b with order -> "ACGT" (.rdata VA 0x1400a20b1).
+ * called from VA 0x14001564b with order -> "ACGT" (.rdata VA 0x1400a20b1).  Its uint32 twin (the same source
+ * instantiated for bits_per_element = 32: `mov rcx,[rcx]` up front, `inc DWORD PTR [rcx+rax*4]` at VA
+ * 0x14001b47d) is the leaf at
+ *     VA 0x14001b360 .. 0x14001b4c3   (file offset 0x1a760, 0x163 bytes), same signature with
+ *     std::vector<uint32_t>&
+ * and is mapped the same way for the uint32 golden vectors (refcode_cgr_u32; golden generation only).
  * We map those bytes from the file where it lies (nothing is copied into the repo), build the two
  * MSVC container headers the code dereferences ([rcx] = data pointer of the vector; the string is
  * {ptr/SSO buffer @0, size @0x10, capacity @0x18}), and call it through an ms_abi pointer.
@@ -36,6 +41,8 @@
 
 #define FILL_FILE_OFF 0x15440l
 #define FILL_LEN 0x168
+#define FILL32_FILE_OFF 0x1a760l
+#define FILL32_LEN 0x163
 #define ORDER_FILE_OFF 0xa0ab1l
 
 typedef void(__attribute__((ms_abi)) * fill_fn)(void *vec, void *str, uint32_t k, void *order);
@@ -50,7 +57,7 @@ struct msvc_vector {
     void *first, *last, *end;
 };
 
-static void *g_code = NULL;
+static void *g_code = NULL, *g_code32 = NULL;
 static char g_order[8];
 
 static int map_code(const unsigned char *buf) {
@@ -161,5 +168,44 @@ int refcode_cgr_u16_batch(const char *chars, const uint64_t *start, uint64_t n, 
         if (pthread_create(&th[made], NULL, batch_worker, &b)) break;
     if (made == 0) batch_worker(&b);
     for (int t = 0; t < made; t++) pthread_join(th[t], NULL);
+    return 0;
+}
+
+
+/* ---- the uint32 twin (golden generation in the build container only) ------------------------------ */
+int refcode_load_u32(const char *pe_path) {
+    if (g_code32) return 0;
+    static const unsigned char prologue[] = {0x53, 0x56, 0x57, 0x48, 0x83, 0xec, 0x40};
+    unsigned char buf[FILL32_LEN];
+    FILE *f = fopen(pe_path, "rb");
+    if (!f) return -1;
+    if (fseek(f, FILL32_FILE_OFF, SEEK_SET) || fread(buf, 1, FILL32_LEN, f) != FILL32_LEN) {
+        fclose(f);
+        return -2;
+    }
+    if (fseek(f, ORDER_FILE_OFF, SEEK_SET) || fread(g_order, 1, 4, f) != 4) {
+        fclose(f);
+        return -3;
+    }
+    fclose(f);
+    /* prologue, the `inc DWORD PTR [rcx+rax*4]` at +0x11d, the final jmp */
+    if (memcmp(buf, prologue, sizeof prologue) != 0 || buf[0x11d] != 0xff || buf[0x11e] != 0x04 || buf[0x11f] != 0x81 ||
+        buf[FILL32_LEN - 5] != 0xe9)
+        return -4;
+    void *m = mmap(NULL, 4096, PROT_READ | PROT_WRITE | PROT_EXEC, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m == MAP_FAILED) return -5;
+    memset(m, 0xcc, 4096);
+    memcpy(m, buf, FILL32_LEN);
+    g_code32 = m;
+    return 0;
+}
+
+/* count must hold 4^k zero-initialised uint32. */
+int refcode_cgr_u32(const char *rec, uint64_t n, uint32_t k, uint32_t *count) {
+    if (!g_code32) return -1;
+    struct msvc_string s = {(char *)rec, 0, n, n < 16 ? 16 : n};
+    struct msvc_vector v = {count, count + ((uint64_t)1 << (2 * k)), count + ((uint64_t)1 << (2 * k))};
+    char *order = g_order;
+    ((fill_fn)g_code32)(&v, &s, k, &order);
     return 0;
 }

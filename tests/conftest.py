@@ -23,6 +23,23 @@ def refcode_cases():
         return json.loads(f.read())["cases"]
 
 
+def _record_of(case):
+    """a golden case's input: stored verbatim, or as a recipe for the long trivial ones"""
+    if case.get("record") is not None:
+        return case["record"].encode("latin-1")
+    r = case["recipe"]
+    return r.get("prefix", "").encode() + r["repeat"].encode() * r["times"]
+
+
+@pytest.fixture(scope="session")
+def refcode_cases_u32():
+    """Outputs of the reference's own CGR machine code, bits_per_element = 32 instantiation
+    (oracle/refcode/gen_golden_u32.py): (name, record bytes, {k: summary})."""
+    with gzip.open(os.path.join(GOLDEN, "refcode_cgr_u32.json.gz")) as f:
+        cases = json.loads(f.read())["cases"]
+    return [(c["name"], _record_of(c), c["k"]) for c in cases]
+
+
 @pytest.fixture(scope="session")
 def demo_records():
     """record[0] of the 4 bundled HIV-1 genomes, in the reference's sorted-path order."""

@@ -310,3 +310,81 @@ def test_header_is_plain_c_and_the_example_links(tmp_path):
                            "-Wl,-rpath," + libdir, "-o", exe])
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 1 and b"usage:" in r.stderr
+
+
+# ---- A.1 front half, adversarial inputs with hand-written expectations ---------------------------------------
+# getline / trim / '>' / record[0] (generation_cgr_mac_avx2 @0x10000d691-0x10000d83e) cannot be extracted from the
+# reference binaries as a leaf function, so this part of the path is SPEC-PINNED only: the
+# library and the oracle are both written from the same reading of the disassembly.  The expectations below are
+# therefore literals derived by hand from that reading -- std::getline splits at '\n' only; boost::trim strips
+# std::isspace characters (space, \t \n \v \f \r) from both ends of the line and nothing inside it; a trimmed line
+# that is empty or starts with '>' ends the current record; NUL is an ordinary character -- so that a change in
+# EITHER implementation shows up.
+ADVERSARIAL = [
+    (b"ACGT", b"ACGT"),                                     # no header, no trailing newline
+    (b">h\r\nAC\r\nGT\r\n", b"ACGT"),                       # CRLF
+    (b">h\nAC\n\nGT\n", b"AC"),                             # a blank line ends the record
+    (b"\n\n\nAC\nGT", b"ACGT"),                             # leading blank lines open nothing
+    (b"  AC \t\n\tGT  \n", b"ACGT"),                        # leading / trailing blanks and tabs
+    (b"AC GT\n", b"AC GT"),                                 # inner whitespace is kept (and skipped by the CGR loop)
+    (b"AC\x00GT\nTT\n", b"AC\x00GTTT"),                     # NUL bytes are ordinary characters
+    (b">a\n>b\n>c\nGG\n>d\nTT", b"GG"),                     # consecutive headers, second record ignored
+    (b" >indented header\nAC\n", b"AC"),                    # the '>' test sees the TRIMMED line
+    (b"AC\n \t \nGT\n", b"AC"),                             # a whitespace-only line is a blank line
+    (b"AC\rGT\n", b"AC\rGT"),                               # a lone CR inside a line is not a line break
+    (b"\x0bAC\x0c\n", b"AC"),                               # VT / FF are whitespace
+    (b"AC\n>", b"AC"),                                      # a final '>' without newline
+    (b">h\nacgtnN\nRYKM\n", b"acgtnNRYKM"),                 # lower case and IUPAC stay in the record
+    (b"A" * 70000 + b"\r\n" + b"C" * 3, b"A" * 70000 + b"CCC"),
+]
+NO_RECORD = [b"", b">only header", b">h\n", b"\n\r\n \t\n", b">a\n>b\n\n"]
+
+
+def test_fasta_record0_adversarial_literals(tmp_path):
+    import ctypes
+    from kameris_b200 import _lib
+    from kameris_b200.job_steps import backend
+    from oracle import oracle as O
+    lib = _lib.load()
+    d = tmp_path / "fa"
+    d.mkdir()
+    for i, (body, want) in enumerate(ADVERSARIAL):
+        out = ctypes.create_string_buffer(len(body) + 1)
+        n = lib.kam_fasta_record0(body, len(body), out)
+        assert n == len(want) and out.raw[:n] == want, (i, body[:40])
+        assert O.fasta_record0(body) == want, (i, body[:40])
+        (d / ("f%03d.fa" % i)).write_bytes(body)
+    paths = backend.list_input_files(str(d))
+    chars, start = backend.read_records_packed(paths)
+    for i, (_, want) in enumerate(ADVERSARIAL):
+        assert chars[int(start[i]):int(start[i + 1])].tobytes() == want, i
+    for body in NO_RECORD:
+        out = ctypes.create_string_buffer(len(body) + 1)
+        assert lib.kam_fasta_record0(body, len(body), out) == -1, body
+        with pytest.raises(ValueError):
+            O.fasta_record0(body)
+        p = tmp_path / "none.fa"
+        p.write_bytes(body)
+        with pytest.raises(ValueError, match="none.fa"):
+            backend.read_records_packed([str(p)])
+
+
+def test_directory_entries_that_are_not_regular_files_fail_fast(tmp_path):
+    """generation_cgr takes EVERY directory entry (no regular-file filter, @0x1000017c9): a sub-directory, a FIFO
+    or a dangling symlink in the FASTA directory must fail the step with the entry's name, not hang or be skipped."""
+    from kameris_b200.job_steps import backend
+    d = tmp_path / "fa"
+    d.mkdir()
+    (d / "a.fa").write_bytes(b">a\nACGT\n")
+    for name, make in (("b_dir", lambda p: os.mkdir(p)), ("b_fifo", lambda p: os.mkfifo(p)),
+                       ("b_dangling", lambda p: os.symlink(str(tmp_path / "nowhere"), p))):
+        p = str(d / name)
+        make(p)
+        with pytest.raises(OSError, match=name):
+            backend.read_records_packed(backend.list_input_files(str(d)))
+        if os.path.isdir(p) and not os.path.islink(p):
+            os.rmdir(p)
+        else:
+            os.unlink(p)
+    chars, start = backend.read_records_packed(backend.list_input_files(str(d)))
+    assert chars.tobytes() == b"ACGT"

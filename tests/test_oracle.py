@@ -26,6 +26,26 @@ def test_oracle_matches_reference_machine_code(refcode_cases):
     assert n >= 200
 
 
+def test_oracle_u32_matches_reference_machine_code(refcode_cases_u32):
+    """bits_per_element = 32: the C and numpy restatements == the outputs of the reference's uint32 fill
+    (generation_cgr_windows_avx2.exe VA 0x14001b360), including counts above 65535 that the uint16 build wraps."""
+    n, big = 0, 0
+    for name, rec, ks in refcode_cases_u32:
+        for kstr, e in ks.items():
+            k = int(kstr)
+            v = O.cgr_count(rec, k, 32)
+            assert v.dtype == np.uint32
+            assert hashlib.sha1(v.astype("<u4").tobytes()).hexdigest() == e["sha1"], (name, k)
+            assert int(v.astype(np.uint64).sum()) == e["sum"] and int(v.max()) == e["max"]
+            if "vector" in e:
+                assert v.tolist() == e["vector"]
+            if k <= 9 and len(rec) <= 20000:
+                assert np.array_equal(O.cgr_count_numpy(rec, k, 32), v), (name, k)
+            big += e["max"] > 65535
+            n += 1
+    assert n >= 100 and big >= 5
+
+
 def test_appendix_b_demo_values(demo_records):
     # SURVEY.md Appendix B: sha1(u16 LE)[:16] at k=6 and k=9, k=1 order [C,G,A,T]
     expect = {"A1.fasta": ("81ad32aac3d4d91d", "97378f11765d317a", [1505, 2030, 3216, 1897]),

@@ -134,6 +134,18 @@ def test_golden_reference_machine_code(R, refcode_cases):
             assert hashlib.sha1(got[i].astype("<u2").tobytes()).hexdigest() == e["sha1"], (c["name"], k)
 
 
+def test_golden_reference_machine_code_u32(R, refcode_cases_u32):
+    """bits_per_element = 32 against the reference's own uint32 fill (VA 0x14001b360): every golden case,
+    including counts above 65535 (paths A, L and B all meet here: 70 000 x 'A', 400 000 bases of 'AC')."""
+    ks = sorted({int(k) for _, _, d in refcode_cases_u32 for k in d if int(k) <= 11})
+    for k in ks:
+        cases = [(n, r, d[str(k)]) for n, r, d in refcode_cases_u32 if str(k) in d]
+        got = _gpu_counts(R, [r for _, r, _ in cases], k, 32)
+        for i, (name, _, e) in enumerate(cases):
+            assert got.dtype == np.uint32
+            assert hashlib.sha1(got[i].astype("<u4").tobytes()).hexdigest() == e["sha1"], (name, k)
+
+
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("bits", [16, 32])
 def test_demo_and_random_vs_oracle(R, demo_records, k, bits):
