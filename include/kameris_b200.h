@@ -177,6 +177,13 @@ int kam_normalize(const void *d_counts, int count_bits, uint32_t n, uint64_t d, 
  * copy back are pipelined over chunks on internal streams; blocking. */
 int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_t n_seqs, int k,
                    int count_bits, int out_kind, void *h_out);
+/* The same step for a job whose next step is `distances` (kameris/subcommands/run_job.py:175-180 runs the steps
+ * of an experiment back to back): besides (or, with h_out == NULL, instead of) returning the vectors to the host,
+ * the dense COUNT rows (uint16/uint32 per count_bits, whatever out_kind is) stay in the caller's device matrix
+ * d_counts (row s at d_counts + s * counts_stride elements), complete when the call returns.  kam_dists_device
+ * then works on them directly: the step neither re-reads the .mm-repr nor uploads it again. */
+int kam_kmers_host_keep(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_t n_seqs, int k,
+                        int count_bits, int out_kind, void *h_out, void *d_counts, uint64_t counts_stride);
 /* How kam_kmers_host brings the vectors back: 0 = always dense (kernel writes the rows, the copy engine moves
  * them), 1 = default: chunks whose vectors are mostly zeros (k >= 7 and entry lists <= 1/4 of the dense bytes)
  * return as kam_kmer_count_sparse lists and are expanded into h_out by the host threads, 2 = sparse whenever
@@ -321,11 +328,22 @@ int kam_peer_copy(void *d_dst, const void *d_src, size_t bytes, void *stream);
 
 /* Host-buffer form of the whole `distances` step: x is the n x d matrix read from a .mm-repr,
  * outputs are packed triangles (NULL = not requested).  euclid is taken between the rows as
- * stored (count vectors of a `counts` file, frequency vectors of a `frequencies` file).  Blocking;
- * allocates and frees its device buffers. */
+ * stored (count vectors of a `counts` file, frequency vectors of a `frequencies` file).  Blocking; may be
+ * called from any thread (calls are serialised per process); device buffers are kept between calls
+ * (kam_host_release frees them). */
 int kam_dists_host(const void *h_x, int elem, uint32_t n, uint64_t d, unsigned metrics,
                    uint32_t *h_manhat, float *h_info, float *h_euclid, float *h_cosine,
                    float *h_pearson);
+/* The same with the matrix already on the device (row stride ld elements; complete before the call: the work
+ * runs on an internal stream), e.g. the counts kam_kmers_host_keep left there.  euclid_on_freq != 0: euclid
+ * between the frequency vectors x / sum(x) -- what the step computes on the `frequencies` file made from these
+ * counts (cosine and pearson do not depend on the scaling, info only on which bins are non-zero; manhat on a
+ * frequencies file truncates per addition (quirk Q5) and must be computed from the float rows themselves). */
+int kam_dists_device(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, unsigned metrics,
+                     int euclid_on_freq, uint32_t *h_manhat, float *h_info, float *h_euclid, float *h_cosine,
+                     float *h_pearson);
+/* frees the device buffers the host-buffer entry points keep between calls */
+void kam_host_release(void);
 
 /* ---------------------------------------------------------------------------------------------
  * mds job step (kameris/job_steps/mds.py:10-35): classical multidimensional scaling.

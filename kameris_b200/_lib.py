@@ -41,6 +41,7 @@ SIGNATURES = {
                              c_uint64, c_void_p]),
     "kam_normalize": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_int, c_void_p, c_uint64, c_void_p]),
     "kam_kmers_host": (c_int, [c_void_p, c_void_p, c_uint32, c_int, c_int, c_int, c_void_p]),
+    "kam_kmers_host_keep": (c_int, [c_void_p, c_void_p, c_uint32, c_int, c_int, c_int, c_void_p, c_void_p, c_uint64]),
     "kam_kmers_host_set_sparse": (None, [c_int]),
     "kam_host_set_threads": (None, [c_int]),
     "kam_host_threads": (c_int, []),
@@ -94,6 +95,9 @@ SIGNATURES = {
     "kam_col_scale": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_void_p, c_void_p, c_uint64, c_void_p]),
     "kam_dists_host": (c_int, [c_void_p, c_int, c_uint32, c_uint64, ctypes.c_uint, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
+    "kam_dists_device": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, ctypes.c_uint, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+    "kam_host_release": (None, []),
 }
 
 _lib = None

@@ -337,14 +337,32 @@ struct Job {
     const uint8_t *h_chars;
     const uint64_t *h_char_start;
     int k, count_bits, out_kind;
-    void *h_out;
+    void *h_out;            // may be null: the caller only wants the resident counts
+    void *d_keep;           // may be null; else the dense count rows also stay on the device
+    uint64_t keep_stride;   // elements between rows of d_keep
     size_t bins, row_bytes;
     bool out_pinned, in_pinned;
 };
 
+// the chunk's dense count vectors into the caller's device matrix (the `distances` step that follows in a job
+// reads them there instead of re-reading the .mm-repr and uploading it again)
+int issue_keep(Slot &s, const Job &j) {
+    if (!j.d_keep) return KAM_OK;
+    int rc = s.kmer_ws.ensure(kam_kmer_workspace_bytes(s.n, j.k));
+    if (rc) return rc;
+    char *dst = (char *)j.d_keep + (size_t)s.first * j.keep_stride * (j.count_bits / 8);
+    return kam_kmer_count((const uint64_t *)s.planes.p, (const uint64_t *)s.base.p, (const uint32_t *)s.head.p, s.n,
+                          s.nchars, j.k, j.count_bits, KAM_OUT_COUNTS, dst, j.keep_stride, s.kmer_ws.p, s.kmer_ws.cap, s.st);
+}
+
 // the chunk's vectors, densely, straight into the caller's rows (also the redo of a declined sparse chunk)
 int issue_dense(Slot &s, const Job &j) {
     int rc;
+    s.sparse = false;
+    if (!j.h_out) {
+        KAM_CUDA(cudaEventRecord(s.done, s.st));
+        return KAM_OK;
+    }
     if ((rc = s.kmer_ws.ensure(kam_kmer_workspace_bytes(s.n, j.k))) || (rc = s.out.ensure((size_t)s.n * j.row_bytes)))
         return rc;
     rc = kam_kmer_count((const uint64_t *)s.planes.p, (const uint64_t *)s.base.p, (const uint32_t *)s.head.p, s.n,
@@ -414,7 +432,7 @@ int kmers_host_locked(HostCtx &ctx, const Job &j, uint32_t n_seqs) {
         // most a quarter of the dense bytes; decided per chunk from the first sequences' lengths
         const uint64_t c0 = j.h_char_start[first];
         bool sparse = false;
-        if (sparse_k) {
+        if (sparse_k && j.h_out) {
             const uint32_t probe = std::min<uint32_t>(n_seqs - first, SPARSE_MAX_ROWS);
             const uint64_t pc = j.h_char_start[first + probe] - c0;
             sparse = g_sparse_mode == 2 || pc * 4 * 4 <= (uint64_t)probe * j.row_bytes;
@@ -457,6 +475,7 @@ int kmers_host_locked(HostCtx &ctx, const Job &j, uint32_t n_seqs) {
         rc = kam_pack_ascii((const uint8_t *)s.chars.p, (const uint64_t *)s.starts.p, n, nchars, (uint64_t *)s.planes.p,
                             (uint64_t *)s.base.p, (uint32_t *)s.head.p, s.pack_ws.p, s.pack_ws.cap, s.st);
         if (rc) return rc;
+        if ((rc = issue_keep(s, j))) return rc;
         if (sparse) {
             const size_t eb = (size_t)(nchars ? nchars : 1) * 4;
             if ((rc = s.kmer_ws.ensure(kam_kmer_workspace_bytes(n, j.k))) || (rc = s.entries.ensure(eb)) ||
@@ -487,8 +506,8 @@ int kmers_host_locked(HostCtx &ctx, const Job &j, uint32_t n_seqs) {
 
 extern "C" {
 
-int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_t n_seqs, int k, int count_bits,
-                   int out_kind, void *h_out) {
+int kam_kmers_host_keep(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_t n_seqs, int k, int count_bits,
+                        int out_kind, void *h_out, void *d_counts, uint64_t counts_stride) {
     if (k < 1 || 2 * k > 64) {
         kam_set_error("k is too large to fit in the index");
         return KAM_E_INVALID;
@@ -496,7 +515,8 @@ int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_
     KAM_REQUIRE(k <= 15, "k > 15 not supported by this build");
     KAM_REQUIRE(count_bits == 16 || count_bits == 32, "count_bits must be 16 or 32");
     KAM_REQUIRE(out_kind >= KAM_OUT_COUNTS && out_kind <= KAM_OUT_FREQ_F64, "bad out_kind");
-    KAM_REQUIRE(h_char_start && h_out, "null pointer");
+    KAM_REQUIRE(h_char_start && (h_out || d_counts), "null pointer");
+    KAM_REQUIRE(!d_counts || counts_stride >= ((uint64_t)1 << (2 * k)), "counts_stride smaller than 4^k");
     if (n_seqs == 0) return KAM_OK;
     KAM_REQUIRE(h_chars || h_char_start[n_seqs] == h_char_start[0], "null character buffer");
     std::lock_guard<std::mutex> lock(g_call);
@@ -510,14 +530,25 @@ int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_
     j.count_bits = count_bits;
     j.out_kind = out_kind;
     j.h_out = h_out;
+    j.d_keep = d_counts;
+    j.keep_stride = counts_stride;
     j.bins = (size_t)1 << (2 * k);
     const size_t esz = out_kind == KAM_OUT_COUNTS ? (size_t)count_bits / 8 : (out_kind == KAM_OUT_FREQ_F32 ? 4 : 8);
     j.row_bytes = j.bins * esz;
-    j.out_pinned = is_pinned(h_out);
+    j.out_pinned = h_out && is_pinned(h_out);
     j.in_pinned = h_chars && is_pinned(h_chars);
     rc = kmers_host_locked(*ctx, j, n_seqs);
     if (rc) abandon(*ctx);
+    else if (d_counts)
+        for (auto &s : ctx->slot)            // the kept rows are complete when the call returns
+            if (s.st) cudaStreamSynchronize(s.st);
     return rc;
+}
+
+int kam_kmers_host(const uint8_t *h_chars, const uint64_t *h_char_start, uint32_t n_seqs, int k, int count_bits,
+                   int out_kind, void *h_out) {
+    KAM_REQUIRE(h_out, "null pointer");
+    return kam_kmers_host_keep(h_chars, h_char_start, n_seqs, k, count_bits, out_kind, h_out, nullptr, 0);
 }
 
 void kam_kmers_host_set_sparse(int mode) { g_sparse_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
