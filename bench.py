@@ -572,6 +572,9 @@ def main():
             else:
                 for key, val in d.get("rooflines", {}).items():
                     also[key] = val
+                if "pipeline" in d:
+                    e2e_also["kmers_dists_pipeline"] = compact(d["pipeline"], ("value", "unit", "ms", "h2d_bytes_per_step",
+                                                                                "d2h_bytes_per_step"))
                 for key, val in d.get("e2e", {}).items():
                     if isinstance(val, dict) and "value" in val:
                         e2e_also["dists_host_" + key] = compact(val, ("value", "unit", "ms", "h2d_bytes_per_step",

@@ -7,6 +7,8 @@
   manhattan : BASELINE config 4 shape -- M reads x C=1000 centroids, D=4^6, uint32-exact manhat
               (byte path, VABSDIFF4) ; bound = CUDA-core issue rate, reported as pair-elements/s.
 """
+import time
+
 import numpy as np
 
 
@@ -238,7 +240,6 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
     # ---- e2e: the whole `distances` step on HOST buffers through kam_dists_host ---------------------------
     # (what run_backend_dists calls between reading the .mm-repr and writing the .mm-dist files): H2D of the
     # count vectors, kernels, D2H of the packed triangles, device buffers allocated and freed inside the call
-    import time
     ne, ke = 16384, 6
     de = 4 ** ke
     xe = synth_counts(torch, dev, ne, 9000, ke, 20261006).cpu().pin_memory()
@@ -271,6 +272,46 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
                         "gram_d4096": flat(out["gram_d4096"]), "gram_limb": flat(out["gram_limb"]),
                         "manhattan_u8": flat(out["manhattan"]), "manhattan_u32": flat(out["manhattan_u32"]),
                         "manhattan_f32_centroids": flat(out["manhattan_f32_centroids"]), "info": flat(out["info"])}
+    # ---- e2e of a kmers -> distances job (run_job.py:175-180): host ASCII records -> host count vectors AND
+    # host distance triangles, the count matrix handed over on the device (kam_kmers_host_keep + kam_dists_device)
+    npl, kpl, Lp = 10000, 6, 9000
+    dpl = 4 ** kpl
+    rng = np.random.Generator(np.random.PCG64(20261010))
+    pch = torch.from_numpy(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.choice(4, size=npl * Lp, p=[0.36, 0.18, 0.24, 0.22])]).pin_memory()
+    pst = (np.arange(npl + 1, dtype=np.uint64) * np.uint64(Lp))
+    h_vec = torch.empty((npl, dpl), dtype=torch.uint16).pin_memory()
+    ppl = npl * (npl - 1) // 2
+    h_tri = [torch.empty(ppl, dtype=torch.int32).pin_memory(), torch.empty(ppl, dtype=torch.float32).pin_memory()]
+    d_keep = torch.empty((npl, dpl), dtype=torch.uint16, device=dev)
+
+    def pipeline(handover):
+        if handover:
+            _lib.check(lib.kam_kmers_host_keep(pch.data_ptr(), pst.ctypes.data, npl, kpl, 16, 0, h_vec.data_ptr(),
+                                               d_keep.data_ptr(), dpl))
+            _lib.check(lib.kam_dists_device(d_keep.data_ptr(), 1, npl, dpl, dpl, 1 | 8, 0, h_tri[0].data_ptr(), None, None,
+                                            h_tri[1].data_ptr(), None))
+        else:
+            _lib.check(lib.kam_kmers_host(pch.data_ptr(), pst.ctypes.data, npl, kpl, 16, 0, h_vec.data_ptr()))
+            _lib.check(lib.kam_dists_host(h_vec.data_ptr(), 1, npl, dpl, 1 | 8, h_tri[0].data_ptr(), None, None,
+                                          h_tri[1].data_ptr(), None))
+    pl_res = {}
+    for name, ho in (("device_handover", True), ("reupload", False)):
+        pipeline(ho)
+        pipeline(ho)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            pipeline(ho)
+            ts.append(time.perf_counter() - t0)
+        dt = sorted(ts)[2]
+        pl_res[name] = {"ms": dt * 1e3, "vectors_per_s": npl / dt, "pairs_per_s": ppl / dt}
+    out["pipeline"] = {"api": "kam_kmers_host_keep + kam_dists_device (device hand-over) vs kam_kmers_host + kam_dists_host",
+                       "config": {"workload": "%d sequences x %d bp, k=%d uint16 counts to the host + manhat and cosine "
+                                              "triangles (%d pairs each) to the host" % (npl, Lp, kpl, ppl)},
+                       "value": npl / (pl_res["device_handover"]["ms"] * 1e-3), "unit": "vectors/s",
+                       "ms": pl_res["device_handover"]["ms"], **pl_res,
+                       "h2d_bytes_per_step": npl * Lp, "d2h_bytes_per_step": npl * dpl * 2 + 2 * ppl * 4}
+    del pch, h_vec, h_tri, d_keep
     out["e2e"] = {"api": "kam_dists_host (C ABI, pinned host buffers)",
                   "config": {"workload": "%d count vectors (9 kb genomes, k=%d, D=%d, uint16): %d pairs" % (ne, ke, de, pe)},
                   **e2e}

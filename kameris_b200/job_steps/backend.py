@@ -112,6 +112,47 @@ def kmers_from_records(records, k, bits_per_element, mode):
 
 CHUNK_BYTES = 256 << 20        # pinned staging per buffer; two buffers alternate
 
+# ---- hand-over between the steps of one job ------------------------------------------------------------------
+# run-job runs the steps of an experiment back to back (kameris/subcommands/run_job.py:175-180): `kmers` writes a
+# .mm-repr, `distances` reads it again.  The count matrix the kmers step computed stays on the device (when it
+# fits RESIDENT_MAX_BYTES), remembered under the output file's path, size and mtime; a distances step whose
+# input file still matches takes it from there -- no re-read of the file, no second upload.  The files written
+# are the same either way.
+RESIDENT_MAX_BYTES = int(float(os.environ.get('KAM_RESIDENT_GB', '16')) * (1 << 30))
+_resident = {}
+resident_hits = 0
+
+
+def set_resident_limit(nbytes):
+    global RESIDENT_MAX_BYTES
+    RESIDENT_MAX_BYTES = int(nbytes)
+    if nbytes <= 0:
+        release_resident()
+
+
+def release_resident():
+    _resident.clear()
+
+
+def _remember(path, counts, mode):
+    st = os.stat(path)
+    _resident.clear()                                   # one matrix at a time
+    _resident[os.path.realpath(path)] = {'size': st.st_size, 'mtime_ns': st.st_mtime_ns, 'counts': counts, 'mode': mode}
+
+
+def _recall(path):
+    e = _resident.get(os.path.realpath(path))
+    if e is None:
+        return None
+    try:
+        st = os.stat(path)
+    except OSError:
+        st = None
+    if st is None or st.st_size != e['size'] or st.st_mtime_ns != e['mtime_ns']:
+        _resident.clear()                               # the file changed since: forget the matrix
+        return None
+    return e
+
 
 def kmers_to_file(records, k, bits_per_element, mode, output_file, row_offset=0, total_rows=None, create=True):
     """records (a list of bytes, or the (chars, start) pair of read_records_packed) -> `.mm-repr`, streamed: the batch is cut into chunks of rows; while chunk c is being
@@ -144,6 +185,14 @@ def kmers_to_file(records, k, bits_per_element, mode, output_file, row_offset=0,
         except RuntimeError:
             pass
         bufs.append(t)
+    keep = None
+    cdt = torch.uint16 if bits_per_element == 16 else torch.uint32
+    if create and row_offset == 0 and total_rows is None and n > 1 and torch.cuda.is_available() and \
+            n * d * (bits_per_element // 8) <= RESIDENT_MAX_BYTES:
+        try:
+            keep = torch.empty((n, d), dtype=cdt, device=torch.device('cuda', torch.cuda.current_device()))
+        except RuntimeError:                              # no room on the device: the hand-over is optional
+            keep = None
     if create:
         writer = formats.repr_writer(output_file, np.zeros((1, d), dtype=ndt), n if total_rows is None else total_rows,
                                      create_file=True)
@@ -167,8 +216,9 @@ def kmers_to_file(records, k, bits_per_element, mode, output_file, row_offset=0,
                     futs[slot].result()           # the write that used this buffer has finished
                 sub = (start[i0:i1 + 1] - start[i0]).copy()
                 base = chars.ctypes.data + int(start[i0]) if chars.size else None
-                _lib.check(lib.kam_kmers_host(base, sub.ctypes.data, i1 - i0, k, bits_per_element, kind,
-                                              bufs[slot].data_ptr()))
+                dk = keep.data_ptr() + i0 * d * (bits_per_element // 8) if keep is not None else None
+                _lib.check(lib.kam_kmers_host_keep(base, sub.ctypes.data, i1 - i0, k, bits_per_element, kind,
+                                                   bufs[slot].data_ptr(), dk, d))
                 # positional, multi-threaded write of the chunk's rows (formats.pwrite_from)
                 futs[slot] = wpool.submit(formats.pwrite_from, fd, view(bufs[slot], i1 - i0), base_off + i0 * row_bytes)
             for f in futs:
@@ -176,6 +226,8 @@ def kmers_to_file(records, k, bits_per_element, mode, output_file, row_offset=0,
                     f.result()
     finally:
         writer.file.close()
+    if keep is not None:
+        _remember(output_file, keep, mode)
 
 
 def _world():
@@ -422,12 +474,49 @@ def dists_to_files_sharded(input_file, output_prefix, metrics, dist, device=None
     return n, rows
 
 
+def dists_from_device_counts(counts, metrics, euclid_on_freq):
+    """device count matrix (uint16/uint32) -> {metric: packed triangle ndarray} through kam_dists_device"""
+    lib = _lib.load()
+    n, d = counts.shape
+    pairs = n * (n - 1) // 2
+    bits = {'manhat': _lib.KAM_M_MANHAT, 'info': _lib.KAM_M_INFO, 'euclid': _lib.KAM_M_EUCLID,
+            'cosine': _lib.KAM_M_COSINE, 'pearson': _lib.KAM_M_PEARSON}
+    out, mask = {}, 0
+    for m in metrics:
+        out[m] = np.zeros(pairs, dtype=np.uint32 if m == 'manhat' else np.float32)
+        mask |= bits[m]
+
+    def p(m):
+        return out[m].ctypes.data if m in out else None
+    import torch
+    with torch.cuda.device(counts.device):
+        _lib.check(lib.kam_dists_device(counts.data_ptr(), _lib.KAM_U16 if counts.element_size() == 2 else _lib.KAM_U32,
+                                        n, d, counts.stride(0), mask, int(euclid_on_freq), p('manhat'), p('info'),
+                                        p('euclid'), p('cosine'), p('pearson')))
+    return out
+
+
 def _dists_single(options, metrics):
     """the step in one process (what run_backend_dists does outside a process group)"""
-    with formats.repr_reader(options['input_file']) as reader:
-        x = reader.read_all()                 # raises "Sparse matrices are not supported"
-    n = x.shape[0]
-    res = dists_from_matrix(x, metrics)
+    global resident_hits
+    res, n = {}, None
+    held = _recall(options['input_file'])
+    todo = list(metrics)
+    if held is not None:
+        # counts file: everything from the resident matrix.  frequencies file: the rows are count / sum, so
+        # cosine / pearson / info are those of the counts and euclid is euclid between the frequency vectors;
+        # only `manhat` depends on the float rows themselves (it truncates per addition, quirk Q5).
+        mine = todo if held['mode'] != 'frequencies' else [m for m in todo if m != 'manhat']
+        if mine:
+            n = held['counts'].shape[0]
+            res.update(dists_from_device_counts(held['counts'], mine, held['mode'] == 'frequencies'))
+            todo = [m for m in todo if m not in mine]
+            resident_hits += 1
+    if todo:
+        with formats.repr_reader(options['input_file']) as reader:
+            x = reader.read_all()                 # raises "Sparse matrices are not supported"
+        n = x.shape[0]
+        res.update(dists_from_matrix(x, todo))
     for m in metrics:
         w = formats.dist_writer('%s-%s.mm-dist' % (options['output_prefix'], m), res[m].dtype, n)
         w.write_triangle(res[m])

@@ -10,6 +10,7 @@ import pytest
 
 from kameris_b200 import formats
 from oracle import oracle as O
+from tests.helpers import HIV_P
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -145,3 +146,55 @@ def test_dists_gram_metrics_on_frequencies_file(backend, genomes, tmp_path, k):
         tri, n = formats.dist_reader.read_triangle("%s-%s.mm-dist" % (prefix, m))
         assert n == 4 and tri.dtype == np.float32
         np.testing.assert_allclose(tri, O.cdist_triangle(x, m), rtol=1e-5, err_msg=m)
+
+
+def test_kmers_then_distances_hand_over_on_the_device(tmp_path):
+    """run-job runs kmers then distances (run_job.py:175-180): with the device-resident hand-over the distances
+    step takes the count matrix the kmers step left on the GPU; the files must be byte-identical to the ones made
+    by reading the .mm-repr back, for a counts file and for a frequencies file, and a file that changed after the
+    kmers step must NOT be served from the device."""
+    from kameris_b200 import formats
+    from kameris_b200.job_steps import backend
+    from tests.helpers import synth_records
+    d = tmp_path / "fa"
+    d.mkdir()
+    recs = synth_records(150, 2500, seed=41, jitter=2000, dirty=0.003, p=HIV_P)
+    for i, r in enumerate(recs):
+        (d / ("%04d.fa" % i)).write_bytes(b">s\n" + r + b"\n")
+    names = ["manhat", "info", "euclid", "cosine", "pearson"]
+    limit = backend.RESIDENT_MAX_BYTES
+    try:
+        for mode in ("counts", "frequencies"):
+            out = {}
+            for tag, lim in (("file", 0), ("dev", 1 << 30)):
+                backend.set_resident_limit(lim)
+                hits0 = backend.resident_hits
+                rep = str(tmp_path / ("%s-%s.mm-repr" % (mode, tag)))
+                backend.run_backend_kmers({"fasta_output_dir": str(d), "output_file": rep, "k": 6, "bits_per_element": 16,
+                                           "mode": mode}, {})
+                backend.run_backend_dists({"input_file": rep, "output_prefix": str(tmp_path / ("%s-%s" % (mode, tag))),
+                                           "distances": names}, {})
+                assert (backend.resident_hits > hits0) == (tag == "dev")
+                out[tag] = [open(rep, "rb").read()] + [open(str(tmp_path / ("%s-%s-%s.mm-dist" % (mode, tag, m))), "rb").read()
+                                                       for m in names]
+            for a, b, what in zip(out["file"], out["dev"], ["repr"] + names):
+                assert len(a) > 34 and a == b, (mode, what)
+        # a .mm-repr rewritten after the kmers step is read from the file again
+        backend.set_resident_limit(1 << 30)
+        rep = str(tmp_path / "stale.mm-repr")
+        backend.run_backend_kmers({"fasta_output_dir": str(d), "output_file": rep, "k": 5, "bits_per_element": 16,
+                                   "mode": "counts"}, {})
+        with formats.repr_reader(rep) as r:
+            x = r.read_all()
+        x[0, :] = 7
+        w = formats.repr_writer(rep, x[:1], len(x), create_file=True)
+        w.write_all(x)
+        w.close()
+        hits0 = backend.resident_hits
+        backend.run_backend_dists({"input_file": rep, "output_prefix": str(tmp_path / "stale"), "distances": ["manhat"]}, {})
+        assert backend.resident_hits == hits0
+        tri, n = formats.dist_reader.read_triangle(str(tmp_path / "stale-manhat.mm-dist"))
+        assert tri[0] == int(np.abs(x[0].astype(np.int64) - x[1].astype(np.int64)).sum())
+    finally:
+        backend.set_resident_limit(limit)
+        backend.release_resident()
