@@ -153,12 +153,15 @@ HostPool &pool() {
 }
 
 // ---- expansion of one entry list into one dense row ------------------------------------------------------
-// The row is produced in chunks of CHUNK bytes.  A chunk without entries is streamed out as zeros.  A chunk
-// with entries is composed in a small buffer that stays in L1 (fill, scatter the entries, then copy it out with
-// non-temporal stores): composing cache line by cache line instead made every 16-byte load of the line wait for
-// the scalar stores just before it (failed store forwarding) and cost ~90 cycles per entry, which bounded
-// uint16 rows -- nearly every line of a k=9 count row of a 9 kb genome holds an entry -- at half the DRAM rate.
-constexpr size_t EXPAND_CHUNK = 2048;
+// Every 64-byte line of the row is written exactly once with non-temporal stores: runs of lines without an
+// entry are streamed as zeros straight from a register; a line that holds entries is composed in a small
+// buffer and streamed out from there.  The copy-out of a composed line is DELAYED by a few lines (a ring of
+// line buffers): a 16-byte load right behind the 2/4/8-byte stores that composed the line cannot be forwarded
+// from the store buffer and waits for them to drain (measured: ~90 cycles per entry, half the DRAM rate on
+// uint16 rows, where nearly every line of a k = 9 row of a 9 kb genome holds an entry); a few lines later the
+// stores have long retired.  (Composing whole 2 KB chunks in L1 instead cost a second pass over every byte and
+// was slower on float64 rows, where three lines out of four are plain zeros.)
+constexpr int EXPAND_RING = 4;
 
 template <typename OUT>
 inline OUT convert_host(uint32_t c, double sum, int out_kind) {
@@ -167,64 +170,166 @@ inline OUT convert_host(uint32_t c, double sum, int out_kind) {
     return (OUT)c;
 }
 
-inline void stream_zero(char *p, size_t bytes) {
-    const __m128i z = _mm_setzero_si128();
-    for (size_t i = 0; i < bytes; i += 64) {
-        _mm_stream_si128((__m128i *)(p + i), z);
-        _mm_stream_si128((__m128i *)(p + i + 16), z);
-        _mm_stream_si128((__m128i *)(p + i + 32), z);
-        _mm_stream_si128((__m128i *)(p + i + 48), z);
-    }
-}
+// The body of the expansion, compiled three times: for SSE2 (any x86-64), AVX2 and AVX-512 (one 64-byte store
+// per line), chosen once at run time from the CPU's capabilities.  ZERO_LINES(p, n): n zero lines to p,
+// non-temporal; CLEAR_LINE(t): zero a line buffer; COPY_LINE(dst, src): line buffer -> memory, non-temporal.
+#define KAM_EXPAND_ROW_BODY                                                                                        \
+    unsigned long long s = 0;                                                                                      \
+    uint32_t maxc = 0;                                                                                             \
+    for (uint32_t e = 0; e < nnz; ++e) {                                                                           \
+        const uint32_t c = ent[e] & 0xffu;                                                                         \
+        s += c;                                                                                                    \
+        maxc = c > maxc ? c : maxc;                                                                                \
+    }                                                                                                              \
+    OUT lut[256];                                                                                                  \
+    for (uint32_t c = 0; c <= maxc; ++c) lut[c] = convert_host<OUT>(c, (double)s, out_kind);                       \
+    const OUT zero = lut[0]; /* an empty sequence in a frequencies file is 0/0 = NaN everywhere, like numpy */    \
+    const size_t row_bytes = bins * sizeof(OUT);                                                                   \
+    const bool plain_zero = out_kind == KAM_OUT_COUNTS || s != 0;                                                  \
+    if (((uintptr_t)row & 63) != 0 || row_bytes % 64 != 0 || !plain_zero) { /* odd placement / tiny / NaN rows */ \
+        for (size_t i = 0; i < bins; ++i) row[i] = zero;                                                           \
+        for (uint32_t e = 0; e < nnz; ++e) row[ent[e] >> 8] = lut[ent[e] & 0xffu];                                 \
+        return;                                                                                                    \
+    }                                                                                                              \
+    constexpr uint32_t EPL = 64 / sizeof(OUT); /* elements per 64-byte line */                                     \
+    constexpr uint32_t LSH = EPL == 32 ? 5 : (EPL == 16 ? 4 : 3);                                                  \
+    char *p = (char *)row;                                                                                         \
+    const size_t nlines = bins / EPL;                                                                              \
+    alignas(64) OUT ring[EXPAND_RING][EPL];                                                                        \
+    char *pend[EXPAND_RING];                                                                                       \
+    for (int i = 0; i < EXPAND_RING; ++i) pend[i] = nullptr;                                                       \
+    int cur = 0;                                                                                                   \
+    size_t line = 0;                                                                                               \
+    uint32_t e = 0;                                                                                                \
+    while (e < nnz) {                                                                                              \
+        uint32_t bin = ent[e] >> 8;                                                                                \
+        const size_t l = bin >> LSH;                                                                               \
+        if (l > line) ZERO_LINES(p + line * 64, l - line);                                                         \
+        if (pend[cur]) COPY_LINE(pend[cur], (const char *)ring[cur]); /* composed EXPAND_RING lines ago */         \
+        OUT *t = ring[cur];                                                                                        \
+        CLEAR_LINE((char *)t);                                                                                     \
+        do {                                                                                                       \
+            t[bin & (EPL - 1)] = lut[ent[e] & 0xffu];                                                              \
+            ++e;                                                                                                   \
+            if (e == nnz) break;                                                                                   \
+            bin = ent[e] >> 8;                                                                                     \
+        } while ((bin >> LSH) == l);                                                                               \
+        pend[cur] = p + l * 64;                                                                                    \
+        cur = (cur + 1) % EXPAND_RING;                                                                             \
+        line = l + 1;                                                                                              \
+    }                                                                                                              \
+    for (int i = 0; i < EXPAND_RING; ++i, cur = (cur + 1) % EXPAND_RING)                                           \
+        if (pend[cur]) COPY_LINE(pend[cur], (const char *)ring[cur]);                                              \
+    if (nlines > line) ZERO_LINES(p + line * 64, nlines - line);
 
-inline void stream_copy(char *dst, const char *src, size_t bytes) {
-    for (size_t i = 0; i < bytes; i += 64) {
-        const __m128i a = _mm_load_si128((const __m128i *)(src + i)), b = _mm_load_si128((const __m128i *)(src + i + 16));
-        const __m128i c = _mm_load_si128((const __m128i *)(src + i + 32)), d = _mm_load_si128((const __m128i *)(src + i + 48));
-        _mm_stream_si128((__m128i *)(dst + i), a);
-        _mm_stream_si128((__m128i *)(dst + i + 16), b);
-        _mm_stream_si128((__m128i *)(dst + i + 32), c);
-        _mm_stream_si128((__m128i *)(dst + i + 48), d);
+// ---- SSE2
+#define ZERO_LINES(q, n)                                           \
+    do {                                                           \
+        char *zq = (q);                                            \
+        const __m128i z = _mm_setzero_si128();                     \
+        for (size_t zi = 0; zi < (size_t)(n); ++zi, zq += 64) {    \
+            _mm_stream_si128((__m128i *)zq, z);                    \
+            _mm_stream_si128((__m128i *)(zq + 16), z);             \
+            _mm_stream_si128((__m128i *)(zq + 32), z);             \
+            _mm_stream_si128((__m128i *)(zq + 48), z);             \
+        }                                                          \
+    } while (0)
+#define CLEAR_LINE(t)                                              \
+    do {                                                           \
+        const __m128i z = _mm_setzero_si128();                     \
+        _mm_store_si128((__m128i *)(t), z);                        \
+        _mm_store_si128((__m128i *)((t) + 16), z);                 \
+        _mm_store_si128((__m128i *)((t) + 32), z);                 \
+        _mm_store_si128((__m128i *)((t) + 48), z);                 \
+    } while (0)
+#define COPY_LINE(dst, src)                                                                \
+    do {                                                                                   \
+        const __m128i a = _mm_load_si128((const __m128i *)(src));                          \
+        const __m128i b = _mm_load_si128((const __m128i *)((src) + 16));                   \
+        const __m128i c = _mm_load_si128((const __m128i *)((src) + 32));                   \
+        const __m128i d = _mm_load_si128((const __m128i *)((src) + 48));                   \
+        _mm_stream_si128((__m128i *)(dst), a);                                             \
+        _mm_stream_si128((__m128i *)((dst) + 16), b);                                      \
+        _mm_stream_si128((__m128i *)((dst) + 32), c);                                      \
+        _mm_stream_si128((__m128i *)((dst) + 48), d);                                      \
+    } while (0)
+template <typename OUT>
+void expand_row_sse2(OUT *row, size_t bins, const uint32_t *ent, uint32_t nnz, int out_kind) {
+    KAM_EXPAND_ROW_BODY
+}
+#undef ZERO_LINES
+#undef CLEAR_LINE
+#undef COPY_LINE
+
+// ---- AVX2
+#define ZERO_LINES(q, n)                                           \
+    do {                                                           \
+        char *zq = (q);                                            \
+        const __m256i z = _mm256_setzero_si256();                  \
+        for (size_t zi = 0; zi < (size_t)(n); ++zi, zq += 64) {    \
+            _mm256_stream_si256((__m256i *)zq, z);                 \
+            _mm256_stream_si256((__m256i *)(zq + 32), z);          \
+        }                                                          \
+    } while (0)
+#define CLEAR_LINE(t)                                              \
+    do {                                                           \
+        const __m256i z = _mm256_setzero_si256();                  \
+        _mm256_store_si256((__m256i *)(t), z);                     \
+        _mm256_store_si256((__m256i *)((t) + 32), z);              \
+    } while (0)
+#define COPY_LINE(dst, src)                                                                \
+    do {                                                                                   \
+        const __m256i a = _mm256_load_si256((const __m256i *)(src));                       \
+        const __m256i b = _mm256_load_si256((const __m256i *)((src) + 32));                \
+        _mm256_stream_si256((__m256i *)(dst), a);                                          \
+        _mm256_stream_si256((__m256i *)((dst) + 32), b);                                   \
+    } while (0)
+template <typename OUT>
+__attribute__((target("avx2"))) void expand_row_avx2(OUT *row, size_t bins, const uint32_t *ent, uint32_t nnz,
+                                                     int out_kind) {
+    KAM_EXPAND_ROW_BODY
+}
+#undef ZERO_LINES
+#undef CLEAR_LINE
+#undef COPY_LINE
+
+// ---- AVX-512: one instruction per line
+#define ZERO_LINES(q, n)                                           \
+    do {                                                           \
+        char *zq = (q);                                            \
+        const __m512i z = _mm512_setzero_si512();                  \
+        for (size_t zi = 0; zi < (size_t)(n); ++zi, zq += 64) _mm512_stream_si512((__m512i *)zq, z); \
+    } while (0)
+#define CLEAR_LINE(t) _mm512_store_si512((__m512i *)(t), _mm512_setzero_si512())
+#define COPY_LINE(dst, src) _mm512_stream_si512((__m512i *)(dst), _mm512_load_si512((const __m512i *)(src)))
+template <typename OUT>
+__attribute__((target("avx512f"))) void expand_row_avx512(OUT *row, size_t bins, const uint32_t *ent, uint32_t nnz,
+                                                          int out_kind) {
+    KAM_EXPAND_ROW_BODY
+}
+#undef ZERO_LINES
+#undef CLEAR_LINE
+#undef COPY_LINE
+
+int g_expand_isa = -1;   // 0 SSE2, 1 AVX2, 2 AVX-512; KAM_HOST_ISA=sse2|avx2|avx512 in the environment overrides
+int expand_isa() {
+    if (g_expand_isa < 0) {
+        int isa = __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+        if (const char *e = getenv("KAM_HOST_ISA")) {
+            const int want = !strcmp(e, "sse2") ? 0 : (!strcmp(e, "avx2") ? 1 : (!strcmp(e, "avx512") ? 2 : isa));
+            if (want < isa) isa = want;
+        }
+        g_expand_isa = isa;
     }
+    return g_expand_isa;
 }
 
 template <typename OUT>
 void expand_row(OUT *row, size_t bins, const uint32_t *ent, uint32_t nnz, int out_kind) {
-    unsigned long long s = 0;
-    uint32_t maxc = 0;
-    for (uint32_t e = 0; e < nnz; ++e) {
-        const uint32_t c = ent[e] & 0xffu;
-        s += c;
-        maxc = c > maxc ? c : maxc;
-    }
-    OUT lut[256];
-    for (uint32_t c = 0; c <= maxc; ++c) lut[c] = convert_host<OUT>(c, (double)s, out_kind);
-    const OUT zero = lut[0];        // an empty sequence in a frequencies file is 0/0 = NaN everywhere, like numpy
-    const size_t row_bytes = bins * sizeof(OUT);
-    if (((uintptr_t)row & 15) != 0 || row_bytes % EXPAND_CHUNK != 0) {   // odd placement / tiny rows: plain stores
-        for (size_t i = 0; i < bins; ++i) row[i] = zero;
-        for (uint32_t e = 0; e < nnz; ++e) row[ent[e] >> 8] = lut[ent[e] & 0xffu];
-        return;
-    }
-    constexpr uint32_t CE = EXPAND_CHUNK / sizeof(OUT);   // elements per chunk
-    const bool plain_zero = out_kind == KAM_OUT_COUNTS || s != 0;
-    alignas(64) OUT buf[CE];
-    char *p = (char *)row;
-    uint32_t e = 0;
-    uint32_t next_bin = nnz ? ent[0] >> 8 : 0xffffffffu;
-    for (size_t c0 = 0; c0 < bins; c0 += CE, p += EXPAND_CHUNK) {
-        if (next_bin >= c0 + CE && plain_zero) {
-            stream_zero(p, EXPAND_CHUNK);
-            continue;
-        }
-        if (plain_zero) memset(buf, 0, EXPAND_CHUNK);
-        else for (uint32_t i = 0; i < CE; ++i) buf[i] = zero;
-        while (next_bin < c0 + CE) {
-            buf[next_bin - c0] = lut[ent[e] & 0xffu];
-            ++e;
-            next_bin = e < nnz ? ent[e] >> 8 : 0xffffffffu;
-        }
-        stream_copy(p, (const char *)buf, EXPAND_CHUNK);
+    switch (expand_isa()) {
+        case 2: expand_row_avx512<OUT>(row, bins, ent, nnz, out_kind); break;
+        case 1: expand_row_avx2<OUT>(row, bins, ent, nnz, out_kind); break;
+        default: expand_row_sse2<OUT>(row, bins, ent, nnz, out_kind);
     }
 }
 
