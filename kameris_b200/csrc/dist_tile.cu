@@ -226,10 +226,13 @@ __global__ void max_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint
 template <typename T>
 __global__ void manhat_serial_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,
                                      uint32_t row_end, uint32_t *__restrict__ tri) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t i = row_begin + blockIdx.y;
-    if (i >= row_end || j >= n || j <= i) return;
-    const T *a = x + (uint64_t)i * ld, *b = x + (uint64_t)j * ld;
+    // rows in gridDim.x (up to 2^31 - 1 blocks); the column blocks of a row, at most n / 128, in gridDim.y
+    const uint32_t i = row_begin + blockIdx.x;
+    if (i >= row_end) return;
+    const T *a = x + (uint64_t)i * ld;
+    for (uint32_t j = blockIdx.y * blockDim.x + threadIdx.x; j < n; j += gridDim.y * blockDim.x) {
+    if (j <= i) continue;
+    const T *b = x + (uint64_t)j * ld;
     uint32_t acc = 0;
     for (uint64_t e = 0; e < d; ++e) {
         if constexpr (std::is_same<T, float>::value) {
@@ -247,6 +250,7 @@ __global__ void manhat_serial_kernel(const T *__restrict__ x, uint32_t n, uint64
         }
     }
     tri[tri_base(n, i) + j] = acc;
+    }
 }
 
 inline uint32_t pad4(uint32_t n) { return (n + 3u) & ~3u; }
@@ -355,7 +359,9 @@ int kam_manhattan_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_
     if (n < 2 || row_begin >= row_end) return KAM_OK;
     if (row_end > n) row_end = n;
     if (elem == KAM_U64 || elem == KAM_F32 || elem == KAM_F64) {
-        dim3 grid((n + 127) / 128, row_end - row_begin);
+        uint32_t gy = (n + 127) / 128;
+        if (gy > 65535) gy = 65535;
+        dim3 grid(row_end - row_begin, gy);
         if (elem == KAM_U64) manhat_serial_kernel<uint64_t><<<grid, 128, 0, st>>>((const uint64_t *)d_x, n, d, ld, row_begin, row_end, d_tri);
         else if (elem == KAM_F32) manhat_serial_kernel<float><<<grid, 128, 0, st>>>((const float *)d_x, n, d, ld, row_begin, row_end, d_tri);
         else manhat_serial_kernel<double><<<grid, 128, 0, st>>>((const double *)d_x, n, d, ld, row_begin, row_end, d_tri);

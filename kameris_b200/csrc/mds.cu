@@ -99,10 +99,10 @@ __global__ void __launch_bounds__(1024) mds_mean_kernel(const double *__restrict
 __global__ void __launch_bounds__(256) mds_center_kernel(double *__restrict__ B, uint32_t n,
                                                          const double *__restrict__ tot,
                                                          const double *__restrict__ mean) {
-    const uint32_t i = blockIdx.y;
+    const uint32_t i = blockIdx.x;                       // rows in gridDim.x: n may exceed the 65535 of gridDim.y
     const double ti = tot[i], m = mean[0];
     double *r = B + (uint64_t)i * n;
-    for (uint32_t j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256)
+    for (uint32_t j = blockIdx.y * 256 + threadIdx.x; j < n; j += gridDim.y * 256)
         r[j] = ((r[j] - tot[j]) - ti + m) * -0.5;
 }
 
@@ -372,7 +372,7 @@ int kam_mds_center(const void *d_tri, int elem, uint32_t n, double *d_B, void *d
     mds_mean_kernel<<<1, 1024, 0, st>>>(tot, n, mean);
     unsigned gx = (n + 255) / 256;
     if (gx > 64) gx = 64;
-    mds_center_kernel<<<dim3(gx, n), 256, 0, st>>>(d_B, n, tot, mean);
+    mds_center_kernel<<<dim3(n, gx), 256, 0, st>>>(d_B, n, tot, mean);
     KAM_CUDA(cudaGetLastError());
     return KAM_OK;
 }

@@ -112,8 +112,14 @@ def top_eigenpairs(B, dim, tol=1e-12, max_iter=5000, seed=0, stats=None, check_e
                 break
             Q_good.copy_(Q)
         Q[:, :b] = orth(Y[:, :b])
+    converged = bool((res <= tol * scale).all()) or b == n
+    if not converged:
+        import logging
+        logging.getLogger('kameris').warning(
+            'mds: the subspace iteration stopped after %d sweeps with relative residual %.3g (tolerance %.3g): '
+            'the embedding is approximate', it, float((res / scale).max()), tol)
     if stats is not None:
-        stats.update({"iterations": it, "residual": float((res / scale).max()), "block": b,
+        stats.update({"iterations": it, "residual": float((res / scale).max()), "block": b, "converged": converged,
                       "orthonormalisation": "householder" if householder else "cholesky-qr2"})
     w = theta[order]
     desc = torch.argsort(w, descending=True)
