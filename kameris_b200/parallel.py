@@ -177,6 +177,20 @@ def ring_schedule(world):
     return plan
 
 
+def ring_groups(world):
+    """Steps s >= 1 of ring_schedule that run as ONE kernel launch: the first full block alone (work can start as
+    soon as one shard has arrived), the remaining full blocks two at a time -- their column shards sit side by side
+    in one receive buffer, which halves the wave-quantisation loss of small blocks (8 ranks x 5000 rows: 400 tiles
+    on 74 CTA pairs is 5.4 -> 6 waves, 800 tiles 10.8 -> 11) -- and the half block shared by two ranks last."""
+    last = world // 2
+    shared = last if (world % 2 == 0 and world > 1) else None
+    full = [s for s in range(1, last + 1) if s != shared]
+    groups = [[s] for s in full[:1]] + [full[i:i + 2] for i in range(1, len(full), 2)]
+    if shared is not None:
+        groups.append([shared])
+    return groups
+
+
 _PEER = {}      # device index -> this rank's exported operand buffer and the peers' buffers it has opened
 
 
@@ -324,29 +338,40 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
         rb = _align(max(n, 1) * dpad * esz)
         return rb, rb + max(n, 1) * 8, rb + 2 * max(n, 1) * 8
 
-    # 3. start fetching the shards of the later steps, in the order they are needed
-    plan = ring_schedule(world)[rank]
+    # 3. start fetching the shards of the later steps, in the order they are needed.  Steps that run as ONE
+    #    launch (ring_groups) share a receive buffer laid out [rows of all its shards | S | G].
+    plan = {st: (a, c, part) for st, a, c, part in ring_schedule(world)[rank]}
+    groups = ring_groups(world) if transport == "peer" else [[st] for st in range(1, world // 2 + 1)]
     bufs, ready = {}, {}
     if transport == "peer":
         side = _peer_state(dev).get("stream")
         if side is None:
             side = _peer_state(dev)["stream"] = torch.cuda.Stream(dev)
-        for s in range(1, world // 2 + 1):
-            src = (rank + s) % world
-            nb = layout(counts[src])[2]
-            bufs[s] = torch.empty(nb, dtype=torch.uint8, device=dev)
+        for gi, g in enumerate(groups):
+            srcs = [(rank + st) % world for st in g]
+            n_g = sum(counts[r] for r in srcs)
+            sg_, gg_, nb = layout(n_g)
+            bufs[gi] = torch.empty(nb, dtype=torch.uint8, device=dev)
+            off = 0
             with torch.cuda.device(dev):
-                _lib.check(lib.kam_peer_copy(bufs[s].data_ptr(), _peer_open(lib, dev, src, handles[src]), nb,
-                                             side.cuda_stream))
-            ready[s] = torch.cuda.Event()
-            ready[s].record(side)
+                for src in srcs:
+                    n_s = counts[src]
+                    ss_, gs_, _ = layout(n_s)
+                    peer = _peer_open(lib, dev, src, handles[src])
+                    for dst_off, src_off, nbytes in ((off * dpad * esz, 0, n_s * dpad * esz), (sg_ + off * 8, ss_, n_s * 8),
+                                                     (gg_ + off * 8, gs_, n_s * 8)):
+                        _lib.check(lib.kam_peer_copy(bufs[gi].data_ptr() + dst_off, peer + src_off, nbytes,
+                                                     side.cuda_stream))
+                    off += n_s
+            ready[gi] = torch.cuda.Event()
+            ready[gi].record(side)
     elif transport == "nccl":
         # each pair of ops is its own NCCL group, so they complete in order while the compute stream works
-        for s in range(1, world // 2 + 1):
-            src, dst = (rank + s) % world, (rank - s) % world
-            bufs[s] = torch.empty(layout(counts[src])[2], dtype=torch.uint8, device=dev)
-            ready[s] = dist.batch_isend_irecv([dist.P2POp(dist.isend, keep[-1][:layout(n_loc)[2]], dst, group),
-                                               dist.P2POp(dist.irecv, bufs[s], src, group)])
+        for gi, g in enumerate(groups):
+            src, dst = (rank + g[0]) % world, (rank - g[0]) % world
+            bufs[gi] = torch.empty(layout(counts[src])[2], dtype=torch.uint8, device=dev)
+            ready[gi] = dist.batch_isend_irecv([dist.P2POp(dist.isend, keep[-1][:layout(n_loc)[2]], dst, group),
+                                                dist.P2POp(dist.irecv, bufs[gi], src, group)])
     elif world > 1:
         raise ValueError("unknown ring transport %r" % transport)
 
@@ -355,36 +380,38 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
         sm_reserve = int(os.environ.get("KAM_RING_SM_RESERVE", "16"))
     if transport != "nccl":
         sm_reserve = 0              # copy-engine transfers need no SM
-    last_step = world // 2
     out_blocks = []
-    for s, a, c, part in plan:
+    for gi, g in enumerate([[0]] + groups):
+        gi -= 1                     # index into bufs / ready; -1 = the local triangular block
+        a, c, part = plan[g[0]]
         # NCCL transport: SMs are left to the send/recv kernels only while transfers are still in flight
-        sm_limit = max(sms - sm_reserve, 2) if (sm_reserve and s < last_step) else 0
-        if s > 0:
-            mark("wait%d" % s)
+        sm_limit = max(sms - sm_reserve, 2) if (sm_reserve and gi < len(groups) - 1) else 0
+        if gi >= 0:
+            mark("wait%d" % g[0])
             if transport == "peer":
-                cur.wait_event(ready[s])
+                cur.wait_event(ready[gi])
             else:
-                for w in ready[s]:
+                for w in ready[gi]:
                     w.wait()        # the compute stream waits for the transfer, the host does not
-        mark("block%d" % s)
-        mine, theirs = (base, n_loc), ((bufs[s].data_ptr(), counts[(rank + s) % world]) if s > 0 else (base, n_loc))
+        mark("block%d" % g[0])
+        cols = [(rank + st) % world for st in g] if gi >= 0 else [rank]
+        n_g = sum(counts[r] for r in cols)
+        mine, theirs = (base, n_loc), ((bufs[gi].data_ptr(), n_g) if gi >= 0 else (base, n_loc))
         if part == "hi":            # A = the received shard a (rows of the shared block), B = my shard
             (pa, n_a), (pb, n_b) = theirs, mine
-        else:                        # A = my shard, B = my shard (tri) or the received one
+        else:                        # A = my shard, B = my shard (tri) or the received one(s)
             (pa, n_a), (pb, n_b) = mine, theirs
         sa, ga, _ = layout(n_a)
         sb, gb, _ = layout(n_b)
         h = n_a // 2
         r0, r1 = {"tri": (0, n_a), "full": (0, n_a), "lo": (0, h), "hi": (h, n_a)}[part]
-        blk = {"row_shard": a, "col_shard": c, "rows": (r0, r1), "tri": part == "tri"}
-        ptrs = {}
+        ptrs, outs = {}, {}
         for m in metrics:
             # every entry of a rectangular block is written by the kernel; a triangular block keeps zeros
             # on and below its diagonal
             alloc = torch.zeros if part == "tri" else torch.empty
             t = alloc((max(r1 - r0, 1), max(n_b, 1)), dtype=torch.float32, device=dev)
-            blk[m] = t[:r1 - r0, :n_b]
+            outs[m] = t
             ptrs[m] = t.data_ptr() - r0 * n_b * 4          # the kernel indexes rows from 0
         ws = torch.empty(lib.kam_gram_block_workspace_bytes(n_a, n_b), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
@@ -392,8 +419,16 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
                                           int(part == "tri"), r0, r1, mask, int(euclid_on_freq),
                                           ptrs.get("euclid"), ptrs.get("cosine"), ptrs.get("pearson"), n_b, sm_limit,
                                           ws.data_ptr(), ws.numel(), stream))
-        blk["_keep"] = ws
-        out_blocks.append(blk)
+        # one block per (row shard, column shard): a merged launch is cut along its column shards
+        off = 0
+        for st in g:
+            a_s, c_s, _ = plan[st]
+            n_c = n_b if len(g) == 1 else counts[c_s]
+            blk = {"row_shard": a_s, "col_shard": c_s, "rows": (r0, r1), "tri": part == "tri", "_keep": ws}
+            for m in metrics:
+                blk[m] = outs[m][:r1 - r0, off:off + n_c]
+            off += n_c
+            out_blocks.append(blk)
     mark("end")
     cur.synchronize()
     if transport == "peer":

@@ -288,3 +288,21 @@ def test_sharded_steps_agree_on_failure(tmp_path, which):
     assert ("no FASTA record" in got[1]) if which == "kmers" else ("injected" in got[1]), got
     assert not os.path.exists(os.path.join(root, "bad.mm-repr"))
     assert not os.path.exists(os.path.join(root, "bad-manhat.mm-dist"))
+
+
+def test_ring_groups_cover_every_step_once():
+    """launch groups of the ring: every step s = 1..world//2 exactly once and in order, the first group a single
+    step (work starts after ONE shard), merged groups only of full blocks, the shared half block alone and last"""
+    for world in range(1, 17):
+        groups = parallel.ring_groups(world)
+        flat = [s for g in groups for s in g]
+        assert flat == list(range(1, world // 2 + 1)), world
+        plan = {s: part for s, _, _, part in parallel.ring_schedule(world)[0]}
+        for g in groups:
+            assert 1 <= len(g) <= 2
+            if len(g) > 1:
+                assert all(plan[s] == "full" for s in g), (world, g)
+        if groups:
+            assert len(groups[0]) == 1
+        if world % 2 == 0 and world > 1:
+            assert groups[-1] == [world // 2] and plan[world // 2] in ("lo", "hi")
