@@ -194,6 +194,11 @@ def test_kmers_to_file_streaming_writer_with_host_stand_in(tmp_path, monkeypatch
             return getattr(real, name)
 
         @staticmethod
+        def kam_kmers_host_keep(base, starts, n, kk, b, kind, out_ptr, d_counts, stride):
+            assert d_counts is None             # no device here: nothing can stay resident
+            return Fake.kam_kmers_host(base, starts, n, kk, b, kind, out_ptr)
+
+        @staticmethod
         def kam_kmers_host(base, starts, n, kk, b, kind, out_ptr):
             st = np.ctypeslib.as_array(ctypes.cast(starts, ctypes.POINTER(ctypes.c_uint64)), shape=(n + 1,))
             raw = ctypes.string_at(base, int(st[n])) if base else b""
