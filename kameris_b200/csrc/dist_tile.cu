@@ -42,7 +42,12 @@ struct OpT {
 template <int OP>
 __device__ __forceinline__ void pair_op(typename OpT<OP>::acc_t *acc, uint32_t a, uint32_t b) {
     if constexpr (OP == OP_SAD32) acc[0] = __usad(a, b, acc[0]);
-    else if constexpr (OP == OP_SAD8X4) acc[0] += __vsadu4(a, b);
+    else if constexpr (OP == OP_SAD8X4) {
+        // the accumulating form, spelled out: with `acc += __vsadu4(a, b)` the compiler issued VABSDIFF4 into a
+        // zero accumulator and folded pairs of results into the sum with IADD3 -- 1.5 ALU-pipe instructions per
+        // pair-op instead of 1 (SASS of round 1; the kernel sat at 0.70 of the measured VABSDIFF4 rate)
+        asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(acc[0]) : "r"(a), "r"(b));
+    }
     else if constexpr (OP == OP_JACC) {
         acc[0] += __popc(a | b);   // union
         acc[1] += __popc(a ^ b);   // union - intersection
