@@ -177,15 +177,22 @@ def ring_schedule(world):
     return plan
 
 
-def ring_groups(world):
-    """Steps s >= 1 of ring_schedule that run as ONE kernel launch: the first full block alone (work can start as
-    soon as one shard has arrived), the remaining full blocks two at a time -- their column shards sit side by side
-    in one receive buffer, which halves the wave-quantisation loss of small blocks (8 ranks x 5000 rows: 400 tiles
-    on 74 CTA pairs is 5.4 -> 6 waves, 800 tiles 10.8 -> 11) -- and the half block shared by two ranks last."""
+def ring_groups(world, merge=None):
+    """Steps s >= 1 of ring_schedule grouped into kernel launches.  Default: one launch per step.  With merge
+    (KAM_RING_MERGE=1): the first full block alone, the remaining full blocks two at a time on a shared receive
+    buffer -- fewer, larger launches lose less to wave quantisation (8 ranks x 5000 rows: 400 tiles on 74 CTA
+    pairs is 5.4 -> 6 waves, 800 tiles 10.8 -> 11; measured 7.2 -> 6.6 ms for the two blocks) but must wait for
+    BOTH shards: at the ~550 GB/s a rank pulls while all eight pull at once that cost 1.3 ms more than it saved
+    (17.3 vs 16.3 ms per call), so it is off unless the shards are small against the blocks."""
+    if merge is None:
+        merge = os.environ.get("KAM_RING_MERGE", "0") == "1"
     last = world // 2
     shared = last if (world % 2 == 0 and world > 1) else None
     full = [s for s in range(1, last + 1) if s != shared]
-    groups = [[s] for s in full[:1]] + [full[i:i + 2] for i in range(1, len(full), 2)]
+    if merge:
+        groups = [[s] for s in full[:1]] + [full[i:i + 2] for i in range(1, len(full), 2)]
+    else:
+        groups = [[s] for s in full]
     if shared is not None:
         groups.append([shared])
     return groups
@@ -342,11 +349,14 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
     #    launch (ring_groups) share a receive buffer laid out [rows of all its shards | S | G].
     plan = {st: (a, c, part) for st, a, c, part in ring_schedule(world)[rank]}
     groups = ring_groups(world) if transport == "peer" else [[st] for st in range(1, world // 2 + 1)]
+    split_pull = os.environ.get("KAM_RING_SPLIT_PULL", "1") == "1"
     bufs, ready = {}, {}
     if transport == "peer":
         side = _peer_state(dev).get("stream")
         if side is None:
             side = _peer_state(dev)["stream"] = torch.cuda.Stream(dev)
+            _peer_state(dev)["stream2"] = torch.cuda.Stream(dev)
+        side2 = _peer_state(dev)["stream2"]     # a second copy engine takes the upper half of every shard's rows
         for gi, g in enumerate(groups):
             srcs = [(rank + st) % world for st in g]
             n_g = sum(counts[r] for r in srcs)
@@ -358,11 +368,19 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
                     n_s = counts[src]
                     ss_, gs_, _ = layout(n_s)
                     peer = _peer_open(lib, dev, src, handles[src])
-                    for dst_off, src_off, nbytes in ((off * dpad * esz, 0, n_s * dpad * esz), (sg_ + off * 8, ss_, n_s * 8),
-                                                     (gg_ + off * 8, gs_, n_s * 8)):
-                        _lib.check(lib.kam_peer_copy(bufs[gi].data_ptr() + dst_off, peer + src_off, nbytes,
-                                                     side.cuda_stream))
+                    rb = n_s * dpad * esz
+                    h1 = (n_s // 2) * dpad * esz if split_pull else rb
+                    for dst_off, src_off, nbytes, stm in ((off * dpad * esz, 0, h1, side),
+                                                          (off * dpad * esz + h1, h1, rb - h1, side2),
+                                                          (sg_ + off * 8, ss_, n_s * 8, side),
+                                                          (gg_ + off * 8, gs_, n_s * 8, side)):
+                        if nbytes:
+                            _lib.check(lib.kam_peer_copy(bufs[gi].data_ptr() + dst_off, peer + src_off, nbytes,
+                                                         stm.cuda_stream))
                     off += n_s
+            ev2 = torch.cuda.Event()
+            ev2.record(side2)
+            side.wait_event(ev2)                # the group is ready when both halves have landed
             ready[gi] = torch.cuda.Event()
             ready[gi].record(side)
     elif transport == "nccl":
@@ -433,6 +451,7 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
     cur.synchronize()
     if transport == "peer":
         torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.current_stream(dev).wait_stream(side2)
         dist.barrier(group)         # nobody overwrites or frees its exported rows while a peer still reads them
     for b in out_blocks:
         b.pop("_keep", None)

@@ -13,7 +13,8 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 x = ring_bench.gen_shard(dev, rank, world, ring_bench.N_TOTAL, 9, 2026100300)
 parallel.gram_ring(x, ("cosine", "pearson"))
-for tr, res in ([("local", 0)] if world == 1 else [("peer", 0), ("nccl", 16), ("peer", 0)]):
+for tr, res, split in ([("local", 0, "1")] if world == 1 else [("peer", 0, "1"), ("peer", 0, "0"), ("peer", 0, "1")]):
+    os.environ["KAM_RING_SPLIT_PULL"] = split
     best = None
     for rep in range(3):
         t = {}
@@ -28,6 +29,6 @@ for tr, res in ([("local", 0)] if world == 1 else [("peer", 0), ("nccl", 16), ("
         if best is None or ms < best[0]:
             best = (ms, t)
     if rank == 0:
-        print(json.dumps({"world": world, "sm_reserve": res, "ms": best[0], **best[1]}), flush=True)
+        print(json.dumps({"world": world, "split_pull": split, "ms": best[0], **best[1]}), flush=True)
 if world > 1:
     dist.destroy_process_group()

@@ -299,7 +299,9 @@ def test_ring_groups_cover_every_step_once():
     """launch groups of the ring: every step s = 1..world//2 exactly once and in order, the first group a single
     step (work starts after ONE shard), merged groups only of full blocks, the shared half block alone and last"""
     for world in range(1, 17):
-        groups = parallel.ring_groups(world)
+        for merge in (False, True):
+            assert [s for g in parallel.ring_groups(world, merge) for s in g] == list(range(1, world // 2 + 1))
+        groups = parallel.ring_groups(world, merge=True)
         flat = [s for g in groups for s in g]
         assert flat == list(range(1, world // 2 + 1)), world
         plan = {s: part for s, _, _, part in parallel.ring_schedule(world)[0]}
