@@ -156,6 +156,11 @@ void kam_kmer_set_warp_path(int on);
 /* test hook: 0 sends long sequences (and uint8-counter overflows) straight to the global-memory RED.ADD
  * path instead of the shared-memory uint16 tile kernel (default 1); identical vectors either way. */
 void kam_kmer_set_long_path(int on);
+/* test hook: 0 keeps long sequences at k <= 9 on the tiled shared-memory kernel (one CTA per (sequence, tile),
+ * one scan of the sequence per tile) instead of the one-pass kernel that holds the whole 4^k table of a sequence
+ * in the shared memory of one CTA (default 1; at k = 9 only for batches of at least half as many long sequences
+ * as the device has SMs -- 2 lifts that condition); identical vectors either way. */
+void kam_kmer_set_long_one_pass(int on);
 /* test hook: 0 makes the CTA-per-sequence kernel scan 8 k-mer end positions per thread and trip (the first
  * version) instead of one whole plane word of 32 (default 1); identical vectors either way. */
 void kam_kmer_set_word_scan(int on);

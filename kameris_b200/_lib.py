@@ -36,6 +36,7 @@ SIGNATURES = {
     "kam_kmer_sweep_set_fused_top": (None, [c_int]),
     "kam_kmer_set_warp_path": (None, [c_int]),
     "kam_kmer_set_long_path": (None, [c_int]),
+    "kam_kmer_set_long_one_pass": (None, [c_int]),
     "kam_kmer_set_word_scan": (None, [c_int]),
     "kam_cgr_pool": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_int, c_void_p, c_uint64, c_void_p,
                              c_uint64, c_void_p]),

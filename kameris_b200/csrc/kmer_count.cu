@@ -1127,6 +1127,321 @@ __global__ void __launch_bounds__(LG_THREADS, 1) cgr_long_kernel(const uint2 *__
     }
 }
 
+// ---- path L, one pass (k <= 9): the whole 4^k table in shared memory --------------------------------
+// cgr_long_kernel above is bound by what it spends AROUND an increment: at k = 9 only one k-mer in four
+// falls into the tile a CTA holds, so every plane word is fetched, masked and bit-looped four times, the
+// bit loop diverges, and ncu shows the ALU pipe at 79 % for 1.9 increments per clock and SM against the
+// 12 the shared-memory atomics can do.  Here the table of ONE sequence is complete in the shared memory of
+// ONE CTA, so every k-mer is an increment: no tile mask, no bit loop, no divergence -- each thread takes a
+// plane word and issues its 32 increments straight-line.
+//   k <= 8: 4^k uint16 counters packed two to a word (<= 128 KB), exactly the counters of the kernel above.
+//   k == 9: 262144 counters do not fit at 16 or 8 bits (227 KB per CTA) but do at SIX: five 6-bit fields
+//           per 32-bit word, word = bin / 5, 52429 words = 205 KB (l1_locate: one widening multiply gives the
+//           word and the field's bit offset).  A field overflows
+//           at 64 while the mean count of a 5 Mb genome is 19, so a field is kept below 32 + slack by its
+//           own incrementers: ATOMS returns the old word (same rate as without, scratch/atoms_bench.cu);
+//           the thread that sees its field at exactly 32 takes 32 back out (one more ATOMS) and adds 1 to
+//           the sequence's uint32 side table in global memory (RED.ADD, once per 32 increments of a hot
+//           bin).  count = field + 32 * side.  All word arithmetic is addition mod 2^32, so the final word
+//           is right whatever the interleaving, PROVIDED no field ever carried into its neighbour; a
+//           field can only reach 64 through an increment that observes 63 (by induction from field 0 up:
+//           carries only come from a lower field that itself overflowed), and that thread raises the
+//           abort flag -- the sequence is then redone by the tiled kernel above (uint16, no such limit).
+//           It takes > 30 increments of ONE bin in flight between an ATOMS and its follow-up, i.e. a
+//           homopolymer / tandem-repeat run of several hundred bases.  The sum of everything read out
+//           must equal the number of k-mers as well (belt and braces, as above).
+// Work item = sequence; one CTA per SM, persistent over the list.
+constexpr uint32_t L1_MAX_CTAS = 160;   // side tables in the workspace: one per CTA
+constexpr int L1_SIX_K = 9;             // the order whose table needs 6-bit fields; below it uint16 counters fit
+int g_long_one_pass = 1;                // test hook: 0 = tiled kernel only, 2 = one pass however few the sequences
+
+// shared-memory atomics by 32-bit shared address (the table base stays in one register instead of being
+// re-derived from the generic pointer around every call)
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Field of a bin inside its word.  One 32 x 32 -> 64 multiply by ceil(2^32 / 5) gives both: the high word is
+// bin / 5, the low word is (bin % 5) / 5 as a binary fraction (+ < 2^18), whose top five bits are
+// 0, 6, 12, 19, 25 -- five bit offsets at least six apart, so the fields sit THERE (bits 18 and 31 unused) and
+// no second multiply is needed for "6 * (bin % 5)".
+constexpr uint32_t L1_DIV5 = 0x33333334u;
+__device__ __forceinline__ void l1_locate(uint32_t bin, uint32_t &word, uint32_t &sh) {
+    uint32_t lo;   // spelled in PTX: left to itself the compiler shifts the 64-bit product about instead
+    asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo), "=r"(word) : "r"(bin), "n"(L1_DIV5));
+    sh = lo >> 27;
+}
+
+// G increments at once: the address arithmetic of the G bins interleaves, the G results are tested together.
+// flags: bit 0 = the side table was used, bit 1 = a field carried into its neighbour (abort)
+// s_blk: one bit per 64 bins, set where the side table holds something (the read-out looks only there)
+template <bool SIX, int G>
+__device__ __forceinline__ void l1_count(const uint32_t (&bin)[G], uint32_t tab_addr, uint32_t *side, uint32_t *s_blk,
+                                         uint32_t &flags) {
+    if constexpr (SIX) {
+        uint32_t a[G], sh[G], old[G], hot = 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            uint32_t q;
+            l1_locate(bin[j], q, sh[j]);
+            asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a[j]) : "r"(q), "r"(tab_addr));
+            old[j] = atoms_add(a[j], 1u << sh[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) hot |= (old[j] >> sh[j]) & 32u;
+        if (hot) {   // some field already held >= 32 (rare on a bin of average count, routine on a hot bin)
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const uint32_t t = (old[j] >> sh[j]) & 63u;
+                if (t >= 32u) {
+                    if (t == 32u) {   // this thread brings the field back under 32 and credits the side table
+                        reds_add(a[j], 0u - (32u << sh[j]));
+                        atomicAdd(&side[bin[j]], 1u);
+                        atomicOr(&s_blk[bin[j] >> 11], 1u << ((bin[j] >> 6) & 31u));
+                        flags |= 1u;
+                    } else if (t == 63u) {
+                        flags |= 2u;   // this increment carried into the neighbouring field
+                    }
+                }
+            }
+        }
+    } else {
+        (void)side, (void)flags, (void)s_blk;
+#pragma unroll
+        for (int j = 0; j < G; ++j) reds_add(tab_addr + ((bin[j] << 1) & ~3u), 1u << ((bin[j] & 1u) << 4));
+    }
+}
+
+template <typename OUT, bool SIX>
+__global__ void __launch_bounds__(LG_THREADS, 1) cgr_long1_kernel(const uint2 *__restrict__ planes,
+                                                                  const uint64_t *__restrict__ base_start,
+                                                                  const uint32_t *__restrict__ head_mask,
+                                                                  const uint32_t *__restrict__ list,
+                                                                  const uint32_t *__restrict__ n_list_ptr, int k,
+                                                                  OUT *__restrict__ out, uint64_t out_stride,
+                                                                  uint32_t *__restrict__ queue2,
+                                                                  uint32_t *__restrict__ side_tables,
+                                                                  uint32_t *__restrict__ spill2_count,
+                                                                  uint32_t *__restrict__ spill2_list,
+                                                                  unsigned long long *__restrict__ spill2_maxlen) {
+    constexpr bool IS_FREQ = !std::is_integral<OUT>::value;
+    constexpr int BPS = 16 / (int)sizeof(OUT);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw);
+    __shared__ uint32_t s_item;
+    __shared__ uint32_t s_flags[2];   // [0] the side table was used, [1] abort
+    __shared__ uint32_t s_blk[SIX ? (1u << (2 * L1_SIX_K - 11)) : 1];
+    __shared__ unsigned long long s_diff;
+    __shared__ OUT s_lut[256];
+    (void)s_lut;
+    const uint32_t n_list = *n_list_ptr;
+    if (n_list == 0) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t bins = 1u << (2 * k);
+    const uint32_t n_words = SIX ? (bins + 4u) / 5u : bins >> 1;
+    uint32_t *side = SIX ? side_tables + (size_t)blockIdx.x * bins : nullptr;
+    const uint32_t mask = (1u << k) - 1u;
+    const uint32_t shc = 32u - (uint32_t)(k - 1);
+    const uint32_t ymul = 1u << (2 * k);   // mulhi by 2^(2k) = shift right by 32-2k, on the FMA pipe
+    uint32_t tab_addr;   // opaque to the compiler, or it re-derives the shared window base around every group
+    asm volatile("mov.u32 %0, %1;" : "=r"(tab_addr) : "r"((uint32_t)__cvta_generic_to_shared(tab)));
+
+    for (uint32_t i = threadIdx.x; i < n_words; i += LG_THREADS) tab[i] = 0;
+    if constexpr (SIX) {
+        for (uint32_t i = threadIdx.x; i < (bins >> 11); i += LG_THREADS) s_blk[i] = 0;
+        uint4 *s4 = reinterpret_cast<uint4 *>(side);
+        for (uint32_t i = threadIdx.x; i < bins / 4; i += LG_THREADS) s4[i] = make_uint4(0, 0, 0, 0);
+    }
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_item = atomicAdd(queue2, 1u);
+            s_diff = 0;
+            s_flags[0] = 0;
+            s_flags[1] = 0;
+        }
+        __syncthreads();
+        const uint32_t li = s_item;
+        if (li >= n_list) break;
+        const uint32_t s = list[li];
+        const SeqInfo q = seq_info(base_start, head_mask, s, k);
+        const double sum = (double)(q.n > q.lead ? q.n - q.lead : 0);
+        if constexpr (IS_FREQ) {
+            if (threadIdx.x < 256) s_lut[threadIdx.x] = convert_count<OUT>(threadIdx.x, 0.0, sum);
+        }
+        unsigned long long issued = 0;
+        uint32_t flags = 0;
+        if (q.n >= (uint64_t)k) {
+            const uint64_t pa = q.p0 + (uint64_t)(k - 1), pe = q.p0 + q.n;   // k-mer end positions [pa, pe)
+            if (threadIdx.x == 0) issued = pe - pa;
+            const uint64_t Wf0 = (pa + 31) >> 5, Wf1 = pe >> 5;              // plane words lying wholly inside
+            // x window of end position b: bits b+shc.. of (hi.x:lo.x); y window pushed to the top of a register by
+            // a funnel shift left of 31-b, brought down to bits k..2k-1 (zeros above), merged under the x window
+            auto bin_of = [&](unsigned long long vxs, uint32_t ylo, uint32_t yhi, uint32_t b) {
+                const uint32_t xw = (uint32_t)(vxs >> b);
+                const uint32_t yw = __umulhi(__funnelshift_l(ylo, yhi, 31u - b), ymul);
+                return (xw & mask) | (yw & ~mask);
+            };
+            constexpr int G = SIX ? 8 : 8;
+            const uint64_t Wfirst = Wf0 + (threadIdx.x & ~31u);
+            uint2 nxt = make_uint2(0, 0), nxt0 = make_uint2(0, 0);   // the next trip's words are fetched a trip ahead
+            if (Wfirst + lane < Wf1) nxt = __ldg(planes + Wfirst + lane);
+            if (lane == 0 && Wfirst < Wf1 && Wfirst) nxt0 = __ldg(planes + Wfirst - 1);
+            for (uint64_t Wb = Wfirst; Wb < Wf1; Wb += LG_THREADS) {   // warp-uniform trips
+                const uint64_t W = Wb + lane;
+                const uint2 hi = nxt;
+                uint2 lo;
+                lo.x = __shfl_up_sync(0xffffffffu, hi.x, 1);
+                lo.y = __shfl_up_sync(0xffffffffu, hi.y, 1);
+                if (lane == 0) lo = nxt0;
+                const uint64_t Wn = W + LG_THREADS;
+                nxt = make_uint2(0, 0);
+                if (Wn < Wf1) nxt = __ldg(planes + Wn);
+                if (lane == 0 && Wn < Wf1) nxt0 = __ldg(planes + Wn - 1);
+                if (W < Wf1) {
+                    const unsigned long long vxs = (((unsigned long long)hi.x << 32) | lo.x) >> shc;
+#pragma unroll
+                    for (uint32_t b = 0; b < 32; b += G) {
+                        uint32_t bin[G];
+#pragma unroll
+                        for (int j = 0; j < G; ++j) bin[j] = bin_of(vxs, lo.y, hi.y, b + j);
+                        l1_count<SIX, G>(bin, tab_addr, side, s_blk, flags);
+                    }
+                }
+                __syncwarp();
+            }
+            // the (at most two) ragged words at the ends: warp 0, lane = end position
+            if (threadIdx.x < 32) {
+                auto edge = [&](uint64_t W, uint32_t m) {
+                    const uint2 hi = __ldg(planes + W);
+                    const uint2 lo = W ? __ldg(planes + W - 1) : make_uint2(0, 0);
+                    if ((m >> lane) & 1u) {
+                        const unsigned long long vxs = (((unsigned long long)hi.x << 32) | lo.x) >> shc;
+                        const uint32_t bin[1] = {bin_of(vxs, lo.y, hi.y, lane)};
+                        l1_count<SIX, 1>(bin, tab_addr, side, s_blk, flags);
+                    }
+                };
+                const uint32_t a5 = (uint32_t)(pa & 31), e5 = (uint32_t)(pe & 31);
+                if (Wf0 > Wf1) {
+                    edge(pa >> 5, (0xffffffffu << a5) & ~(0xffffffffu << e5));   // a5 < e5, both inside one word
+                } else {
+                    if (a5) edge(Wf0 - 1, 0xffffffffu << a5);
+                    if (e5) edge(Wf1, ~(0xffffffffu << e5));
+                }
+            }
+        }
+        if (threadIdx.x == 0 && q.lead < (uint32_t)(k - 1)) {   // dirty head (rare)
+            head_partials(planes, q, k, [&](uint32_t bin) {
+                const uint32_t b1[1] = {bin};
+                l1_count<SIX, 1>(b1, tab_addr, side, s_blk, flags);
+                issued += 1;
+            });
+        }
+        if (flags & 1u) s_flags[0] = 1;
+        if (flags & 2u) s_flags[1] = 1;
+        __syncthreads();
+        const bool use_side = SIX && s_flags[0] != 0;
+        const bool aborted = SIX && s_flags[1] != 0;
+
+        // ---- read-out: convert, stream out, add up what the counters hold
+        OUT *row = out + (uint64_t)s * out_stride;
+        unsigned long long held = 0;
+        const bool vec_ok = (bins % BPS == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+        auto counter = [&](uint32_t bin) -> uint32_t {
+            if constexpr (SIX) {
+                uint32_t qq, sh;
+                l1_locate(bin, qq, sh);
+                return (tab[qq] >> sh) & 63u;
+            } else {
+                return (tab[bin >> 1] >> ((bin & 1u) << 4)) & 0xffffu;
+            }
+        };
+        if (!aborted) {
+            if (vec_ok) {
+                const uint32_t n_stores = bins / BPS;
+                for (uint32_t c = threadIdx.x; c < n_stores; c += LG_THREADS) {
+                    union {
+                        uint4 v;
+                        OUT e[BPS];
+                    } u;
+                    uint32_t cn[BPS];
+#pragma unroll
+                    for (int i = 0; i < BPS; ++i) cn[i] = counter(c * BPS + i);
+                    if constexpr (SIX) {
+                        const uint32_t b0 = c * BPS;
+                        if (use_side && ((s_blk[b0 >> 11] >> ((b0 >> 6) & 31u)) & 1u)) {   // BPS divides 64
+                            uint32_t h[BPS];
+                            if constexpr (BPS == 8) {
+                                const uint4 h0 = *reinterpret_cast<const uint4 *>(side + b0);
+                                const uint4 h1 = *reinterpret_cast<const uint4 *>(side + b0 + 4);
+                                h[0] = h0.x, h[1] = h0.y, h[2] = h0.z, h[3] = h0.w, h[4] = h1.x, h[5] = h1.y, h[6] = h1.z, h[7] = h1.w;
+                            } else if constexpr (BPS == 4) {
+                                const uint4 h0 = *reinterpret_cast<const uint4 *>(side + b0);
+                                h[0] = h0.x, h[1] = h0.y, h[2] = h0.z, h[3] = h0.w;
+                            } else {
+                                const uint2 h0 = *reinterpret_cast<const uint2 *>(side + b0);
+                                h[0] = h0.x, h[1] = h0.y;
+                            }
+                            uint32_t any = 0;
+#pragma unroll
+                            for (int i = 0; i < BPS; ++i) cn[i] += h[i] << 5, any |= h[i];
+                            if (any) {
+#pragma unroll
+                                for (int i = 0; i < BPS; ++i) side[b0 + i] = 0;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < BPS; ++i) held += cn[i];
+#pragma unroll
+                    for (int i = 0; i < BPS; ++i) {
+                        if constexpr (IS_FREQ) u.e[i] = cn[i] < 256u ? s_lut[cn[i]] : convert_count<OUT>(cn[i], 0.0, sum);
+                        else u.e[i] = (OUT)cn[i];
+                    }
+                    st_stream16(row + (uint64_t)c * BPS, u.v);
+                }
+            } else {   // misaligned rows (odd strides)
+                for (uint32_t i = threadIdx.x; i < bins; i += LG_THREADS) {
+                    uint32_t c = counter(i);
+                    if constexpr (SIX) {
+                        if (use_side) {
+                            c += side[i] << 5;
+                            side[i] = 0;
+                        }
+                    }
+                    held += c;
+                    row[i] = IS_FREQ ? (c < 256u ? s_lut[c] : convert_count<OUT>(c, 0.0, sum)) : convert_count<OUT>(c, 0.0, sum);
+                }
+            }
+        } else if constexpr (SIX) {
+            if (use_side) {
+                uint4 *s4 = reinterpret_cast<uint4 *>(side);
+                for (uint32_t i = threadIdx.x; i < bins / 4; i += LG_THREADS) s4[i] = make_uint4(0, 0, 0, 0);
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_words; i += LG_THREADS) tab[i] = 0;
+        if constexpr (SIX) {
+            if (use_side)
+                for (uint32_t i = threadIdx.x; i < (bins >> 11); i += LG_THREADS) s_blk[i] = 0;
+        }
+        // a wrapped / carried counter: redo the sequence elsewhere
+        const unsigned long long d = warp_sum64(issued - held);
+        if (lane == 0 && d) atomicAdd(&s_diff, d);
+        __syncthreads();
+        if (threadIdx.x == 0 && (aborted || s_diff != 0)) {
+            spill2_list[atomicAdd(spill2_count, 1u)] = s;
+            atomicMax(spill2_maxlen, (unsigned long long)q.n);
+        }
+    }
+}
+
 // ---- path B ------------------------------------------------------------------------------------
 // grid (chunks, batch): CTA (c, b) counts bases [c*B_CHUNK, (c+1)*B_CHUNK) of sequence
 // spill_list[first + b] into tables[b] (4^k uint32, zeroed beforehand) with RED.ADD.
@@ -1206,8 +1521,12 @@ struct KmerWs {
     unsigned long long *spill2_maxlen;// [1]
     uint32_t *spill2_list;           // [n_seqs]
     uint32_t *ovf_flag;              // [n_seqs]
+    uint32_t *queue3;                // [1]   the tiled path L kernel when it runs behind the one-pass kernel
+    uint32_t *spill3_count;          // [1]
+    unsigned long long *spill3_maxlen;// [1]
+    uint32_t *spill3_list;           // [n_seqs]
     unsigned long long *sums;        // [batch]
-    uint32_t *tables;                // [batch][4^k]
+    uint32_t *tables;                // [batch][4^k]; the one-pass path L kernel's side tables alias it
     uint32_t batch;
 };
 
@@ -1233,8 +1552,14 @@ inline size_t ws_layout(uint32_t n_seqs, int k, void *base, KmerWs *w) {
     void *list = take((size_t)(n_seqs ? n_seqs : 1) * 4);
     void *list2 = take((size_t)(n_seqs ? n_seqs : 1) * 4);
     void *flags = take((size_t)(n_seqs ? n_seqs : 1) * 4);
+    void *list3 = take((size_t)(n_seqs ? n_seqs : 1) * 4);
     void *sums = take((size_t)1024 * 8);   // spill_batch() never exceeds 1024 (any k: the sweep reuses this layout)
-    void *tables = take((size_t)batch * (((size_t)1 << (2 * k)) * 4));
+    size_t n_tables = batch;
+    if (k == L1_SIX_K) {   // one uint32 side table per CTA of cgr_long1_kernel<.., true>
+        const size_t ctas = n_seqs < L1_MAX_CTAS ? (n_seqs ? n_seqs : 1) : L1_MAX_CTAS;
+        if (ctas > n_tables) n_tables = ctas;
+    }
+    void *tables = take(n_tables * (((size_t)1 << (2 * k)) * 4));
     if (w) {
         w->queue = (uint32_t *)hdr;
         w->spill_count = (uint32_t *)hdr + 1;
@@ -1245,6 +1570,10 @@ inline size_t ws_layout(uint32_t n_seqs, int k, void *base, KmerWs *w) {
         w->spill2_maxlen = (unsigned long long *)((char *)hdr + 24);
         w->spill2_list = (uint32_t *)list2;
         w->ovf_flag = (uint32_t *)flags;
+        w->queue3 = (uint32_t *)hdr + 8;
+        w->spill3_count = (uint32_t *)hdr + 9;
+        w->spill3_maxlen = (unsigned long long *)((char *)hdr + 40);
+        w->spill3_list = (uint32_t *)list3;
         w->sums = (unsigned long long *)sums;
         w->tables = (uint32_t *)tables;
         w->batch = batch;
@@ -1331,30 +1660,98 @@ int run_spill(const uint2 *planes, const uint64_t *base_start, const uint32_t *h
     return KAM_OK;
 }
 
-// the sequences path A declined (too long for its tiles, or a uint8 counter overflowed): path L where
-// its tiles apply, and path B for whatever overflows even uint16 counters (one more 16-byte read-back)
+// the tiled path L kernel over `list` (h.count entries); sequences whose uint16 counters wrap go to `out_*`
+template <typename OUT>
+int launch_long_tiled(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, int k, OUT *out,
+                      uint64_t out_stride, const KmerWs &w, const uint32_t *list, uint32_t count, uint32_t *queue,
+                      uint32_t *out_count, uint32_t *out_list, unsigned long long *out_maxlen, cudaStream_t st) {
+    KAM_CUDA(cudaMemsetAsync(w.ovf_flag, 0, (size_t)count * 4, st));
+    const uint32_t tile_log2 = 2 * k < LG_TILE_LOG2 ? 2 * k : LG_TILE_LOG2;
+    const size_t smem = ((size_t)1 << tile_log2) * 2;
+    const uint64_t items = (uint64_t)count << (2 * k - tile_log2);
+    uint64_t grid = (uint64_t)kam_sm_count();   // 128 KB of counters: one CTA per SM, persistent over the item queue
+    if (grid > items) grid = items;
+    auto kern = cgr_long_kernel<OUT>;
+    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, LG_THREADS, smem, st>>>(planes, base_start, head_mask, list, count, k, out, out_stride, queue,
+                                                   w.ovf_flag, out_count, out_list, out_maxlen);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+// the one-pass path L kernel over the spill list of path A; the number of entries is read on the device
+// (count_hint only sizes the grid), so the launch does not have to wait for path A's read-back
+template <typename OUT>
+int launch_long_one_pass(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, int k, OUT *out,
+                         uint64_t out_stride, const KmerWs &w, uint32_t count_hint, cudaStream_t st) {
+    const bool six = k == L1_SIX_K;
+    const uint32_t bins = 1u << (2 * k);
+    size_t smem = six ? (size_t)((bins + 4) / 5) * 4 : (size_t)bins * 2;
+    smem = kam_align_up(smem, 16);
+    uint64_t grid = (uint64_t)kam_sm_count();
+    if (grid > L1_MAX_CTAS) grid = L1_MAX_CTAS;
+    if (grid > count_hint) grid = count_hint;
+    auto kern = six ? cgr_long1_kernel<OUT, true> : cgr_long1_kernel<OUT, false>;
+    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, LG_THREADS, smem, st>>>(planes, base_start, head_mask, w.spill_list, w.spill_count, k, out,
+                                                   out_stride, w.queue2, w.tables, w.spill2_count, w.spill2_list,
+                                                   w.spill2_maxlen);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+inline int read_hdr(const uint32_t *p, SpillInfo *h, cudaStream_t st) {
+    KAM_CUDA(cudaMemcpyAsync(h, p, 16, cudaMemcpyDeviceToHost, st));
+    KAM_CUDA(cudaStreamSynchronize(st));
+    return KAM_OK;
+}
+
+// whether a batch of `count` long sequences at order k is better off with the one-pass kernel: at k = 9 it
+// occupies one SM per sequence where the tiled kernel has four work items per sequence
+inline bool one_pass_pays(int k, uint64_t count) {
+    if (k < 7 || k > L1_SIX_K || !g_long_path || !g_long_one_pass) return false;
+    return k < L1_SIX_K || g_long_one_pass == 2 || count * 2 >= (uint64_t)kam_sm_count();
+}
+
+// stages behind the one-pass kernel: h2 = what it gave up on
+template <typename OUT>
+int run_after_one_pass(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, int k, int count_bits,
+                       OUT *out, uint64_t out_stride, const KmerWs &w, const SpillInfo &h2, cudaStream_t st) {
+    if (h2.count == 0) return KAM_OK;
+    if (k < L1_SIX_K)   // uint16 counters wrapped: the tiled kernel has the same counters
+        return run_spill<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, w.spill2_list, h2, st);
+    int rc;
+    if ((rc = launch_long_tiled<OUT>(planes, base_start, head_mask, k, out, out_stride, w, w.spill2_list, h2.count,
+                                     w.queue3, w.spill3_count, w.spill3_list, w.spill3_maxlen, st)))
+        return rc;
+    SpillInfo h3;
+    if ((rc = read_hdr(w.queue3, &h3, st))) return rc;
+    return run_spill<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, w.spill3_list, h3, st);
+}
+
+// the sequences path A declined (too long for its tiles, or a uint8 counter overflowed): path L where it
+// applies -- in one pass with the whole table in shared memory for k <= 9, what that kernel gives up on
+// (k = 9: a run of one k-mer that outpaces the 6-bit fields) and k = 10, 11 in tiles -- and path B for
+// whatever overflows even uint16 counters (one 16-byte read-back per stage that found something)
 template <typename OUT>
 int run_overflow(const uint2 *planes, const uint64_t *base_start, const uint32_t *head_mask, int k, int count_bits,
                  OUT *out, uint64_t out_stride, const KmerWs &w, const SpillInfo &h, cudaStream_t st) {
     if (h.count == 0) return KAM_OK;
     if (k < 7 || k > LG_MAX_K || !g_long_path)
         return run_spill<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, w.spill_list, h, st);
-    KAM_CUDA(cudaMemsetAsync(w.queue2, 0, 16, st));
-    KAM_CUDA(cudaMemsetAsync(w.ovf_flag, 0, (size_t)h.count * 4, st));
-    const uint32_t tile_log2 = 2 * k < LG_TILE_LOG2 ? 2 * k : LG_TILE_LOG2;
-    const size_t smem = ((size_t)1 << tile_log2) * 2;
-    const uint64_t items = (uint64_t)h.count << (2 * k - tile_log2);
-    uint64_t grid = (uint64_t)kam_sm_count();   // 128 KB of counters: one CTA per SM, persistent over the item queue
-    if (grid > items) grid = items;
-    auto kern = cgr_long_kernel<OUT>;
-    KAM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, LG_THREADS, smem, st>>>(planes, base_start, head_mask, w.spill_list, h.count, k, out,
-                                                   out_stride, w.queue2, w.ovf_flag, w.spill2_count, w.spill2_list,
-                                                   w.spill2_maxlen);
-    KAM_CUDA(cudaGetLastError());
+    int rc;
+    KAM_CUDA(cudaMemsetAsync(w.queue2, 0, 48, st));   // the queues / counts / maxima of stages two and three
+    if (one_pass_pays(k, h.count)) {
+        if ((rc = launch_long_one_pass<OUT>(planes, base_start, head_mask, k, out, out_stride, w, h.count, st))) return rc;
+        SpillInfo h2;
+        if ((rc = read_hdr(w.queue2, &h2, st))) return rc;
+        return run_after_one_pass<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, h2, st);
+    }
+    if ((rc = launch_long_tiled<OUT>(planes, base_start, head_mask, k, out, out_stride, w, w.spill_list, h.count,
+                                     w.queue2, w.spill2_count, w.spill2_list, w.spill2_maxlen, st)))
+        return rc;
     SpillInfo h2;
-    KAM_CUDA(cudaMemcpyAsync(&h2, w.queue2, 16, cudaMemcpyDeviceToHost, st));
-    KAM_CUDA(cudaStreamSynchronize(st));
+    if ((rc = read_hdr(w.queue2, &h2, st))) return rc;
     return run_spill<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, w.spill2_list, h2, st);
 }
 
@@ -1386,6 +1783,15 @@ int run_kmer(const uint2 *planes, const uint64_t *base_start, const uint32_t *he
     if (rc) return rc;
     if (k <= 6 && !(short_reads && g_warp_path)) return KAM_OK;   // uint32 counters, single tile: nothing can spill
 
+    // A batch of megabase sequences: path A has just put (nearly) all of them on its list, so the one-pass
+    // path L kernel is launched right behind it -- it reads the length of the list on the device -- and the
+    // host reads both kernels' verdicts back in one go instead of waiting in between.
+    if (total_bases / n_seqs > A_MAX_LEN && one_pass_pays(k, n_seqs)) {
+        if ((rc = launch_long_one_pass<OUT>(planes, base_start, head_mask, k, out, out_stride, w, n_seqs, st))) return rc;
+        SpillInfo h2;
+        if ((rc = read_hdr(w.queue2, &h2, st))) return rc;
+        return run_after_one_pass<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, h2, st);
+    }
     SpillInfo h;
     if ((rc = read_spill(w, &h, st))) return rc;
     return run_overflow<OUT>(planes, base_start, head_mask, k, count_bits, out, out_stride, w, h, st);
@@ -1543,5 +1949,6 @@ void kam_kmer_sweep_set_fused_top(int k) { g_sweep_top = k; }
 void kam_kmer_set_warp_path(int on) { g_warp_path = on; }
 void kam_kmer_set_word_scan(int on) { g_word_scan = on; }
 void kam_kmer_set_long_path(int on) { g_long_path = on; }
+void kam_kmer_set_long_one_pass(int on) { g_long_one_pass = on; }
 
 }  // extern "C"

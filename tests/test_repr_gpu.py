@@ -237,24 +237,66 @@ def test_tile_kernel_scan_variants(R, k, out, bits):
                 assert np.array_equal(got[i], O.frequencies(c), equal_nan=True), (k, i)
 
 
-@pytest.mark.parametrize("long_path", [1, 0])
+@pytest.mark.parametrize("long_path", [2, 1, 0])
 @pytest.mark.parametrize("k,bits", [(9, 16), (9, 32), (8, 16), (7, 16), (2, 16), (10, 16), (11, 32), (12, 16)])
 def test_long_sequences_spill_path(R, k, bits, long_path):
-    """Sequences beyond path A (length, or uint8 overflow) take the shared-memory uint16 tile kernel
-    (path L, 7 <= k <= 11) and, when even a uint16 counter overflows (70 000 x 'A'), the RED.ADD path B;
-    long_path=0 sends all of them to path B directly.  Dirty heads included."""
+    """Sequences beyond path A (length, or uint8 overflow) take path L -- for k <= 9 the one-pass kernel with
+    the whole table in shared memory (long_path=2: uint16 counters below k = 9, 6-bit fields + side table at
+    k = 9), else / behind it the tiled uint16 kernel (long_path=1 forces it) -- and, when even a uint16 counter
+    overflows (70 000 x 'A'), the RED.ADD path B; long_path=0 sends all of them to path B directly.  The
+    homopolymer and the dinucleotide repeat make the 6-bit kernel give up (every increment of a warp lands in
+    one field), so the whole chain of fall-backs runs.  Dirty heads included."""
     recs = synth_records(3, 400000, seed=11 + k, dirty=0.001) + [b"ACGT" * 3000, b"A" * 70000,
                                                                  synth_records(1, 9000, seed=2)[0],
                                                                  b"NNA" + synth_records(1, 200000, seed=3)[0],
                                                                  b"AC" * 140000]
     from kameris_b200 import _lib
-    _lib.load().kam_kmer_set_long_path(long_path)
+    _lib.load().kam_kmer_set_long_path(1 if long_path else 0)
+    _lib.load().kam_kmer_set_long_one_pass(2 if long_path == 2 else 0)   # 2: however few the sequences
     try:
         got = _gpu_counts(R, recs, k, bits)
     finally:
         _lib.load().kam_kmer_set_long_path(1)
+        _lib.load().kam_kmer_set_long_one_pass(1)
     for i, r in enumerate(recs):
         assert np.array_equal(got[i], O.cgr_count(r, k, bits)), (i, k, bits)
+
+
+@pytest.mark.parametrize("out,bits", [("counts", 16), ("counts", 32), ("freq64", 16)])
+@pytest.mark.parametrize("k", [9, 8])
+def test_long_one_pass_hot_bins_and_many_sequences(R, out, bits, k):
+    """The one-pass path L kernel where its 6-bit fields matter (k = 9): composition-skewed sequences whose
+    hottest bins hold hundreds (every 32 increments of a bin move into the side table), more sequences than
+    CTAs (persistent loop, side table and block bitmap re-used clean), ragged ends that are not multiples of
+    32, a tandem repeat inside an ordinary sequence (a burst on a few bins), sequences of one plane word and
+    less than k bases in between, and short sequences path A keeps for itself.  Bit-exact against the oracle,
+    and the tiled kernel must give the same bytes."""
+    rng = np.random.Generator(np.random.PCG64(5 + k))
+    recs = []
+    for i in range(170):
+        L = int(rng.integers(131100, 140000)) if i % 9 else int(rng.integers(300000, 420000))
+        p = [[0.4, 0.1, 0.1, 0.4], [0.15, 0.35, 0.35, 0.15], None][i % 3]
+        recs.append(synth_records(1, L, seed=1000 + i, dirty=0.0005 if i % 4 == 0 else 0.0, p=p)[0])
+    r = bytearray(recs[5])
+    r[70000:70900] = b"ACG" * 300
+    recs[5] = bytes(r)
+    recs[7] = recs[7][:60000] + b"T" * 45 + recs[7][60000:]
+    recs += [b"ACGTTGCA", b"", b"ACGTACGTACGTAC", synth_records(1, 5000, seed=9)[0]]
+    from kameris_b200 import _lib
+    got = _gpu_counts(R, recs, k, bits, out)
+    _lib.load().kam_kmer_set_long_one_pass(0)
+    try:
+        tiled = _gpu_counts(R, recs, k, bits, out)
+    finally:
+        _lib.load().kam_kmer_set_long_one_pass(1)
+    assert np.array_equal(got, tiled, equal_nan=True)
+    for i in list(range(0, len(recs), 7)) + [5, 7] + list(range(len(recs) - 4, len(recs))):
+        c = O.cgr_count(recs[i], k, bits)
+        if out == "counts":
+            assert np.array_equal(got[i], c), (i, k, bits)
+        else:
+            with np.errstate(all="ignore"):
+                assert np.array_equal(got[i], O.frequencies(c), equal_nan=True), (i, k)
 
 
 @pytest.mark.parametrize("out", ["freq32", "freq64"])
