@@ -3,11 +3,13 @@ BASELINE.json, each on its own kernel.
 
   short_reads    : config 4 shape -- 1 000 000 reads x 150 bp, k=6, uint16 counts: warp-per-read kernel
                    (cgr_warp_kernel).  HBM-bound; algorithmic bytes/vector = ceil(L/4) + 4^6 * 2 = 8230.
-  long_sequences : config 5 shape -- 148 sequences x 5 Mb, k=9, float32 frequencies: shared-memory
-                   uint16 tile kernel (cgr_long_kernel), 4 passes over a sequence's planes.  Bound by the
-                   shared-memory atomic increment rate (one increment per k-mer; ~12 per clock per SM
-                   measured with scratch/atoms_bench.cu), not by HBM: reported as k-mers/s against that
-                   rate, with the HBM figure beside it.
+  long_sequences : config 5 shape -- 148 sequences x 5 Mb, k=9, float32 frequencies: the one-pass path L
+                   kernel (cgr_long1_kernel: the whole 4^9 table of a sequence as 6-bit fields in the shared
+                   memory of one CTA, one increment per k-mer, one scan of the planes).  Bound by the
+                   shared-memory atomic increment rate (~12 per clock per SM measured with
+                   scratch/atoms_bench.cu), not by HBM: reported as k-mers/s against that rate, with the HBM
+                   figure beside it; `tiled_ms` is the same call on the tiled uint16 kernel it replaced
+                   (cgr_long_kernel, four scans per sequence).
 """
 import torch
 
@@ -62,15 +64,21 @@ def run(dev, hbm_peak):
     o = torch.empty((n, 4 ** k), dtype=torch.float32, device=dev)
     ws = R.kmer_workspace(n, k, dev)
     t = _time(lambda: R.kmer_vectors(b, k, 16, "freq32", out_tensor=o, workspace=ws), 5)
+    from . import _lib
+    _lib.load().kam_kmer_set_long_one_pass(0)
+    try:
+        t_tiled = _time(lambda: R.kmer_vectors(b, k, 16, "freq32", out_tensor=o, workspace=ws), 3)
+    finally:
+        _lib.load().kam_kmer_set_long_one_pass(1)
     byt = n * ((L + 3) // 4 + 4 ** k * 4)
     atom_peak = sms * 12.0 * 1.965e9            # measured shared-memory increment rate (scratch/atoms_bench.cu)
     out["long_sequences"] = {"metric": "kmers_per_sec_k9", "value": n * L / t, "unit": "k-mers/s", "ms": t * 1e3,
-                             "sequences_per_s": n / t,
+                             "sequences_per_s": n / t, "tiled_ms": t_tiled * 1e3,
                              "config": {"workload": "%d sequences x 5 Mb, k=9, float32 frequencies (configs[4] shape)" % n,
-                                        "includes": "path A pass that routes every sequence to path L + read-back of "
-                                                    "the overflow list"},
+                                        "includes": "path A pass that routes every sequence to path L, the zeroing of "
+                                                    "the side tables, one read-back of the overflow lists"},
                              "roofline": {"bound": "shared-memory atomics", "achieved": n * L / t / 1e9,
                                           "peak": atom_peak / 1e9, "unit": "G increments/s",
-                                          "frac": n * L / t / atom_peak, "kernel": "cgr_long_kernel<float>",
+                                          "frac": n * L / t / atom_peak, "kernel": "cgr_long1_kernel<float, 6-bit fields>",
                                           "hbm_GBps": byt / t / 1e9, "hbm_frac": byt / t / 1e9 / hbm_peak}}
     return out
