@@ -479,7 +479,12 @@ def main():
     also, e2e_also, selfcheck = {}, {}, None
     if not args.no_ring:
         from kameris_b200 import ring_bench
+        ring_sampler = ClockSampler(dev.index)                     # a 100-200 ms tensor-core launch: was it power-capped?
+        if rank == 0:
+            ring_sampler.start()
         also["gram_ring"] = guarded(ring_bench.run_gram_ring, dist_pg, dev, rank, world, tf_peak)
+        if rank == 0 and isinstance(also["gram_ring"], dict):
+            also["gram_ring"]["clocks"] = ring_sampler.stop()
         torch.cuda.empty_cache()
         also["manhat_sharded"] = guarded(ring_bench.run_manhat_sharded, dist_pg, dev, rank, world)
         torch.cuda.empty_cache()

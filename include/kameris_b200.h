@@ -310,6 +310,25 @@ int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_
                    int operand_kind, uint64_t d, int triangular, uint32_t row_begin, uint32_t row_end,
                    unsigned metrics, int euclid_on_freq, float *d_out_euclid, float *d_out_cosine,
                    float *d_out_pearson, uint64_t out_ld, int sm_limit, void *d_ws, size_t ws_bytes, void *stream);
+/* The exchange step of the multi-GPU `distances` step fused into the Gram kernel (the step
+ * being sharded: kameris/job_steps/backend.py:59-66).  ONE persistent launch computes every block of a rank:
+ * rows of A against the rows of B, where B is the concatenation [rows of A itself | rows of other ranks' shards]
+ * and the latter are still being pulled over NVLink by the copy engines when the kernel starts (kam_peer_pull).
+ *   triangular_head != 0: B starts with the rows of A (d_op_b == d_op_a); pairs j <= i are skipped there.
+ *   h_segments: n_segments x (column tile begin, column tile end, row tile begin, row tile end), tiles of 256
+ *     rows; the tiles of a segment are scheduled after those of the segments before it, so list the segments in
+ *     the order their rows arrive.
+ *   d_ready: one word per chunk of `ready_tiles` column tiles, zero until the rows of those tiles are in place
+ *     (NULL: everything is there).  The TMA producer of a tile waits for its word (acquire, system scope) before it
+ *     loads the tile's B rows, so transfers overlap the tensor-core work tile by tile and the launch never idles
+ *     at a block boundary.  d_S_b / d_G_b (all n_b rows) must be complete at launch.
+ * Output: dense rows out[i * out_ld + j], j indexing the rows of B.  Workspace: kam_gram_block_workspace_bytes. */
+int kam_gram_fused(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_G_a, uint32_t n_a,
+                   const void *d_op_b, const uint64_t *d_S_b, const uint64_t *d_G_b, uint32_t n_b,
+                   int operand_kind, uint64_t d, int triangular_head, const uint32_t *h_segments,
+                   uint32_t n_segments, const uint32_t *d_ready, uint32_t ready_tiles, unsigned metrics,
+                   int euclid_on_freq, float *d_out_euclid, float *d_out_cosine, float *d_out_pearson,
+                   uint64_t out_ld, int sm_limit, void *d_ws, size_t ws_bytes, void *stream);
 /* tuning hook: row tiles (of 128 rows) per strip of the tile schedule (default 12); larger strips re-use the
  * column panels longer in L2 at the price of more row panels in flight. */
 void kam_gram_set_strip(int row_tiles);
@@ -330,6 +349,21 @@ int kam_peer_export(const void *d_ptr, unsigned char *handle);
 int kam_peer_open(const unsigned char *handle, void **d_mapped);
 int kam_peer_close(void *d_mapped);
 int kam_peer_copy(void *d_dst, const void *d_src, size_t bytes, void *stream);
+/* A batch of copy-engine transfers with arrival flags: the pieces are enqueued in order, all pieces of chunk c on
+ * streams[c % n_streams] (two streams = two copy engines), and behind the last piece of chunk c the stream writes
+ * d_flags[c] = 1 (cuStreamWriteValue32: no kernel) -- what a running kam_gram_fused launch waits for.  Pieces
+ * with chunk == KAM_PEER_NO_FLAG go to streams[0] and set nothing.  kam_peer_signal is the flag write alone. */
+#define KAM_PEER_NO_FLAG 0xffffffffu
+typedef struct {
+    void *d_dst;
+    const void *d_src;
+    uint64_t bytes;
+    uint32_t chunk;
+    uint32_t reserved;
+} kam_peer_piece;
+int kam_peer_pull(const kam_peer_piece *pieces, uint32_t n_pieces, uint32_t *d_flags, void *const *streams,
+                  uint32_t n_streams);
+int kam_peer_signal(uint32_t *d_flag, void *stream);
 
 /* Host-buffer form of the whole `distances` step: x is the n x d matrix read from a .mm-repr,
  * outputs are packed triangles (NULL = not requested).  euclid is taken between the rows as

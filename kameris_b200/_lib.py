@@ -17,6 +17,13 @@ KAM_M_MANHAT, KAM_M_INFO, KAM_M_EUCLID, KAM_M_COSINE, KAM_M_PEARSON = 1, 2, 4, 8
 KAM_GRAM_U8, KAM_GRAM_F16 = 0, 1
 KAM_SPARSE_DECLINED = 0xffffffff
 KAM_PEER_HANDLE_BYTES = 64
+KAM_PEER_NO_FLAG = 0xffffffff
+
+
+class PeerPiece(ctypes.Structure):
+    """kam_peer_piece (include/kameris_b200.h)"""
+    _fields_ = [("d_dst", ctypes.c_void_p), ("d_src", ctypes.c_void_p), ("bytes", ctypes.c_uint64),
+                ("chunk", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 # every symbol include/kameris_b200.h declares: (restype, argtypes)
 SIGNATURES = {
@@ -76,6 +83,9 @@ SIGNATURES = {
     "kam_gram_block": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_uint32, c_int,
                                c_uint64, c_int, c_uint32, c_uint32, ctypes.c_uint, c_int, c_void_p, c_void_p, c_void_p,
                                c_uint64, c_int, c_void_p, c_size_t, c_void_p]),
+    "kam_gram_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_uint32, c_int,
+                               c_uint64, c_int, c_void_p, c_uint32, c_void_p, c_uint32, ctypes.c_uint, c_int, c_void_p,
+                               c_void_p, c_void_p, c_uint64, c_int, c_void_p, c_size_t, c_void_p]),
     "kam_gram_set_strip": (None, [c_int]),
     "kam_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
     "kam_peer_free": (c_int, [c_void_p]),
@@ -83,6 +93,8 @@ SIGNATURES = {
     "kam_peer_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "kam_peer_close": (c_int, [c_void_p]),
     "kam_peer_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kam_peer_pull": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p, c_uint32]),
+    "kam_peer_signal": (c_int, [c_void_p, c_void_p]),
     "kam_gram_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, ctypes.c_uint,
                              c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "kam_mds_workspace_bytes": (c_size_t, [c_uint32]),

@@ -28,6 +28,10 @@ struct GramGeom {
     uint32_t tri;                 // 1: A and B are the same matrix, only pairs j > i exist
     unsigned long long ld;        // 0: packed strict upper triangle of n_a (tri only); else dense row stride
     const RowK *rk_a, *rk_b;      // per-row constants of A's and B's rows
+    // fused exchange (kam_gram_fused): B's rows arrive over NVLink while the kernel runs.  ready[t / ready_tiles]
+    // becomes non-zero once the rows of column tile t (256 rows of B) are in place; nullptr = all there.
+    const uint32_t *ready = nullptr;
+    uint32_t ready_tiles = 1;
 };
 
 #ifdef __CUDACC__

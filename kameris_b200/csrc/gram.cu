@@ -122,6 +122,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // each 32 x 32 chunk goes through a padded shared-memory tile per warp and leaves as 32 row-contiguous
 // 128-byte stores.
 constexpr int EP_PITCH = 33;
+// fused exchange: the TMA producer of a tile whose B rows are still on their way (copy engines pull them from a
+// peer's memory and write ready[chunk] behind each chunk, peer.cu: kam_peer_pull) waits here.  The flag is read
+// with acquire semantics at system scope; the rows were written by a copy engine and are read next by the TMA
+// unit (async proxy), hence the proxy fence.  A flag that never comes (a peer died) traps after ~10 s instead of
+// hanging the device.
+__device__ __forceinline__ void wait_rows_ready(const uint32_t *flag) {
+    uint32_t v, spin = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v) break;
+        __nanosleep(256);
+        if (++spin > (1u << 25)) __trap();
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 constexpr int EP_ROWS = 16;                                            // rows per staging round (half a warp's 32)
 constexpr uint32_t EP_TILE_BYTES = 8 * EP_ROWS * EP_PITCH * 4;         // eight epilogue warps
 
@@ -247,6 +263,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
             for (uint32_t t = blockIdx.x / CL; t < n_tiles; t += gridDim.x / CL) {
                 const uint2 tile = tiles[t];
                 const uint32_t bi = tile.x * CL + crank;
+                if (gg.ready) wait_rows_ready(gg.ready + tile.y / gg.ready_tiles);
                 for (uint32_t kb = 0; kb < k_iters; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
@@ -457,6 +474,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_pair_kernel(const __grid_co
                 const uint2 tile = tiles[t];
                 const int32_t arow = (int32_t)((tile.x * 2 + crank) * BM);
                 const int32_t brow = (int32_t)(tile.y * BN + crank * (BN / 2));
+                if (gg.ready) wait_rows_ready(gg.ready + tile.y / gg.ready_tiles);
                 for (uint32_t kb = 0; kb < k_iters; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     if (leader) mbar_arrive_expect_tx(&full[stage], 2 * P_STAGE_BYTES);
@@ -805,6 +823,7 @@ int launch_gram(const void *opA, const void *opB, const uint2 *d_tiles, size_t n
 struct TileList {
     int dev = -1;
     uint32_t tr0 = 0, tr1 = 0, tc = 0, tri = 0, cl = 0, strip = 0;
+    uint64_t sig = 0;           // 0: the list of one block; else the hash of a fused call's segments
     uint2 *d = nullptr, *h = nullptr;
     cudaEvent_t up = nullptr;   // the upload; launches on other streams wait for it
     size_t n = 0;
@@ -815,19 +834,32 @@ TileList g_tiles[TILE_CACHE];
 uint64_t g_tile_stamp = 0;
 std::mutex g_tile_mu;
 
-// a list entry is (row-tile group, column tile); a group is CL consecutive 128-row tiles handled by the CL
-// CTAs of a cluster.  Strips of ~12 row tiles, column-major inside a strip, so the ~148 tiles in flight share
-// about a dozen A panels and a dozen B panels in L2.
-int tile_list(const GramGeom &gg, uint32_t CL, cudaStream_t st, const uint2 **d_list, size_t *n_list) {
+// one strip-ordered rectangle of tiles: row groups [g0, g1) x column tiles [c0, c1).  A list entry is
+// (row-tile group, column tile); a group is CL consecutive 128-row tiles handled by the CL CTAs of a cluster.
+// Strips of ~12 row tiles, column-major inside a strip, so the ~148 tiles in flight share about a dozen A panels
+// and a dozen B panels in L2.
+void push_rect(std::vector<uint2> &tiles, uint32_t CL, uint32_t g0, uint32_t g1, uint32_t c0, uint32_t c1, bool tri) {
     const uint32_t GM = BM * CL;
-    const uint32_t tr0 = gg.row_begin / GM, tr1 = (gg.row_end - 1) / GM + 1, tc = (gg.n_b + BN - 1) / BN;
+    const uint32_t STRIP = g_strip / CL ? g_strip / CL : 1;
+    for (uint32_t s0 = g0; s0 < g1; s0 += STRIP) {
+        const uint32_t s1 = s0 + STRIP < g1 ? s0 + STRIP : g1;
+        for (uint32_t bj = c0; bj < c1; ++bj)
+            for (uint32_t bg = s0; bg < s1; ++bg)
+                if (!tri || (uint64_t)bj * BN + BN - 1 > (uint64_t)bg * GM) tiles.push_back(make_uint2(bg, bj));
+    }
+}
+
+// The list of a key, built by `build` on a miss and kept in device memory owned by the library next to the
+// pinned host copy it was uploaded from.
+template <class Build>
+int tile_list_cached(const TileList &key, cudaStream_t st, const uint2 **d_list, size_t *n_list, Build build) {
     int dev = 0;
     KAM_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_tile_mu);
     TileList *slot = &g_tiles[0];
     for (auto &t : g_tiles) {
-        if (t.d && t.dev == dev && t.tr0 == tr0 && t.tr1 == tr1 && t.tc == tc && t.tri == gg.tri && t.cl == CL &&
-            t.strip == g_strip) {
+        if (t.d && t.dev == dev && t.tr0 == key.tr0 && t.tr1 == key.tr1 && t.tc == key.tc && t.tri == key.tri &&
+            t.cl == key.cl && t.strip == g_strip && t.sig == key.sig) {
             KAM_CUDA(cudaStreamWaitEvent(st, t.up, 0));
             t.stamp = ++g_tile_stamp;
             *d_list = t.d;
@@ -837,13 +869,7 @@ int tile_list(const GramGeom &gg, uint32_t CL, cudaStream_t st, const uint2 **d_
         if (t.stamp < slot->stamp) slot = &t;
     }
     std::vector<uint2> tiles;
-    const uint32_t STRIP = g_strip / CL ? g_strip / CL : 1;
-    for (uint32_t s0 = tr0; s0 < tr1; s0 += STRIP) {
-        const uint32_t s1 = s0 + STRIP < tr1 ? s0 + STRIP : tr1;
-        for (uint32_t bj = 0; bj < tc; ++bj)
-            for (uint32_t bg = s0; bg < s1; ++bg)
-                if (!gg.tri || (uint64_t)bj * BN + BN - 1 > (uint64_t)bg * GM) tiles.push_back(make_uint2(bg, bj));
-    }
+    build(tiles);
     if (slot->d) {   // evict: earlier launches that read this list were enqueued on streams we do not know
         int cur = dev;
         if (slot->dev != dev) cudaSetDevice(slot->dev);
@@ -872,19 +898,56 @@ int tile_list(const GramGeom &gg, uint32_t CL, cudaStream_t st, const uint2 **d_
     KAM_CUDA(cudaEventCreateWithFlags(&slot->up, cudaEventDisableTiming));
     KAM_CUDA(cudaEventRecord(slot->up, st));
     slot->dev = dev;
-    slot->tr0 = tr0, slot->tr1 = tr1, slot->tc = tc, slot->tri = gg.tri, slot->cl = CL, slot->strip = g_strip;
+    slot->tr0 = key.tr0, slot->tr1 = key.tr1, slot->tc = key.tc, slot->tri = key.tri, slot->cl = key.cl;
+    slot->strip = g_strip, slot->sig = key.sig;
     slot->stamp = ++g_tile_stamp;
     *d_list = slot->d;
     *n_list = slot->n;
     return KAM_OK;
 }
 
+// Tile lists are cached per geometry: the list of a block depends only on (first row group, last row group,
+// column tiles, triangular?, cluster size), so a launch neither waits for the upload nor re-builds the list (the
+// first version built a std::vector per call and synchronised the stream before it went out of scope).
+int tile_list(const GramGeom &gg, uint32_t CL, cudaStream_t st, const uint2 **d_list, size_t *n_list) {
+    const uint32_t GM = BM * CL;
+    TileList key;
+    key.tr0 = gg.row_begin / GM, key.tr1 = (gg.row_end - 1) / GM + 1, key.tc = (gg.n_b + BN - 1) / BN;
+    key.tri = gg.tri, key.cl = CL;
+    return tile_list_cached(key, st, d_list, n_list, [&](std::vector<uint2> &tiles) {
+        push_rect(tiles, CL, key.tr0, key.tr1, 0, key.tc, gg.tri != 0);
+    });
+}
+
+// A fused call's list: the rectangles of its segments one after the other, in the order their B rows arrive.
+// A segment is (first column tile, end column tile, first row tile, end row tile) in units of 256 rows.
+int tile_list_segments(const GramGeom &gg, const uint32_t *segs, uint32_t n_segs, uint32_t CL, cudaStream_t st,
+                       const uint2 **d_list, size_t *n_list) {
+    TileList key;
+    key.tr0 = 0, key.tr1 = (gg.n_a + BM * CL - 1) / (BM * CL), key.tc = (gg.n_b + BN - 1) / BN;
+    key.tri = gg.tri, key.cl = CL;
+    uint64_t h = 1469598103934665603ull;
+    for (uint32_t i = 0; i < 4 * n_segs; ++i) h = (h ^ segs[i]) * 1099511628211ull;
+    key.sig = h | 1ull;
+    const uint32_t per = 256 / (BM * CL);   // row groups per 256-row tile (1 for clusters of 2, 2 without)
+    return tile_list_cached(key, st, d_list, n_list, [&](std::vector<uint2> &tiles) {
+        for (uint32_t i = 0; i < n_segs; ++i) {
+            const uint32_t *q = segs + 4 * i;
+            const uint32_t c1 = q[1] < key.tc ? q[1] : key.tc;
+            const uint32_t g1 = q[3] * per < key.tr1 ? q[3] * per : key.tr1;
+            push_rect(tiles, CL, q[2] * per, g1, q[0], c1, gg.tri != 0);
+        }
+    });
+}
+
 int gram_block(const void *opA, const void *opB, bool i8, uint64_t d, const GramGeom &gg, GramOut go, uint32_t sm_limit,
-               cudaStream_t st, uint64_t kext = 0, uint64_t pitch = 0) {
+               cudaStream_t st, uint64_t kext = 0, uint64_t pitch = 0, const uint32_t *segs = nullptr,
+               uint32_t n_segs = 0) {
     const uint32_t CL = g_cluster;
     const uint2 *d_tiles = nullptr;
     size_t n_tiles = 0;
-    int rc = tile_list(gg, CL, st, &d_tiles, &n_tiles);
+    int rc = segs ? tile_list_segments(gg, segs, n_segs, CL, st, &d_tiles, &n_tiles)
+                  : tile_list(gg, CL, st, &d_tiles, &n_tiles);
     if (rc) return rc;
     if (n_tiles == 0) return KAM_OK;
     if (CL == 2 && g_pair)
@@ -977,18 +1040,19 @@ size_t kam_gram_block_workspace_bytes(uint32_t n_a, uint32_t n_b) {
            kam_align_up(max_tiles(n_a, n_b) * sizeof(uint2), 1024);
 }
 
-int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_G_a, uint32_t n_a, const void *d_op_b,
+static int gram_block_impl(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_G_a, uint32_t n_a, const void *d_op_b,
                    const uint64_t *d_S_b, const uint64_t *d_G_b, uint32_t n_b, int operand_kind, uint64_t d,
                    int triangular, uint32_t row_begin, uint32_t row_end, unsigned metrics, int euclid_on_freq,
                    float *d_out_euclid, float *d_out_cosine, float *d_out_pearson, uint64_t out_ld, int sm_limit,
-                   void *d_ws, size_t ws_bytes, void *stream) {
+                   void *d_ws, size_t ws_bytes, void *stream, const uint32_t *segs, uint32_t n_segs,
+                           const uint32_t *d_ready, uint32_t ready_tiles) {
     KAM_REQUIRE(d_op_a && d_op_b && d_S_a && d_G_a && d_S_b && d_G_b && d_ws, "null pointer");
     KAM_REQUIRE(operand_kind == KAM_GRAM_U8 || operand_kind == KAM_GRAM_F16, "bad operand kind");
     KAM_REQUIRE((metrics & ~(KAM_M_EUCLID | KAM_M_COSINE | KAM_M_PEARSON)) == 0 && metrics != 0, "bad metrics mask");
     KAM_REQUIRE(!(metrics & KAM_M_EUCLID) || d_out_euclid, "null euclid output");
     KAM_REQUIRE(!(metrics & KAM_M_COSINE) || d_out_cosine, "null cosine output");
     KAM_REQUIRE(!(metrics & KAM_M_PEARSON) || d_out_pearson, "null pearson output");
-    KAM_REQUIRE(!triangular || (d_op_a == d_op_b && n_a == n_b), "a triangular block needs A == B");
+    KAM_REQUIRE(!triangular || (d_op_a == d_op_b && (segs ? n_a <= n_b : n_a == n_b)), "a triangular block needs A == B");
     KAM_REQUIRE(triangular || out_ld >= n_b, "dense output needs out_ld >= n_b");
     KAM_REQUIRE(out_ld == 0 || out_ld >= n_b, "out_ld smaller than n_b");
     if (n_a == 0 || n_b == 0 || row_begin >= row_end) return KAM_OK;
@@ -1002,7 +1066,7 @@ int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_
     RowK *rk_b = (RowK *)((char *)d_ws + kam_align_up((size_t)n_a * sizeof(RowK), 1024));
     rowk_kernel<<<(n_a + 255) / 256, 256, 0, st>>>((const unsigned long long *)d_S_a, (const unsigned long long *)d_G_a,
                                                    n_a, (double)d, euclid_on_freq, rk_a);
-    if (d_op_b != d_op_a || d_S_b != d_S_a)
+    if (d_op_b != d_op_a || d_S_b != d_S_a || n_b != n_a)
         rowk_kernel<<<(n_b + 255) / 256, 256, 0, st>>>((const unsigned long long *)d_S_b,
                                                        (const unsigned long long *)d_G_b, n_b, (double)d,
                                                        euclid_on_freq, rk_b);
@@ -1022,7 +1086,37 @@ int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_
     gg.ld = out_ld;
     gg.rk_a = rk_a;
     gg.rk_b = rk_b;
-    return gram_block(d_op_a, d_op_b, operand_kind == KAM_GRAM_U8, d, gg, go, sm_limit > 0 ? (uint32_t)sm_limit : 0u, st);
+    gg.ready = d_ready;
+    gg.ready_tiles = ready_tiles ? ready_tiles : 1u;
+    return gram_block(d_op_a, d_op_b, operand_kind == KAM_GRAM_U8, d, gg, go, sm_limit > 0 ? (uint32_t)sm_limit : 0u, st,
+                      0, 0, segs, n_segs);
+}
+
+int kam_gram_block(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_G_a, uint32_t n_a, const void *d_op_b,
+                   const uint64_t *d_S_b, const uint64_t *d_G_b, uint32_t n_b, int operand_kind, uint64_t d,
+                   int triangular, uint32_t row_begin, uint32_t row_end, unsigned metrics, int euclid_on_freq,
+                   float *d_out_euclid, float *d_out_cosine, float *d_out_pearson, uint64_t out_ld, int sm_limit,
+                   void *d_ws, size_t ws_bytes, void *stream) {
+    return gram_block_impl(d_op_a, d_S_a, d_G_a, n_a, d_op_b, d_S_b, d_G_b, n_b, operand_kind, d, triangular, row_begin,
+                           row_end, metrics, euclid_on_freq, d_out_euclid, d_out_cosine, d_out_pearson, out_ld,
+                           sm_limit, d_ws, ws_bytes, stream, nullptr, 0, nullptr, 1);
+}
+
+int kam_gram_fused(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_G_a, uint32_t n_a, const void *d_op_b,
+                   const uint64_t *d_S_b, const uint64_t *d_G_b, uint32_t n_b, int operand_kind, uint64_t d,
+                   int triangular_head, const uint32_t *h_segments, uint32_t n_segments, const uint32_t *d_ready,
+                   uint32_t ready_tiles, unsigned metrics, int euclid_on_freq, float *d_out_euclid,
+                   float *d_out_cosine, float *d_out_pearson, uint64_t out_ld, int sm_limit, void *d_ws,
+                   size_t ws_bytes, void *stream) {
+    KAM_REQUIRE(h_segments && n_segments >= 1 && n_segments <= 64, "kam_gram_fused: 1..64 segments");
+    KAM_REQUIRE(out_ld >= n_b, "kam_gram_fused writes dense rows: out_ld >= n_b");
+    KAM_REQUIRE(!triangular_head || d_op_a == d_op_b, "a triangular head needs B to start with the rows of A");
+    for (uint32_t i = 0; i < n_segments; ++i)
+        KAM_REQUIRE(h_segments[4 * i] <= h_segments[4 * i + 1] && h_segments[4 * i + 2] <= h_segments[4 * i + 3],
+                    "kam_gram_fused: a segment is (col tile begin <= end, row tile begin <= end)");
+    return gram_block_impl(d_op_a, d_S_a, d_G_a, n_a, d_op_b, d_S_b, d_G_b, n_b, operand_kind, d, triangular_head, 0,
+                           n_a, metrics, euclid_on_freq, d_out_euclid, d_out_cosine, d_out_pearson, out_ld, sm_limit,
+                           d_ws, ws_bytes, stream, h_segments, n_segments, d_ready, ready_tiles);
 }
 
 int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin, uint32_t row_end,

@@ -5,6 +5,7 @@
 // that owns every SM's shared memory they either wait or -- landing one per TPC -- keep whole TPCs away from
 // the clusters (measured: the overlapped block ran 33-100 % longer).  A pull by the copy engines from the
 // owner's exported buffer uses no SM at all.
+#include <cuda.h>
 #include <string.h>
 
 #include <mutex>
@@ -20,6 +21,23 @@ struct Opened {
 constexpr int MAX_OPEN = 64;
 Opened g_open[MAX_OPEN];
 std::mutex g_mu;
+
+// cuStreamWriteValue32 through the runtime's driver entry point (no link-time libcuda dependency): a 4-byte
+// write the stream performs in order, without a kernel and without a copy-engine descriptor.
+typedef CUresult (*write_value32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+write_value32_fn write_value32() {
+    static write_value32_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return (write_value32_fn)p;
+    }();
+    return fn;
+}
+uint32_t *g_one = nullptr;   // pinned word holding 1: the source of the flag copies when the stream write is not to be had
 }  // namespace
 
 static_assert(sizeof(cudaIpcMemHandle_t) == KAM_PEER_HANDLE_BYTES, "handle size");
@@ -94,6 +112,46 @@ int kam_peer_close(void *d_mapped) {
 int kam_peer_copy(void *d_dst, const void *d_src, size_t bytes, void *stream) {
     KAM_REQUIRE(bytes == 0 || (d_dst && d_src), "null pointer");
     if (bytes) KAM_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return KAM_OK;
+}
+
+int kam_peer_signal(uint32_t *d_flag, void *stream) {
+    KAM_REQUIRE(d_flag, "null pointer");
+    if (write_value32_fn fn = write_value32()) {
+        const CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)d_flag, 1u, 0u /* default: ordered after prior work */);
+        if (r == CUDA_SUCCESS) return KAM_OK;
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (!g_one) {
+            KAM_CUDA(cudaMallocHost(&g_one, sizeof(uint32_t)));
+            *g_one = 1u;
+        }
+    }
+    KAM_CUDA(cudaMemcpyAsync(d_flag, g_one, sizeof(uint32_t), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return KAM_OK;
+}
+
+int kam_peer_pull(const kam_peer_piece *pieces, uint32_t n_pieces, uint32_t *d_flags, void *const *streams,
+                  uint32_t n_streams) {
+    KAM_REQUIRE(n_pieces == 0 || pieces, "null pointer");
+    KAM_REQUIRE(streams && n_streams >= 1, "kam_peer_pull needs at least one stream");
+    for (uint32_t i = 0; i < n_pieces; ++i) {
+        const kam_peer_piece &p = pieces[i];
+        KAM_REQUIRE(i == 0 || pieces[i - 1].chunk <= p.chunk || pieces[i - 1].chunk == KAM_PEER_NO_FLAG,
+                    "kam_peer_pull: pieces must come in chunk order");
+        cudaStream_t st = (cudaStream_t)streams[p.chunk == KAM_PEER_NO_FLAG ? 0 : p.chunk % n_streams];
+        if (p.bytes) {
+            KAM_REQUIRE(p.d_dst && p.d_src, "null pointer in a piece");
+            KAM_CUDA(cudaMemcpyAsync(p.d_dst, p.d_src, p.bytes, cudaMemcpyDefault, st));
+        }
+        const bool last_of_chunk = i + 1 == n_pieces || pieces[i + 1].chunk != p.chunk;
+        if (p.chunk != KAM_PEER_NO_FLAG && last_of_chunk) {
+            KAM_REQUIRE(d_flags, "kam_peer_pull: flagged pieces need d_flags");
+            int rc = kam_peer_signal(d_flags + p.chunk, st);
+            if (rc) return rc;
+        }
+    }
     return KAM_OK;
 }
 

@@ -244,6 +244,250 @@ def _align(x, a=256):
     return (x + a - 1) // a * a
 
 
+def shared_split(n_rows):
+    """Rows of the lower-numbered shard that its owner takes of a block two ranks share (fused ring): the first
+    h rows -- half of them, rounded up to whole 256-row tiles so that the split is a property of the tile list
+    -- the other rank takes rows [h, n_rows)."""
+    return min(n_rows, ((n_rows + 1) // 2 + 255) // 256 * 256)
+
+
+def fused_plan(rank, counts):
+    """What rank `rank` computes in the ONE launch of the fused ring.  Its B matrix is the concatenation of its own
+    rows and the rows it pulls, in the order of ring_schedule's steps.  Returns a list of
+        {"src", "src_rows": (s0, s1), "b_rows": (b0, b1), "part", "a_rows": (r0, r1)}
+    -- B rows [b0, b1) hold rows [s0, s1) of shard `src`; the rank computes its own rows [r0, r1) against them.
+    part: 'tri' (own rows), 'full', 'lo' (rows [0, h) of mine against all of src) or 'hi' (all my rows against
+    rows [h, n) of src: the other half of the block the two ranks share, held transposed)."""
+    world = len(counts)
+    n_loc = counts[rank]
+    plan = [{"src": rank, "src_rows": (0, n_loc), "b_rows": (0, n_loc), "part": "tri", "a_rows": (0, n_loc)}]
+    off = n_loc
+    for s in range(1, world // 2 + 1):
+        c = (rank + s) % world
+        if world % 2 == 0 and s == world // 2:
+            if rank < c:
+                h = shared_split(n_loc)
+                e = {"src": c, "src_rows": (0, counts[c]), "part": "lo", "a_rows": (0, h)}
+            else:
+                h = shared_split(counts[c])
+                e = {"src": c, "src_rows": (h, counts[c]), "part": "hi", "a_rows": (0, n_loc)}
+        else:
+            e = {"src": c, "src_rows": (0, counts[c]), "part": "full", "a_rows": (0, n_loc)}
+        n = e["src_rows"][1] - e["src_rows"][0]
+        e["b_rows"] = (off, off + n)
+        off += n
+        plan.append(e)
+    return plan
+
+
+def fused_segments(plan):
+    """Tile-list segments (column tile begin, end, row tile begin, end; tiles of 256 rows) of a fused_plan: the
+    column tiles of B in arrival order, each tile in the first segment that reaches it; a tile that straddles two
+    shards goes with the earlier one (it waits for the chunk that completes it).  Only the 'lo' share limits
+    the rows."""
+    segs, done = [], 0
+    n_a = plan[0]["a_rows"][1]
+    all_rows = (n_a + 255) // 256
+    for e in plan:
+        end = (e["b_rows"][1] + 255) // 256
+        if end > done:
+            rows = all_rows if e["part"] != "lo" else min(all_rows, (e["a_rows"][1] + 255) // 256)
+            segs.append((done, end, 0, rows))
+            done = end
+    return segs
+
+
+def _gather_small(t_cpu, dev, group):
+    """all-gather of a few bytes per rank -> CPU tensor [world, len]; over the device for NCCL, on the host for gloo"""
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) == "gloo":
+        parts = [torch.empty_like(t_cpu) for _ in range(world)]
+        dist.all_gather(parts, t_cpu, group=group)
+        return torch.stack(parts)
+    out = torch.empty((world, t_cpu.numel()), dtype=t_cpu.dtype, device=dev)
+    dist.all_gather_into_tensor(out, t_cpu.to(dev), group=group)
+    return out.cpu()
+
+
+def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
+    """gram_ring for ranks of one NVLink box, the exchange fused into the kernel: ONE kam_gram_fused launch per
+    rank computes all its blocks while the copy engines pull the other shards' operand rows chunk by chunk from
+    the owners' exported buffers (kam_peer_pull); every chunk is followed by a flag the kernel's TMA producers
+    wait for, tile by tile.  No launch boundary between blocks (the per-step launches lost 2 of 24 waves of tiles
+    to quantisation at 8 ranks x 5000 rows) and no block waits for a whole shard."""
+    import ctypes
+    from . import _lib
+    from . import dist as D
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = x_local.device
+    n_loc, d = x_local.shape
+    elem = D._ELEM[x_local.dtype]
+    cur = torch.cuda.current_stream(dev)
+    stream = cur.cuda_stream
+    dpad = int(lib.kam_gram_dpad(d))
+    bits = {"euclid": _lib.KAM_M_EUCLID, "cosine": _lib.KAM_M_COSINE, "pearson": _lib.KAM_M_PEARSON}
+    mask = 0
+    for m in metrics:
+        mask |= bits[m]
+    marks = []
+
+    def mark(label):
+        if timing is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(cur)
+            marks.append((label, e))
+
+    mark("start")
+    # 1. who holds how many rows -> what this rank pulls, its B matrix and its tile segments
+    counts = [int(v) for v in _gather_small(torch.tensor([n_loc], dtype=torch.int64), dev, group)[:, 0].tolist()]
+    plan = fused_plan(rank, counts)
+    n_b = plan[-1]["b_rows"][1]
+
+    def header(n):                   # exported buffer: [S | G | operand rows ...]; offsets of G and of the rows
+        hb = _align(max(n, 1) * 8, 1024)
+        return hb, 2 * hb
+
+    # 2. own operand rows + statistics into the exported buffer; the operand kind is a global decision, and the
+    #    gather that takes it also carries the buffer handles and proves every owner's rows complete
+    for kind, esz in ((_lib.KAM_GRAM_U8, 1), (_lib.KAM_GRAM_F16, 2)):
+        g_off, rows_off = header(n_loc)
+        base, handle = _peer_buffer(lib, dev, rows_off + max(n_b, 1) * dpad * esz)
+        flags = torch.zeros(8, dtype=torch.int64, device=dev)
+        if n_loc:
+            with torch.cuda.device(dev):
+                _lib.check(lib.kam_gram_prepare(x_local.data_ptr(), elem, n_loc, d, x_local.stride(0), kind,
+                                                base + rows_off, base, base + g_off, flags.data_ptr(), stream))
+        mine = torch.zeros(24 + _lib.KAM_PEER_HANDLE_BYTES, dtype=torch.uint8)
+        mine[:24] = flags[:3].cpu().view(torch.uint8)                 # (host sync: my rows are complete)
+        mine[24:] = torch.frombuffer(bytearray(handle), dtype=torch.uint8)
+        infos = _gather_small(mine, dev, group)
+        fl = infos[:, :24].contiguous().view(torch.int64).view(world, 3)
+        mx, gmax, bad = int(fl[:, 0].max()), int(fl[:, 1].max()), int(fl[:, 2].max())
+        if bad:
+            raise ValueError("%d floating-point row(s) are not frequency vectors (count / sum): "
+                             "use distances_sharded()" % bad)
+        ok = (mx <= 255 and gmax < 2 ** 31) if kind == _lib.KAM_GRAM_U8 else (mx <= 2048 and gmax < 2 ** 24)
+        if ok:
+            break
+        dist.barrier(group)          # nobody re-converts into a buffer a peer might (wrongly) still read
+    else:
+        raise NotImplementedError("counts outside the tensor-exact envelope: use distances_sharded()")
+    handles = [bytes(infos[r, 24:].tolist()) for r in range(world)]
+    mark("prepared")
+
+    # 3. statistics of all B rows (needed complete at launch: a few KB per shard, pulled first), arrival flags
+    row_b = dpad * esz
+    tile_b = 256 * row_b
+    ready_tiles = int(os.environ.get("KAM_RING_CHUNK_TILES", "0")) or max(1, (32 << 20) // tile_b)
+    chunk_rows = 256 * ready_tiles
+    n_chunks = (max(n_b, 1) + chunk_rows - 1) // chunk_rows
+    stats = torch.empty((2, max(n_b, 1)), dtype=torch.int64, device=dev)
+    ready = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
+    local_chunks = n_loc // chunk_rows if n_b > n_loc else n_chunks   # chunks made of own rows only
+    if local_chunks:
+        ready[:local_chunks] = 1
+    st = _peer_state(dev)
+    if st.get("stream") is None:
+        st["stream"], st["stream2"] = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    side, side2 = st["stream"], st["stream2"]
+    for sd in (side, side2):
+        sd.wait_stream(cur)          # the flags are zeroed, the statistics buffer exists
+    pieces_stats, pieces = [], []
+    S_b, G_b = stats[0].data_ptr(), stats[1].data_ptr()
+    for e in plan:
+        s0, s1 = e["src_rows"]
+        b0 = e["b_rows"][0]
+        peer = base if e["src"] == rank else _peer_open(lib, dev, e["src"], handles[e["src"]])
+        g_src, rows_src = header(counts[e["src"]])
+        if s1 > s0:
+            pieces_stats.append((S_b + b0 * 8, peer + s0 * 8, (s1 - s0) * 8, _lib.KAM_PEER_NO_FLAG))
+            pieces_stats.append((G_b + b0 * 8, peer + g_src + s0 * 8, (s1 - s0) * 8, _lib.KAM_PEER_NO_FLAG))
+        e["_peer_rows"] = peer + rows_src
+    if n_loc == 0:
+        pieces_stats = []            # a rank without rows computes nothing: it only serves its peers
+    for c in range(local_chunks, n_chunks if n_loc else 0):
+        lo, hi = c * chunk_rows, min((c + 1) * chunk_rows, n_b)
+        for e in plan[1:]:
+            b0, b1 = e["b_rows"]
+            x0, x1 = max(lo, b0), min(hi, b1)
+            if x1 > x0:
+                pieces.append((base + rows_off + x0 * row_b, e["_peer_rows"] + (e["src_rows"][0] + x0 - b0) * row_b,
+                               (x1 - x0) * row_b, c))
+        if not pieces or pieces[-1][3] != c:
+            pieces.append((0, 0, 0, c))                              # nothing to pull: the flag alone
+
+    def pull(plist, streams):
+        if not plist:
+            return
+        arr = (_lib.PeerPiece * len(plist))()
+        for i, (dst, src, nbytes, chunk) in enumerate(plist):
+            arr[i].d_dst, arr[i].d_src, arr[i].bytes, arr[i].chunk = dst, src, nbytes, chunk
+        sp = (ctypes.c_void_p * len(streams))(*[sd.cuda_stream for sd in streams])
+        with torch.cuda.device(dev):
+            _lib.check(lib.kam_peer_pull(arr, len(plist), ready.data_ptr(), sp, len(streams)))
+
+    pull(pieces_stats, [side])
+    got_stats = torch.cuda.Event()
+    got_stats.record(side)
+    side2.wait_event(got_stats)      # (keeps the two copy streams' first chunks behind the small transfers)
+
+    # 4. outputs and the one launch; then the chunk transfers it waits for
+    outs, ptrs = {}, {}
+    for m in metrics:
+        t = torch.empty((max(n_loc, 1), max(n_b, 1)), dtype=torch.float32, device=dev)
+        t[:, :n_loc].zero_()         # the triangular head keeps zeros on and below its diagonal
+        outs[m], ptrs[m] = t, t.data_ptr()
+    ws = torch.empty(lib.kam_gram_block_workspace_bytes(n_loc, n_b), dtype=torch.uint8, device=dev)
+    segs = fused_segments(plan)
+    seg_arr = (ctypes.c_uint32 * (4 * len(segs)))(*[v for sg in segs for v in sg])
+    mark("wait_stats")
+    cur.wait_event(got_stats)
+    mark("block")
+    if n_loc and n_b:
+        with torch.cuda.device(dev):
+            _lib.check(lib.kam_gram_fused(base + rows_off, base, base + g_off, n_loc, base + rows_off, S_b, G_b, n_b, kind,
+                                          d, 1, seg_arr, len(segs), ready.data_ptr(), ready_tiles, mask,
+                                          int(euclid_on_freq), ptrs.get("euclid"), ptrs.get("cosine"),
+                                          ptrs.get("pearson"), max(n_b, 1), 0, ws.data_ptr(), ws.numel(), stream))
+    pull(pieces, [side, side2])
+    mark("end")
+    cur.synchronize()
+    cur.wait_stream(side)
+    cur.wait_stream(side2)
+    dist.barrier(group)              # nobody overwrites or frees its exported rows while a peer still reads them
+
+    out_blocks = []
+    for e in plan:
+        b0, b1 = e["b_rows"]
+        r0, r1 = e["a_rows"]
+        if e["part"] == "hi":        # held transposed: pairs (row s of shard src, my row j)
+            blk = {"row_shard": e["src"], "col_shard": rank, "rows": e["src_rows"], "tri": False}
+            for m in metrics:
+                blk[m] = outs[m][:n_loc, b0:b1].t()
+        else:
+            blk = {"row_shard": rank, "col_shard": e["src"], "rows": (r0, r1), "tri": e["part"] == "tri"}
+            for m in metrics:
+                blk[m] = outs[m][r0:r1, b0:b1]
+        if blk["rows"][1] > blk["rows"][0] or e["part"] == "tri":
+            out_blocks.append(blk)
+    if timing is not None:
+        t = {"prepare_ms": 0.0, "block_ms": 0.0, "exposed_comm_ms": 0.0, "other_ms": 0.0, "blocks_ms": []}
+        for (la, ea), (_, eb) in zip(marks[:-1], marks[1:]):
+            dt = ea.elapsed_time(eb)
+            key = "prepare_ms" if la == "start" else "block_ms" if la == "block" else \
+                "exposed_comm_ms" if la == "wait_stats" else "other_ms"
+            t[key] += dt
+            if la == "block":
+                t["blocks_ms"].append(round(dt, 3))
+        t.update(sm_reserve=0, transport="peer (fused: one launch, chunk flags)",
+                 operand="uint8" if kind == _lib.KAM_GRAM_U8 else "fp16",
+                 recv_bytes=int((n_b - n_loc) * row_b), chunks=int(n_chunks - local_chunks),
+                 chunk_bytes=int(chunk_rows * row_b), tiles_segments=[list(sg) for sg in segs])
+        timing.update(t)
+    return out_blocks, counts
+
+
 def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group=None, sm_reserve=None, timing=None,
               transport=None):
     """euclid / cosine / pearson over the rows of all ranks, block-cyclic pair ownership.
@@ -282,6 +526,8 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
         transport = os.environ.get("KAM_RING_TRANSPORT", "peer")
     if world == 1:
         transport = "local"
+    if transport == "peer" and os.environ.get("KAM_RING_FUSED", "1") == "1":
+        return _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing)
     cur = torch.cuda.current_stream(dev)
     stream = cur.cuda_stream
     dpad = int(lib.kam_gram_dpad(d))
@@ -333,9 +579,7 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
         if handle:
             info[:_lib.KAM_PEER_HANDLE_BYTES] = torch.frombuffer(bytearray(handle), dtype=torch.uint8)
         info[_lib.KAM_PEER_HANDLE_BYTES:] = torch.tensor([n_loc], dtype=torch.int64).view(torch.uint8)
-        infos = torch.empty((world, info.numel()), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(infos, info.to(dev), group=group)
-        infos = infos.cpu()
+        infos = _gather_small(info, dev, group)
         counts = [int(infos[r, _lib.KAM_PEER_HANDLE_BYTES:].view(torch.int64)[0]) for r in range(world)]
         handles = [bytes(infos[r, :_lib.KAM_PEER_HANDLE_BYTES].tolist()) for r in range(world)]
     else:

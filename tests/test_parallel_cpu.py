@@ -313,3 +313,44 @@ def test_ring_groups_cover_every_step_once():
             assert len(groups[0]) == 1
         if world % 2 == 0 and world > 1:
             assert groups[-1] == [world // 2] and plan[world // 2] in ("lo", "hi")
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_fused_plan_covers_every_pair_once_and_segments_hold_every_tile(world):
+    """the fused ring's plan (parallel.fused_plan / fused_segments, host logic of kam_gram_fused): over all ranks
+    every unordered pair of rows is computed exactly once -- ragged shards, one below a tile, one empty -- and a
+    rank's tile segments contain every (row tile, column tile) its entries need, each column tile in one segment"""
+    from kameris_b200 import parallel
+    counts = [(517, 300, 0, 1025, 40, 256, 777, 513)[r] for r in range(world)]
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    n = int(offs[-1])
+    cover = np.zeros((n, n), dtype=np.int32)
+    for rank in range(world):
+        plan = parallel.fused_plan(rank, counts)
+        segs = parallel.fused_segments(plan)
+        assert plan[0]["part"] == "tri" and plan[0]["b_rows"] == (0, counts[rank])
+        prev_end = 0
+        for c0, c1, r0, r1 in segs:
+            assert c0 == prev_end and c1 > c0 and r0 == 0
+            prev_end = c1
+        assert prev_end == (plan[-1]["b_rows"][1] + 255) // 256
+        for e in plan:
+            b0, b1 = e["b_rows"]
+            s0, s1 = e["src_rows"]
+            a0, a1 = e["a_rows"]
+            assert b1 - b0 == s1 - s0
+            gi = offs[rank] + np.arange(a0, a1)
+            gj = offs[e["src"]] + np.arange(s0, s1)
+            if e["part"] == "tri":
+                for i in range(a0, a1):
+                    cover[offs[rank] + i, offs[rank] + i + 1:offs[rank] + a1] += 1
+            elif gi.size and gj.size:
+                lo, hi = np.minimum.outer(gi, gj), np.maximum.outer(gi, gj)
+                np.add.at(cover, (lo.ravel(), hi.ravel()), 1)
+            # every tile of this entry's rectangle lies in a segment with enough rows
+            for ct in range(b0 // 256, (b1 + 255) // 256 if b1 > b0 else b0 // 256):
+                seg = [sg for sg in segs if sg[0] <= ct < sg[1]]
+                assert len(seg) == 1
+                assert seg[0][3] * 256 >= a1 or seg[0][3] == (counts[rank] + 255) // 256
+    iu = np.triu(np.ones((n, n), dtype=bool), 1)
+    assert (cover[iu] == 1).all() and (cover[~iu] == 0).all()
