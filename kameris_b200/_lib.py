@@ -60,6 +60,8 @@ SIGNATURES = {
     "kam_fasta_file_sizes": (c_int, [c_void_p, c_uint32, c_void_p, c_int]),
     "kam_fasta_read_files": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "kam_manhattan_workspace_bytes": (c_size_t, [c_uint32, c_uint64]),
+    "kam_manhattan_workspace_bytes_levels": (c_size_t, [c_uint32, c_uint64, c_uint32]),
+    "kam_dist_set_tensor": (None, [c_int]),
     "kam_manhattan_tri": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_uint32, c_uint32, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
     "kam_manhattan_rect": (c_int, [c_void_p, c_void_p, c_int, c_uint32, c_uint32, c_uint64, c_uint64, c_uint64,

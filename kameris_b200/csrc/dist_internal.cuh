@@ -19,6 +19,10 @@ struct GramOut {
     float *euclid, *cosine, *pearson;   // nullptr = not requested
     int *raw = nullptr;                 // when set: the exact int32 Gram entry itself, dense [row * ld + col]
                                         // (limb-split path: three partial Grams are combined afterwards)
+    // thermometer operands (gram.cu: kam_thermo_*): G_ij = sum_e min(c_i[e], c_j[e]) resp. |supp_i & supp_j|;
+    // the RowK fields `a` / `q` then hold the BIT PATTERNS of the integers sum(c) / nnz(c), not doubles
+    uint32_t *manhat = nullptr;         // sum(c_i) + sum(c_j) - 2 G_ij  (mod 2^32, like the reference's uint32 sum)
+    float *info = nullptr;              // U = nnz_i + nnz_j - G_ij: U == 0 ? 0 : (1.0f / (float)U) * (float)(U - G_ij)
 };
 
 // geometry of one Gram block: rows of matrix A against rows of matrix B
@@ -74,6 +78,21 @@ int kam_float_prepass(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_
                       unsigned long long *S, unsigned long long *G, unsigned long long *flags, cudaStream_t st);
 int kam_float_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,
                        uint32_t row_end, RowK *rk, GramOut go, cudaStream_t st);
+
+// manhat / info on the tensor cores (gram.cu): thermometer-coded operand rows of one matrix
+struct ThermoOp {
+    const uint8_t *op = nullptr;   // [n][levels * dpad]: byte e of level t (1-based, at (t-1) * dpad) = (c[e] >= t)
+    const RowK *rk = nullptr;      // a = bits of sum(c), q = bits of nnz(c)
+    uint32_t n = 0, levels = 0;
+    uint64_t d = 0;
+};
+size_t kam_thermo_bytes(uint32_t n, uint64_t d, uint32_t levels);
+int kam_thermo_prepare(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t levels, void *d_ws,
+                       ThermoOp *out, cudaStream_t st);
+// rows [row_begin, row_end) of A against all rows of B (tri: A and B are the same operand, pairs j > i, packed
+// triangle when out_ld == 0); `info` uses level 1 only
+int kam_thermo_pairs(const ThermoOp &A, const ThermoOp &B, bool tri, uint32_t row_begin, uint32_t row_end,
+                     uint32_t *d_manhat, float *d_info, uint64_t out_ld, cudaStream_t st);
 
 size_t kam_int_gram_xt_bytes(uint32_t n, uint64_t d);
 int kam_int_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,

@@ -337,6 +337,17 @@ int max_of(const void *x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_
     return KAM_OK;
 }
 
+// manhat / info as tensor-core contractions over thermometer-coded rows (gram.cu: kam_thermo_*): 0 = never,
+// 1 = when the shape fills tiles of 256 x 256 pairs and the largest count is small (default), 2 = whenever the
+// operands can be encoded (tests: the small golden cases of the reference's machine code run through it too)
+int g_tensor_mode = 1;
+constexpr uint32_t THERMO_MAX_LEVELS = 16;   // break-even against VABSDIFF4 is ~25 levels; the operand grows with it
+
+inline bool thermo_shape_ok(uint32_t rows, uint32_t cols) {
+    return g_tensor_mode == 2 || (g_tensor_mode == 1 && rows >= 512 && cols >= 128);
+}
+inline bool thermo_elem_ok(int elem) { return elem == KAM_U8 || elem == KAM_U16 || elem == KAM_U32; }
+
 }  // namespace
 
 // exact integer Gram metrics for inputs outside the fp16/fp32-exact envelope of gram.cu
@@ -353,8 +364,20 @@ extern "C" {
 
 size_t kam_manhattan_workspace_bytes(uint32_t rows_total, uint64_t d) {
     // worst case: one uint32 word per element, plus padding for two operands and the flag word
-    return xt_bytes(rows_total, (uint32_t)d) + 2 * 4096 + 1024;
+    // ... and never less than the tensor path needs for counts up to 4 (thermometer rows of 4 levels); a caller
+    // that wants it for larger counts passes kam_manhattan_workspace_bytes_levels(rows, d, max count)
+    const size_t classic = xt_bytes(rows_total, (uint32_t)d) + 2 * 4096 + 1024;
+    const size_t tensor = kam_thermo_bytes(rows_total, d, 4) + 1024;
+    return classic > tensor ? classic : tensor;
 }
+
+size_t kam_manhattan_workspace_bytes_levels(uint32_t rows_total, uint64_t d, uint32_t max_count) {
+    const uint32_t levels = max_count < 1 ? 1 : max_count > THERMO_MAX_LEVELS ? THERMO_MAX_LEVELS : max_count;
+    const size_t base = kam_manhattan_workspace_bytes(rows_total, d), tensor = kam_thermo_bytes(rows_total, d, levels) + 1024;
+    return base > tensor ? base : tensor;
+}
+
+void kam_dist_set_tensor(int mode) { g_tensor_mode = mode < 0 ? 0 : mode > 2 ? 2 : mode; }
 
 int kam_manhattan_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,
                       uint32_t row_end, uint32_t *d_tri, void *d_ws, size_t ws_bytes, void *stream) {
@@ -384,6 +407,15 @@ int kam_manhattan_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_
     uint32_t mx = 0;
     int rc = max_of(d_x, elem, n, d, ld, flag, &mx, st);
     if (rc) return rc;
+    {   // small counts: sum |a - b| = S_a + S_b - 2 sum min(a, b) on the tensor cores (thermometer rows)
+        const uint32_t levels = mx ? mx : 1;
+        if (levels <= THERMO_MAX_LEVELS && thermo_shape_ok(n, n) && (uint64_t)levels * d < (1ull << 31) &&
+            ws_bytes >= 1024 + kam_thermo_bytes(n, d, levels)) {
+            ThermoOp op;
+            if ((rc = kam_thermo_prepare(d_x, elem, n, d, ld, levels, (char *)d_ws + 1024, &op, st))) return rc;
+            return kam_thermo_pairs(op, op, true, row_begin, row_end, d_tri, nullptr, 0, st);
+        }
+    }
     if (mx <= 255) {   // every count fits a byte: four elements per VABSDIFF4
         if ((rc = convert_dispatch<OP_SAD8X4>(d_x, elem, n, d, ld, xt, st))) return rc;
         return launch_pairs<OP_SAD8X4, true>(xt, n, xt, n, kw_of(OP_SAD8X4, d), row_begin, row_end, d_tri, st);
@@ -407,6 +439,18 @@ int kam_manhattan_rect(const void *d_x, const void *d_y, int elem, uint32_t m, u
     uint32_t mx = 0, my = 0;
     int rc;
     if ((rc = max_of(d_x, elem, m, d, ldx, flag, &mx, st)) || (rc = max_of(d_y, elem, c, d, ldy, flag, &my, st))) return rc;
+    {
+        const uint32_t top = mx > my ? mx : my, levels = top ? top : 1;
+        const size_t need_x = kam_thermo_bytes(m, d, levels);
+        if (levels <= THERMO_MAX_LEVELS && thermo_shape_ok(m, c) && (uint64_t)levels * d < (1ull << 31) &&
+            ws_bytes >= 1024 + need_x + kam_thermo_bytes(c, d, levels)) {
+            ThermoOp ox, oy;
+            if ((rc = kam_thermo_prepare(d_x, elem, m, d, ldx, levels, (char *)d_ws + 1024, &ox, st)) ||
+                (rc = kam_thermo_prepare(d_y, elem, c, d, ldy, levels, (char *)d_ws + 1024 + need_x, &oy, st)))
+                return rc;
+            return kam_thermo_pairs(ox, oy, false, 0, m, d_out, nullptr, c, st);
+        }
+    }
     const bool bytes = mx <= 255 && my <= 255;
     const uint32_t kw = kw_of(bytes ? OP_SAD8X4 : OP_SAD32, d);
     uint32_t *xt = (uint32_t *)((char *)d_ws + 1024);
@@ -443,7 +487,11 @@ int kam_manhattan_rect_f32(const void *d_x, int elem_x, const float *d_y, uint32
     return launch_pairs<OP_L1F32, false>(xt, m, yt, c, kw, 0, m, d_out, st);
 }
 
-size_t kam_info_workspace_bytes(uint32_t n, uint64_t d) { return xt_bytes(n, kw_of(OP_JACC, d)) + 1024; }
+static size_t info_classic_bytes(uint32_t n, uint64_t d) { return xt_bytes(n, kw_of(OP_JACC, d)) + 1024; }
+size_t kam_info_workspace_bytes(uint32_t n, uint64_t d) {   // presence bits, or presence BYTES for the tensor path
+    const size_t classic = info_classic_bytes(n, d), tensor = kam_thermo_bytes(n, d, 1) + 1024;
+    return classic > tensor ? classic : tensor;
+}
 
 int kam_info_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,
                  uint32_t row_end, float *d_tri, void *d_ws, size_t ws_bytes, void *stream) {
@@ -451,11 +499,19 @@ int kam_info_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     KAM_REQUIRE(elem >= KAM_U8 && elem <= KAM_F64, "bad element type");
     KAM_REQUIRE(d >= 1 && d < (1ull << 32) && ld >= d, "bad d / ld");
     if (n < 2 || row_begin >= row_end) return KAM_OK;
-    if (ws_bytes < kam_info_workspace_bytes(n, d)) {
+    if (ws_bytes < info_classic_bytes(n, d)) {
         kam_set_error("kam_info_tri: workspace too small");
         return KAM_E_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (row_end > n) row_end = n;
+    // |supp_i & supp_j| is the Gram of the presence vectors: tensor cores (gram.cu: level 1 of the thermometer rows)
+    if (thermo_elem_ok(elem) && thermo_shape_ok(n, n) && ws_bytes >= 1024 + kam_thermo_bytes(n, d, 1)) {
+        ThermoOp op;
+        int rc = kam_thermo_prepare(d_x, elem, n, d, ld, 1, (char *)d_ws + 1024, &op, st);
+        if (rc) return rc;
+        return kam_thermo_pairs(op, op, true, row_begin, row_end, nullptr, d_tri, 0, st);
+    }
     uint32_t *xt = (uint32_t *)((char *)d_ws + 1024);
     int rc = convert_dispatch<OP_JACC>(d_x, elem, n, d, ld, xt, st);
     if (rc) return rc;

@@ -184,6 +184,25 @@ __device__ __forceinline__ void gram_store_chunk(const GramGeom &gg, const GramO
         put(reinterpret_cast<float *>(go.raw), val);
         return;
     }
+    if (I8 && (go.manhat || go.info)) {   // thermometer operands: integer epilogue, the reference's own formulas
+        if (go.manhat) {
+            const uint32_t si = (uint32_t)__double_as_longlong(ri.a);
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                val[c] = __uint_as_float(si + (uint32_t)__double_as_longlong(colk[c].a) - 2u * v[c]);
+            put(reinterpret_cast<float *>(go.manhat), val);
+        }
+        if (go.info) {   // generation_dists @0x10001bc13: U == 0 ? 0 : (1.0f / (float)U) * (float)(U - I), single precision
+            const uint32_t ni = (uint32_t)__double_as_longlong(ri.q);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const uint32_t U = ni + (uint32_t)__double_as_longlong(colk[c].q) - v[c];
+                val[c] = U == 0 ? 0.0f : __fmul_rn(__fdiv_rn(1.0f, (float)U), (float)(U - v[c]));
+            }
+            put(go.info, val);
+        }
+        return;
+    }
     if (go.cosine) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
@@ -721,6 +740,70 @@ __global__ void __launch_bounds__(256) gram_limb_combine_kernel(const int *__res
     gram_store(go, idx, g, rk[row], rk[j]);
 }
 
+// ---- thermometer operands: the reference's two metrics, `manhat` and `info`, as contractions ------------------
+// sum_e |a_e - b_e| = sum(a) + sum(b) - 2 sum_e min(a_e, b_e), and for counts up to T
+// min(a_e, b_e) = sum_{t=1..T} [a_e >= t][b_e >= t]: an integer Gram of rows of T * d indicator bytes.  Level 1 is
+// the presence vector, whose Gram is |supp_a & supp_b| -- all `info` needs (union = nnz_a + nnz_b - intersection).
+// k-mer counts of short reads and of kilobase genomes at k = 9 rarely pass 3, so T is small and kind::i8 tcgen05
+// runs T * d MACs per pair at ~25x the CUDA cores' VABSDIFF4 / POPC rate per element.  One CTA per row.
+template <typename T>
+__global__ void __launch_bounds__(256) thermo_prepass_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
+                                                             uint64_t dpad, uint32_t levels, uint8_t *__restrict__ op,
+                                                             RowK *__restrict__ rk, int vec_ok) {
+    __shared__ unsigned long long red[2][8];
+    const uint32_t row = blockIdx.x;
+    const T *xr = x + (uint64_t)row * ld;
+    uint8_t *out = op + (uint64_t)row * levels * dpad;
+    unsigned long long s = 0, nz = 0;
+    for (uint64_t e = (uint64_t)threadIdx.x * 16; e < dpad; e += 256 * 16) {   // dpad is a multiple of 128
+        unsigned c[16];
+        if (vec_ok && e < d) {   // d % 16 == 0 and 16-byte aligned rows
+            constexpr int NV = (int)sizeof(T);
+            uint4 v[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) v[i] = __ldg(reinterpret_cast<const uint4 *>(xr + e) + i);
+            const T *t = reinterpret_cast<const T *>(v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c[i] = (unsigned)t[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c[i] = e + i < d ? (unsigned)xr[e + i] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            s += c[i];
+            nz += c[i] != 0;
+        }
+        for (uint32_t t = 1; t <= levels; ++t) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                w[q] = (c[4 * q] >= t ? 1u : 0u) | (c[4 * q + 1] >= t ? 0x100u : 0u) | (c[4 * q + 2] >= t ? 0x10000u : 0u) |
+                       (c[4 * q + 3] >= t ? 0x1000000u : 0u);
+            *reinterpret_cast<uint4 *>(out + (uint64_t)(t - 1) * dpad + e) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    s = warp_sum64(s);
+    nz = warp_sum64(nz);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s;
+        red[1][threadIdx.x >> 5] = nz;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long ts = 0, tz = 0;
+        for (int w = 0; w < 8; ++w) {
+            ts += red[0][w];
+            tz += red[1][w];
+        }
+        RowK r;
+        r.rn = r.S = r.mu = r.rp = 0.0;
+        r.a = __longlong_as_double((long long)ts);   // bit patterns of the integers (GramOut::manhat / info)
+        r.q = __longlong_as_double((long long)tz);
+        rk[row] = r;
+    }
+}
+
 __global__ void rowk_kernel(const unsigned long long *__restrict__ S, const unsigned long long *__restrict__ G,
                             uint32_t n, double D, int euclid_on_freq, RowK *__restrict__ rk) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1015,6 +1098,74 @@ int read_flags(const unsigned long long *d_flags, unsigned long long (&h)[3], cu
 }
 
 }  // namespace
+
+size_t kam_thermo_bytes(uint32_t n, uint64_t d, uint32_t levels) {
+    return kam_align_up((size_t)n * sizeof(RowK), 1024) + kam_align_up((size_t)n * levels * dpad_of(d), 1024) + 1024;
+}
+
+int kam_thermo_prepare(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t levels, void *d_ws,
+                       ThermoOp *out, cudaStream_t st) {
+    RowK *rk = (RowK *)d_ws;
+    uint8_t *op = (uint8_t *)d_ws + kam_align_up((size_t)n * sizeof(RowK), 1024);
+    const uint64_t dpad = dpad_of(d);
+    const size_t esz = elem == KAM_U8 ? 1 : elem == KAM_U16 ? 2 : 4;
+    const int vec_ok = (d % 16 == 0) && ((ld * esz) % 16 == 0) && (((uintptr_t)d_x & 15) == 0);
+    if (n) {
+        if (elem == KAM_U8)
+            thermo_prepass_kernel<uint8_t><<<n, 256, 0, st>>>((const uint8_t *)d_x, n, d, ld, dpad, levels, op, rk, vec_ok);
+        else if (elem == KAM_U16)
+            thermo_prepass_kernel<uint16_t><<<n, 256, 0, st>>>((const uint16_t *)d_x, n, d, ld, dpad, levels, op, rk, vec_ok);
+        else
+            thermo_prepass_kernel<uint32_t><<<n, 256, 0, st>>>((const uint32_t *)d_x, n, d, ld, dpad, levels, op, rk, vec_ok);
+        KAM_CUDA(cudaGetLastError());
+    }
+    out->op = op;
+    out->rk = rk;
+    out->n = n;
+    out->levels = levels;
+    out->d = d;
+    return KAM_OK;
+}
+
+int kam_thermo_pairs(const ThermoOp &A, const ThermoOp &B, bool tri, uint32_t row_begin, uint32_t row_end,
+                     uint32_t *d_manhat, float *d_info, uint64_t out_ld, cudaStream_t st) {
+    if (A.n == 0 || B.n == 0 || row_begin >= row_end) return KAM_OK;
+    const uint64_t dp = dpad_of(A.d);
+    const uint32_t T = A.levels < B.levels ? A.levels : B.levels;   // (callers encode both with the same T)
+    GramGeom gg;
+    gg.n_a = A.n;
+    gg.n_b = B.n;
+    gg.row_begin = row_begin;
+    gg.row_end = row_end < A.n ? row_end : A.n;
+    gg.tri = tri ? 1u : 0u;
+    gg.ld = out_ld;
+    gg.rk_a = A.rk;
+    gg.rk_b = B.rk;
+    int rc;
+    if (d_manhat) {
+        GramOut go;
+        go.euclid = go.cosine = go.pearson = nullptr;
+        go.manhat = d_manhat;
+        // the operands may carry different numbers of levels: each side is addressed with its own pitch only when
+        // they agree; otherwise the common prefix of levels is used (a count above T on one side is a caller error)
+        if (A.levels != B.levels) {
+            kam_set_error("kam_thermo_pairs: operands encoded with different numbers of levels");
+            return KAM_E_INVALID;
+        }
+        if ((rc = gram_block(A.op, B.op, true, A.d, gg, go, 0, st, (uint64_t)T * dp, (uint64_t)T * dp))) return rc;
+    }
+    if (d_info) {
+        GramOut go;
+        go.euclid = go.cosine = go.pearson = nullptr;
+        go.info = d_info;
+        if (A.levels != B.levels) {
+            kam_set_error("kam_thermo_pairs: operands encoded with different numbers of levels");
+            return KAM_E_INVALID;
+        }
+        if ((rc = gram_block(A.op, B.op, true, A.d, gg, go, 0, st, dp, (uint64_t)T * dp))) return rc;   // level 1 only
+    }
+    return KAM_OK;
+}
 
 extern "C" {
 

@@ -376,71 +376,84 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
     handles = [bytes(infos[r, 24:].tolist()) for r in range(world)]
     mark("prepared")
 
-    # 3. statistics of all B rows (needed complete at launch: a few KB per shard, pulled first), arrival flags
-    row_b = dpad * esz
-    tile_b = 256 * row_b
-    ready_tiles = int(os.environ.get("KAM_RING_CHUNK_TILES", "0")) or max(1, (32 << 20) // tile_b)
-    chunk_rows = 256 * ready_tiles
-    n_chunks = (max(n_b, 1) + chunk_rows - 1) // chunk_rows
-    stats = torch.empty((2, max(n_b, 1)), dtype=torch.int64, device=dev)
-    ready = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
-    local_chunks = n_loc // chunk_rows if n_b > n_loc else n_chunks   # chunks made of own rows only
-    if local_chunks:
-        ready[:local_chunks] = 1
-    st = _peer_state(dev)
-    if st.get("stream") is None:
-        st["stream"], st["stream2"] = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    side, side2 = st["stream"], st["stream2"]
-    for sd in (side, side2):
-        sd.wait_stream(cur)          # the flags are zeroed, the statistics buffer exists
-    pieces_stats, pieces = [], []
-    S_b, G_b = stats[0].data_ptr(), stats[1].data_ptr()
-    for e in plan:
-        s0, s1 = e["src_rows"]
-        b0 = e["b_rows"][0]
-        peer = base if e["src"] == rank else _peer_open(lib, dev, e["src"], handles[e["src"]])
-        g_src, rows_src = header(counts[e["src"]])
-        if s1 > s0:
-            pieces_stats.append((S_b + b0 * 8, peer + s0 * 8, (s1 - s0) * 8, _lib.KAM_PEER_NO_FLAG))
-            pieces_stats.append((G_b + b0 * 8, peer + g_src + s0 * 8, (s1 - s0) * 8, _lib.KAM_PEER_NO_FLAG))
-        e["_peer_rows"] = peer + rows_src
-    if n_loc == 0:
-        pieces_stats = []            # a rank without rows computes nothing: it only serves its peers
-    for c in range(local_chunks, n_chunks if n_loc else 0):
-        lo, hi = c * chunk_rows, min((c + 1) * chunk_rows, n_b)
-        for e in plan[1:]:
-            b0, b1 = e["b_rows"]
-            x0, x1 = max(lo, b0), min(hi, b1)
-            if x1 > x0:
-                pieces.append((base + rows_off + x0 * row_b, e["_peer_rows"] + (e["src_rows"][0] + x0 - b0) * row_b,
-                               (x1 - x0) * row_b, c))
-        if not pieces or pieces[-1][3] != c:
-            pieces.append((0, 0, 0, c))                              # nothing to pull: the flag alone
-
-    def pull(plist, streams):
-        if not plist:
-            return
-        arr = (_lib.PeerPiece * len(plist))()
-        for i, (dst, src, nbytes, chunk) in enumerate(plist):
-            arr[i].d_dst, arr[i].d_src, arr[i].bytes, arr[i].chunk = dst, src, nbytes, chunk
-        sp = (ctypes.c_void_p * len(streams))(*[sd.cuda_stream for sd in streams])
-        with torch.cuda.device(dev):
-            _lib.check(lib.kam_peer_pull(arr, len(plist), ready.data_ptr(), sp, len(streams)))
-
-    pull(pieces_stats, [side])
-    got_stats = torch.cuda.Event()
-    got_stats.record(side)
-    side2.wait_event(got_stats)      # (keeps the two copy streams' first chunks behind the small transfers)
-
-    # 4. outputs and the one launch; then the chunk transfers it waits for
+    # 3. outputs (their fill runs while the host prepares the transfers), then the transfer lists: statistics of
+    #    all B rows (needed complete at launch: a few KB per shard, pulled first) and the operand chunks with
+    #    their arrival flags.  Lists, flags and the statistics buffer are kept per geometry between calls.
     outs, ptrs = {}, {}
     for m in metrics:
         t = torch.empty((max(n_loc, 1), max(n_b, 1)), dtype=torch.float32, device=dev)
         t[:, :n_loc].zero_()         # the triangular head keeps zeros on and below its diagonal
         outs[m], ptrs[m] = t, t.data_ptr()
     ws = torch.empty(lib.kam_gram_block_workspace_bytes(n_loc, n_b), dtype=torch.uint8, device=dev)
-    segs = fused_segments(plan)
-    seg_arr = (ctypes.c_uint32 * (4 * len(segs)))(*[v for sg in segs for v in sg])
+    row_b = dpad * esz
+    tile_b = 256 * row_b
+    ready_tiles = int(os.environ.get("KAM_RING_CHUNK_TILES", "0")) or max(1, (32 << 20) // tile_b)
+    st = _peer_state(dev)
+    if st.get("stream") is None:
+        st["stream"], st["stream2"] = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    side, side2 = st["stream"], st["stream2"]
+    key = (tuple(counts), tuple(handles), kind, d, base, ready_tiles, rank)
+    fc = st.get("fused")
+    if fc is None or fc["key"] != key:
+        chunk_rows = 256 * ready_tiles
+        n_chunks = (max(n_b, 1) + chunk_rows - 1) // chunk_rows
+        local_chunks = n_loc // chunk_rows if n_b > n_loc else n_chunks   # chunks made of own rows only
+        stats = torch.empty((2, max(n_b, 1)), dtype=torch.int64, device=dev)
+        ready0 = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
+        ready0[:local_chunks] = 1
+        pieces_stats, pieces = [], []
+        S_b, G_b = stats[0].data_ptr(), stats[1].data_ptr()
+        for e in plan:
+            s0, s1 = e["src_rows"]
+            b0 = e["b_rows"][0]
+            peer = base if e["src"] == rank else _peer_open(lib, dev, e["src"], handles[e["src"]])
+            g_src, rows_src = header(counts[e["src"]])
+            if s1 > s0 and n_loc:    # (a rank without rows computes nothing: it only serves its peers)
+                pieces_stats.append((S_b + b0 * 8, peer + s0 * 8, (s1 - s0) * 8, _lib.KAM_PEER_NO_FLAG))
+                pieces_stats.append((G_b + b0 * 8, peer + g_src + s0 * 8, (s1 - s0) * 8, _lib.KAM_PEER_NO_FLAG))
+            e["_peer_rows"] = peer + rows_src
+        for c in range(local_chunks, n_chunks if n_loc else 0):
+            lo, hi = c * chunk_rows, min((c + 1) * chunk_rows, n_b)
+            for e in plan[1:]:
+                b0, b1 = e["b_rows"]
+                x0, x1 = max(lo, b0), min(hi, b1)
+                if x1 > x0:
+                    pieces.append((base + rows_off + x0 * row_b,
+                                   e["_peer_rows"] + (e["src_rows"][0] + x0 - b0) * row_b, (x1 - x0) * row_b, c))
+            if not pieces or pieces[-1][3] != c:
+                pieces.append((0, 0, 0, c))                          # nothing to pull: the flag alone
+
+        def as_array(plist):
+            arr = (_lib.PeerPiece * max(len(plist), 1))()
+            for i, (dst, src, nbytes, chunk) in enumerate(plist):
+                arr[i].d_dst, arr[i].d_src, arr[i].bytes, arr[i].chunk = dst, src, nbytes, chunk
+            return arr, len(plist)
+
+        segs = fused_segments(plan)
+        fc = st["fused"] = {"key": key, "stats": stats, "ready0": ready0, "ready": torch.empty_like(ready0),
+                            "pieces_stats": as_array(pieces_stats), "pieces": as_array(pieces), "segs": segs,
+                            "seg_arr": (ctypes.c_uint32 * (4 * len(segs)))(*[v for sg in segs for v in sg]),
+                            "chunks": n_chunks - local_chunks, "chunk_bytes": chunk_rows * row_b}
+    ready, segs, seg_arr = fc["ready"], fc["segs"], fc["seg_arr"]
+    S_b, G_b = fc["stats"][0].data_ptr(), fc["stats"][1].data_ptr()
+    ready.copy_(fc["ready0"])        # (the launch of the call before has finished: every call ends synchronised)
+    for sd in (side, side2):
+        sd.wait_stream(cur)          # the flags are reset, the statistics buffer exists
+
+    def pull(pieces_n, streams):
+        arr, n_p = pieces_n
+        if not n_p:
+            return
+        sp = (ctypes.c_void_p * len(streams))(*[sd.cuda_stream for sd in streams])
+        with torch.cuda.device(dev):
+            _lib.check(lib.kam_peer_pull(arr, n_p, ready.data_ptr(), sp, len(streams)))
+
+    pull(fc["pieces_stats"], [side])
+    got_stats = torch.cuda.Event()
+    got_stats.record(side)
+    side2.wait_event(got_stats)      # (keeps the two copy streams' first chunks behind the small transfers)
+
+    # 4. the one launch; then the chunk transfers it waits for
     mark("wait_stats")
     cur.wait_event(got_stats)
     mark("block")
@@ -450,7 +463,7 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
                                           d, 1, seg_arr, len(segs), ready.data_ptr(), ready_tiles, mask,
                                           int(euclid_on_freq), ptrs.get("euclid"), ptrs.get("cosine"),
                                           ptrs.get("pearson"), max(n_b, 1), 0, ws.data_ptr(), ws.numel(), stream))
-    pull(pieces, [side, side2])
+    pull(fc["pieces"], [side, side2])
     mark("end")
     cur.synchronize()
     cur.wait_stream(side)
@@ -482,8 +495,8 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
                 t["blocks_ms"].append(round(dt, 3))
         t.update(sm_reserve=0, transport="peer (fused: one launch, chunk flags)",
                  operand="uint8" if kind == _lib.KAM_GRAM_U8 else "fp16",
-                 recv_bytes=int((n_b - n_loc) * row_b), chunks=int(n_chunks - local_chunks),
-                 chunk_bytes=int(chunk_rows * row_b), tiles_segments=[list(sg) for sg in segs])
+                 recv_bytes=int((n_b - n_loc) * row_b), chunks=int(fc["chunks"]), chunk_bytes=int(fc["chunk_bytes"]),
+                 tiles_segments=[list(sg) for sg in segs])
         timing.update(t)
     return out_blocks, counts
 
@@ -502,8 +515,12 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
 
     transport: how a shard reaches the rank that needs it.
       "peer" (default; ranks of one NVLink box): the owner keeps its operand rows and row statistics in a
-          buffer exported over CUDA IPC (kam_peer_*), the reader PULLS them with a copy-engine transfer on a
-          side stream -- no SM is involved, so the persistent cluster kernel keeps all 148 SMs;
+          buffer exported over CUDA IPC (kam_peer_*), the reader PULLS them with copy-engine transfers on
+          side streams -- no SM is involved, so the persistent cluster kernel keeps all 148 SMs.  By default the
+          exchange is FUSED into the kernel (_gram_ring_fused: one kam_gram_fused launch per rank, the shards
+          arrive chunk by chunk while it runs, its TMA producers wait on per-chunk flags; the block two ranks
+          share is split along whole 256-row tiles and the second rank's half comes back as a transposed view);
+          KAM_RING_FUSED=0 keeps one launch per step, each waiting for its whole shard;
       "nccl": isend/irecv pairs; their kernels need SMs, `sm_reserve` of which (default 16) the Gram kernel
           leaves free while transfers are in flight.
     KAM_RING_TRANSPORT / KAM_RING_SM_RESERVE in the environment override the defaults.

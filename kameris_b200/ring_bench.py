@@ -95,8 +95,9 @@ def run_gram_ring(dist_pg, dev, rank, world, tf_peak, reps=2, n_total=N_TOTAL):
             "n_total": n_all, "d": d, "pairs": pairs, "metrics": "cosine+pearson", "check_cosine_0_1": chk,
             "achieved": flops / (best * 1e-3) / 1e12 / world, "peak": i8_peak, "unit_roofline": "TFLOP/s per GPU",
             "frac": flops / (best * 1e-3) / 1e12 / world / i8_peak,
-            "kernel": "gram_pair_kernel<i8> (tcgen05 cta_group::2) + ring exchange of operand shards",
-            "includes": "operand pre-pass, statistics all-gather, ring send/recv, every block's kernel", **tim}
+            "kernel": "gram_pair_kernel<i8> (tcgen05 cta_group::2), the exchange fused in: one launch per rank, operand "
+                      "chunks pulled from peer memory by the copy engines, per-chunk arrival flags awaited by the TMA producers",
+            "includes": "operand pre-pass, the two small all-gathers, every transfer, the launch", **tim}
 
 
 def run_manhat_sharded(dist_pg, dev, rank, world, reps=2, n_total=32768, k=6):
