@@ -226,16 +226,18 @@ int kam_fasta_read_files(const char *const *paths, uint32_t n, const uint64_t *f
  * computes (all j>i); entries of other rows are left untouched.
  * ------------------------------------------------------------------------------------------- */
 /* manhat and info on the tensor cores (the reference's two metrics: generation_dists row lambda, manhat body
- * @0x10001bd87, info body @0x10001bab5).  Neither is a contraction as written, but for counts up to T
- *     sum_e |a_e - b_e| = sum(a) + sum(b) - 2 sum_e min(a_e, b_e),   min(a_e, b_e) = sum_{t=1..T} [a_e >= t][b_e >= t]
+ * @0x10001bd87, info body @0x10001bab5).  Neither is a contraction as written, but
+ *     sum_e |a_e - b_e| = sum(a) + sum(b) - 2 sum_e min(a_e, b_e),   min(a_e, b_e) = sum_{t >= 1} [a_e >= t][b_e >= t]
  * so the pairwise min-sums are an exact integer Gram (tcgen05 kind::i8, int32 accumulators) of "thermometer" rows
- * of T x d indicator bytes, and info's |supp_a & supp_b| is the Gram of level 1 alone.  The same uint32 sums
- * (mod 2^32) and the same float32 formula come out, bit for bit.  Taken when the largest count is <= 16, the shape
- * fills 256 x 256 tiles (>= 512 rows, >= 128 columns) and the workspace holds the T-level operand rows
- * (kam_manhattan_workspace_bytes covers T <= 4, kam_manhattan_workspace_bytes_levels any T); otherwise the
- * CUDA-core tile kernel below runs (VABSDIFF4 / VABSDIFF / POPC).  kam_dist_set_tensor: 0 = never, 1 = as described
- * (default), 2 = for every shape (tests). */
-size_t kam_manhattan_workspace_bytes_levels(uint32_t rows, uint64_t d, uint32_t max_count);
+ * of indicator bytes -- column e gets as many bytes as the largest count any row holds there, so a row is
+ * K = sum of the column maxima bytes long (2-3 x 4^k for k-mer counts) -- and info's |supp_a & supp_b| is the Gram
+ * of the presence bytes.  The same uint32 sums (mod 2^32) and the same float32 formula come out, bit for bit.
+ * Taken when every count is <= 255, K <= 12 d, the shape fills 256 x 256 tiles (>= 512 rows, >= 128 columns) and
+ * the workspace holds the operand rows (kam_manhattan_workspace_bytes covers K <= 4 d,
+ * kam_manhattan_workspace_bytes_levels(rows, d, a) K <= a d); otherwise the CUDA-core tile kernel below runs
+ * (VABSDIFF4 / VABSDIFF / POPC).  kam_dist_set_tensor: 0 = never, 1 = as described (default), 2 = for every shape
+ * and any K that fits (tests). */
+size_t kam_manhattan_workspace_bytes_levels(uint32_t rows, uint64_t d, uint32_t avg_levels);
 void kam_dist_set_tensor(int mode);
 /* The manhattan entry points synchronise `stream` once (they look at the largest element to pick
  * the tensor path or the 4-elements-per-instruction byte path when every count is <= 255).

@@ -79,18 +79,31 @@ int kam_float_prepass(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_
 int kam_float_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin,
                        uint32_t row_end, RowK *rk, GramOut go, cudaStream_t st);
 
-// manhat / info on the tensor cores (gram.cu): thermometer-coded operand rows of one matrix
+// manhat / info on the tensor cores (gram.cu): thermometer-coded operand rows of one matrix.  Column e of the
+// input owns the K positions [off[e], off[e + 1]) of an operand row; byte t of them is (c[e] > t).  off is the
+// running sum of the per-column maxima over BOTH matrices of a product, so a column costs as many MACs as its
+// largest count anywhere (a few hot k-mers do not inflate the other 4^k columns); info uses one byte per column.
 struct ThermoOp {
-    const uint8_t *op = nullptr;   // [n][levels * dpad]: byte e of level t (1-based, at (t-1) * dpad) = (c[e] >= t)
+    const uint8_t *op = nullptr;   // [n][kpad]
     const RowK *rk = nullptr;      // a = bits of sum(c), q = bits of nnz(c)
-    uint32_t n = 0, levels = 0;
-    uint64_t d = 0;
+    uint32_t n = 0;
+    uint64_t d = 0, kpad = 0;      // kpad: row length in bytes (a multiple of 128)
 };
-size_t kam_thermo_bytes(uint32_t n, uint64_t d, uint32_t levels);
-int kam_thermo_prepare(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t levels, void *d_ws,
-                       ThermoOp *out, cudaStream_t st);
+size_t kam_thermo_cols_bytes(uint64_t d);                       // colmax[d] + off[d + 1] + 2 statistics words
+size_t kam_thermo_bytes(uint32_t n, uint64_t kpad);             // RowK[n] + operand rows
+uint64_t kam_thermo_kpad(uint64_t k_total);
+// colmax[e] = max(colmax[e], max_r x[r][e])  (the caller zeroes colmax)
+int kam_thermo_colmax(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t *colmax, cudaStream_t st);
+// off = exclusive running sum of colmax (d + 1 entries); h_stats = {largest count, sum of the maxima}; synchronises
+int kam_thermo_layout(const uint32_t *colmax, uint64_t d, uint32_t *off, unsigned long long *d_stats,
+                      unsigned long long (&h_stats)[2], cudaStream_t st);
+int kam_thermo_encode(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, const uint32_t *off,
+                      uint64_t kpad, void *d_ws, ThermoOp *out, cudaStream_t st);
+// info: presence bytes, one per column (kpad = d rounded up to 128)
+int kam_thermo_presence(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, void *d_ws, ThermoOp *out,
+                        cudaStream_t st);
 // rows [row_begin, row_end) of A against all rows of B (tri: A and B are the same operand, pairs j > i, packed
-// triangle when out_ld == 0); `info` uses level 1 only
+// triangle when out_ld == 0); exactly one of d_manhat / d_info
 int kam_thermo_pairs(const ThermoOp &A, const ThermoOp &B, bool tri, uint32_t row_begin, uint32_t row_end,
                      uint32_t *d_manhat, float *d_info, uint64_t out_ld, cudaStream_t st);
 

@@ -341,7 +341,10 @@ int max_of(const void *x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_
 // 1 = when the shape fills tiles of 256 x 256 pairs and the largest count is small (default), 2 = whenever the
 // operands can be encoded (tests: the small golden cases of the reference's machine code run through it too)
 int g_tensor_mode = 1;
-constexpr uint32_t THERMO_MAX_LEVELS = 16;   // break-even against VABSDIFF4 is ~25 levels; the operand grows with it
+// the tensor path pays sum-of-column-maxima MACs per pair where the byte kernel pays d VABSDIFF4 lane-operations:
+// it wins up to ~20 bytes per column on average; beyond THERMO_MAX_AVG (and always above a count of 255) the
+// CUDA-core kernels run
+constexpr uint32_t THERMO_MAX_AVG = 12;
 
 inline bool thermo_shape_ok(uint32_t rows, uint32_t cols) {
     return g_tensor_mode == 2 || (g_tensor_mode == 1 && rows >= 512 && cols >= 128);
@@ -362,18 +365,22 @@ int kam_int_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t
 
 extern "C" {
 
+static size_t thermo_need(uint32_t rows, uint64_t d, uint64_t avg_levels) {   // flag + column arrays + operand rows
+    return 1024 + kam_thermo_cols_bytes(d) + kam_thermo_bytes(rows, kam_thermo_kpad(avg_levels * d));
+}
+
 size_t kam_manhattan_workspace_bytes(uint32_t rows_total, uint64_t d) {
     // worst case: one uint32 word per element, plus padding for two operands and the flag word
-    // ... and never less than the tensor path needs for counts up to 4 (thermometer rows of 4 levels); a caller
-    // that wants it for larger counts passes kam_manhattan_workspace_bytes_levels(rows, d, max count)
+    // ... and never less than the tensor path needs while the column maxima sum to 4 d (thermometer rows of 4 d
+    // bytes); a caller that wants it for heavier data passes kam_manhattan_workspace_bytes_levels(rows, d, average)
     const size_t classic = xt_bytes(rows_total, (uint32_t)d) + 2 * 4096 + 1024;
-    const size_t tensor = kam_thermo_bytes(rows_total, d, 4) + 1024;
+    const size_t tensor = thermo_need(rows_total, d, 4);
     return classic > tensor ? classic : tensor;
 }
 
-size_t kam_manhattan_workspace_bytes_levels(uint32_t rows_total, uint64_t d, uint32_t max_count) {
-    const uint32_t levels = max_count < 1 ? 1 : max_count > THERMO_MAX_LEVELS ? THERMO_MAX_LEVELS : max_count;
-    const size_t base = kam_manhattan_workspace_bytes(rows_total, d), tensor = kam_thermo_bytes(rows_total, d, levels) + 1024;
+size_t kam_manhattan_workspace_bytes_levels(uint32_t rows_total, uint64_t d, uint32_t avg_levels) {
+    const uint32_t levels = avg_levels < 1 ? 1 : avg_levels > THERMO_MAX_AVG ? THERMO_MAX_AVG : avg_levels;
+    const size_t base = kam_manhattan_workspace_bytes(rows_total, d), tensor = thermo_need(rows_total, d, levels);
     return base > tensor ? base : tensor;
 }
 
@@ -405,16 +412,27 @@ int kam_manhattan_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_
     uint32_t *flag = (uint32_t *)d_ws;
     uint32_t *xt = (uint32_t *)((char *)d_ws + 1024);
     uint32_t mx = 0;
-    int rc = max_of(d_x, elem, n, d, ld, flag, &mx, st);
-    if (rc) return rc;
-    {   // small counts: sum |a - b| = S_a + S_b - 2 sum min(a, b) on the tensor cores (thermometer rows)
-        const uint32_t levels = mx ? mx : 1;
-        if (levels <= THERMO_MAX_LEVELS && thermo_shape_ok(n, n) && (uint64_t)levels * d < (1ull << 31) &&
-            ws_bytes >= 1024 + kam_thermo_bytes(n, d, levels)) {
+    int rc;
+    if (thermo_shape_ok(n, n) && ws_bytes >= thermo_need(n, d, 1)) {
+        // small counts: sum |a - b| = S_a + S_b - 2 sum min(a, b) on the tensor cores (thermometer rows, gram.cu).
+        // The per-column maxima decide the layout (and give the largest count the other paths need).
+        uint32_t *colmax = (uint32_t *)((char *)d_ws + 1024), *off = colmax + d;
+        unsigned long long *stats = (unsigned long long *)(off + d + 2);
+        unsigned long long hs[2] = {0, 0};
+        KAM_CUDA(cudaMemsetAsync(colmax, 0, d * 4, st));
+        if ((rc = kam_thermo_colmax(d_x, elem, n, d, ld, colmax, st)) || (rc = kam_thermo_layout(colmax, d, off, stats, hs, st)))
+            return rc;
+        mx = (uint32_t)(hs[0] > 0xffffffffull ? 0xffffffffull : hs[0]);
+        const uint64_t kpad = kam_thermo_kpad(hs[1]);
+        const size_t need = 1024 + kam_thermo_cols_bytes(d) + kam_thermo_bytes(n, kpad);
+        if (mx <= 255 && hs[1] < (1ull << 31) && need <= ws_bytes && (g_tensor_mode == 2 || hs[1] <= (uint64_t)THERMO_MAX_AVG * d)) {
             ThermoOp op;
-            if ((rc = kam_thermo_prepare(d_x, elem, n, d, ld, levels, (char *)d_ws + 1024, &op, st))) return rc;
+            if ((rc = kam_thermo_encode(d_x, elem, n, d, ld, off, kpad, (char *)d_ws + 1024 + kam_thermo_cols_bytes(d), &op, st)))
+                return rc;
             return kam_thermo_pairs(op, op, true, row_begin, row_end, d_tri, nullptr, 0, st);
         }
+    } else if ((rc = max_of(d_x, elem, n, d, ld, flag, &mx, st))) {
+        return rc;
     }
     if (mx <= 255) {   // every count fits a byte: four elements per VABSDIFF4
         if ((rc = convert_dispatch<OP_SAD8X4>(d_x, elem, n, d, ld, xt, st))) return rc;
@@ -438,18 +456,27 @@ int kam_manhattan_rect(const void *d_x, const void *d_y, int elem, uint32_t m, u
     uint32_t *flag = (uint32_t *)d_ws;
     uint32_t mx = 0, my = 0;
     int rc;
-    if ((rc = max_of(d_x, elem, m, d, ldx, flag, &mx, st)) || (rc = max_of(d_y, elem, c, d, ldy, flag, &my, st))) return rc;
-    {
-        const uint32_t top = mx > my ? mx : my, levels = top ? top : 1;
-        const size_t need_x = kam_thermo_bytes(m, d, levels);
-        if (levels <= THERMO_MAX_LEVELS && thermo_shape_ok(m, c) && (uint64_t)levels * d < (1ull << 31) &&
-            ws_bytes >= 1024 + need_x + kam_thermo_bytes(c, d, levels)) {
+    if (thermo_shape_ok(m, c) && ws_bytes >= thermo_need(m, d, 1) + kam_thermo_bytes(c, kam_thermo_kpad(d))) {
+        uint32_t *colmax = (uint32_t *)((char *)d_ws + 1024), *off = colmax + d;
+        unsigned long long *stats = (unsigned long long *)(off + d + 2);
+        unsigned long long hs[2] = {0, 0};
+        KAM_CUDA(cudaMemsetAsync(colmax, 0, d * 4, st));
+        if ((rc = kam_thermo_colmax(d_x, elem, m, d, ldx, colmax, st)) || (rc = kam_thermo_colmax(d_y, elem, c, d, ldy, colmax, st)) ||
+            (rc = kam_thermo_layout(colmax, d, off, stats, hs, st)))
+            return rc;
+        mx = my = (uint32_t)(hs[0] > 0xffffffffull ? 0xffffffffull : hs[0]);
+        const uint64_t kpad = kam_thermo_kpad(hs[1]);
+        const size_t at_x = 1024 + kam_thermo_cols_bytes(d), at_y = at_x + kam_thermo_bytes(m, kpad);
+        if (mx <= 255 && hs[1] < (1ull << 31) && at_y + kam_thermo_bytes(c, kpad) <= ws_bytes &&
+            (g_tensor_mode == 2 || hs[1] <= (uint64_t)THERMO_MAX_AVG * d)) {
             ThermoOp ox, oy;
-            if ((rc = kam_thermo_prepare(d_x, elem, m, d, ldx, levels, (char *)d_ws + 1024, &ox, st)) ||
-                (rc = kam_thermo_prepare(d_y, elem, c, d, ldy, levels, (char *)d_ws + 1024 + need_x, &oy, st)))
+            if ((rc = kam_thermo_encode(d_x, elem, m, d, ldx, off, kpad, (char *)d_ws + at_x, &ox, st)) ||
+                (rc = kam_thermo_encode(d_y, elem, c, d, ldy, off, kpad, (char *)d_ws + at_y, &oy, st)))
                 return rc;
             return kam_thermo_pairs(ox, oy, false, 0, m, d_out, nullptr, c, st);
         }
+    } else if ((rc = max_of(d_x, elem, m, d, ldx, flag, &mx, st)) || (rc = max_of(d_y, elem, c, d, ldy, flag, &my, st))) {
+        return rc;
     }
     const bool bytes = mx <= 255 && my <= 255;
     const uint32_t kw = kw_of(bytes ? OP_SAD8X4 : OP_SAD32, d);
@@ -489,7 +516,7 @@ int kam_manhattan_rect_f32(const void *d_x, int elem_x, const float *d_y, uint32
 
 static size_t info_classic_bytes(uint32_t n, uint64_t d) { return xt_bytes(n, kw_of(OP_JACC, d)) + 1024; }
 size_t kam_info_workspace_bytes(uint32_t n, uint64_t d) {   // presence bits, or presence BYTES for the tensor path
-    const size_t classic = info_classic_bytes(n, d), tensor = kam_thermo_bytes(n, d, 1) + 1024;
+    const size_t classic = info_classic_bytes(n, d), tensor = kam_thermo_bytes(n, kam_thermo_kpad(d)) + 1024;
     return classic > tensor ? classic : tensor;
 }
 
@@ -506,9 +533,9 @@ int kam_info_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld,
     cudaStream_t st = (cudaStream_t)stream;
     if (row_end > n) row_end = n;
     // |supp_i & supp_j| is the Gram of the presence vectors: tensor cores (gram.cu: level 1 of the thermometer rows)
-    if (thermo_elem_ok(elem) && thermo_shape_ok(n, n) && ws_bytes >= 1024 + kam_thermo_bytes(n, d, 1)) {
+    if (thermo_elem_ok(elem) && thermo_shape_ok(n, n) && ws_bytes >= 1024 + kam_thermo_bytes(n, kam_thermo_kpad(d))) {
         ThermoOp op;
-        int rc = kam_thermo_prepare(d_x, elem, n, d, ld, 1, (char *)d_ws + 1024, &op, st);
+        int rc = kam_thermo_presence(d_x, elem, n, d, ld, (char *)d_ws + 1024, &op, st);
         if (rc) return rc;
         return kam_thermo_pairs(op, op, true, row_begin, row_end, nullptr, d_tri, 0, st);
     }

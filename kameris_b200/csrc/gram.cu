@@ -741,19 +741,22 @@ __global__ void __launch_bounds__(256) gram_limb_combine_kernel(const int *__res
 }
 
 // ---- thermometer operands: the reference's two metrics, `manhat` and `info`, as contractions ------------------
-// sum_e |a_e - b_e| = sum(a) + sum(b) - 2 sum_e min(a_e, b_e), and for counts up to T
-// min(a_e, b_e) = sum_{t=1..T} [a_e >= t][b_e >= t]: an integer Gram of rows of T * d indicator bytes.  Level 1 is
-// the presence vector, whose Gram is |supp_a & supp_b| -- all `info` needs (union = nnz_a + nnz_b - intersection).
-// k-mer counts of short reads and of kilobase genomes at k = 9 rarely pass 3, so T is small and kind::i8 tcgen05
-// runs T * d MACs per pair at ~25x the CUDA cores' VABSDIFF4 / POPC rate per element.  One CTA per row.
+// sum_e |a_e - b_e| = sum(a) + sum(b) - 2 sum_e min(a_e, b_e), and min(a_e, b_e) = sum_{t >= 1} [a_e >= t][b_e >= t]:
+// an integer Gram of rows of indicator bytes.  Column e gets as many bytes as the largest count ANY row holds there
+// (colmax[e]; K = sum of the column maxima, typically 2-3 x 4^k for k-mer counts: a few hot k-mers cost a few extra
+// bytes, not a level for every column).  One byte per column, (c_e >= 1), is the presence vector, whose Gram is
+// |supp_a & supp_b| -- all `info` needs (union = nnz_a + nnz_b - intersection).  kind::i8 tcgen05 then does K MACs
+// per pair where the CUDA cores do 4^k VABSDIFF4 / POPC lane-operations at ~1/25 of the rate.
+
+// presence bytes (info): one CTA per row, 16 columns per thread and step
 template <typename T>
-__global__ void __launch_bounds__(256) thermo_prepass_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
-                                                             uint64_t dpad, uint32_t levels, uint8_t *__restrict__ op,
-                                                             RowK *__restrict__ rk, int vec_ok) {
+__global__ void __launch_bounds__(256) thermo_presence_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
+                                                              uint64_t dpad, uint8_t *__restrict__ op,
+                                                              RowK *__restrict__ rk, int vec_ok) {
     __shared__ unsigned long long red[2][8];
     const uint32_t row = blockIdx.x;
     const T *xr = x + (uint64_t)row * ld;
-    uint8_t *out = op + (uint64_t)row * levels * dpad;
+    uint8_t *out = op + (uint64_t)row * dpad;
     unsigned long long s = 0, nz = 0;
     for (uint64_t e = (uint64_t)threadIdx.x * 16; e < dpad; e += 256 * 16) {   // dpad is a multiple of 128
         unsigned c[16];
@@ -769,19 +772,18 @@ __global__ void __launch_bounds__(256) thermo_prepass_kernel(const T *__restrict
 #pragma unroll
             for (int i = 0; i < 16; ++i) c[i] = e + i < d ? (unsigned)xr[e + i] : 0u;
         }
+        uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            s += c[i];
-            nz += c[i] != 0;
-        }
-        for (uint32_t t = 1; t <= levels; ++t) {
-            uint32_t w[4];
+        for (int q = 0; q < 4; ++q) {
+            w[q] = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                w[q] = (c[4 * q] >= t ? 1u : 0u) | (c[4 * q + 1] >= t ? 0x100u : 0u) | (c[4 * q + 2] >= t ? 0x10000u : 0u) |
-                       (c[4 * q + 3] >= t ? 0x1000000u : 0u);
-            *reinterpret_cast<uint4 *>(out + (uint64_t)(t - 1) * dpad + e) = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int i = 0; i < 4; ++i) {
+                s += c[4 * q + i];
+                nz += c[4 * q + i] != 0;
+                w[q] |= (c[4 * q + i] != 0 ? 1u : 0u) << (8 * i);
+            }
         }
+        *reinterpret_cast<uint4 *>(out + e) = make_uint4(w[0], w[1], w[2], w[3]);
     }
     s = warp_sum64(s);
     nz = warp_sum64(nz);
@@ -801,6 +803,173 @@ __global__ void __launch_bounds__(256) thermo_prepass_kernel(const T *__restrict
         r.a = __longlong_as_double((long long)ts);   // bit patterns of the integers (GramOut::manhat / info)
         r.q = __longlong_as_double((long long)tz);
         rk[row] = r;
+    }
+}
+
+// per-column maxima: a thread owns VEC adjacent columns (one 4-byte load per row), a CTA a slab of rows
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) thermo_colmax_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
+                                                            uint32_t rows_per_cta, uint32_t *__restrict__ colmax) {
+    const uint64_t e = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * VEC;
+    if (e >= d) return;
+    const uint32_t r0 = blockIdx.y * rows_per_cta, r1 = r0 + rows_per_cta < n ? r0 + rows_per_cta : n;
+    unsigned m[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) m[i] = 0;
+    const T *p = x + (uint64_t)r0 * ld + e;
+#pragma unroll 8
+    for (uint32_t r = r0; r < r1; ++r, p += ld) {
+        if constexpr (VEC == 1) {
+            m[0] = max(m[0], (unsigned)__ldg(p));
+        } else {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(p));
+            if constexpr (VEC == 2) {
+                m[0] = max(m[0], w & 0xffffu);
+                m[1] = max(m[1], w >> 16);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) m[i] = max(m[i], (w >> (8 * i)) & 0xffu);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+        if (m[i] && e + i < d) atomicMax(&colmax[e + i], m[i]);
+}
+
+// off[e] = sum of colmax[0..e) (d + 1 entries), the largest count and the total; ONE CTA (d is 4^k: at most a few MB)
+__global__ void __launch_bounds__(1024) thermo_scan_kernel(const uint32_t *__restrict__ colmax, uint64_t d,
+                                                           uint32_t *__restrict__ off, unsigned long long *__restrict__ stats) {
+    __shared__ unsigned long long wsum[32], step_total;
+    __shared__ unsigned wmax[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long carry = 0;
+    unsigned mx = 0;
+    for (uint64_t base = 0; base < d; base += 4096) {
+        const uint64_t e = base + (uint64_t)threadIdx.x * 4;
+        unsigned v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[i] = e + i < d ? colmax[e + i] : 0u;
+            mx = max(mx, v[i]);
+        }
+        unsigned long long t = (unsigned long long)v[0] + v[1] + v[2] + v[3], inc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = wsum[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += u;
+            }
+            wsum[lane] = winc - w;            // exclusive prefix of the warp totals
+            if (lane == 31) step_total = winc;
+        }
+        __syncthreads();
+        unsigned long long ex = carry + wsum[warp] + (inc - t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (e + i < d) off[e + i] = (uint32_t)ex;
+            ex += v[i];
+        }
+        carry += step_total;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) wmax[warp] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned m = 0;
+        for (int w = 0; w < 32; ++w) m = max(m, wmax[w]);
+        off[d] = (uint32_t)carry;
+        stats[0] = m;
+        stats[1] = carry;
+    }
+}
+
+// operand rows: a CTA takes TH_ROWS rows and walks the columns in chunks; the bytes of a chunk are composed in
+// shared memory (a column's bytes sit at off[e] - chunk origin) and leave as 16-byte stores; a chunk whose bytes do
+// not fit (very large counts) is written directly.  Also the rows' sum(c) and nnz(c).
+constexpr int TH_ROWS = 4, TH_CHUNK = 2048, TH_SB = 8192;
+template <typename T>
+__global__ void __launch_bounds__(256) thermo_encode_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
+                                                            const uint32_t *__restrict__ off, uint64_t kpad,
+                                                            uint8_t *__restrict__ op, RowK *__restrict__ rk) {
+    __shared__ __align__(16) uint8_t sbuf[TH_ROWS][TH_SB];
+    __shared__ unsigned long long red[2][TH_ROWS][8];
+    const uint32_t row0 = blockIdx.x * TH_ROWS, tid = threadIdx.x;
+    const uint32_t nrows = n - row0 < (uint32_t)TH_ROWS ? n - row0 : (uint32_t)TH_ROWS;
+    unsigned long long s[TH_ROWS], nz[TH_ROWS];
+#pragma unroll
+    for (int r = 0; r < TH_ROWS; ++r) s[r] = nz[r] = 0;
+    for (uint64_t e0 = 0; e0 < d; e0 += TH_CHUNK) {
+        const uint64_t e1 = e0 + TH_CHUNK < d ? e0 + TH_CHUNK : d;
+        const uint32_t kb = off[e0], ke = off[e1];
+        const uint32_t a0 = kb & ~15u;
+        const bool staged = ke - a0 <= (uint32_t)TH_SB;
+        for (uint64_t e = e0 + tid; e < e1; e += 256) {
+            const uint32_t o = off[e], cm = off[e + 1] - o;
+#pragma unroll
+            for (int r = 0; r < TH_ROWS; ++r) {
+                if ((uint32_t)r < nrows) {
+                    const unsigned c = (unsigned)x[(uint64_t)(row0 + r) * ld + e];
+                    s[r] += c;
+                    nz[r] += c != 0;
+                    uint8_t *dst = staged ? &sbuf[r][o - a0] : op + (uint64_t)(row0 + r) * kpad + o;
+                    for (uint32_t t = 0; t < cm; ++t) dst[t] = c > t ? 1 : 0;
+                }
+            }
+        }
+        if (staged) {
+            __syncthreads();
+            const uint32_t up = (kb + 15u) & ~15u;
+            const uint32_t head_end = up < ke ? up : ke;
+            const uint32_t tail_begin = (ke & ~15u) > head_end ? (ke & ~15u) : head_end;
+            for (uint32_t r = 0; r < nrows; ++r) {
+                uint8_t *base = op + (uint64_t)(row0 + r) * kpad;
+                for (uint32_t g = head_end + tid * 16; g < tail_begin; g += 256 * 16)
+                    *reinterpret_cast<uint4 *>(base + g) = *reinterpret_cast<const uint4 *>(&sbuf[r][g - a0]);
+                if (tid < 16) {
+                    const uint32_t p = kb + tid;
+                    if (p < head_end) base[p] = sbuf[r][p - a0];
+                } else if (tid < 32) {
+                    const uint32_t p = tail_begin + (tid - 16);
+                    if (p < ke) base[p] = sbuf[r][p - a0];
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t k_total = off[d];
+    for (uint32_t r = 0; r < nrows; ++r)
+        for (uint64_t p = (uint64_t)k_total + tid; p < kpad; p += 256) op[(uint64_t)(row0 + r) * kpad + p] = 0;
+#pragma unroll
+    for (int r = 0; r < TH_ROWS; ++r) {
+        const unsigned long long a = warp_sum64(s[r]), b = warp_sum64(nz[r]);
+        if ((tid & 31) == 0) {
+            red[0][r][tid >> 5] = a;
+            red[1][r][tid >> 5] = b;
+        }
+    }
+    __syncthreads();
+    if (tid < nrows) {
+        unsigned long long ts = 0, tz = 0;
+        for (int w = 0; w < 8; ++w) {
+            ts += red[0][tid][w];
+            tz += red[1][tid][w];
+        }
+        RowK r;
+        r.rn = r.S = r.mu = r.rp = 0.0;
+        r.a = __longlong_as_double((long long)ts);
+        r.q = __longlong_as_double((long long)tz);
+        rk[row0 + tid] = r;
     }
 }
 
@@ -1099,12 +1268,70 @@ int read_flags(const unsigned long long *d_flags, unsigned long long (&h)[3], cu
 
 }  // namespace
 
-size_t kam_thermo_bytes(uint32_t n, uint64_t d, uint32_t levels) {
-    return kam_align_up((size_t)n * sizeof(RowK), 1024) + kam_align_up((size_t)n * levels * dpad_of(d), 1024) + 1024;
+size_t kam_thermo_cols_bytes(uint64_t d) { return kam_align_up((size_t)(2 * d + 2) * 4 + 16, 1024); }
+uint64_t kam_thermo_kpad(uint64_t k_total) { return k_total ? (k_total + BK_BYTES - 1) / BK_BYTES * BK_BYTES : BK_BYTES; }
+size_t kam_thermo_bytes(uint32_t n, uint64_t kpad) {
+    return kam_align_up((size_t)n * sizeof(RowK), 1024) + kam_align_up((size_t)n * kpad, 1024) + 1024;
 }
 
-int kam_thermo_prepare(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t levels, void *d_ws,
-                       ThermoOp *out, cudaStream_t st) {
+int kam_thermo_colmax(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t *colmax, cudaStream_t st) {
+    if (n == 0) return KAM_OK;
+    const size_t esz = elem == KAM_U8 ? 1 : elem == KAM_U16 ? 2 : 4;
+    const bool vec = ((ld * esz) % 4 == 0) && (((uintptr_t)d_x & 3) == 0) && (d * esz) % 4 == 0;
+    const uint32_t per = vec ? (uint32_t)(4 / esz) : 1u;
+    const uint32_t gx = (uint32_t)((d + 256ull * per - 1) / (256ull * per));
+    uint32_t slabs = (uint32_t)kam_sm_count() * 8 / (gx ? gx : 1);
+    if (slabs < 1) slabs = 1;
+    if (slabs > (n + 63) / 64) slabs = (n + 63) / 64;       // at least 64 rows per CTA
+    if (slabs > 65535) slabs = 65535;
+    const uint32_t rows_per = (n + slabs - 1) / slabs;
+    const dim3 grid(gx, (n + rows_per - 1) / rows_per);
+    if (elem == KAM_U8) {
+        if (vec) thermo_colmax_kernel<uint8_t, 4><<<grid, 256, 0, st>>>((const uint8_t *)d_x, n, d, ld, rows_per, colmax);
+        else thermo_colmax_kernel<uint8_t, 1><<<grid, 256, 0, st>>>((const uint8_t *)d_x, n, d, ld, rows_per, colmax);
+    } else if (elem == KAM_U16) {
+        if (vec) thermo_colmax_kernel<uint16_t, 2><<<grid, 256, 0, st>>>((const uint16_t *)d_x, n, d, ld, rows_per, colmax);
+        else thermo_colmax_kernel<uint16_t, 1><<<grid, 256, 0, st>>>((const uint16_t *)d_x, n, d, ld, rows_per, colmax);
+    } else {
+        thermo_colmax_kernel<uint32_t, 1><<<grid, 256, 0, st>>>((const uint32_t *)d_x, n, d, ld, rows_per, colmax);
+    }
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+int kam_thermo_layout(const uint32_t *colmax, uint64_t d, uint32_t *off, unsigned long long *d_stats,
+                      unsigned long long (&h_stats)[2], cudaStream_t st) {
+    thermo_scan_kernel<<<1, 1024, 0, st>>>(colmax, d, off, d_stats);
+    KAM_CUDA(cudaGetLastError());
+    KAM_CUDA(cudaMemcpyAsync(h_stats, d_stats, 16, cudaMemcpyDeviceToHost, st));
+    KAM_CUDA(cudaStreamSynchronize(st));
+    return KAM_OK;
+}
+
+int kam_thermo_encode(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, const uint32_t *off,
+                      uint64_t kpad, void *d_ws, ThermoOp *out, cudaStream_t st) {
+    RowK *rk = (RowK *)d_ws;
+    uint8_t *op = (uint8_t *)d_ws + kam_align_up((size_t)n * sizeof(RowK), 1024);
+    if (n) {
+        const uint32_t grid = (n + TH_ROWS - 1) / TH_ROWS;
+        if (elem == KAM_U8)
+            thermo_encode_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)d_x, n, d, ld, off, kpad, op, rk);
+        else if (elem == KAM_U16)
+            thermo_encode_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)d_x, n, d, ld, off, kpad, op, rk);
+        else
+            thermo_encode_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)d_x, n, d, ld, off, kpad, op, rk);
+        KAM_CUDA(cudaGetLastError());
+    }
+    out->op = op;
+    out->rk = rk;
+    out->n = n;
+    out->d = d;
+    out->kpad = kpad;
+    return KAM_OK;
+}
+
+int kam_thermo_presence(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, void *d_ws, ThermoOp *out,
+                        cudaStream_t st) {
     RowK *rk = (RowK *)d_ws;
     uint8_t *op = (uint8_t *)d_ws + kam_align_up((size_t)n * sizeof(RowK), 1024);
     const uint64_t dpad = dpad_of(d);
@@ -1112,26 +1339,28 @@ int kam_thermo_prepare(const void *d_x, int elem, uint32_t n, uint64_t d, uint64
     const int vec_ok = (d % 16 == 0) && ((ld * esz) % 16 == 0) && (((uintptr_t)d_x & 15) == 0);
     if (n) {
         if (elem == KAM_U8)
-            thermo_prepass_kernel<uint8_t><<<n, 256, 0, st>>>((const uint8_t *)d_x, n, d, ld, dpad, levels, op, rk, vec_ok);
+            thermo_presence_kernel<uint8_t><<<n, 256, 0, st>>>((const uint8_t *)d_x, n, d, ld, dpad, op, rk, vec_ok);
         else if (elem == KAM_U16)
-            thermo_prepass_kernel<uint16_t><<<n, 256, 0, st>>>((const uint16_t *)d_x, n, d, ld, dpad, levels, op, rk, vec_ok);
+            thermo_presence_kernel<uint16_t><<<n, 256, 0, st>>>((const uint16_t *)d_x, n, d, ld, dpad, op, rk, vec_ok);
         else
-            thermo_prepass_kernel<uint32_t><<<n, 256, 0, st>>>((const uint32_t *)d_x, n, d, ld, dpad, levels, op, rk, vec_ok);
+            thermo_presence_kernel<uint32_t><<<n, 256, 0, st>>>((const uint32_t *)d_x, n, d, ld, dpad, op, rk, vec_ok);
         KAM_CUDA(cudaGetLastError());
     }
     out->op = op;
     out->rk = rk;
     out->n = n;
-    out->levels = levels;
     out->d = d;
+    out->kpad = dpad;
     return KAM_OK;
 }
 
 int kam_thermo_pairs(const ThermoOp &A, const ThermoOp &B, bool tri, uint32_t row_begin, uint32_t row_end,
                      uint32_t *d_manhat, float *d_info, uint64_t out_ld, cudaStream_t st) {
     if (A.n == 0 || B.n == 0 || row_begin >= row_end) return KAM_OK;
-    const uint64_t dp = dpad_of(A.d);
-    const uint32_t T = A.levels < B.levels ? A.levels : B.levels;   // (callers encode both with the same T)
+    if (A.kpad != B.kpad || (d_manhat != nullptr) == (d_info != nullptr)) {
+        kam_set_error("kam_thermo_pairs: operands of different layouts, or not exactly one output");
+        return KAM_E_INVALID;
+    }
     GramGeom gg;
     gg.n_a = A.n;
     gg.n_b = B.n;
@@ -1141,30 +1370,11 @@ int kam_thermo_pairs(const ThermoOp &A, const ThermoOp &B, bool tri, uint32_t ro
     gg.ld = out_ld;
     gg.rk_a = A.rk;
     gg.rk_b = B.rk;
-    int rc;
-    if (d_manhat) {
-        GramOut go;
-        go.euclid = go.cosine = go.pearson = nullptr;
-        go.manhat = d_manhat;
-        // the operands may carry different numbers of levels: each side is addressed with its own pitch only when
-        // they agree; otherwise the common prefix of levels is used (a count above T on one side is a caller error)
-        if (A.levels != B.levels) {
-            kam_set_error("kam_thermo_pairs: operands encoded with different numbers of levels");
-            return KAM_E_INVALID;
-        }
-        if ((rc = gram_block(A.op, B.op, true, A.d, gg, go, 0, st, (uint64_t)T * dp, (uint64_t)T * dp))) return rc;
-    }
-    if (d_info) {
-        GramOut go;
-        go.euclid = go.cosine = go.pearson = nullptr;
-        go.info = d_info;
-        if (A.levels != B.levels) {
-            kam_set_error("kam_thermo_pairs: operands encoded with different numbers of levels");
-            return KAM_E_INVALID;
-        }
-        if ((rc = gram_block(A.op, B.op, true, A.d, gg, go, 0, st, dp, (uint64_t)T * dp))) return rc;   // level 1 only
-    }
-    return KAM_OK;
+    GramOut go;
+    go.euclid = go.cosine = go.pearson = nullptr;
+    go.manhat = d_manhat;
+    go.info = d_info;
+    return gram_block(A.op, B.op, true, A.d, gg, go, 0, st, A.kpad, A.kpad);
 }
 
 extern "C" {

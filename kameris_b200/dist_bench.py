@@ -203,9 +203,48 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
                              "frac": pairs * dd / t / peak, "kernel": kernel.split(":")[0],
                              "peak_source": "measured issue rate of the inner op (scratch/pairop_bench.cu): %.1f "
                                             "pair-elements per clk and SM" % op_peak[key]}}
+    def tensor_line(t, pairs, dd, k_total, workload, kernel, t_core, includes):
+        """manhat / info as a Gram of thermometer rows: the tensor pipe does K = sum of column maxima MACs per pair"""
+        kpad = (k_total + 127) // 128 * 128
+        fl = 2.0 * kpad * pairs
+        return {"metric": "distance_pairs_per_sec", "value": pairs / t, "unit": "pairs/s", "ms": t * 1e3,
+                "config": {"workload": workload, "includes": includes, "operand_bytes_per_row": kpad},
+                "roofline": {"bound": "tensor", "achieved": fl / t / 1e12, "peak": 2.0 * tf_peak, "unit": "TFLOP/s",
+                             "frac": fl / t / 1e12 / (2.0 * tf_peak), "kernel": kernel, "K": kpad, "K_over_d": kpad / dd,
+                             "pair_elements_per_s": pairs * dd / t,
+                             "speedup_vs_cuda_core_kernel": (t_core / t) if t_core else None}}
+
+    def col_total(*mats):            # sum over columns of the largest count any row holds (counts far below 2^15)
+        cm = None
+        for x in mats:
+            a = x.view(torch.int16).amax(dim=0)
+            cm = a if cm is None else torch.maximum(cm, a)
+        return int(cm.to(torch.int64).sum()), int(cm.max())
+
+    ktot, top = col_total(reads, cent)
+    avg = -(-ktot // d6)
+    lib.kam_dist_set_tensor(0)
     t = _time(torch, lambda: manh(reads, cent), reps)
     out["manhattan"] = pair_line(t, m * c, d6, "u8", "pair_tile_kernel<SAD8X4>: VABSDIFF4.U8.ACC",
-                                 "%d reads (150 bp, k=6 counts) x %d centroids, D=4096, uint32 manhat" % (m, c))
+                                 "%d reads (150 bp, k=6 counts) x %d centroids, D=4096, uint32 manhat, "
+                                 "CUDA-core path (kam_dist_set_tensor(0))" % (m, c))
+    lib.kam_dist_set_tensor(1)
+    if top <= 255 and avg <= 12:
+        ws_t = torch.empty(lib.kam_manhattan_workspace_bytes_levels(m, d6, avg) +
+                           lib.kam_manhattan_workspace_bytes_levels(c, d6, avg), dtype=torch.uint8, device=dev)
+
+        def manh_t():
+            _lib.check(lib.kam_manhattan_rect(reads.data_ptr(), cent.data_ptr(), 1, m, c, d6, reads.stride(0),
+                                              cent.stride(0), o.data_ptr(), ws_t.data_ptr(), ws_t.numel(), stream))
+        o_core = o.clone()
+        tt = _time(torch, manh_t, reps)
+        assert torch.equal(o, o_core), "tensor-path manhat differs from the CUDA-core kernel"
+        out["manhattan_tensor"] = tensor_line(
+            tt, m * c, d6, ktot, "the same %d x %d uint32 manhat on the tensor cores (default path; largest count %d, "
+            "column maxima sum to %.2f d)" % (m, c, top, ktot / d6),
+            "thermo_colmax / scan / encode kernels + gram_pair_kernel<i8> (integer epilogue)", t,
+            "column-maxima pre-pass, thermometer operand rows of both sides, Gram launch")
+        del ws_t, o_core
     big = cent.clone()
     big.view(torch.int16)[0, 0] = 300                 # one count above 255 -> the exact 32-bit path
     t = _time(torch, lambda: manh(reads, big), reps)
@@ -230,11 +269,48 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
     def info():
         _lib.check(lib.kam_info_tri(xi.data_ptr(), 1, ni, d6, xi.stride(0), 0, ni, ti_.data_ptr(), wsi.data_ptr(),
                                     wsi.numel(), stream))
+    lib.kam_dist_set_tensor(0)
     t = _time(torch, info, reps)
     out["info"] = pair_line(t, pi_, d6, "info", "pair_tile_kernel<JACC>: LOP3 + POPC",
-                            "N=%d count vectors (9 kb genomes, k=6, D=4096), reference `info` triangle" % ni,
-                            "presence-bitmap pre-pass + tile kernel")
-    del xi, ti_, wsi, ws
+                            "N=%d count vectors (9 kb genomes, k=6, D=4096), reference `info` triangle, CUDA-core path "
+                            "(kam_dist_set_tensor(0))" % ni, "presence-bitmap pre-pass + tile kernel")
+    lib.kam_dist_set_tensor(1)
+    t_core = ti_.clone()
+    tt = _time(torch, info, reps)
+    assert torch.equal(ti_, t_core), "tensor-path info differs from the CUDA-core kernel"
+    out["info_tensor"] = tensor_line(tt, pi_, d6, d6, "the same `info` triangle on the tensor cores (default path): Gram of "
+                                     "the presence bytes", "thermo_presence_kernel + gram_pair_kernel<i8> (float32 epilogue)",
+                                     t, "presence-byte operand rows + Gram launch")
+    del xi, ti_, wsi, ws, t_core
+    torch.cuda.empty_cache()
+    # the reference's own workload: `manhat` between 9 kb genomes at k = 9 (D = 4^9; counts rarely pass 3)
+    n9, d9 = 8192, 4 ** 9
+    x9 = synth_counts(torch, dev, n9, 9000, 9, 20261012)
+    ktot9, top9 = col_total(x9)
+    avg9 = -(-ktot9 // d9)
+    p9 = n9 * (n9 - 1) // 2
+    tri9 = torch.empty(p9, dtype=torch.int32, device=dev)
+    ws9 = torch.empty(lib.kam_manhattan_workspace_bytes_levels(n9, d9, avg9), dtype=torch.uint8, device=dev)
+
+    def man9():
+        _lib.check(lib.kam_manhattan_tri(x9.data_ptr(), 1, n9, d9, x9.stride(0), 0, n9, tri9.data_ptr(), ws9.data_ptr(),
+                                         ws9.numel(), stream))
+    lib.kam_dist_set_tensor(0)
+    t = _time(torch, man9, 2)
+    out["manhattan_k9"] = pair_line(t, p9, d9, "u8", "pair_tile_kernel<SAD8X4>: VABSDIFF4.U8.ACC",
+                                    "N=%d genomes (9 kb, k=9, D=%d) uint32 manhat triangle, CUDA-core path" % (n9, d9))
+    lib.kam_dist_set_tensor(1)
+    if top9 <= 255 and avg9 <= 12:
+        t_core = tri9.clone()
+        tt = _time(torch, man9, reps)
+        assert torch.equal(tri9, t_core), "tensor-path manhat (k=9) differs from the CUDA-core kernel"
+        out["manhattan_k9_tensor"] = tensor_line(
+            tt, p9, d9, ktot9, "the same triangle on the tensor cores (default path; largest count %d, column maxima "
+            "sum to %.2f d)" % (top9, ktot9 / d9),
+            "thermo_colmax / scan / encode kernels + gram_pair_kernel<i8> (integer epilogue)", t,
+            "column-maxima pre-pass, thermometer operand rows, Gram launch")
+        del t_core
+    del x9, tri9, ws9
     torch.cuda.empty_cache()
 
     # ---- e2e: the whole `distances` step on HOST buffers through kam_dists_host ---------------------------
@@ -272,6 +348,9 @@ def run(torch, dev, hbm_peak, tf_peak, n_gram=8192, reps=2):
                         "gram_d4096": flat(out["gram_d4096"]), "gram_limb": flat(out["gram_limb"]),
                         "manhattan_u8": flat(out["manhattan"]), "manhattan_u32": flat(out["manhattan_u32"]),
                         "manhattan_f32_centroids": flat(out["manhattan_f32_centroids"]), "info": flat(out["info"])}
+    for key in ("manhattan_tensor", "info_tensor", "manhattan_k9", "manhattan_k9_tensor"):
+        if key in out:
+            out["rooflines"][key] = flat(out[key])
     # ---- e2e of a kmers -> distances job (run_job.py:175-180): host ASCII records -> host count vectors AND
     # host distance triangles, the count matrix handed over on the device (kam_kmers_host_keep + kam_dists_device)
     npl, kpl, Lp = 10000, 6, 9000
