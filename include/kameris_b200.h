@@ -343,6 +343,9 @@ int kam_gram_fused(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_
                    uint32_t n_segments, const uint32_t *d_ready, uint32_t ready_tiles, unsigned metrics,
                    int euclid_on_freq, float *d_out_euclid, float *d_out_cosine, float *d_out_pearson,
                    uint64_t out_ld, int sm_limit, void *d_ws, size_t ws_bytes, void *stream);
+/* diagnostics hook of kam_gram_fused: three device words that receive the cycles its TMA producers spent waiting for
+ * rows (sum, longest single wait, number of waits); NULL = off (default). */
+void kam_gram_set_wait_probe(uint64_t *d_three_words);
 /* tuning hook: row tiles (of 128 rows) per strip of the tile schedule (default 12); larger strips re-use the
  * column panels longer in L2 at the price of more row panels in flight. */
 void kam_gram_set_strip(int row_tiles);

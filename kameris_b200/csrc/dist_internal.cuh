@@ -36,6 +36,7 @@ struct GramGeom {
     // becomes non-zero once the rows of column tile t (256 rows of B) are in place; nullptr = all there.
     const uint32_t *ready = nullptr;
     uint32_t ready_tiles = 1;
+    unsigned long long *wait_probe = nullptr;   // diagnostics: [0] += cycles producers spent waiting, [1] = max of one wait
 };
 
 #ifdef __CUDACC__

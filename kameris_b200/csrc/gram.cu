@@ -122,13 +122,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // each 32 x 32 chunk goes through a padded shared-memory tile per warp and leaves as 32 row-contiguous
 // 128-byte stores.
 constexpr int EP_PITCH = 33;
+// Which flag a tile waits for is decided per WAVE of the static schedule (tile_list_segments): all CTA pairs of a
+// wave wait for the same chunk -- the last one any tile of the wave (or of an earlier wave) needs -- and so resume
+// together.  Pairs that waited for their own tile's chunk only drifted apart in their K loops by the length of
+// their different waits, and the ~18 operand panels the tiles in flight share no longer met in L2: measured at 8
+// ranks, 0.14 ms of waiting per CTA cost 5 ms of a 13 ms launch (profiles/r2_ring_fused_8gpu.jsonl).
 // fused exchange: the TMA producer of a tile whose B rows are still on their way (copy engines pull them from a
 // peer's memory and write ready[chunk] behind each chunk, peer.cu: kam_peer_pull) waits here.  The flag is read
 // with acquire semantics at system scope; the rows were written by a copy engine and are read next by the TMA
 // unit (async proxy), hence the proxy fence.  A flag that never comes (a peer died) traps after ~10 s instead of
 // hanging the device.
-__device__ __forceinline__ void wait_rows_ready(const uint32_t *flag) {
+__device__ __forceinline__ void wait_rows_ready(const uint32_t *flag, unsigned long long *probe) {
     uint32_t v, spin = 0;
+    const long long t0 = probe ? clock64() : 0;
     for (;;) {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (v) break;
@@ -136,6 +142,12 @@ __device__ __forceinline__ void wait_rows_ready(const uint32_t *flag) {
         if (++spin > (1u << 25)) __trap();
     }
     asm volatile("fence.proxy.async;" ::: "memory");
+    if (probe && spin) {
+        const unsigned long long dt = (unsigned long long)(clock64() - t0);
+        atomicAdd(probe, dt);
+        atomicMax(probe + 1, dt);
+        atomicAdd(probe + 2, 1ull);
+    }
 }
 
 constexpr int EP_ROWS = 16;                                            // rows per staging round (half a warp's 32)
@@ -280,9 +292,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = blockIdx.x / CL; t < n_tiles; t += gridDim.x / CL) {
-                const uint2 tile = tiles[t];
+                uint2 tile = tiles[t];
+                if (gg.ready) {   // fused exchange: the high half of .x is the chunk this tile's WAVE waits for
+                    wait_rows_ready(gg.ready + (tile.x >> 16), gg.wait_probe);
+                    tile.x &= 0xffffu;
+                }
                 const uint32_t bi = tile.x * CL + crank;
-                if (gg.ready) wait_rows_ready(gg.ready + tile.y / gg.ready_tiles);
                 for (uint32_t kb = 0; kb < k_iters; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
@@ -339,7 +354,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
         const uint32_t et = threadIdx.x - 64;              // 0..255
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = blockIdx.x / CL; t < n_tiles; t += gridDim.x / CL) {
-            const uint2 tile = tiles[t];
+            uint2 tile = tiles[t];
+            if (gg.ready) tile.x &= 0xffffu;
             const uint32_t r0 = (tile.x * CL + crank) * BM, c0 = tile.y * BN;
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EP_WARPS) : "memory");   // previous tile's colk fully consumed
             for (uint32_t c = et; c < (uint32_t)BN; c += 32 * EP_WARPS) {
@@ -490,10 +506,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_pair_kernel(const __grid_co
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = blockIdx.x / 2; t < n_tiles; t += gridDim.x / 2) {
-                const uint2 tile = tiles[t];
+                uint2 tile = tiles[t];
+                if (gg.ready) {   // fused exchange: the high half of .x is the chunk this tile's WAVE waits for
+                    wait_rows_ready(gg.ready + (tile.x >> 16), gg.wait_probe);
+                    tile.x &= 0xffffu;
+                }
                 const int32_t arow = (int32_t)((tile.x * 2 + crank) * BM);
                 const int32_t brow = (int32_t)(tile.y * BN + crank * (BN / 2));
-                if (gg.ready) wait_rows_ready(gg.ready + tile.y / gg.ready_tiles);
                 for (uint32_t kb = 0; kb < k_iters; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     if (leader) mbar_arrive_expect_tx(&full[stage], 2 * P_STAGE_BYTES);
@@ -542,7 +561,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_pair_kernel(const __grid_co
         const uint32_t et = threadIdx.x - 64;
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = blockIdx.x / 2; t < n_tiles; t += gridDim.x / 2) {
-            const uint2 tile = tiles[t];
+            uint2 tile = tiles[t];
+            if (gg.ready) tile.x &= 0xffffu;
             const uint32_t r0 = (tile.x * 2 + crank) * BM, c0 = tile.y * BN;
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EP_WARPS) : "memory");
             for (uint32_t c = et; c < (uint32_t)BN; c += 32 * EP_WARPS) {
@@ -999,6 +1019,7 @@ bool g_limb = true;        // test hook: false = inputs outside the uint8 / fp16
 bool g_pair = true;        // cta_group::2 kernel (gram_pair_kernel, default) or the cluster-multicast one
 uint32_t g_cluster = 2;
 uint32_t g_strip = 12;      // row tiles (of 128) per strip of the tile order (tuning hook)
+unsigned long long *g_wait_probe = nullptr;   // diagnostics hook of the fused exchange (kam_gram_set_wait_probe)
 
 inline uint64_t dpad_of(uint64_t d) { return (d + BK_BYTES - 1) / BK_BYTES * BK_BYTES; }   // elements (either width)
 
@@ -1090,9 +1111,11 @@ std::mutex g_tile_mu;
 // (row-tile group, column tile); a group is CL consecutive 128-row tiles handled by the CL CTAs of a cluster.
 // Strips of ~12 row tiles, column-major inside a strip, so the ~148 tiles in flight share about a dozen A panels
 // and a dozen B panels in L2.
-void push_rect(std::vector<uint2> &tiles, uint32_t CL, uint32_t g0, uint32_t g1, uint32_t c0, uint32_t c1, bool tri) {
+void push_rect(std::vector<uint2> &tiles, uint32_t CL, uint32_t g0, uint32_t g1, uint32_t c0, uint32_t c1, bool tri,
+               uint32_t strip_tiles = 0) {
     const uint32_t GM = BM * CL;
-    const uint32_t STRIP = g_strip / CL ? g_strip / CL : 1;
+    if (!strip_tiles) strip_tiles = g_strip;
+    const uint32_t STRIP = strip_tiles / CL ? strip_tiles / CL : 1;
     for (uint32_t s0 = g0; s0 < g1; s0 += STRIP) {
         const uint32_t s1 = s0 + STRIP < g1 ? s0 + STRIP : g1;
         for (uint32_t bj = c0; bj < c1; ++bj)
@@ -1173,13 +1196,15 @@ int tile_list(const GramGeom &gg, uint32_t CL, cudaStream_t st, const uint2 **d_
 
 // A fused call's list: the rectangles of its segments one after the other, in the order their B rows arrive.
 // A segment is (first column tile, end column tile, first row tile, end row tile) in units of 256 rows.
-int tile_list_segments(const GramGeom &gg, const uint32_t *segs, uint32_t n_segs, uint32_t CL, cudaStream_t st,
-                       const uint2 **d_list, size_t *n_list) {
+int tile_list_segments(const GramGeom &gg, const uint32_t *segs, uint32_t n_segs, uint32_t CL, uint32_t pairs,
+                       cudaStream_t st, const uint2 **d_list, size_t *n_list) {
     TileList key;
     key.tr0 = 0, key.tr1 = (gg.n_a + BM * CL - 1) / (BM * CL), key.tc = (gg.n_b + BN - 1) / BN;
     key.tri = gg.tri, key.cl = CL;
     uint64_t h = 1469598103934665603ull;
     for (uint32_t i = 0; i < 4 * n_segs; ++i) h = (h ^ segs[i]) * 1099511628211ull;
+    h = (h ^ pairs) * 1099511628211ull;
+    h = (h ^ (gg.ready ? gg.ready_tiles : 0u)) * 1099511628211ull;
     key.sig = h | 1ull;
     const uint32_t per = 256 / (BM * CL);   // row groups per 256-row tile (1 for clusters of 2, 2 without)
     return tile_list_cached(key, st, d_list, n_list, [&](std::vector<uint2> &tiles) {
@@ -1187,7 +1212,19 @@ int tile_list_segments(const GramGeom &gg, const uint32_t *segs, uint32_t n_segs
             const uint32_t *q = segs + 4 * i;
             const uint32_t c1 = q[1] < key.tc ? q[1] : key.tc;
             const uint32_t g1 = q[3] * per < key.tr1 ? q[3] * per : key.tr1;
-            push_rect(tiles, CL, q[2] * per, g1, q[0], c1, gg.tri != 0);
+            // strips twice as tall as for a resident operand: the ~74 tiles in flight then span 6 columns x 12 row
+            // groups instead of 12 x 6 -- the same number of panels in L2, half the look-ahead into rows that are
+            // still arriving (8 ranks x 5000 rows: no wait at all instead of 0.3 ms per wave)
+            push_rect(tiles, CL, q[2] * per, g1, q[0], c1, gg.tri != 0, gg.ready ? 2 * g_strip : 0);
+        }
+        if (gg.ready) {   // per wave of `pairs` tiles: the chunk to wait for, in the high half of .x
+            const size_t P = pairs < tiles.size() ? pairs : tiles.size();
+            uint32_t need = 0;
+            for (size_t w0 = 0; w0 < tiles.size(); w0 += P) {
+                const size_t w1 = w0 + P < tiles.size() ? w0 + P : tiles.size();
+                for (size_t t = w0; t < w1; ++t) need = std::max(need, tiles[t].y / gg.ready_tiles);
+                for (size_t t = w0; t < w1; ++t) tiles[t].x |= need << 16;
+            }
         }
     });
 }
@@ -1198,7 +1235,10 @@ int gram_block(const void *opA, const void *opB, bool i8, uint64_t d, const Gram
     const uint32_t CL = g_cluster;
     const uint2 *d_tiles = nullptr;
     size_t n_tiles = 0;
-    int rc = segs ? tile_list_segments(gg, segs, n_segs, CL, st, &d_tiles, &n_tiles)
+    uint32_t sms = (uint32_t)kam_sm_count();
+    if (sm_limit && sm_limit < sms) sms = sm_limit;
+    const uint32_t pairs = sms / CL ? sms / CL : 1u;      // clusters of the launch (launch_gram)
+    int rc = segs ? tile_list_segments(gg, segs, n_segs, CL, pairs, st, &d_tiles, &n_tiles)
                   : tile_list(gg, CL, st, &d_tiles, &n_tiles);
     if (rc) return rc;
     if (n_tiles == 0) return KAM_OK;
@@ -1449,6 +1489,7 @@ static int gram_block_impl(const void *d_op_a, const uint64_t *d_S_a, const uint
     gg.rk_b = rk_b;
     gg.ready = d_ready;
     gg.ready_tiles = ready_tiles ? ready_tiles : 1u;
+    gg.wait_probe = g_wait_probe;
     return gram_block(d_op_a, d_op_b, operand_kind == KAM_GRAM_U8, d, gg, go, sm_limit > 0 ? (uint32_t)sm_limit : 0u, st,
                       0, 0, segs, n_segs);
 }
@@ -1471,6 +1512,8 @@ int kam_gram_fused(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_
                    size_t ws_bytes, void *stream) {
     KAM_REQUIRE(h_segments && n_segments >= 1 && n_segments <= 64, "kam_gram_fused: 1..64 segments");
     KAM_REQUIRE(out_ld >= n_b, "kam_gram_fused writes dense rows: out_ld >= n_b");
+    KAM_REQUIRE(n_a <= 65535u * 128u, "kam_gram_fused: at most 65535 row tiles");
+    KAM_REQUIRE(!d_ready || (n_b + BN - 1) / BN / (ready_tiles ? ready_tiles : 1u) <= 65535u, "kam_gram_fused: at most 65536 chunks");
     KAM_REQUIRE(!triangular_head || d_op_a == d_op_b, "a triangular head needs B to start with the rows of A");
     for (uint32_t i = 0; i < n_segments; ++i)
         KAM_REQUIRE(h_segments[4 * i] <= h_segments[4 * i + 1] && h_segments[4 * i + 2] <= h_segments[4 * i + 3],
@@ -1607,6 +1650,7 @@ void kam_gram_set_float_recover(int on) { g_float_recover = on != 0; }
 void kam_gram_set_cluster(int cl) { g_cluster = cl == 1 ? 1u : 2u; }
 void kam_gram_set_pair(int on) { g_pair = on != 0; }
 void kam_gram_set_limb(int on) { g_limb = on != 0; }
+void kam_gram_set_wait_probe(uint64_t *d_three_words) { g_wait_probe = (unsigned long long *)d_three_words; }
 void kam_gram_set_strip(int row_tiles) { g_strip = row_tiles >= 2 ? (uint32_t)row_tiles : 2u; }
 
 }  // extern "C"

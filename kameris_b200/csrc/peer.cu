@@ -6,6 +6,7 @@
 // the clusters (measured: the overlapped block ran 33-100 % longer).  A pull by the copy engines from the
 // owner's exported buffer uses no SM at all.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -117,7 +118,9 @@ int kam_peer_copy(void *d_dst, const void *d_src, size_t bytes, void *stream) {
 
 int kam_peer_signal(uint32_t *d_flag, void *stream) {
     KAM_REQUIRE(d_flag, "null pointer");
-    if (write_value32_fn fn = write_value32()) {
+    const char *mode = getenv("KAM_PEER_FLAG");   // "copy": a 4-byte host-to-device copy instead of the stream write
+    const bool by_copy = mode && strcmp(mode, "copy") == 0;
+    if (write_value32_fn fn = by_copy ? nullptr : write_value32()) {
         const CUresult r = fn((CUstream)stream, (CUdeviceptr)(uintptr_t)d_flag, 1u, 0u /* default: ordered after prior work */);
         if (r == CUDA_SUCCESS) return KAM_OK;
     }

@@ -457,6 +457,10 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
     mark("wait_stats")
     cur.wait_event(got_stats)
     mark("block")
+    probe = None
+    if timing is not None and os.environ.get("KAM_RING_PROBE", "0") == "1":
+        probe = torch.zeros(4, dtype=torch.int64, device=dev)
+        lib.kam_gram_set_wait_probe(probe.data_ptr())
     if n_loc and n_b:
         with torch.cuda.device(dev):
             _lib.check(lib.kam_gram_fused(base + rows_off, base, base + g_off, n_loc, base + rows_off, S_b, G_b, n_b, kind,
@@ -465,9 +469,15 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
                                           ptrs.get("pearson"), max(n_b, 1), 0, ws.data_ptr(), ws.numel(), stream))
     pull(fc["pieces"], [side, side2])
     mark("end")
+    pulled = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] if timing is not None else None
+    if pulled:
+        pulled[0].record(side)
+        pulled[1].record(side2)
     cur.synchronize()
     cur.wait_stream(side)
     cur.wait_stream(side2)
+    if probe is not None:
+        lib.kam_gram_set_wait_probe(None)
     dist.barrier(group)              # nobody overwrites or frees its exported rows while a peer still reads them
 
     out_blocks = []
@@ -493,6 +503,11 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
             t[key] += dt
             if la == "block":
                 t["blocks_ms"].append(round(dt, 3))
+        blk_ev = [e for la, e in marks if la == "block"][0]
+        t["pull_done_ms_after_launch"] = [round(blk_ev.elapsed_time(pe), 3) for pe in pulled]
+        if probe is not None:
+            pv = probe.tolist()
+            t["producer_wait"] = {"sum_ms_over_all_ctas": pv[0] / 1.965e6, "longest_ms": pv[1] / 1.965e6, "waits": pv[2]}
         t.update(sm_reserve=0, transport="peer (fused: one launch, chunk flags)",
                  operand="uint8" if kind == _lib.KAM_GRAM_U8 else "fp16",
                  recv_bytes=int((n_b - n_loc) * row_b), chunks=int(fc["chunks"]), chunk_bytes=int(fc["chunk_bytes"]),
