@@ -343,6 +343,28 @@ int kam_gram_fused(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_
                    uint32_t n_segments, const uint32_t *d_ready, uint32_t ready_tiles, unsigned metrics,
                    int euclid_on_freq, float *d_out_euclid, float *d_out_cosine, float *d_out_pearson,
                    uint64_t out_ld, int sm_limit, void *d_ws, size_t ws_bytes, void *stream);
+/* manhat / info across ranks (parallel.thermo_ring): the pieces of the tensor path above as
+ * entry points, so that every rank encodes ITS rows with a layout all ranks share and the operand rows travel and
+ * are consumed exactly like those of the Gram metrics (kam_peer_pull + one fused launch).
+ *   kam_dist_colmax   d_colmax[e] = max(d_colmax[e], max_r x[r][e])   (caller zeroes it; all-reduce(MAX) it over ranks)
+ *   kam_dist_layout   d_off[0..d] = running sum of d_colmax; h_stats = {largest count, K = their sum}; synchronises
+ *   kam_dist_encode   rows of kpad = kam_dist_kpad(K) bytes (d_off != NULL: manhat) or of kam_gram_dpad(d) presence bytes
+ *                     (d_off == NULL: info) into d_operand, sum(c) and nnz(c) per row into d_S / d_NZ;
+ *                     workspace: 48 bytes per row
+ *   kam_thermo_fused  kam_gram_fused's arguments (B = [rows of A | rows of other ranks], segments, arrival flags) with
+ *                     the statistics d_S / d_NZ; metric = KAM_M_MANHAT (uint32 out) or KAM_M_INFO (float32 out) */
+int kam_dist_colmax(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t *d_colmax, void *stream);
+int kam_dist_layout(const uint32_t *d_colmax, uint64_t d, uint32_t *d_off, uint64_t *d_stats, uint64_t *h_stats,
+                    void *stream);
+uint64_t kam_dist_kpad(uint64_t k_total);
+int kam_dist_encode(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, const uint32_t *d_off,
+                    uint64_t kpad, void *d_operand, uint64_t *d_S, uint64_t *d_NZ, void *d_ws, size_t ws_bytes,
+                    void *stream);
+int kam_thermo_fused(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_NZ_a, uint32_t n_a,
+                     const void *d_op_b, const uint64_t *d_S_b, const uint64_t *d_NZ_b, uint32_t n_b, uint64_t d,
+                     uint64_t kpad, int triangular_head, const uint32_t *h_segments, uint32_t n_segments,
+                     const uint32_t *d_ready, uint32_t ready_tiles, unsigned metric, void *d_out, uint64_t out_ld,
+                     void *d_ws, size_t ws_bytes, void *stream);
 /* diagnostics hook of kam_gram_fused: three device words that receive the cycles its TMA producers spent waiting for
  * rows (sum, longest single wait, number of waits); NULL = off (default). */
 void kam_gram_set_wait_probe(uint64_t *d_three_words);

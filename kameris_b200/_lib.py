@@ -88,6 +88,14 @@ SIGNATURES = {
     "kam_gram_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_uint32, c_int,
                                c_uint64, c_int, c_void_p, c_uint32, c_void_p, c_uint32, ctypes.c_uint, c_int, c_void_p,
                                c_void_p, c_void_p, c_uint64, c_int, c_void_p, c_size_t, c_void_p]),
+    "kam_dist_colmax": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_void_p, c_void_p]),
+    "kam_dist_layout": (c_int, [c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kam_dist_kpad": (c_uint64, [c_uint64]),
+    "kam_dist_encode": (c_int, [c_void_p, c_int, c_uint32, c_uint64, c_uint64, c_void_p, c_uint64, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_size_t, c_void_p]),
+    "kam_thermo_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_uint32, c_uint64,
+                                 c_uint64, c_int, c_void_p, c_uint32, c_void_p, c_uint32, ctypes.c_uint, c_void_p,
+                                 c_uint64, c_void_p, c_size_t, c_void_p]),
     "kam_gram_set_wait_probe": (None, [c_void_p]),
     "kam_gram_set_strip": (None, [c_int]),
     "kam_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),

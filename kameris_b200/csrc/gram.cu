@@ -290,11 +290,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_tcgen05_kernel(const __grid
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, seen = 0;
             for (uint32_t t = blockIdx.x / CL; t < n_tiles; t += gridDim.x / CL) {
                 uint2 tile = tiles[t];
-                if (gg.ready) {   // fused exchange: the high half of .x is the chunk this tile's WAVE waits for
-                    wait_rows_ready(gg.ready + (tile.x >> 16), gg.wait_probe);
+                if (gg.ready) {   // fused exchange: the high half of .x is the last chunk this tile's WAVE needs; the
+                                  // chunks arrive on two copy streams, so every flag up to it is looked at
+                    for (const uint32_t need = tile.x >> 16; seen <= need; ++seen) wait_rows_ready(gg.ready + seen, gg.wait_probe);
                     tile.x &= 0xffffu;
                 }
                 const uint32_t bi = tile.x * CL + crank;
@@ -504,11 +505,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gram_pair_kernel(const __grid_co
     if (warp == 0) {
         // ===== TMA producer (both CTAs) =====
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, seen = 0;
             for (uint32_t t = blockIdx.x / 2; t < n_tiles; t += gridDim.x / 2) {
                 uint2 tile = tiles[t];
-                if (gg.ready) {   // fused exchange: the high half of .x is the chunk this tile's WAVE waits for
-                    wait_rows_ready(gg.ready + (tile.x >> 16), gg.wait_probe);
+                if (gg.ready) {   // fused exchange: the high half of .x is the last chunk this tile's WAVE needs; the
+                                  // chunks arrive on two copy streams, so every flag up to it is looked at
+                    for (const uint32_t need = tile.x >> 16; seen <= need; ++seen) wait_rows_ready(gg.ready + seen, gg.wait_probe);
                     tile.x &= 0xffffu;
                 }
                 const int32_t arow = (int32_t)((tile.x * 2 + crank) * BM);
@@ -914,36 +916,95 @@ __global__ void __launch_bounds__(1024) thermo_scan_kernel(const uint32_t *__res
     }
 }
 
-// operand rows: a CTA takes TH_ROWS rows and walks the columns in chunks; the bytes of a chunk are composed in
-// shared memory (a column's bytes sit at off[e] - chunk origin) and leave as 16-byte stores; a chunk whose bytes do
-// not fit (very large counts) is written directly.  Also the rows' sum(c) and nnz(c).
-constexpr int TH_ROWS = 4, TH_CHUNK = 2048, TH_SB = 8192;
+// operand rows: a CTA takes TH_ROWS rows and walks the columns in chunks (sized by the host so that a chunk's bytes
+// fit TH_SB); the bytes of a chunk are composed in shared memory (a column's bytes sit at off[e] - chunk origin) and
+// leave as 16-byte stores.  k-mer count rows are mostly zeros (a 150 bp read fills 3 % of 4^6 bins, a 9 kb genome
+// 3 % of 4^9), so the chunk is zero-filled with vector stores and only the NON-ZERO counts touch it afterwards: a
+// thread owns 16 columns -- their 17 offsets are loaded once, with 16-byte loads, and serve all rows -- reads them
+// row by row with 16-byte loads and writes c one-bytes for the few columns that hold something.  (The first version
+// wrote every byte of every column from a per-column loop through a generic pointer: ~90 instructions per element,
+// 2.0 ms for 131 072 x 4096 against 0.74 ms for the Gram it feeds.)  A chunk whose bytes do not fit the buffer
+// (very large column maxima) is written directly.  Also sum(c), nnz(c).
+constexpr int TH_ROWS = 4, TH_SB = 12160;   // 4 x 12160 + the reduction scratch = the 48 KB of static shared memory
 template <typename T>
 __global__ void __launch_bounds__(256) thermo_encode_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
                                                             const uint32_t *__restrict__ off, uint64_t kpad,
-                                                            uint8_t *__restrict__ op, RowK *__restrict__ rk) {
+                                                            uint8_t *__restrict__ op, RowK *__restrict__ rk, int vec_ok,
+                                                            uint32_t chunk) {
     __shared__ __align__(16) uint8_t sbuf[TH_ROWS][TH_SB];
     __shared__ unsigned long long red[2][TH_ROWS][8];
     const uint32_t row0 = blockIdx.x * TH_ROWS, tid = threadIdx.x;
     const uint32_t nrows = n - row0 < (uint32_t)TH_ROWS ? n - row0 : (uint32_t)TH_ROWS;
+    const bool off_vec = (((uintptr_t)off) & 15) == 0;
     unsigned long long s[TH_ROWS], nz[TH_ROWS];
 #pragma unroll
     for (int r = 0; r < TH_ROWS; ++r) s[r] = nz[r] = 0;
-    for (uint64_t e0 = 0; e0 < d; e0 += TH_CHUNK) {
-        const uint64_t e1 = e0 + TH_CHUNK < d ? e0 + TH_CHUNK : d;
+    for (uint64_t e0 = 0; e0 < d; e0 += chunk) {
+        const uint64_t e1 = e0 + chunk < d ? e0 + chunk : d;
         const uint32_t kb = off[e0], ke = off[e1];
         const uint32_t a0 = kb & ~15u;
         const bool staged = ke - a0 <= (uint32_t)TH_SB;
-        for (uint64_t e = e0 + tid; e < e1; e += 256) {
-            const uint32_t o = off[e], cm = off[e + 1] - o;
+        if (staged) {
+            const uint32_t words = (ke - a0 + 15u) >> 4;
+            for (uint32_t r = 0; r < nrows; ++r)
+                for (uint32_t g = tid; g < words; g += 256) reinterpret_cast<uint4 *>(sbuf[r])[g] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+        }
+        for (uint64_t e = e0 + (uint64_t)tid * 16; e < e1; e += 256 * 16) {
+            uint32_t o[17];
+            if (off_vec && e + 16 <= d) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(off + e) + i);
+                    o[4 * i] = v.x, o[4 * i + 1] = v.y, o[4 * i + 2] = v.z, o[4 * i + 3] = v.w;
+                }
+                o[16] = __ldg(off + e + 16);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 17; ++i) o[i] = off[e + i < d ? e + i : d];
+            }
+            const bool full = vec_ok && e + 16 <= e1;   // d % 16 == 0 and 16-byte aligned rows
 #pragma unroll
             for (int r = 0; r < TH_ROWS; ++r) {
-                if ((uint32_t)r < nrows) {
-                    const unsigned c = (unsigned)x[(uint64_t)(row0 + r) * ld + e];
-                    s[r] += c;
-                    nz[r] += c != 0;
-                    uint8_t *dst = staged ? &sbuf[r][o - a0] : op + (uint64_t)(row0 + r) * kpad + o;
-                    for (uint32_t t = 0; t < cm; ++t) dst[t] = c > t ? 1 : 0;
+                if ((uint32_t)r >= nrows) break;
+                const T *xr = x + (uint64_t)(row0 + r) * ld;
+                unsigned c[16];
+                if (full) {
+                    constexpr int NV = (int)sizeof(T);
+                    uint4 v[NV];
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) v[i] = __ldg(reinterpret_cast<const uint4 *>(xr + e) + i);
+                    const T *t = reinterpret_cast<const T *>(v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) c[i] = (unsigned)t[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) c[i] = e + i < e1 ? (unsigned)xr[e + i] : 0u;
+                }
+                unsigned any = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    s[r] += c[i];
+                    nz[r] += c[i] != 0;
+                    any |= c[i];
+                }
+                if (staged) {
+                    if (any) {
+                        uint8_t *rowbuf = sbuf[r] - a0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c[i]) {
+                                uint8_t *dst = rowbuf + o[i];
+                                dst[0] = 1;
+                                for (uint32_t t = 1; t < c[i]; ++t) dst[t] = 1;
+                            }
+                    }
+                } else {   // direct: every byte of every column, zeros included
+                    uint8_t *grow = op + (uint64_t)(row0 + r) * kpad;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (e + i < e1)
+                            for (uint32_t t = 0, cm = o[i + 1] - o[i]; t < cm; ++t) grow[o[i] + t] = c[i] > t ? 1 : 0;
                 }
             }
         }
@@ -1010,6 +1071,25 @@ __global__ void rowk_kernel(const unsigned long long *__restrict__ S, const unsi
         r.q = 1.0;
         r.a = g;
     }
+    rk[i] = r;
+}
+
+// thermometer operands across processes: the integers behind RowK.a / .q travel as plain uint64 arrays
+__global__ void thermo_stats_from_rowk(const RowK *__restrict__ rk, uint32_t n, unsigned long long *__restrict__ S,
+                                       unsigned long long *__restrict__ NZ) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    S[i] = (unsigned long long)__double_as_longlong(rk[i].a);
+    NZ[i] = (unsigned long long)__double_as_longlong(rk[i].q);
+}
+__global__ void thermo_rowk_from_stats(const unsigned long long *__restrict__ S, const unsigned long long *__restrict__ NZ,
+                                       uint32_t n, RowK *__restrict__ rk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RowK r;
+    r.rn = r.S = r.mu = r.rp = 0.0;
+    r.a = __longlong_as_double((long long)S[i]);
+    r.q = __longlong_as_double((long long)NZ[i]);
     rk[i] = r;
 }
 
@@ -1348,20 +1428,17 @@ int kam_thermo_layout(const uint32_t *colmax, uint64_t d, uint32_t *off, unsigne
     return KAM_OK;
 }
 
+static int thermo_encode_to(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, const uint32_t *off,
+                            uint64_t kpad, uint8_t *op, RowK *rk, cudaStream_t st);
+static int thermo_presence_to(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint8_t *op, RowK *rk,
+                              cudaStream_t st);
+
 int kam_thermo_encode(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, const uint32_t *off,
                       uint64_t kpad, void *d_ws, ThermoOp *out, cudaStream_t st) {
     RowK *rk = (RowK *)d_ws;
     uint8_t *op = (uint8_t *)d_ws + kam_align_up((size_t)n * sizeof(RowK), 1024);
-    if (n) {
-        const uint32_t grid = (n + TH_ROWS - 1) / TH_ROWS;
-        if (elem == KAM_U8)
-            thermo_encode_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)d_x, n, d, ld, off, kpad, op, rk);
-        else if (elem == KAM_U16)
-            thermo_encode_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)d_x, n, d, ld, off, kpad, op, rk);
-        else
-            thermo_encode_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)d_x, n, d, ld, off, kpad, op, rk);
-        KAM_CUDA(cudaGetLastError());
-    }
+    int rc = thermo_encode_to(d_x, elem, n, d, ld, off, kpad, op, rk, st);
+    if (rc) return rc;
     out->op = op;
     out->rk = rk;
     out->n = n;
@@ -1370,10 +1447,44 @@ int kam_thermo_encode(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_
     return KAM_OK;
 }
 
+static int thermo_encode_to(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, const uint32_t *off,
+                            uint64_t kpad, uint8_t *op, RowK *rk, cudaStream_t st) {
+    if (n) {
+        const uint32_t grid = (n + TH_ROWS - 1) / TH_ROWS;
+        const size_t esz = elem == KAM_U8 ? 1 : elem == KAM_U16 ? 2 : 4;
+        const int vec_ok = (d % 16 == 0) && ((ld * esz) % 16 == 0) && (((uintptr_t)d_x & 15) == 0);
+        // columns per chunk: as many as keep a chunk's bytes inside the kernel's buffer at the average bytes per
+        // column (x 1.25 for unevenness), whole groups of 4096 where that allows: 256 threads x 16 columns
+        const uint64_t avg_x4 = (kpad * 5 + d - 1) / d;                       // 1.25 x 4 x bytes per column
+        uint64_t chunk = (uint64_t)TH_SB * 4 / (avg_x4 ? avg_x4 : 1);
+        chunk = chunk >= 4096 ? 4096 : chunk >= 16 ? chunk / 16 * 16 : 16;
+        if (elem == KAM_U8)
+            thermo_encode_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)d_x, n, d, ld, off, kpad, op, rk, vec_ok, (uint32_t)chunk);
+        else if (elem == KAM_U16)
+            thermo_encode_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)d_x, n, d, ld, off, kpad, op, rk, vec_ok, (uint32_t)chunk);
+        else
+            thermo_encode_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)d_x, n, d, ld, off, kpad, op, rk, vec_ok, (uint32_t)chunk);
+        KAM_CUDA(cudaGetLastError());
+    }
+    return KAM_OK;
+}
+
 int kam_thermo_presence(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, void *d_ws, ThermoOp *out,
                         cudaStream_t st) {
     RowK *rk = (RowK *)d_ws;
     uint8_t *op = (uint8_t *)d_ws + kam_align_up((size_t)n * sizeof(RowK), 1024);
+    int rc = thermo_presence_to(d_x, elem, n, d, ld, op, rk, st);
+    if (rc) return rc;
+    out->op = op;
+    out->rk = rk;
+    out->n = n;
+    out->d = d;
+    out->kpad = dpad_of(d);
+    return KAM_OK;
+}
+
+static int thermo_presence_to(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint8_t *op, RowK *rk,
+                              cudaStream_t st) {
     const uint64_t dpad = dpad_of(d);
     const size_t esz = elem == KAM_U8 ? 1 : elem == KAM_U16 ? 2 : 4;
     const int vec_ok = (d % 16 == 0) && ((ld * esz) % 16 == 0) && (((uintptr_t)d_x & 15) == 0);
@@ -1386,11 +1497,6 @@ int kam_thermo_presence(const void *d_x, int elem, uint32_t n, uint64_t d, uint6
             thermo_presence_kernel<uint32_t><<<n, 256, 0, st>>>((const uint32_t *)d_x, n, d, ld, dpad, op, rk, vec_ok);
         KAM_CUDA(cudaGetLastError());
     }
-    out->op = op;
-    out->rk = rk;
-    out->n = n;
-    out->d = d;
-    out->kpad = dpad;
     return KAM_OK;
 }
 
@@ -1521,6 +1627,97 @@ int kam_gram_fused(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_
     return gram_block_impl(d_op_a, d_S_a, d_G_a, n_a, d_op_b, d_S_b, d_G_b, n_b, operand_kind, d, triangular_head, 0,
                            n_a, metrics, euclid_on_freq, d_out_euclid, d_out_cosine, d_out_pearson, out_ld, sm_limit,
                            d_ws, ws_bytes, stream, h_segments, n_segments, d_ready, ready_tiles);
+}
+
+// ---- manhat / info across ranks: the pieces of the tensor path as entry points (parallel.thermo_ring) ----------
+int kam_dist_colmax(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t *d_colmax, void *stream) {
+    KAM_REQUIRE(d_colmax && (d_x || n == 0), "null pointer");
+    KAM_REQUIRE(elem == KAM_U8 || elem == KAM_U16 || elem == KAM_U32, "the tensor path takes uint8/16/32 counts");
+    KAM_REQUIRE(d >= 1 && d < (1ull << 32) && ld >= d, "bad d / ld");
+    return kam_thermo_colmax(d_x, elem, n, d, ld, d_colmax, (cudaStream_t)stream);
+}
+
+int kam_dist_layout(const uint32_t *d_colmax, uint64_t d, uint32_t *d_off, uint64_t *d_stats, uint64_t *h_stats,
+                    void *stream) {
+    KAM_REQUIRE(d_colmax && d_off && d_stats && h_stats, "null pointer");
+    unsigned long long hs[2] = {0, 0};
+    int rc = kam_thermo_layout(d_colmax, d, d_off, (unsigned long long *)d_stats, hs, (cudaStream_t)stream);
+    h_stats[0] = hs[0];
+    h_stats[1] = hs[1];
+    return rc;
+}
+
+uint64_t kam_dist_kpad(uint64_t k_total) { return kam_thermo_kpad(k_total); }
+
+int kam_dist_encode(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, const uint32_t *d_off, uint64_t kpad,
+                    void *d_operand, uint64_t *d_S, uint64_t *d_NZ, void *d_ws, size_t ws_bytes, void *stream) {
+    KAM_REQUIRE(d_operand && d_S && d_NZ && d_ws && (d_x || n == 0), "null pointer");
+    KAM_REQUIRE(elem == KAM_U8 || elem == KAM_U16 || elem == KAM_U32, "the tensor path takes uint8/16/32 counts");
+    KAM_REQUIRE(d >= 1 && d < (1ull << 32) && ld >= d, "bad d / ld");
+    KAM_REQUIRE(kpad % BK_BYTES == 0 && kpad >= (d_off ? (uint64_t)BK_BYTES : dpad_of(d)), "bad kpad");
+    KAM_REQUIRE(((uintptr_t)d_operand & 127) == 0, "operand must be 128-byte aligned");
+    if (ws_bytes < (size_t)n * sizeof(RowK)) {
+        kam_set_error("kam_dist_encode: workspace too small (48 bytes per row)");
+        return KAM_E_WORKSPACE;
+    }
+    if (n == 0) return KAM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    RowK *rk = (RowK *)d_ws;
+    int rc = d_off ? thermo_encode_to(d_x, elem, n, d, ld, d_off, kpad, (uint8_t *)d_operand, rk, st)
+                   : thermo_presence_to(d_x, elem, n, d, ld, (uint8_t *)d_operand, rk, st);
+    if (rc) return rc;
+    if (!d_off && kpad != dpad_of(d)) {
+        kam_set_error("kam_dist_encode: presence rows are dpad bytes long");
+        return KAM_E_INVALID;
+    }
+    thermo_stats_from_rowk<<<(n + 255) / 256, 256, 0, st>>>(rk, n, (unsigned long long *)d_S, (unsigned long long *)d_NZ);
+    KAM_CUDA(cudaGetLastError());
+    return KAM_OK;
+}
+
+int kam_thermo_fused(const void *d_op_a, const uint64_t *d_S_a, const uint64_t *d_NZ_a, uint32_t n_a, const void *d_op_b,
+                     const uint64_t *d_S_b, const uint64_t *d_NZ_b, uint32_t n_b, uint64_t d, uint64_t kpad,
+                     int triangular_head, const uint32_t *h_segments, uint32_t n_segments, const uint32_t *d_ready,
+                     uint32_t ready_tiles, unsigned metric, void *d_out, uint64_t out_ld, void *d_ws, size_t ws_bytes,
+                     void *stream) {
+    KAM_REQUIRE(d_op_a && d_op_b && d_S_a && d_NZ_a && d_S_b && d_NZ_b && d_ws && d_out, "null pointer");
+    KAM_REQUIRE(metric == KAM_M_MANHAT || metric == KAM_M_INFO, "kam_thermo_fused computes manhat or info");
+    KAM_REQUIRE(h_segments && n_segments >= 1 && n_segments <= 64, "kam_thermo_fused: 1..64 segments");
+    KAM_REQUIRE(out_ld >= n_b, "kam_thermo_fused writes dense rows: out_ld >= n_b");
+    KAM_REQUIRE(!triangular_head || (d_op_a == d_op_b && n_a <= n_b), "a triangular head needs B to start with the rows of A");
+    KAM_REQUIRE(kpad % BK_BYTES == 0 && kpad >= (uint64_t)BK_BYTES && kpad < (1ull << 31), "bad kpad");
+    KAM_REQUIRE(n_a <= 65535u * 128u, "kam_thermo_fused: at most 65535 row tiles");
+    KAM_REQUIRE(!d_ready || (n_b + BN - 1) / BN / (ready_tiles ? ready_tiles : 1u) <= 65535u, "kam_thermo_fused: at most 65536 chunks");
+    if (n_a == 0 || n_b == 0) return KAM_OK;
+    if (ws_bytes < kam_gram_block_workspace_bytes(n_a, n_b)) {
+        kam_set_error("kam_thermo_fused: workspace too small");
+        return KAM_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    RowK *rk_a = (RowK *)d_ws;
+    RowK *rk_b = (RowK *)((char *)d_ws + kam_align_up((size_t)n_a * sizeof(RowK), 1024));
+    thermo_rowk_from_stats<<<(n_a + 255) / 256, 256, 0, st>>>((const unsigned long long *)d_S_a,
+                                                              (const unsigned long long *)d_NZ_a, n_a, rk_a);
+    thermo_rowk_from_stats<<<(n_b + 255) / 256, 256, 0, st>>>((const unsigned long long *)d_S_b,
+                                                              (const unsigned long long *)d_NZ_b, n_b, rk_b);
+    KAM_CUDA(cudaGetLastError());
+    GramOut go;
+    go.euclid = go.cosine = go.pearson = nullptr;
+    if (metric == KAM_M_MANHAT) go.manhat = (uint32_t *)d_out;
+    else go.info = (float *)d_out;
+    GramGeom gg;
+    gg.n_a = n_a;
+    gg.n_b = n_b;
+    gg.row_begin = 0;
+    gg.row_end = n_a;
+    gg.tri = triangular_head ? 1u : 0u;
+    gg.ld = out_ld;
+    gg.rk_a = rk_a;
+    gg.rk_b = rk_b;
+    gg.ready = d_ready;
+    gg.ready_tiles = ready_tiles ? ready_tiles : 1u;
+    gg.wait_probe = g_wait_probe;
+    return gram_block(d_op_a, d_op_b, true, d, gg, go, 0, st, kpad, kpad, h_segments, n_segments);
 }
 
 int kam_gram_tri(const void *d_x, int elem, uint32_t n, uint64_t d, uint64_t ld, uint32_t row_begin, uint32_t row_end,

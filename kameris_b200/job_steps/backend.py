@@ -400,7 +400,7 @@ def _write_ring_blocks(blocks, counts, metrics, paths, n):
                     def put(seg):
                         i, j0, vals = seg
                         if vals.size:
-                            os.pwrite(fd, np.ascontiguousarray(vals, dtype=np.float32).data,
+                            os.pwrite(fd, np.ascontiguousarray(vals).data,        # float32, or manhat's uint32 bits
                                       formats.DIST_HEADER + 4 * (tri_row_offset(n, i) + j0 - i - 1))
                     list(pool.map(put, segs))
 
@@ -452,6 +452,19 @@ def dists_to_files_sharded(input_file, output_prefix, metrics, dist, device=None
                     rest = [m for m in metrics if m not in gram]
                 except (NotImplementedError, ValueError):
                     pass          # decided from all-reduced flags: every rank takes the all-gather path below
+            # manhat / info ride the same schedule on the tensor cores (thermometer-coded rows) where the counts
+            # allow it; the decision comes from all-reduced column maxima, so every rank decides alike
+            ref_metrics = [m for m in rest if m in ('manhat', 'info')]
+            if ref_metrics and compute is None and t.is_cuda and x.dtype in (np.uint8, np.uint16, np.uint32) \
+                    and world > 1 and os.environ.get('KAM_RING_FUSED', '1') == '1':
+                for m in ref_metrics:
+                    try:
+                        blocks, counts = parallel.thermo_ring(t, (m,))
+                    except NotImplementedError:
+                        continue
+                    _write_ring_blocks(blocks, counts, [m], paths, n)
+                    del blocks
+                    rest = [r for r in rest if r != m]
             if rest:
                 slices, rows, n_all = parallel.distances_sharded(t, rest, compute=compute, euclid_on_freq=False)
                 assert n_all == n

@@ -309,7 +309,7 @@ def _gather_small(t_cpu, dev, group):
     return out.cpu()
 
 
-def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
+def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing, thermo=None):
     """gram_ring for ranks of one NVLink box, the exchange fused into the kernel: ONE kam_gram_fused launch per
     rank computes all its blocks while the copy engines pull the other shards' operand rows chunk by chunk from
     the owners' exported buffers (kam_peer_pull); every chunk is followed by a flag the kernel's TMA producers
@@ -328,8 +328,10 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
     dpad = int(lib.kam_gram_dpad(d))
     bits = {"euclid": _lib.KAM_M_EUCLID, "cosine": _lib.KAM_M_COSINE, "pearson": _lib.KAM_M_PEARSON}
     mask = 0
+    if thermo is not None:
+        metrics = (thermo,)
     for m in metrics:
-        mask |= bits[m]
+        mask |= bits.get(m, 0)
     marks = []
 
     def mark(label):
@@ -350,7 +352,50 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
 
     # 2. own operand rows + statistics into the exported buffer; the operand kind is a global decision, and the
     #    gather that takes it also carries the buffer handles and proves every owner's rows complete
-    for kind, esz in ((_lib.KAM_GRAM_U8, 1), (_lib.KAM_GRAM_F16, 2)):
+    kinds = ((_lib.KAM_GRAM_U8, 1), (_lib.KAM_GRAM_F16, 2))
+    if thermo is not None:
+        # manhat / info: thermometer-coded rows (kam_dist_*); the layout of a manhat row follows the per-column
+        # maxima over the rows of ALL ranks (one all-reduce of 4^k words), so every rank encodes alike
+        if elem not in (_lib.KAM_U8, _lib.KAM_U16, _lib.KAM_U32):
+            raise NotImplementedError("the tensor path of manhat / info takes uint8/16/32 counts")
+        g_off, rows_off = header(n_loc)
+        off_ptr, kpad = None, dpad
+        if thermo == "manhat":
+            colmax = torch.zeros(d, dtype=torch.int32, device=dev)
+            if n_loc:
+                with torch.cuda.device(dev):
+                    _lib.check(lib.kam_dist_colmax(x_local.data_ptr(), elem, n_loc, d, x_local.stride(0), colmax.data_ptr(),
+                                                   stream))
+            if dist.get_backend(group) == "gloo":
+                c = colmax.cpu()
+                dist.all_reduce(c, op=dist.ReduceOp.MAX, group=group)
+                colmax.copy_(c)
+            else:
+                dist.all_reduce(colmax, op=dist.ReduceOp.MAX, group=group)
+            off = torch.empty(d + 2, dtype=torch.int32, device=dev)
+            stats = torch.empty(2, dtype=torch.int64, device=dev)
+            hs = (ctypes.c_uint64 * 2)()
+            with torch.cuda.device(dev):
+                _lib.check(lib.kam_dist_layout(colmax.data_ptr(), d, off.data_ptr(), stats.data_ptr(), hs, stream))
+            top, ktot = int(hs[0]), int(hs[1])
+            limit = int(os.environ.get("KAM_THERMO_MAX_AVG", "12"))
+            if top > 255 or ktot >= 2 ** 31 or ktot > limit * d:
+                raise NotImplementedError("manhat: counts too large for the tensor path (largest %d, column maxima sum "
+                                          "to %.1f d): use distances_sharded()" % (top, ktot / d))
+            off_ptr, kpad = off.data_ptr(), int(lib.kam_dist_kpad(ktot))
+        base, handle = _peer_buffer(lib, dev, rows_off + max(n_b, 1) * kpad)
+        if n_loc:
+            enc_ws = torch.empty(n_loc * 48, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.kam_dist_encode(x_local.data_ptr(), elem, n_loc, d, x_local.stride(0), off_ptr, kpad,
+                                               base + rows_off, base, base + g_off, enc_ws.data_ptr(), enc_ws.numel(),
+                                               stream))
+        cur.synchronize()                                             # my rows are complete
+        mine = torch.zeros(24 + _lib.KAM_PEER_HANDLE_BYTES, dtype=torch.uint8)
+        mine[24:] = torch.frombuffer(bytearray(handle), dtype=torch.uint8)
+        infos = _gather_small(mine, dev, group)
+        kind, esz, dpad, kinds = "thermo-" + thermo, 1, kpad, ()      # (rows of kpad bytes from here on)
+    for kind, esz in kinds:
         g_off, rows_off = header(n_loc)
         base, handle = _peer_buffer(lib, dev, rows_off + max(n_b, 1) * dpad * esz)
         flags = torch.zeros(8, dtype=torch.int64, device=dev)
@@ -372,7 +417,8 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
             break
         dist.barrier(group)          # nobody re-converts into a buffer a peer might (wrongly) still read
     else:
-        raise NotImplementedError("counts outside the tensor-exact envelope: use distances_sharded()")
+        if thermo is None:
+            raise NotImplementedError("counts outside the tensor-exact envelope: use distances_sharded()")
     handles = [bytes(infos[r, 24:].tolist()) for r in range(world)]
     mark("prepared")
 
@@ -381,7 +427,7 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
     #    their arrival flags.  Lists, flags and the statistics buffer are kept per geometry between calls.
     outs, ptrs = {}, {}
     for m in metrics:
-        t = torch.empty((max(n_loc, 1), max(n_b, 1)), dtype=torch.float32, device=dev)
+        t = torch.empty((max(n_loc, 1), max(n_b, 1)), dtype=torch.int32 if m == "manhat" else torch.float32, device=dev)
         t[:, :n_loc].zero_()         # the triangular head keeps zeros on and below its diagonal
         outs[m], ptrs[m] = t, t.data_ptr()
     ws = torch.empty(lib.kam_gram_block_workspace_bytes(n_loc, n_b), dtype=torch.uint8, device=dev)
@@ -392,7 +438,7 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
     if st.get("stream") is None:
         st["stream"], st["stream2"] = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     side, side2 = st["stream"], st["stream2"]
-    key = (tuple(counts), tuple(handles), kind, d, base, ready_tiles, rank)
+    key = (tuple(counts), tuple(handles), kind, d, dpad, base, ready_tiles, rank)
     fc = st.get("fused")
     if fc is None or fc["key"] != key:
         chunk_rows = 256 * ready_tiles
@@ -461,7 +507,13 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
     if timing is not None and os.environ.get("KAM_RING_PROBE", "0") == "1":
         probe = torch.zeros(4, dtype=torch.int64, device=dev)
         lib.kam_gram_set_wait_probe(probe.data_ptr())
-    if n_loc and n_b:
+    if n_loc and n_b and thermo is not None:
+        with torch.cuda.device(dev):
+            _lib.check(lib.kam_thermo_fused(base + rows_off, base, base + g_off, n_loc, base + rows_off, S_b, G_b, n_b, d,
+                                            dpad, 1, seg_arr, len(segs), ready.data_ptr(), ready_tiles,
+                                            _lib.KAM_M_MANHAT if thermo == "manhat" else _lib.KAM_M_INFO, ptrs[thermo],
+                                            max(n_b, 1), ws.data_ptr(), ws.numel(), stream))
+    elif n_loc and n_b:
         with torch.cuda.device(dev):
             _lib.check(lib.kam_gram_fused(base + rows_off, base, base + g_off, n_loc, base + rows_off, S_b, G_b, n_b, kind,
                                           d, 1, seg_arr, len(segs), ready.data_ptr(), ready_tiles, mask,
@@ -509,11 +561,38 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing):
             pv = probe.tolist()
             t["producer_wait"] = {"sum_ms_over_all_ctas": pv[0] / 1.965e6, "longest_ms": pv[1] / 1.965e6, "waits": pv[2]}
         t.update(sm_reserve=0, transport="peer (fused: one launch, chunk flags)",
-                 operand="uint8" if kind == _lib.KAM_GRAM_U8 else "fp16",
+                 operand=kind if thermo else ("uint8" if kind == _lib.KAM_GRAM_U8 else "fp16"), operand_row_bytes=int(row_b),
                  recv_bytes=int((n_b - n_loc) * row_b), chunks=int(fc["chunks"]), chunk_bytes=int(fc["chunk_bytes"]),
                  tiles_segments=[list(sg) for sg in segs])
         timing.update(t)
     return out_blocks, counts
+
+
+def thermo_ring(x_local, metrics=("manhat",), group=None, timing=None):
+    """`manhat` / `info` over the rows of all ranks of one NVLink box, on the tensor cores and on the schedule of
+    gram_ring: every rank encodes its count rows as thermometer bytes (manhat: one layout for all ranks, from the
+    all-reduced per-column maxima; info: presence bytes), the rows travel chunk by chunk from the owners' exported
+    buffers while ONE fused launch per rank and metric (kam_thermo_fused) computes all its blocks.  Returns
+    (blocks, counts) like gram_ring; `manhat` entries are the reference's uint32 sums (int32 storage), `info`
+    float32.  Raises NotImplementedError where the tensor path does not apply (counts above 255, column maxima
+    summing to more than 12 d, 64-bit or floating-point rows, no process group): use distances_sharded() then."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
+        raise NotImplementedError("thermo_ring needs a process group of at least two ranks")
+    merged = None
+    for m in metrics:
+        if m not in ("manhat", "info"):
+            raise ValueError("thermo_ring computes manhat and info")
+        t = {} if timing is not None else None
+        blocks, counts = _gram_ring_fused(x_local, (), True, group, t, thermo=m)
+        if timing is not None:
+            timing[m] = t
+        if merged is None:
+            merged = blocks
+        else:
+            for dst, src in zip(merged, blocks):
+                assert (dst["row_shard"], dst["col_shard"], dst["rows"]) == (src["row_shard"], src["col_shard"], src["rows"])
+                dst[m] = src[m]
+    return merged, counts
 
 
 def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group=None, sm_reserve=None, timing=None,

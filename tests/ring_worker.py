@@ -46,6 +46,15 @@ def main():
     ref = D.gram_tri(x_all, metrics)
     covered = torch.zeros((n, n), dtype=torch.int32, device=dev)
     ok = True
+    # the reference's own metrics on the same schedule (thermometer-coded rows, kam_thermo_fused)
+    if world > 1 and os.environ.get("KAM_RING_FUSED", "1") == "1":
+        ref.update({"manhat": D.manhattan_tri(x_all), "info": D.info_tri(x_all)})
+        tblocks, tcounts = parallel.thermo_ring(x_all[offs[rank]:offs[rank + 1]].contiguous(), ("manhat", "info"))
+        assert tcounts == rows and len(tblocks) == len(blocks)
+        for blk, tb in zip(blocks, tblocks):
+            assert (blk["row_shard"], blk["col_shard"], blk["rows"]) == (tb["row_shard"], tb["col_shard"], tb["rows"])
+            blk["manhat"], blk["info"] = tb["manhat"], tb["info"]
+        metrics = metrics + ("manhat", "info")
     for blk in blocks:
         a, c = blk["row_shard"], blk["col_shard"]
         r0, r1 = blk["rows"]

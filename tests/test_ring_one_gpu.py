@@ -1,5 +1,6 @@
-"""The multi-GPU `distances` exchange (parallel.gram_ring: one fused kam_gram_fused launch per rank, operand
-shards pulled over CUDA IPC by the copy engines, per-chunk arrival flags) exercised on a box with ONE GPU:
+"""The multi-GPU `distances` exchange (parallel.gram_ring and parallel.thermo_ring: one fused kam_gram_fused /
+kam_thermo_fused launch per rank, operand shards pulled over CUDA IPC by the copy engines, per-chunk arrival
+flags; euclid / cosine / pearson AND the reference's manhat / info) exercised on a box with ONE GPU:
 2, 3 and 4 ranks (gloo for the small collectives) share cuda:0.  Every block of every rank must equal the
 single-GPU triangle exactly and the ranks must cover every pair exactly once (tests/ring_worker.py)."""
 import os
@@ -27,7 +28,8 @@ def _ring(rows, k, env_extra):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(len(rows)),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "ring_worker.py"), "gloo", str(k)] + [str(r) for r in rows]
-    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), **env_extra)
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), KAM_THERMO_MAX_AVG="64",
+               **env_extra)
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
     out = r.stdout.decode(errors="replace")
     assert r.returncode == 0 and "OK" in out, out[:5000] + "\n...\n" + out[-1500:]
