@@ -486,6 +486,8 @@ def main():
         if rank == 0 and isinstance(also["gram_ring"], dict):
             also["gram_ring"]["clocks"] = ring_sampler.stop()
         torch.cuda.empty_cache()
+        also["manhat_ring"] = guarded(ring_bench.run_manhat_ring, dist_pg, dev, rank, world, tf_peak)
+        torch.cuda.empty_cache()
         also["manhat_sharded"] = guarded(ring_bench.run_manhat_sharded, dist_pg, dev, rank, world)
         torch.cuda.empty_cache()
         if world > 1:

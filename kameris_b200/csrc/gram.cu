@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(1024) thermo_scan_kernel(const uint32_t *__res
 // (very large column maxima) is written directly.  Also sum(c), nnz(c).
 constexpr int TH_ROWS = 4, TH_SB = 12160;   // 4 x 12160 + the reduction scratch = the 48 KB of static shared memory
 template <typename T>
-__global__ void __launch_bounds__(256) thermo_encode_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
+__global__ void __launch_bounds__(256, 3) thermo_encode_kernel(const T *__restrict__ x, uint32_t n, uint64_t d, uint64_t ld,
                                                             const uint32_t *__restrict__ off, uint64_t kpad,
                                                             uint8_t *__restrict__ op, RowK *__restrict__ rk, int vec_ok,
                                                             uint32_t chunk) {
@@ -964,17 +964,24 @@ __global__ void __launch_bounds__(256) thermo_encode_kernel(const T *__restrict_
                 for (int i = 0; i < 17; ++i) o[i] = off[e + i < d ? e + i : d];
             }
             const bool full = vec_ok && e + 16 <= e1;   // d % 16 == 0 and 16-byte aligned rows
+            constexpr int NV = (int)sizeof(T);
+            uint4 v[TH_ROWS][NV];                        // all rows' loads in flight before any is looked at
+            if (full) {
+#pragma unroll
+                for (int r = 0; r < TH_ROWS; ++r)
+                    if ((uint32_t)r < nrows) {
+                        const T *xr = x + (uint64_t)(row0 + r) * ld;
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) v[r][i] = __ldg(reinterpret_cast<const uint4 *>(xr + e) + i);
+                    }
+            }
 #pragma unroll
             for (int r = 0; r < TH_ROWS; ++r) {
                 if ((uint32_t)r >= nrows) break;
                 const T *xr = x + (uint64_t)(row0 + r) * ld;
                 unsigned c[16];
                 if (full) {
-                    constexpr int NV = (int)sizeof(T);
-                    uint4 v[NV];
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) v[i] = __ldg(reinterpret_cast<const uint4 *>(xr + e) + i);
-                    const T *t = reinterpret_cast<const T *>(v);
+                    const T *t = reinterpret_cast<const T *>(v[r]);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) c[i] = (unsigned)t[i];
                 } else {
@@ -1458,6 +1465,7 @@ static int thermo_encode_to(const void *d_x, int elem, uint32_t n, uint64_t d, u
         const uint64_t avg_x4 = (kpad * 5 + d - 1) / d;                       // 1.25 x 4 x bytes per column
         uint64_t chunk = (uint64_t)TH_SB * 4 / (avg_x4 ? avg_x4 : 1);
         chunk = chunk >= 4096 ? 4096 : chunk >= 16 ? chunk / 16 * 16 : 16;
+        if (kpad <= (uint64_t)TH_SB && d <= 4096) chunk = 4096;              // a whole row fits: one chunk
         if (elem == KAM_U8)
             thermo_encode_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)d_x, n, d, ld, off, kpad, op, rk, vec_ok, (uint32_t)chunk);
         else if (elem == KAM_U16)

@@ -80,7 +80,16 @@ int dists_locked(DistCtx &c, const void *d_x, int elem, uint32_t n, uint64_t d, 
     int rc;
     if ((rc = c.tri[0].ensure(pairs * 4))) return rc;
     if (metrics & KAM_M_MANHAT) {
-        const size_t wb = kam_manhattan_workspace_bytes(n, d);
+        // room for the tensor path up to its own limit (column maxima summing to 12 d) where the device has it to
+        // spare, else the standard size (4 d; heavier data then takes the CUDA-core kernel)
+        size_t wb = kam_manhattan_workspace_bytes(n, d);
+        {
+            const size_t want = kam_manhattan_workspace_bytes_levels(n, d, 12);
+            size_t free_b = 0, total_b = 0;
+            if (want > c.ws.cap && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && want < (free_b + c.ws.cap) / 2) wb = want;
+            else if (want <= c.ws.cap) wb = want;
+            cudaGetLastError();
+        }
         if ((rc = c.ws.ensure(wb))) return rc;
         if ((rc = kam_manhattan_tri(d_x, elem, n, d, ld, 0, n, (uint32_t *)c.tri[0].p, c.ws.p, c.ws.cap, st))) return rc;
         KAM_CUDA(cudaMemcpyAsync(h_manhat, c.tri[0].p, pairs * 4, cudaMemcpyDeviceToHost, st));

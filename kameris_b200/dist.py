@@ -39,8 +39,9 @@ def tri_len(n):
     return n * (n - 1) // 2
 
 
-def manhattan_tri(x, rows=None, out=None):
-    """`manhat` of every pair i<j: uint32 packed triangle (as int32 storage)."""
+def manhattan_tri(x, rows=None, out=None, levels=None):
+    """`manhat` of every pair i<j: uint32 packed triangle (as int32 storage).  levels: size the workspace for the
+    tensor path up to column maxima summing to `levels` x d (default: 4 x d; see kam_manhattan_workspace_bytes_levels)."""
     lib = _lib.load()
     x = _prep(x)
     n, d = x.shape
@@ -48,7 +49,9 @@ def manhattan_tri(x, rows=None, out=None):
     r0, r1 = rows if rows is not None else (0, n)
     if out is None:
         out = torch.zeros(max(tri_len(n), 1), dtype=torch.int32, device=dev)
-    ws = torch.empty(lib.kam_manhattan_workspace_bytes(n, d), dtype=torch.uint8, device=dev)
+    nbytes = lib.kam_manhattan_workspace_bytes(n, d) if levels is None else \
+        lib.kam_manhattan_workspace_bytes_levels(n, d, int(levels))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         check(lib.kam_manhattan_tri(_ptr(x), _ELEM[x.dtype], n, d, x.stride(0), r0, r1, _ptr(out), _ptr(ws),
                                     ws.numel(), _stream(dev)))

@@ -100,6 +100,51 @@ def run_gram_ring(dist_pg, dev, rank, world, tf_peak, reps=2, n_total=N_TOTAL):
             "includes": "operand pre-pass, the two small all-gathers, every transfer, the launch", **tim}
 
 
+def run_manhat_ring(dist_pg, dev, rank, world, tf_peak, reps=2, n_total=N_TOTAL):
+    """STRONG scaling of the reference's own metric on the reference's own workload: `manhat` between the same
+    40 000 genomes at k = 9, on the tensor cores (thermometer-coded rows): one GPU = kam_manhattan_tri, N GPUs =
+    parallel.thermo_ring (all-reduced column maxima, every rank encodes its shard, ONE fused launch per rank)."""
+    from . import parallel
+    from . import dist as D
+    x = gen_shard(dev, rank, world, n_total, K, 2026100300)
+    n_loc, d = x.shape
+    n_all = n_loc * world
+    pairs = n_all * (n_all - 1) // 2
+    if world > 1:
+        run = lambda t: parallel.thermo_ring(x, ("manhat",), timing=t)[0]      # noqa: E731
+    else:
+        run = lambda t: D.manhattan_tri(x)                                         # noqa: E731
+    r = run(None)
+    del r
+    best, tim = None, {}
+    for _ in range(reps):
+        t = {}
+        _barrier(dist_pg, dev, world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = run(t)
+        e1.record()
+        _barrier(dist_pg, dev, world)
+        del r
+        ms = _max_over_ranks(dist_pg, dev, world, [e0.elapsed_time(e1)])[0]
+        if best is None or ms < best:
+            best, tim = ms, t.get("manhat", {})
+    torch.cuda.empty_cache()
+    out = {"value": pairs / (best * 1e-3), "unit": "pairs/s", "ms": best, "n_gpus": world, "scaling": "strong",
+           "n_total": n_all, "d": d, "pairs": pairs, "metric_name": "manhat (uint32, bit-exact)",
+           "kernel": "thermo_colmax / scan / encode + gram_pair_kernel<i8> (integer epilogue)" +
+                     ("; exchange fused into the launch (kam_thermo_fused)" if world > 1 else "")}
+    if tim:
+        row_b = tim.get("operand_row_bytes")
+        out.update({"operand_row_bytes": row_b, "block_ms": tim.get("block_ms"), "prepare_ms": tim.get("prepare_ms"),
+                    "recv_bytes_per_rank": tim.get("recv_bytes")})
+        if row_b:
+            fl = 2.0 * row_b * pairs
+            out.update({"achieved": fl / (best * 1e-3) / 1e12 / world, "peak": 2.0 * tf_peak, "unit_roofline": "TFLOP/s per GPU",
+                        "frac": fl / (best * 1e-3) / 1e12 / world / (2.0 * tf_peak)})
+    return out
+
+
 def run_manhat_sharded(dist_pg, dev, rank, world, reps=2, n_total=32768, k=6):
     from . import parallel
     x = gen_shard(dev, rank, world, n_total, k, 2026100400)

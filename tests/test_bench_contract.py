@@ -101,7 +101,7 @@ def test_gpu_arm_prints_one_complete_line_without_errors():
                 "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert key in d, key
     assert d["gpu_launches"] > 0 and d["e2e"]["value"] > 0 and d["roofline"]["frac"] > 0
-    for key in ("gram_ring", "manhat_sharded", "pack", "gram_i8", "gram_f16", "manhattan_u8", "manhattan_u32", "manhattan_f32_centroids", "info", "gram_d4096", "gram_limb", "short_reads",
+    for key in ("gram_ring", "manhat_ring", "manhat_sharded", "pack", "gram_i8", "gram_f16", "manhattan_u8", "manhattan_u32", "manhattan_f32_centroids", "info", "gram_d4096", "gram_limb", "short_reads",
                 "long_sequences", "manhattan_tensor", "info_tensor", "manhattan_k9", "manhattan_k9_tensor"):
         assert key in d["roofline"]["also"], key
     assert "counts_mode" in d["e2e"]["also"] and d["e2e"]["also"]["counts_mode"]["value"] > 0
