@@ -11,8 +11,9 @@ One step = one pass of the `kmers` hot path over the whole batch.
           (kam_pack_ascii) -> float32 frequency vectors (kam_kmer_count), both inside the timed step
   roofline : HBM, for the dominant kernel (cgr_tile_kernel, timed with its own CUDA events inside the
           steps); algorithmic bytes/vector = ceil(L/4) + 4^k*4 against MEASURED_PEAKS.json.
-          roofline.also carries the other kernels' figures (Gram uint8 / fp16 / D=4096, manhattan, info,
-          float L1, short reads, megabase sequences, pack, and the multi-GPU Gram ring)
+          roofline.also carries the other kernels' figures (Gram uint8 / fp16 / D=4096 / limb-split, manhattan
+          and info on the CUDA cores AND on the tensor cores (thermometer-coded rows), float L1, short reads,
+          megabase sequences, pack, and the multi-GPU rings)
   e2e   : vectors/s of the whole `kmers` step in the reference's default mode (frequencies, as in
           demo/hiv1-lanl.yml) through kam_kmers_host with HOST buffers: ASCII records in pinned host memory
           -> H2D -> pack -> count -> float64 frequency vectors (the reference's .mm-repr value type, bit-exact
@@ -29,9 +30,12 @@ With --gpus N (torchrun, one rank per GPU):
   * the `kmers` legs are WEAK scaling: every rank its own 10 000-sequence shard (sequences are independent:
     no data-path collective); value = all ranks' vectors / max-over-ranks time;
   * the `distances` legs are STRONG scaling on a fixed set (kameris_b200/ring_bench.py): 40 000 x 4^9 count
-    vectors, cosine+pearson by the ring-scheduled tcgen05 Gram (NCCL send/recv overlapped with the blocks),
-    and manhat by all-gather + balanced triangle row blocks -- reported under roofline.also.gram_ring /
-    .manhat_sharded at EVERY N (1 included), so the scaling record covers the path that has an exchange step;
+    vectors, cosine+pearson by the ring-scheduled tcgen05 Gram with the exchange fused into ONE launch per rank
+    (operand chunks pulled from peer memory by the copy engines, arrival flags awaited by the TMA producers),
+    the reference's own `manhat` of the same set on the same schedule (thermometer-coded rows), and manhat of
+    32 768 x 4^6 vectors by all-gather + balanced triangle row blocks -- reported under roofline.also.gram_ring /
+    .manhat_ring / .manhat_sharded at EVERY N (1 included), so the scaling record covers the path that has an
+    exchange step;
   * for N > 1 the sharded job steps are checked byte for byte against one process (config.multi_gpu_self_check).
 """
 import argparse
