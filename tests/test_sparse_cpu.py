@@ -69,3 +69,18 @@ def test_expand_rejects_bad_lists():
     with pytest.raises(_lib.KamError):
         R.sparse_expand(np.zeros(1, dtype=np.uint32), np.array([0], dtype=np.uint64),
                         np.array([0xffffffff], dtype=np.uint32), 7)             # a declined vector
+
+
+def test_expand_scalar_bodies_still_agree():
+    """count rows take the AVX-512 VPEXPAND path where the CPU has it; KAM_HOST_EXPAND=scalar (read once per
+    process) keeps the line-composition bodies: the same tests in a child process with it set"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("KAM_HOST_EXPAND") == "scalar":
+        pytest.skip("already the child")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_sparse_cpu.py"), "-x", "-q",
+                        "-k", "matches_oracle or misaligned"], cwd=root, env=dict(os.environ, KAM_HOST_EXPAND="scalar"),
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert r.returncode == 0, r.stdout.decode(errors="replace")[-2000:]
