@@ -166,6 +166,27 @@ def test_abi_argument_validation_without_gpu():
     assert lib.kam_manhattan_tri(p, 9, 10, 16, 16, 0, 10, p, p, 1 << 30, None) == -1
     assert lib.kam_dists_host(p, 1, 10, 16, 0, None, None, None, None, None) == -1                 # no metric asked
     assert lib.kam_gram_dpad(4 ** 9) == 4 ** 9 and lib.kam_gram_dpad(4) == 128
+    # the fused exchange and the tensor path of manhat / info (round 2)
+    seg = (ctypes.c_uint32 * 4)(0, 1, 0, 1)
+    bad = (ctypes.c_uint32 * 4)(2, 1, 0, 1)                       # column tile begin > end
+    assert lib.kam_gram_fused(p, p, p, 10, p, p, p, 10, 0, 16, 1, None, 1, None, 1, 8, 0, None, p, None, 10, 0, p, 1 << 20,
+                              None) == -1                          # no segments
+    assert lib.kam_gram_fused(p, p, p, 10, p, p, p, 10, 0, 16, 1, bad, 1, None, 1, 8, 0, None, p, None, 10, 0, p, 1 << 20,
+                              None) == -1
+    assert b"segment" in lib.kam_last_error()
+    assert lib.kam_gram_fused(p, p, p, 10, p, p, p, 20, 0, 16, 1, seg, 1, None, 1, 8, 0, None, p, None, 10, 0, p, 1 << 20,
+                              None) == -1                          # out_ld < n_b
+    assert lib.kam_thermo_fused(p, p, p, 10, p, p, p, 10, 16, 128, 1, seg, 1, None, 1, 4, p, 10, p, 1 << 20, None) == -1
+    assert b"manhat or info" in lib.kam_last_error()               # metric must be KAM_M_MANHAT or KAM_M_INFO
+    assert lib.kam_thermo_fused(p, p, p, 10, p, p, p, 10, 16, 100, 1, seg, 1, None, 1, 1, p, 10, p, 1 << 20, None) == -1
+    assert b"kpad" in lib.kam_last_error()                         # rows are multiples of 128 bytes
+    assert lib.kam_dist_colmax(p, 4, 10, 16, 16, p, None) == -1   # float rows
+    assert lib.kam_dist_encode(p, 1, 10, 16, 16, p, 100, p, p, p, p, 1 << 20, None) == -1
+    assert lib.kam_dist_encode(p, 1, 10, 16, 16, p, 128, ctypes.c_void_p(1024), p, p, p, 16, None) == -3    # workspace too small
+    assert lib.kam_dist_kpad(0) == 128 and lib.kam_dist_kpad(129) == 256
+    assert lib.kam_peer_pull(None, 1, None, None, 0) == -1
+    assert lib.kam_manhattan_workspace_bytes_levels(1000, 4096, 9) > lib.kam_manhattan_workspace_bytes(1000, 4096)
+    assert lib.kam_manhattan_workspace_bytes_levels(1000, 4096, 2) == lib.kam_manhattan_workspace_bytes(1000, 4096)
 
 
 def test_native_fasta_ingest_matches_record0_semantics(tmp_path):
