@@ -212,8 +212,10 @@ def _peer_buffer(lib, dev, nbytes):
     st = _peer_state(dev)
     if st["bytes"] < nbytes:
         if st["ptr"]:
-            torch.cuda.synchronize(dev)
-            _lib.check(lib.kam_peer_free(st["ptr"]))
+            # a peer may still hold this buffer mapped from an earlier call (it drops the mapping when it opens the
+            # next handle): freeing exported memory under an open mapping is undefined, so the buffer is only
+            # retired here and freed behind the closing barrier of the call (_peer_free_retired)
+            st.setdefault("retired", []).append(st["ptr"])
             st["ptr"], st["bytes"] = 0, 0
         want = nbytes + nbytes // 8 + 4096
         p = ctypes.c_void_p()
@@ -222,6 +224,16 @@ def _peer_buffer(lib, dev, nbytes):
         _lib.check(lib.kam_peer_export(p, h))
         st["ptr"], st["bytes"], st["handle"] = p.value, want, h.raw
     return st["ptr"], st["handle"]
+
+
+def _peer_free_retired(lib, dev):
+    """behind a call's closing barrier: every rank that reads this rank's rows has opened the new buffer (and with
+    that closed its mapping of the old one), so the buffers retired by _peer_buffer can go"""
+    from . import _lib
+    st = _peer_state(dev)
+    for p in st.pop("retired", []):
+        torch.cuda.synchronize(dev)
+        _lib.check(lib.kam_peer_free(p))
 
 
 def _peer_open(lib, dev, src_rank, handle):
@@ -531,6 +543,7 @@ def _gram_ring_fused(x_local, metrics, euclid_on_freq, group, timing, thermo=Non
     if probe is not None:
         lib.kam_gram_set_wait_probe(None)
     dist.barrier(group)              # nobody overwrites or frees its exported rows while a peer still reads them
+    _peer_free_retired(lib, dev)
 
     out_blocks = []
     for e in plan:
@@ -808,6 +821,7 @@ def gram_ring(x_local, metrics=("cosine", "pearson"), euclid_on_freq=True, group
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.current_stream(dev).wait_stream(side2)
         dist.barrier(group)         # nobody overwrites or frees its exported rows while a peer still reads them
+        _peer_free_retired(lib, dev)
     for b in out_blocks:
         b.pop("_keep", None)
     if timing is not None:
