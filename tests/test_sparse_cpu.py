@@ -84,3 +84,42 @@ def test_expand_scalar_bodies_still_agree():
                         "-k", "matches_oracle or misaligned"], cwd=root, env=dict(os.environ, KAM_HOST_EXPAND="scalar"),
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     assert r.returncode == 0, r.stdout.decode(errors="replace")[-2000:]
+
+
+@pytest.mark.parametrize("k,maxc", [(6, 3), (8, 15), (8, 16), (9, 31), (9, 32), (10, 255)])
+def test_expand_line_paths_dense_clusters_and_lookup_limits(k, maxc):
+    """the AVX-512 line paths (vpexpand of a line's occupancy mask and its consecutive entries): lines with more
+    than 16 entries (a fully occupied uint16 line has 32), empty lines, the last line of a row, and largest counts
+    right at and past what the two-register quotient lookups hold (15 / 16 for float64, 31 / 32 for float32)"""
+    from kameris_b200 import repr as R
+    rng = np.random.Generator(np.random.PCG64(1000 * k + maxc))
+    bins = 4 ** k
+    rows = []
+    for kind in range(5):
+        v = np.zeros(bins, dtype=np.uint32)
+        if kind == 0:                                   # sparse, like a k-mer vector
+            idx = rng.choice(bins, size=min(bins // 30 + 1, 9000), replace=False)
+        elif kind == 1:                                 # dense clusters: whole lines occupied
+            starts = rng.choice(bins // 64, size=5, replace=False) * 64
+            idx = np.concatenate([np.arange(s, s + 64) for s in starts] + [np.array([0, 1, bins - 1])])
+        elif kind == 2:                                 # every second bin of a stretch: 16 per uint16 line, 8 per uint32 line
+            idx = np.arange(128, 128 + 512, 2)
+        elif kind == 3:                                 # one entry only, in the last bin
+            idx = np.array([bins - 1])
+        else:                                           # nothing at all (0/0 rows for the frequencies)
+            idx = np.array([], dtype=np.int64)
+        v[idx] = rng.integers(1, maxc + 1, size=len(idx))
+        if len(idx):
+            v[idx[0]] = maxc
+        rows.append(v)
+    counts = np.stack(rows)
+    ent, start, nnz = _lists(counts)
+    assert np.array_equal(R.sparse_expand(ent, start, nnz, k, 16, "counts"), counts.astype(np.uint16))
+    assert np.array_equal(R.sparse_expand(ent, start, nnz, k, 32, "counts"), counts)
+    f64 = R.sparse_expand(ent, start, nnz, k, 16, "freq64")
+    f32 = R.sparse_expand(ent, start, nnz, k, 16, "freq32")
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i, c in enumerate(counts):
+            want = c.astype(np.float64) / c.sum()
+            assert np.array_equal(f64[i], want, equal_nan=True), i
+            assert np.array_equal(f32[i], want.astype(np.float32), equal_nan=True), i
